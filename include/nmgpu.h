@@ -1,0 +1,163 @@
+/* nmgpu.h -- C ABI of libnmgpu.so: B200 (sm_100a) coupling-matrix assembly by exact
+ * intersections, and the C / C^T sparse matrix-vector products.
+ *
+ * This is the drop-in boundary for ONE path of fdrmrc/non_matching_test_suite.  Each entry
+ * point names the reference interface it replaces (file:line relative to the reference's
+ * code/ directory).  The C++ wrapper include/coupling_utilities.h keeps the reference's
+ * own signatures on top of this ABI; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain C, no exceptions, no STL: every function returns an nm_status; a message for
+ *     the last failure is available from nm_last_error().
+ *   - the caller owns every buffer it passes or receives; nothing is retained from a host
+ *     pointer after the call returns.  The context owns all device memory and its stream.
+ *   - `where` says where the caller's buffers live: NM_HOST (pageable or pinned host
+ *     memory) or NM_DEVICE (device memory of the context's GPU).
+ *   - a context is not thread-safe; use one context per GPU / per rank.  Calls return
+ *     after the work is complete (internally asynchronous on a private stream).
+ *   - indices are 32-bit unsigned (deal.II types::global_dof_index without
+ *     DEAL_II_WITH_64BIT_INDICES, as in the reference image), row pointers 64-bit.
+ *   - matrix orientation: "stored" = n_space_dofs x n_immersed_dofs, the matrix the
+ *     reference drivers call coupling_matrix (its vmult is their `Ct`, its Tvmult their `C`).
+ *   - there is no CPU fallback: without a CUDA device every call fails with NM_ERR_CUDA.
+ */
+#ifndef NMGPU_H
+#define NMGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nm_ctx nm_ctx;
+
+typedef enum {
+  NM_OK = 0,
+  NM_ERR_INVALID = 1,     /* bad argument (sizes, null pointers, degree == 0, ...)          */
+  NM_ERR_CUDA = 2,        /* CUDA runtime failure, or no device                             */
+  NM_ERR_UNSUPPORTED = 3, /* outside the implemented scope (stated in the message)          */
+  NM_ERR_STATE = 4,       /* call order: e.g. nm_build_sparsity before nm_intersect         */
+  NM_ERR_NOMEM = 5
+} nm_status;
+
+enum { NM_HOST = 0, NM_DEVICE = 1 };
+
+/* Counters of one nm_intersect() call. */
+typedef struct {
+  uint64_t n_candidates;   /* closed bounding-box overlaps  (coupling_utilities.cc:53-55)   */
+  uint64_t n_accepted;     /* pairs with sum of weights > tol (coupling_utilities.cc:59-65) */
+  uint64_t n_qpoints;      /* quadrature points over all accepted pairs                     */
+  uint64_t n_dropped;      /* sub-simplices dropped by |J| < 1e-12 (intersections.cc:710)   */
+  uint64_t n_marginal;     /* candidates with 0 < measure < 1e-12 * measure(immersed cell): */
+                           /* the pairs whose accept/reject decision is rounding-sensitive  */
+  uint64_t n_split_ties;   /* immersed quads whose Delaunay split depends on CGAL's         */
+                           /* insertion order (cocircular / coincident in xy-projection)    */
+} nm_counts;
+
+/* Device time of the phases of the last calls, milliseconds (CUDA events on the context's
+ * stream).  Index with the NM_T_* constants. */
+enum {
+  NM_T_UPLOAD = 0,     /* host->device copies + layout kernels of nm_set_*                 */
+  NM_T_INDEX = 1,      /* background grid-hash build                                       */
+  NM_T_CANDIDATES = 2, /* count + scan + fill of candidate pairs                           */
+  NM_T_SPLIT = 3,      /* exact Delaunay split of immersed quads (3D)                      */
+  NM_T_CLIP = 4,       /* per-pair clipping + quadrature + local coupling vector           */
+  NM_T_MERGE = 5,      /* per-immersed-cell merge through constraint lines -> rows of C    */
+  NM_T_TRANSPOSE = 6,  /* C -> stored orientation CSR                                      */
+  NM_T_SPMV = 7,       /* last nm_spmv, stored orientation                                 */
+  NM_T_SPMV_T = 8,     /* last nm_spmv, transposed                                         */
+  NM_T_DOWNLOAD = 9,   /* device->host copies of the last nm_get_*                         */
+  NM_T_COUNT = 16
+};
+
+int nm_version(void);
+
+/* Create / destroy a context bound to CUDA device `device`. */
+int nm_create(nm_ctx **ctx, int device);
+int nm_destroy(nm_ctx *ctx);
+const char *nm_last_error(const nm_ctx *ctx);
+
+/* Background grid = what the wrapper reads from `space_cache` / `space_dh` /
+ * `space_constraints`:
+ *   verts  [n_cells][2^d][d]  mapping.get_vertices(cell), deal.II lexicographic order
+ *                              (intersections.h:39-58 -- the CGAL re-ordering is not needed)
+ *   dofs   [n_cells][2^d]     cell->get_dof_indices()      (coupling_utilities.h:109-115,276-283)
+ *   constraint lines of the closed AffineConstraints object, CSR over the ascending list
+ *   c_dof[n_constrained]: masters c_master[c_ptr[i]..c_ptr[i+1]) with weights c_weight
+ *   (a line without masters = Dirichlet row).            (coupling_utilities.h:127-129,285-287)
+ * Scope: FE_Q(1) on axis-aligned cells (every reference config).
+ * Cells that are not axis-aligned boxes are rejected with NM_ERR_UNSUPPORTED. */
+int nm_set_background(nm_ctx *ctx, int spacedim, uint64_t n_cells, const double *verts, const uint32_t *dofs,
+                      uint64_t n_dofs, uint64_t n_constrained, const uint32_t *c_dof, const uint64_t *c_ptr,
+                      const uint32_t *c_master, const double *c_weight, int where);
+
+/* Same, with the cells given as boxes lo[n][d], hi[n][d] (one third of the transfer). */
+int nm_set_background_boxes(nm_ctx *ctx, int spacedim, uint64_t n_cells, const double *lo, const double *hi,
+                            const uint32_t *dofs, uint64_t n_dofs, uint64_t n_constrained, const uint32_t *c_dof,
+                            const uint64_t *c_ptr, const uint32_t *c_master, const double *c_weight, int where);
+
+/* Immersed grid (or this rank's contiguous shard of it) = `immersed_cache` / `immersed_dh`:
+ *   verts [n_cells][2^dim][spacedim] deal.II order, dofs [n_cells][dofs_per_cell].
+ * Scope: dim = spacedim-1, FE_DGQ(0) (dofs_per_cell == 1, DoFs not shared between cells),
+ * no immersed constraints (never filled in the reference: 2d3d/lagrange_multiplier.cc:149). */
+int nm_set_immersed(nm_ctx *ctx, int dim, int spacedim, uint64_t n_cells, const double *verts, const uint32_t *dofs,
+                    uint32_t dofs_per_cell, uint64_t n_dofs, int where);
+
+/* Replaces NonMatching::collect_quadratures_on_overlapped_grids<dim0,dim1,spacedim>
+ * (include/coupling_utilities.h:508-515, src/coupling_utilities.cc:22-69) for <2,1,2> and
+ * <3,2,3>: candidate pairs, exact intersection, quadrature of `degree` (the reference passes
+ * it on as QGaussSimplex's n_points_1D: intersections.cc:695,776,812), acceptance by
+ * sum(weights) > tol.  degree == 0 -> NM_ERR_INVALID (the reference AssertThrows). */
+int nm_intersect(nm_ctx *ctx, unsigned degree, double tol, nm_counts *counts);
+
+/* Results of nm_intersect, ordered by (immersed cell, background cell) ascending.
+ * Any output pointer may be NULL. */
+int nm_get_candidates(nm_ctx *ctx, uint32_t *immersed, uint32_t *background, int where);
+int nm_get_pairs(nm_ctx *ctx, uint32_t *immersed, uint32_t *background, double *sum_w, int where);
+/* Quadrature<spacedim> of every accepted pair: q_offset[n_accepted+1], points
+ * [n_qpoints][spacedim], weights[n_qpoints]  (what the reference returns in its tuples). */
+int nm_get_quadrature(nm_ctx *ctx, uint64_t *q_offset, double *points, double *weights, int where);
+/* Per-immersed-quad split code (bit t: triangle omitting vertex t is used; 0x80: tie). */
+int nm_get_split_codes(nm_ctx *ctx, uint8_t *codes, int where);
+
+/* Replaces create_coupling_sparsity_pattern_with_exact_intersections
+ * (include/coupling_utilities.h:28-152): pattern of the stored matrix with
+ * keep_constrained_entries = true. */
+int nm_build_sparsity(nm_ctx *ctx, uint64_t *nnz);
+
+/* Replaces create_coupling_mass_matrix_with_exact_intersections
+ * (include/coupling_utilities.h:154-304) on the context's own intersection data (fused
+ * path: the quadrature points never leave the device). */
+int nm_assemble(nm_ctx *ctx);
+
+/* The same entry point fed with the caller's `cells_and_quads` vector, exactly as the
+ * reference signature passes it: inverse mapping of the given points to the background
+ * reference cell, shape-function products, scatter (coupling_utilities.h:238-289).
+ * pair (immersed[i], background[i]) owns points q_offset[i] .. q_offset[i+1]. */
+int nm_assemble_from_quadrature(nm_ctx *ctx, uint64_t n_pairs, const uint32_t *immersed, const uint32_t *background,
+                                const uint64_t *q_offset, const double *points, const double *weights, int where);
+
+/* CSR of the matrix.  transpose = 0: stored orientation (rows = space DoFs, n_space+1
+ * row pointers); transpose = 1: rows = immersed DoFs.  Columns ascending in every row.
+ * val may be NULL (pattern only). */
+int nm_get_csr(nm_ctx *ctx, int transpose, uint64_t *rowptr, uint32_t *col, double *val, int where);
+
+/* transpose = 0: y[n_space] = A x[n_immersed]      (reference: Ct.vmult,  2d3d/...cc:627)
+ * transpose = 1: y[n_immersed] = A^T x[n_space]    (reference: C = transpose_operator(Ct), :628)
+ * With a sharded immersed grid y (transpose=0) is this rank's partial sum -- all-reduce it;
+ * y (transpose=1) is non-zero only in this rank's immersed DoFs. */
+int nm_spmv(nm_ctx *ctx, int transpose, const double *x, double *y, int where);
+
+/* Device milliseconds per phase (NM_T_*), `n` entries copied. */
+int nm_get_timings(nm_ctx *ctx, float *ms, int n);
+/* Bytes of device memory currently held by the context. */
+int nm_device_bytes(nm_ctx *ctx, uint64_t *bytes);
+/* The CUDA stream (cudaStream_t) the context launches on, for callers that time with events. */
+int nm_get_stream(nm_ctx *ctx, void **stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NMGPU_H */

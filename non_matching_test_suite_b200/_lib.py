@@ -1,0 +1,234 @@
+"""ctypes binding of libnmgpu.so (the C ABI of include/nmgpu.h).
+
+There is no fallback of any kind: if the shared library is missing or no CUDA device is
+present, the calls raise.  torch is used only to own device memory handed to / received
+from the library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnmgpu.so")
+
+NM_HOST, NM_DEVICE = 0, 1
+STATUS = {0: "NM_OK", 1: "NM_ERR_INVALID", 2: "NM_ERR_CUDA", 3: "NM_ERR_UNSUPPORTED", 4: "NM_ERR_STATE", 5: "NM_ERR_NOMEM"}
+PHASES = ["upload", "index", "candidates", "split", "clip", "merge", "transpose", "spmv", "spmv_t", "download"]
+
+# every symbol include/nmgpu.h declares
+SYMBOLS = ["nm_version", "nm_create", "nm_destroy", "nm_last_error", "nm_set_background", "nm_set_background_boxes",
+           "nm_set_immersed", "nm_intersect", "nm_get_candidates", "nm_get_pairs", "nm_get_quadrature",
+           "nm_get_split_codes", "nm_build_sparsity", "nm_assemble", "nm_assemble_from_quadrature", "nm_get_csr",
+           "nm_spmv", "nm_get_timings", "nm_device_bytes", "nm_get_stream"]
+
+
+class NmError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("%s: %s" % (STATUS.get(code, str(code)), msg))
+        self.code = code
+
+
+class Counts(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("n_candidates", "n_accepted", "n_qpoints", "n_dropped", "n_marginal", "n_split_ties")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+_lib = None
+
+
+def load():
+    """Load libnmgpu.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libnmgpu.so not found at %s -- run `python __graft_entry__.py build` (nvcc, sm_100a)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    P, U64, I = C.c_void_p, C.c_uint64, C.c_int
+    L.nm_version.restype = I
+    L.nm_create.argtypes = [C.POINTER(P), I]
+    L.nm_destroy.argtypes = [P]
+    L.nm_last_error.restype = C.c_char_p
+    L.nm_last_error.argtypes = [P]
+    L.nm_set_background.argtypes = [P, I, U64, P, P, U64, U64, P, P, P, P, I]
+    L.nm_set_background_boxes.argtypes = [P, I, U64, P, P, P, U64, U64, P, P, P, P, I]
+    L.nm_set_immersed.argtypes = [P, I, I, U64, P, P, C.c_uint32, U64, I]
+    L.nm_intersect.argtypes = [P, C.c_uint, C.c_double, C.POINTER(Counts)]
+    L.nm_get_candidates.argtypes = [P, P, P, I]
+    L.nm_get_pairs.argtypes = [P, P, P, P, I]
+    L.nm_get_quadrature.argtypes = [P, P, P, P, I]
+    L.nm_get_split_codes.argtypes = [P, P, I]
+    L.nm_build_sparsity.argtypes = [P, C.POINTER(U64)]
+    L.nm_assemble.argtypes = [P]
+    L.nm_assemble_from_quadrature.argtypes = [P, U64, P, P, P, P, P, I]
+    L.nm_get_csr.argtypes = [P, I, P, P, P, I]
+    L.nm_spmv.argtypes = [P, I, P, P, I]
+    L.nm_get_timings.argtypes = [P, P, I]
+    L.nm_device_bytes.argtypes = [P, C.POINTER(U64)]
+    L.nm_get_stream.argtypes = [P, C.POINTER(P)]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    """(pointer, where) of a torch tensor (CPU or CUDA) or numpy array; None -> (None, host)."""
+    if a is None:
+        return None, NM_HOST
+    if isinstance(a, torch.Tensor):
+        assert a.is_contiguous(), "tensor must be contiguous"
+        return C.c_void_p(a.data_ptr()), (NM_DEVICE if a.is_cuda else NM_HOST)
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p), NM_HOST
+
+
+def _where(*arrs) -> int:
+    ws = {_ptr(a)[1] for a in arrs if a is not None}
+    if len(ws) > 1:
+        raise ValueError("all arrays of one call must live on the same side (host or device)")
+    return ws.pop() if ws else NM_HOST
+
+
+class Context:
+    """One nm_ctx: one GPU, one background grid, one immersed shard."""
+
+    def __init__(self, device: int = 0):
+        self.L = load()
+        self.h = C.c_void_p()
+        rc = self.L.nm_create(C.byref(self.h), device)
+        if rc != 0:
+            raise NmError(rc, "nm_create(device=%d) failed -- libnmgpu.so needs a CUDA device; there is no CPU path" % device)
+        self.device = device
+        self.counts = None
+        self.spacedim = None
+        self.n_space_dofs = self.n_im_dofs = 0
+
+    def close(self):
+        if self.h:
+            self.L.nm_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc: int):
+        if rc != 0:
+            raise NmError(rc, self.L.nm_last_error(self.h).decode())
+
+    # ---- inputs -------------------------------------------------------------------------
+    def set_background(self, spacedim, verts=None, lo=None, hi=None, dofs=None, n_dofs=0, c_dof=None, c_ptr=None,
+                       c_master=None, c_weight=None):
+        """Either verts [n, 2^d, d] (deal.II order) or boxes lo/hi [n, d]; dofs [n, 2^d] uint32/int32;
+        constraint lines as CSR over ascending c_dof (c_ptr uint64/int64)."""
+        n_c = 0 if c_dof is None else int(c_dof.shape[0])
+        w = _where(verts, lo, hi, dofs, c_dof, c_ptr, c_master, c_weight)
+        n = int(dofs.shape[0])
+        if verts is not None:
+            rc = self.L.nm_set_background(self.h, spacedim, n, _ptr(verts)[0], _ptr(dofs)[0], n_dofs, n_c, _ptr(c_dof)[0],
+                                          _ptr(c_ptr)[0], _ptr(c_master)[0], _ptr(c_weight)[0], w)
+        else:
+            rc = self.L.nm_set_background_boxes(self.h, spacedim, n, _ptr(lo)[0], _ptr(hi)[0], _ptr(dofs)[0], n_dofs, n_c,
+                                                _ptr(c_dof)[0], _ptr(c_ptr)[0], _ptr(c_master)[0], _ptr(c_weight)[0], w)
+        self._chk(rc)
+        self.spacedim, self.n_space_dofs = spacedim, n_dofs
+
+    def set_immersed(self, dim, spacedim, verts, dofs, n_dofs, dofs_per_cell=1):
+        w = _where(verts, dofs)
+        self._chk(self.L.nm_set_immersed(self.h, dim, spacedim, int(verts.shape[0]), _ptr(verts)[0], _ptr(dofs)[0],
+                                         dofs_per_cell, n_dofs, w))
+        self.n_im_dofs = n_dofs
+        self.n_im = int(verts.shape[0])
+
+    # ---- intersection -------------------------------------------------------------------
+    def intersect(self, degree: int = 3, tol: float = 1e-15) -> dict:
+        c = Counts()
+        self._chk(self.L.nm_intersect(self.h, degree, tol, C.byref(c)))
+        self.counts = c.as_dict()
+        return self.counts
+
+    def _out(self, n, dtype, device):
+        if device == "cpu":
+            return torch.empty(n, dtype=dtype)
+        return torch.empty(n, dtype=dtype, device="cuda:%d" % self.device)
+
+    def candidates(self, device="cpu"):
+        n = self.counts["n_candidates"]
+        im, bg = self._out(n, torch.int32, device), self._out(n, torch.int32, device)
+        self._chk(self.L.nm_get_candidates(self.h, _ptr(im)[0], _ptr(bg)[0], _where(im)))
+        return im, bg
+
+    def pairs(self, device="cpu"):
+        n = self.counts["n_accepted"]
+        im, bg, sw = self._out(n, torch.int32, device), self._out(n, torch.int32, device), self._out(n, torch.float64, device)
+        self._chk(self.L.nm_get_pairs(self.h, _ptr(im)[0], _ptr(bg)[0], _ptr(sw)[0], _where(im)))
+        return im, bg, sw
+
+    def quadrature(self, device="cpu"):
+        na, nq = self.counts["n_accepted"], self.counts["n_qpoints"]
+        off = self._out(na + 1, torch.int64, device)
+        pts = self._out(nq * self.spacedim, torch.float64, device).reshape(nq, self.spacedim)
+        w = self._out(nq, torch.float64, device)
+        self._chk(self.L.nm_get_quadrature(self.h, _ptr(off)[0], _ptr(pts)[0], _ptr(w)[0], _where(off)))
+        return off, pts, w
+
+    def split_codes(self):
+        out = torch.empty(self.n_im, dtype=torch.uint8)
+        self._chk(self.L.nm_get_split_codes(self.h, _ptr(out)[0], NM_HOST))
+        return out
+
+    # ---- matrix -------------------------------------------------------------------------
+    def build_sparsity(self) -> int:
+        nnz = C.c_uint64(0)
+        self._chk(self.L.nm_build_sparsity(self.h, C.byref(nnz)))
+        self.nnz = int(nnz.value)
+        return self.nnz
+
+    def assemble(self):
+        self._chk(self.L.nm_assemble(self.h))
+
+    def assemble_from_quadrature(self, im, bg, q_offset, points, weights):
+        w = _where(im, bg, q_offset, points, weights)
+        self._chk(self.L.nm_assemble_from_quadrature(self.h, int(im.shape[0]), _ptr(im)[0], _ptr(bg)[0], _ptr(q_offset)[0],
+                                                     _ptr(points)[0], _ptr(weights)[0], w))
+
+    def csr(self, transpose: bool = False, values: bool = True, device="cpu"):
+        nnz = self.build_sparsity()
+        n_rows = self.n_im_dofs if transpose else self.n_space_dofs
+        rp = self._out(n_rows + 1, torch.int64, device)
+        col = self._out(nnz, torch.int32, device)
+        val = self._out(nnz, torch.float64, device) if values else None
+        self._chk(self.L.nm_get_csr(self.h, int(transpose), _ptr(rp)[0], _ptr(col)[0], _ptr(val)[0], _where(rp)))
+        return rp, col, val
+
+    def spmv(self, x, transpose: bool = False, out=None):
+        """transpose=False: y[n_space] = A x[n_im]  (Ct.vmult);  True: y[n_im] = A^T x[n_space]  (C.Tvmult)."""
+        ny = self.n_im_dofs if transpose else self.n_space_dofs
+        if out is None:
+            out = torch.empty(ny, dtype=torch.float64, device=x.device) if isinstance(x, torch.Tensor) else np.empty(ny)
+        self._chk(self.L.nm_spmv(self.h, int(transpose), _ptr(x)[0], _ptr(out)[0], _where(x, out)))
+        return out
+
+    # ---- introspection ------------------------------------------------------------------
+    def timings(self) -> dict:
+        buf = (C.c_float * 16)()
+        self._chk(self.L.nm_get_timings(self.h, buf, 16))
+        return {name: float(buf[i]) for i, name in enumerate(PHASES)}
+
+    def device_bytes(self) -> int:
+        b = C.c_uint64(0)
+        self._chk(self.L.nm_device_bytes(self.h, C.byref(b)))
+        return int(b.value)
+
+    def stream(self) -> int:
+        s = C.c_void_p()
+        self._chk(self.L.nm_get_stream(self.h, C.byref(s)))
+        return s.value or 0

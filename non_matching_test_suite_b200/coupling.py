@@ -1,0 +1,136 @@
+"""Host-side mirror of the reference's three entry points, on top of the C ABI.
+
+Same names, argument meaning and error behaviour as
+  dealii::NonMatching::collect_quadratures_on_overlapped_grids            (code/include/coupling_utilities.h:508-515)
+  create_coupling_sparsity_pattern_with_exact_intersections               (code/include/coupling_utilities.h:28-38)
+  create_coupling_mass_matrix_with_exact_intersections                    (code/include/coupling_utilities.h:154-168)
+with the deal.II objects replaced by the flat arrays a wrapper extracts from them
+(`grids.BackgroundGrid` plays GridTools::Cache + DoFHandler + AffineConstraints of the space
+grid, `grids.ImmersedGrid` those of the immersed grid).  The C++ drop-in header with the
+reference's exact signatures is include/coupling_utilities.h; this module is what the tests
+and the benchmark drive.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from .grids import BackgroundGrid, ImmersedGrid
+
+
+def _u32(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.int32).contiguous()
+
+
+def make_context(space: BackgroundGrid, immersed: ImmersedGrid, device: int = 0, boxes: bool = False,
+                 on_device: bool = False) -> _lib.Context:
+    """Marshal both grids into a fresh context.  boxes=True sends lo/hi instead of the 2^d vertices;
+    on_device=True hands over CUDA tensors (inputs already resident in HBM)."""
+    ctx = _lib.Context(device)
+    set_grids(ctx, space, immersed, boxes=boxes, on_device=on_device)
+    return ctx
+
+
+def set_grids(ctx: _lib.Context, space: BackgroundGrid, immersed: ImmersedGrid, boxes: bool = False, on_device: bool = False):
+    dev = "cuda:%d" % ctx.device if on_device else "cpu"
+    mv = lambda t: t.to(dev).contiguous()
+    kw = dict(dofs=mv(_u32(space.dofs)), n_dofs=space.n_dofs, c_dof=mv(_u32(space.c_dof)), c_ptr=mv(space.c_ptr.to(torch.int64)),
+              c_master=mv(_u32(space.c_master)), c_weight=mv(space.c_weight))
+    if boxes:
+        ctx.set_background(space.spacedim, lo=mv(space.lo), hi=mv(space.hi), **kw)
+    else:
+        ctx.set_background(space.spacedim, verts=mv(space.vertices()), **kw)
+    ctx.set_immersed(immersed.dim, immersed.spacedim, mv(immersed.verts), mv(_u32(immersed.dofs)), immersed.n_dofs,
+                     dofs_per_cell=int(immersed.dofs.shape[1]))
+
+
+@dataclass
+class IntersectionInfo:
+    """The reference's std::vector<std::tuple<cell, cell, Quadrature<spacedim>>>, flattened:
+    pair i = (space_cell[i], immersed_cell[i]) with points[q_offset[i]:q_offset[i+1]]."""
+
+    ctx: _lib.Context
+    space_cell: torch.Tensor
+    immersed_cell: torch.Tensor
+    sum_w: torch.Tensor
+    q_offset: Optional[torch.Tensor] = None
+    points: Optional[torch.Tensor] = None
+    weights: Optional[torch.Tensor] = None
+    counts: Optional[dict] = None
+
+    def __len__(self):
+        return int(self.space_cell.shape[0])
+
+    def quadrature(self, i: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        a, b = int(self.q_offset[i]), int(self.q_offset[i + 1])
+        return self.points[a:b], self.weights[a:b]
+
+
+def collect_quadratures_on_overlapped_grids(space: BackgroundGrid, immersed: ImmersedGrid, degree: int, tol: float = 1e-14,
+                                            ctx: Optional[_lib.Context] = None, with_quadrature: bool = True,
+                                            device: int = 0) -> IntersectionInfo:
+    """Reference: code/src/coupling_utilities.cc:22-69.  `degree` must be > 0 (AssertThrow there, ValueError here)."""
+    if immersed.dim > space.spacedim:
+        raise ValueError("Intrinsic dimension of the immersed object must be smaller than dim0.")
+    if degree <= 0:
+        raise ValueError("Invalid quadrature degree.")
+    if ctx is None:
+        ctx = make_context(space, immersed, device=device)
+    counts = ctx.intersect(degree, tol)
+    im, bg, sw = ctx.pairs()
+    info = IntersectionInfo(ctx, bg, im, sw, counts=counts)
+    if with_quadrature:
+        info.q_offset, info.points, info.weights = ctx.quadrature()
+    return info
+
+
+def create_coupling_sparsity_pattern_with_exact_intersections(intersections_info: IntersectionInfo, space: BackgroundGrid,
+                                                              immersed: ImmersedGrid):
+    """Reference: code/include/coupling_utilities.h:28-152.  Returns the pattern of the stored
+    n_space_dofs x n_immersed_dofs matrix as CSR (rowptr, col), columns ascending, constrained
+    rows kept (keep_constrained_entries = true)."""
+    ctx = intersections_info.ctx
+    if ctx.n_space_dofs != space.n_dofs or ctx.n_im_dofs != immersed.n_dofs:
+        raise ValueError("sparsity dimensions do not match the DoF handlers")      # AssertDimension :40-41
+    rp, col, _ = ctx.csr(transpose=False, values=False)
+    return rp, col
+
+
+class CouplingMatrix:
+    """The stored coupling matrix; vmult / Tvmult are the reference's `Ct` / `C` operators
+    (code/examples/lagrange_multiplier/2d3d/lagrange_multiplier.cc:627-628)."""
+
+    def __init__(self, ctx: _lib.Context):
+        self.ctx = ctx
+        self.m, self.n = ctx.n_space_dofs, ctx.n_im_dofs
+
+    def vmult(self, src, dst=None):
+        return self.ctx.spmv(src, transpose=False, out=dst)
+
+    def Tvmult(self, src, dst=None):
+        return self.ctx.spmv(src, transpose=True, out=dst)
+
+    def csr(self, transpose=False, device="cpu"):
+        return self.ctx.csr(transpose=transpose, values=True, device=device)
+
+
+def create_coupling_mass_matrix_with_exact_intersections(space: BackgroundGrid, immersed: ImmersedGrid,
+                                                         cells_and_quads: IntersectionInfo, use_given_quadrature: bool = True
+                                                         ) -> CouplingMatrix:
+    """Reference: code/include/coupling_utilities.h:154-304 (the function compresses the matrix itself).
+    use_given_quadrature=True feeds the points/weights of `cells_and_quads` back through the
+    inverse-mapping + shape-function kernel, exactly like the reference signature;
+    False uses the fused device path (the points never left the GPU)."""
+    ctx = cells_and_quads.ctx
+    if ctx.n_space_dofs != space.n_dofs or ctx.n_im_dofs != immersed.n_dofs:
+        raise ValueError("matrix dimensions do not match the DoF handlers")         # AssertDimension :170-171
+    if use_given_quadrature and cells_and_quads.points is not None:
+        ctx.assemble_from_quadrature(cells_and_quads.immersed_cell.contiguous(), cells_and_quads.space_cell.contiguous(),
+                                     cells_and_quads.q_offset.contiguous(), cells_and_quads.points.contiguous(),
+                                     cells_and_quads.weights.contiguous())
+    else:
+        ctx.assemble()
+    return CouplingMatrix(ctx)

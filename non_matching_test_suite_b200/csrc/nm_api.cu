@@ -1,0 +1,484 @@
+// C ABI of libnmgpu.so (declared in include/nmgpu.h).  Marshalling, state checks and phase
+// orchestration only; the kernels live in nm_index.cu, nm_clip.cu and nm_matrix.cu.
+#include <stdarg.h>
+
+#include <new>
+
+#include "nm_common.cuh"
+
+int nm_bg_layout(nm_ctx *ctx, int d, uint64_t n, const double *verts_dev, const double *lo_dev, const double *hi_dev);
+int nm_constraints_layout(nm_ctx *ctx);
+int nm_accepted_index(nm_ctx *ctx, uint64_t **idx_dev);
+int nm_c_rows_compact(nm_ctx *ctx, uint64_t *rowptr_dev, uint32_t *col_dev, double *val_dev);
+
+int nm_fail(nm_ctx *c, int code, const char *fmt, ...)
+{
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+int nm_ensure(nm_ctx *ctx, DevBuf &b, size_t bytes)
+{
+  if (bytes <= b.cap && b.p) return NM_OK;
+  if (b.p) {
+    // contents are never needed across a growth
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t want = bytes < 256 ? 256 : bytes;
+  want = (want + 255) & ~size_t(255);
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    b.p = nullptr;
+    cudaGetLastError();
+    return nm_fail(ctx, NM_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s", want, cudaGetErrorString(e));
+  }
+  b.cap = want;
+  return NM_OK;
+}
+
+int nm_upload(nm_ctx *ctx, DevBuf &b, const void *src, size_t bytes, int where)
+{
+  NM_TRY(nm_ensure(ctx, b, bytes));
+  if (bytes == 0) return NM_OK;
+  if (!src) return nm_fail(ctx, NM_ERR_INVALID, "null input pointer");
+  NM_CUDA(cudaMemcpyAsync(b.p, src, bytes, where == NM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+  return NM_OK;
+}
+
+int nm_download(nm_ctx *ctx, void *dst, const void *src, size_t bytes, int where)
+{
+  if (bytes == 0 || !dst) return NM_OK;
+  NM_CUDA(cudaMemcpyAsync(dst, src, bytes, where == NM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+  return NM_OK;
+}
+
+static void free_all(nm_ctx *c)
+{
+  DevBuf *bufs[] = {&c->bg_box, &c->bg_dofs, &c->line_of, &c->c_ptr, &c->c_master, &c->c_weight, &c->im_verts, &c->im_dofs, &c->im_split,
+                    &c->im_measure, &c->idx_keys, &c->idx_keys_alt, &c->idx_vals, &c->idx_vals_alt, &c->idx_hash, &c->idx_tmp, &c->cand_ptr,
+                    &c->cand_im, &c->cand_bg, &c->cand_sumw, &c->cand_local, &c->cand_nq, &c->cand_acc, &c->counters, &c->c_rowstart,
+                    &c->c_rowlen, &c->c_col, &c->c_val, &c->a_rowptr, &c->a_col, &c->a_val, &c->a_cursor, &c->scan_tmp, &c->scratch_a,
+                    &c->scratch_b, &c->stage_x, &c->stage_y, &c->h2d_stage};
+  for (DevBuf *b : bufs) {
+    if (b->p) cudaFree(b->p);
+    b->p = nullptr;
+    b->cap = 0;
+  }
+}
+
+static uint64_t held_bytes(nm_ctx *c)
+{
+  DevBuf *bufs[] = {&c->bg_box, &c->bg_dofs, &c->line_of, &c->c_ptr, &c->c_master, &c->c_weight, &c->im_verts, &c->im_dofs, &c->im_split,
+                    &c->im_measure, &c->idx_keys, &c->idx_keys_alt, &c->idx_vals, &c->idx_vals_alt, &c->idx_hash, &c->idx_tmp, &c->cand_ptr,
+                    &c->cand_im, &c->cand_bg, &c->cand_sumw, &c->cand_local, &c->cand_nq, &c->cand_acc, &c->counters, &c->c_rowstart,
+                    &c->c_rowlen, &c->c_col, &c->c_val, &c->a_rowptr, &c->a_col, &c->a_val, &c->a_cursor, &c->scan_tmp, &c->scratch_a,
+                    &c->scratch_b, &c->stage_x, &c->stage_y, &c->h2d_stage};
+  uint64_t s = 0;
+  for (DevBuf *b : bufs) s += b->cap;
+  return s;
+}
+
+extern "C" {
+
+int nm_version(void) { return 100; }
+
+int nm_create(nm_ctx **out, int device)
+{
+  if (!out) return NM_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0 || device < 0 || device >= n) { cudaGetLastError(); return NM_ERR_CUDA; }
+  nm_ctx *ctx = new (std::nothrow) nm_ctx();
+  if (!ctx) return NM_ERR_NOMEM;
+  ctx->device = device;
+  memset(ctx->t_ms, 0, sizeof(ctx->t_ms));
+  memset(&ctx->counts, 0, sizeof(ctx->counts));
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+    cudaGetLastError();
+    delete ctx;
+    return NM_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  if (nm_ensure(ctx, ctx->counters, 64 * sizeof(uint64_t)) != NM_OK) { delete ctx; return NM_ERR_NOMEM; }
+  *out = ctx;
+  return NM_OK;
+}
+
+int nm_destroy(nm_ctx *ctx)
+{
+  if (!ctx) return NM_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  free_all(ctx);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return NM_OK;
+}
+
+const char *nm_last_error(const nm_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+static int set_background_common(nm_ctx *ctx, int spacedim, uint64_t n_cells, const double *verts, const double *lo, const double *hi,
+                                 const uint32_t *dofs, uint64_t n_dofs, uint64_t n_constrained, const uint32_t *c_dof,
+                                 const uint64_t *c_ptr, const uint32_t *c_master, const double *c_weight, int where)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  if (spacedim != 2 && spacedim != 3) return nm_fail(ctx, NM_ERR_INVALID, "spacedim must be 2 or 3 (got %d)", spacedim);
+  if (n_cells >= 0xffffffffULL || n_dofs >= 0xffffffffULL) return nm_fail(ctx, NM_ERR_UNSUPPORTED, "cell / DoF counts must fit 32 bits");
+  if (n_cells && (!dofs || (!verts && (!lo || !hi)))) return nm_fail(ctx, NM_ERR_INVALID, "null background arrays");
+  if (n_constrained && (!c_dof || !c_ptr)) return nm_fail(ctx, NM_ERR_INVALID, "null constraint arrays");
+  ctx->bg_set = ctx->index_valid = ctx->intersect_valid = ctx->matrix_valid = false;
+  const int NV = 1 << spacedim;
+  PhaseTimer tm(ctx, NM_T_UPLOAD);
+  ctx->spacedim = spacedim;
+  ctx->n_bg = n_cells;
+  ctx->n_space_dofs = n_dofs;
+  ctx->n_constrained = n_constrained;
+  // geometry
+  if (verts) {
+    const double *v_dev = verts;
+    if (where == NM_HOST) { NM_TRY(nm_upload(ctx, ctx->h2d_stage, verts, n_cells * NV * spacedim * sizeof(double), NM_HOST)); v_dev = ctx->h2d_stage.as<double>(); }
+    NM_TRY(nm_bg_layout(ctx, spacedim, n_cells, v_dev, nullptr, nullptr));
+  } else {
+    const double *lo_dev = lo, *hi_dev = hi;
+    if (where == NM_HOST) {
+      const size_t b = n_cells * spacedim * sizeof(double);
+      NM_TRY(nm_ensure(ctx, ctx->h2d_stage, 2 * b + 512));
+      if (b) {
+        NM_CUDA(cudaMemcpyAsync(ctx->h2d_stage.p, lo, b, cudaMemcpyHostToDevice, ctx->stream));
+        NM_CUDA(cudaMemcpyAsync(ctx->h2d_stage.as<char>() + ((b + 255) & ~size_t(255)), hi, b, cudaMemcpyHostToDevice, ctx->stream));
+      }
+      lo_dev = ctx->h2d_stage.as<double>();
+      hi_dev = reinterpret_cast<const double *>(ctx->h2d_stage.as<char>() + ((b + 255) & ~size_t(255)));
+    }
+    NM_TRY(nm_bg_layout(ctx, spacedim, n_cells, nullptr, lo_dev, hi_dev));
+  }
+  // dofs + constraint lines
+  NM_TRY(nm_upload(ctx, ctx->bg_dofs, dofs, n_cells * NV * sizeof(uint32_t), where));
+  uint64_t n_masters = 0;
+  if (n_constrained) {
+    if (where == NM_HOST) n_masters = c_ptr[n_constrained];
+    else { NM_CUDA(cudaMemcpyAsync(&n_masters, c_ptr + n_constrained, 8, cudaMemcpyDeviceToHost, ctx->stream)); NM_CUDA(cudaStreamSynchronize(ctx->stream)); }
+    if (n_masters && (!c_master || !c_weight)) return nm_fail(ctx, NM_ERR_INVALID, "null constraint master arrays");
+  }
+  ctx->n_cmasters = n_masters;
+  NM_TRY(nm_upload(ctx, ctx->scratch_a, c_dof, n_constrained * sizeof(uint32_t), where));
+  if (n_constrained) NM_TRY(nm_upload(ctx, ctx->c_ptr, c_ptr, (n_constrained + 1) * sizeof(uint64_t), where));
+  else { NM_TRY(nm_ensure(ctx, ctx->c_ptr, 16)); NM_CUDA(cudaMemsetAsync(ctx->c_ptr.p, 0, 16, ctx->stream)); }
+  NM_TRY(nm_upload(ctx, ctx->c_master, c_master, n_masters * sizeof(uint32_t), where));
+  NM_TRY(nm_upload(ctx, ctx->c_weight, c_weight, n_masters * sizeof(double), where));
+  NM_TRY(nm_constraints_layout(ctx));
+  tm.stop();
+  ctx->bg_set = true;
+  return NM_OK;
+}
+
+int nm_set_background(nm_ctx *ctx, int spacedim, uint64_t n_cells, const double *verts, const uint32_t *dofs, uint64_t n_dofs,
+                      uint64_t n_constrained, const uint32_t *c_dof, const uint64_t *c_ptr, const uint32_t *c_master,
+                      const double *c_weight, int where)
+{
+  if (ctx && n_cells && !verts) return nm_fail(ctx, NM_ERR_INVALID, "null vertex array");
+  return set_background_common(ctx, spacedim, n_cells, verts ? verts : (const double *)1, nullptr, nullptr, dofs, n_dofs, n_constrained, c_dof,
+                               c_ptr, c_master, c_weight, where);
+}
+
+int nm_set_background_boxes(nm_ctx *ctx, int spacedim, uint64_t n_cells, const double *lo, const double *hi, const uint32_t *dofs,
+                            uint64_t n_dofs, uint64_t n_constrained, const uint32_t *c_dof, const uint64_t *c_ptr,
+                            const uint32_t *c_master, const double *c_weight, int where)
+{
+  if (ctx && n_cells && (!lo || !hi)) return nm_fail(ctx, NM_ERR_INVALID, "null box arrays");
+  return set_background_common(ctx, spacedim, n_cells, nullptr, lo ? lo : (const double *)1, hi ? hi : (const double *)1, dofs, n_dofs,
+                               n_constrained, c_dof, c_ptr, c_master, c_weight, where);
+}
+
+int nm_set_immersed(nm_ctx *ctx, int dim, int spacedim, uint64_t n_cells, const double *verts, const uint32_t *dofs,
+                    uint32_t dofs_per_cell, uint64_t n_dofs, int where)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  if (spacedim != 2 && spacedim != 3) return nm_fail(ctx, NM_ERR_INVALID, "spacedim must be 2 or 3 (got %d)", spacedim);
+  if (dim != spacedim - 1)
+    return nm_fail(ctx, NM_ERR_UNSUPPORTED, "only codimension-1 immersed grids are implemented (<2,1,2> and <3,2,3>); got dim=%d spacedim=%d", dim, spacedim);
+  if (dofs_per_cell != 1)
+    return nm_fail(ctx, NM_ERR_UNSUPPORTED, "immersed space must be FE_DGQ(0) (1 DoF per cell); got %u DoFs per cell", dofs_per_cell);
+  if (n_cells >= 0xffffffffULL || n_dofs >= 0xffffffffULL) return nm_fail(ctx, NM_ERR_UNSUPPORTED, "cell / DoF counts must fit 32 bits");
+  if (n_cells && (!verts || !dofs)) return nm_fail(ctx, NM_ERR_INVALID, "null immersed arrays");
+  ctx->im_set = ctx->intersect_valid = ctx->matrix_valid = false;
+  PhaseTimer tm(ctx, NM_T_UPLOAD, /*accumulate=*/ctx->bg_set);
+  ctx->dim1 = dim;
+  ctx->n_im = n_cells;
+  ctx->n_im_dofs = n_dofs;
+  if (ctx->bg_set && ctx->spacedim != spacedim) return nm_fail(ctx, NM_ERR_INVALID, "immersed spacedim %d != background spacedim %d", spacedim, ctx->spacedim);
+  const int NVI = 1 << dim;
+  NM_TRY(nm_upload(ctx, ctx->im_verts, verts, n_cells * NVI * spacedim * sizeof(double), where));
+  NM_TRY(nm_upload(ctx, ctx->im_dofs, dofs, n_cells * sizeof(uint32_t), where));
+  tm.stop();
+  ctx->im_set = true;
+  return NM_OK;
+}
+
+int nm_intersect(nm_ctx *ctx, unsigned degree, double tol, nm_counts *counts)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->bg_set || !ctx->im_set) return nm_fail(ctx, NM_ERR_STATE, "nm_set_background and nm_set_immersed must precede nm_intersect");
+  if (ctx->dim1 != ctx->spacedim - 1) return nm_fail(ctx, NM_ERR_INVALID, "immersed/background dimensions do not match");
+  if (degree == 0) return nm_fail(ctx, NM_ERR_INVALID, "Invalid quadrature degree.");  // coupling_utilities.cc:32
+  ctx->intersect_valid = ctx->matrix_valid = false;
+  ctx->local_from_user = false;
+  ctx->degree = degree;
+  ctx->tol = tol;
+  if (!ctx->index_valid) {
+    PhaseTimer t(ctx, NM_T_INDEX);
+    NM_TRY(nm_index_build(ctx));
+    t.stop();
+  }
+  {
+    PhaseTimer t(ctx, NM_T_CANDIDATES);
+    NM_TRY(nm_candidates_run(ctx));
+    t.stop();
+  }
+  {
+    PhaseTimer t(ctx, NM_T_SPLIT);
+    NM_TRY(nm_split_run(ctx));
+    t.stop();
+  }
+  {
+    PhaseTimer t(ctx, NM_T_CLIP);
+    NM_TRY(nm_clip_run(ctx));
+    t.stop();
+  }
+  ctx->intersect_valid = true;
+  if (counts) *counts = ctx->counts;
+  return NM_OK;
+}
+
+int nm_get_candidates(nm_ctx *ctx, uint32_t *immersed, uint32_t *background, int where)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->intersect_valid) return nm_fail(ctx, NM_ERR_STATE, "nm_intersect has not been run");
+  PhaseTimer tm(ctx, NM_T_DOWNLOAD);
+  const uint64_t n = ctx->counts.n_candidates;
+  NM_TRY(nm_download(ctx, immersed, ctx->cand_im.p, n * 4, where));
+  NM_TRY(nm_download(ctx, background, ctx->cand_bg.p, n * 4, where));
+  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  tm.stop();
+  return NM_OK;
+}
+
+}  // extern "C"
+
+namespace {
+template <typename T>
+__global__ void gather_by_idx(uint64_t n, const uint64_t *__restrict__ idx, const T *__restrict__ src, T *__restrict__ dst)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+}  // namespace
+
+extern "C" {
+
+int nm_get_pairs(nm_ctx *ctx, uint32_t *immersed, uint32_t *background, double *sum_w, int where)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->intersect_valid) return nm_fail(ctx, NM_ERR_STATE, "nm_intersect has not been run");
+  PhaseTimer tm(ctx, NM_T_DOWNLOAD);
+  const uint64_t na = ctx->counts.n_accepted;
+  uint64_t *idx = nullptr;
+  NM_TRY(nm_accepted_index(ctx, &idx));
+  NM_TRY(nm_ensure(ctx, ctx->stage_y, (na + 1) * 8));
+  const unsigned B = nm_blocks(na, 256);
+  if (na && immersed) {
+    uint32_t *dst = where == NM_DEVICE ? immersed : ctx->stage_y.as<uint32_t>();
+    gather_by_idx<uint32_t><<<B, 256, 0, ctx->stream>>>(na, idx, ctx->cand_im.as<uint32_t>(), dst);
+    if (where == NM_HOST) { NM_TRY(nm_download(ctx, immersed, dst, na * 4, NM_HOST)); NM_CUDA(cudaStreamSynchronize(ctx->stream)); }
+  }
+  if (na && background) {
+    uint32_t *dst = where == NM_DEVICE ? background : ctx->stage_y.as<uint32_t>();
+    gather_by_idx<uint32_t><<<B, 256, 0, ctx->stream>>>(na, idx, ctx->cand_bg.as<uint32_t>(), dst);
+    if (where == NM_HOST) { NM_TRY(nm_download(ctx, background, dst, na * 4, NM_HOST)); NM_CUDA(cudaStreamSynchronize(ctx->stream)); }
+  }
+  if (na && sum_w) {
+    double *dst = where == NM_DEVICE ? sum_w : ctx->stage_y.as<double>();
+    gather_by_idx<double><<<B, 256, 0, ctx->stream>>>(na, idx, ctx->cand_sumw.as<double>(), dst);
+    if (where == NM_HOST) { NM_TRY(nm_download(ctx, sum_w, dst, na * 8, NM_HOST)); }
+  }
+  NM_CUDA(cudaGetLastError());
+  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  tm.stop();
+  return NM_OK;
+}
+
+int nm_get_quadrature(nm_ctx *ctx, uint64_t *q_offset, double *points, double *weights, int where)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->intersect_valid || ctx->local_from_user) return nm_fail(ctx, NM_ERR_STATE, "nm_intersect has not been run");
+  PhaseTimer tm(ctx, NM_T_DOWNLOAD);
+  NM_TRY(nm_quadrature_emit(ctx, q_offset, points, weights, where));
+  tm.stop();
+  return NM_OK;
+}
+
+int nm_get_split_codes(nm_ctx *ctx, uint8_t *codes, int where)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->intersect_valid) return nm_fail(ctx, NM_ERR_STATE, "nm_intersect has not been run");
+  if (ctx->spacedim != 3) return nm_fail(ctx, NM_ERR_INVALID, "split codes exist for immersed quads (spacedim 3) only");
+  NM_TRY(nm_download(ctx, codes, ctx->im_split.p, ctx->n_im, where));
+  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return NM_OK;
+}
+
+static int ensure_matrix(nm_ctx *ctx)
+{
+  if (!ctx->intersect_valid) return nm_fail(ctx, NM_ERR_STATE, "nm_intersect has not been run");
+  if (!ctx->matrix_valid) NM_TRY(nm_matrix_build(ctx));
+  return NM_OK;
+}
+
+int nm_build_sparsity(nm_ctx *ctx, uint64_t *nnz)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  NM_TRY(ensure_matrix(ctx));
+  if (nnz) *nnz = ctx->nnz;
+  return NM_OK;
+}
+
+int nm_assemble(nm_ctx *ctx)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  // pattern and values come out of the same merge; if the local vectors were replaced by
+  // nm_assemble_from_quadrature in between, rebuild from the intersection data
+  if (ctx->local_from_user) {
+    if (!ctx->intersect_valid) return nm_fail(ctx, NM_ERR_STATE, "nm_intersect has not been run");
+    PhaseTimer t(ctx, NM_T_CLIP);
+    NM_TRY(nm_clip_run(ctx));
+    t.stop();
+    ctx->local_from_user = false;
+    ctx->matrix_valid = false;
+  }
+  return ensure_matrix(ctx);
+}
+
+int nm_assemble_from_quadrature(nm_ctx *ctx, uint64_t n_pairs, const uint32_t *immersed, const uint32_t *background,
+                                const uint64_t *q_offset, const double *points, const double *weights, int where)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->bg_set || !ctx->im_set) return nm_fail(ctx, NM_ERR_STATE, "grids have not been set");
+  if (n_pairs && (!immersed || !background || !q_offset || !points || !weights)) return nm_fail(ctx, NM_ERR_INVALID, "null quadrature arrays");
+  if (!ctx->intersect_valid) {
+    // the candidate list is the addressing scheme of the per-pair vectors
+    if (!ctx->index_valid) { PhaseTimer t(ctx, NM_T_INDEX); NM_TRY(nm_index_build(ctx)); t.stop(); }
+    { PhaseTimer t(ctx, NM_T_CANDIDATES); NM_TRY(nm_candidates_run(ctx)); t.stop(); }
+    if (ctx->tol == 0) ctx->tol = 1e-15;
+    ctx->intersect_valid = true;
+  }
+  ctx->matrix_valid = false;
+  {
+    PhaseTimer t(ctx, NM_T_CLIP);
+    NM_TRY(nm_local_from_quadrature(ctx, n_pairs, immersed, background, q_offset, points, weights, where));
+    t.stop();
+  }
+  ctx->local_from_user = true;
+  return ensure_matrix(ctx);
+}
+
+int nm_get_csr(nm_ctx *ctx, int transpose, uint64_t *rowptr, uint32_t *col, double *val, int where)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  NM_TRY(ensure_matrix(ctx));
+  PhaseTimer tm(ctx, NM_T_DOWNLOAD);
+  if (!transpose) {
+    NM_TRY(nm_download(ctx, rowptr, ctx->a_rowptr.p, (ctx->n_space_dofs + 1) * 8, where));
+    NM_TRY(nm_download(ctx, col, ctx->a_col.p, ctx->nnz * 4, where));
+    NM_TRY(nm_download(ctx, val, ctx->a_val.p, ctx->nnz * 8, where));
+  } else {
+    uint64_t *rp = rowptr; uint32_t *cl = col; double *vl = val;
+    if (where == NM_HOST || !rowptr) {
+      NM_TRY(nm_ensure(ctx, ctx->stage_x, (ctx->n_im_dofs + 2) * 8));
+      rp = ctx->stage_x.as<uint64_t>();
+    }
+    if (where == NM_HOST) {
+      NM_TRY(nm_ensure(ctx, ctx->stage_y, (ctx->nnz + 1) * 8));
+      NM_TRY(nm_ensure(ctx, ctx->scratch_b, (ctx->nnz + 1) * 4));
+      cl = col ? ctx->scratch_b.as<uint32_t>() : nullptr;
+      vl = val ? ctx->stage_y.as<double>() : nullptr;
+    }
+    if (!cl && vl) return nm_fail(ctx, NM_ERR_INVALID, "values without columns requested");
+    NM_TRY(nm_c_rows_compact(ctx, rp, cl, vl));
+    if (where == NM_HOST) {
+      NM_TRY(nm_download(ctx, rowptr, rp, (ctx->n_im_dofs + 1) * 8, NM_HOST));
+      NM_TRY(nm_download(ctx, col, cl, ctx->nnz * 4, NM_HOST));
+      NM_TRY(nm_download(ctx, val, vl, ctx->nnz * 8, NM_HOST));
+    }
+  }
+  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  tm.stop();
+  return NM_OK;
+}
+
+int nm_spmv(nm_ctx *ctx, int transpose, const double *x, double *y, int where)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  if (!x || !y) return nm_fail(ctx, NM_ERR_INVALID, "null vector");
+  NM_TRY(ensure_matrix(ctx));
+  const uint64_t nx = transpose ? ctx->n_space_dofs : ctx->n_im_dofs, ny = transpose ? ctx->n_im_dofs : ctx->n_space_dofs;
+  const double *xd = x;
+  double *yd = y;
+  if (where == NM_HOST) {
+    NM_TRY(nm_upload(ctx, ctx->stage_x, x, nx * 8, NM_HOST));
+    NM_TRY(nm_ensure(ctx, ctx->stage_y, (ny + 1) * 8));
+    xd = ctx->stage_x.as<double>();
+    yd = ctx->stage_y.as<double>();
+  }
+  NM_TRY(nm_spmv_run(ctx, transpose, xd, yd));
+  if (where == NM_HOST) NM_TRY(nm_download(ctx, y, yd, ny * 8, NM_HOST));
+  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return NM_OK;
+}
+
+int nm_get_timings(nm_ctx *ctx, float *ms, int n)
+{
+  if (!ctx || !ms) return NM_ERR_INVALID;
+  for (int i = 0; i < n && i < NM_T_COUNT; ++i) ms[i] = ctx->t_ms[i];
+  return NM_OK;
+}
+
+int nm_device_bytes(nm_ctx *ctx, uint64_t *bytes)
+{
+  if (!ctx || !bytes) return NM_ERR_INVALID;
+  *bytes = held_bytes(ctx);
+  return NM_OK;
+}
+
+int nm_get_stream(nm_ctx *ctx, void **stream)
+{
+  if (!ctx || !stream) return NM_ERR_INVALID;
+  *stream = (void *)ctx->stream;
+  return NM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,631 @@
+// Subsystems (2) and (3a): per-pair FP64 intersection + quadrature + local coupling vector.
+//
+// Replaces, for every candidate pair,
+//   CGALWrappers::compute_intersection_of_cells<2,1,2> / <3,2,3>   code/src/intersections.cc:358-393, 437-509
+//   QGaussSimplexExt::mapped_quadrature                             code/src/intersections.cc:693-746
+//   the acceptance test sum(weights) > tol                          code/src/coupling_utilities.cc:59-65
+//   local(i,0) += phi_i(F^-1(x_q)) * 1 * w_q                        code/include/coupling_utilities.h:248-274
+// by one thread per candidate: the immersed simplex is clipped against the axis-aligned
+// background cell (Liang-Barsky for a segment, Sutherland-Hodgman for a triangle), the
+// result is fanned into simplices, each gets the reference's QGaussSimplex rule, sub-simplices
+// with |J| < 1e-12 are dropped as in the reference, and the Q1 x P0 products are accumulated
+// without the points ever leaving registers.  Work is done in cell-local coordinates
+// (x - lo), which is exact in sign and keeps full precision for band cells of size 1e-6.
+#include "nm_common.cuh"
+#include "nm_predicates.cuh"
+
+namespace {
+
+struct Rule {
+  int n;
+  double x[16][2];
+  double w[16];
+};
+__constant__ Rule c_rule;
+
+// QGaussSimplex<dim>(n_points_1D) of deal.II 9.4 for the sizes the path uses
+// (code/src/intersections.cc:693-695: the `degree` argument is passed as n_points_1D).
+bool make_rule(int dim1, unsigned n, Rule &r)
+{
+  memset(&r, 0, sizeof(r));
+  if (dim1 == 1) {  // Gauss-Legendre on [0,1]
+    switch (n) {
+      case 1: r.n = 1; r.x[0][0] = 0.5; r.w[0] = 1.0; return true;
+      case 2: { double a = 0.5 / sqrt(3.0); r.n = 2; r.x[0][0] = 0.5 - a; r.x[1][0] = 0.5 + a; r.w[0] = r.w[1] = 0.5; return true; }
+      case 3: { double a = 0.5 * sqrt(0.6); r.n = 3; r.x[0][0] = 0.5 - a; r.x[1][0] = 0.5; r.x[2][0] = 0.5 + a;
+                r.w[0] = r.w[2] = 5.0 / 18.0; r.w[1] = 4.0 / 9.0; return true; }
+      case 4: { double s = sqrt(1.2), a = 0.5 * sqrt(3.0 / 7.0 - 2.0 / 7.0 * s), b = 0.5 * sqrt(3.0 / 7.0 + 2.0 / 7.0 * s);
+                double wa = (18.0 + sqrt(30.0)) / 72.0, wb = (18.0 - sqrt(30.0)) / 72.0;
+                r.n = 4; r.x[0][0] = 0.5 - b; r.x[1][0] = 0.5 - a; r.x[2][0] = 0.5 + a; r.x[3][0] = 0.5 + b;
+                r.w[0] = r.w[3] = wb; r.w[1] = r.w[2] = wa; return true; }
+    }
+    return false;
+  }
+  if (n == 1) { r.n = 1; r.x[0][0] = r.x[0][1] = 1.0 / 3.0; r.w[0] = 0.5; return true; }
+  if (n == 2) {
+    r.n = 3;
+    const double a = 1.0 / 6.0, b = 2.0 / 3.0;
+    r.x[0][0] = a; r.x[0][1] = a; r.x[1][0] = b; r.x[1][1] = a; r.x[2][0] = a; r.x[2][1] = b;
+    r.w[0] = r.w[1] = r.w[2] = 1.0 / 6.0;
+    return true;
+  }
+  if (n == 3) {  // 7-point, degree 5
+    r.n = 7;
+    const double s = sqrt(15.0), a = (6.0 - s) / 21.0, b = (6.0 + s) / 21.0;
+    const double wa = 0.5 * (155.0 - s) / 1200.0, wb = 0.5 * (155.0 + s) / 1200.0;
+    r.x[0][0] = r.x[0][1] = 1.0 / 3.0; r.w[0] = 0.5 * 9.0 / 40.0;
+    r.x[1][0] = a; r.x[1][1] = a; r.x[2][0] = 1 - 2 * a; r.x[2][1] = a; r.x[3][0] = a; r.x[3][1] = 1 - 2 * a;
+    r.x[4][0] = b; r.x[4][1] = b; r.x[5][0] = 1 - 2 * b; r.x[5][1] = b; r.x[6][0] = b; r.x[6][1] = 1 - 2 * b;
+    r.w[1] = r.w[2] = r.w[3] = wa; r.w[4] = r.w[5] = r.w[6] = wb;
+    return true;
+  }
+  return false;
+}
+
+__device__ __constant__ int c_triples[4][3] = {{1, 2, 3}, {0, 2, 3}, {0, 1, 3}, {0, 1, 2}};
+
+// ---------------------------------------------------------------------------------------
+// quad split (rule R2) + immersed cell measure
+// ---------------------------------------------------------------------------------------
+__global__ void split_kernel(uint64_t n, const double *__restrict__ verts, uint8_t *__restrict__ code_out,
+                             double *__restrict__ measure, unsigned long long *n_ties)
+{
+  uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  double q[4][3];
+#pragma unroll
+  for (int v = 0; v < 4; ++v)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) q[v][k] = verts[m * 12 + v * 3 + k];
+  const double *P[4] = {q[0], q[1], q[2], q[3]};
+  int code = -1;
+  // points coinciding in projection: CGAL keeps one of them (which one depends on its
+  // spatial sort) -> flagged; the later index is dropped
+  for (int i = 0; i < 4 && code < 0; ++i)
+    for (int j = i + 1; j < 4 && code < 0; ++j)
+      if (P[i][0] == P[j][0] && P[i][1] == P[j][1]) {
+        int keep[3], c = 0;
+        for (int k = 0; k < 4; ++k) if (k != j) keep[c++] = k;
+        const double *a = P[keep[0]], *b = P[keep[1]], *cc = P[keep[2]];
+        bool dup = (a[0] == b[0] && a[1] == b[1]) || (b[0] == cc[0] && b[1] == cc[1]) || (a[0] == cc[0] && a[1] == cc[1]);
+        int o = dup ? 0 : nmpred::orient2d(a, b, cc);
+        code = (dup || o == 0 || o == 2) ? 0x80 : (0x80 | (1 << j));
+      }
+  if (code < 0) {
+    code = 0;
+    bool tie = false;
+    for (int t = 0; t < 4; ++t) {
+      const double *a = P[c_triples[t][0]], *b = P[c_triples[t][1]], *c = P[c_triples[t][2]];
+      int o = nmpred::orient2d(a, b, c);
+      if (o == 2) { tie = true; continue; }
+      if (o == 0) continue;
+      int ic = nmpred::incircle(a, b, c, P[t]);
+      if (ic == 2) { tie = true; continue; }
+      ic *= o;
+      if (ic < 0) code |= 1 << t;
+      else if (ic == 0) tie = true;
+    }
+    if (tie) code = 0x80 | (1 << 2) | (1 << 1);
+  }
+  code_out[m] = (uint8_t)code;
+  if (code & 0x80) atomicAdd(n_ties, 1ULL);
+  double area = 0;
+  for (int t = 0; t < 4; ++t)
+    if ((code >> t) & 1) {
+      const double *a = P[c_triples[t][0]], *b = P[c_triples[t][1]], *c = P[c_triples[t][2]];
+      double e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, e2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+      double nx = e1[1] * e2[2] - e1[2] * e2[1], ny = e1[2] * e2[0] - e1[0] * e2[2], nz = e1[0] * e2[1] - e1[1] * e2[0];
+      area += 0.5 * sqrt(nx * nx + ny * ny + nz * nz);
+    }
+  measure[m] = area;
+}
+
+__global__ void segment_measure_kernel(uint64_t n, const double *__restrict__ verts, double *__restrict__ measure)
+{
+  uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  const double *v = verts + m * 4;
+  measure[m] = hypot(v[2] - v[0], v[3] - v[1]);
+}
+
+// ---------------------------------------------------------------------------------------
+// geometry helpers (cell-local coordinates: box = [0, H])
+// ---------------------------------------------------------------------------------------
+#define NM_MAXV 12
+
+struct Poly {
+  double x[NM_MAXV], y[NM_MAXV], z[NM_MAXV];
+  int n;
+};
+
+// one Sutherland-Hodgman step against the closed half-space  s * (p[axis] - bound) >= 0
+template <int AXIS, int UPPER>
+__device__ inline void clip_step(const Poly &in, Poly &out, double bound)
+{
+  int m = 0;
+  const int n = in.n;
+  for (int i = 0; i < n; ++i) {
+    const int j = (i + 1 == n) ? 0 : i + 1;
+    const double pc = AXIS == 0 ? in.x[i] : (AXIS == 1 ? in.y[i] : in.z[i]);
+    const double qc = AXIS == 0 ? in.x[j] : (AXIS == 1 ? in.y[j] : in.z[j]);
+    const double dp = UPPER ? bound - pc : pc - bound;
+    const double dq = UPPER ? bound - qc : qc - bound;
+    if (dp >= 0.0) { out.x[m] = in.x[i]; out.y[m] = in.y[i]; out.z[m] = in.z[i]; ++m; }
+    if ((dp > 0.0 && dq < 0.0) || (dp < 0.0 && dq > 0.0)) {
+      const double t = dp / (dp - dq);
+      double nx = in.x[i] + t * (in.x[j] - in.x[i]);
+      double ny = in.y[i] + t * (in.y[j] - in.y[i]);
+      double nz = in.z[i] + t * (in.z[j] - in.z[i]);
+      // the new vertex lies on the plane by construction: pin it there so that later
+      // inside-tests see it as inside (no sliver re-clipping)
+      if (AXIS == 0) nx = bound; else if (AXIS == 1) ny = bound; else nz = bound;
+      if (m < NM_MAXV) { out.x[m] = nx; out.y[m] = ny; out.z[m] = nz; ++m; }
+    }
+  }
+  out.n = m;
+}
+
+template <class F>
+__device__ inline void triangle_in_box(const double (*tri)[3], const double *H, F &&visit_subtriangle)
+{
+  // trivial reject on the triangle's own box (candidates come from the quad's box)
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double mn = fmin(tri[0][k], fmin(tri[1][k], tri[2][k]));
+    const double mx = fmax(tri[0][k], fmax(tri[1][k], tri[2][k]));
+    if (mx < 0.0 || mn > H[k]) return;
+  }
+  Poly A, B;
+  A.n = 3;
+#pragma unroll
+  for (int v = 0; v < 3; ++v) { A.x[v] = tri[v][0]; A.y[v] = tri[v][1]; A.z[v] = tri[v][2]; }
+  clip_step<0, 0>(A, B, 0.0);  if (B.n < 3) return;
+  clip_step<0, 1>(B, A, H[0]); if (A.n < 3) return;
+  clip_step<1, 0>(A, B, 0.0);  if (B.n < 3) return;
+  clip_step<1, 1>(B, A, H[1]); if (A.n < 3) return;
+  clip_step<2, 0>(A, B, 0.0);  if (B.n < 3) return;
+  clip_step<2, 1>(B, A, H[2]); if (A.n < 3) return;
+  for (int j = 1; j + 1 < A.n; ++j) {
+    const double a[3] = {A.x[0], A.y[0], A.z[0]};
+    const double e1[3] = {A.x[j] - a[0], A.y[j] - a[1], A.z[j] - a[2]};
+    const double e2[3] = {A.x[j + 1] - a[0], A.y[j + 1] - a[1], A.z[j + 1] - a[2]};
+    visit_subtriangle(a, e1, e2);
+  }
+}
+
+// Liang-Barsky on the closed box [0,H]; false for empty or single-point results
+__device__ inline bool segment_in_box(const double *p0, const double *p1, const double *H, double &t0, double &t1)
+{
+  t0 = 0.0; t1 = 1.0;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const double d = p1[k] - p0[k];
+    if (d == 0.0) {
+      if (p0[k] < 0.0 || p0[k] > H[k]) return false;
+    } else {
+      double ta = (0.0 - p0[k]) / d, tb = (H[k] - p0[k]) / d;
+      if (ta > tb) { const double s = ta; ta = tb; tb = s; }
+      t0 = fmax(t0, ta); t1 = fmin(t1, tb);
+      if (t0 > t1) return false;
+    }
+  }
+  return t0 < t1;
+}
+
+struct PairAcc {
+  double sumw;
+  double loc[8];
+  unsigned nq;
+  unsigned dropped;
+};
+
+__device__ inline void q1_add_3d(PairAcc &o, double u0, double u1, double u2, double w)
+{
+  const double a0 = w - w * u0, a1 = w * u0;
+  const double b00 = a0 - a0 * u1, b10 = a1 - a1 * u1, b01 = a0 * u1, b11 = a1 * u1;
+  o.loc[4] += b00 * u2; o.loc[5] += b10 * u2; o.loc[6] += b01 * u2; o.loc[7] += b11 * u2;
+  o.loc[0] += b00 - b00 * u2; o.loc[1] += b10 - b10 * u2; o.loc[2] += b01 - b01 * u2; o.loc[3] += b11 - b11 * u2;
+  o.sumw += w;
+}
+__device__ inline void q1_add_2d(PairAcc &o, double u0, double u1, double w)
+{
+  const double a0 = w - w * u0, a1 = w * u0;
+  o.loc[2] += a0 * u1; o.loc[3] += a1 * u1;
+  o.loc[0] += a0 - a0 * u1; o.loc[1] += a1 - a1 * u1;
+  o.sumw += w;
+}
+
+// sub-triangle (a, a+e1, a+e2) in cell-local coordinates; `emit(x_local[3], w)` per point
+template <class E>
+__device__ inline void subtriangle_rule(const double *a, const double *e1, const double *e2, double tol, PairAcc &o, E &&emit)
+{
+  const double nx = e1[1] * e2[2] - e1[2] * e2[1], ny = e1[2] * e2[0] - e1[0] * e2[2], nz = e1[0] * e2[1] - e1[1] * e2[0];
+  const double J2 = nx * nx + ny * ny + nz * nz;
+  if (!(0.25 * J2 > tol * tol)) return;                 // squared_area > tol^2   intersections.cc:477,493
+  const double J = sqrt(J2);                             // 2 * area = |det B|      intersections.cc:702-707
+  if (J < 1e-12) { o.dropped++; return; }                // intersections.cc:710
+  const int nq = c_rule.n;
+  for (int q = 0; q < nq; ++q) {
+    const double s = c_rule.x[q][0], t = c_rule.x[q][1];
+    const double x[3] = {a[0] + s * e1[0] + t * e2[0], a[1] + s * e1[1] + t * e2[1], a[2] + s * e1[2] + t * e2[2]};
+    emit(x, J * c_rule.w[q]);
+  }
+  o.nq += nq;
+}
+
+template <class E>
+__device__ inline void pair_3d(const double *__restrict__ box, const double *__restrict__ quad, int code, double tol, PairAcc &o, E &&emit)
+{
+  const double lo[3] = {box[0], box[1], box[2]};
+  const double H[3] = {box[4] - lo[0], box[5] - lo[1], box[6] - lo[2]};
+  double q[4][3];
+#pragma unroll
+  for (int v = 0; v < 4; ++v)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) q[v][k] = quad[v * 3 + k] - lo[k];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    if (!((code >> t) & 1)) continue;
+    // triple t omits vertex t
+    const int i0 = t == 0 ? 1 : 0, i1 = t <= 1 ? 2 : 1, i2 = t <= 2 ? 3 : 2;
+    const double tri[3][3] = {{q[i0][0], q[i0][1], q[i0][2]}, {q[i1][0], q[i1][1], q[i1][2]}, {q[i2][0], q[i2][1], q[i2][2]}};
+    triangle_in_box(tri, H, [&](const double *a, const double *e1, const double *e2) { subtriangle_rule(a, e1, e2, tol, o, emit); });
+  }
+}
+
+template <class E>
+__device__ inline void pair_2d(const double *__restrict__ box, const double *__restrict__ seg, PairAcc &o, E &&emit)
+{
+  const double lo[2] = {box[0], box[1]};
+  const double H[2] = {box[4] - lo[0], box[5] - lo[1]};
+  const double p0[2] = {seg[0] - lo[0], seg[1] - lo[1]}, p1[2] = {seg[2] - lo[0], seg[3] - lo[1]};
+  double t0, t1;
+  if (!segment_in_box(p0, p1, H, t0, t1)) return;
+  const double d[2] = {p1[0] - p0[0], p1[1] - p0[1]};
+  const double a[2] = {p0[0] + t0 * d[0], p0[1] + t0 * d[1]};
+  const double e[2] = {(t1 - t0) * d[0], (t1 - t0) * d[1]};
+  const double J = sqrt(e[0] * e[0] + e[1] * e[1]);       // |det B| = length     intersections.cc:702-707
+  if (J < 1e-12) { o.dropped++; return; }                  // intersections.cc:710
+  const int nq = c_rule.n;
+  for (int q = 0; q < nq; ++q) {
+    const double s = c_rule.x[q][0];
+    const double x[2] = {a[0] + s * e[0], a[1] + s * e[1]};
+    emit(x, J * c_rule.w[q]);
+  }
+  o.nq += nq;
+}
+
+// ---------------------------------------------------------------------------------------
+// the fused kernel: one thread per candidate
+// ---------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(128) clip_local_kernel(uint64_t n_cand, const uint32_t *__restrict__ cand_im,
+                                                         const uint32_t *__restrict__ cand_bg, const double *__restrict__ bg_box,
+                                                         const double *__restrict__ im_verts, const uint8_t *__restrict__ split,
+                                                         const double *__restrict__ im_measure, double tol,
+                                                         double *__restrict__ sumw_out, double *__restrict__ local_out,
+                                                         uint16_t *__restrict__ nq_out, uint8_t *__restrict__ acc_out,
+                                                         unsigned long long *counters)
+{
+  constexpr int NL = 1 << D;
+  const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned acc = 0, nq = 0, dropped = 0, marginal = 0;
+  if (c < n_cand) {
+    const uint32_t m = cand_im[c], b = cand_bg[c];
+    const double *box = bg_box + (uint64_t)b * 8;
+    PairAcc o;
+    o.sumw = 0; o.nq = 0; o.dropped = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o.loc[i] = 0;
+    if (D == 3) {
+      const double ih[3] = {1.0 / (box[4] - box[0]), 1.0 / (box[5] - box[1]), 1.0 / (box[6] - box[2])};
+      pair_3d(box, im_verts + (uint64_t)m * 12, split[m], tol, o,
+              [&](const double *x, double w) { q1_add_3d(o, x[0] * ih[0], x[1] * ih[1], x[2] * ih[2], w); });
+    } else {
+      const double ih[2] = {1.0 / (box[4] - box[0]), 1.0 / (box[5] - box[1])};
+      pair_2d(box, im_verts + (uint64_t)m * 4, o, [&](const double *x, double w) { q1_add_2d(o, x[0] * ih[0], x[1] * ih[1], w); });
+    }
+    const bool ok = o.sumw > tol;                          // coupling_utilities.cc:61
+    sumw_out[c] = o.sumw;
+    acc_out[c] = ok ? 1 : 0;
+    nq_out[c] = (uint16_t)(ok ? o.nq : 0);
+    if (ok) {
+      double2 *dst = reinterpret_cast<double2 *>(local_out + c * NL);
+#pragma unroll
+      for (int i = 0; i < NL / 2; ++i) dst[i] = make_double2(o.loc[2 * i], o.loc[2 * i + 1]);
+      acc = 1; nq = o.nq;
+    }
+    dropped = o.dropped;
+    marginal = (o.sumw > 0.0 && o.sumw < 1e-12 * im_measure[m]) ? 1 : 0;
+  }
+  // block-level counters
+  __shared__ unsigned s_cnt[4];
+  if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  acc = __reduce_add_sync(0xffffffffu, acc);
+  nq = __reduce_add_sync(0xffffffffu, nq);
+  dropped = __reduce_add_sync(0xffffffffu, dropped);
+  marginal = __reduce_add_sync(0xffffffffu, marginal);
+  if ((threadIdx.x & 31) == 0) {
+    if (acc) atomicAdd(&s_cnt[0], acc);
+    if (nq) atomicAdd(&s_cnt[1], nq);
+    if (dropped) atomicAdd(&s_cnt[2], dropped);
+    if (marginal) atomicAdd(&s_cnt[3], marginal);
+  }
+  __syncthreads();
+  if (threadIdx.x < 4 && s_cnt[threadIdx.x]) atomicAdd(&counters[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+}
+
+// ---------------------------------------------------------------------------------------
+// unfused variants for the drop-in wrapper
+// ---------------------------------------------------------------------------------------
+// points/weights of every accepted pair (what the reference returns as Quadrature<spacedim>)
+template <int D>
+__global__ void emit_quadrature_kernel(uint64_t n_acc, const uint64_t *__restrict__ acc_idx, const uint32_t *__restrict__ cand_im,
+                                       const uint32_t *__restrict__ cand_bg, const double *__restrict__ bg_box,
+                                       const double *__restrict__ im_verts, const uint8_t *__restrict__ split, double tol,
+                                       const uint64_t *__restrict__ q_off, double *__restrict__ pts, double *__restrict__ wts)
+{
+  const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_acc) return;
+  const uint64_t c = acc_idx[p];
+  const uint32_t m = cand_im[c], b = cand_bg[c];
+  const double *box = bg_box + (uint64_t)b * 8;
+  PairAcc o;
+  o.sumw = 0; o.nq = 0; o.dropped = 0;
+  uint64_t w = q_off[p];
+  if (D == 3) {
+    pair_3d(box, im_verts + (uint64_t)m * 12, split[m], tol, o, [&](const double *x, double wq) {
+      pts[w * 3 + 0] = x[0] + box[0]; pts[w * 3 + 1] = x[1] + box[1]; pts[w * 3 + 2] = x[2] + box[2];
+      wts[w] = wq; ++w;
+    });
+  } else {
+    pair_2d(box, im_verts + (uint64_t)m * 4, o, [&](const double *x, double wq) {
+      pts[w * 2 + 0] = x[0] + box[0]; pts[w * 2 + 1] = x[1] + box[1];
+      wts[w] = wq; ++w;
+    });
+  }
+}
+
+__global__ void gather_nq_kernel(uint64_t n_acc, const uint64_t *__restrict__ acc_idx, const uint16_t *__restrict__ nq, uint32_t *__restrict__ out)
+{
+  const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n_acc) out[p] = nq[acc_idx[p]];
+  if (p == n_acc) out[p] = 0;
+}
+
+// local coupling vector from caller-supplied quadrature (coupling_utilities.h:238-274):
+// xi_q = F^-1(x_q) on the axis-aligned cell, local(i) += phi_i(xi_q) w_q.
+template <int D>
+__global__ void local_from_quadrature_kernel(uint64_t n_pairs, const uint32_t *__restrict__ im, const uint32_t *__restrict__ bg,
+                                             const uint64_t *__restrict__ q_off, const double *__restrict__ pts,
+                                             const double *__restrict__ wts, const uint64_t *__restrict__ cand_ptr,
+                                             const uint32_t *__restrict__ cand_bg, const double *__restrict__ bg_box, uint64_t n_im,
+                                             double *__restrict__ sumw_out, double *__restrict__ local_out,
+                                             uint8_t *__restrict__ acc_out, unsigned long long *n_missing)
+{
+  constexpr int NL = 1 << D;
+  const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  const uint32_t m = im[p], b = bg[p];
+  if (m >= n_im) { atomicAdd(n_missing, 1ULL); return; }
+  // locate the pair in the candidate list (sorted by background id inside the cell's run)
+  uint64_t lo = cand_ptr[m], hi = cand_ptr[m + 1];
+  while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (cand_bg[mid] < b) lo = mid + 1; else hi = mid; }
+  if (lo >= cand_ptr[m + 1] || cand_bg[lo] != b) { atomicAdd(n_missing, 1ULL); return; }
+  const double *box = bg_box + (uint64_t)b * 8;
+  PairAcc o;
+  o.sumw = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o.loc[i] = 0;
+  double ih[3];
+#pragma unroll
+  for (int k = 0; k < D; ++k) ih[k] = 1.0 / (box[4 + k] - box[k]);
+  for (uint64_t q = q_off[p]; q < q_off[p + 1]; ++q) {
+    const double *x = pts + q * D;
+    if (D == 3) q1_add_3d(o, (x[0] - box[0]) * ih[0], (x[1] - box[1]) * ih[1], (x[2] - box[2]) * ih[2], wts[q]);
+    else q1_add_2d(o, (x[0] - box[0]) * ih[0], (x[1] - box[1]) * ih[1], wts[q]);
+  }
+  sumw_out[lo] = o.sumw;
+  acc_out[lo] = 1;
+#pragma unroll
+  for (int i = 0; i < NL; ++i) local_out[lo * NL + i] = o.loc[i];
+}
+
+__global__ void flag_to_u64(uint64_t n, const uint8_t *__restrict__ f, uint64_t *__restrict__ out)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = f[i];
+  if (i == n) out[i] = 0;
+}
+__global__ void compact_idx(uint64_t n, const uint8_t *__restrict__ f, const uint64_t *__restrict__ pos, uint64_t *__restrict__ idx)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && f[i]) idx[pos[i]] = i;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+int nm_split_run(nm_ctx *ctx)
+{
+  const uint64_t n = ctx->n_im;
+  NM_TRY(nm_ensure(ctx, ctx->im_split, n + 1));
+  NM_TRY(nm_ensure(ctx, ctx->im_measure, (n + 1) * sizeof(double)));
+  NM_TRY(nm_ensure(ctx, ctx->counters, 64 * sizeof(uint64_t)));
+  unsigned long long *ties = ctx->counters.as<unsigned long long>() + 8;
+  NM_CUDA(cudaMemsetAsync(ties, 0, 8, ctx->stream));
+  ctx->counts.n_split_ties = 0;
+  if (n == 0) return NM_OK;
+  if (ctx->spacedim == 3) {
+    split_kernel<<<nm_blocks(n, 128), 128, 0, ctx->stream>>>(n, ctx->im_verts.as<double>(), ctx->im_split.as<uint8_t>(),
+                                                              ctx->im_measure.as<double>(), ties);
+    NM_CUDA(cudaGetLastError());
+    unsigned long long h = 0;
+    NM_CUDA(cudaMemcpyAsync(&h, ties, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    NM_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->counts.n_split_ties = h;
+  } else {
+    segment_measure_kernel<<<nm_blocks(n, 256), 256, 0, ctx->stream>>>(n, ctx->im_verts.as<double>(), ctx->im_measure.as<double>());
+    NM_CUDA(cudaGetLastError());
+  }
+  return NM_OK;
+}
+
+static int upload_rule(nm_ctx *ctx)
+{
+  Rule r;
+  if (!make_rule(ctx->dim1, ctx->degree, r))
+    return nm_fail(ctx, NM_ERR_UNSUPPORTED, "QGaussSimplex<%d>(n_points_1D=%u) is not tabulated (supported: %s)", ctx->dim1,
+                   ctx->degree, ctx->dim1 == 1 ? "1..4" : "1..3");
+  NM_CUDA(cudaMemcpyToSymbolAsync(c_rule, &r, sizeof(Rule), 0, cudaMemcpyHostToDevice, ctx->stream));
+  return NM_OK;
+}
+
+int nm_clip_run(nm_ctx *ctx)
+{
+  const int d = ctx->spacedim;
+  const uint64_t nc = ctx->counts.n_candidates;
+  const int NL = 1 << d;
+  NM_TRY(upload_rule(ctx));
+  NM_TRY(nm_ensure(ctx, ctx->cand_sumw, (nc + 1) * sizeof(double)));
+  NM_TRY(nm_ensure(ctx, ctx->cand_local, (nc + 1) * NL * sizeof(double)));
+  NM_TRY(nm_ensure(ctx, ctx->cand_nq, (nc + 1) * sizeof(uint16_t)));
+  NM_TRY(nm_ensure(ctx, ctx->scratch_b, (nc + 2) * sizeof(uint64_t)));  // reused later for compaction
+  NM_TRY(nm_ensure(ctx, ctx->cand_acc, nc + 1));
+  unsigned long long *cnt = ctx->counters.as<unsigned long long>();
+  NM_CUDA(cudaMemsetAsync(cnt, 0, 4 * sizeof(unsigned long long), ctx->stream));
+  ctx->counts.n_accepted = ctx->counts.n_qpoints = ctx->counts.n_dropped = ctx->counts.n_marginal = 0;
+  if (nc == 0) return NM_OK;
+  const unsigned T = 128, B = nm_blocks(nc, T);
+  if (d == 3)
+    clip_local_kernel<3><<<B, T, 0, ctx->stream>>>(nc, ctx->cand_im.as<uint32_t>(), ctx->cand_bg.as<uint32_t>(), ctx->bg_box.as<double>(),
+                                                   ctx->im_verts.as<double>(), ctx->im_split.as<uint8_t>(), ctx->im_measure.as<double>(),
+                                                   ctx->tol, ctx->cand_sumw.as<double>(), ctx->cand_local.as<double>(),
+                                                   ctx->cand_nq.as<uint16_t>(), ctx->cand_acc.as<uint8_t>(), cnt);
+  else
+    clip_local_kernel<2><<<B, T, 0, ctx->stream>>>(nc, ctx->cand_im.as<uint32_t>(), ctx->cand_bg.as<uint32_t>(), ctx->bg_box.as<double>(),
+                                                   ctx->im_verts.as<double>(), nullptr, ctx->im_measure.as<double>(), ctx->tol,
+                                                   ctx->cand_sumw.as<double>(), ctx->cand_local.as<double>(), ctx->cand_nq.as<uint16_t>(),
+                                                   ctx->cand_acc.as<uint8_t>(), cnt);
+  NM_CUDA(cudaGetLastError());
+  unsigned long long h[4];
+  NM_CUDA(cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->counts.n_accepted = h[0];
+  ctx->counts.n_qpoints = h[1];
+  ctx->counts.n_dropped = h[2];
+  ctx->counts.n_marginal = h[3];
+  return NM_OK;
+}
+
+// accepted-candidate index list (ascending) in ctx->scratch_b[nc+2 ...]; returns device pointer
+int nm_accepted_index(nm_ctx *ctx, uint64_t **idx_dev)
+{
+  const uint64_t nc = ctx->counts.n_candidates, na = ctx->counts.n_accepted;
+  NM_TRY(nm_ensure(ctx, ctx->scratch_b, (nc + 2) * sizeof(uint64_t)));
+  NM_TRY(nm_ensure(ctx, ctx->stage_x, (nc + 2) * sizeof(uint64_t)));
+  NM_TRY(nm_ensure(ctx, ctx->a_cursor, (na + 2) * sizeof(uint64_t)));
+  uint64_t *flags = ctx->scratch_b.as<uint64_t>(), *pos = ctx->stage_x.as<uint64_t>();
+  flag_to_u64<<<nm_blocks(nc + 1, 256), 256, 0, ctx->stream>>>(nc, ctx->cand_acc.as<uint8_t>(), flags);
+  NM_TRY(nm_exclusive_scan_u64(ctx, flags, pos, nc + 1));
+  if (nc) compact_idx<<<nm_blocks(nc, 256), 256, 0, ctx->stream>>>(nc, ctx->cand_acc.as<uint8_t>(), pos, ctx->a_cursor.as<uint64_t>());
+  NM_CUDA(cudaGetLastError());
+  *idx_dev = ctx->a_cursor.as<uint64_t>();
+  return NM_OK;
+}
+
+int nm_quadrature_emit(nm_ctx *ctx, uint64_t *q_offset, double *points, double *weights, int where)
+{
+  const int d = ctx->spacedim;
+  const uint64_t na = ctx->counts.n_accepted, nq = ctx->counts.n_qpoints;
+  uint64_t *acc_idx = nullptr;
+  NM_TRY(nm_accepted_index(ctx, &acc_idx));
+  // offsets
+  DevBuf &cnt32 = ctx->scratch_a;
+  NM_TRY(nm_ensure(ctx, cnt32, (na + 2) * sizeof(uint32_t)));
+  DevBuf &offs = ctx->c_rowstart;  // scratch use is safe: matrix build re-creates it
+  ctx->matrix_valid = false;
+  NM_TRY(nm_ensure(ctx, offs, (na + 2) * sizeof(uint64_t)));
+  gather_nq_kernel<<<nm_blocks(na + 1, 256), 256, 0, ctx->stream>>>(na, acc_idx, ctx->cand_nq.as<uint16_t>(), cnt32.as<uint32_t>());
+  NM_TRY(nm_exclusive_scan_u32_to_u64(ctx, cnt32.as<uint32_t>(), offs.as<uint64_t>(), na + 1));
+  if (q_offset) NM_TRY(nm_download(ctx, q_offset, offs.p, (na + 1) * sizeof(uint64_t), where));
+  if (!points && !weights) return NM_OK;
+  double *pts_d = points, *w_d = weights;
+  DevBuf &pbuf = ctx->c_val, &wbuf = ctx->c_col;  // scratch use (matrix invalidated above)
+  if (where == NM_HOST || !points || !weights) {
+    NM_TRY(nm_ensure(ctx, pbuf, (nq + 1) * d * sizeof(double)));
+    NM_TRY(nm_ensure(ctx, wbuf, (nq + 1) * sizeof(double)));
+    if (where == NM_HOST || !points) pts_d = pbuf.as<double>();
+    if (where == NM_HOST || !weights) w_d = wbuf.as<double>();
+  }
+  if (na) {
+    if (d == 3)
+      emit_quadrature_kernel<3><<<nm_blocks(na, 128), 128, 0, ctx->stream>>>(na, acc_idx, ctx->cand_im.as<uint32_t>(), ctx->cand_bg.as<uint32_t>(),
+                                                                           ctx->bg_box.as<double>(), ctx->im_verts.as<double>(),
+                                                                           ctx->im_split.as<uint8_t>(), ctx->tol, offs.as<uint64_t>(), pts_d, w_d);
+    else
+      emit_quadrature_kernel<2><<<nm_blocks(na, 128), 128, 0, ctx->stream>>>(na, acc_idx, ctx->cand_im.as<uint32_t>(), ctx->cand_bg.as<uint32_t>(),
+                                                                           ctx->bg_box.as<double>(), ctx->im_verts.as<double>(), nullptr,
+                                                                           ctx->tol, offs.as<uint64_t>(), pts_d, w_d);
+    NM_CUDA(cudaGetLastError());
+  }
+  if (where == NM_HOST) {
+    if (points) NM_TRY(nm_download(ctx, points, pts_d, nq * d * sizeof(double), NM_HOST));
+    if (weights) NM_TRY(nm_download(ctx, weights, w_d, nq * sizeof(double), NM_HOST));
+  }
+  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return NM_OK;
+}
+
+int nm_local_from_quadrature(nm_ctx *ctx, uint64_t n_pairs, const uint32_t *im, const uint32_t *bg, const uint64_t *q_offset,
+                             const double *points, const double *weights, int where)
+{
+  const int d = ctx->spacedim, NL = 1 << d;
+  const uint64_t nc = ctx->counts.n_candidates;
+  uint64_t nq = 0;
+  // all inputs to the device
+  const uint32_t *im_d = im, *bg_d = bg;
+  const uint64_t *qo_d = q_offset;
+  const double *p_d = points, *w_d = weights;
+  if (where == NM_HOST) {
+    nq = n_pairs ? q_offset[n_pairs] : 0;
+    size_t b0 = n_pairs * 4, b1 = n_pairs * 4, b2 = (n_pairs + 1) * 8, b3 = nq * d * 8, b4 = nq * 8;
+    auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+    NM_TRY(nm_ensure(ctx, ctx->h2d_stage, al(b0) + al(b1) + al(b2) + al(b3) + al(b4) + 256));
+    char *base = ctx->h2d_stage.as<char>();
+    char *p0 = base, *p1 = p0 + al(b0), *p2 = p1 + al(b1), *p3 = p2 + al(b2), *p4 = p3 + al(b3);
+    NM_CUDA(cudaMemcpyAsync(p0, im, b0, cudaMemcpyHostToDevice, ctx->stream));
+    NM_CUDA(cudaMemcpyAsync(p1, bg, b1, cudaMemcpyHostToDevice, ctx->stream));
+    NM_CUDA(cudaMemcpyAsync(p2, q_offset, b2, cudaMemcpyHostToDevice, ctx->stream));
+    NM_CUDA(cudaMemcpyAsync(p3, points, b3, cudaMemcpyHostToDevice, ctx->stream));
+    NM_CUDA(cudaMemcpyAsync(p4, weights, b4, cudaMemcpyHostToDevice, ctx->stream));
+    im_d = (const uint32_t *)p0; bg_d = (const uint32_t *)p1; qo_d = (const uint64_t *)p2; p_d = (const double *)p3; w_d = (const double *)p4;
+  }
+  NM_TRY(nm_ensure(ctx, ctx->cand_sumw, (nc + 1) * sizeof(double)));
+  NM_TRY(nm_ensure(ctx, ctx->cand_local, (nc + 1) * NL * sizeof(double)));
+  NM_TRY(nm_ensure(ctx, ctx->cand_acc, nc + 1));
+  NM_CUDA(cudaMemsetAsync(ctx->cand_acc.p, 0, nc + 1, ctx->stream));
+  NM_CUDA(cudaMemsetAsync(ctx->cand_sumw.p, 0, (nc + 1) * sizeof(double), ctx->stream));
+  unsigned long long *missing = ctx->counters.as<unsigned long long>() + 9;
+  NM_CUDA(cudaMemsetAsync(missing, 0, 8, ctx->stream));
+  if (n_pairs) {
+    if (d == 3)
+      local_from_quadrature_kernel<3><<<nm_blocks(n_pairs, 128), 128, 0, ctx->stream>>>(
+          n_pairs, im_d, bg_d, qo_d, p_d, w_d, ctx->cand_ptr.as<uint64_t>(), ctx->cand_bg.as<uint32_t>(), ctx->bg_box.as<double>(), ctx->n_im,
+          ctx->cand_sumw.as<double>(), ctx->cand_local.as<double>(), ctx->cand_acc.as<uint8_t>(), missing);
+    else
+      local_from_quadrature_kernel<2><<<nm_blocks(n_pairs, 128), 128, 0, ctx->stream>>>(
+          n_pairs, im_d, bg_d, qo_d, p_d, w_d, ctx->cand_ptr.as<uint64_t>(), ctx->cand_bg.as<uint32_t>(), ctx->bg_box.as<double>(), ctx->n_im,
+          ctx->cand_sumw.as<double>(), ctx->cand_local.as<double>(), ctx->cand_acc.as<uint8_t>(), missing);
+    NM_CUDA(cudaGetLastError());
+  }
+  unsigned long long h = 0;
+  NM_CUDA(cudaMemcpyAsync(&h, missing, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (h) return nm_fail(ctx, NM_ERR_INVALID, "%llu of the given pairs do not have overlapping bounding boxes on the grids set in this context", h);
+  ctx->counts.n_accepted = n_pairs;
+  return NM_OK;
+}

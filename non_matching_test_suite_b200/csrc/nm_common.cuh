@@ -1,0 +1,157 @@
+// Shared host-side state and helpers of libnmgpu.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "../../include/nmgpu.h"
+
+#define NM_SM_COUNT_B200 148
+
+// ---------------------------------------------------------------------------------------
+// device buffer that only grows; reused across calls so that a step does no cudaMalloc
+// ---------------------------------------------------------------------------------------
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// Background grid-hash slot: one occupied grid cell of one level.
+struct HashSlot {
+  unsigned long long key;  // packed (level, ix, iy, iz); ~0 = empty
+  uint32_t start;          // first entry in `entries`
+  uint32_t count;
+};
+
+struct GridIndex {
+  int d = 0;
+  double org[3] = {0, 0, 0};
+  double g0 = 0;            // spacing of level 0
+  uint32_t level_mask = 0;  // bit k: level k holds cells
+  int max_idx[32][3];       // largest occupied index per level/axis (query clamp)
+  uint32_t n_entries = 0;
+  uint32_t hash_cap = 0;    // power of two
+};
+
+struct nm_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int sm_count = NM_SM_COUNT_B200;
+
+  // ---- background ----
+  int spacedim = 0;
+  uint64_t n_bg = 0, n_space_dofs = 0, n_constrained = 0, n_cmasters = 0;
+  DevBuf bg_box;    // [n_bg][8] doubles: lo[0..2] pad hi[0..2] pad  (64 B, two sectors)
+  DevBuf bg_dofs;   // [n_bg][2^d] u32
+  DevBuf line_of;   // [n_space_dofs] int32: constraint line of a DoF or -1
+  DevBuf c_ptr;     // [n_constrained+1] u64
+  DevBuf c_master;  // u32
+  DevBuf c_weight;  // f64
+  bool bg_set = false, index_valid = false;
+
+  // ---- immersed ----
+  int dim1 = 0;
+  uint64_t n_im = 0, n_im_dofs = 0;
+  DevBuf im_verts;    // [n_im][2^dim1][spacedim] f64 (AoS, cell-major)
+  DevBuf im_dofs;     // [n_im] u32
+  DevBuf im_split;    // [n_im] u8 (3D)
+  DevBuf im_measure;  // [n_im] f64
+  bool im_set = false;
+
+  // ---- grid hash ----
+  GridIndex gi;
+  DevBuf idx_keys, idx_keys_alt, idx_vals, idx_vals_alt, idx_hash, idx_tmp;
+
+  // ---- intersection results ----
+  unsigned degree = 0;
+  double tol = 0;
+  nm_counts counts;
+  DevBuf cand_ptr;    // [n_im+1] u64
+  DevBuf cand_im;     // [n_cand] u32
+  DevBuf cand_bg;     // [n_cand] u32
+  DevBuf cand_sumw;   // [n_cand] f64
+  DevBuf cand_local;  // [n_cand][2^d] f64
+  DevBuf cand_nq;     // [n_cand] u16
+  DevBuf cand_acc;    // [n_cand] u8: pair accepted (sum of weights > tol)
+  DevBuf counters;    // device counters (u64 x 8)
+  bool intersect_valid = false;
+  bool local_from_user = false;  // cand_local was filled by nm_assemble_from_quadrature
+
+  // ---- matrix ----
+  // C orientation (rows = immersed cells of this shard), non-compact row storage
+  DevBuf c_rowstart;  // [n_im+1] u64 (capacity offsets)
+  DevBuf c_rowlen;    // [n_im] u32
+  DevBuf c_col;       // u32
+  DevBuf c_val;       // f64
+  uint64_t nnz = 0;
+  // stored orientation (rows = space dofs), compact CSR
+  DevBuf a_rowptr;  // [n_space_dofs+1] u64
+  DevBuf a_col;     // u32 (immersed dof)
+  DevBuf a_val;     // f64
+  DevBuf a_cursor;  // scratch
+  bool matrix_valid = false;
+
+  // ---- scratch ----
+  DevBuf scan_tmp, scratch_a, scratch_b, stage_x, stage_y, h2d_stage;
+
+  // ---- timing ----
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float t_ms[NM_T_COUNT];
+};
+
+// ---------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------
+int nm_fail(nm_ctx *c, int code, const char *fmt, ...);
+
+#define NM_CUDA(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return nm_fail(ctx, NM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+#define NM_TRY(call)            \
+  do {                          \
+    int rc__ = (call);          \
+    if (rc__ != NM_OK) return rc__; \
+  } while (0)
+
+int nm_ensure(nm_ctx *ctx, DevBuf &b, size_t bytes);
+int nm_upload(nm_ctx *ctx, DevBuf &b, const void *src, size_t bytes, int where);
+int nm_download(nm_ctx *ctx, void *dst, const void *src, size_t bytes, int where);
+
+struct PhaseTimer {
+  nm_ctx *c;
+  int phase;
+  bool accumulate;
+  PhaseTimer(nm_ctx *ctx, int ph, bool acc = false) : c(ctx), phase(ph), accumulate(acc) { cudaEventRecord(c->ev0, c->stream); }
+  void stop()
+  {
+    cudaEventRecord(c->ev1, c->stream);
+    cudaEventSynchronize(c->ev1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    if (accumulate) c->t_ms[phase] += ms; else c->t_ms[phase] = ms;
+  }
+};
+
+static inline unsigned nm_blocks(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// ---- phases implemented in the other translation units ----
+int nm_index_build(nm_ctx *ctx);
+int nm_candidates_run(nm_ctx *ctx);
+int nm_split_run(nm_ctx *ctx);
+int nm_clip_run(nm_ctx *ctx);
+int nm_quadrature_emit(nm_ctx *ctx, uint64_t *q_offset, double *points, double *weights, int where);
+int nm_local_from_quadrature(nm_ctx *ctx, uint64_t n_pairs, const uint32_t *im, const uint32_t *bg, const uint64_t *q_offset,
+                             const double *points, const double *weights, int where);
+int nm_matrix_build(nm_ctx *ctx);
+int nm_spmv_run(nm_ctx *ctx, int transpose, const double *x_dev, double *y_dev);
+int nm_exclusive_scan_u64(nm_ctx *ctx, const uint64_t *in, uint64_t *out, uint64_t n);
+int nm_exclusive_scan_u32_to_u64(nm_ctx *ctx, const uint32_t *in, uint64_t *out, uint64_t n);

@@ -1,0 +1,533 @@
+// Subsystem (1): bounding-box candidate pairs on the device.
+//
+// Replaces the Boost R-tree query loop of the reference
+//   for (immersed_box, immersed_cell) in immersed_tree:
+//     for (space_box, space_cell) in space_tree | queried(intersects(immersed_box))
+// (code/src/coupling_utilities.cc:40-55) with a multi-level uniform grid hash over the
+// background boxes.  The result is the exact set { (im, bg) : closed boxes overlap on the raw
+// doubles } -- the grid only produces a superset, the final test is the comparison itself.
+//
+// Grid: level k has spacing g0 * 2^k (g0 = smallest background cell extent); a background
+// cell lives on the smallest level whose spacing covers its extent.  Cell index functions are
+// monotone in the coordinate, so two boxes that overlap as closed intervals always share a
+// grid cell -- no epsilon is involved:
+//     background cell : [ floor(t(lo)), max(floor(t(lo)), ceil(t(hi)) - 1) ]
+//     query box       : [ ceil(t(lo)) - 1, floor(t(hi)) ]            t(x) = (x - org) * inv_k
+// (the asymmetric ends make a cell of a grid-aligned tree occupy exactly one grid cell while a
+// query box that only touches it still finds it).  A pair seen from several grid cells is
+// reported from the cell whose index is the per-axis max of the two lower ends.
+#include <cub/cub.cuh>
+
+#include "nm_common.cuh"
+
+namespace {
+
+struct GridDev {
+  int d;
+  double org[3];
+  double inv[32];
+  double g0;
+  uint32_t level_mask;
+  const HashSlot *hash;
+  uint32_t hash_mask;
+  const uint32_t *entries;  // background ids, grouped by grid cell
+  int idx_bits;
+};
+
+__host__ __device__ inline unsigned long long pack_key(int d, int level, long long ix, long long iy, long long iz)
+{
+  if (d == 2) return ((unsigned long long)level << 58) | ((unsigned long long)iy << 29) | (unsigned long long)ix;
+  return ((unsigned long long)level << 57) | ((unsigned long long)iz << 38) | ((unsigned long long)iy << 19) | (unsigned long long)ix;
+}
+
+__device__ inline unsigned long long mix64(unsigned long long k)
+{
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+  return k;
+}
+
+__device__ inline long long g_floor(double x, double org, double inv) { return (long long)floor((x - org) * inv); }
+__device__ inline long long g_ceilm1(double x, double org, double inv) { return (long long)ceil((x - org) * inv) - 1; }
+
+__device__ inline int level_of(double ext, double g0)
+{
+  int k = 0;
+  double g = g0;
+  while (g < ext && k < 31) { g *= 2.0; ++k; }
+  return k;
+}
+
+// ---------------------------------------------------------------------------------------
+// background layout kernels
+// ---------------------------------------------------------------------------------------
+// verts [n][2^d][d] -> box [n][8]; flags cells that are not axis-aligned boxes in deal.II
+// vertex order (vertex v: bit k selects the upper end along axis k).
+template <int D>
+__global__ void bg_boxes_from_verts(uint64_t n, const double *__restrict__ verts, double *__restrict__ box, int *bad)
+{
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  constexpr int NV = 1 << D;
+  const double *v = verts + i * NV * D;
+  double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < D; ++k) { lo[k] = v[k]; hi[k] = v[(NV - 1) * D + k]; ok &= lo[k] <= hi[k]; }
+#pragma unroll
+  for (int q = 0; q < NV; ++q)
+#pragma unroll
+    for (int k = 0; k < D; ++k) ok &= v[q * D + k] == (((q >> k) & 1) ? hi[k] : lo[k]);
+  if (!ok) atomicAdd(bad, 1);
+  double *b = box + i * 8;
+  b[0] = lo[0]; b[1] = lo[1]; b[2] = lo[2]; b[3] = 0;
+  b[4] = hi[0]; b[5] = hi[1]; b[6] = hi[2]; b[7] = 0;
+}
+
+template <int D>
+__global__ void bg_boxes_from_lohi(uint64_t n, const double *__restrict__ lo, const double *__restrict__ hi,
+                                   double *__restrict__ box, int *bad)
+{
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double *b = box + i * 8;
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    b[k] = k < D ? lo[i * D + k] : 0.0;
+    b[4 + k] = k < D ? hi[i * D + k] : 0.0;
+    ok &= b[k] <= b[4 + k];
+  }
+  b[3] = b[7] = 0;
+  if (!ok) atomicAdd(bad, 1);
+}
+
+__global__ void fill_line_of(uint64_t n_c, const uint32_t *__restrict__ c_dof, int32_t *__restrict__ line_of, uint64_t n_dofs, int *bad)
+{
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_c) return;
+  uint32_t d = c_dof[i];
+  if (d >= n_dofs) { atomicAdd(bad, 1); return; }
+  line_of[d] = (int32_t)i;
+}
+
+// per-block partial min of lo, min positive extent, max hi  -> out[block][8]
+template <int D>
+__global__ void bg_stats(uint64_t n, const double *__restrict__ box, double *__restrict__ out)
+{
+  double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY}, g = INFINITY, gm = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const double *b = box + i * 8;
+    double e = 0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      mn[k] = fmin(mn[k], b[k]);
+      mx[k] = fmax(mx[k], b[4 + k]);
+      e = fmax(e, b[4 + k] - b[k]);
+    }
+    if (e > 0) g = fmin(g, e);
+    gm = fmax(gm, e);
+  }
+  typedef cub::BlockReduce<double, 256> BR;
+  __shared__ typename BR::TempStorage tmp;
+  double r[8];
+  for (int k = 0; k < 3; ++k) { r[k] = BR(tmp).Reduce(mn[k], cub::Min()); __syncthreads(); }
+  for (int k = 0; k < 3; ++k) { r[3 + k] = BR(tmp).Reduce(mx[k], cub::Max()); __syncthreads(); }
+  r[6] = BR(tmp).Reduce(g, cub::Min()); __syncthreads();
+  r[7] = BR(tmp).Reduce(gm, cub::Max());
+  if (threadIdx.x == 0)
+    for (int k = 0; k < 8; ++k) out[blockIdx.x * 8 + k] = r[k];
+}
+
+// ---------------------------------------------------------------------------------------
+// grid entries
+// ---------------------------------------------------------------------------------------
+template <int D>
+__device__ inline void bg_range(const GridDev &G, const double *b, int &level, long long *L, long long *H)
+{
+  double e = 0;
+#pragma unroll
+  for (int k = 0; k < D; ++k) e = fmax(e, b[4 + k] - b[k]);
+  level = level_of(e, G.g0);
+  const double inv = G.inv[level];
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    L[k] = g_floor(b[k], G.org[k], inv);
+    long long h = g_ceilm1(b[4 + k], G.org[k], inv);
+    H[k] = h > L[k] ? h : L[k];
+  }
+  for (int k = D; k < 3; ++k) L[k] = H[k] = 0;
+}
+
+template <int D>
+__global__ void entries_count(GridDev G, uint64_t n, const double *__restrict__ box, uint32_t *__restrict__ cnt,
+                              unsigned *level_mask, int *bad)
+{
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int level; long long L[3], H[3];
+  bg_range<D>(G, box + i * 8, level, L, H);
+  uint64_t c = 1;
+  const long long lim = 1LL << G.idx_bits;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    c *= (uint64_t)(H[k] - L[k] + 1);
+    if (L[k] < 0 || H[k] >= lim) atomicAdd(bad, 1);
+  }
+  if (c > 64) { atomicAdd(bad, 1); c = 0; }
+  cnt[i] = (uint32_t)c;
+  atomicOr(level_mask, 1u << level);
+}
+
+template <int D>
+__global__ void entries_fill(GridDev G, uint64_t n, const double *__restrict__ box, const uint64_t *__restrict__ off,
+                             unsigned long long *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int level; long long L[3], H[3];
+  bg_range<D>(G, box + i * 8, level, L, H);
+  uint64_t o = off[i];
+  for (long long z = L[2]; z <= H[2]; ++z)
+    for (long long y = L[1]; y <= H[1]; ++y)
+      for (long long x = L[0]; x <= H[0]; ++x) {
+        keys[o] = pack_key(D, level, x, y, z);
+        vals[o] = (uint32_t)i;
+        ++o;
+      }
+}
+
+__global__ void hash_clear(HashSlot *h, uint32_t cap)
+{
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cap) { h[i].key = ~0ULL; h[i].start = 0; h[i].count = 0; }
+}
+
+__global__ void hash_insert_runs(uint32_t n, const unsigned long long *__restrict__ keys, HashSlot *h, uint32_t mask)
+{
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long k = keys[i];
+  if (i > 0 && keys[i - 1] == k) return;
+  uint32_t e = i + 1;
+  while (e < n && keys[e] == k) ++e;
+  uint32_t s = (uint32_t)mix64(k) & mask;
+  while (true) {
+    unsigned long long old = atomicCAS(&h[s].key, ~0ULL, k);
+    if (old == ~0ULL) { h[s].start = i; h[s].count = e - i; return; }
+    s = (s + 1) & mask;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// candidate query
+// ---------------------------------------------------------------------------------------
+template <int D, typename Emit>
+__device__ inline void query_box(const GridDev &G, const double *__restrict__ bg_box, const double *qlo, const double *qhi, Emit emit)
+{
+  const long long lim = (1LL << G.idx_bits) - 1;
+  uint32_t lm = G.level_mask;
+  while (lm) {
+    const int level = __ffs(lm) - 1;
+    lm &= lm - 1;
+    const double inv = G.inv[level];
+    long long L[3] = {0, 0, 0}, H[3] = {0, 0, 0};
+    bool empty = false;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      L[k] = g_ceilm1(qlo[k], G.org[k], inv);
+      H[k] = g_floor(qhi[k], G.org[k], inv);
+      if (L[k] < 0) L[k] = 0;
+      if (H[k] > lim) H[k] = lim;
+      empty |= L[k] > H[k];
+    }
+    if (empty) continue;
+    for (long long z = L[2]; z <= H[2]; ++z)
+      for (long long y = L[1]; y <= H[1]; ++y)
+        for (long long x = L[0]; x <= H[0]; ++x) {
+          const unsigned long long key = pack_key(D, level, x, y, z);
+          uint32_t s = (uint32_t)mix64(key) & G.hash_mask;
+          uint32_t start = 0, count = 0;
+          while (true) {
+            const unsigned long long k = G.hash[s].key;
+            if (k == key) { start = G.hash[s].start; count = G.hash[s].count; break; }
+            if (k == ~0ULL) break;
+            s = (s + 1) & G.hash_mask;
+          }
+          const long long cell[3] = {x, y, z};
+          for (uint32_t e = 0; e < count; ++e) {
+            const uint32_t b = G.entries[start + e];
+            const double *bb = bg_box + (uint64_t)b * 8;
+            bool hit = true;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+              const double blo = bb[k], bhi = bb[4 + k];
+              hit &= (blo <= qhi[k]) && (qlo[k] <= bhi);  // the reference's closed-box test, verbatim semantics
+              // report the pair from one grid cell only: the per-axis max of the lower ends
+              long long lb = g_floor(blo, G.org[k], inv);
+              long long first = lb > L[k] ? lb : L[k];
+              hit &= cell[k] == first;
+            }
+            if (hit) emit(b);
+          }
+        }
+  }
+}
+
+template <int D, int NVI>
+__device__ inline void im_box(const double *__restrict__ v, double *lo, double *hi)
+{
+#pragma unroll
+  for (int k = 0; k < D; ++k) { lo[k] = v[k]; hi[k] = v[k]; }
+#pragma unroll
+  for (int q = 1; q < NVI; ++q)
+#pragma unroll
+    for (int k = 0; k < D; ++k) { lo[k] = fmin(lo[k], v[q * D + k]); hi[k] = fmax(hi[k], v[q * D + k]); }
+}
+
+template <int D>
+__global__ void cand_count(GridDev G, uint64_t n_im, const double *__restrict__ im_verts, const double *__restrict__ bg_box,
+                           uint32_t *__restrict__ cnt)
+{
+  uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n_im) return;
+  constexpr int NVI = 1 << (D - 1);
+  double lo[3], hi[3];
+  im_box<D, NVI>(im_verts + m * NVI * D, lo, hi);
+  uint32_t c = 0;
+  query_box<D>(G, bg_box, lo, hi, [&](uint32_t) { ++c; });
+  cnt[m] = c;
+}
+
+template <int D>
+__global__ void cand_fill(GridDev G, uint64_t n_im, const double *__restrict__ im_verts, const double *__restrict__ bg_box,
+                          const uint64_t *__restrict__ ptr, uint32_t *__restrict__ cand_im, uint32_t *__restrict__ cand_bg)
+{
+  uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n_im) return;
+  constexpr int NVI = 1 << (D - 1);
+  double lo[3], hi[3];
+  im_box<D, NVI>(im_verts + m * NVI * D, lo, hi);
+  const uint64_t p0 = ptr[m];
+  uint64_t p = p0;
+  // insertion into the (short) sorted run of this immersed cell: output ordered by (im, bg)
+  query_box<D>(G, bg_box, lo, hi, [&](uint32_t b) {
+    uint64_t j = p;
+    while (j > p0 && cand_bg[j - 1] > b) { cand_bg[j] = cand_bg[j - 1]; --j; }
+    cand_bg[j] = b;
+    cand_im[p] = (uint32_t)m;
+    ++p;
+  });
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+int nm_exclusive_scan_u64(nm_ctx *ctx, const uint64_t *in, uint64_t *out, uint64_t n)
+{
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, ctx->stream);
+  NM_TRY(nm_ensure(ctx, ctx->scan_tmp, bytes));
+  NM_CUDA(cub::DeviceScan::ExclusiveSum(ctx->scan_tmp.p, bytes, in, out, n, ctx->stream));
+  return NM_OK;
+}
+
+namespace {
+struct U32ToU64 {
+  __host__ __device__ uint64_t operator()(uint32_t v) const { return (uint64_t)v; }
+};
+}  // namespace
+
+int nm_exclusive_scan_u32_to_u64(nm_ctx *ctx, const uint32_t *in, uint64_t *out, uint64_t n)
+{
+  cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t *> it(in, U32ToU64());
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, out, n, ctx->stream);
+  NM_TRY(nm_ensure(ctx, ctx->scan_tmp, bytes));
+  NM_CUDA(cub::DeviceScan::ExclusiveSum(ctx->scan_tmp.p, bytes, it, out, n, ctx->stream));
+  return NM_OK;
+}
+
+int nm_bg_layout(nm_ctx *ctx, int d, uint64_t n, const double *verts_dev, const double *lo_dev, const double *hi_dev)
+{
+  NM_TRY(nm_ensure(ctx, ctx->bg_box, n * 8 * sizeof(double)));
+  NM_TRY(nm_ensure(ctx, ctx->counters, 64 * sizeof(uint64_t)));
+  int *bad = ctx->counters.as<int>();
+  NM_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
+  const unsigned T = 256, B = nm_blocks(n, T);
+  if (n) {
+    if (verts_dev) {
+      if (d == 2) bg_boxes_from_verts<2><<<B, T, 0, ctx->stream>>>(n, verts_dev, ctx->bg_box.as<double>(), bad);
+      else bg_boxes_from_verts<3><<<B, T, 0, ctx->stream>>>(n, verts_dev, ctx->bg_box.as<double>(), bad);
+    } else {
+      if (d == 2) bg_boxes_from_lohi<2><<<B, T, 0, ctx->stream>>>(n, lo_dev, hi_dev, ctx->bg_box.as<double>(), bad);
+      else bg_boxes_from_lohi<3><<<B, T, 0, ctx->stream>>>(n, lo_dev, hi_dev, ctx->bg_box.as<double>(), bad);
+    }
+    NM_CUDA(cudaGetLastError());
+  }
+  int h_bad = 0;
+  NM_CUDA(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (h_bad)
+    return nm_fail(ctx, NM_ERR_UNSUPPORTED,
+                   "%d background cell(s) are not axis-aligned boxes in deal.II vertex order; only Cartesian "
+                   "background cells (hyper_cube refinements, as in every reference config) are implemented", h_bad);
+  return NM_OK;
+}
+
+int nm_constraints_layout(nm_ctx *ctx)
+{
+  NM_TRY(nm_ensure(ctx, ctx->line_of, (ctx->n_space_dofs + 1) * sizeof(int32_t)));
+  NM_CUDA(cudaMemsetAsync(ctx->line_of.p, 0xff, ctx->n_space_dofs * sizeof(int32_t), ctx->stream));
+  if (ctx->n_constrained) {
+    int *bad = ctx->counters.as<int>();
+    NM_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
+    fill_line_of<<<nm_blocks(ctx->n_constrained, 256), 256, 0, ctx->stream>>>(
+        ctx->n_constrained, ctx->scratch_a.as<uint32_t>(), ctx->line_of.as<int32_t>(), ctx->n_space_dofs, bad);
+    NM_CUDA(cudaGetLastError());
+    int h_bad = 0;
+    NM_CUDA(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    NM_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h_bad) return nm_fail(ctx, NM_ERR_INVALID, "%d constrained DoF index(es) >= n_dofs", h_bad);
+  }
+  return NM_OK;
+}
+
+static GridDev make_grid_dev(const nm_ctx *ctx)
+{
+  GridDev G;
+  memset(&G, 0, sizeof(G));
+  G.d = ctx->gi.d;
+  for (int k = 0; k < 3; ++k) G.org[k] = ctx->gi.org[k];
+  double g = ctx->gi.g0;
+  G.g0 = g;
+  for (int k = 0; k < 32; ++k) { G.inv[k] = 1.0 / g; g *= 2.0; }
+  G.level_mask = ctx->gi.level_mask;
+  G.hash = ctx->idx_hash.as<HashSlot>();
+  G.hash_mask = ctx->gi.hash_cap - 1;
+  G.entries = ctx->idx_vals.as<uint32_t>();
+  G.idx_bits = ctx->gi.d == 2 ? 29 : 19;
+  return G;
+}
+
+int nm_index_build(nm_ctx *ctx)
+{
+  const int d = ctx->spacedim;
+  const uint64_t n = ctx->n_bg;
+  ctx->gi = GridIndex();
+  ctx->gi.d = d;
+  ctx->index_valid = false;
+  if (n == 0) { ctx->gi.g0 = 1; ctx->gi.hash_cap = 1; ctx->index_valid = true;
+    NM_TRY(nm_ensure(ctx, ctx->idx_hash, sizeof(HashSlot)));
+    hash_clear<<<1, 32, 0, ctx->stream>>>(ctx->idx_hash.as<HashSlot>(), 1);
+    return NM_OK; }
+  // 1. origin and level-0 spacing
+  const unsigned SB = 256;
+  NM_TRY(nm_ensure(ctx, ctx->idx_tmp, SB * 8 * sizeof(double)));
+  if (d == 2) bg_stats<2><<<SB, 256, 0, ctx->stream>>>(n, ctx->bg_box.as<double>(), ctx->idx_tmp.as<double>());
+  else bg_stats<3><<<SB, 256, 0, ctx->stream>>>(n, ctx->bg_box.as<double>(), ctx->idx_tmp.as<double>());
+  NM_CUDA(cudaGetLastError());
+  static thread_local double h_stats[SB * 8];
+  NM_CUDA(cudaMemcpyAsync(h_stats, ctx->idx_tmp.p, sizeof(h_stats), cudaMemcpyDeviceToHost, ctx->stream));
+  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  double org[3] = {INFINITY, INFINITY, INFINITY}, top[3] = {-INFINITY, -INFINITY, -INFINITY}, g0 = INFINITY, gmax = 0;
+  for (unsigned b = 0; b < SB; ++b) {
+    for (int k = 0; k < 3; ++k) { org[k] = fmin(org[k], h_stats[b * 8 + k]); top[k] = fmax(top[k], h_stats[b * 8 + 3 + k]); }
+    g0 = fmin(g0, h_stats[b * 8 + 6]);
+    gmax = fmax(gmax, h_stats[b * 8 + 7]);
+  }
+  if (!(g0 < INFINITY)) g0 = 1.0;  // all cells degenerate
+  for (int k = 0; k < 3; ++k) ctx->gi.org[k] = k < d ? org[k] : 0.0;
+  ctx->gi.g0 = g0;
+  if (gmax > g0 * 2147483648.0)
+    return nm_fail(ctx, NM_ERR_UNSUPPORTED, "background cell extents span more than 31 octaves (%g .. %g)", g0, gmax);
+  const int bits = d == 2 ? 29 : 19;
+  for (int k = 0; k < d; ++k)
+    if ((top[k] - org[k]) / g0 >= (double)(1LL << bits) - 2)
+      return nm_fail(ctx, NM_ERR_UNSUPPORTED,
+                     "background spans more than 2^%d finest cells along axis %d (extent %g, finest cell %g)", bits, k,
+                     top[k] - org[k], g0);
+
+  // 2. entries: count, scan, fill
+  GridDev G = make_grid_dev(ctx);
+  NM_TRY(nm_ensure(ctx, ctx->scratch_a, n * sizeof(uint32_t)));
+  NM_TRY(nm_ensure(ctx, ctx->scratch_b, (n + 1) * sizeof(uint64_t)));
+  NM_TRY(nm_ensure(ctx, ctx->counters, 64 * sizeof(uint64_t)));
+  unsigned *lmask = ctx->counters.as<unsigned>() + 2;
+  int *bad = ctx->counters.as<int>();
+  NM_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 64, ctx->stream));
+  const unsigned T = 256, B = nm_blocks(n, T);
+  if (d == 2) entries_count<2><<<B, T, 0, ctx->stream>>>(G, n, ctx->bg_box.as<double>(), ctx->scratch_a.as<uint32_t>(), lmask, bad);
+  else entries_count<3><<<B, T, 0, ctx->stream>>>(G, n, ctx->bg_box.as<double>(), ctx->scratch_a.as<uint32_t>(), lmask, bad);
+  NM_CUDA(cudaGetLastError());
+  NM_TRY(nm_exclusive_scan_u32_to_u64(ctx, ctx->scratch_a.as<uint32_t>(), ctx->scratch_b.as<uint64_t>(), n));
+  uint64_t last_off = 0; uint32_t last_cnt = 0; unsigned h_hdr[4];
+  NM_CUDA(cudaMemcpyAsync(&last_off, ctx->scratch_b.as<uint64_t>() + (n - 1), 8, cudaMemcpyDeviceToHost, ctx->stream));
+  NM_CUDA(cudaMemcpyAsync(&last_cnt, ctx->scratch_a.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
+  NM_CUDA(cudaMemcpyAsync(h_hdr, ctx->counters.p, sizeof(h_hdr), cudaMemcpyDeviceToHost, ctx->stream));
+  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (h_hdr[0]) return nm_fail(ctx, NM_ERR_UNSUPPORTED, "background cells outside the indexable grid range");
+  const uint64_t ne = last_off + last_cnt;
+  if (ne >= 0xffffffffULL) return nm_fail(ctx, NM_ERR_UNSUPPORTED, "grid index needs %llu entries (limit 2^32)", (unsigned long long)ne);
+  ctx->gi.level_mask = h_hdr[2];
+  ctx->gi.n_entries = (uint32_t)ne;
+  NM_TRY(nm_ensure(ctx, ctx->idx_keys, ne * 8));
+  NM_TRY(nm_ensure(ctx, ctx->idx_keys_alt, ne * 8));
+  NM_TRY(nm_ensure(ctx, ctx->idx_vals, ne * 4));
+  NM_TRY(nm_ensure(ctx, ctx->idx_vals_alt, ne * 4));
+  if (d == 2) entries_fill<2><<<B, T, 0, ctx->stream>>>(G, n, ctx->bg_box.as<double>(), ctx->scratch_b.as<uint64_t>(),
+                                                       ctx->idx_keys_alt.as<unsigned long long>(), ctx->idx_vals_alt.as<uint32_t>());
+  else entries_fill<3><<<B, T, 0, ctx->stream>>>(G, n, ctx->bg_box.as<double>(), ctx->scratch_b.as<uint64_t>(),
+                                                 ctx->idx_keys_alt.as<unsigned long long>(), ctx->idx_vals_alt.as<uint32_t>());
+  NM_CUDA(cudaGetLastError());
+  // 3. sort by grid cell (stable: background ids stay ascending inside a cell)
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, ctx->idx_keys_alt.as<unsigned long long>(), ctx->idx_keys.as<unsigned long long>(),
+                                  ctx->idx_vals_alt.as<uint32_t>(), ctx->idx_vals.as<uint32_t>(), (int64_t)ne, 0, 63, ctx->stream);
+  NM_TRY(nm_ensure(ctx, ctx->scan_tmp, bytes));
+  NM_CUDA(cub::DeviceRadixSort::SortPairs(ctx->scan_tmp.p, bytes, ctx->idx_keys_alt.as<unsigned long long>(),
+                                          ctx->idx_keys.as<unsigned long long>(), ctx->idx_vals_alt.as<uint32_t>(),
+                                          ctx->idx_vals.as<uint32_t>(), (int64_t)ne, 0, 63, ctx->stream));
+  // 4. hash: occupied grid cell -> run of entries
+  uint32_t cap = 64;
+  while (cap < 2 * ne) cap <<= 1;
+  ctx->gi.hash_cap = cap;
+  NM_TRY(nm_ensure(ctx, ctx->idx_hash, (size_t)cap * sizeof(HashSlot)));
+  hash_clear<<<nm_blocks(cap, 256), 256, 0, ctx->stream>>>(ctx->idx_hash.as<HashSlot>(), cap);
+  hash_insert_runs<<<nm_blocks(ne, 256), 256, 0, ctx->stream>>>((uint32_t)ne, ctx->idx_keys.as<unsigned long long>(),
+                                                                ctx->idx_hash.as<HashSlot>(), cap - 1);
+  NM_CUDA(cudaGetLastError());
+  ctx->index_valid = true;
+  return NM_OK;
+}
+
+int nm_candidates_run(nm_ctx *ctx)
+{
+  const int d = ctx->spacedim;
+  const uint64_t n_im = ctx->n_im;
+  GridDev G = make_grid_dev(ctx);
+  NM_TRY(nm_ensure(ctx, ctx->scratch_a, (n_im + 1) * sizeof(uint32_t)));
+  NM_TRY(nm_ensure(ctx, ctx->cand_ptr, (n_im + 1) * sizeof(uint64_t)));
+  ctx->counts.n_candidates = 0;
+  if (n_im == 0) { NM_CUDA(cudaMemsetAsync(ctx->cand_ptr.p, 0, 8, ctx->stream)); return NM_OK; }
+  const unsigned T = 128, B = nm_blocks(n_im, T);
+  NM_CUDA(cudaMemsetAsync(ctx->scratch_a.as<uint32_t>() + n_im, 0, 4, ctx->stream));
+  if (d == 2) cand_count<2><<<B, T, 0, ctx->stream>>>(G, n_im, ctx->im_verts.as<double>(), ctx->bg_box.as<double>(), ctx->scratch_a.as<uint32_t>());
+  else cand_count<3><<<B, T, 0, ctx->stream>>>(G, n_im, ctx->im_verts.as<double>(), ctx->bg_box.as<double>(), ctx->scratch_a.as<uint32_t>());
+  NM_CUDA(cudaGetLastError());
+  NM_TRY(nm_exclusive_scan_u32_to_u64(ctx, ctx->scratch_a.as<uint32_t>(), ctx->cand_ptr.as<uint64_t>(), n_im + 1));
+  uint64_t n_cand = 0;
+  NM_CUDA(cudaMemcpyAsync(&n_cand, ctx->cand_ptr.as<uint64_t>() + n_im, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (n_cand >= 0xffffffffULL * 16) return nm_fail(ctx, NM_ERR_UNSUPPORTED, "too many candidate pairs (%llu)", (unsigned long long)n_cand);
+  ctx->counts.n_candidates = n_cand;
+  NM_TRY(nm_ensure(ctx, ctx->cand_im, (n_cand + 1) * 4));
+  NM_TRY(nm_ensure(ctx, ctx->cand_bg, (n_cand + 1) * 4));
+  if (d == 2) cand_fill<2><<<B, T, 0, ctx->stream>>>(G, n_im, ctx->im_verts.as<double>(), ctx->bg_box.as<double>(), ctx->cand_ptr.as<uint64_t>(),
+                                                    ctx->cand_im.as<uint32_t>(), ctx->cand_bg.as<uint32_t>());
+  else cand_fill<3><<<B, T, 0, ctx->stream>>>(G, n_im, ctx->im_verts.as<double>(), ctx->bg_box.as<double>(), ctx->cand_ptr.as<uint64_t>(),
+                                              ctx->cand_im.as<uint32_t>(), ctx->cand_bg.as<uint32_t>());
+  NM_CUDA(cudaGetLastError());
+  return NM_OK;
+}

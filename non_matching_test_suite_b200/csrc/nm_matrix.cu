@@ -1,0 +1,470 @@
+// Subsystems (3b) and (4): scatter through constraint lines into a device-built CSR matrix,
+// and the C / C^T sparse matrix-vector products.
+//
+// Replaces
+//   create_coupling_sparsity_pattern_with_exact_intersections   code/include/coupling_utilities.h:100-139
+//     (AffineConstraints::add_entries_local_to_global with keep_constrained_entries = true)
+//   the scatter of create_coupling_mass_matrix_with_exact_intersections   :276-289
+//     (AffineConstraints::distribute_local_to_global, rectangular version, + compress(add))
+//   Ct.vmult / C.Tvmult on the Trilinos matrix   code/examples/lagrange_multiplier/2d3d/lagrange_multiplier.cc:627-643
+//
+// Design: the immersed space is discontinuous (FE_DGQ), so an immersed cell owns its column of
+// the stored matrix exclusively.  One warp merges all accepted pairs of one immersed cell:
+// every (space dof, value) contribution is expanded through its constraint line, the entries
+// are sorted by dof in shared memory and equal dofs are summed in a fixed order.  No global
+// atomics, no global sort, bit-reproducible values.  The rows produced this way are the rows
+// of C (= columns of the stored matrix); the stored orientation is obtained by one device
+// transpose (histogram, scan, scatter, per-row sort).
+#include <cub/cub.cuh>
+
+#include "nm_common.cuh"
+
+namespace {
+
+constexpr int WARP_CAP = 512;    // entries a warp can merge in shared memory
+constexpr int BLOCK_CAP = 8192;  // entries a 256-thread block can merge
+
+// ---------------------------------------------------------------------------------------
+// capacity of each row of C: accepted pairs x (dofs + masters)
+// ---------------------------------------------------------------------------------------
+template <int NL>
+__global__ void row_capacity_kernel(uint64_t n_im, const uint64_t *__restrict__ cand_ptr, const uint32_t *__restrict__ cand_bg,
+                                    const uint8_t *__restrict__ acc, const uint32_t *__restrict__ bg_dofs,
+                                    const int32_t *__restrict__ line_of, const uint64_t *__restrict__ c_ptr,
+                                    uint32_t *__restrict__ cap, unsigned *max_cap, unsigned *n_big)
+{
+  const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n_im) return;
+  uint32_t c = 0;
+  for (uint64_t p = cand_ptr[m]; p < cand_ptr[m + 1]; ++p) {
+    if (!acc[p]) continue;
+    const uint32_t *dofs = bg_dofs + (uint64_t)cand_bg[p] * NL;
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      const int32_t ln = line_of[dofs[i]];
+      c += 1 + (ln >= 0 ? (uint32_t)(c_ptr[ln + 1] - c_ptr[ln]) : 0u);
+    }
+  }
+  cap[m] = c;
+  if (c > WARP_CAP) { atomicAdd(n_big, 1u); atomicMax(max_cap, c); }
+}
+
+__global__ void list_big_rows(uint64_t n_im, const uint32_t *__restrict__ cap, uint32_t *__restrict__ list, unsigned *cursor)
+{
+  const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < n_im && cap[m] > WARP_CAP) list[atomicAdd(cursor, 1u)] = (uint32_t)m;
+}
+
+// ---------------------------------------------------------------------------------------
+// merge: one group (warp or block) per immersed cell
+// ---------------------------------------------------------------------------------------
+template <int G> __device__ inline void group_sync() { if (G == 32) __syncwarp(); else __syncthreads(); }
+
+// exclusive scan of one value per thread inside the group; returns the offset, `total` to all
+template <int G>
+__device__ inline unsigned group_scan(unsigned v, unsigned &total, unsigned *s_tmp)
+{
+  const unsigned lane = threadIdx.x & 31;
+  unsigned inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= (unsigned)o) inc += t;
+  }
+  if (G == 32) {
+    total = __shfl_sync(0xffffffffu, inc, 31);
+    return inc - v;
+  }
+  const unsigned w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 31) s_tmp[w] = inc;
+  __syncthreads();
+  unsigned base = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < G / 32; ++i) { unsigned t = s_tmp[i]; if ((unsigned)i < w) base += t; tot += t; }
+  total = tot;
+  return base + inc - v;
+}
+
+template <int NL, int G, int CAP>
+__device__ inline void merge_cell(uint64_t m, unsigned tid, unsigned long long *s_key, double *s_val, unsigned *s_tmp,
+                                  const uint64_t *__restrict__ cand_ptr, const uint32_t *__restrict__ cand_bg,
+                                  const uint8_t *__restrict__ acc, const double *__restrict__ local,
+                                  const uint32_t *__restrict__ bg_dofs, const int32_t *__restrict__ line_of,
+                                  const uint64_t *__restrict__ c_ptr, const uint32_t *__restrict__ c_master,
+                                  const double *__restrict__ c_weight, const uint64_t *__restrict__ rowstart,
+                                  uint32_t *__restrict__ rowlen, uint32_t *__restrict__ out_col, double *__restrict__ out_val)
+{
+  const uint64_t p0 = cand_ptr[m], p1 = cand_ptr[m + 1];
+  // 1. emit (dof, value) entries, constraint lines expanded, in a fixed order
+  unsigned E = 0;
+  for (uint64_t base = p0; base < p1; base += G) {
+    const uint64_t p = base + tid;
+    const bool on = p < p1 && acc[p];
+    unsigned cnt = 0;
+    uint32_t dofs[NL];
+    int32_t ln[NL];
+    if (on) {
+      const uint32_t *dp = bg_dofs + (uint64_t)cand_bg[p] * NL;
+#pragma unroll
+      for (int i = 0; i < NL; ++i) {
+        dofs[i] = dp[i];
+        ln[i] = line_of[dofs[i]];
+        cnt += 1 + (ln[i] >= 0 ? (unsigned)(c_ptr[ln[i] + 1] - c_ptr[ln[i]]) : 0u);
+      }
+    }
+    unsigned total;
+    unsigned off = E + group_scan<G>(cnt, total, s_tmp);
+    if (on) {
+#pragma unroll
+      for (int i = 0; i < NL; ++i) {
+        const double v = local[p * NL + i];
+        if (ln[i] < 0) {
+          s_key[off] = ((unsigned long long)dofs[i] << 32) | off; s_val[off] = v; ++off;
+        } else {
+          // keep_constrained_entries: the constrained row is in the pattern, structurally zero
+          s_key[off] = ((unsigned long long)dofs[i] << 32) | off; s_val[off] = 0.0; ++off;
+          for (uint64_t k = c_ptr[ln[i]]; k < c_ptr[ln[i] + 1]; ++k) {
+            s_key[off] = ((unsigned long long)c_master[k] << 32) | off; s_val[off] = c_weight[k] * v; ++off;
+          }
+        }
+      }
+    }
+    E += total;
+  }
+  if (E == 0) { if (tid == 0) rowlen[m] = 0; return; }
+  // 2. bitonic sort by (dof, emission index)
+  unsigned n2 = 32;
+  while (n2 < E) n2 <<= 1;
+  for (unsigned i = E + tid; i < n2; i += G) { s_key[i] = ~0ULL; s_val[i] = 0.0; }
+  group_sync<G>();
+  for (unsigned k = 2; k <= n2; k <<= 1)
+    for (unsigned j = k >> 1; j > 0; j >>= 1) {
+      for (unsigned i = tid; i < n2; i += G) {
+        const unsigned l = i ^ j;
+        if (l > i) {
+          const unsigned long long a = s_key[i], b = s_key[l];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) {
+            s_key[i] = b; s_key[l] = a;
+            const double t = s_val[i]; s_val[i] = s_val[l]; s_val[l] = t;
+          }
+        }
+      }
+      group_sync<G>();
+    }
+  // 3. heads of equal-dof runs -> one matrix entry each, summed in emission order
+  unsigned written = 0;
+  const uint64_t dst = rowstart[m];
+  for (unsigned base = 0; base < E; base += G) {
+    const unsigned i = base + tid;
+    bool head = false;
+    uint32_t dof = 0;
+    if (i < E) {
+      dof = (uint32_t)(s_key[i] >> 32);
+      head = i == 0 || (uint32_t)(s_key[i - 1] >> 32) != dof;
+    }
+    unsigned total;
+    const unsigned rank = written + group_scan<G>(head ? 1u : 0u, total, s_tmp);
+    if (head) {
+      double s = s_val[i];
+      for (unsigned j = i + 1; j < E && (uint32_t)(s_key[j] >> 32) == dof; ++j) s += s_val[j];
+      out_col[dst + rank] = dof;
+      out_val[dst + rank] = s;
+    }
+    written += total;
+  }
+  if (tid == 0) rowlen[m] = written;
+}
+
+template <int NL>
+__global__ void __launch_bounds__(256) merge_rows_warp(uint64_t n_im, const uint32_t *__restrict__ cap, const uint64_t *cand_ptr,
+                                                       const uint32_t *cand_bg, const uint8_t *acc, const double *local,
+                                                       const uint32_t *bg_dofs, const int32_t *line_of, const uint64_t *c_ptr,
+                                                       const uint32_t *c_master, const double *c_weight, const uint64_t *rowstart,
+                                                       uint32_t *rowlen, uint32_t *out_col, double *out_val)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  const unsigned w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned long long *s_key = reinterpret_cast<unsigned long long *>(smem) + (size_t)w * WARP_CAP;
+  double *s_val = reinterpret_cast<double *>(smem + (size_t)(blockDim.x >> 5) * WARP_CAP * 8) + (size_t)w * WARP_CAP;
+  const uint64_t m = (uint64_t)blockIdx.x * (blockDim.x >> 5) + w;
+  if (m >= n_im) return;
+  if (cap[m] > WARP_CAP) return;  // handled by merge_rows_block
+  merge_cell<NL, 32, WARP_CAP>(m, lane, s_key, s_val, nullptr, cand_ptr, cand_bg, acc, local, bg_dofs, line_of, c_ptr, c_master,
+                               c_weight, rowstart, rowlen, out_col, out_val);
+}
+
+template <int NL>
+__global__ void __launch_bounds__(256) merge_rows_block(unsigned n_big, const uint32_t *__restrict__ big, const uint64_t *cand_ptr,
+                                                        const uint32_t *cand_bg, const uint8_t *acc, const double *local,
+                                                        const uint32_t *bg_dofs, const int32_t *line_of, const uint64_t *c_ptr,
+                                                        const uint32_t *c_master, const double *c_weight, const uint64_t *rowstart,
+                                                        uint32_t *rowlen, uint32_t *out_col, double *out_val)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ unsigned s_tmp[8];
+  unsigned long long *s_key = reinterpret_cast<unsigned long long *>(smem);
+  double *s_val = reinterpret_cast<double *>(smem + (size_t)BLOCK_CAP * 8);
+  if (blockIdx.x >= n_big) return;
+  merge_cell<NL, 256, BLOCK_CAP>(big[blockIdx.x], threadIdx.x, s_key, s_val, s_tmp, cand_ptr, cand_bg, acc, local, bg_dofs, line_of, c_ptr,
+                                 c_master, c_weight, rowstart, rowlen, out_col, out_val);
+}
+
+// ---------------------------------------------------------------------------------------
+// transpose C (rows = immersed cells) -> stored orientation (rows = space dofs)
+// ---------------------------------------------------------------------------------------
+template <int LANES>
+__global__ void t_count(uint64_t n_im, const uint64_t *__restrict__ rowstart, const uint32_t *__restrict__ rowlen,
+                        const uint32_t *__restrict__ col, uint32_t *__restrict__ cnt)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t m = t / LANES;
+  const unsigned l = t % LANES;
+  if (m >= n_im) return;
+  const uint64_t s = rowstart[m];
+  const uint32_t n = rowlen[m];
+  for (uint32_t k = l; k < n; k += LANES) atomicAdd(&cnt[col[s + k]], 1u);
+}
+
+template <int LANES>
+__global__ void t_scatter(uint64_t n_im, const uint64_t *__restrict__ rowstart, const uint32_t *__restrict__ rowlen,
+                          const uint32_t *__restrict__ col, const double *__restrict__ val, const uint32_t *__restrict__ im_dofs,
+                          const uint64_t *__restrict__ a_rowptr, uint32_t *__restrict__ cursor, uint32_t *__restrict__ a_col,
+                          double *__restrict__ a_val)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t m = t / LANES;
+  const unsigned l = t % LANES;
+  if (m >= n_im) return;
+  const uint64_t s = rowstart[m];
+  const uint32_t n = rowlen[m];
+  const uint32_t c = im_dofs[m];
+  for (uint32_t k = l; k < n; k += LANES) {
+    const uint32_t r = col[s + k];
+    const uint64_t pos = a_rowptr[r] + atomicAdd(&cursor[r], 1u);
+    a_col[pos] = c;
+    a_val[pos] = val[s + k];
+  }
+}
+
+// columns ascending in every row (rows are short: a space dof meets a handful of immersed cells)
+__global__ void t_sort_rows(uint64_t n_rows, const uint64_t *__restrict__ rowptr, uint32_t *__restrict__ col, double *__restrict__ val)
+{
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const uint64_t s = rowptr[r], e = rowptr[r + 1];
+  for (uint64_t i = s + 1; i < e; ++i) {
+    const uint32_t c = col[i];
+    const double v = val[i];
+    uint64_t j = i;
+    while (j > s && col[j - 1] > c) { col[j] = col[j - 1]; val[j] = val[j - 1]; --j; }
+    col[j] = c; val[j] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// SpMV: LANES threads per row, FP64, shuffle reduction
+// ---------------------------------------------------------------------------------------
+template <int LANES>
+__global__ void __launch_bounds__(256) spmv_csr(uint64_t n_rows, const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col,
+                                                const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t r = t / LANES;
+  const unsigned l = threadIdx.x % LANES;
+  double s = 0.0;
+  if (r < n_rows) {
+    const uint64_t b = rowptr[r], e = rowptr[r + 1];
+    for (uint64_t k = b + l; k < e; k += LANES) s += val[k] * __ldg(x + col[k]);
+  }
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, LANES);
+  if (r < n_rows && l == 0) y[r] = s;
+}
+
+// rows of C: (start, len) storage, result scattered to the immersed dof of the cell
+template <int LANES>
+__global__ void __launch_bounds__(256) spmv_crows(uint64_t n_im, const uint64_t *__restrict__ rowstart, const uint32_t *__restrict__ rowlen,
+                                                  const uint32_t *__restrict__ col, const double *__restrict__ val,
+                                                  const uint32_t *__restrict__ im_dofs, const double *__restrict__ x, double *__restrict__ y)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t r = t / LANES;
+  const unsigned l = threadIdx.x % LANES;
+  double s = 0.0;
+  if (r < n_im) {
+    const uint64_t b = rowstart[r];
+    const uint32_t n = rowlen[r];
+    for (uint32_t k = l; k < n; k += LANES) s += val[b + k] * __ldg(x + col[b + k]);
+  }
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, LANES);
+  if (r < n_im && l == 0) y[im_dofs[r]] = s;
+}
+
+__global__ void __attribute__((unused)) rowlen_to_u64(uint64_t n, const uint32_t *__restrict__ len, uint64_t *__restrict__ out)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = len[i];
+  if (i == n) out[i] = 0;
+}
+
+// compact copy of C's rows (for nm_get_csr(transpose = 1)): row index = immersed dof
+template <int LANES>
+__global__ void c_compact(uint64_t n_im, const uint64_t *__restrict__ rowstart, const uint32_t *__restrict__ rowlen,
+                          const uint32_t *__restrict__ col, const double *__restrict__ val, const uint32_t *__restrict__ im_dofs,
+                          const uint64_t *__restrict__ out_ptr, uint32_t *__restrict__ out_col, double *__restrict__ out_val)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t m = t / LANES;
+  const unsigned l = t % LANES;
+  if (m >= n_im) return;
+  const uint64_t s = rowstart[m], d = out_ptr[im_dofs[m]];
+  const uint32_t n = rowlen[m];
+  for (uint32_t k = l; k < n; k += LANES) { out_col[d + k] = col[s + k]; if (out_val) out_val[d + k] = val[s + k]; }
+}
+
+__global__ void scatter_len_by_dof(uint64_t n_im, const uint32_t *__restrict__ rowlen, const uint32_t *__restrict__ im_dofs, uint32_t *__restrict__ out)
+{
+  const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < n_im) out[im_dofs[m]] = rowlen[m];
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+template <int NL>
+static int matrix_build_t(nm_ctx *ctx)
+{
+  const uint64_t n_im = ctx->n_im, n_rows = ctx->n_space_dofs;
+  ctx->matrix_valid = false;
+  ctx->nnz = 0;
+  PhaseTimer tm(ctx, NM_T_MERGE);
+  NM_TRY(nm_ensure(ctx, ctx->scratch_a, (n_im + 1) * sizeof(uint32_t)));
+  NM_TRY(nm_ensure(ctx, ctx->c_rowstart, (n_im + 2) * sizeof(uint64_t)));
+  NM_TRY(nm_ensure(ctx, ctx->c_rowlen, (n_im + 1) * sizeof(uint32_t)));
+  NM_TRY(nm_ensure(ctx, ctx->counters, 64 * sizeof(uint64_t)));
+  unsigned *hdr = ctx->counters.as<unsigned>() + 32;  // [0] max cap, [1] n_big, [2] cursor
+  NM_CUDA(cudaMemsetAsync(hdr, 0, 16, ctx->stream));
+  NM_CUDA(cudaMemsetAsync(ctx->scratch_a.as<uint32_t>() + n_im, 0, 4, ctx->stream));
+  if (n_im) {
+    row_capacity_kernel<NL><<<nm_blocks(n_im, 128), 128, 0, ctx->stream>>>(
+        n_im, ctx->cand_ptr.as<uint64_t>(), ctx->cand_bg.as<uint32_t>(), ctx->cand_acc.as<uint8_t>(), ctx->bg_dofs.as<uint32_t>(),
+        ctx->line_of.as<int32_t>(), ctx->c_ptr.as<uint64_t>(), ctx->scratch_a.as<uint32_t>(), hdr, hdr + 1);
+    NM_CUDA(cudaGetLastError());
+  }
+  NM_TRY(nm_exclusive_scan_u32_to_u64(ctx, ctx->scratch_a.as<uint32_t>(), ctx->c_rowstart.as<uint64_t>(), n_im + 1));
+  uint64_t total_cap = 0;
+  unsigned h_hdr[2];
+  NM_CUDA(cudaMemcpyAsync(&total_cap, ctx->c_rowstart.as<uint64_t>() + n_im, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  NM_CUDA(cudaMemcpyAsync(h_hdr, hdr, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (h_hdr[0] > (unsigned)BLOCK_CAP)
+    return nm_fail(ctx, NM_ERR_UNSUPPORTED,
+                   "an immersed cell couples to %u (dof, value) contributions; at most %d per immersed cell are implemented "
+                   "(immersed cells far larger than background cells)", h_hdr[0], BLOCK_CAP);
+  NM_TRY(nm_ensure(ctx, ctx->c_col, (total_cap + 1) * sizeof(uint32_t)));
+  NM_TRY(nm_ensure(ctx, ctx->c_val, (total_cap + 1) * sizeof(double)));
+  if (n_im) {
+    const int warps = 8;
+    const size_t smem = (size_t)warps * WARP_CAP * 16;
+    NM_CUDA(cudaFuncSetAttribute(merge_rows_warp<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    merge_rows_warp<NL><<<nm_blocks(n_im, warps), warps * 32, smem, ctx->stream>>>(
+        n_im, ctx->scratch_a.as<uint32_t>(), ctx->cand_ptr.as<uint64_t>(), ctx->cand_bg.as<uint32_t>(), ctx->cand_acc.as<uint8_t>(),
+        ctx->cand_local.as<double>(), ctx->bg_dofs.as<uint32_t>(), ctx->line_of.as<int32_t>(), ctx->c_ptr.as<uint64_t>(),
+        ctx->c_master.as<uint32_t>(), ctx->c_weight.as<double>(), ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(),
+        ctx->c_col.as<uint32_t>(), ctx->c_val.as<double>());
+    NM_CUDA(cudaGetLastError());
+    if (h_hdr[1]) {
+      NM_TRY(nm_ensure(ctx, ctx->scratch_b, (size_t)h_hdr[1] * 4 + 16));
+      list_big_rows<<<nm_blocks(n_im, 256), 256, 0, ctx->stream>>>(n_im, ctx->scratch_a.as<uint32_t>(), ctx->scratch_b.as<uint32_t>(), hdr + 2);
+      const size_t smem_b = (size_t)BLOCK_CAP * 16;
+      NM_CUDA(cudaFuncSetAttribute(merge_rows_block<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+      merge_rows_block<NL><<<h_hdr[1], 256, smem_b, ctx->stream>>>(
+          h_hdr[1], ctx->scratch_b.as<uint32_t>(), ctx->cand_ptr.as<uint64_t>(), ctx->cand_bg.as<uint32_t>(), ctx->cand_acc.as<uint8_t>(),
+          ctx->cand_local.as<double>(), ctx->bg_dofs.as<uint32_t>(), ctx->line_of.as<int32_t>(), ctx->c_ptr.as<uint64_t>(),
+          ctx->c_master.as<uint32_t>(), ctx->c_weight.as<double>(), ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(),
+          ctx->c_col.as<uint32_t>(), ctx->c_val.as<double>());
+      NM_CUDA(cudaGetLastError());
+    }
+  }
+  tm.stop();
+
+  // ---- transpose ----
+  PhaseTimer tt(ctx, NM_T_TRANSPOSE);
+  NM_TRY(nm_ensure(ctx, ctx->a_cursor, (n_rows + 2) * sizeof(uint32_t) * 2));
+  NM_TRY(nm_ensure(ctx, ctx->a_rowptr, (n_rows + 2) * sizeof(uint64_t)));
+  uint32_t *cnt = ctx->a_cursor.as<uint32_t>(), *cursor = cnt + (n_rows + 2);
+  NM_CUDA(cudaMemsetAsync(cnt, 0, (n_rows + 2) * sizeof(uint32_t) * 2, ctx->stream));
+  constexpr int TL = NL == 8 ? 8 : 4;
+  if (n_im) {
+    t_count<TL><<<nm_blocks(n_im * TL, 256), 256, 0, ctx->stream>>>(n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(),
+                                                                   ctx->c_col.as<uint32_t>(), cnt);
+    NM_CUDA(cudaGetLastError());
+  }
+  NM_TRY(nm_exclusive_scan_u32_to_u64(ctx, cnt, ctx->a_rowptr.as<uint64_t>(), n_rows + 1));
+  uint64_t nnz = 0;
+  NM_CUDA(cudaMemcpyAsync(&nnz, ctx->a_rowptr.as<uint64_t>() + n_rows, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->nnz = nnz;
+  NM_TRY(nm_ensure(ctx, ctx->a_col, (nnz + 1) * sizeof(uint32_t)));
+  NM_TRY(nm_ensure(ctx, ctx->a_val, (nnz + 1) * sizeof(double)));
+  if (n_im) {
+    t_scatter<TL><<<nm_blocks(n_im * TL, 256), 256, 0, ctx->stream>>>(
+        n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(), ctx->c_val.as<double>(),
+        ctx->im_dofs.as<uint32_t>(), ctx->a_rowptr.as<uint64_t>(), cursor, ctx->a_col.as<uint32_t>(), ctx->a_val.as<double>());
+    NM_CUDA(cudaGetLastError());
+  }
+  if (n_rows) {
+    t_sort_rows<<<nm_blocks(n_rows, 256), 256, 0, ctx->stream>>>(n_rows, ctx->a_rowptr.as<uint64_t>(), ctx->a_col.as<uint32_t>(), ctx->a_val.as<double>());
+    NM_CUDA(cudaGetLastError());
+  }
+  tt.stop();
+  ctx->matrix_valid = true;
+  return NM_OK;
+}
+
+int nm_matrix_build(nm_ctx *ctx) { return ctx->spacedim == 3 ? matrix_build_t<8>(ctx) : matrix_build_t<4>(ctx); }
+
+int nm_spmv_run(nm_ctx *ctx, int transpose, const double *x, double *y)
+{
+  const uint64_t n_rows = ctx->n_space_dofs, n_im = ctx->n_im;
+  PhaseTimer tm(ctx, transpose ? NM_T_SPMV_T : NM_T_SPMV);
+  if (!transpose) {
+    const double avg = n_rows ? (double)ctx->nnz / (double)n_rows : 0;
+    if (n_rows) {
+      if (avg > 12) spmv_csr<8><<<nm_blocks(n_rows * 8, 256), 256, 0, ctx->stream>>>(n_rows, ctx->a_rowptr.as<uint64_t>(), ctx->a_col.as<uint32_t>(), ctx->a_val.as<double>(), x, y);
+      else if (avg > 5) spmv_csr<4><<<nm_blocks(n_rows * 4, 256), 256, 0, ctx->stream>>>(n_rows, ctx->a_rowptr.as<uint64_t>(), ctx->a_col.as<uint32_t>(), ctx->a_val.as<double>(), x, y);
+      else spmv_csr<2><<<nm_blocks(n_rows * 2, 256), 256, 0, ctx->stream>>>(n_rows, ctx->a_rowptr.as<uint64_t>(), ctx->a_col.as<uint32_t>(), ctx->a_val.as<double>(), x, y);
+    }
+  } else {
+    NM_CUDA(cudaMemsetAsync(y, 0, ctx->n_im_dofs * sizeof(double), ctx->stream));
+    const double avg = n_im ? (double)ctx->nnz / (double)n_im : 0;
+    if (n_im) {
+      if (avg > 24) spmv_crows<16><<<nm_blocks(n_im * 16, 256), 256, 0, ctx->stream>>>(n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(), ctx->c_val.as<double>(), ctx->im_dofs.as<uint32_t>(), x, y);
+      else if (avg > 10) spmv_crows<8><<<nm_blocks(n_im * 8, 256), 256, 0, ctx->stream>>>(n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(), ctx->c_val.as<double>(), ctx->im_dofs.as<uint32_t>(), x, y);
+      else spmv_crows<4><<<nm_blocks(n_im * 4, 256), 256, 0, ctx->stream>>>(n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(), ctx->c_val.as<double>(), ctx->im_dofs.as<uint32_t>(), x, y);
+    }
+  }
+  NM_CUDA(cudaGetLastError());
+  tm.stop();
+  return NM_OK;
+}
+
+// compact CSR with rows = immersed dofs (device buffers owned by the caller of this helper)
+int nm_c_rows_compact(nm_ctx *ctx, uint64_t *rowptr_dev, uint32_t *col_dev, double *val_dev)
+{
+  const uint64_t n_im = ctx->n_im, n_cols = ctx->n_im_dofs;
+  NM_TRY(nm_ensure(ctx, ctx->scratch_a, (n_cols + 2) * sizeof(uint32_t)));
+  NM_CUDA(cudaMemsetAsync(ctx->scratch_a.p, 0, (n_cols + 2) * sizeof(uint32_t), ctx->stream));
+  if (n_im) scatter_len_by_dof<<<nm_blocks(n_im, 256), 256, 0, ctx->stream>>>(n_im, ctx->c_rowlen.as<uint32_t>(), ctx->im_dofs.as<uint32_t>(), ctx->scratch_a.as<uint32_t>());
+  NM_TRY(nm_exclusive_scan_u32_to_u64(ctx, ctx->scratch_a.as<uint32_t>(), rowptr_dev, n_cols + 1));
+  if (n_im && col_dev)
+    c_compact<8><<<nm_blocks(n_im * 8, 256), 256, 0, ctx->stream>>>(n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(),
+                                                                 ctx->c_val.as<double>(), ctx->im_dofs.as<uint32_t>(), rowptr_dev, col_dev, val_dev);
+  NM_CUDA(cudaGetLastError());
+  return NM_OK;
+}
