@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: coupling-matrix assembly by exact intersections + C / C^T SpMV.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+One "step" = one full pass over the workload: hand both grids to the library, candidate pairs,
+clipping + quadrature + local coupling vectors, merge through the constraint lines into CSR
+(both orientations), one Ct.vmult and one C.Tvmult (+ all-reduce of the partial Ct.vmult result
+when the immersed grid is sharded over several GPUs).
+
+`value`  : accepted intersection pairs per second, whole job, inputs already resident in HBM.
+`e2e`    : the same through the public API with HOST (pinned) buffers, host->device copies of
+           both grids and device->host read-back of the CSR matrix and both product vectors
+           inside the timed region.
+Workload : refined 2D-in-3D sphere (data/lm_2d3d.smooth_sphere.prm geometry, BASELINE.json
+           configs[3]); synthetic band-only background, deterministic geometry, no RNG in the mesh.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "coupling-matrix intersection pairs/s (+ C SpMV GB/s in `spmv`)"
+UNIT = "pairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", default="sphere", choices=["sphere", "disk", "flower"])
+    ap.add_argument("--cycle", type=int, default=None, help="refinement cycle of the workload (default: 8 for sphere)")
+    ap.add_argument("--ref-cycle", type=int, default=None, help="refinement cycle of the CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+DEFAULT_CYCLE = {"sphere": 8, "disk": 14, "flower": 14}
+
+
+# --------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the CPU restatement (oracle/nm_oracle.c) on the box's host cores
+# --------------------------------------------------------------------------------------------
+def cpu_sample(config, cycle, steps, warmup):
+    import torch
+    from non_matching_test_suite_b200.grids import make_config
+    from oracle import c_oracle as co
+    co.build()
+    cores = co.lib().nmo_num_threads()
+    bg, im = make_config(config, cycle, band_only=True)
+    times, acc = [], 0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        r = co.assemble(bg, im, n1d=3, tol=1e-15)
+        x = torch.ones(im.n_dofs, dtype=torch.float64).numpy()
+        co.spmv(0, r["rowptr"], r["col"], r["val"], x, bg.n_dofs, im.n_dofs)
+        u = torch.ones(bg.n_dofs, dtype=torch.float64).numpy()
+        co.spmv(1, r["rowptr"], r["col"], r["val"], u, bg.n_dofs, im.n_dofs)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+        acc = int(r["accepted"].shape[0])
+    ms = 1e3 * sum(times) / len(times)
+    sample = "%s cycle %d: %d background cells (band only), %d immersed cells, %d accepted pairs per step" % (
+        config, cycle, bg.n_cells, im.n_cells, acc)
+    return dict(value=acc / (ms * 1e-3), unit=UNIT, cores=cores, kind="port", sample=sample), ms, acc
+
+
+def pick_ref_cycle(args):
+    if args.ref_cycle is not None:
+        return args.ref_cycle
+    n = os.cpu_count() or 8
+    if args.config == "sphere":
+        return 6 if n >= 24 else 5
+    return 10
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cyc = pick_ref_cycle(args)
+    base, ms, acc = cpu_sample(args.config, cyc, max(1, args.steps), max(0, min(args.warmup, 1)))
+    workload_cycle = args.cycle if args.cycle is not None else DEFAULT_CYCLE[args.config]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(args.config, workload_cycle, args.gpus, None),
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU restatement of the reference algorithm (oracle/nm_oracle.c, FP64, OpenMP over all host threads); the real "
+                "deal.II/CGAL reference cannot be built in this image (SURVEY.md 8(c)). Each step is a bounded sample of the workload.",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(config, cycle, n_gpus, extra):
+    names = {"sphere": "lm_2d3d.smooth_sphere.prm geometry (2D sphere in 3D cube, quad-vs-hex clipping)",
+             "disk": "lm_1d2d_disk.smooth.prm geometry", "flower": "lm_1d2d_flower.smooth.prm geometry"}
+    c = {"workload": "%s, synthetic refinement cycle %d, band-only background with hanging-node constraints" % (names[config], cycle),
+         "sharding": "immersed-cell ranges, %d shard(s)" % n_gpus, "degree": 3, "tol": 1e-15,
+         "l2_policy": "inputs and intermediates are larger than L2 (no flush needed)"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# --------------------------------------------------------------------------------------------
+# native arm
+# --------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    from non_matching_test_suite_b200 import _lib, coupling
+    from non_matching_test_suite_b200.grids import make_config, shard_problem
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cycle = args.cycle if args.cycle is not None else DEFAULT_CYCLE[args.config]
+
+    # ---- workload: generated on the GPU, this rank's shard kept -----------------------------------
+    t0 = time.time()
+    bg, im, info = shard_problem(args.config, cycle, rank, world, device=dev)
+    torch.cuda.synchronize()
+    t_gen = time.time() - t0
+    d = bg.spacedim
+    u32 = lambda t: t.to(torch.int32).contiguous()
+    dev_in = dict(verts=bg.vertices().contiguous(), dofs=u32(bg.dofs), c_dof=u32(bg.c_dof), c_ptr=bg.c_ptr.contiguous(),
+                  c_master=u32(bg.c_master), c_weight=bg.c_weight.contiguous(), im_verts=im.verts.contiguous(), im_dofs=u32(im.dofs))
+    x_dev = (torch.rand(im.n_dofs, dtype=torch.float64, device=dev, generator=torch.Generator(device=dev).manual_seed(0)) * 2 - 1)
+    u_dev = (torch.rand(bg.n_dofs, dtype=torch.float64, device=dev, generator=torch.Generator(device=dev).manual_seed(1)) * 2 - 1)
+    y_dev = torch.empty(bg.n_dofs, dtype=torch.float64, device=dev)
+    z_dev = torch.empty(im.n_dofs, dtype=torch.float64, device=dev)
+
+    ctx = _lib.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+
+    def step(inp, x, u, y, z, host):
+        ctx.set_background(d, verts=inp["verts"], dofs=inp["dofs"], n_dofs=bg.n_dofs, c_dof=inp["c_dof"], c_ptr=inp["c_ptr"],
+                           c_master=inp["c_master"], c_weight=inp["c_weight"])
+        ctx.set_immersed(im.dim, im.spacedim, inp["im_verts"], inp["im_dofs"], im.n_dofs)
+        counts = ctx.intersect(3, 1e-15)
+        ctx.build_sparsity()
+        ctx.assemble()
+        ctx.spmv(x, transpose=False, out=y)      # Ct.vmult : partial background vector
+        ctx.spmv(u, transpose=True, out=z)       # C.Tvmult : this shard's immersed entries
+        if world > 1:
+            yy = y if not host else y_dev.copy_(y, non_blocking=True)
+            dist.all_reduce(yy)                  # the only collective of the path
+            if host:
+                y.copy_(yy)
+        out = None
+        if host:
+            out = ctx.csr(transpose=False, values=True)   # D2H of the assembled matrix
+        return counts, out
+
+    def timed(inp, x, u, y, z, host, steps, warmup):
+        for _ in range(warmup):
+            counts, out = step(inp, x, u, y, z, host)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        phases = {}
+        l0 = ctx.launch_count()
+        e0.record(stream)
+        for _ in range(steps):
+            counts, out = step(inp, x, u, y, z, host)
+            for k, v in ctx.timings().items():
+                phases[k] = phases.get(k, 0.0) + v / steps
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        launches = (ctx.launch_count() - l0) // steps
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), counts, phases, launches, out
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, counts, phases, launches, _ = timed(dev_in, x_dev, u_dev, y_dev, z_dev, False, args.steps, args.warmup)
+    clocks = sampler.stop()
+
+    n_acc, n_cand = counts["n_accepted"], counts["n_candidates"]
+    nnz = ctx.nnz
+    tot = torch.tensor([n_acc, n_cand, nnz], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot)
+    tot_acc, tot_cand, tot_nnz = (int(v) for v in tot.tolist())
+    value = tot_acc / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (this rank; CUDA events on the library's stream) ---------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    per_cand = 296 if d == 3 else 104      # pair ids 8 B + background cell 2^d*d*8 B + immersed cell 2^(d-1)*d*8 B
+    per_acc_vals = 64 if d == 3 else 32    # 2^d local values written per accepted pair
+    kernels = {
+        "clip_local_kernel": (phases["k_clip"], n_cand * per_cand + n_acc * per_acc_vals),
+        "cand_count+cand_fill": (phases["k_cand_count"] + phases["k_cand_fill"], 0),
+        "merge_rows_warp": (phases["k_merge"], n_acc * ((36 if d == 3 else 20) + per_acc_vals)),
+    }
+    dom = max(kernels, key=lambda k: kernels[k][0])
+    dom_ms, dom_bytes = kernels["clip_local_kernel"]
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    roofline = {"kernel": "clip_local_kernel<%d>" % d, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
+                "kernel_ms": dom_ms, "largest_kernel_by_time": dom,
+                "kernel_ms_all": {k: v[0] for k, v in kernels.items()}}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            tj = json.load(open(traffic_file))
+            roofline["traffic"] = tj.get("clip_local_kernel_bytes_per_candidate", 0) * n_cand or None
+            roofline["traffic_source"] = tj.get("source")
+        except Exception:
+            pass
+    a_bytes = 12 * nnz + 16 * bg.n_dofs + 8 * im.n_dofs
+    c_bytes = 12 * nnz + 16 * im.n_cells + 8 * bg.n_dofs
+    spmv = {"Ct_vmult_GBs": a_bytes / (phases["spmv"] * 1e-3) / 1e9, "C_Tvmult_GBs": c_bytes / (phases["spmv_t"] * 1e-3) / 1e9,
+            "Ct_vmult_frac_hbm": a_bytes / (phases["spmv"] * 1e-3) / 1e9 / peak, "C_Tvmult_frac_hbm": c_bytes / (phases["spmv_t"] * 1e-3) / 1e9 / peak,
+            "nnz": nnz, "bytes_formula": "12*nnz + 16*n_rows + 8*n_cols", "note": "per rank, excludes the all-reduce"}
+
+    # ---- end to end: host buffers in, matrix + vectors out ----------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host_in = {k: v.cpu().pin_memory() for k, v in dev_in.items()}
+        xh, uh = x_dev.cpu().pin_memory(), u_dev.cpu().pin_memory()
+        yh = torch.empty(bg.n_dofs, dtype=torch.float64).pin_memory()
+        zh = torch.empty(im.n_dofs, dtype=torch.float64).pin_memory()
+        e_steps = max(1, min(args.steps, 3))
+        ms_e, counts_e, _, _, out = timed(host_in, xh, uh, yh, zh, True, e_steps, 1)
+        h2d = sum(v.numel() * v.element_size() for v in host_in.values()) + xh.numel() * 8 + uh.numel() * 8
+        d2h = sum(t.numel() * t.element_size() for t in out) + yh.numel() * 8 + zh.numel() * 8
+        e2e = {"value": tot_acc / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": ms_e, "steps": e_steps,
+               "api": "coupling/_lib.Context: set_background(host verts)+set_immersed+intersect+build_sparsity+assemble+spmv x2+csr() read-back"}
+        del host_in
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base, _, _ = cpu_sample(args.config, pick_ref_cycle(args), 1, 0)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.config, cycle, world, info),
+            "pairs": tot_acc, "candidates": tot_cand, "nnz": tot_nnz, "nnz_per_s": tot_nnz / (ms * 1e-3),
+            "pairs_per_min": value * 60.0,
+            "counts_rank0": counts, "phases_ms_rank0": phases, "roofline": roofline, "spmv": spmv,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "cpu_baseline": cpu_base,
+            "device_bytes_rank0": ctx.device_bytes(), "gen_seconds": t_gen,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

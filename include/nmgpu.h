@@ -69,6 +69,11 @@ enum {
   NM_T_SPMV = 7,       /* last nm_spmv, stored orientation                                 */
   NM_T_SPMV_T = 8,     /* last nm_spmv, transposed                                         */
   NM_T_DOWNLOAD = 9,   /* device->host copies of the last nm_get_*                         */
+  /* single kernels, events directly around the launch */
+  NM_T_K_CLIP = 10,        /* clip_local_kernel                                            */
+  NM_T_K_CAND_COUNT = 11,  /* cand_count                                                   */
+  NM_T_K_CAND_FILL = 12,   /* cand_fill                                                    */
+  NM_T_K_MERGE = 13,       /* merge_rows_warp                                              */
   NM_T_COUNT = 16
 };
 
@@ -152,6 +157,8 @@ int nm_spmv(nm_ctx *ctx, int transpose, const double *x, double *y, int where);
 
 /* Device milliseconds per phase (NM_T_*), `n` entries copied. */
 int nm_get_timings(nm_ctx *ctx, float *ms, int n);
+/* Number of this library's kernel launches since nm_create (cub's internal kernels excluded). */
+int nm_get_launch_count(nm_ctx *ctx, uint64_t *n);
 /* Bytes of device memory currently held by the context. */
 int nm_device_bytes(nm_ctx *ctx, uint64_t *bytes);
 /* The CUDA stream (cudaStream_t) the context launches on, for callers that time with events. */

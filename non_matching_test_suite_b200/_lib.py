@@ -18,13 +18,14 @@ LIB_PATH = os.path.join(_HERE, "libnmgpu.so")
 
 NM_HOST, NM_DEVICE = 0, 1
 STATUS = {0: "NM_OK", 1: "NM_ERR_INVALID", 2: "NM_ERR_CUDA", 3: "NM_ERR_UNSUPPORTED", 4: "NM_ERR_STATE", 5: "NM_ERR_NOMEM"}
-PHASES = ["upload", "index", "candidates", "split", "clip", "merge", "transpose", "spmv", "spmv_t", "download"]
+PHASES = ["upload", "index", "candidates", "split", "clip", "merge", "transpose", "spmv", "spmv_t", "download",
+          "k_clip", "k_cand_count", "k_cand_fill", "k_merge"]
 
 # every symbol include/nmgpu.h declares
 SYMBOLS = ["nm_version", "nm_create", "nm_destroy", "nm_last_error", "nm_set_background", "nm_set_background_boxes",
            "nm_set_immersed", "nm_intersect", "nm_get_candidates", "nm_get_pairs", "nm_get_quadrature",
            "nm_get_split_codes", "nm_build_sparsity", "nm_assemble", "nm_assemble_from_quadrature", "nm_get_csr",
-           "nm_spmv", "nm_get_timings", "nm_device_bytes", "nm_get_stream"]
+           "nm_spmv", "nm_get_timings", "nm_get_launch_count", "nm_device_bytes", "nm_get_stream"]
 
 
 class NmError(RuntimeError):
@@ -72,6 +73,7 @@ def load():
     L.nm_spmv.argtypes = [P, I, P, P, I]
     L.nm_get_timings.argtypes = [P, P, I]
     L.nm_device_bytes.argtypes = [P, C.POINTER(U64)]
+    L.nm_get_launch_count.argtypes = [P, C.POINTER(U64)]
     L.nm_get_stream.argtypes = [P, C.POINTER(P)]
     _lib = L
     return L
@@ -222,6 +224,11 @@ class Context:
         buf = (C.c_float * 16)()
         self._chk(self.L.nm_get_timings(self.h, buf, 16))
         return {name: float(buf[i]) for i, name in enumerate(PHASES)}
+
+    def launch_count(self) -> int:
+        n = C.c_uint64(0)
+        self._chk(self.L.nm_get_launch_count(self.h, C.byref(n)))
+        return int(n.value)
 
     def device_bytes(self) -> int:
         b = C.c_uint64(0)

@@ -1,6 +1,7 @@
 // C ABI of libnmgpu.so (declared in include/nmgpu.h).  Marshalling, state checks and phase
 // orchestration only; the kernels live in nm_index.cu, nm_clip.cu and nm_matrix.cu.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <new>
 
@@ -103,11 +104,13 @@ int nm_create(nm_ctx **out, int device)
   memset(ctx->t_ms, 0, sizeof(ctx->t_ms));
   memset(&ctx->counts, 0, sizeof(ctx->counts));
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev2) != cudaSuccess || cudaEventCreate(&ctx->ev3) != cudaSuccess) {
     cudaGetLastError();
     delete ctx;
     return NM_ERR_CUDA;
   }
+  { const char *e = getenv("NMGPU_FORCE_QUADRATURE"); ctx->force_quadrature_kernel = e && e[0] == '1'; }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   if (nm_ensure(ctx, ctx->counters, 64 * sizeof(uint64_t)) != NM_OK) { delete ctx; return NM_ERR_NOMEM; }
@@ -123,6 +126,8 @@ int nm_destroy(nm_ctx *ctx)
   free_all(ctx);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+  if (ctx->ev3) cudaEventDestroy(ctx->ev3);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return NM_OK;
@@ -306,17 +311,17 @@ int nm_get_pairs(nm_ctx *ctx, uint32_t *immersed, uint32_t *background, double *
   const unsigned B = nm_blocks(na, 256);
   if (na && immersed) {
     uint32_t *dst = where == NM_DEVICE ? immersed : ctx->stage_y.as<uint32_t>();
-    gather_by_idx<uint32_t><<<B, 256, 0, ctx->stream>>>(na, idx, ctx->cand_im.as<uint32_t>(), dst);
+    gather_by_idx<uint32_t><<<B, 256, 0, NM_LS(ctx)>>>(na, idx, ctx->cand_im.as<uint32_t>(), dst);
     if (where == NM_HOST) { NM_TRY(nm_download(ctx, immersed, dst, na * 4, NM_HOST)); NM_CUDA(cudaStreamSynchronize(ctx->stream)); }
   }
   if (na && background) {
     uint32_t *dst = where == NM_DEVICE ? background : ctx->stage_y.as<uint32_t>();
-    gather_by_idx<uint32_t><<<B, 256, 0, ctx->stream>>>(na, idx, ctx->cand_bg.as<uint32_t>(), dst);
+    gather_by_idx<uint32_t><<<B, 256, 0, NM_LS(ctx)>>>(na, idx, ctx->cand_bg.as<uint32_t>(), dst);
     if (where == NM_HOST) { NM_TRY(nm_download(ctx, background, dst, na * 4, NM_HOST)); NM_CUDA(cudaStreamSynchronize(ctx->stream)); }
   }
   if (na && sum_w) {
     double *dst = where == NM_DEVICE ? sum_w : ctx->stage_y.as<double>();
-    gather_by_idx<double><<<B, 256, 0, ctx->stream>>>(na, idx, ctx->cand_sumw.as<double>(), dst);
+    gather_by_idx<double><<<B, 256, 0, NM_LS(ctx)>>>(na, idx, ctx->cand_sumw.as<double>(), dst);
     if (where == NM_HOST) { NM_TRY(nm_download(ctx, sum_w, dst, na * 8, NM_HOST)); }
   }
   NM_CUDA(cudaGetLastError());
@@ -464,6 +469,13 @@ int nm_get_timings(nm_ctx *ctx, float *ms, int n)
 {
   if (!ctx || !ms) return NM_ERR_INVALID;
   for (int i = 0; i < n && i < NM_T_COUNT; ++i) ms[i] = ctx->t_ms[i];
+  return NM_OK;
+}
+
+int nm_get_launch_count(nm_ctx *ctx, uint64_t *n)
+{
+  if (!ctx || !n) return NM_ERR_INVALID;
+  *n = ctx->n_launches;
   return NM_OK;
 }
 

@@ -357,6 +357,215 @@ __global__ void __launch_bounds__(128) clip_local_kernel(uint64_t n_cand, const 
 }
 
 // ---------------------------------------------------------------------------------------
+// 3D throughput kernel: warp-level work queue + closed-form moments
+// ---------------------------------------------------------------------------------------
+// One thread per candidate leaves two thirds of the lanes idle (candidates whose triangles miss
+// the cell retire at once, the others clip polygons of different sizes).  Here a warp walks a
+// contiguous range of candidates; stage 1 (all lanes: one candidate each) only loads the pair and
+// rejects triangles by their own bounding box, the surviving (candidate, triangle) items go to a
+// per-warp ring in shared memory, and stage 2 always runs on 32 queued items (one per lane):
+// Sutherland-Hodgman clip, then the integrals of 1, u, v, w, uv, uw, vw, uvw over the clipped
+// polygon in closed form (u,v,w = reference coordinates of the background cell, affine on the
+// triangle):  for a triangle of area A with vertex values f_i, g_i, h_i of affine f, g, h
+//     int f     = A/3  * Sf
+//     int f g   = A/12 * (Sf Sg + S(fg))
+//     int f g h = A/60 * (Sf Sg Sh + Sf S(gh) + Sg S(fh) + Sh S(fg) + 2 S(fgh))
+// which is what the reference's degree-5 rule evaluates exactly for the Q1 x P0 integrand
+// (degree <= 3 on a planar piece; SURVEY.md rule R1).  The items of one candidate sit next to
+// each other in the ring, so they are combined with two shuffles in a fixed order.
+struct ItemOut {
+  double area2;   // sum of J = 2 * area over kept sub-triangles
+  double m[7];    // A-weighted sums for u, v, w, uv, uw, vw, uvw (constants applied at the end)
+  unsigned nfan, dropped;
+};
+
+__device__ inline void item_clip_moments(const double *__restrict__ box, const double *__restrict__ quad, int t, double tol, ItemOut &o)
+{
+  const double lo[3] = {box[0], box[1], box[2]};
+  const double H[3] = {box[4] - lo[0], box[5] - lo[1], box[6] - lo[2]};
+  const int i0 = t == 0 ? 1 : 0, i1 = t <= 1 ? 2 : 1, i2 = t <= 2 ? 3 : 2;
+  Poly A, B;
+  A.n = 3;
+  A.x[0] = quad[i0 * 3 + 0] - lo[0]; A.y[0] = quad[i0 * 3 + 1] - lo[1]; A.z[0] = quad[i0 * 3 + 2] - lo[2];
+  A.x[1] = quad[i1 * 3 + 0] - lo[0]; A.y[1] = quad[i1 * 3 + 1] - lo[1]; A.z[1] = quad[i1 * 3 + 2] - lo[2];
+  A.x[2] = quad[i2 * 3 + 0] - lo[0]; A.y[2] = quad[i2 * 3 + 1] - lo[1]; A.z[2] = quad[i2 * 3 + 2] - lo[2];
+  // unit normal of the parent triangle: J of a coplanar sub-triangle = |cross . n|
+  double nx, ny, nz;
+  {
+    const double e1[3] = {A.x[1] - A.x[0], A.y[1] - A.y[0], A.z[1] - A.z[0]}, e2[3] = {A.x[2] - A.x[0], A.y[2] - A.y[0], A.z[2] - A.z[0]};
+    nx = e1[1] * e2[2] - e1[2] * e2[1]; ny = e1[2] * e2[0] - e1[0] * e2[2]; nz = e1[0] * e2[1] - e1[1] * e2[0];
+    const double n2 = nx * nx + ny * ny + nz * nz;
+    if (!(n2 > 0.0)) return;
+    const double inv = rsqrt(n2);
+    nx *= inv; ny *= inv; nz *= inv;
+  }
+  clip_step<0, 0>(A, B, 0.0);  if (B.n < 3) return;
+  clip_step<0, 1>(B, A, H[0]); if (A.n < 3) return;
+  clip_step<1, 0>(A, B, 0.0);  if (B.n < 3) return;
+  clip_step<1, 1>(B, A, H[1]); if (A.n < 3) return;
+  clip_step<2, 0>(A, B, 0.0);  if (B.n < 3) return;
+  clip_step<2, 1>(B, A, H[2]); if (A.n < 3) return;
+  const double ih[3] = {1.0 / H[0], 1.0 / H[1], 1.0 / H[2]};
+  const double ax = A.x[0], ay = A.y[0], az = A.z[0];
+  const double f0 = ax * ih[0], g0 = ay * ih[1], h0 = az * ih[2];
+  double px = A.x[1], py = A.y[1], pz = A.z[1];
+  double f1 = px * ih[0], g1 = py * ih[1], h1 = pz * ih[2];
+  for (int j = 2; j < A.n; ++j) {
+    const double qx = A.x[j], qy = A.y[j], qz = A.z[j];
+    const double f2 = qx * ih[0], g2 = qy * ih[1], h2 = qz * ih[2];
+    const double e1x = px - ax, e1y = py - ay, e1z = pz - az, e2x = qx - ax, e2y = qy - ay, e2z = qz - az;
+    const double J = fabs((e1y * e2z - e1z * e2y) * nx + (e1z * e2x - e1x * e2z) * ny + (e1x * e2y - e1y * e2x) * nz);
+    if (0.25 * J * J > tol * tol) {                      // squared_area > tol^2     intersections.cc:477,493
+      if (J < 1e-12) {                                   // intersections.cc:710
+        o.dropped++;
+      } else {
+        const double Sf = f0 + f1 + f2, Sg = g0 + g1 + g2, Sh = h0 + h1 + h2;
+        const double fg = f0 * g0 + f1 * g1 + f2 * g2, fh = f0 * h0 + f1 * h1 + f2 * h2, gh = g0 * h0 + g1 * h1 + g2 * h2;
+        const double fgh = f0 * g0 * h0 + f1 * g1 * h1 + f2 * g2 * h2;
+        o.area2 += J;
+        o.m[0] += J * Sf; o.m[1] += J * Sg; o.m[2] += J * Sh;
+        o.m[3] += J * (Sf * Sg + fg); o.m[4] += J * (Sf * Sh + fh); o.m[5] += J * (Sg * Sh + gh);
+        o.m[6] += J * (Sf * Sg * Sh + Sf * gh + Sg * fh + Sh * fg + 2.0 * fgh);
+        o.nfan++;
+      }
+    }
+    px = qx; py = qy; pz = qz; f1 = f2; g1 = g2; h1 = h2;
+  }
+}
+
+constexpr int CM_WARPS = 8;    // warps per block
+constexpr int CM_CHUNKS = 8;   // chunks of 32 candidates per warp
+
+__global__ void __launch_bounds__(CM_WARPS * 32) clip_moments3_kernel(
+    uint64_t n_cand, const uint32_t *__restrict__ cand_im, const uint32_t *__restrict__ cand_bg, const double *__restrict__ bg_box,
+    const double *__restrict__ im_verts, const uint8_t *__restrict__ split, const double *__restrict__ im_measure, double tol,
+    unsigned nq_per_tri, double *__restrict__ sumw_out, double *__restrict__ local_out, uint16_t *__restrict__ nq_out,
+    uint8_t *__restrict__ acc_out, unsigned long long *counters)
+{
+  __shared__ uint32_t s_ring[CM_WARPS][128];
+  const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t *ring = s_ring[w];
+  const uint64_t wstart = ((uint64_t)blockIdx.x * CM_WARPS + w) * (32 * CM_CHUNKS);
+  const uint64_t wend = wstart + 32 * CM_CHUNKS < n_cand ? wstart + 32 * CM_CHUNKS : n_cand;
+  unsigned head = 0, count = 0;  // ring state, warp-uniform
+  unsigned c_acc = 0, c_nq = 0, c_drop = 0, c_marg = 0;
+  for (uint64_t base = wstart; base < wend || count > 0; base += 32) {
+    // ---- stage 1: one candidate per lane -> items ------------------------------------------------
+    unsigned nitems = 0, items = 0;  // up to three 2-bit triangle ids packed in `items`
+    const uint64_t c = base + lane;
+    if (base < wend && c < wend) {
+      const uint32_t m = cand_im[c], b = cand_bg[c];
+      const double *box = bg_box + (uint64_t)b * 8;
+      const double *quad = im_verts + (uint64_t)m * 12;
+      const int code = split[m];
+      double q[4][3];
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) q[v][k] = quad[v * 3 + k];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if (!((code >> t) & 1)) continue;
+        const int i0 = t == 0 ? 1 : 0, i1 = t <= 1 ? 2 : 1, i2 = t <= 2 ? 3 : 2;
+        bool hit = true;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double mn = fmin(q[i0][k], fmin(q[i1][k], q[i2][k])), mx = fmax(q[i0][k], fmax(q[i1][k], q[i2][k]));
+          hit &= !(mx < box[k] || mn > box[4 + k]);      // same test as on translated coordinates (sign-exact)
+        }
+        if (hit) { items |= (unsigned)t << (2 * nitems); ++nitems; }
+      }
+      if (nitems == 0) { sumw_out[c] = 0.0; acc_out[c] = 0; nq_out[c] = 0; }
+    }
+    // push (warp-aggregated, candidate order preserved)
+    unsigned inc = nitems;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (unsigned)o) inc += v; }
+    const unsigned total = __shfl_sync(0xffffffffu, inc, 31);
+    unsigned pos = head + count + inc - nitems;
+    for (unsigned k = 0; k < nitems; ++k) ring[(pos + k) & 127] = ((uint32_t)(c - wstart) << 2) | ((items >> (2 * k)) & 3);
+    count += total;
+    __syncwarp();
+    const bool last = base + 32 >= wend;
+    // ---- stage 2: 32 queued items at a time ------------------------------------------------------
+    while (count >= 32 || (last && count > 0)) {
+      unsigned take = count < 32 ? count : 32;
+      if (take < count) {  // do not split the items of one candidate between two rounds
+        const uint32_t nxt = ring[(head + take) & 127] >> 2;
+        while (take > 0 && (ring[(head + take - 1) & 127] >> 2) == nxt) --take;
+      }
+      const bool on = lane < take;
+      const uint32_t it = on ? ring[(head + lane) & 127] : 0xffffffffu;
+      const uint32_t cl = it >> 2;
+      ItemOut o;
+      o.area2 = 0; o.nfan = 0; o.dropped = 0;
+#pragma unroll
+      for (int i = 0; i < 7; ++i) o.m[i] = 0;
+      uint32_t m = 0;
+      const uint64_t cc = wstart + cl;
+      if (on) {
+        m = cand_im[cc];
+        item_clip_moments(bg_box + (uint64_t)cand_bg[cc] * 8, im_verts + (uint64_t)m * 12, (int)(it & 3), tol, o);
+      }
+      // combine the (adjacent, at most three) items of a candidate in ring order
+      const uint32_t cl1 = __shfl_down_sync(0xffffffffu, cl, 1), cl2 = __shfl_down_sync(0xffffffffu, cl, 2);
+      const uint32_t clp = __shfl_up_sync(0xffffffffu, cl, 1);
+      const bool same1 = on && lane + 1 < 32 && cl1 == cl, same2 = on && lane + 2 < 32 && cl2 == cl;
+      const bool is_head = on && (lane == 0 || clp != cl);
+      double tot[8];
+      tot[0] = o.area2;
+#pragma unroll
+      for (int i = 0; i < 7; ++i) tot[i + 1] = o.m[i];
+      unsigned nfan = o.nfan;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const double a1 = __shfl_down_sync(0xffffffffu, tot[i], 1), a2 = __shfl_down_sync(0xffffffffu, tot[i], 2);
+        tot[i] = tot[i] + (same1 ? a1 : 0.0) + (same2 ? a2 : 0.0);
+      }
+      {
+        const unsigned n1 = __shfl_down_sync(0xffffffffu, nfan, 1), n2 = __shfl_down_sync(0xffffffffu, nfan, 2);
+        nfan += (same1 ? n1 : 0u) + (same2 ? n2 : 0u);
+      }
+      c_drop += o.dropped;
+      if (is_head) {
+        const double sumw = 0.5 * tot[0];
+        const bool ok = sumw > tol;                        // coupling_utilities.cc:61
+        sumw_out[cc] = sumw;
+        acc_out[cc] = ok ? 1 : 0;
+        const unsigned nq = ok ? nfan * nq_per_tri : 0u;
+        nq_out[cc] = (uint16_t)nq;
+        if (ok) {
+          const double M1 = sumw, Mu = tot[1] * (1.0 / 6.0), Mv = tot[2] * (1.0 / 6.0), Mw = tot[3] * (1.0 / 6.0);
+          const double Muv = tot[4] * (1.0 / 24.0), Muw = tot[5] * (1.0 / 24.0), Mvw = tot[6] * (1.0 / 24.0), Muvw = tot[7] * (1.0 / 120.0);
+          // phi_i = prod_k (bit_k(i) ? u_k : 1 - u_k)
+          const double l7 = Muvw, l3 = Muv - Muvw, l5 = Muw - Muvw, l6 = Mvw - Muvw;
+          const double l1 = Mu - Muv - l5, l2 = Mv - Muv - l6, l4 = Mw - Muw - l6;
+          const double l0 = M1 - (l1 + l2 + l3 + l4 + l5 + l6 + l7);
+          double2 *dst = reinterpret_cast<double2 *>(local_out + cc * 8);
+          dst[0] = make_double2(l0, l1); dst[1] = make_double2(l2, l3); dst[2] = make_double2(l4, l5); dst[3] = make_double2(l6, l7);
+          c_acc++; c_nq += nq;
+        }
+        if (sumw > 0.0 && sumw < 1e-12 * im_measure[m]) c_marg++;
+      }
+      head = (head + take) & 127;
+      count -= take;
+      __syncwarp();
+    }
+    if (base >= wend) break;
+  }
+  c_acc = __reduce_add_sync(0xffffffffu, c_acc);
+  c_nq = __reduce_add_sync(0xffffffffu, c_nq);
+  c_drop = __reduce_add_sync(0xffffffffu, c_drop);
+  c_marg = __reduce_add_sync(0xffffffffu, c_marg);
+  if (lane == 0) {
+    if (c_acc) atomicAdd(&counters[0], (unsigned long long)c_acc);
+    if (c_nq) atomicAdd(&counters[1], (unsigned long long)c_nq);
+    if (c_drop) atomicAdd(&counters[2], (unsigned long long)c_drop);
+    if (c_marg) atomicAdd(&counters[3], (unsigned long long)c_marg);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // unfused variants for the drop-in wrapper
 // ---------------------------------------------------------------------------------------
 // points/weights of every accepted pair (what the reference returns as Quadrature<spacedim>)
@@ -460,7 +669,7 @@ int nm_split_run(nm_ctx *ctx)
   ctx->counts.n_split_ties = 0;
   if (n == 0) return NM_OK;
   if (ctx->spacedim == 3) {
-    split_kernel<<<nm_blocks(n, 128), 128, 0, ctx->stream>>>(n, ctx->im_verts.as<double>(), ctx->im_split.as<uint8_t>(),
+    split_kernel<<<nm_blocks(n, 128), 128, 0, NM_LS(ctx)>>>(n, ctx->im_verts.as<double>(), ctx->im_split.as<uint8_t>(),
                                                               ctx->im_measure.as<double>(), ties);
     NM_CUDA(cudaGetLastError());
     unsigned long long h = 0;
@@ -468,7 +677,7 @@ int nm_split_run(nm_ctx *ctx)
     NM_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->counts.n_split_ties = h;
   } else {
-    segment_measure_kernel<<<nm_blocks(n, 256), 256, 0, ctx->stream>>>(n, ctx->im_verts.as<double>(), ctx->im_measure.as<double>());
+    segment_measure_kernel<<<nm_blocks(n, 256), 256, 0, NM_LS(ctx)>>>(n, ctx->im_verts.as<double>(), ctx->im_measure.as<double>());
     NM_CUDA(cudaGetLastError());
   }
   return NM_OK;
@@ -500,16 +709,25 @@ int nm_clip_run(nm_ctx *ctx)
   ctx->counts.n_accepted = ctx->counts.n_qpoints = ctx->counts.n_dropped = ctx->counts.n_marginal = 0;
   if (nc == 0) return NM_OK;
   const unsigned T = 128, B = nm_blocks(nc, T);
-  if (d == 3)
-    clip_local_kernel<3><<<B, T, 0, ctx->stream>>>(nc, ctx->cand_im.as<uint32_t>(), ctx->cand_bg.as<uint32_t>(), ctx->bg_box.as<double>(),
+  KernelTimer kt(ctx, NM_T_K_CLIP);
+  // closed-form moments are what a rule exact to degree 3 returns: the reference's degree = 3
+  // (QGaussSimplex<2>(3), exact to degree 5) qualifies; lower rules go through the quadrature kernel
+  if (d == 3 && ctx->degree == 3 && !ctx->force_quadrature_kernel)
+    clip_moments3_kernel<<<nm_blocks(nc, CM_WARPS * 32 * CM_CHUNKS), CM_WARPS * 32, 0, NM_LS(ctx)>>>(
+        nc, ctx->cand_im.as<uint32_t>(), ctx->cand_bg.as<uint32_t>(), ctx->bg_box.as<double>(), ctx->im_verts.as<double>(),
+        ctx->im_split.as<uint8_t>(), ctx->im_measure.as<double>(), ctx->tol, 7u, ctx->cand_sumw.as<double>(),
+        ctx->cand_local.as<double>(), ctx->cand_nq.as<uint16_t>(), ctx->cand_acc.as<uint8_t>(), cnt);
+  else if (d == 3)
+    clip_local_kernel<3><<<B, T, 0, NM_LS(ctx)>>>(nc, ctx->cand_im.as<uint32_t>(), ctx->cand_bg.as<uint32_t>(), ctx->bg_box.as<double>(),
                                                    ctx->im_verts.as<double>(), ctx->im_split.as<uint8_t>(), ctx->im_measure.as<double>(),
                                                    ctx->tol, ctx->cand_sumw.as<double>(), ctx->cand_local.as<double>(),
                                                    ctx->cand_nq.as<uint16_t>(), ctx->cand_acc.as<uint8_t>(), cnt);
   else
-    clip_local_kernel<2><<<B, T, 0, ctx->stream>>>(nc, ctx->cand_im.as<uint32_t>(), ctx->cand_bg.as<uint32_t>(), ctx->bg_box.as<double>(),
+    clip_local_kernel<2><<<B, T, 0, NM_LS(ctx)>>>(nc, ctx->cand_im.as<uint32_t>(), ctx->cand_bg.as<uint32_t>(), ctx->bg_box.as<double>(),
                                                    ctx->im_verts.as<double>(), nullptr, ctx->im_measure.as<double>(), ctx->tol,
                                                    ctx->cand_sumw.as<double>(), ctx->cand_local.as<double>(), ctx->cand_nq.as<uint16_t>(),
                                                    ctx->cand_acc.as<uint8_t>(), cnt);
+  kt.stop();
   NM_CUDA(cudaGetLastError());
   unsigned long long h[4];
   NM_CUDA(cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
@@ -529,9 +747,9 @@ int nm_accepted_index(nm_ctx *ctx, uint64_t **idx_dev)
   NM_TRY(nm_ensure(ctx, ctx->stage_x, (nc + 2) * sizeof(uint64_t)));
   NM_TRY(nm_ensure(ctx, ctx->a_cursor, (na + 2) * sizeof(uint64_t)));
   uint64_t *flags = ctx->scratch_b.as<uint64_t>(), *pos = ctx->stage_x.as<uint64_t>();
-  flag_to_u64<<<nm_blocks(nc + 1, 256), 256, 0, ctx->stream>>>(nc, ctx->cand_acc.as<uint8_t>(), flags);
+  flag_to_u64<<<nm_blocks(nc + 1, 256), 256, 0, NM_LS(ctx)>>>(nc, ctx->cand_acc.as<uint8_t>(), flags);
   NM_TRY(nm_exclusive_scan_u64(ctx, flags, pos, nc + 1));
-  if (nc) compact_idx<<<nm_blocks(nc, 256), 256, 0, ctx->stream>>>(nc, ctx->cand_acc.as<uint8_t>(), pos, ctx->a_cursor.as<uint64_t>());
+  if (nc) compact_idx<<<nm_blocks(nc, 256), 256, 0, NM_LS(ctx)>>>(nc, ctx->cand_acc.as<uint8_t>(), pos, ctx->a_cursor.as<uint64_t>());
   NM_CUDA(cudaGetLastError());
   *idx_dev = ctx->a_cursor.as<uint64_t>();
   return NM_OK;
@@ -549,7 +767,7 @@ int nm_quadrature_emit(nm_ctx *ctx, uint64_t *q_offset, double *points, double *
   DevBuf &offs = ctx->c_rowstart;  // scratch use is safe: matrix build re-creates it
   ctx->matrix_valid = false;
   NM_TRY(nm_ensure(ctx, offs, (na + 2) * sizeof(uint64_t)));
-  gather_nq_kernel<<<nm_blocks(na + 1, 256), 256, 0, ctx->stream>>>(na, acc_idx, ctx->cand_nq.as<uint16_t>(), cnt32.as<uint32_t>());
+  gather_nq_kernel<<<nm_blocks(na + 1, 256), 256, 0, NM_LS(ctx)>>>(na, acc_idx, ctx->cand_nq.as<uint16_t>(), cnt32.as<uint32_t>());
   NM_TRY(nm_exclusive_scan_u32_to_u64(ctx, cnt32.as<uint32_t>(), offs.as<uint64_t>(), na + 1));
   if (q_offset) NM_TRY(nm_download(ctx, q_offset, offs.p, (na + 1) * sizeof(uint64_t), where));
   if (!points && !weights) return NM_OK;
@@ -563,11 +781,11 @@ int nm_quadrature_emit(nm_ctx *ctx, uint64_t *q_offset, double *points, double *
   }
   if (na) {
     if (d == 3)
-      emit_quadrature_kernel<3><<<nm_blocks(na, 128), 128, 0, ctx->stream>>>(na, acc_idx, ctx->cand_im.as<uint32_t>(), ctx->cand_bg.as<uint32_t>(),
+      emit_quadrature_kernel<3><<<nm_blocks(na, 128), 128, 0, NM_LS(ctx)>>>(na, acc_idx, ctx->cand_im.as<uint32_t>(), ctx->cand_bg.as<uint32_t>(),
                                                                            ctx->bg_box.as<double>(), ctx->im_verts.as<double>(),
                                                                            ctx->im_split.as<uint8_t>(), ctx->tol, offs.as<uint64_t>(), pts_d, w_d);
     else
-      emit_quadrature_kernel<2><<<nm_blocks(na, 128), 128, 0, ctx->stream>>>(na, acc_idx, ctx->cand_im.as<uint32_t>(), ctx->cand_bg.as<uint32_t>(),
+      emit_quadrature_kernel<2><<<nm_blocks(na, 128), 128, 0, NM_LS(ctx)>>>(na, acc_idx, ctx->cand_im.as<uint32_t>(), ctx->cand_bg.as<uint32_t>(),
                                                                            ctx->bg_box.as<double>(), ctx->im_verts.as<double>(), nullptr,
                                                                            ctx->tol, offs.as<uint64_t>(), pts_d, w_d);
     NM_CUDA(cudaGetLastError());
@@ -613,11 +831,11 @@ int nm_local_from_quadrature(nm_ctx *ctx, uint64_t n_pairs, const uint32_t *im, 
   NM_CUDA(cudaMemsetAsync(missing, 0, 8, ctx->stream));
   if (n_pairs) {
     if (d == 3)
-      local_from_quadrature_kernel<3><<<nm_blocks(n_pairs, 128), 128, 0, ctx->stream>>>(
+      local_from_quadrature_kernel<3><<<nm_blocks(n_pairs, 128), 128, 0, NM_LS(ctx)>>>(
           n_pairs, im_d, bg_d, qo_d, p_d, w_d, ctx->cand_ptr.as<uint64_t>(), ctx->cand_bg.as<uint32_t>(), ctx->bg_box.as<double>(), ctx->n_im,
           ctx->cand_sumw.as<double>(), ctx->cand_local.as<double>(), ctx->cand_acc.as<uint8_t>(), missing);
     else
-      local_from_quadrature_kernel<2><<<nm_blocks(n_pairs, 128), 128, 0, ctx->stream>>>(
+      local_from_quadrature_kernel<2><<<nm_blocks(n_pairs, 128), 128, 0, NM_LS(ctx)>>>(
           n_pairs, im_d, bg_d, qo_d, p_d, w_d, ctx->cand_ptr.as<uint64_t>(), ctx->cand_bg.as<uint32_t>(), ctx->bg_box.as<double>(), ctx->n_im,
           ctx->cand_sumw.as<double>(), ctx->cand_local.as<double>(), ctx->cand_acc.as<uint8_t>(), missing);
     NM_CUDA(cudaGetLastError());

@@ -80,6 +80,7 @@ struct nm_ctx {
   DevBuf cand_acc;    // [n_cand] u8: pair accepted (sum of weights > tol)
   DevBuf counters;    // device counters (u64 x 8)
   bool intersect_valid = false;
+  bool force_quadrature_kernel = false;  // NMGPU_FORCE_QUADRATURE=1: per-point kernel even where moments apply
   bool local_from_user = false;  // cand_local was filled by nm_assemble_from_quadrature
 
   // ---- matrix ----
@@ -100,7 +101,8 @@ struct nm_ctx {
   DevBuf scan_tmp, scratch_a, scratch_b, stage_x, stage_y, h2d_stage;
 
   // ---- timing ----
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  uint64_t n_launches = 0;  // kernels of this library launched so far (cub's internal ones not counted)
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   float t_ms[NM_T_COUNT];
 };
 
@@ -138,6 +140,24 @@ struct PhaseTimer {
     float ms = 0;
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     if (accumulate) c->t_ms[phase] += ms; else c->t_ms[phase] = ms;
+  }
+};
+
+// launch-stream accessor that also counts the launch
+#define NM_LS(c) (++(c)->n_launches, (c)->stream)
+
+// events around ONE kernel launch (independent of the phase timers)
+struct KernelTimer {
+  nm_ctx *c;
+  int slot;
+  KernelTimer(nm_ctx *ctx, int s) : c(ctx), slot(s) { cudaEventRecord(c->ev2, c->stream); }
+  void stop()
+  {
+    cudaEventRecord(c->ev3, c->stream);
+    cudaEventSynchronize(c->ev3);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev2, c->ev3);
+    c->t_ms[slot] = ms;
   }
 };
 

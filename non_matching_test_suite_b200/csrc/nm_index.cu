@@ -358,11 +358,11 @@ int nm_bg_layout(nm_ctx *ctx, int d, uint64_t n, const double *verts_dev, const 
   const unsigned T = 256, B = nm_blocks(n, T);
   if (n) {
     if (verts_dev) {
-      if (d == 2) bg_boxes_from_verts<2><<<B, T, 0, ctx->stream>>>(n, verts_dev, ctx->bg_box.as<double>(), bad);
-      else bg_boxes_from_verts<3><<<B, T, 0, ctx->stream>>>(n, verts_dev, ctx->bg_box.as<double>(), bad);
+      if (d == 2) bg_boxes_from_verts<2><<<B, T, 0, NM_LS(ctx)>>>(n, verts_dev, ctx->bg_box.as<double>(), bad);
+      else bg_boxes_from_verts<3><<<B, T, 0, NM_LS(ctx)>>>(n, verts_dev, ctx->bg_box.as<double>(), bad);
     } else {
-      if (d == 2) bg_boxes_from_lohi<2><<<B, T, 0, ctx->stream>>>(n, lo_dev, hi_dev, ctx->bg_box.as<double>(), bad);
-      else bg_boxes_from_lohi<3><<<B, T, 0, ctx->stream>>>(n, lo_dev, hi_dev, ctx->bg_box.as<double>(), bad);
+      if (d == 2) bg_boxes_from_lohi<2><<<B, T, 0, NM_LS(ctx)>>>(n, lo_dev, hi_dev, ctx->bg_box.as<double>(), bad);
+      else bg_boxes_from_lohi<3><<<B, T, 0, NM_LS(ctx)>>>(n, lo_dev, hi_dev, ctx->bg_box.as<double>(), bad);
     }
     NM_CUDA(cudaGetLastError());
   }
@@ -383,7 +383,7 @@ int nm_constraints_layout(nm_ctx *ctx)
   if (ctx->n_constrained) {
     int *bad = ctx->counters.as<int>();
     NM_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
-    fill_line_of<<<nm_blocks(ctx->n_constrained, 256), 256, 0, ctx->stream>>>(
+    fill_line_of<<<nm_blocks(ctx->n_constrained, 256), 256, 0, NM_LS(ctx)>>>(
         ctx->n_constrained, ctx->scratch_a.as<uint32_t>(), ctx->line_of.as<int32_t>(), ctx->n_space_dofs, bad);
     NM_CUDA(cudaGetLastError());
     int h_bad = 0;
@@ -420,13 +420,13 @@ int nm_index_build(nm_ctx *ctx)
   ctx->index_valid = false;
   if (n == 0) { ctx->gi.g0 = 1; ctx->gi.hash_cap = 1; ctx->index_valid = true;
     NM_TRY(nm_ensure(ctx, ctx->idx_hash, sizeof(HashSlot)));
-    hash_clear<<<1, 32, 0, ctx->stream>>>(ctx->idx_hash.as<HashSlot>(), 1);
+    hash_clear<<<1, 32, 0, NM_LS(ctx)>>>(ctx->idx_hash.as<HashSlot>(), 1);
     return NM_OK; }
   // 1. origin and level-0 spacing
   const unsigned SB = 256;
   NM_TRY(nm_ensure(ctx, ctx->idx_tmp, SB * 8 * sizeof(double)));
-  if (d == 2) bg_stats<2><<<SB, 256, 0, ctx->stream>>>(n, ctx->bg_box.as<double>(), ctx->idx_tmp.as<double>());
-  else bg_stats<3><<<SB, 256, 0, ctx->stream>>>(n, ctx->bg_box.as<double>(), ctx->idx_tmp.as<double>());
+  if (d == 2) bg_stats<2><<<SB, 256, 0, NM_LS(ctx)>>>(n, ctx->bg_box.as<double>(), ctx->idx_tmp.as<double>());
+  else bg_stats<3><<<SB, 256, 0, NM_LS(ctx)>>>(n, ctx->bg_box.as<double>(), ctx->idx_tmp.as<double>());
   NM_CUDA(cudaGetLastError());
   static thread_local double h_stats[SB * 8];
   NM_CUDA(cudaMemcpyAsync(h_stats, ctx->idx_tmp.p, sizeof(h_stats), cudaMemcpyDeviceToHost, ctx->stream));
@@ -458,8 +458,8 @@ int nm_index_build(nm_ctx *ctx)
   int *bad = ctx->counters.as<int>();
   NM_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 64, ctx->stream));
   const unsigned T = 256, B = nm_blocks(n, T);
-  if (d == 2) entries_count<2><<<B, T, 0, ctx->stream>>>(G, n, ctx->bg_box.as<double>(), ctx->scratch_a.as<uint32_t>(), lmask, bad);
-  else entries_count<3><<<B, T, 0, ctx->stream>>>(G, n, ctx->bg_box.as<double>(), ctx->scratch_a.as<uint32_t>(), lmask, bad);
+  if (d == 2) entries_count<2><<<B, T, 0, NM_LS(ctx)>>>(G, n, ctx->bg_box.as<double>(), ctx->scratch_a.as<uint32_t>(), lmask, bad);
+  else entries_count<3><<<B, T, 0, NM_LS(ctx)>>>(G, n, ctx->bg_box.as<double>(), ctx->scratch_a.as<uint32_t>(), lmask, bad);
   NM_CUDA(cudaGetLastError());
   NM_TRY(nm_exclusive_scan_u32_to_u64(ctx, ctx->scratch_a.as<uint32_t>(), ctx->scratch_b.as<uint64_t>(), n));
   uint64_t last_off = 0; uint32_t last_cnt = 0; unsigned h_hdr[4];
@@ -476,9 +476,9 @@ int nm_index_build(nm_ctx *ctx)
   NM_TRY(nm_ensure(ctx, ctx->idx_keys_alt, ne * 8));
   NM_TRY(nm_ensure(ctx, ctx->idx_vals, ne * 4));
   NM_TRY(nm_ensure(ctx, ctx->idx_vals_alt, ne * 4));
-  if (d == 2) entries_fill<2><<<B, T, 0, ctx->stream>>>(G, n, ctx->bg_box.as<double>(), ctx->scratch_b.as<uint64_t>(),
+  if (d == 2) entries_fill<2><<<B, T, 0, NM_LS(ctx)>>>(G, n, ctx->bg_box.as<double>(), ctx->scratch_b.as<uint64_t>(),
                                                        ctx->idx_keys_alt.as<unsigned long long>(), ctx->idx_vals_alt.as<uint32_t>());
-  else entries_fill<3><<<B, T, 0, ctx->stream>>>(G, n, ctx->bg_box.as<double>(), ctx->scratch_b.as<uint64_t>(),
+  else entries_fill<3><<<B, T, 0, NM_LS(ctx)>>>(G, n, ctx->bg_box.as<double>(), ctx->scratch_b.as<uint64_t>(),
                                                  ctx->idx_keys_alt.as<unsigned long long>(), ctx->idx_vals_alt.as<uint32_t>());
   NM_CUDA(cudaGetLastError());
   // 3. sort by grid cell (stable: background ids stay ascending inside a cell)
@@ -494,8 +494,8 @@ int nm_index_build(nm_ctx *ctx)
   while (cap < 2 * ne) cap <<= 1;
   ctx->gi.hash_cap = cap;
   NM_TRY(nm_ensure(ctx, ctx->idx_hash, (size_t)cap * sizeof(HashSlot)));
-  hash_clear<<<nm_blocks(cap, 256), 256, 0, ctx->stream>>>(ctx->idx_hash.as<HashSlot>(), cap);
-  hash_insert_runs<<<nm_blocks(ne, 256), 256, 0, ctx->stream>>>((uint32_t)ne, ctx->idx_keys.as<unsigned long long>(),
+  hash_clear<<<nm_blocks(cap, 256), 256, 0, NM_LS(ctx)>>>(ctx->idx_hash.as<HashSlot>(), cap);
+  hash_insert_runs<<<nm_blocks(ne, 256), 256, 0, NM_LS(ctx)>>>((uint32_t)ne, ctx->idx_keys.as<unsigned long long>(),
                                                                 ctx->idx_hash.as<HashSlot>(), cap - 1);
   NM_CUDA(cudaGetLastError());
   ctx->index_valid = true;
@@ -513,8 +513,10 @@ int nm_candidates_run(nm_ctx *ctx)
   if (n_im == 0) { NM_CUDA(cudaMemsetAsync(ctx->cand_ptr.p, 0, 8, ctx->stream)); return NM_OK; }
   const unsigned T = 128, B = nm_blocks(n_im, T);
   NM_CUDA(cudaMemsetAsync(ctx->scratch_a.as<uint32_t>() + n_im, 0, 4, ctx->stream));
-  if (d == 2) cand_count<2><<<B, T, 0, ctx->stream>>>(G, n_im, ctx->im_verts.as<double>(), ctx->bg_box.as<double>(), ctx->scratch_a.as<uint32_t>());
-  else cand_count<3><<<B, T, 0, ctx->stream>>>(G, n_im, ctx->im_verts.as<double>(), ctx->bg_box.as<double>(), ctx->scratch_a.as<uint32_t>());
+  KernelTimer kc(ctx, NM_T_K_CAND_COUNT);
+  if (d == 2) cand_count<2><<<B, T, 0, NM_LS(ctx)>>>(G, n_im, ctx->im_verts.as<double>(), ctx->bg_box.as<double>(), ctx->scratch_a.as<uint32_t>());
+  else cand_count<3><<<B, T, 0, NM_LS(ctx)>>>(G, n_im, ctx->im_verts.as<double>(), ctx->bg_box.as<double>(), ctx->scratch_a.as<uint32_t>());
+  kc.stop();
   NM_CUDA(cudaGetLastError());
   NM_TRY(nm_exclusive_scan_u32_to_u64(ctx, ctx->scratch_a.as<uint32_t>(), ctx->cand_ptr.as<uint64_t>(), n_im + 1));
   uint64_t n_cand = 0;
@@ -524,10 +526,12 @@ int nm_candidates_run(nm_ctx *ctx)
   ctx->counts.n_candidates = n_cand;
   NM_TRY(nm_ensure(ctx, ctx->cand_im, (n_cand + 1) * 4));
   NM_TRY(nm_ensure(ctx, ctx->cand_bg, (n_cand + 1) * 4));
-  if (d == 2) cand_fill<2><<<B, T, 0, ctx->stream>>>(G, n_im, ctx->im_verts.as<double>(), ctx->bg_box.as<double>(), ctx->cand_ptr.as<uint64_t>(),
+  KernelTimer kf(ctx, NM_T_K_CAND_FILL);
+  if (d == 2) cand_fill<2><<<B, T, 0, NM_LS(ctx)>>>(G, n_im, ctx->im_verts.as<double>(), ctx->bg_box.as<double>(), ctx->cand_ptr.as<uint64_t>(),
                                                     ctx->cand_im.as<uint32_t>(), ctx->cand_bg.as<uint32_t>());
-  else cand_fill<3><<<B, T, 0, ctx->stream>>>(G, n_im, ctx->im_verts.as<double>(), ctx->bg_box.as<double>(), ctx->cand_ptr.as<uint64_t>(),
+  else cand_fill<3><<<B, T, 0, NM_LS(ctx)>>>(G, n_im, ctx->im_verts.as<double>(), ctx->bg_box.as<double>(), ctx->cand_ptr.as<uint64_t>(),
                                               ctx->cand_im.as<uint32_t>(), ctx->cand_bg.as<uint32_t>());
+  kf.stop();
   NM_CUDA(cudaGetLastError());
   return NM_OK;
 }

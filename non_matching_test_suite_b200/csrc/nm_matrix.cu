@@ -351,7 +351,7 @@ static int matrix_build_t(nm_ctx *ctx)
   NM_CUDA(cudaMemsetAsync(hdr, 0, 16, ctx->stream));
   NM_CUDA(cudaMemsetAsync(ctx->scratch_a.as<uint32_t>() + n_im, 0, 4, ctx->stream));
   if (n_im) {
-    row_capacity_kernel<NL><<<nm_blocks(n_im, 128), 128, 0, ctx->stream>>>(
+    row_capacity_kernel<NL><<<nm_blocks(n_im, 128), 128, 0, NM_LS(ctx)>>>(
         n_im, ctx->cand_ptr.as<uint64_t>(), ctx->cand_bg.as<uint32_t>(), ctx->cand_acc.as<uint8_t>(), ctx->bg_dofs.as<uint32_t>(),
         ctx->line_of.as<int32_t>(), ctx->c_ptr.as<uint64_t>(), ctx->scratch_a.as<uint32_t>(), hdr, hdr + 1);
     NM_CUDA(cudaGetLastError());
@@ -372,18 +372,20 @@ static int matrix_build_t(nm_ctx *ctx)
     const int warps = 8;
     const size_t smem = (size_t)warps * WARP_CAP * 16;
     NM_CUDA(cudaFuncSetAttribute(merge_rows_warp<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    merge_rows_warp<NL><<<nm_blocks(n_im, warps), warps * 32, smem, ctx->stream>>>(
+    KernelTimer km(ctx, NM_T_K_MERGE);
+    merge_rows_warp<NL><<<nm_blocks(n_im, warps), warps * 32, smem, NM_LS(ctx)>>>(
         n_im, ctx->scratch_a.as<uint32_t>(), ctx->cand_ptr.as<uint64_t>(), ctx->cand_bg.as<uint32_t>(), ctx->cand_acc.as<uint8_t>(),
         ctx->cand_local.as<double>(), ctx->bg_dofs.as<uint32_t>(), ctx->line_of.as<int32_t>(), ctx->c_ptr.as<uint64_t>(),
         ctx->c_master.as<uint32_t>(), ctx->c_weight.as<double>(), ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(),
         ctx->c_col.as<uint32_t>(), ctx->c_val.as<double>());
+    km.stop();
     NM_CUDA(cudaGetLastError());
     if (h_hdr[1]) {
       NM_TRY(nm_ensure(ctx, ctx->scratch_b, (size_t)h_hdr[1] * 4 + 16));
-      list_big_rows<<<nm_blocks(n_im, 256), 256, 0, ctx->stream>>>(n_im, ctx->scratch_a.as<uint32_t>(), ctx->scratch_b.as<uint32_t>(), hdr + 2);
+      list_big_rows<<<nm_blocks(n_im, 256), 256, 0, NM_LS(ctx)>>>(n_im, ctx->scratch_a.as<uint32_t>(), ctx->scratch_b.as<uint32_t>(), hdr + 2);
       const size_t smem_b = (size_t)BLOCK_CAP * 16;
       NM_CUDA(cudaFuncSetAttribute(merge_rows_block<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-      merge_rows_block<NL><<<h_hdr[1], 256, smem_b, ctx->stream>>>(
+      merge_rows_block<NL><<<h_hdr[1], 256, smem_b, NM_LS(ctx)>>>(
           h_hdr[1], ctx->scratch_b.as<uint32_t>(), ctx->cand_ptr.as<uint64_t>(), ctx->cand_bg.as<uint32_t>(), ctx->cand_acc.as<uint8_t>(),
           ctx->cand_local.as<double>(), ctx->bg_dofs.as<uint32_t>(), ctx->line_of.as<int32_t>(), ctx->c_ptr.as<uint64_t>(),
           ctx->c_master.as<uint32_t>(), ctx->c_weight.as<double>(), ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(),
@@ -401,7 +403,7 @@ static int matrix_build_t(nm_ctx *ctx)
   NM_CUDA(cudaMemsetAsync(cnt, 0, (n_rows + 2) * sizeof(uint32_t) * 2, ctx->stream));
   constexpr int TL = NL == 8 ? 8 : 4;
   if (n_im) {
-    t_count<TL><<<nm_blocks(n_im * TL, 256), 256, 0, ctx->stream>>>(n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(),
+    t_count<TL><<<nm_blocks(n_im * TL, 256), 256, 0, NM_LS(ctx)>>>(n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(),
                                                                    ctx->c_col.as<uint32_t>(), cnt);
     NM_CUDA(cudaGetLastError());
   }
@@ -413,13 +415,13 @@ static int matrix_build_t(nm_ctx *ctx)
   NM_TRY(nm_ensure(ctx, ctx->a_col, (nnz + 1) * sizeof(uint32_t)));
   NM_TRY(nm_ensure(ctx, ctx->a_val, (nnz + 1) * sizeof(double)));
   if (n_im) {
-    t_scatter<TL><<<nm_blocks(n_im * TL, 256), 256, 0, ctx->stream>>>(
+    t_scatter<TL><<<nm_blocks(n_im * TL, 256), 256, 0, NM_LS(ctx)>>>(
         n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(), ctx->c_val.as<double>(),
         ctx->im_dofs.as<uint32_t>(), ctx->a_rowptr.as<uint64_t>(), cursor, ctx->a_col.as<uint32_t>(), ctx->a_val.as<double>());
     NM_CUDA(cudaGetLastError());
   }
   if (n_rows) {
-    t_sort_rows<<<nm_blocks(n_rows, 256), 256, 0, ctx->stream>>>(n_rows, ctx->a_rowptr.as<uint64_t>(), ctx->a_col.as<uint32_t>(), ctx->a_val.as<double>());
+    t_sort_rows<<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr.as<uint64_t>(), ctx->a_col.as<uint32_t>(), ctx->a_val.as<double>());
     NM_CUDA(cudaGetLastError());
   }
   tt.stop();
@@ -436,17 +438,17 @@ int nm_spmv_run(nm_ctx *ctx, int transpose, const double *x, double *y)
   if (!transpose) {
     const double avg = n_rows ? (double)ctx->nnz / (double)n_rows : 0;
     if (n_rows) {
-      if (avg > 12) spmv_csr<8><<<nm_blocks(n_rows * 8, 256), 256, 0, ctx->stream>>>(n_rows, ctx->a_rowptr.as<uint64_t>(), ctx->a_col.as<uint32_t>(), ctx->a_val.as<double>(), x, y);
-      else if (avg > 5) spmv_csr<4><<<nm_blocks(n_rows * 4, 256), 256, 0, ctx->stream>>>(n_rows, ctx->a_rowptr.as<uint64_t>(), ctx->a_col.as<uint32_t>(), ctx->a_val.as<double>(), x, y);
-      else spmv_csr<2><<<nm_blocks(n_rows * 2, 256), 256, 0, ctx->stream>>>(n_rows, ctx->a_rowptr.as<uint64_t>(), ctx->a_col.as<uint32_t>(), ctx->a_val.as<double>(), x, y);
+      if (avg > 12) spmv_csr<8><<<nm_blocks(n_rows * 8, 256), 256, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr.as<uint64_t>(), ctx->a_col.as<uint32_t>(), ctx->a_val.as<double>(), x, y);
+      else if (avg > 5) spmv_csr<4><<<nm_blocks(n_rows * 4, 256), 256, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr.as<uint64_t>(), ctx->a_col.as<uint32_t>(), ctx->a_val.as<double>(), x, y);
+      else spmv_csr<2><<<nm_blocks(n_rows * 2, 256), 256, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr.as<uint64_t>(), ctx->a_col.as<uint32_t>(), ctx->a_val.as<double>(), x, y);
     }
   } else {
     NM_CUDA(cudaMemsetAsync(y, 0, ctx->n_im_dofs * sizeof(double), ctx->stream));
     const double avg = n_im ? (double)ctx->nnz / (double)n_im : 0;
     if (n_im) {
-      if (avg > 24) spmv_crows<16><<<nm_blocks(n_im * 16, 256), 256, 0, ctx->stream>>>(n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(), ctx->c_val.as<double>(), ctx->im_dofs.as<uint32_t>(), x, y);
-      else if (avg > 10) spmv_crows<8><<<nm_blocks(n_im * 8, 256), 256, 0, ctx->stream>>>(n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(), ctx->c_val.as<double>(), ctx->im_dofs.as<uint32_t>(), x, y);
-      else spmv_crows<4><<<nm_blocks(n_im * 4, 256), 256, 0, ctx->stream>>>(n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(), ctx->c_val.as<double>(), ctx->im_dofs.as<uint32_t>(), x, y);
+      if (avg > 24) spmv_crows<16><<<nm_blocks(n_im * 16, 256), 256, 0, NM_LS(ctx)>>>(n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(), ctx->c_val.as<double>(), ctx->im_dofs.as<uint32_t>(), x, y);
+      else if (avg > 10) spmv_crows<8><<<nm_blocks(n_im * 8, 256), 256, 0, NM_LS(ctx)>>>(n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(), ctx->c_val.as<double>(), ctx->im_dofs.as<uint32_t>(), x, y);
+      else spmv_crows<4><<<nm_blocks(n_im * 4, 256), 256, 0, NM_LS(ctx)>>>(n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(), ctx->c_val.as<double>(), ctx->im_dofs.as<uint32_t>(), x, y);
     }
   }
   NM_CUDA(cudaGetLastError());
@@ -460,10 +462,10 @@ int nm_c_rows_compact(nm_ctx *ctx, uint64_t *rowptr_dev, uint32_t *col_dev, doub
   const uint64_t n_im = ctx->n_im, n_cols = ctx->n_im_dofs;
   NM_TRY(nm_ensure(ctx, ctx->scratch_a, (n_cols + 2) * sizeof(uint32_t)));
   NM_CUDA(cudaMemsetAsync(ctx->scratch_a.p, 0, (n_cols + 2) * sizeof(uint32_t), ctx->stream));
-  if (n_im) scatter_len_by_dof<<<nm_blocks(n_im, 256), 256, 0, ctx->stream>>>(n_im, ctx->c_rowlen.as<uint32_t>(), ctx->im_dofs.as<uint32_t>(), ctx->scratch_a.as<uint32_t>());
+  if (n_im) scatter_len_by_dof<<<nm_blocks(n_im, 256), 256, 0, NM_LS(ctx)>>>(n_im, ctx->c_rowlen.as<uint32_t>(), ctx->im_dofs.as<uint32_t>(), ctx->scratch_a.as<uint32_t>());
   NM_TRY(nm_exclusive_scan_u32_to_u64(ctx, ctx->scratch_a.as<uint32_t>(), rowptr_dev, n_cols + 1));
   if (n_im && col_dev)
-    c_compact<8><<<nm_blocks(n_im * 8, 256), 256, 0, ctx->stream>>>(n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(),
+    c_compact<8><<<nm_blocks(n_im * 8, 256), 256, 0, NM_LS(ctx)>>>(n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(),
                                                                  ctx->c_val.as<double>(), ctx->im_dofs.as<uint32_t>(), rowptr_dev, col_dev, val_dev);
   NM_CUDA(cudaGetLastError());
   return NM_OK;

@@ -523,3 +523,41 @@ def make_config(name: str, cycle: int, band_only: Optional[bool] = None, device=
     near = im.boxes() if band_only else None
     bg = background_grid(lmap, cycle, near=near, dirichlet=dirichlet)
     return bg, im
+
+
+# --------------------------------------------------------------------------- #
+# sharding by immersed-cell ranges
+# --------------------------------------------------------------------------- #
+def shard_range(n_cells: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced immersed-cell range of `rank`."""
+    base, rem = divmod(n_cells, world)
+    first = rank * base + min(rank, rem)
+    return first, first + base + (1 if rank < rem else 0)
+
+
+def restrict_background(bg: BackgroundGrid, blo: torch.Tensor, bhi: torch.Tensor) -> BackgroundGrid:
+    """Keep the cells whose closed box meets one of the boxes; DoF numbering and constraint
+    lines stay global (every rank addresses the same background vector)."""
+    keep = torch.zeros(bg.n_cells, dtype=torch.bool, device=bg.lo.device)
+    for lvl in torch.unique(bg.level).tolist():
+        sel = torch.nonzero(bg.level == lvl).flatten()
+        pos = _floor_index(bg.lo[sel] + 0.5 * (bg.hi[sel] - bg.lo[sel]), int(lvl))
+        near = _pack(overlapping_cells(blo, bhi, int(lvl)))
+        keep[sel] = torch.isin(_pack(pos), near)
+    idx = torch.nonzero(keep).flatten()
+    return BackgroundGrid(bg.spacedim, bg.lo[idx], bg.hi[idx], bg.dofs[idx], bg.n_dofs, bg.level[idx], bg.c_dof, bg.c_ptr,
+                          bg.c_master, bg.c_weight, bg.dof_coords)
+
+
+def shard_problem(name: str, cycle: int, rank: int = 0, world: int = 1, device="cpu"):
+    """This rank's share of config `name` at `cycle`: a contiguous range of immersed cells and the
+    background cells near them, with global DoF numbering."""
+    bg, im = make_config(name, cycle, band_only=True, device=device)
+    info = {"global_background_cells": bg.n_cells, "global_immersed_cells": im.n_cells, "background_dofs": bg.n_dofs}
+    if world > 1:
+        first, last = shard_range(im.n_cells, rank, world)
+        im = im.slice(first, last)
+        blo, bhi = im.boxes()
+        bg = restrict_background(bg, blo, bhi)
+    info.update({"rank0_background_cells": bg.n_cells, "rank0_immersed_cells": im.n_cells})
+    return bg, im, info
