@@ -165,6 +165,121 @@ __device__ inline void clip_step(const Poly &in, Poly &out, double bound)
   out.n = m;
 }
 
+// Polygon for the throughput kernel: coordinate-major so that one routine serves all six planes
+// (a single copy of the code keeps the kernel inside the instruction cache).
+struct PolyC {
+  double c[3][NM_MAXV];
+  int n;
+};
+
+// Convex variant of the Sutherland-Hodgman step.  The inside vertices of a convex polygon form
+// one cyclic run, so the step is: classify all vertices (bit mask), compute the (at most two)
+// crossing points -- every lane does the same two reciprocals in lockstep instead of branching
+// per edge -- and copy the run.  Emits the same vertex set as clip_step, rotated.
+// Returns false (and leaves `out` untouched) when the plane does not cut: the caller keeps `in`.
+__device__ inline bool clip_convex(const PolyC &in, PolyC &out, int axis, bool upper, double bound)
+{
+  const int n = in.n;
+  const double sgn = upper ? -1.0 : 1.0;
+  unsigned inside = 0;
+#pragma unroll 1
+  for (int i = 0; i < n; ++i) inside |= (sgn * (in.c[axis][i] - bound) >= 0.0 ? 1u : 0u) << i;
+  const unsigned full = (1u << n) - 1u;
+  if (inside == 0u) { out.n = 0; return true; }
+  if (inside == full) return false;
+  int s = 0, len = n;
+  const bool cut = true;
+  int m = 0;
+  {
+    const unsigned prev = ((inside << 1) | (inside >> (n - 1))) & full;  // bit i: vertex i-1 inside
+    s = __ffs(inside & ~prev) - 1;                                         // run start
+    const unsigned rot = ((inside >> s) | (inside << (n - s))) & full;     // run as the low bits
+    len = __ffs(~rot) - 1;                                                 // run length (< n)
+    // entering edge  p = s-1 (outside) -> q = s (inside)
+    const int ip = s == 0 ? n - 1 : s - 1;
+    const double dp = sgn * (in.c[axis][ip] - bound), dq = sgn * (in.c[axis][s] - bound);
+    if (dq > 0.0) {
+      const double t = dp * __drcp_rn(dp - dq);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) out.c[k][0] = in.c[k][ip] + t * (in.c[k][s] - in.c[k][ip]);
+      out.c[axis][0] = bound;  // on the plane by construction: later inside-tests see it as inside
+      m = 1;
+    }
+  }
+  for (int k = 0; k < len; ++k) {
+    int i = s + k;
+    if (i >= n) i -= n;
+    out.c[0][m] = in.c[0][i]; out.c[1][m] = in.c[1][i]; out.c[2][m] = in.c[2][i];
+    ++m;
+  }
+  {
+    // leaving edge  p = e (inside) -> q = e+1 (outside)
+    int ie = s + len - 1; if (ie >= n) ie -= n;
+    const int iq = ie + 1 == n ? 0 : ie + 1;
+    const double dp = sgn * (in.c[axis][ie] - bound), dq = sgn * (in.c[axis][iq] - bound);
+    if (dp > 0.0 && m < NM_MAXV) {
+      const double t = dp * __drcp_rn(dp - dq);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) out.c[k][m] = in.c[k][ie] + t * (in.c[k][iq] - in.c[k][ie]);
+      out.c[axis][m] = bound;
+      ++m;
+    }
+  }
+  out.n = m;
+  (void)cut;
+  return true;
+}
+
+// Separating-axis test triangle vs box [0,H] (box normals, triangle normal, 9 edge cross
+// products).  Conservative on equality (touching = overlap); used only to keep triangles that
+// cannot contribute out of the clipping stage.
+__device__ inline bool tri_box_overlap(const double (*v)[3], const double *H)
+{
+  const double h[3] = {0.5 * H[0], 0.5 * H[1], 0.5 * H[2]};
+  double p[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) p[i][k] = v[i][k] - h[k];
+  bool sep = false;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double mn = fmin(p[0][k], fmin(p[1][k], p[2][k])), mx = fmax(p[0][k], fmax(p[1][k], p[2][k]));
+    sep |= mn > h[k] || mx < -h[k];
+  }
+  const double f[3][3] = {{p[1][0] - p[0][0], p[1][1] - p[0][1], p[1][2] - p[0][2]},
+                          {p[2][0] - p[1][0], p[2][1] - p[1][1], p[2][2] - p[1][2]},
+                          {p[0][0] - p[2][0], p[0][1] - p[2][1], p[0][2] - p[2][2]}};
+  {
+    const double nx = f[0][1] * f[1][2] - f[0][2] * f[1][1], ny = f[0][2] * f[1][0] - f[0][0] * f[1][2], nz = f[0][0] * f[1][1] - f[0][1] * f[1][0];
+    const double d = nx * p[0][0] + ny * p[0][1] + nz * p[0][2];
+    const double r = h[0] * fabs(nx) + h[1] * fabs(ny) + h[2] * fabs(nz);
+    sep |= fabs(d) > r;
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    {  // e_x x f_j = (0, -fz, fy)
+      const double a = -f[j][2], b = f[j][1];
+      const double q0 = a * p[0][1] + b * p[0][2], q1 = a * p[1][1] + b * p[1][2], q2 = a * p[2][1] + b * p[2][2];
+      const double r = h[1] * fabs(a) + h[2] * fabs(b);
+      sep |= fmin(q0, fmin(q1, q2)) > r || fmax(q0, fmax(q1, q2)) < -r;
+    }
+    {  // e_y x f_j = (fz, 0, -fx)
+      const double a = f[j][2], b = -f[j][0];
+      const double q0 = a * p[0][0] + b * p[0][2], q1 = a * p[1][0] + b * p[1][2], q2 = a * p[2][0] + b * p[2][2];
+      const double r = h[0] * fabs(a) + h[2] * fabs(b);
+      sep |= fmin(q0, fmin(q1, q2)) > r || fmax(q0, fmax(q1, q2)) < -r;
+    }
+    {  // e_z x f_j = (-fy, fx, 0)
+      const double a = -f[j][1], b = f[j][0];
+      const double q0 = a * p[0][0] + b * p[0][1], q1 = a * p[1][0] + b * p[1][1], q2 = a * p[2][0] + b * p[2][1];
+      const double r = h[0] * fabs(a) + h[1] * fabs(b);
+      sep |= fmin(q0, fmin(q1, q2)) > r || fmax(q0, fmax(q1, q2)) < -r;
+    }
+  }
+  return !sep;
+}
+
 template <class F>
 __device__ inline void triangle_in_box(const double (*tri)[3], const double *H, F &&visit_subtriangle)
 {
@@ -383,35 +498,42 @@ __device__ inline void item_clip_moments(const double *__restrict__ box, const d
 {
   const double lo[3] = {box[0], box[1], box[2]};
   const double H[3] = {box[4] - lo[0], box[5] - lo[1], box[6] - lo[2]};
-  const int i0 = t == 0 ? 1 : 0, i1 = t <= 1 ? 2 : 1, i2 = t <= 2 ? 3 : 2;
-  Poly A, B;
-  A.n = 3;
-  A.x[0] = quad[i0 * 3 + 0] - lo[0]; A.y[0] = quad[i0 * 3 + 1] - lo[1]; A.z[0] = quad[i0 * 3 + 2] - lo[2];
-  A.x[1] = quad[i1 * 3 + 0] - lo[0]; A.y[1] = quad[i1 * 3 + 1] - lo[1]; A.z[1] = quad[i1 * 3 + 2] - lo[2];
-  A.x[2] = quad[i2 * 3 + 0] - lo[0]; A.y[2] = quad[i2 * 3 + 1] - lo[1]; A.z[2] = quad[i2 * 3 + 2] - lo[2];
+  const int iv[3] = {t == 0 ? 1 : 0, t <= 1 ? 2 : 1, t <= 2 ? 3 : 2};
+  PolyC P[2];
+  P[0].n = 3;
+#pragma unroll
+  for (int v = 0; v < 3; ++v)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) P[0].c[k][v] = quad[iv[v] * 3 + k] - lo[k];
   // unit normal of the parent triangle: J of a coplanar sub-triangle = |cross . n|
   double nx, ny, nz;
   {
-    const double e1[3] = {A.x[1] - A.x[0], A.y[1] - A.y[0], A.z[1] - A.z[0]}, e2[3] = {A.x[2] - A.x[0], A.y[2] - A.y[0], A.z[2] - A.z[0]};
+    const double e1[3] = {P[0].c[0][1] - P[0].c[0][0], P[0].c[1][1] - P[0].c[1][0], P[0].c[2][1] - P[0].c[2][0]};
+    const double e2[3] = {P[0].c[0][2] - P[0].c[0][0], P[0].c[1][2] - P[0].c[1][0], P[0].c[2][2] - P[0].c[2][0]};
     nx = e1[1] * e2[2] - e1[2] * e2[1]; ny = e1[2] * e2[0] - e1[0] * e2[2]; nz = e1[0] * e2[1] - e1[1] * e2[0];
     const double n2 = nx * nx + ny * ny + nz * nz;
     if (!(n2 > 0.0)) return;
     const double inv = rsqrt(n2);
     nx *= inv; ny *= inv; nz *= inv;
   }
-  clip_step<0, 0>(A, B, 0.0);  if (B.n < 3) return;
-  clip_step<0, 1>(B, A, H[0]); if (A.n < 3) return;
-  clip_step<1, 0>(A, B, 0.0);  if (B.n < 3) return;
-  clip_step<1, 1>(B, A, H[1]); if (A.n < 3) return;
-  clip_step<2, 0>(A, B, 0.0);  if (B.n < 3) return;
-  clip_step<2, 1>(B, A, H[2]); if (A.n < 3) return;
-  const double ih[3] = {1.0 / H[0], 1.0 / H[1], 1.0 / H[2]};
-  const double ax = A.x[0], ay = A.y[0], az = A.z[0];
+  int cur = 0;
+#pragma unroll 1
+  for (int plane = 0; plane < 6; ++plane) {
+    const int axis = plane >> 1;
+    const bool upper = plane & 1;
+    if (clip_convex(P[cur], P[cur ^ 1], axis, upper, upper ? H[axis] : 0.0)) {
+      cur ^= 1;
+      if (P[cur].n < 3) return;
+    }
+  }
+  const PolyC &A = P[cur];
+  const double ih[3] = {__drcp_rn(H[0]), __drcp_rn(H[1]), __drcp_rn(H[2])};
+  const double ax = A.c[0][0], ay = A.c[1][0], az = A.c[2][0];
   const double f0 = ax * ih[0], g0 = ay * ih[1], h0 = az * ih[2];
-  double px = A.x[1], py = A.y[1], pz = A.z[1];
+  double px = A.c[0][1], py = A.c[1][1], pz = A.c[2][1];
   double f1 = px * ih[0], g1 = py * ih[1], h1 = pz * ih[2];
   for (int j = 2; j < A.n; ++j) {
-    const double qx = A.x[j], qy = A.y[j], qz = A.z[j];
+    const double qx = A.c[0][j], qy = A.c[1][j], qz = A.c[2][j];
     const double f2 = qx * ih[0], g2 = qy * ih[1], h2 = qz * ih[2];
     const double e1x = px - ax, e1y = py - ay, e1z = pz - az, e2x = qx - ax, e2y = qy - ay, e2z = qz - az;
     const double J = fabs((e1y * e2z - e1z * e2y) * nx + (e1z * e2x - e1x * e2z) * ny + (e1x * e2y - e1y * e2x) * nz);
@@ -433,10 +555,16 @@ __device__ inline void item_clip_moments(const double *__restrict__ box, const d
   }
 }
 
-constexpr int CM_WARPS = 8;    // warps per block
+#ifndef CM_MINB
+#define CM_MINB 2
+#endif
+#ifndef CM_WARPS_N
+#define CM_WARPS_N 8
+#endif
+constexpr int CM_WARPS = CM_WARPS_N;    // warps per block
 constexpr int CM_CHUNKS = 8;   // chunks of 32 candidates per warp
 
-__global__ void __launch_bounds__(CM_WARPS * 32) clip_moments3_kernel(
+__global__ void __launch_bounds__(CM_WARPS * 32, CM_MINB) clip_moments3_kernel(
     uint64_t n_cand, const uint32_t *__restrict__ cand_im, const uint32_t *__restrict__ cand_bg, const double *__restrict__ bg_box,
     const double *__restrict__ im_verts, const uint8_t *__restrict__ split, const double *__restrict__ im_measure, double tol,
     unsigned nq_per_tri, double *__restrict__ sumw_out, double *__restrict__ local_out, uint16_t *__restrict__ nq_out,
@@ -458,22 +586,20 @@ __global__ void __launch_bounds__(CM_WARPS * 32) clip_moments3_kernel(
       const double *box = bg_box + (uint64_t)b * 8;
       const double *quad = im_verts + (uint64_t)m * 12;
       const int code = split[m];
-      double q[4][3];
+      const double H[3] = {box[4] - box[0], box[5] - box[1], box[6] - box[2]};
+      // k-th triangle of the split code: every lane runs the same (usually two) iterations
+      unsigned rem = (unsigned)code & 15u;
+#pragma unroll 1
+      while (rem) {
+        const int t = __ffs(rem) - 1;
+        rem &= rem - 1;
+        const int iv[3] = {t == 0 ? 1 : 0, t <= 1 ? 2 : 1, t <= 2 ? 3 : 2};
+        double tri[3][3];
 #pragma unroll
-      for (int v = 0; v < 4; ++v)
+        for (int v = 0; v < 3; ++v)
 #pragma unroll
-        for (int k = 0; k < 3; ++k) q[v][k] = quad[v * 3 + k];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        if (!((code >> t) & 1)) continue;
-        const int i0 = t == 0 ? 1 : 0, i1 = t <= 1 ? 2 : 1, i2 = t <= 2 ? 3 : 2;
-        bool hit = true;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const double mn = fmin(q[i0][k], fmin(q[i1][k], q[i2][k])), mx = fmax(q[i0][k], fmax(q[i1][k], q[i2][k]));
-          hit &= !(mx < box[k] || mn > box[4 + k]);      // same test as on translated coordinates (sign-exact)
-        }
-        if (hit) { items |= (unsigned)t << (2 * nitems); ++nitems; }
+          for (int k = 0; k < 3; ++k) tri[v][k] = quad[iv[v] * 3 + k] - box[k];
+        if (tri_box_overlap(tri, H)) { items |= (unsigned)t << (2 * nitems); ++nitems; }
       }
       if (nitems == 0) { sumw_out[c] = 0.0; acc_out[c] = 0; nq_out[c] = 0; }
     }

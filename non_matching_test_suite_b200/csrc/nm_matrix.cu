@@ -23,6 +23,9 @@ namespace {
 
 constexpr int WARP_CAP = 512;    // entries a warp can merge in shared memory
 constexpr int BLOCK_CAP = 8192;  // entries a 256-thread block can merge
+constexpr int HASH_CAP = 192;    // contributions the hash-table fast path accepts per immersed cell
+constexpr int HASH_SLOTS = 256;
+constexpr unsigned HASH_EMPTY = 0xffffffffu;
 
 // ---------------------------------------------------------------------------------------
 // capacity of each row of C: accepted pairs x (dofs + masters)
@@ -47,6 +50,7 @@ __global__ void row_capacity_kernel(uint64_t n_im, const uint64_t *__restrict__ 
   }
   cap[m] = c;
   if (c > WARP_CAP) { atomicAdd(n_big, 1u); atomicMax(max_cap, c); }
+  if (c > HASH_CAP) atomicAdd(n_big + 2, 1u);
 }
 
 __global__ void list_big_rows(uint64_t n_im, const uint32_t *__restrict__ cap, uint32_t *__restrict__ list, unsigned *cursor)
@@ -177,6 +181,104 @@ __device__ inline void merge_cell(uint64_t m, unsigned tid, unsigned long long *
   if (tid == 0) rowlen[m] = written;
 }
 
+// ---------------------------------------------------------------------------------------
+// fast path of the merge: per-warp hash table in shared memory instead of a sort
+// ---------------------------------------------------------------------------------------
+// A cell with at most HASH_CAP contributions has at most HASH_CAP distinct space dofs: they are
+// deduplicated with a 256-slot open-addressing table (atomicCAS on the 32-bit key), values are
+// accumulated per slot, and only the distinct keys (~35 for a sphere quad instead of ~80-130
+// contributions) are ordered, by rank counting.  Contributions are added vertex position by
+// vertex position; distinct background cells never share a vertex at the same local position,
+// so on a proper mesh every shared-memory add inside one instruction hits a different slot and
+// the summation order is the program order (bit-reproducible).  Through constraint lines several
+// lanes may add to the same master in one instruction; that order is the hardware's.
+
+__device__ inline unsigned hash_insert(unsigned *keys, unsigned dof)
+{
+  unsigned s = (dof * 2654435761u) >> 24;
+  while (true) {
+    const unsigned old = atomicCAS(&keys[s], HASH_EMPTY, dof);
+    if (old == HASH_EMPTY || old == dof) return s;
+    s = (s + 1) & (HASH_SLOTS - 1);
+  }
+}
+
+template <int NL>
+__global__ void __launch_bounds__(256) merge_rows_hash(uint64_t n_im, const uint32_t *__restrict__ cap, const uint64_t *__restrict__ cand_ptr,
+                                                       const uint32_t *__restrict__ cand_bg, const uint8_t *__restrict__ acc,
+                                                       const double *__restrict__ local, const uint32_t *__restrict__ bg_dofs,
+                                                       const int32_t *__restrict__ line_of, const uint64_t *__restrict__ c_ptr,
+                                                       const uint32_t *__restrict__ c_master, const double *__restrict__ c_weight,
+                                                       const uint64_t *__restrict__ rowstart, uint32_t *__restrict__ rowlen,
+                                                       uint32_t *__restrict__ out_col, double *__restrict__ out_val)
+{
+  __shared__ unsigned s_keys[8][HASH_SLOTS];
+  __shared__ double s_vals[8][HASH_SLOTS];
+  __shared__ unsigned s_list[8][HASH_SLOTS];
+  const unsigned w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint64_t m = (uint64_t)blockIdx.x * 8 + w;
+  if (m >= n_im) return;
+  const uint32_t cp = cap[m];
+  if (cp > HASH_CAP) return;  // sort-based kernels take these
+  if (cp == 0) { if (lane == 0) rowlen[m] = 0; return; }
+  unsigned *keys = s_keys[w];
+  double *vals = s_vals[w];
+  unsigned *list = s_list[w];
+#pragma unroll
+  for (int k = 0; k < HASH_SLOTS / 32; ++k) { keys[lane + 32 * k] = HASH_EMPTY; vals[lane + 32 * k] = 0.0; }
+  __syncwarp();
+  const uint64_t p0 = cand_ptr[m], p1 = cand_ptr[m + 1];
+  for (uint64_t base = p0; base < p1; base += 32) {
+    const uint64_t p = base + lane;
+    const bool on = p < p1 && acc[p];
+    uint32_t dofs[NL];
+    double v[NL];
+    if (on) {
+      const uint32_t *dp = bg_dofs + (uint64_t)cand_bg[p] * NL;
+      const double *lp = local + p * NL;
+#pragma unroll
+      for (int i = 0; i < NL; ++i) { dofs[i] = dp[i]; v[i] = lp[i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      if (on) {
+        const int32_t ln = line_of[dofs[i]];
+        const unsigned s = hash_insert(keys, dofs[i]);
+        if (ln < 0) {
+          atomicAdd(&vals[s], v[i]);
+        } else {
+          // keep_constrained_entries: the constrained row stays in the pattern, structurally zero;
+          // its value goes to the masters of the line (none for a Dirichlet row)
+          for (uint64_t k = c_ptr[ln]; k < c_ptr[ln + 1]; ++k) atomicAdd(&vals[hash_insert(keys, c_master[k])], c_weight[k] * v[i]);
+        }
+      }
+      __syncwarp();
+    }
+  }
+  // distinct keys -> list
+  unsigned D = 0;
+#pragma unroll
+  for (int k = 0; k < HASH_SLOTS / 32; ++k) {
+    const unsigned s = lane + 32 * k;
+    const bool occ = keys[s] != HASH_EMPTY;
+    const unsigned bal = __ballot_sync(0xffffffffu, occ);
+    if (occ) list[D + __popc(bal & ((1u << lane) - 1u))] = s;
+    D += __popc(bal);
+  }
+  __syncwarp();
+  // rank of every key among the distinct keys = its position in the row
+  const uint64_t dst = rowstart[m];
+  for (unsigned e = lane; e < D; e += 32) {
+    const unsigned s = list[e];
+    const unsigned key = keys[s];
+    unsigned rank = 0;
+    for (unsigned f = 0; f < D; ++f) rank += keys[list[f]] < key ? 1u : 0u;
+    out_col[dst + rank] = key;
+    out_val[dst + rank] = vals[s];
+  }
+  if (lane == 0) rowlen[m] = D;
+}
+
 template <int NL>
 __global__ void __launch_bounds__(256) merge_rows_warp(uint64_t n_im, const uint32_t *__restrict__ cap, const uint64_t *cand_ptr,
                                                        const uint32_t *cand_bg, const uint8_t *acc, const double *local,
@@ -190,7 +292,7 @@ __global__ void __launch_bounds__(256) merge_rows_warp(uint64_t n_im, const uint
   double *s_val = reinterpret_cast<double *>(smem + (size_t)(blockDim.x >> 5) * WARP_CAP * 8) + (size_t)w * WARP_CAP;
   const uint64_t m = (uint64_t)blockIdx.x * (blockDim.x >> 5) + w;
   if (m >= n_im) return;
-  if (cap[m] > WARP_CAP) return;  // handled by merge_rows_block
+  if (cap[m] > WARP_CAP || cap[m] <= HASH_CAP) return;  // block kernel / hash kernel take those
   merge_cell<NL, 32, WARP_CAP>(m, lane, s_key, s_val, nullptr, cand_ptr, cand_bg, acc, local, bg_dofs, line_of, c_ptr, c_master,
                                c_weight, rowstart, rowlen, out_col, out_val);
 }
@@ -347,7 +449,7 @@ static int matrix_build_t(nm_ctx *ctx)
   NM_TRY(nm_ensure(ctx, ctx->c_rowstart, (n_im + 2) * sizeof(uint64_t)));
   NM_TRY(nm_ensure(ctx, ctx->c_rowlen, (n_im + 1) * sizeof(uint32_t)));
   NM_TRY(nm_ensure(ctx, ctx->counters, 64 * sizeof(uint64_t)));
-  unsigned *hdr = ctx->counters.as<unsigned>() + 32;  // [0] max cap, [1] n_big, [2] cursor
+  unsigned *hdr = ctx->counters.as<unsigned>() + 32;  // [0] max cap, [1] n_big, [2] cursor, [3] rows above HASH_CAP
   NM_CUDA(cudaMemsetAsync(hdr, 0, 16, ctx->stream));
   NM_CUDA(cudaMemsetAsync(ctx->scratch_a.as<uint32_t>() + n_im, 0, 4, ctx->stream));
   if (n_im) {
@@ -358,9 +460,9 @@ static int matrix_build_t(nm_ctx *ctx)
   }
   NM_TRY(nm_exclusive_scan_u32_to_u64(ctx, ctx->scratch_a.as<uint32_t>(), ctx->c_rowstart.as<uint64_t>(), n_im + 1));
   uint64_t total_cap = 0;
-  unsigned h_hdr[2];
+  unsigned h_hdr[4];
   NM_CUDA(cudaMemcpyAsync(&total_cap, ctx->c_rowstart.as<uint64_t>() + n_im, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  NM_CUDA(cudaMemcpyAsync(h_hdr, hdr, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  NM_CUDA(cudaMemcpyAsync(h_hdr, hdr, 16, cudaMemcpyDeviceToHost, ctx->stream));
   NM_CUDA(cudaStreamSynchronize(ctx->stream));
   if (h_hdr[0] > (unsigned)BLOCK_CAP)
     return nm_fail(ctx, NM_ERR_UNSUPPORTED,
@@ -373,12 +475,18 @@ static int matrix_build_t(nm_ctx *ctx)
     const size_t smem = (size_t)warps * WARP_CAP * 16;
     NM_CUDA(cudaFuncSetAttribute(merge_rows_warp<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KernelTimer km(ctx, NM_T_K_MERGE);
-    merge_rows_warp<NL><<<nm_blocks(n_im, warps), warps * 32, smem, NM_LS(ctx)>>>(
+    merge_rows_hash<NL><<<nm_blocks(n_im, 8), 256, 0, NM_LS(ctx)>>>(
         n_im, ctx->scratch_a.as<uint32_t>(), ctx->cand_ptr.as<uint64_t>(), ctx->cand_bg.as<uint32_t>(), ctx->cand_acc.as<uint8_t>(),
         ctx->cand_local.as<double>(), ctx->bg_dofs.as<uint32_t>(), ctx->line_of.as<int32_t>(), ctx->c_ptr.as<uint64_t>(),
         ctx->c_master.as<uint32_t>(), ctx->c_weight.as<double>(), ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(),
         ctx->c_col.as<uint32_t>(), ctx->c_val.as<double>());
     km.stop();
+    if (h_hdr[3])
+    merge_rows_warp<NL><<<nm_blocks(n_im, warps), warps * 32, smem, NM_LS(ctx)>>>(
+        n_im, ctx->scratch_a.as<uint32_t>(), ctx->cand_ptr.as<uint64_t>(), ctx->cand_bg.as<uint32_t>(), ctx->cand_acc.as<uint8_t>(),
+        ctx->cand_local.as<double>(), ctx->bg_dofs.as<uint32_t>(), ctx->line_of.as<int32_t>(), ctx->c_ptr.as<uint64_t>(),
+        ctx->c_master.as<uint32_t>(), ctx->c_weight.as<double>(), ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(),
+        ctx->c_col.as<uint32_t>(), ctx->c_val.as<double>());
     NM_CUDA(cudaGetLastError());
     if (h_hdr[1]) {
       NM_TRY(nm_ensure(ctx, ctx->scratch_b, (size_t)h_hdr[1] * 4 + 16));
