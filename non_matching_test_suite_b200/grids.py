@@ -406,6 +406,12 @@ def background_grid(lmap: LevelMap, cycles: int, near: Optional[Tuple[torch.Tens
         # a hanging node on the boundary keeps its hanging-node line (deal.II: boundary
         # values do not overwrite existing lines)
         dir_dofs = dir_dofs[~torch.isin(dir_dofs, con_dof)]
+        # closing the constraints resolves masters that are Dirichlet rows: they only feed the
+        # inhomogeneity, so they leave the line (AffineConstraints::close())
+        keep = ~torch.isin(con_master, dir_dofs)
+        hang_dofs = torch.unique(con_dof)
+        con_dof, con_master, con_w = con_dof[keep], con_master[keep], con_w[keep]
+        dir_dofs = torch.unique(torch.cat([dir_dofs, hang_dofs]))   # lines that lost all masters stay as lines
     c_dof_all = torch.unique(torch.cat([con_dof, dir_dofs]))
     row = torch.searchsorted(c_dof_all, con_dof)
     order = torch.argsort(row * n_dofs + con_master)

@@ -1,0 +1,59 @@
+"""world_size-2 gloo test of the sharded path's host logic: immersed-cell ranges own disjoint columns,
+Ct.vmult needs exactly one all-reduce, C.Tvmult results are disjoint."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import scipy.sparse as sp
+    from non_matching_test_suite_b200.distributed import ShardedCouplingOperator
+    from non_matching_test_suite_b200.grids import shard_problem
+    from oracle import c_oracle as co
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    bg, im, _ = shard_problem("disk", 2, rank, world)
+    r = co.assemble(bg, im, threads=1)
+    A = sp.csr_matrix((r["val"], r["col"].astype(np.int64), r["rowptr"].astype(np.int64)), shape=(bg.n_dofs, im.n_dofs))
+    op = ShardedCouplingOperator(lambda x: torch.from_numpy(A @ x.numpy()), lambda u: torch.from_numpy(A.T @ u.numpy()),
+                                 bg.n_dofs, im.n_dofs)
+    g = torch.Generator().manual_seed(0)
+    lam = torch.rand(im.n_dofs, dtype=torch.float64, generator=g)
+    u = torch.rand(bg.n_dofs, dtype=torch.float64, generator=g)
+    y, z = op.vmult(lam), op.Tvmult(u)
+    # columns owned by this rank only
+    owned = np.unique(A.nonzero()[1])
+    if rank == 0:
+        torch.save({"y": y, "z": z, "owned": owned}, out)
+    else:
+        torch.save({"owned": owned}, out + ".1")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo(tmp_path, c_oracle):
+    import scipy.sparse as sp
+    from non_matching_test_suite_b200.grids import shard_problem
+    out = str(tmp_path / "r0.pt")
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out, weights_only=False)
+    other = torch.load(out + ".1", weights_only=False)
+    assert len(np.intersect1d(got["owned"], other["owned"])) == 0      # disjoint C rows
+    bg, im, _ = shard_problem("disk", 2, 0, 1)
+    r = c_oracle.assemble(bg, im)
+    A = sp.csr_matrix((r["val"], r["col"].astype(np.int64), r["rowptr"].astype(np.int64)), shape=(bg.n_dofs, im.n_dofs))
+    g = torch.Generator().manual_seed(0)
+    lam = torch.rand(im.n_dofs, dtype=torch.float64, generator=g)
+    u = torch.rand(bg.n_dofs, dtype=torch.float64, generator=g)
+    assert np.allclose(got["y"].numpy(), A @ lam.numpy(), rtol=1e-13, atol=1e-16)
+    assert np.allclose(got["z"].numpy(), A.T @ u.numpy(), rtol=1e-13, atol=1e-16)
