@@ -94,7 +94,12 @@ def _where(*arrs) -> int:
     ws = {_ptr(a)[1] for a in arrs if a is not None}
     if len(ws) > 1:
         raise ValueError("all arrays of one call must live on the same side (host or device)")
-    return ws.pop() if ws else NM_HOST
+    w = ws.pop() if ws else NM_HOST
+    if w == NM_DEVICE:
+        # the library works on its own stream: whatever produced these tensors on torch's
+        # current stream must have finished before the pointers are handed over
+        torch.cuda.current_stream().synchronize()
+    return w
 
 
 class Context:
