@@ -1,0 +1,303 @@
+// Drop-in replacement for the reference's code/include/coupling_utilities.h, hot path only.
+//
+// Same namespace, names and signatures as the reference, implemented as thin marshalling over
+// the C ABI of libnmgpu.so (include/nmgpu.h):
+//
+//   collect_quadratures_on_overlapped_grids<dim0,dim1,spacedim>          reference :508-515, src/coupling_utilities.cc:22-69
+//   create_coupling_sparsity_pattern_with_exact_intersections<...>       reference :28-152
+//   create_coupling_mass_matrix_with_exact_intersections<...>            reference :154-304
+//
+// Implemented instantiations: <2,1,2> and <3,2,3> with FE_Q(1) on Cartesian background cells and
+// FE_DGQ(0) on the immersed grid (every LM configuration in data/*.prm).  Anything else raises
+// ExcNotImplemented -- there is no CPU fallback.  The Nitsche entry points of the reference
+// header (:306-481) are not part of this path; keep the reference's own versions for them.
+//
+// Build: add -I<repo>/include and link -L<repo>/non_matching_test_suite_b200 -lnmgpu.
+// The GPU is chosen with the environment variable NMGPU_DEVICE (default 0; with MPI set it to the
+// local rank).  See INTEGRATION.md.
+#ifndef nmgpu_coupling_utilities_h
+#define nmgpu_coupling_utilities_h
+
+#include <deal.II/base/point.h>
+#include <deal.II/base/quadrature.h>
+#include <deal.II/dofs/dof_handler.h>
+#include <deal.II/fe/component_mask.h>
+#include <deal.II/fe/mapping.h>
+#include <deal.II/grid/grid_tools_cache.h>
+#include <deal.II/grid/tria.h>
+#include <deal.II/lac/affine_constraints.h>
+
+#include <cstdint>
+#include <cstdlib>
+#include <map>
+#include <memory>
+#include <tuple>
+#include <utility>
+#include <vector>
+
+#include "nmgpu.h"
+
+namespace dealii {
+namespace NonMatching {
+
+namespace nmgpu_detail {
+
+// One GPU context per (space triangulation, immersed triangulation) pair.  The three reference
+// calls of one refinement cycle find each other through the triangulation addresses.
+struct Session {
+  nm_ctx *ctx = nullptr;
+  bool grids_set = false;
+  std::uint64_t n_space = 0, n_immersed = 0;
+  std::vector<unsigned int> space_local_of_active;     // active_cell_index -> row in the arrays sent to the GPU (or -1)
+  std::vector<unsigned int> immersed_local_of_active;
+  ~Session() { if (ctx) nm_destroy(ctx); }
+};
+
+inline Session &session(const void *space_tria, const void *immersed_tria)
+{
+  static std::map<std::pair<const void *, const void *>, std::unique_ptr<Session>> sessions;
+  auto &slot = sessions[{space_tria, immersed_tria}];
+  if (!slot) {
+    slot = std::make_unique<Session>();
+    const char *dev = std::getenv("NMGPU_DEVICE");
+    const int rc = nm_create(&slot->ctx, dev ? std::atoi(dev) : 0);
+    AssertThrow(rc == NM_OK, ExcMessage("nmgpu: no CUDA device / context creation failed (there is no CPU fallback)"));
+  }
+  return *slot;
+}
+
+inline void check(const Session &s, int rc)
+{
+  AssertThrow(rc == NM_OK, ExcMessage(std::string("nmgpu: ") + nm_last_error(s.ctx)));
+}
+
+// mapping.get_vertices(cell) of every (locally owned) active cell, cell-major, deal.II order
+// (what the reference feeds to CGAL through get_vertices_in_cgal_order, intersections.h:39-58).
+template <int dim, int spacedim>
+void gather_vertices(const Triangulation<dim, spacedim> &tria, const Mapping<dim, spacedim> &mapping, const bool owned_only,
+                     std::vector<double> &verts, std::vector<unsigned int> &local_of_active,
+                     std::vector<typename Triangulation<dim, spacedim>::cell_iterator> *cells)
+{
+  constexpr unsigned int nv = 1u << dim;
+  local_of_active.assign(tria.n_active_cells(), static_cast<unsigned int>(-1));
+  verts.clear();
+  unsigned int n = 0;
+  for (const auto &cell : tria.active_cell_iterators()) {
+    if (owned_only && !cell->is_locally_owned())
+      continue;
+    const auto v = mapping.get_vertices(cell);
+    AssertThrow(v.size() == nv, ExcNotImplemented());
+    for (unsigned int i = 0; i < nv; ++i)
+      for (unsigned int d = 0; d < spacedim; ++d)
+        verts.push_back(v[i][d]);
+    local_of_active[cell->active_cell_index()] = n++;
+    if (cells)
+      cells->push_back(cell);
+  }
+}
+
+template <int dim0, int dim1, int spacedim>
+void set_grids(Session &s, const Triangulation<dim0, spacedim> &space, const Mapping<dim0, spacedim> &mapping0,
+               const Triangulation<dim1, spacedim> &immersed, const Mapping<dim1, spacedim> &mapping1,
+               std::vector<typename Triangulation<dim0, spacedim>::cell_iterator> *space_cells,
+               std::vector<typename Triangulation<dim1, spacedim>::cell_iterator> *immersed_cells)
+{
+  std::vector<double> v0, v1;
+  // locally owned background cells, the whole immersed grid (coupling_utilities.cc:40-45)
+  gather_vertices(space, mapping0, true, v0, s.space_local_of_active, space_cells);
+  gather_vertices(immersed, mapping1, false, v1, s.immersed_local_of_active, immersed_cells);
+  s.n_space = v0.size() / ((1u << dim0) * spacedim);
+  s.n_immersed = v1.size() / ((1u << dim1) * spacedim);
+  check(s, nm_set_background(s.ctx, spacedim, s.n_space, v0.data(), nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, NM_HOST));
+  check(s, nm_set_immersed(s.ctx, dim1, spacedim, s.n_immersed, v1.data(), nullptr, 1, 0, NM_HOST));
+  s.grids_set = true;
+}
+
+// DoF indices per cell + the lines of the closed AffineConstraints object as CSR.
+template <int dim0, int dim1, int spacedim, typename number>
+void set_dofs(Session &s, const DoFHandler<dim0, spacedim> &space_dh, const DoFHandler<dim1, spacedim> &immersed_dh,
+              const AffineConstraints<number> &constraints, const AffineConstraints<number> &immersed_constraints)
+{
+  const auto &space_fe = space_dh.get_fe();
+  const auto &immersed_fe = immersed_dh.get_fe();
+  AssertThrow(space_fe.n_components() == 1 && immersed_fe.n_components() == 1, ExcNotImplemented());
+  AssertThrow(space_fe.n_dofs_per_cell() == (1u << dim0), ExcMessage("nmgpu: the background space must be FE_Q(1)"));
+  AssertThrow(immersed_fe.n_dofs_per_cell() == 1, ExcMessage("nmgpu: the immersed space must be FE_DGQ(0)"));
+  AssertThrow(immersed_constraints.n_constraints() == 0, ExcNotImplemented());
+
+  std::vector<std::uint32_t> d0(s.n_space * (1u << dim0)), d1(s.n_immersed);
+  std::vector<types::global_dof_index> tmp0(1u << dim0), tmp1(1);
+  for (const auto &cell : space_dh.active_cell_iterators()) {
+    const unsigned int l = s.space_local_of_active[cell->active_cell_index()];
+    if (l == static_cast<unsigned int>(-1))
+      continue;
+    cell->get_dof_indices(tmp0);
+    for (unsigned int i = 0; i < tmp0.size(); ++i)
+      d0[std::size_t(l) * tmp0.size() + i] = static_cast<std::uint32_t>(tmp0[i]);
+  }
+  for (const auto &cell : immersed_dh.active_cell_iterators()) {
+    cell->get_dof_indices(tmp1);
+    d1[s.immersed_local_of_active[cell->active_cell_index()]] = static_cast<std::uint32_t>(tmp1[0]);
+  }
+  std::vector<std::uint32_t> c_dof, c_master;
+  std::vector<std::uint64_t> c_ptr(1, 0);
+  std::vector<double> c_weight;
+  for (types::global_dof_index i = 0; i < space_dh.n_dofs(); ++i)
+    if (constraints.is_constrained(i)) {
+      c_dof.push_back(static_cast<std::uint32_t>(i));
+      if (const auto *entries = constraints.get_constraint_entries(i))
+        for (const auto &e : *entries) {
+          c_master.push_back(static_cast<std::uint32_t>(e.first));
+          c_weight.push_back(static_cast<double>(e.second));
+        }
+      c_ptr.push_back(c_master.size());
+    }
+  check(s, nm_set_background_dofs(s.ctx, d0.data(), space_dh.n_dofs(), c_dof.size(), c_dof.data(), c_ptr.data(), c_master.data(),
+                                  c_weight.data(), NM_HOST));
+  check(s, nm_set_immersed_dofs(s.ctx, d1.data(), 1, immersed_dh.n_dofs(), NM_HOST));
+}
+
+// Hand the caller's (cell, cell, Quadrature) tuples to the device: inverse mapping, shape
+// values and scatter all happen there (reference :238-289).
+template <int dim0, int dim1, int spacedim>
+void assemble_from_info(Session &s,
+                        const std::vector<std::tuple<typename Triangulation<dim0, spacedim>::cell_iterator,
+                                                     typename Triangulation<dim1, spacedim>::cell_iterator, Quadrature<spacedim>>> &info)
+{
+  std::vector<std::uint32_t> im, bg;
+  std::vector<std::uint64_t> off(1, 0);
+  std::vector<double> pts, w;
+  for (const auto &t : info) {
+    bg.push_back(s.space_local_of_active[std::get<0>(t)->active_cell_index()]);
+    im.push_back(s.immersed_local_of_active[std::get<1>(t)->active_cell_index()]);
+    const auto &q = std::get<2>(t);
+    for (unsigned int k = 0; k < q.size(); ++k) {
+      for (unsigned int d = 0; d < spacedim; ++d)
+        pts.push_back(q.point(k)[d]);
+      w.push_back(q.weight(k));
+    }
+    off.push_back(w.size());
+  }
+  check(s, nm_assemble_from_quadrature(s.ctx, info.size(), im.data(), bg.data(), off.data(), pts.data(), w.data(), NM_HOST));
+}
+
+} // namespace nmgpu_detail
+
+template <int dim0, int dim1, int spacedim>
+std::vector<std::tuple<typename Triangulation<dim0, spacedim>::cell_iterator, typename Triangulation<dim1, spacedim>::cell_iterator,
+                       Quadrature<spacedim>>>
+collect_quadratures_on_overlapped_grids(const GridTools::Cache<dim0, spacedim> &space_cache,
+                                        const GridTools::Cache<dim1, spacedim> &immersed_cache, const unsigned int degree,
+                                        const double tol = 1e-14)
+{
+  AssertThrow(dim1 <= dim0, ExcMessage("Intrinsic dimension of the immersed object must be smaller than dim0."));
+  AssertThrow(degree > 0, ExcMessage("Invalid quadrature degree."));
+  AssertThrow(dim1 + 1 == dim0 && dim0 == spacedim && (spacedim == 2 || spacedim == 3), ExcNotImplemented());
+
+  using SpaceIt = typename Triangulation<dim0, spacedim>::cell_iterator;
+  using ImmIt = typename Triangulation<dim1, spacedim>::cell_iterator;
+  auto &s = nmgpu_detail::session(&space_cache.get_triangulation(), &immersed_cache.get_triangulation());
+  std::vector<SpaceIt> space_cells;
+  std::vector<ImmIt> immersed_cells;
+  nmgpu_detail::set_grids<dim0, dim1, spacedim>(s, space_cache.get_triangulation(), space_cache.get_mapping(),
+                                                immersed_cache.get_triangulation(), immersed_cache.get_mapping(), &space_cells,
+                                                &immersed_cells);
+  nm_counts counts;
+  nmgpu_detail::check(s, nm_intersect(s.ctx, degree, tol, &counts));
+
+  std::vector<std::uint32_t> im(counts.n_accepted), bg(counts.n_accepted);
+  std::vector<std::uint64_t> off(counts.n_accepted + 1);
+  std::vector<double> pts(counts.n_qpoints * spacedim), w(counts.n_qpoints);
+  nmgpu_detail::check(s, nm_get_pairs(s.ctx, im.data(), bg.data(), nullptr, NM_HOST));
+  nmgpu_detail::check(s, nm_get_quadrature(s.ctx, off.data(), pts.data(), w.data(), NM_HOST));
+
+  std::vector<std::tuple<SpaceIt, ImmIt, Quadrature<spacedim>>> cells_with_quadratures;
+  cells_with_quadratures.reserve(counts.n_accepted);
+  for (std::uint64_t p = 0; p < counts.n_accepted; ++p) {
+    const std::size_t nq = off[p + 1] - off[p];
+    std::vector<Point<spacedim>> qp(nq);
+    std::vector<double> qw(w.begin() + off[p], w.begin() + off[p + 1]);
+    for (std::size_t k = 0; k < nq; ++k)
+      for (unsigned int d = 0; d < spacedim; ++d)
+        qp[k][d] = pts[(off[p] + k) * spacedim + d];
+    cells_with_quadratures.emplace_back(space_cells[bg[p]], immersed_cells[im[p]], Quadrature<spacedim>(qp, qw));
+  }
+  return cells_with_quadratures;
+}
+
+template <int dim0, int dim1, int spacedim, typename Sparsity, typename number>
+void create_coupling_sparsity_pattern_with_exact_intersections(
+    const std::vector<std::tuple<typename dealii::Triangulation<dim0, spacedim>::cell_iterator,
+                                 typename dealii::Triangulation<dim1, spacedim>::cell_iterator, dealii::Quadrature<spacedim>>>
+        &intersections_info,
+    const DoFHandler<dim0, spacedim> &space_dh, const DoFHandler<dim1, spacedim> &immersed_dh, Sparsity &sparsity,
+    const AffineConstraints<number> &constraints, const ComponentMask &space_comps, const ComponentMask &immersed_comps,
+    const AffineConstraints<number> &immersed_constraints)
+{
+  AssertDimension(sparsity.n_rows(), space_dh.n_dofs());
+  AssertDimension(sparsity.n_cols(), immersed_dh.n_dofs());
+  Assert((dim1 <= dim0) && (dim0 <= spacedim), ExcMessage("This function can only work if dim1<=dim0<=spacedim"));
+  AssertThrow(space_comps.size() <= 1 && immersed_comps.size() <= 1, ExcNotImplemented());
+
+  auto &s = nmgpu_detail::session(&space_dh.get_triangulation(), &immersed_dh.get_triangulation());
+  AssertThrow(s.grids_set, ExcMessage("nmgpu: collect_quadratures_on_overlapped_grids must be called on these grids first"));
+  nmgpu_detail::set_dofs<dim0, dim1, spacedim>(s, space_dh, immersed_dh, constraints, immersed_constraints);
+  nmgpu_detail::assemble_from_info<dim0, dim1, spacedim>(s, intersections_info);
+
+  std::uint64_t nnz = 0;
+  nmgpu_detail::check(s, nm_build_sparsity(s.ctx, &nnz));
+  std::vector<std::uint64_t> rowptr(space_dh.n_dofs() + 1);
+  std::vector<std::uint32_t> col(nnz);
+  nmgpu_detail::check(s, nm_get_csr(s.ctx, 0, rowptr.data(), col.data(), nullptr, NM_HOST));
+  std::vector<types::global_dof_index> cols;
+  for (types::global_dof_index r = 0; r < space_dh.n_dofs(); ++r)
+    if (rowptr[r + 1] > rowptr[r]) {
+      cols.assign(col.begin() + rowptr[r], col.begin() + rowptr[r + 1]);
+      sparsity.add_entries(r, cols.begin(), cols.end(), /*indices_are_sorted=*/true);
+    }
+}
+
+template <int dim0, int dim1, int spacedim, typename Matrix>
+void create_coupling_mass_matrix_with_exact_intersections(
+    const DoFHandler<dim0, spacedim> &space_dh, const DoFHandler<dim1, spacedim> &immersed_dh,
+    const std::vector<std::tuple<typename Triangulation<dim0, spacedim>::cell_iterator,
+                                 typename Triangulation<dim1, spacedim>::cell_iterator, Quadrature<spacedim>>> &cells_and_quads,
+    Matrix &matrix, const AffineConstraints<typename Matrix::value_type> &space_constraints, const ComponentMask &space_comps,
+    const ComponentMask &immersed_comps, const Mapping<dim0, spacedim> &space_mapping, const Mapping<dim1, spacedim> &immersed_mapping,
+    const AffineConstraints<typename Matrix::value_type> &immersed_constraints)
+{
+  AssertDimension(matrix.m(), space_dh.n_dofs());
+  AssertDimension(matrix.n(), immersed_dh.n_dofs());
+  Assert((dim1 <= dim0) && (dim0 <= spacedim), ExcMessage("This function can only work if dim1<=dim0<=spacedim"));
+  AssertThrow(space_comps.size() <= 1 && immersed_comps.size() <= 1, ExcNotImplemented());
+
+  auto &s = nmgpu_detail::session(&space_dh.get_triangulation(), &immersed_dh.get_triangulation());
+  if (!s.grids_set)  // the caller built cells_and_quads elsewhere: take the geometry from the mappings given here
+    nmgpu_detail::set_grids<dim0, dim1, spacedim>(s, space_dh.get_triangulation(), space_mapping, immersed_dh.get_triangulation(),
+                                                  immersed_mapping, nullptr, nullptr);
+  nmgpu_detail::set_dofs<dim0, dim1, spacedim>(s, space_dh, immersed_dh, space_constraints, immersed_constraints);
+  nmgpu_detail::assemble_from_info<dim0, dim1, spacedim>(s, cells_and_quads);
+
+  std::uint64_t nnz = 0;
+  nmgpu_detail::check(s, nm_build_sparsity(s.ctx, &nnz));
+  std::vector<std::uint64_t> rowptr(space_dh.n_dofs() + 1);
+  std::vector<std::uint32_t> col(nnz);
+  std::vector<double> val(nnz);
+  nmgpu_detail::check(s, nm_get_csr(s.ctx, 0, rowptr.data(), col.data(), val.data(), NM_HOST));
+  std::vector<types::global_dof_index> cols;
+  std::vector<typename Matrix::value_type> vals;
+  for (types::global_dof_index r = 0; r < space_dh.n_dofs(); ++r)
+    if (rowptr[r + 1] > rowptr[r]) {
+      cols.assign(col.begin() + rowptr[r], col.begin() + rowptr[r + 1]);
+      vals.assign(val.begin() + rowptr[r], val.begin() + rowptr[r + 1]);
+      // zeros are skipped exactly like distribute_local_to_global does (constrained rows stay structural zeros)
+      matrix.add(r, static_cast<types::global_dof_index>(cols.size()), cols.data(), vals.data(), /*elide_zero_values=*/true,
+                 /*col_indices_are_sorted=*/true);
+    }
+  matrix.compress(VectorOperation::add); // reference :289
+}
+
+} // namespace NonMatching
+} // namespace dealii
+
+#endif

@@ -103,6 +103,15 @@ int nm_set_background_boxes(nm_ctx *ctx, int spacedim, uint64_t n_cells, const d
                             const uint32_t *dofs, uint64_t n_dofs, uint64_t n_constrained, const uint32_t *c_dof,
                             const uint64_t *c_ptr, const uint32_t *c_master, const double *c_weight, int where);
 
+/* DoF indices and constraint lines of the background, for callers that learn them after the
+ * geometry (the reference's collect_quadratures_on_overlapped_grids sees only the two
+ * GridTools::Cache objects; the DoFHandlers arrive with the sparsity / matrix calls).  `dofs`
+ * may be NULL in nm_set_background* and nm_set_immersed when these follow.  Results of
+ * nm_intersect stay valid. */
+int nm_set_background_dofs(nm_ctx *ctx, const uint32_t *dofs, uint64_t n_dofs, uint64_t n_constrained, const uint32_t *c_dof,
+                           const uint64_t *c_ptr, const uint32_t *c_master, const double *c_weight, int where);
+int nm_set_immersed_dofs(nm_ctx *ctx, const uint32_t *dofs, uint32_t dofs_per_cell, uint64_t n_dofs, int where);
+
 /* Immersed grid (or this rank's contiguous shard of it) = `immersed_cache` / `immersed_dh`:
  *   verts [n_cells][2^dim][spacedim] deal.II order, dofs [n_cells][dofs_per_cell].
  * Scope: dim = spacedim-1, FE_DGQ(0) (dofs_per_cell == 1, DoFs not shared between cells),

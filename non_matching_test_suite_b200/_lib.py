@@ -23,7 +23,7 @@ PHASES = ["upload", "index", "candidates", "split", "clip", "merge", "transpose"
 
 # every symbol include/nmgpu.h declares
 SYMBOLS = ["nm_version", "nm_create", "nm_destroy", "nm_last_error", "nm_set_background", "nm_set_background_boxes",
-           "nm_set_immersed", "nm_intersect", "nm_get_candidates", "nm_get_pairs", "nm_get_quadrature",
+           "nm_set_background_dofs", "nm_set_immersed_dofs", "nm_set_immersed", "nm_intersect", "nm_get_candidates", "nm_get_pairs", "nm_get_quadrature",
            "nm_get_split_codes", "nm_build_sparsity", "nm_assemble", "nm_assemble_from_quadrature", "nm_get_csr",
            "nm_spmv", "nm_get_timings", "nm_get_launch_count", "nm_device_bytes", "nm_get_stream"]
 
@@ -61,6 +61,8 @@ def load():
     L.nm_set_background.argtypes = [P, I, U64, P, P, U64, U64, P, P, P, P, I]
     L.nm_set_background_boxes.argtypes = [P, I, U64, P, P, P, U64, U64, P, P, P, P, I]
     L.nm_set_immersed.argtypes = [P, I, I, U64, P, P, C.c_uint32, U64, I]
+    L.nm_set_background_dofs.argtypes = [P, P, U64, U64, P, P, P, P, I]
+    L.nm_set_immersed_dofs.argtypes = [P, P, C.c_uint32, U64, I]
     L.nm_intersect.argtypes = [P, C.c_uint, C.c_double, C.POINTER(Counts)]
     L.nm_get_candidates.argtypes = [P, P, P, I]
     L.nm_get_pairs.argtypes = [P, P, P, P, I]
@@ -138,7 +140,7 @@ class Context:
         constraint lines as CSR over ascending c_dof (c_ptr uint64/int64)."""
         n_c = 0 if c_dof is None else int(c_dof.shape[0])
         w = _where(verts, lo, hi, dofs, c_dof, c_ptr, c_master, c_weight)
-        n = int(dofs.shape[0])
+        n = int((verts if verts is not None else lo).shape[0])
         if verts is not None:
             rc = self.L.nm_set_background(self.h, spacedim, n, _ptr(verts)[0], _ptr(dofs)[0], n_dofs, n_c, _ptr(c_dof)[0],
                                           _ptr(c_ptr)[0], _ptr(c_master)[0], _ptr(c_weight)[0], w)
@@ -147,6 +149,17 @@ class Context:
                                                 _ptr(c_dof)[0], _ptr(c_ptr)[0], _ptr(c_master)[0], _ptr(c_weight)[0], w)
         self._chk(rc)
         self.spacedim, self.n_space_dofs = spacedim, n_dofs
+
+    def set_background_dofs(self, dofs, n_dofs, c_dof=None, c_ptr=None, c_master=None, c_weight=None):
+        n_c = 0 if c_dof is None else int(c_dof.shape[0])
+        w = _where(dofs, c_dof, c_ptr, c_master, c_weight)
+        self._chk(self.L.nm_set_background_dofs(self.h, _ptr(dofs)[0], n_dofs, n_c, _ptr(c_dof)[0], _ptr(c_ptr)[0],
+                                                _ptr(c_master)[0], _ptr(c_weight)[0], w))
+        self.n_space_dofs = n_dofs
+
+    def set_immersed_dofs(self, dofs, n_dofs, dofs_per_cell=1):
+        self._chk(self.L.nm_set_immersed_dofs(self.h, _ptr(dofs)[0], dofs_per_cell, n_dofs, _where(dofs)))
+        self.n_im_dofs = n_dofs
 
     def set_immersed(self, dim, spacedim, verts, dofs, n_dofs, dofs_per_cell=1):
         w = _where(verts, dofs)

@@ -143,7 +143,7 @@ static int set_background_common(nm_ctx *ctx, int spacedim, uint64_t n_cells, co
   NM_CUDA(cudaSetDevice(ctx->device));
   if (spacedim != 2 && spacedim != 3) return nm_fail(ctx, NM_ERR_INVALID, "spacedim must be 2 or 3 (got %d)", spacedim);
   if (n_cells >= 0xffffffffULL || n_dofs >= 0xffffffffULL) return nm_fail(ctx, NM_ERR_UNSUPPORTED, "cell / DoF counts must fit 32 bits");
-  if (n_cells && (!dofs || (!verts && (!lo || !hi)))) return nm_fail(ctx, NM_ERR_INVALID, "null background arrays");
+  if (n_cells && !verts && (!lo || !hi)) return nm_fail(ctx, NM_ERR_INVALID, "null background arrays");
   if (n_constrained && (!c_dof || !c_ptr)) return nm_fail(ctx, NM_ERR_INVALID, "null constraint arrays");
   ctx->bg_set = ctx->index_valid = ctx->intersect_valid = ctx->matrix_valid = false;
   const int NV = 1 << spacedim;
@@ -171,8 +171,9 @@ static int set_background_common(nm_ctx *ctx, int spacedim, uint64_t n_cells, co
     }
     NM_TRY(nm_bg_layout(ctx, spacedim, n_cells, nullptr, lo_dev, hi_dev));
   }
-  // dofs + constraint lines
-  NM_TRY(nm_upload(ctx, ctx->bg_dofs, dofs, n_cells * NV * sizeof(uint32_t), where));
+  // dofs + constraint lines (dofs may follow later through nm_set_background_dofs)
+  ctx->bg_dofs_set = dofs != nullptr || n_cells == 0;
+  if (dofs) NM_TRY(nm_upload(ctx, ctx->bg_dofs, dofs, n_cells * NV * sizeof(uint32_t), where));
   uint64_t n_masters = 0;
   if (n_constrained) {
     if (where == NM_HOST) n_masters = c_ptr[n_constrained];
@@ -188,6 +189,60 @@ static int set_background_common(nm_ctx *ctx, int spacedim, uint64_t n_cells, co
   NM_TRY(nm_constraints_layout(ctx));
   tm.stop();
   ctx->bg_set = true;
+  return NM_OK;
+}
+
+static int set_constraints(nm_ctx *ctx, uint64_t n_dofs, uint64_t n_constrained, const uint32_t *c_dof, const uint64_t *c_ptr,
+                           const uint32_t *c_master, const double *c_weight, int where)
+{
+  if (n_constrained && (!c_dof || !c_ptr)) return nm_fail(ctx, NM_ERR_INVALID, "null constraint arrays");
+  ctx->n_space_dofs = n_dofs;
+  ctx->n_constrained = n_constrained;
+  uint64_t n_masters = 0;
+  if (n_constrained) {
+    if (where == NM_HOST) n_masters = c_ptr[n_constrained];
+    else { NM_CUDA(cudaMemcpyAsync(&n_masters, c_ptr + n_constrained, 8, cudaMemcpyDeviceToHost, ctx->stream)); NM_CUDA(cudaStreamSynchronize(ctx->stream)); }
+    if (n_masters && (!c_master || !c_weight)) return nm_fail(ctx, NM_ERR_INVALID, "null constraint master arrays");
+  }
+  ctx->n_cmasters = n_masters;
+  NM_TRY(nm_upload(ctx, ctx->scratch_a, c_dof, n_constrained * sizeof(uint32_t), where));
+  if (n_constrained) NM_TRY(nm_upload(ctx, ctx->c_ptr, c_ptr, (n_constrained + 1) * sizeof(uint64_t), where));
+  else { NM_TRY(nm_ensure(ctx, ctx->c_ptr, 16)); NM_CUDA(cudaMemsetAsync(ctx->c_ptr.p, 0, 16, ctx->stream)); }
+  NM_TRY(nm_upload(ctx, ctx->c_master, c_master, n_masters * sizeof(uint32_t), where));
+  NM_TRY(nm_upload(ctx, ctx->c_weight, c_weight, n_masters * sizeof(double), where));
+  return nm_constraints_layout(ctx);
+}
+
+int nm_set_background_dofs(nm_ctx *ctx, const uint32_t *dofs, uint64_t n_dofs, uint64_t n_constrained, const uint32_t *c_dof,
+                           const uint64_t *c_ptr, const uint32_t *c_master, const double *c_weight, int where)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->bg_set) return nm_fail(ctx, NM_ERR_STATE, "nm_set_background must precede nm_set_background_dofs");
+  if (ctx->n_bg && !dofs) return nm_fail(ctx, NM_ERR_INVALID, "null DoF array");
+  if (n_dofs >= 0xffffffffULL) return nm_fail(ctx, NM_ERR_UNSUPPORTED, "DoF counts must fit 32 bits");
+  ctx->matrix_valid = false;  // intersection results stay valid: they do not depend on the numbering
+  PhaseTimer tm(ctx, NM_T_UPLOAD, true);
+  NM_TRY(nm_upload(ctx, ctx->bg_dofs, dofs, ctx->n_bg * (1u << ctx->spacedim) * sizeof(uint32_t), where));
+  NM_TRY(set_constraints(ctx, n_dofs, n_constrained, c_dof, c_ptr, c_master, c_weight, where));
+  tm.stop();
+  ctx->bg_dofs_set = true;
+  return NM_OK;
+}
+
+int nm_set_immersed_dofs(nm_ctx *ctx, const uint32_t *dofs, uint32_t dofs_per_cell, uint64_t n_dofs, int where)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->im_set) return nm_fail(ctx, NM_ERR_STATE, "nm_set_immersed must precede nm_set_immersed_dofs");
+  if (dofs_per_cell != 1)
+    return nm_fail(ctx, NM_ERR_UNSUPPORTED, "immersed space must be FE_DGQ(0) (1 DoF per cell); got %u DoFs per cell", dofs_per_cell);
+  if (ctx->n_im && !dofs) return nm_fail(ctx, NM_ERR_INVALID, "null DoF array");
+  if (n_dofs >= 0xffffffffULL) return nm_fail(ctx, NM_ERR_UNSUPPORTED, "DoF counts must fit 32 bits");
+  ctx->matrix_valid = false;
+  ctx->n_im_dofs = n_dofs;
+  NM_TRY(nm_upload(ctx, ctx->im_dofs, dofs, ctx->n_im * sizeof(uint32_t), where));
+  ctx->im_dofs_set = true;
   return NM_OK;
 }
 
@@ -220,7 +275,7 @@ int nm_set_immersed(nm_ctx *ctx, int dim, int spacedim, uint64_t n_cells, const 
   if (dofs_per_cell != 1)
     return nm_fail(ctx, NM_ERR_UNSUPPORTED, "immersed space must be FE_DGQ(0) (1 DoF per cell); got %u DoFs per cell", dofs_per_cell);
   if (n_cells >= 0xffffffffULL || n_dofs >= 0xffffffffULL) return nm_fail(ctx, NM_ERR_UNSUPPORTED, "cell / DoF counts must fit 32 bits");
-  if (n_cells && (!verts || !dofs)) return nm_fail(ctx, NM_ERR_INVALID, "null immersed arrays");
+  if (n_cells && !verts) return nm_fail(ctx, NM_ERR_INVALID, "null immersed arrays");
   ctx->im_set = ctx->intersect_valid = ctx->matrix_valid = false;
   PhaseTimer tm(ctx, NM_T_UPLOAD, /*accumulate=*/ctx->bg_set);
   ctx->dim1 = dim;
@@ -229,7 +284,8 @@ int nm_set_immersed(nm_ctx *ctx, int dim, int spacedim, uint64_t n_cells, const 
   if (ctx->bg_set && ctx->spacedim != spacedim) return nm_fail(ctx, NM_ERR_INVALID, "immersed spacedim %d != background spacedim %d", spacedim, ctx->spacedim);
   const int NVI = 1 << dim;
   NM_TRY(nm_upload(ctx, ctx->im_verts, verts, n_cells * NVI * spacedim * sizeof(double), where));
-  NM_TRY(nm_upload(ctx, ctx->im_dofs, dofs, n_cells * sizeof(uint32_t), where));
+  ctx->im_dofs_set = dofs != nullptr || n_cells == 0;
+  if (dofs) NM_TRY(nm_upload(ctx, ctx->im_dofs, dofs, n_cells * sizeof(uint32_t), where));
   tm.stop();
   ctx->im_set = true;
   return NM_OK;
@@ -355,6 +411,8 @@ int nm_get_split_codes(nm_ctx *ctx, uint8_t *codes, int where)
 static int ensure_matrix(nm_ctx *ctx)
 {
   if (!ctx->intersect_valid) return nm_fail(ctx, NM_ERR_STATE, "nm_intersect has not been run");
+  if (!ctx->bg_dofs_set || !ctx->im_dofs_set)
+    return nm_fail(ctx, NM_ERR_STATE, "DoF indices have not been set (nm_set_background_dofs / nm_set_immersed_dofs)");
   if (!ctx->matrix_valid) NM_TRY(nm_matrix_build(ctx));
   return NM_OK;
 }

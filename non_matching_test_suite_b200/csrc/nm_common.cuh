@@ -52,7 +52,7 @@ struct nm_ctx {
   DevBuf c_ptr;     // [n_constrained+1] u64
   DevBuf c_master;  // u32
   DevBuf c_weight;  // f64
-  bool bg_set = false, index_valid = false;
+  bool bg_set = false, bg_dofs_set = false, index_valid = false;
 
   // ---- immersed ----
   int dim1 = 0;
@@ -61,7 +61,7 @@ struct nm_ctx {
   DevBuf im_dofs;     // [n_im] u32
   DevBuf im_split;    // [n_im] u8 (3D)
   DevBuf im_measure;  // [n_im] f64
-  bool im_set = false;
+  bool im_set = false, im_dofs_set = false;
 
   // ---- grid hash ----
   GridIndex gi;

@@ -1,0 +1,102 @@
+// Drives include/coupling_utilities.h (the reference's three entry points, same signatures)
+// against the deal.II stub on grids written by tests/test_gpu_dropin.py; prints what a driver
+// would see: number of pairs, total area, the pattern and the matrix.
+#include <coupling_utilities.h>
+
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+
+using namespace dealii;
+
+template <int dim0, int dim1, int spacedim> int run(std::ifstream &in, const char *out_path)
+{
+  Triangulation<dim0, spacedim> space;
+  Triangulation<dim1, spacedim> immersed;
+  DoFHandler<dim0, spacedim> space_dh;
+  DoFHandler<dim1, spacedim> immersed_dh;
+  AffineConstraints<double> constraints, immersed_constraints;
+  unsigned n_bg, n_im, n_space_dofs, n_im_dofs, n_lines;
+  in >> n_bg >> n_space_dofs;
+  space.cells.resize(n_bg);
+  space_dh.fe.dpc = 1u << dim0;
+  space_dh.table.resize(std::size_t(n_bg) * space_dh.fe.dpc);
+  for (unsigned c = 0; c < n_bg; ++c) {
+    for (unsigned v = 0; v < (1u << dim0); ++v)
+      for (int d = 0; d < spacedim; ++d) in >> space.cells[c][v][d];
+    for (unsigned v = 0; v < (1u << dim0); ++v) in >> space_dh.table[std::size_t(c) * space_dh.fe.dpc + v];
+  }
+  in >> n_lines;
+  for (unsigned l = 0; l < n_lines; ++l) {
+    unsigned dof, nm;
+    in >> dof >> nm;
+    auto &line = constraints.lines[dof];
+    for (unsigned k = 0; k < nm; ++k) {
+      unsigned m; double w;
+      in >> m >> w;
+      line.emplace_back(m, w);
+    }
+  }
+  in >> n_im >> n_im_dofs;
+  immersed.cells.resize(n_im);
+  immersed_dh.fe.dpc = 1;
+  immersed_dh.table.resize(n_im);
+  for (unsigned c = 0; c < n_im; ++c) {
+    for (unsigned v = 0; v < (1u << dim1); ++v)
+      for (int d = 0; d < spacedim; ++d) in >> immersed.cells[c][v][d];
+    in >> immersed_dh.table[c];
+  }
+  space_dh.tria = &space; space_dh.ndofs = n_space_dofs;
+  immersed_dh.tria = &immersed; immersed_dh.ndofs = n_im_dofs;
+  Mapping<dim0, spacedim> space_mapping;
+  Mapping<dim1, spacedim> immersed_mapping;
+  GridTools::Cache<dim0, spacedim> space_cache(space, space_mapping);
+  GridTools::Cache<dim1, spacedim> immersed_cache(immersed, immersed_mapping);
+
+  // the three calls of PoissonLM::run / setup_coupling / assemble_system
+  const auto cells_and_quads = NonMatching::collect_quadratures_on_overlapped_grids(space_cache, immersed_cache, 3, 1e-15);
+  double area = 0;
+  for (const auto &t : cells_and_quads)
+    for (const double w : std::get<2>(t).get_weights()) area += w;
+  DynamicSparsityPattern dsp(n_space_dofs, n_im_dofs);
+  NonMatching::create_coupling_sparsity_pattern_with_exact_intersections(cells_and_quads, space_dh, immersed_dh, dsp, constraints,
+                                                                        ComponentMask(), ComponentMask(), immersed_constraints);
+  StubSparseMatrix<double> matrix(n_space_dofs, n_im_dofs);
+  NonMatching::create_coupling_mass_matrix_with_exact_intersections(space_dh, immersed_dh, cells_and_quads, matrix, constraints,
+                                                                   ComponentMask(), ComponentMask(), space_mapping, immersed_mapping,
+                                                                   immersed_constraints);
+  if (!matrix.compressed) return 3;
+  std::FILE *f = std::fopen(out_path, "w");
+  std::fprintf(f, "%zu %.17g\n", cells_and_quads.size(), area);
+  std::size_t nnz = 0;
+  for (const auto &r : dsp.entries) nnz += r.size();
+  std::fprintf(f, "%zu\n", nnz);
+  for (unsigned r = 0; r < dsp.rows; ++r)
+    for (auto c : dsp.entries[r]) {
+      auto it = matrix.data[r].find(c);
+      std::fprintf(f, "%u %u %.17g\n", r, c, it == matrix.data[r].end() ? 0.0 : it->second);
+    }
+  std::fclose(f);
+  // error behaviour of the reference: AssertThrow(degree > 0)
+  try {
+    NonMatching::collect_quadratures_on_overlapped_grids(space_cache, immersed_cache, 0, 1e-15);
+    return 4;
+  } catch (const std::exception &e) {
+    if (std::string(e.what()).find("Invalid quadrature degree") == std::string::npos) return 5;
+  }
+  return 0;
+}
+
+int main(int argc, char **argv)
+{
+  if (argc < 3) { std::cerr << "usage: test_dropin <grid.txt> <out.txt>\n"; return 2; }
+  std::ifstream in(argv[1]);
+  int spacedim;
+  in >> spacedim;
+  try {
+    return spacedim == 2 ? run<2, 1, 2>(in, argv[2]) : run<3, 2, 3>(in, argv[2]);
+  } catch (const std::exception &e) {
+    std::cerr << "exception: " << e.what() << "\n";
+    return 1;
+  }
+}

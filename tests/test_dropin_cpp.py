@@ -1,0 +1,68 @@
+"""The C++ drop-in header include/coupling_utilities.h (reference signatures over the C ABI).
+
+CPU: it compiles against the deal.II stub (deal.II is not installed here) and links libnmgpu.so.
+GPU: the compiled driver runs the reference's three calls and its matrix is compared with the oracle.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from non_matching_test_suite_b200.grids import make_config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tests", "cpp", "_build", "test_dropin")
+
+
+def build_driver():
+    os.makedirs(os.path.dirname(BIN), exist_ok=True)
+    lib = os.path.join(ROOT, "non_matching_test_suite_b200")
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+           "-I" + os.path.join(ROOT, "tests", "cpp", "stub"), os.path.join(ROOT, "tests", "cpp", "test_dropin.cpp"), "-o", BIN,
+           "-L" + lib, "-lnmgpu", "-Wl,-rpath," + lib]
+    subprocess.check_call(cmd)
+
+
+def write_grid(path, bg, im):
+    d = bg.spacedim
+    V, D = bg.vertices().numpy(), bg.dofs.numpy()
+    with open(path, "w") as f:
+        f.write("%d\n%d %d\n" % (d, bg.n_cells, bg.n_dofs))
+        for c in range(bg.n_cells):
+            f.write(" ".join(repr(float(x)) for x in V[c].ravel()) + " " + " ".join(str(int(x)) for x in D[c]) + "\n")
+        cd, cp, cm, cw = (t.numpy() for t in (bg.c_dof, bg.c_ptr, bg.c_master, bg.c_weight))
+        f.write("%d\n" % len(cd))
+        for i in range(len(cd)):
+            f.write("%d %d " % (cd[i], cp[i + 1] - cp[i]) + " ".join("%d %r" % (cm[k], float(cw[k])) for k in range(cp[i], cp[i + 1])) + "\n")
+        f.write("%d %d\n" % (im.n_cells, im.n_dofs))
+        IV, ID = im.verts.numpy(), im.dofs.numpy()
+        for c in range(im.n_cells):
+            f.write(" ".join(repr(float(x)) for x in IV[c].ravel()) + " %d\n" % ID[c, 0])
+
+
+def test_header_compiles_against_stub():
+    build_driver()
+    assert os.path.exists(BIN)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,cycle", [("disk", 0), ("sphere", 0)])
+def test_cpp_driver_matches_oracle(tmp_path, c_oracle, name, cycle):
+    build_driver()
+    bg, im = make_config(name, cycle, band_only=False)
+    grid, out = str(tmp_path / "grid.txt"), str(tmp_path / "out.txt")
+    write_grid(grid, bg, im)
+    subprocess.check_call([BIN, grid, out])
+    ref = c_oracle.assemble(bg, im, n1d=3, tol=1e-15)
+    lines = open(out).read().split("\n")
+    n_pairs, area = lines[0].split()
+    assert int(n_pairs) == ref["accepted"].shape[0]
+    assert abs(float(area) - ref["sum_w"].sum()) <= 1e-13 * ref["sum_w"].sum()
+    nnz = int(lines[1])
+    assert nnz == ref["col"].shape[0]
+    rows = np.repeat(np.arange(bg.n_dofs), np.diff(ref["rowptr"].astype(np.int64)))
+    got = np.array([[float(x) for x in l.split()] for l in lines[2:2 + nnz]])
+    assert np.array_equal(got[:, 0].astype(np.int64), rows)
+    assert np.array_equal(got[:, 1].astype(np.uint32), ref["col"])
+    assert np.linalg.norm(got[:, 2] - ref["val"]) <= 1e-12 * np.linalg.norm(ref["val"])
