@@ -220,12 +220,17 @@ class Context:
         self._chk(self.L.nm_assemble_from_quadrature(self.h, int(im.shape[0]), _ptr(im)[0], _ptr(bg)[0], _ptr(q_offset)[0],
                                                      _ptr(points)[0], _ptr(weights)[0], w))
 
-    def csr(self, transpose: bool = False, values: bool = True, device="cpu"):
+    def csr(self, transpose: bool = False, values: bool = True, device="cpu", out=None):
+        """CSR of the matrix; `out=(rowptr, col, val)` reuses caller buffers (e.g. pinned host memory)
+        of at least the needed size and returns views of them."""
         nnz = self.build_sparsity()
         n_rows = self.n_im_dofs if transpose else self.n_space_dofs
-        rp = self._out(n_rows + 1, torch.int64, device)
-        col = self._out(nnz, torch.int32, device)
-        val = self._out(nnz, torch.float64, device) if values else None
+        if out is not None:
+            rp, col, val = out[0][:n_rows + 1], out[1][:nnz], (out[2][:nnz] if values and out[2] is not None else None)
+        else:
+            rp = self._out(n_rows + 1, torch.int64, device)
+            col = self._out(nnz, torch.int32, device)
+            val = self._out(nnz, torch.float64, device) if values else None
         self._chk(self.L.nm_get_csr(self.h, int(transpose), _ptr(rp)[0], _ptr(col)[0], _ptr(val)[0], _where(rp)))
         return rp, col, val
 

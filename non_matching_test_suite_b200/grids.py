@@ -336,7 +336,7 @@ def _balance(lvl: torch.Tensor, d: int, l0: int, lf: int) -> torch.Tensor:
 # background grid
 # --------------------------------------------------------------------------- #
 def background_grid(lmap: LevelMap, cycles: int, near: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-                    dirichlet: bool = True) -> BackgroundGrid:
+                    dirichlet: bool = True, key_exchange=None, want_coords: bool = True) -> BackgroundGrid:
     """Leaves of the cycle-0 tree refined uniformly `cycles` times.
 
     near=None       -> every leaf (what the reference holds; small cycles only)
@@ -390,6 +390,9 @@ def background_grid(lmap: LevelMap, cycles: int, near: Optional[Tuple[torch.Tens
         isin = torch.isin(new, all_keys)
         frontier = new[~isin]
         all_keys = torch.unique(torch.cat([all_keys, frontier]))
+    if key_exchange is not None:
+        # several ranks hold different parts of the band: number the union of their vertices
+        all_keys = key_exchange(all_keys)
     n_dofs = int(all_keys.numel())
     dofs = torch.searchsorted(all_keys, vkey).reshape(-1, nv).to(torch.int32)
     con_dof = torch.searchsorted(all_keys, torch.cat(lines_dof))
@@ -397,11 +400,13 @@ def background_grid(lmap: LevelMap, cycles: int, near: Optional[Tuple[torch.Tens
     con_w = torch.cat(lines_w)
     con_dof, con_master, con_w = _resolve_chains(con_dof, con_master, con_w)
 
-    coords = _cell_coord(_unpack(all_keys, d), Lfine)
+    coords = _cell_coord(_unpack(all_keys, d), Lfine) if want_coords else None
     # Dirichlet lines (no masters) on the boundary of [-1,1]^d
     dir_dofs = torch.empty(0, dtype=I64, device=dev)
     if dirichlet:
-        on_b = ((coords == -1.0) | (coords == 1.0)).any(dim=1)
+        ik = _unpack(all_keys, d)
+        on_b = ((ik == 0) | (ik == (1 << Lfine))).any(dim=1)
+        del ik
         dir_dofs = torch.nonzero(on_b).flatten()
         # a hanging node on the boundary keeps its hanging-node line (deal.II: boundary
         # values do not overwrite existing lines)
@@ -555,15 +560,73 @@ def restrict_background(bg: BackgroundGrid, blo: torch.Tensor, bhi: torch.Tensor
                           bg.c_master, bg.c_weight, bg.dof_coords)
 
 
-def shard_problem(name: str, cycle: int, rank: int = 0, world: int = 1, device="cpu"):
-    """This rank's share of config `name` at `cycle`: a contiguous range of immersed cells and the
-    background cells near them, with global DoF numbering."""
-    bg, im = make_config(name, cycle, band_only=True, device=device)
-    info = {"global_background_cells": bg.n_cells, "global_immersed_cells": im.n_cells, "background_dofs": bg.n_dofs}
-    if world > 1:
-        first, last = shard_range(im.n_cells, rank, world)
-        im = im.slice(first, last)
-        blo, bhi = im.boxes()
-        bg = restrict_background(bg, blo, bhi)
-    info.update({"rank0_background_cells": bg.n_cells, "rank0_immersed_cells": im.n_cells})
+def _exchange_keys(local: torch.Tensor) -> torch.Tensor:
+    """Sorted union of every rank's sorted key list (torch.distributed must be initialised)."""
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    n = torch.tensor([local.numel()], dtype=I64, device=local.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    cap = int(max(int(x.item()) for x in sizes))
+    pad = torch.full((cap,), -1, dtype=I64, device=local.device)
+    pad[:local.numel()] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad)
+    parts = [b[:int(k.item())] for b, k in zip(bufs, sizes)]
+    return torch.unique(torch.cat(parts))
+
+
+def weak_scaling_sizes(name: str, cycle: int, world: int) -> Tuple[int, Optional[int]]:
+    """(background cycle, immersed resolution override) such that every rank keeps roughly the
+    single-GPU number of immersed cells: the immersed grid gets `world` times the cells, the
+    background follows with whole refinement levels."""
+    if world == 1:
+        return cycle, None
+    if name == "sphere":
+        n = int(round(4 * (1 << cycle) * math.sqrt(world)))
+        n += n % 2                                    # even: the equator stays a grid line
+        return cycle + int(math.floor(math.log2(n / (4 * (1 << cycle))) + 1e-9)), n
+    if name == "disk":
+        n = 32 * (1 << cycle) * world
+        return cycle + int(math.floor(math.log2(world) + 1e-9)), n
+    k = int(math.floor(math.log2(world) + 1e-9))      # flower: bisections only
+    return cycle + k, cycle + k
+
+
+def shard_problem(name: str, cycle: int, rank: int = 0, world: int = 1, device="cpu", weak: bool = False,
+                  want_coords: bool = True):
+    """This rank's share of config `name`: a contiguous range of immersed cells and the background
+    cells near them, with global DoF numbering.
+
+    weak=False: the global problem is config `name` at `cycle` (strong scaling; every rank generates the
+                whole band and keeps its part).
+    weak=True : the global problem grows with `world` (weak_scaling_sizes); a rank only generates the band
+                near its own immersed cells and the ranks agree on the DoF numbering by exchanging their
+                vertex keys (needs an initialised process group when world > 1)."""
+    if not weak or world == 1:
+        bg, im = make_config(name, cycle, band_only=True, device=device)
+        info = {"global_background_cells": bg.n_cells, "global_immersed_cells": im.n_cells, "background_dofs": bg.n_dofs}
+        if world > 1:
+            first, last = shard_range(im.n_cells, rank, world)
+            im = im.slice(first, last)
+            blo, bhi = im.boxes()
+            bg = restrict_background(bg, blo, bhi)
+        info.update({"rank0_background_cells": bg.n_cells, "rank0_immersed_cells": im.n_cells})
+        return bg, im, info
+    cfg = CONFIGS[name]
+    d = cfg["d"]
+    bg_cycle, n_im = weak_scaling_sizes(name, cycle, world)
+    if name == "disk":
+        im0, im = circle_grid(32, device=device), circle_grid(n_im, device=device)
+    elif name == "flower":
+        im0, im = flower_grid(0, device=device), flower_grid(n_im, device=device)
+    else:
+        im0, im = sphere_grid(2, device=device), sphere_grid(n_im, device=device)
+    n_global = im.n_cells
+    first, last = shard_range(n_global, rank, world)
+    im = ImmersedGrid(im.dim, im.spacedim, im.verts[first:last].clone(), im.dofs[first:last].clone(), im.n_dofs)
+    lmap = build_level_map(d, 4, cfg["band_rounds"], *im0.boxes())
+    bg = background_grid(lmap, bg_cycle, near=im.boxes(), key_exchange=_exchange_keys, want_coords=want_coords)
+    info = {"global_immersed_cells": n_global, "background_dofs": bg.n_dofs, "background_cycle": bg_cycle,
+            "immersed_resolution": n_im, "rank0_background_cells": bg.n_cells, "rank0_immersed_cells": im.n_cells}
     return bg, im, info
