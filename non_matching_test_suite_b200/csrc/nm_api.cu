@@ -64,9 +64,9 @@ int nm_download(nm_ctx *ctx, void *dst, const void *src, size_t bytes, int where
 static void free_all(nm_ctx *c)
 {
   DevBuf *bufs[] = {&c->bg_box, &c->bg_dofs, &c->line_of, &c->c_ptr, &c->c_master, &c->c_weight, &c->im_verts, &c->im_dofs, &c->im_split,
-                    &c->im_measure, &c->idx_keys, &c->idx_keys_alt, &c->idx_vals, &c->idx_vals_alt, &c->idx_hash, &c->idx_tmp, &c->cand_ptr,
+                    &c->im_measure, &c->idx_keys, &c->idx_keys_alt, &c->idx_vals, &c->idx_vals_alt, &c->idx_hash, &c->idx_tmp, &c->cand_ptr, &c->cand_tmp,
                     &c->cand_im, &c->cand_bg, &c->cand_sumw, &c->cand_local, &c->cand_nq, &c->cand_acc, &c->counters, &c->c_rowstart,
-                    &c->c_rowlen, &c->c_col, &c->c_val, &c->a_rowptr, &c->a_col, &c->a_val, &c->a_cursor, &c->scan_tmp, &c->scratch_a,
+                    &c->c_rowlen, &c->c_col, &c->c_val, &c->a_rowptr, &c->a_rowptr32, &c->a_col, &c->a_val, &c->a_cursor, &c->scan_tmp, &c->scratch_a,
                     &c->scratch_b, &c->stage_x, &c->stage_y, &c->h2d_stage};
   for (DevBuf *b : bufs) {
     if (b->p) cudaFree(b->p);
@@ -78,9 +78,9 @@ static void free_all(nm_ctx *c)
 static uint64_t held_bytes(nm_ctx *c)
 {
   DevBuf *bufs[] = {&c->bg_box, &c->bg_dofs, &c->line_of, &c->c_ptr, &c->c_master, &c->c_weight, &c->im_verts, &c->im_dofs, &c->im_split,
-                    &c->im_measure, &c->idx_keys, &c->idx_keys_alt, &c->idx_vals, &c->idx_vals_alt, &c->idx_hash, &c->idx_tmp, &c->cand_ptr,
+                    &c->im_measure, &c->idx_keys, &c->idx_keys_alt, &c->idx_vals, &c->idx_vals_alt, &c->idx_hash, &c->idx_tmp, &c->cand_ptr, &c->cand_tmp,
                     &c->cand_im, &c->cand_bg, &c->cand_sumw, &c->cand_local, &c->cand_nq, &c->cand_acc, &c->counters, &c->c_rowstart,
-                    &c->c_rowlen, &c->c_col, &c->c_val, &c->a_rowptr, &c->a_col, &c->a_val, &c->a_cursor, &c->scan_tmp, &c->scratch_a,
+                    &c->c_rowlen, &c->c_col, &c->c_val, &c->a_rowptr, &c->a_rowptr32, &c->a_col, &c->a_val, &c->a_cursor, &c->scan_tmp, &c->scratch_a,
                     &c->scratch_b, &c->stage_x, &c->stage_y, &c->h2d_stage};
   uint64_t s = 0;
   for (DevBuf *b : bufs) s += b->cap;
@@ -111,6 +111,7 @@ int nm_create(nm_ctx **out, int device)
     return NM_ERR_CUDA;
   }
   { const char *e = getenv("NMGPU_FORCE_QUADRATURE"); ctx->force_quadrature_kernel = e && e[0] == '1'; }
+  { const char *e = getenv("NMGPU_SPMV_VARIANT"); ctx->spmv_variant = e ? atoi(e) : 0; }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   if (nm_ensure(ctx, ctx->counters, 64 * sizeof(uint64_t)) != NM_OK) { delete ctx; return NM_ERR_NOMEM; }

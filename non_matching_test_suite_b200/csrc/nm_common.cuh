@@ -71,6 +71,7 @@ struct nm_ctx {
   unsigned degree = 0;
   double tol = 0;
   nm_counts counts;
+  DevBuf cand_tmp;    // [n_im][CAP] u32: hits of the single probing pass
   DevBuf cand_ptr;    // [n_im+1] u64
   DevBuf cand_im;     // [n_cand] u32
   DevBuf cand_bg;     // [n_cand] u32
@@ -80,6 +81,7 @@ struct nm_ctx {
   DevBuf cand_acc;    // [n_cand] u8: pair accepted (sum of weights > tol)
   DevBuf counters;    // device counters (u64 x 8)
   bool intersect_valid = false;
+  int spmv_variant = 0;                  // NMGPU_SPMV_VARIANT: tuning knob for lanes/unroll (0 = default)
   bool force_quadrature_kernel = false;  // NMGPU_FORCE_QUADRATURE=1: per-point kernel even where moments apply
   bool local_from_user = false;  // cand_local was filled by nm_assemble_from_quadrature
 
@@ -91,6 +93,8 @@ struct nm_ctx {
   DevBuf c_val;       // f64
   uint64_t nnz = 0;
   // stored orientation (rows = space dofs), compact CSR
+  DevBuf a_rowptr32;  // same as u32 when nnz < 2^32
+  bool a_rowptr32_valid = false;
   DevBuf a_rowptr;  // [n_space_dofs+1] u64
   DevBuf a_col;     // u32 (immersed dof)
   DevBuf a_val;     // f64

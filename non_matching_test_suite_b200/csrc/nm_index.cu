@@ -30,7 +30,9 @@ struct GridDev {
   uint32_t level_mask;
   const HashSlot *hash;
   uint32_t hash_mask;
-  const uint32_t *entries;  // background ids, grouped by grid cell
+  const uint32_t *next;     // chain of the entries of one grid cell: next[entry id]
+  const uint32_t *extra_bg; // background id of entry ids >= n_bg (cells spanning several grid cells)
+  uint32_t n_bg;
   int idx_bits;
 };
 
@@ -158,64 +160,69 @@ __device__ inline void bg_range(const GridDev &G, const double *b, int &level, l
   for (int k = D; k < 3; ++k) L[k] = H[k] = 0;
 }
 
+// number of grid cells every background cell registers in (sum -> table size), levels present
 template <int D>
-__global__ void entries_count(GridDev G, uint64_t n, const double *__restrict__ box, uint32_t *__restrict__ cnt,
+__global__ void entries_count(GridDev G, uint64_t n, const double *__restrict__ box, unsigned long long *total,
                               unsigned *level_mask, int *bad)
 {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int level; long long L[3], H[3];
-  bg_range<D>(G, box + i * 8, level, L, H);
-  uint64_t c = 1;
-  const long long lim = 1LL << G.idx_bits;
+  unsigned long long c = 0;
+  unsigned bit = 0;
+  if (i < n) {
+    int level; long long L[3], H[3];
+    bg_range<D>(G, box + i * 8, level, L, H);
+    c = 1;
+    const long long lim = 1LL << G.idx_bits;
+    bool ok = true;
 #pragma unroll
-  for (int k = 0; k < D; ++k) {
-    c *= (uint64_t)(H[k] - L[k] + 1);
-    if (L[k] < 0 || H[k] >= lim) atomicAdd(bad, 1);
+    for (int k = 0; k < D; ++k) {
+      c *= (unsigned long long)(H[k] - L[k] + 1);
+      ok &= L[k] >= 0 && H[k] < lim;
+    }
+    if (!ok || c > 64) { atomicAdd(bad, 1); c = 0; }
+    bit = 1u << level;
   }
-  if (c > 64) { atomicAdd(bad, 1); c = 0; }
-  cnt[i] = (uint32_t)c;
-  atomicOr(level_mask, 1u << level);
-}
-
-template <int D>
-__global__ void entries_fill(GridDev G, uint64_t n, const double *__restrict__ box, const uint64_t *__restrict__ off,
-                             unsigned long long *__restrict__ keys, uint32_t *__restrict__ vals)
-{
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int level; long long L[3], H[3];
-  bg_range<D>(G, box + i * 8, level, L, H);
-  uint64_t o = off[i];
-  for (long long z = L[2]; z <= H[2]; ++z)
-    for (long long y = L[1]; y <= H[1]; ++y)
-      for (long long x = L[0]; x <= H[0]; ++x) {
-        keys[o] = pack_key(D, level, x, y, z);
-        vals[o] = (uint32_t)i;
-        ++o;
-      }
+  // one atomic per warp
+  c = __reduce_add_sync(0xffffffffu, (unsigned)c);
+  bit = __reduce_or_sync(0xffffffffu, bit);
+  if ((threadIdx.x & 31) == 0 && c) { atomicAdd(total, c); atomicOr(level_mask, bit); }
 }
 
 __global__ void hash_clear(HashSlot *h, uint32_t cap)
 {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < cap) { h[i].key = ~0ULL; h[i].start = 0; h[i].count = 0; }
+  if (i < cap) { h[i].key = ~0ULL; h[i].start = 0xffffffffu; h[i].count = 1; }  // count of a claimed slot starts at 1
 }
 
-__global__ void hash_insert_runs(uint32_t n, const unsigned long long *__restrict__ keys, HashSlot *h, uint32_t mask)
+// Every background cell links itself into the slot of each grid cell it covers.  Entry id = the
+// cell id for its first grid cell (the only one for a grid-aligned tree), ids >= n_bg for the rest.
+// HashSlot.start is the head of the chain, HashSlot.count its length.
+template <int D>
+__global__ void index_insert(GridDev G, uint64_t n, const double *__restrict__ box, HashSlot *h, uint32_t *__restrict__ next,
+                             uint32_t *__restrict__ extra_bg, unsigned *extra_cursor)
 {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  unsigned long long k = keys[i];
-  if (i > 0 && keys[i - 1] == k) return;
-  uint32_t e = i + 1;
-  while (e < n && keys[e] == k) ++e;
-  uint32_t s = (uint32_t)mix64(k) & mask;
-  while (true) {
-    unsigned long long old = atomicCAS(&h[s].key, ~0ULL, k);
-    if (old == ~0ULL) { h[s].start = i; h[s].count = e - i; return; }
-    s = (s + 1) & mask;
-  }
+  int level; long long L[3], H[3];
+  bg_range<D>(G, box + i * 8, level, L, H);
+  bool first = true;
+  for (long long z = L[2]; z <= H[2]; ++z)
+    for (long long y = L[1]; y <= H[1]; ++y)
+      for (long long x = L[0]; x <= H[0]; ++x) {
+        uint32_t e = (uint32_t)i;
+        if (!first) { const unsigned k = atomicAdd(extra_cursor, 1u); extra_bg[k] = (uint32_t)i; e = G.n_bg + k; }
+        first = false;
+        const unsigned long long key = pack_key(D, level, x, y, z);
+        uint32_t s = (uint32_t)mix64(key) & G.hash_mask;
+        while (true) {
+          const unsigned long long old = atomicCAS(&h[s].key, ~0ULL, key);
+          if (old == ~0ULL || old == key) break;
+          s = (s + 1) & G.hash_mask;
+        }
+        const uint32_t prev = atomicExch(&h[s].start, e);
+        next[e] = prev;
+        if (prev != 0xffffffffu) atomicAdd(&h[s].count, 1u);  // the first entry is already counted
+      }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -246,16 +253,17 @@ __device__ inline void query_box(const GridDev &G, const double *__restrict__ bg
         for (long long x = L[0]; x <= H[0]; ++x) {
           const unsigned long long key = pack_key(D, level, x, y, z);
           uint32_t s = (uint32_t)mix64(key) & G.hash_mask;
-          uint32_t start = 0, count = 0;
+          uint32_t e = 0, count = 0;
           while (true) {
             const unsigned long long k = G.hash[s].key;
-            if (k == key) { start = G.hash[s].start; count = G.hash[s].count; break; }
+            if (k == key) { e = G.hash[s].start; count = G.hash[s].count; break; }
             if (k == ~0ULL) break;
             s = (s + 1) & G.hash_mask;
           }
           const long long cell[3] = {x, y, z};
-          for (uint32_t e = 0; e < count; ++e) {
-            const uint32_t b = G.entries[start + e];
+          for (uint32_t c = 0; c < count; ++c) {
+            const uint32_t b = e < G.n_bg ? e : G.extra_bg[e - G.n_bg];
+            if (c + 1 < count) e = G.next[e];
             const double *bb = bg_box + (uint64_t)b * 8;
             bool hit = true;
 #pragma unroll
@@ -284,9 +292,11 @@ __device__ inline void im_box(const double *__restrict__ v, double *lo, double *
     for (int k = 0; k < D; ++k) { lo[k] = fmin(lo[k], v[q * D + k]); hi[k] = fmax(hi[k], v[q * D + k]); }
 }
 
-template <int D>
-__global__ void cand_count(GridDev G, uint64_t n_im, const double *__restrict__ im_verts, const double *__restrict__ bg_box,
-                           uint32_t *__restrict__ cnt)
+// Single probing pass: hits go, insertion-sorted, to a fixed-capacity row per immersed cell;
+// the true count is recorded even when it exceeds the capacity.
+template <int D, int CAP>
+__global__ void cand_probe(GridDev G, uint64_t n_im, const double *__restrict__ im_verts, const double *__restrict__ bg_box,
+                           uint32_t *__restrict__ cnt, uint32_t *__restrict__ tmp)
 {
   uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= n_im) return;
@@ -294,22 +304,41 @@ __global__ void cand_count(GridDev G, uint64_t n_im, const double *__restrict__ 
   double lo[3], hi[3];
   im_box<D, NVI>(im_verts + m * NVI * D, lo, hi);
   uint32_t c = 0;
-  query_box<D>(G, bg_box, lo, hi, [&](uint32_t) { ++c; });
+  uint32_t *row = tmp + m * CAP;
+  query_box<D>(G, bg_box, lo, hi, [&](uint32_t b) {
+    if (c < CAP) {
+      uint32_t j = c;
+      while (j > 0 && row[j - 1] > b) { row[j] = row[j - 1]; --j; }
+      row[j] = b;
+    }
+    ++c;
+  });
   cnt[m] = c;
 }
 
-template <int D>
-__global__ void cand_fill(GridDev G, uint64_t n_im, const double *__restrict__ im_verts, const double *__restrict__ bg_box,
-                          const uint64_t *__restrict__ ptr, uint32_t *__restrict__ cand_im, uint32_t *__restrict__ cand_bg)
+// Second pass: copy the rows to their final place (LANES threads per cell); cells that
+// overflowed the capacity are probed again (rare).
+template <int D, int CAP, int LANES>
+__global__ void cand_place(GridDev G, uint64_t n_im, const double *__restrict__ im_verts, const double *__restrict__ bg_box,
+                           const uint64_t *__restrict__ ptr, const uint32_t *__restrict__ tmp, uint32_t *__restrict__ cand_im,
+                           uint32_t *__restrict__ cand_bg)
 {
-  uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t m = t / LANES;
+  const unsigned l = t % LANES;
   if (m >= n_im) return;
+  const uint64_t p0 = ptr[m];
+  const uint32_t n = (uint32_t)(ptr[m + 1] - p0);
+  if (n <= CAP) {
+    const uint32_t *row = tmp + m * CAP;
+    for (uint32_t k = l; k < n; k += LANES) { cand_bg[p0 + k] = row[k]; cand_im[p0 + k] = (uint32_t)m; }
+    return;
+  }
+  if (l != 0) return;
   constexpr int NVI = 1 << (D - 1);
   double lo[3], hi[3];
   im_box<D, NVI>(im_verts + m * NVI * D, lo, hi);
-  const uint64_t p0 = ptr[m];
   uint64_t p = p0;
-  // insertion into the (short) sorted run of this immersed cell: output ordered by (im, bg)
   query_box<D>(G, bg_box, lo, hi, [&](uint32_t b) {
     uint64_t j = p;
     while (j > p0 && cand_bg[j - 1] > b) { cand_bg[j] = cand_bg[j - 1]; --j; }
@@ -406,7 +435,9 @@ static GridDev make_grid_dev(const nm_ctx *ctx)
   G.level_mask = ctx->gi.level_mask;
   G.hash = ctx->idx_hash.as<HashSlot>();
   G.hash_mask = ctx->gi.hash_cap - 1;
-  G.entries = ctx->idx_vals.as<uint32_t>();
+  G.next = ctx->idx_vals.as<uint32_t>();
+  G.extra_bg = ctx->idx_vals_alt.as<uint32_t>();
+  G.n_bg = (uint32_t)ctx->n_bg;
   G.idx_bits = ctx->gi.d == 2 ? 29 : 19;
   return G;
 }
@@ -449,73 +480,59 @@ int nm_index_build(nm_ctx *ctx)
                      "background spans more than 2^%d finest cells along axis %d (extent %g, finest cell %g)", bits, k,
                      top[k] - org[k], g0);
 
-  // 2. entries: count, scan, fill
+  // 2. size of the table: number of (cell, grid cell) registrations
   GridDev G = make_grid_dev(ctx);
-  NM_TRY(nm_ensure(ctx, ctx->scratch_a, n * sizeof(uint32_t)));
-  NM_TRY(nm_ensure(ctx, ctx->scratch_b, (n + 1) * sizeof(uint64_t)));
   NM_TRY(nm_ensure(ctx, ctx->counters, 64 * sizeof(uint64_t)));
-  unsigned *lmask = ctx->counters.as<unsigned>() + 2;
   int *bad = ctx->counters.as<int>();
+  unsigned *lmask = ctx->counters.as<unsigned>() + 2;
+  unsigned *extra_cursor = ctx->counters.as<unsigned>() + 3;
+  unsigned long long *total = ctx->counters.as<unsigned long long>() + 2;
   NM_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 64, ctx->stream));
   const unsigned T = 256, B = nm_blocks(n, T);
-  if (d == 2) entries_count<2><<<B, T, 0, NM_LS(ctx)>>>(G, n, ctx->bg_box.as<double>(), ctx->scratch_a.as<uint32_t>(), lmask, bad);
-  else entries_count<3><<<B, T, 0, NM_LS(ctx)>>>(G, n, ctx->bg_box.as<double>(), ctx->scratch_a.as<uint32_t>(), lmask, bad);
+  if (d == 2) entries_count<2><<<B, T, 0, NM_LS(ctx)>>>(G, n, ctx->bg_box.as<double>(), total, lmask, bad);
+  else entries_count<3><<<B, T, 0, NM_LS(ctx)>>>(G, n, ctx->bg_box.as<double>(), total, lmask, bad);
   NM_CUDA(cudaGetLastError());
-  NM_TRY(nm_exclusive_scan_u32_to_u64(ctx, ctx->scratch_a.as<uint32_t>(), ctx->scratch_b.as<uint64_t>(), n));
-  uint64_t last_off = 0; uint32_t last_cnt = 0; unsigned h_hdr[4];
-  NM_CUDA(cudaMemcpyAsync(&last_off, ctx->scratch_b.as<uint64_t>() + (n - 1), 8, cudaMemcpyDeviceToHost, ctx->stream));
-  NM_CUDA(cudaMemcpyAsync(&last_cnt, ctx->scratch_a.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
+  unsigned long long h_hdr[3];
   NM_CUDA(cudaMemcpyAsync(h_hdr, ctx->counters.p, sizeof(h_hdr), cudaMemcpyDeviceToHost, ctx->stream));
   NM_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (h_hdr[0]) return nm_fail(ctx, NM_ERR_UNSUPPORTED, "background cells outside the indexable grid range");
-  const uint64_t ne = last_off + last_cnt;
-  if (ne >= 0xffffffffULL) return nm_fail(ctx, NM_ERR_UNSUPPORTED, "grid index needs %llu entries (limit 2^32)", (unsigned long long)ne);
-  ctx->gi.level_mask = h_hdr[2];
+  if ((unsigned)(h_hdr[0] & 0xffffffffu)) return nm_fail(ctx, NM_ERR_UNSUPPORTED, "background cells outside the indexable grid range");
+  const uint64_t ne = h_hdr[2];
+  if (ne >= 0x7fffffffULL) return nm_fail(ctx, NM_ERR_UNSUPPORTED, "grid index needs %llu entries (limit 2^31)", (unsigned long long)ne);
+  ctx->gi.level_mask = (unsigned)(h_hdr[1] & 0xffffffffu);
   ctx->gi.n_entries = (uint32_t)ne;
-  NM_TRY(nm_ensure(ctx, ctx->idx_keys, ne * 8));
-  NM_TRY(nm_ensure(ctx, ctx->idx_keys_alt, ne * 8));
-  NM_TRY(nm_ensure(ctx, ctx->idx_vals, ne * 4));
-  NM_TRY(nm_ensure(ctx, ctx->idx_vals_alt, ne * 4));
-  if (d == 2) entries_fill<2><<<B, T, 0, NM_LS(ctx)>>>(G, n, ctx->bg_box.as<double>(), ctx->scratch_b.as<uint64_t>(),
-                                                       ctx->idx_keys_alt.as<unsigned long long>(), ctx->idx_vals_alt.as<uint32_t>());
-  else entries_fill<3><<<B, T, 0, NM_LS(ctx)>>>(G, n, ctx->bg_box.as<double>(), ctx->scratch_b.as<uint64_t>(),
-                                                 ctx->idx_keys_alt.as<unsigned long long>(), ctx->idx_vals_alt.as<uint32_t>());
-  NM_CUDA(cudaGetLastError());
-  // 3. sort by grid cell (stable: background ids stay ascending inside a cell)
-  size_t bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, ctx->idx_keys_alt.as<unsigned long long>(), ctx->idx_keys.as<unsigned long long>(),
-                                  ctx->idx_vals_alt.as<uint32_t>(), ctx->idx_vals.as<uint32_t>(), (int64_t)ne, 0, 63, ctx->stream);
-  NM_TRY(nm_ensure(ctx, ctx->scan_tmp, bytes));
-  NM_CUDA(cub::DeviceRadixSort::SortPairs(ctx->scan_tmp.p, bytes, ctx->idx_keys_alt.as<unsigned long long>(),
-                                          ctx->idx_keys.as<unsigned long long>(), ctx->idx_vals_alt.as<uint32_t>(),
-                                          ctx->idx_vals.as<uint32_t>(), (int64_t)ne, 0, 63, ctx->stream));
-  // 4. hash: occupied grid cell -> run of entries
+  // 3. hash: occupied grid cell -> chain of background cells
   uint32_t cap = 64;
   while (cap < 2 * ne) cap <<= 1;
   ctx->gi.hash_cap = cap;
   NM_TRY(nm_ensure(ctx, ctx->idx_hash, (size_t)cap * sizeof(HashSlot)));
+  NM_TRY(nm_ensure(ctx, ctx->idx_vals, (ne + 1) * 4));
+  NM_TRY(nm_ensure(ctx, ctx->idx_vals_alt, (ne - n + 1) * 4));
+  G = make_grid_dev(ctx);
   hash_clear<<<nm_blocks(cap, 256), 256, 0, NM_LS(ctx)>>>(ctx->idx_hash.as<HashSlot>(), cap);
-  hash_insert_runs<<<nm_blocks(ne, 256), 256, 0, NM_LS(ctx)>>>((uint32_t)ne, ctx->idx_keys.as<unsigned long long>(),
-                                                                ctx->idx_hash.as<HashSlot>(), cap - 1);
+  if (d == 2) index_insert<2><<<B, T, 0, NM_LS(ctx)>>>(G, n, ctx->bg_box.as<double>(), ctx->idx_hash.as<HashSlot>(), ctx->idx_vals.as<uint32_t>(),
+                                                      ctx->idx_vals_alt.as<uint32_t>(), extra_cursor);
+  else index_insert<3><<<B, T, 0, NM_LS(ctx)>>>(G, n, ctx->bg_box.as<double>(), ctx->idx_hash.as<HashSlot>(), ctx->idx_vals.as<uint32_t>(),
+                                                ctx->idx_vals_alt.as<uint32_t>(), extra_cursor);
   NM_CUDA(cudaGetLastError());
   ctx->index_valid = true;
   return NM_OK;
 }
 
-int nm_candidates_run(nm_ctx *ctx)
+template <int D, int CAP>
+static int candidates_run_t(nm_ctx *ctx)
 {
-  const int d = ctx->spacedim;
   const uint64_t n_im = ctx->n_im;
   GridDev G = make_grid_dev(ctx);
   NM_TRY(nm_ensure(ctx, ctx->scratch_a, (n_im + 1) * sizeof(uint32_t)));
   NM_TRY(nm_ensure(ctx, ctx->cand_ptr, (n_im + 1) * sizeof(uint64_t)));
+  NM_TRY(nm_ensure(ctx, ctx->cand_tmp, (n_im + 1) * CAP * sizeof(uint32_t)));
   ctx->counts.n_candidates = 0;
   if (n_im == 0) { NM_CUDA(cudaMemsetAsync(ctx->cand_ptr.p, 0, 8, ctx->stream)); return NM_OK; }
   const unsigned T = 128, B = nm_blocks(n_im, T);
   NM_CUDA(cudaMemsetAsync(ctx->scratch_a.as<uint32_t>() + n_im, 0, 4, ctx->stream));
   KernelTimer kc(ctx, NM_T_K_CAND_COUNT);
-  if (d == 2) cand_count<2><<<B, T, 0, NM_LS(ctx)>>>(G, n_im, ctx->im_verts.as<double>(), ctx->bg_box.as<double>(), ctx->scratch_a.as<uint32_t>());
-  else cand_count<3><<<B, T, 0, NM_LS(ctx)>>>(G, n_im, ctx->im_verts.as<double>(), ctx->bg_box.as<double>(), ctx->scratch_a.as<uint32_t>());
+  cand_probe<D, CAP><<<B, T, 0, NM_LS(ctx)>>>(G, n_im, ctx->im_verts.as<double>(), ctx->bg_box.as<double>(), ctx->scratch_a.as<uint32_t>(),
+                                             ctx->cand_tmp.as<uint32_t>());
   kc.stop();
   NM_CUDA(cudaGetLastError());
   NM_TRY(nm_exclusive_scan_u32_to_u64(ctx, ctx->scratch_a.as<uint32_t>(), ctx->cand_ptr.as<uint64_t>(), n_im + 1));
@@ -526,12 +543,14 @@ int nm_candidates_run(nm_ctx *ctx)
   ctx->counts.n_candidates = n_cand;
   NM_TRY(nm_ensure(ctx, ctx->cand_im, (n_cand + 1) * 4));
   NM_TRY(nm_ensure(ctx, ctx->cand_bg, (n_cand + 1) * 4));
+  constexpr int LANES = 8;
   KernelTimer kf(ctx, NM_T_K_CAND_FILL);
-  if (d == 2) cand_fill<2><<<B, T, 0, NM_LS(ctx)>>>(G, n_im, ctx->im_verts.as<double>(), ctx->bg_box.as<double>(), ctx->cand_ptr.as<uint64_t>(),
-                                                    ctx->cand_im.as<uint32_t>(), ctx->cand_bg.as<uint32_t>());
-  else cand_fill<3><<<B, T, 0, NM_LS(ctx)>>>(G, n_im, ctx->im_verts.as<double>(), ctx->bg_box.as<double>(), ctx->cand_ptr.as<uint64_t>(),
-                                              ctx->cand_im.as<uint32_t>(), ctx->cand_bg.as<uint32_t>());
+  cand_place<D, CAP, LANES><<<nm_blocks(n_im * LANES, 256), 256, 0, NM_LS(ctx)>>>(G, n_im, ctx->im_verts.as<double>(), ctx->bg_box.as<double>(),
+                                                                                ctx->cand_ptr.as<uint64_t>(), ctx->cand_tmp.as<uint32_t>(),
+                                                                                ctx->cand_im.as<uint32_t>(), ctx->cand_bg.as<uint32_t>());
   kf.stop();
   NM_CUDA(cudaGetLastError());
   return NM_OK;
 }
+
+int nm_candidates_run(nm_ctx *ctx) { return ctx->spacedim == 2 ? candidates_run_t<2, 16>(ctx) : candidates_run_t<3, 40>(ctx); }

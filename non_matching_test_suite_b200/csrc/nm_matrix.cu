@@ -350,12 +350,41 @@ __global__ void t_scatter(uint64_t n_im, const uint64_t *__restrict__ rowstart, 
   }
 }
 
-// columns ascending in every row (rows are short: a space dof meets a handful of immersed cells)
+// columns ascending in every row.  Rows are short (a space dof meets a handful of immersed
+// cells): up to 8 entries are sorted in registers with a fixed network, longer rows in place.
+__device__ inline void cswap(uint32_t &ka, double &va, uint32_t &kb, double &vb)
+{
+  const bool sw = ka > kb;
+  const uint32_t k = sw ? kb : ka, K = sw ? ka : kb;
+  const double v = sw ? vb : va, V = sw ? va : vb;
+  ka = k; kb = K; va = v; vb = V;
+}
+
 __global__ void t_sort_rows(uint64_t n_rows, const uint64_t *__restrict__ rowptr, uint32_t *__restrict__ col, double *__restrict__ val)
 {
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_rows) return;
   const uint64_t s = rowptr[r], e = rowptr[r + 1];
+  const uint64_t n = e - s;
+  if (n <= 1) return;
+  if (n <= 8) {
+    uint32_t k[8];
+    double v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const bool ok = (uint64_t)i < n; k[i] = ok ? col[s + i] : 0xffffffffu; v[i] = ok ? val[s + i] : 0.0; }
+    // 19-comparator network for 8 keys
+    cswap(k[0], v[0], k[1], v[1]); cswap(k[2], v[2], k[3], v[3]); cswap(k[4], v[4], k[5], v[5]); cswap(k[6], v[6], k[7], v[7]);
+    cswap(k[0], v[0], k[2], v[2]); cswap(k[1], v[1], k[3], v[3]); cswap(k[4], v[4], k[6], v[6]); cswap(k[5], v[5], k[7], v[7]);
+    cswap(k[1], v[1], k[2], v[2]); cswap(k[5], v[5], k[6], v[6]); cswap(k[0], v[0], k[4], v[4]); cswap(k[3], v[3], k[7], v[7]);
+    cswap(k[1], v[1], k[5], v[5]); cswap(k[2], v[2], k[6], v[6]);
+    cswap(k[1], v[1], k[4], v[4]); cswap(k[3], v[3], k[6], v[6]);
+    cswap(k[2], v[2], k[4], v[4]); cswap(k[3], v[3], k[5], v[5]);
+    cswap(k[3], v[3], k[4], v[4]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if ((uint64_t)i < n) { col[s + i] = k[i]; val[s + i] = v[i]; }
+    return;
+  }
   for (uint64_t i = s + 1; i < e; ++i) {
     const uint32_t c = col[i];
     const double v = val[i];
@@ -366,27 +395,50 @@ __global__ void t_sort_rows(uint64_t n_rows, const uint64_t *__restrict__ rowptr
 }
 
 // ---------------------------------------------------------------------------------------
-// SpMV: LANES threads per row, FP64, shuffle reduction
+// SpMV: LANES threads per row, FP64, shuffle reduction.  Each lane issues UNROLL independent
+// (col, val, x[col]) load chains before the first FMA: with rows of 3..40 entries the kernels are
+// bound by memory-level parallelism, not by arithmetic.
 // ---------------------------------------------------------------------------------------
-template <int LANES>
-__global__ void __launch_bounds__(256) spmv_csr(uint64_t n_rows, const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col,
+template <int LANES, int UNROLL>
+__device__ inline double row_dot(const uint32_t *__restrict__ col, const double *__restrict__ val, const double *__restrict__ x,
+                                 uint64_t b, uint64_t e, unsigned l)
+{
+  double s = 0.0;
+  for (uint64_t k0 = b + l; k0 < e; k0 += (uint64_t)LANES * UNROLL) {
+    uint32_t c[UNROLL];
+    double v[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const uint64_t k = k0 + (uint64_t)u * LANES;
+      const bool ok = k < e;
+      c[u] = ok ? col[k] : 0u;
+      v[u] = ok ? val[k] : 0.0;
+    }
+    double xv[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) xv[u] = __ldg(x + c[u]);
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) s = fma(v[u], xv[u], s);
+  }
+  return s;
+}
+
+template <int LANES, int UNROLL, typename PTR>
+__global__ void __launch_bounds__(256) spmv_csr(uint64_t n_rows, const PTR *__restrict__ rowptr, const uint32_t *__restrict__ col,
                                                 const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y)
 {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t r = t / LANES;
   const unsigned l = threadIdx.x % LANES;
   double s = 0.0;
-  if (r < n_rows) {
-    const uint64_t b = rowptr[r], e = rowptr[r + 1];
-    for (uint64_t k = b + l; k < e; k += LANES) s += val[k] * __ldg(x + col[k]);
-  }
+  if (r < n_rows) s = row_dot<LANES, UNROLL>(col, val, x, rowptr[r], rowptr[r + 1], l);
 #pragma unroll
   for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, LANES);
   if (r < n_rows && l == 0) y[r] = s;
 }
 
 // rows of C: (start, len) storage, result scattered to the immersed dof of the cell
-template <int LANES>
+template <int LANES, int UNROLL>
 __global__ void __launch_bounds__(256) spmv_crows(uint64_t n_im, const uint64_t *__restrict__ rowstart, const uint32_t *__restrict__ rowlen,
                                                   const uint32_t *__restrict__ col, const double *__restrict__ val,
                                                   const uint32_t *__restrict__ im_dofs, const double *__restrict__ x, double *__restrict__ y)
@@ -397,8 +449,7 @@ __global__ void __launch_bounds__(256) spmv_crows(uint64_t n_im, const uint64_t 
   double s = 0.0;
   if (r < n_im) {
     const uint64_t b = rowstart[r];
-    const uint32_t n = rowlen[r];
-    for (uint32_t k = l; k < n; k += LANES) s += val[b + k] * __ldg(x + col[b + k]);
+    s = row_dot<LANES, UNROLL>(col, val, x, b, b + rowlen[r], l);
   }
 #pragma unroll
   for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, LANES);
@@ -410,6 +461,12 @@ __global__ void __attribute__((unused)) rowlen_to_u64(uint64_t n, const uint32_t
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = len[i];
   if (i == n) out[i] = 0;
+}
+
+__global__ void narrow_rowptr(uint64_t n, const uint64_t *__restrict__ in, uint32_t *__restrict__ out)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint32_t)in[i];
 }
 
 // compact copy of C's rows (for nm_get_csr(transpose = 1)): row index = immersed dof
@@ -532,6 +589,14 @@ static int matrix_build_t(nm_ctx *ctx)
     t_sort_rows<<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr.as<uint64_t>(), ctx->a_col.as<uint32_t>(), ctx->a_val.as<double>());
     NM_CUDA(cudaGetLastError());
   }
+  // 32-bit row offsets for the SpMV when they fit (halves the row-pointer traffic)
+  ctx->a_rowptr32_valid = false;
+  if (nnz < 0xffffffffULL) {
+    NM_TRY(nm_ensure(ctx, ctx->a_rowptr32, (n_rows + 2) * sizeof(uint32_t)));
+    narrow_rowptr<<<nm_blocks(n_rows + 1, 256), 256, 0, NM_LS(ctx)>>>(n_rows + 1, ctx->a_rowptr.as<uint64_t>(), ctx->a_rowptr32.as<uint32_t>());
+    NM_CUDA(cudaGetLastError());
+    ctx->a_rowptr32_valid = true;
+  }
   tt.stop();
   ctx->matrix_valid = true;
   return NM_OK;
@@ -545,18 +610,37 @@ int nm_spmv_run(nm_ctx *ctx, int transpose, const double *x, double *y)
   PhaseTimer tm(ctx, transpose ? NM_T_SPMV_T : NM_T_SPMV);
   if (!transpose) {
     const double avg = n_rows ? (double)ctx->nnz / (double)n_rows : 0;
+    const uint64_t *rp = ctx->a_rowptr.as<uint64_t>();
+    const uint32_t *cl = ctx->a_col.as<uint32_t>();
+    const double *vl = ctx->a_val.as<double>();
     if (n_rows) {
-      if (avg > 12) spmv_csr<8><<<nm_blocks(n_rows * 8, 256), 256, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr.as<uint64_t>(), ctx->a_col.as<uint32_t>(), ctx->a_val.as<double>(), x, y);
-      else if (avg > 5) spmv_csr<4><<<nm_blocks(n_rows * 4, 256), 256, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr.as<uint64_t>(), ctx->a_col.as<uint32_t>(), ctx->a_val.as<double>(), x, y);
-      else spmv_csr<2><<<nm_blocks(n_rows * 2, 256), 256, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr.as<uint64_t>(), ctx->a_col.as<uint32_t>(), ctx->a_val.as<double>(), x, y);
+      if (avg > 24) spmv_csr<8, 4, uint64_t><<<nm_blocks(n_rows * 8, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y);
+      else if (avg > 8) spmv_csr<4, 4, uint64_t><<<nm_blocks(n_rows * 4, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y);
+      else if (ctx->spmv_variant / 10 == 1) spmv_csr<1, 4, uint64_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y);
+      else if (ctx->spmv_variant / 10 == 2) spmv_csr<2, 2, uint64_t><<<nm_blocks(n_rows * 2, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y);
+      else if (ctx->spmv_variant / 10 == 3) spmv_csr<1, 8, uint64_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y);
+      else if (ctx->spmv_variant / 10 == 4) spmv_csr<1, 3, uint64_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y);
+      else if (ctx->spmv_variant / 10 == 5) spmv_csr<1, 2, uint64_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y);
+      else if (ctx->a_rowptr32_valid) spmv_csr<1, 8, uint32_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr32.as<uint32_t>(), cl, vl, x, y);
+      else spmv_csr<1, 8, uint64_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y);
     }
   } else {
     NM_CUDA(cudaMemsetAsync(y, 0, ctx->n_im_dofs * sizeof(double), ctx->stream));
     const double avg = n_im ? (double)ctx->nnz / (double)n_im : 0;
+    const uint64_t *rs = ctx->c_rowstart.as<uint64_t>();
+    const uint32_t *rl = ctx->c_rowlen.as<uint32_t>(), *cl = ctx->c_col.as<uint32_t>(), *idf = ctx->im_dofs.as<uint32_t>();
+    const double *vl = ctx->c_val.as<double>();
     if (n_im) {
-      if (avg > 24) spmv_crows<16><<<nm_blocks(n_im * 16, 256), 256, 0, NM_LS(ctx)>>>(n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(), ctx->c_val.as<double>(), ctx->im_dofs.as<uint32_t>(), x, y);
-      else if (avg > 10) spmv_crows<8><<<nm_blocks(n_im * 8, 256), 256, 0, NM_LS(ctx)>>>(n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(), ctx->c_val.as<double>(), ctx->im_dofs.as<uint32_t>(), x, y);
-      else spmv_crows<4><<<nm_blocks(n_im * 4, 256), 256, 0, NM_LS(ctx)>>>(n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(), ctx->c_val.as<double>(), ctx->im_dofs.as<uint32_t>(), x, y);
+      const int cv = ctx->spmv_variant % 10;
+      if (avg > 20 && cv == 1) spmv_crows<8, 4><<<nm_blocks(n_im * 8, 256), 256, 0, NM_LS(ctx)>>>(n_im, rs, rl, cl, vl, idf, x, y);
+      else if (avg > 20 && cv == 2) spmv_crows<2, 8><<<nm_blocks(n_im * 2, 256), 256, 0, NM_LS(ctx)>>>(n_im, rs, rl, cl, vl, idf, x, y);
+      else if (avg > 20 && cv == 3) spmv_crows<4, 8><<<nm_blocks(n_im * 4, 256), 256, 0, NM_LS(ctx)>>>(n_im, rs, rl, cl, vl, idf, x, y);
+      else if (avg > 20 && cv == 4) spmv_crows<2, 4><<<nm_blocks(n_im * 2, 256), 256, 0, NM_LS(ctx)>>>(n_im, rs, rl, cl, vl, idf, x, y);
+      else if (avg > 20 && cv == 5) spmv_crows<1, 8><<<nm_blocks(n_im, 256), 256, 0, NM_LS(ctx)>>>(n_im, rs, rl, cl, vl, idf, x, y);
+      else if (avg > 20 && cv == 6) spmv_crows<4, 4><<<nm_blocks(n_im * 4, 256), 256, 0, NM_LS(ctx)>>>(n_im, rs, rl, cl, vl, idf, x, y);
+      else if (avg > 20) spmv_crows<4, 8><<<nm_blocks(n_im * 4, 256), 256, 0, NM_LS(ctx)>>>(n_im, rs, rl, cl, vl, idf, x, y);
+      else if (avg > 6) spmv_crows<4, 2><<<nm_blocks(n_im * 4, 256), 256, 0, NM_LS(ctx)>>>(n_im, rs, rl, cl, vl, idf, x, y);
+      else spmv_crows<2, 2><<<nm_blocks(n_im * 2, 256), 256, 0, NM_LS(ctx)>>>(n_im, rs, rl, cl, vl, idf, x, y);
     }
   }
   NM_CUDA(cudaGetLastError());
