@@ -494,46 +494,128 @@ struct ItemOut {
   unsigned nfan, dropped;
 };
 
+// Stage-2 work of one (candidate, triangle) item.
+//
+// The polygon is never copied: vertices live in a pool (3 originals + at most 2 per plane <= 15,
+// local memory), the polygon itself is a list of 4-bit pool indices packed in one 64-bit register,
+// and every pool vertex carries, per plane, one "inside" bit computed when the vertex is created
+// (Cohen-Sutherland outcodes, kept plane-major in 96 bits of registers).  Clipping against a plane
+// is then register work (gather the bits of the polygon's vertices, find the inside run, splice the
+// index list) plus at most two edge/plane crossings, which are the only memory traffic.
+struct VPool {
+  double c[3][16];
+};
+
+__device__ inline unsigned plane_bits(unsigned long long ma, unsigned mb, int p)
+{
+  return p < 4 ? (unsigned)(ma >> (16 * p)) & 0xffffu : (mb >> (16 * (p - 4))) & 0xffffu;
+}
+
+// inside bits of a new vertex (x,y,z) for the planes after `p_done` (all six if p_done < 0)
+__device__ inline void set_outcode(unsigned long long &ma, unsigned &mb, int v, double x, double y, double z, const double *H, int p_done)
+{
+  const bool in[6] = {x >= 0.0, x <= H[0], y >= 0.0, y <= H[1], z >= 0.0, z <= H[2]};
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    const bool on = in[q] || q <= p_done;   // planes already applied (and the creating plane) count as inside
+    if (q < 4) ma |= (unsigned long long)(on ? 1u : 0u) << (16 * q + v);
+    else mb |= (on ? 1u : 0u) << (16 * (q - 4) + v);
+  }
+}
+
 __device__ inline void item_clip_moments(const double *__restrict__ box, const double *__restrict__ quad, int t, double tol, ItemOut &o)
 {
   const double lo[3] = {box[0], box[1], box[2]};
   const double H[3] = {box[4] - lo[0], box[5] - lo[1], box[6] - lo[2]};
   const int iv[3] = {t == 0 ? 1 : 0, t <= 1 ? 2 : 1, t <= 2 ? 3 : 2};
-  PolyC P[2];
-  P[0].n = 3;
+  VPool P;
+  unsigned long long ma = 0;
+  unsigned mb = 0;
 #pragma unroll
-  for (int v = 0; v < 3; ++v)
-#pragma unroll
-    for (int k = 0; k < 3; ++k) P[0].c[k][v] = quad[iv[v] * 3 + k] - lo[k];
+  for (int v = 0; v < 3; ++v) {
+    const double x = quad[iv[v] * 3 + 0] - lo[0], y = quad[iv[v] * 3 + 1] - lo[1], z = quad[iv[v] * 3 + 2] - lo[2];
+    P.c[0][v] = x; P.c[1][v] = y; P.c[2][v] = z;
+    set_outcode(ma, mb, v, x, y, z, H, -1);
+  }
   // unit normal of the parent triangle: J of a coplanar sub-triangle = |cross . n|
   double nx, ny, nz;
   {
-    const double e1[3] = {P[0].c[0][1] - P[0].c[0][0], P[0].c[1][1] - P[0].c[1][0], P[0].c[2][1] - P[0].c[2][0]};
-    const double e2[3] = {P[0].c[0][2] - P[0].c[0][0], P[0].c[1][2] - P[0].c[1][0], P[0].c[2][2] - P[0].c[2][0]};
+    const double e1[3] = {P.c[0][1] - P.c[0][0], P.c[1][1] - P.c[1][0], P.c[2][1] - P.c[2][0]};
+    const double e2[3] = {P.c[0][2] - P.c[0][0], P.c[1][2] - P.c[1][0], P.c[2][2] - P.c[2][0]};
     nx = e1[1] * e2[2] - e1[2] * e2[1]; ny = e1[2] * e2[0] - e1[0] * e2[2]; nz = e1[0] * e2[1] - e1[1] * e2[0];
     const double n2 = nx * nx + ny * ny + nz * nz;
     if (!(n2 > 0.0)) return;
     const double inv = rsqrt(n2);
     nx *= inv; ny *= inv; nz *= inv;
   }
-  int cur = 0;
+  unsigned long long poly = 0x210ULL;  // pool indices, 4 bits each, first vertex in the low nibble
+  int n = 3, nv = 3;
 #pragma unroll 1
-  for (int plane = 0; plane < 6; ++plane) {
-    const int axis = plane >> 1;
-    const bool upper = plane & 1;
-    if (clip_convex(P[cur], P[cur ^ 1], axis, upper, upper ? H[axis] : 0.0)) {
-      cur ^= 1;
-      if (P[cur].n < 3) return;
+  for (int p = 0; p < 6; ++p) {
+    const unsigned bits = plane_bits(ma, mb, p);
+    unsigned inside = 0;
+    for (int i = 0; i < n; ++i) inside |= ((bits >> ((unsigned)(poly >> (4 * i)) & 15u)) & 1u) << i;
+    const unsigned full = (1u << n) - 1u;
+    if (inside == full) continue;
+    if (inside == 0u) return;
+    const int axis = p >> 1;
+    const double sgn = (p & 1) ? -1.0 : 1.0, bound = (p & 1) ? H[axis] : 0.0;
+    const unsigned prev = ((inside << 1) | (inside >> (n - 1))) & full;
+    const int s = __ffs(inside & ~prev) - 1;                                // run start
+    const unsigned rot = ((inside >> s) | (inside << (n - s))) & full;
+    const int len = __ffs(~rot) - 1;                                        // run length (< n)
+    const unsigned long long cyc = (poly >> (4 * s)) | (poly << (4 * (n - s)));  // list rotated so that the run comes first
+    unsigned long long np = 0;
+    int m = 0;
+    {  // entering edge: last outside vertex -> first inside vertex
+      const int vp = (int)((poly >> (4 * (s == 0 ? n - 1 : s - 1))) & 15u), vq = (int)(cyc & 15u);
+      const double dp = sgn * (P.c[axis][vp] - bound), dq = sgn * (P.c[axis][vq] - bound);
+      if (dq > 0.0) {
+        const double tt = dp * __drcp_rn(dp - dq);
+        double x[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) x[k] = P.c[k][vp] + tt * (P.c[k][vq] - P.c[k][vp]);
+        x[axis] = bound;  // on the plane by construction
+#pragma unroll
+        for (int k = 0; k < 3; ++k) P.c[k][nv] = x[k];
+        set_outcode(ma, mb, nv, x[0], x[1], x[2], H, p);
+        np = (unsigned long long)nv;
+        m = 1;
+        ++nv;
+      }
     }
+    np |= (cyc & ((1ULL << (4 * len)) - 1ULL)) << (4 * m);
+    m += len;
+    {  // leaving edge: last inside vertex -> first outside vertex
+      const int vp = (int)((cyc >> (4 * (len - 1))) & 15u), vq = (int)((cyc >> (4 * len)) & 15u);
+      const double dp = sgn * (P.c[axis][vp] - bound), dq = sgn * (P.c[axis][vq] - bound);
+      if (dp > 0.0) {
+        const double tt = dp * __drcp_rn(dp - dq);
+        double x[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) x[k] = P.c[k][vp] + tt * (P.c[k][vq] - P.c[k][vp]);
+        x[axis] = bound;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) P.c[k][nv] = x[k];
+        set_outcode(ma, mb, nv, x[0], x[1], x[2], H, p);
+        np |= (unsigned long long)nv << (4 * m);
+        ++m;
+        ++nv;
+      }
+    }
+    poly = np;
+    n = m;
+    if (n < 3) return;
   }
-  const PolyC &A = P[cur];
   const double ih[3] = {__drcp_rn(H[0]), __drcp_rn(H[1]), __drcp_rn(H[2])};
-  const double ax = A.c[0][0], ay = A.c[1][0], az = A.c[2][0];
+  const int v0 = (int)(poly & 15u), v1 = (int)((poly >> 4) & 15u);
+  const double ax = P.c[0][v0], ay = P.c[1][v0], az = P.c[2][v0];
   const double f0 = ax * ih[0], g0 = ay * ih[1], h0 = az * ih[2];
-  double px = A.c[0][1], py = A.c[1][1], pz = A.c[2][1];
+  double px = P.c[0][v1], py = P.c[1][v1], pz = P.c[2][v1];
   double f1 = px * ih[0], g1 = py * ih[1], h1 = pz * ih[2];
-  for (int j = 2; j < A.n; ++j) {
-    const double qx = A.c[0][j], qy = A.c[1][j], qz = A.c[2][j];
+  for (int j = 2; j < n; ++j) {
+    const int vj = (int)((poly >> (4 * j)) & 15u);
+    const double qx = P.c[0][vj], qy = P.c[1][vj], qz = P.c[2][vj];
     const double f2 = qx * ih[0], g2 = qy * ih[1], h2 = qz * ih[2];
     const double e1x = px - ax, e1y = py - ay, e1z = pz - az, e2x = qx - ax, e2y = qy - ay, e2z = qz - az;
     const double J = fabs((e1y * e2z - e1z * e2y) * nx + (e1z * e2x - e1x * e2z) * ny + (e1x * e2y - e1y * e2x) * nz);
