@@ -256,25 +256,28 @@ __device__ inline bool tri_box_overlap(const double (*v)[3], const double *H)
     const double r = h[0] * fabs(nx) + h[1] * fabs(ny) + h[2] * fabs(nz);
     sep |= fabs(d) > r;
   }
+  // axes e_i x f_j: the two end points of edge j project to the same value, so two projections
+  // (edge start, opposite vertex) bound the triangle
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
+    const int ia = j, ib = (j + 2) % 3;
     {  // e_x x f_j = (0, -fz, fy)
       const double a = -f[j][2], b = f[j][1];
-      const double q0 = a * p[0][1] + b * p[0][2], q1 = a * p[1][1] + b * p[1][2], q2 = a * p[2][1] + b * p[2][2];
+      const double q0 = a * p[ia][1] + b * p[ia][2], q1 = a * p[ib][1] + b * p[ib][2];
       const double r = h[1] * fabs(a) + h[2] * fabs(b);
-      sep |= fmin(q0, fmin(q1, q2)) > r || fmax(q0, fmax(q1, q2)) < -r;
+      sep |= fmin(q0, q1) > r || fmax(q0, q1) < -r;
     }
     {  // e_y x f_j = (fz, 0, -fx)
       const double a = f[j][2], b = -f[j][0];
-      const double q0 = a * p[0][0] + b * p[0][2], q1 = a * p[1][0] + b * p[1][2], q2 = a * p[2][0] + b * p[2][2];
+      const double q0 = a * p[ia][0] + b * p[ia][2], q1 = a * p[ib][0] + b * p[ib][2];
       const double r = h[0] * fabs(a) + h[2] * fabs(b);
-      sep |= fmin(q0, fmin(q1, q2)) > r || fmax(q0, fmax(q1, q2)) < -r;
+      sep |= fmin(q0, q1) > r || fmax(q0, q1) < -r;
     }
     {  // e_z x f_j = (-fy, fx, 0)
       const double a = -f[j][1], b = f[j][0];
-      const double q0 = a * p[0][0] + b * p[0][1], q1 = a * p[1][0] + b * p[1][1], q2 = a * p[2][0] + b * p[2][1];
+      const double q0 = a * p[ia][0] + b * p[ia][1], q1 = a * p[ib][0] + b * p[ib][1];
       const double r = h[0] * fabs(a) + h[1] * fabs(b);
-      sep |= fmin(q0, fmin(q1, q2)) > r || fmax(q0, fmax(q1, q2)) < -r;
+      sep |= fmin(q0, q1) > r || fmax(q0, q1) < -r;
     }
   }
   return !sep;
@@ -497,30 +500,20 @@ struct ItemOut {
 // Stage-2 work of one (candidate, triangle) item.
 //
 // The polygon is never copied: vertices live in a pool (3 originals + at most 2 per plane <= 15,
-// local memory), the polygon itself is a list of 4-bit pool indices packed in one 64-bit register,
-// and every pool vertex carries, per plane, one "inside" bit computed when the vertex is created
-// (Cohen-Sutherland outcodes, kept plane-major in 96 bits of registers).  Clipping against a plane
-// is then register work (gather the bits of the polygon's vertices, find the inside run, splice the
-// index list) plus at most two edge/plane crossings, which are the only memory traffic.
+// local memory); the polygon is a list of 4-bit pool indices packed in one 64-bit register, and a
+// second register holds, position by position, the 6-bit Cohen-Sutherland outcode of each vertex
+// (one "inside" bit per box plane, computed once when the vertex is created).  Classifying the
+// polygon against a plane is a mask of that register, the inside run is found with ffs on the
+// strided bits, and the new polygon is spliced with shifts -- no loop over vertices and no memory
+// traffic except for the (at most two) edge/plane crossings.
 struct VPool {
   double c[3][16];
 };
 
-__device__ inline unsigned plane_bits(unsigned long long ma, unsigned mb, int p)
+__device__ inline unsigned outcode(double x, double y, double z, const double *H)
 {
-  return p < 4 ? (unsigned)(ma >> (16 * p)) & 0xffffu : (mb >> (16 * (p - 4))) & 0xffffu;
-}
-
-// inside bits of a new vertex (x,y,z) for the planes after `p_done` (all six if p_done < 0)
-__device__ inline void set_outcode(unsigned long long &ma, unsigned &mb, int v, double x, double y, double z, const double *H, int p_done)
-{
-  const bool in[6] = {x >= 0.0, x <= H[0], y >= 0.0, y <= H[1], z >= 0.0, z <= H[2]};
-#pragma unroll
-  for (int q = 0; q < 6; ++q) {
-    const bool on = in[q] || q <= p_done;   // planes already applied (and the creating plane) count as inside
-    if (q < 4) ma |= (unsigned long long)(on ? 1u : 0u) << (16 * q + v);
-    else mb |= (on ? 1u : 0u) << (16 * (q - 4) + v);
-  }
+  return (x >= 0.0 ? 1u : 0u) | (x <= H[0] ? 2u : 0u) | (y >= 0.0 ? 4u : 0u) | (y <= H[1] ? 8u : 0u) | (z >= 0.0 ? 16u : 0u) |
+         (z <= H[2] ? 32u : 0u);
 }
 
 __device__ inline void item_clip_moments(const double *__restrict__ box, const double *__restrict__ quad, int t, double tol, ItemOut &o)
@@ -529,13 +522,12 @@ __device__ inline void item_clip_moments(const double *__restrict__ box, const d
   const double H[3] = {box[4] - lo[0], box[5] - lo[1], box[6] - lo[2]};
   const int iv[3] = {t == 0 ? 1 : 0, t <= 1 ? 2 : 1, t <= 2 ? 3 : 2};
   VPool P;
-  unsigned long long ma = 0;
-  unsigned mb = 0;
+  unsigned long long code = 0;         // 6 bits per polygon position
 #pragma unroll
   for (int v = 0; v < 3; ++v) {
     const double x = quad[iv[v] * 3 + 0] - lo[0], y = quad[iv[v] * 3 + 1] - lo[1], z = quad[iv[v] * 3 + 2] - lo[2];
     P.c[0][v] = x; P.c[1][v] = y; P.c[2][v] = z;
-    set_outcode(ma, mb, v, x, y, z, H, -1);
+    code |= (unsigned long long)outcode(x, y, z, H) << (6 * v);
   }
   // unit normal of the parent triangle: J of a coplanar sub-triangle = |cross . n|
   double nx, ny, nz;
@@ -548,27 +540,31 @@ __device__ inline void item_clip_moments(const double *__restrict__ box, const d
     const double inv = rsqrt(n2);
     nx *= inv; ny *= inv; nz *= inv;
   }
-  unsigned long long poly = 0x210ULL;  // pool indices, 4 bits each, first vertex in the low nibble
+  unsigned long long poly = 0x210ULL;  // pool indices, 4 bits per polygon position
   int n = 3, nv = 3;
+  constexpr unsigned long long M6 = 0x0041041041041041ULL;  // bit 0 of every 6-bit group
 #pragma unroll 1
   for (int p = 0; p < 6; ++p) {
-    const unsigned bits = plane_bits(ma, mb, p);
-    unsigned inside = 0;
-    for (int i = 0; i < n; ++i) inside |= ((bits >> ((unsigned)(poly >> (4 * i)) & 15u)) & 1u) << i;
-    const unsigned full = (1u << n) - 1u;
-    if (inside == full) continue;
-    if (inside == 0u) return;
+    const unsigned long long full6 = M6 & ((1ULL << (6 * n)) - 1ULL);
+    const unsigned long long in6 = (code >> p) & full6;
+    if (in6 == full6) continue;
+    if (in6 == 0ULL) return;
     const int axis = p >> 1;
     const double sgn = (p & 1) ? -1.0 : 1.0, bound = (p & 1) ? H[axis] : 0.0;
-    const unsigned prev = ((inside << 1) | (inside >> (n - 1))) & full;
-    const int s = __ffs(inside & ~prev) - 1;                                // run start
-    const unsigned rot = ((inside >> s) | (inside << (n - s))) & full;
-    const int len = __ffs(~rot) - 1;                                        // run length (< n)
-    const unsigned long long cyc = (poly >> (4 * s)) | (poly << (4 * (n - s)));  // list rotated so that the run comes first
-    unsigned long long np = 0;
+    const unsigned long long prev6 = ((in6 << 6) | (in6 >> (6 * (n - 1)))) & full6;       // position i: vertex i-1 inside
+    const int s6 = __ffsll((long long)(in6 & ~prev6)) - 1;                                  // run start (bit index)
+    const int s = __popcll(M6 & ((1ULL << s6) - 1ULL));
+    const unsigned long long rot6 = ((in6 >> s6) | (in6 << (6 * n - s6))) & full6;
+    const int l6 = __ffsll((long long)(~rot6 & full6)) - 1;                                 // run length (bit index), < 6n
+    const int len = __popcll(M6 & ((1ULL << l6) - 1ULL));
+    // both lists rotated so that the run comes first
+    const unsigned long long pr = (poly >> (4 * s)) | (poly << (4 * (n - s)));
+    const unsigned long long cr = (code >> s6) | (code << (6 * n - s6));
+    const unsigned forced = (2u << p) - 1u;   // planes already applied count as inside for a new vertex
+    unsigned long long np = 0, nc = 0;
     int m = 0;
     {  // entering edge: last outside vertex -> first inside vertex
-      const int vp = (int)((poly >> (4 * (s == 0 ? n - 1 : s - 1))) & 15u), vq = (int)(cyc & 15u);
+      const int vp = (int)((poly >> (4 * (s == 0 ? n - 1 : s - 1))) & 15u), vq = (int)(pr & 15u);
       const double dp = sgn * (P.c[axis][vp] - bound), dq = sgn * (P.c[axis][vq] - bound);
       if (dq > 0.0) {
         const double tt = dp * __drcp_rn(dp - dq);
@@ -578,16 +574,17 @@ __device__ inline void item_clip_moments(const double *__restrict__ box, const d
         x[axis] = bound;  // on the plane by construction
 #pragma unroll
         for (int k = 0; k < 3; ++k) P.c[k][nv] = x[k];
-        set_outcode(ma, mb, nv, x[0], x[1], x[2], H, p);
         np = (unsigned long long)nv;
+        nc = (unsigned long long)(outcode(x[0], x[1], x[2], H) | forced);
         m = 1;
         ++nv;
       }
     }
-    np |= (cyc & ((1ULL << (4 * len)) - 1ULL)) << (4 * m);
+    np |= (pr & ((1ULL << (4 * len)) - 1ULL)) << (4 * m);
+    nc |= (cr & ((1ULL << (6 * len)) - 1ULL)) << (6 * m);
     m += len;
     {  // leaving edge: last inside vertex -> first outside vertex
-      const int vp = (int)((cyc >> (4 * (len - 1))) & 15u), vq = (int)((cyc >> (4 * len)) & 15u);
+      const int vp = (int)((pr >> (4 * (len - 1))) & 15u), vq = (int)((pr >> (4 * len)) & 15u);
       const double dp = sgn * (P.c[axis][vp] - bound), dq = sgn * (P.c[axis][vq] - bound);
       if (dp > 0.0) {
         const double tt = dp * __drcp_rn(dp - dq);
@@ -597,13 +594,14 @@ __device__ inline void item_clip_moments(const double *__restrict__ box, const d
         x[axis] = bound;
 #pragma unroll
         for (int k = 0; k < 3; ++k) P.c[k][nv] = x[k];
-        set_outcode(ma, mb, nv, x[0], x[1], x[2], H, p);
         np |= (unsigned long long)nv << (4 * m);
+        nc |= (unsigned long long)(outcode(x[0], x[1], x[2], H) | forced) << (6 * m);
         ++m;
         ++nv;
       }
     }
     poly = np;
+    code = nc;
     n = m;
     if (n < 3) return;
   }
