@@ -294,7 +294,7 @@ def run_native(args):
     if os.path.exists(traffic_file):
         try:
             tj = json.load(open(traffic_file))
-            roofline["traffic"] = tj.get("clip_local_kernel_bytes_per_candidate", 0) * n_cand or None
+            roofline["traffic"] = tj.get("clip_kernel_dram_bytes_per_candidate", 0) * n_cand or None
             roofline["traffic_source"] = tj.get("source")
         except Exception:
             pass

@@ -111,6 +111,7 @@ int nm_create(nm_ctx **out, int device)
     return NM_ERR_CUDA;
   }
   { const char *e = getenv("NMGPU_FORCE_QUADRATURE"); ctx->force_quadrature_kernel = e && e[0] == '1'; }
+  { const char *e = getenv("NMGPU_FORCE_GENERAL_MERGE"); ctx->force_general_merge = e && e[0] == '1'; }
   { const char *e = getenv("NMGPU_SPMV_VARIANT"); ctx->spmv_variant = e ? atoi(e) : 0; }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;

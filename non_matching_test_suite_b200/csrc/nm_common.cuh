@@ -82,6 +82,7 @@ struct nm_ctx {
   DevBuf counters;    // device counters (u64 x 8)
   bool intersect_valid = false;
   int spmv_variant = 0;                  // NMGPU_SPMV_VARIANT: tuning knob for lanes/unroll (0 = default)
+  bool force_general_merge = false;      // NMGPU_FORCE_GENERAL_MERGE=1: skip the single-pass merge (testing)
   bool force_quadrature_kernel = false;  // NMGPU_FORCE_QUADRATURE=1: per-point kernel even where moments apply
   bool local_from_user = false;  // cand_local was filled by nm_assemble_from_quadrature
 

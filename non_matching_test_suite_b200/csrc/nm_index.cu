@@ -160,18 +160,18 @@ __device__ inline void bg_range(const GridDev &G, const double *b, int &level, l
   for (int k = D; k < 3; ++k) L[k] = H[k] = 0;
 }
 
-// number of grid cells every background cell registers in (sum -> table size), levels present
+// number of grid cells every background cell registers in (sum -> table size), levels present.
+// Grid-stride with one atomic per block: a single counter cannot take an atomic per warp.
 template <int D>
 __global__ void entries_count(GridDev G, uint64_t n, const double *__restrict__ box, unsigned long long *total,
                               unsigned *level_mask, int *bad)
 {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned long long c = 0;
-  unsigned bit = 0;
-  if (i < n) {
+  unsigned long long c_sum = 0;
+  unsigned bits = 0, n_bad = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     int level; long long L[3], H[3];
     bg_range<D>(G, box + i * 8, level, L, H);
-    c = 1;
+    unsigned long long c = 1;
     const long long lim = 1LL << G.idx_bits;
     bool ok = true;
 #pragma unroll
@@ -179,13 +179,25 @@ __global__ void entries_count(GridDev G, uint64_t n, const double *__restrict__ 
       c *= (unsigned long long)(H[k] - L[k] + 1);
       ok &= L[k] >= 0 && H[k] < lim;
     }
-    if (!ok || c > 64) { atomicAdd(bad, 1); c = 0; }
-    bit = 1u << level;
+    if (!ok || c > 64) { ++n_bad; c = 0; }
+    c_sum += c;
+    bits |= 1u << level;
   }
-  // one atomic per warp
-  c = __reduce_add_sync(0xffffffffu, (unsigned)c);
-  bit = __reduce_or_sync(0xffffffffu, bit);
-  if ((threadIdx.x & 31) == 0 && c) { atomicAdd(total, c); atomicOr(level_mask, bit); }
+  typedef cub::BlockReduce<unsigned long long, 256> BR;
+  __shared__ typename BR::TempStorage tmp;
+  __shared__ unsigned s_bits, s_bad;
+  if (threadIdx.x == 0) { s_bits = 0; s_bad = 0; }
+  __syncthreads();
+  const unsigned long long tot = BR(tmp).Sum(c_sum);
+  bits = __reduce_or_sync(0xffffffffu, bits);
+  n_bad = __reduce_add_sync(0xffffffffu, n_bad);
+  if ((threadIdx.x & 31) == 0) { atomicOr(&s_bits, bits); if (n_bad) atomicAdd(&s_bad, n_bad); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (tot) atomicAdd(total, tot);
+    if (s_bits) atomicOr(level_mask, s_bits);
+    if (s_bad) atomicAdd(bad, (int)s_bad);
+  }
 }
 
 __global__ void hash_clear(HashSlot *h, uint32_t cap)
@@ -454,7 +466,7 @@ int nm_index_build(nm_ctx *ctx)
     hash_clear<<<1, 32, 0, NM_LS(ctx)>>>(ctx->idx_hash.as<HashSlot>(), 1);
     return NM_OK; }
   // 1. origin and level-0 spacing
-  const unsigned SB = 256;
+  const unsigned SB = 1184;  // 8 blocks per SM
   NM_TRY(nm_ensure(ctx, ctx->idx_tmp, SB * 8 * sizeof(double)));
   if (d == 2) bg_stats<2><<<SB, 256, 0, NM_LS(ctx)>>>(n, ctx->bg_box.as<double>(), ctx->idx_tmp.as<double>());
   else bg_stats<3><<<SB, 256, 0, NM_LS(ctx)>>>(n, ctx->bg_box.as<double>(), ctx->idx_tmp.as<double>());
@@ -489,8 +501,9 @@ int nm_index_build(nm_ctx *ctx)
   unsigned long long *total = ctx->counters.as<unsigned long long>() + 2;
   NM_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 64, ctx->stream));
   const unsigned T = 256, B = nm_blocks(n, T);
-  if (d == 2) entries_count<2><<<B, T, 0, NM_LS(ctx)>>>(G, n, ctx->bg_box.as<double>(), total, lmask, bad);
-  else entries_count<3><<<B, T, 0, NM_LS(ctx)>>>(G, n, ctx->bg_box.as<double>(), total, lmask, bad);
+  const unsigned GB = (unsigned)(B < (unsigned)ctx->sm_count * 8u ? B : (unsigned)ctx->sm_count * 8u);
+  if (d == 2) entries_count<2><<<GB, T, 0, NM_LS(ctx)>>>(G, n, ctx->bg_box.as<double>(), total, lmask, bad);
+  else entries_count<3><<<GB, T, 0, NM_LS(ctx)>>>(G, n, ctx->bg_box.as<double>(), total, lmask, bad);
   NM_CUDA(cudaGetLastError());
   unsigned long long h_hdr[3];
   NM_CUDA(cudaMemcpyAsync(h_hdr, ctx->counters.p, sizeof(h_hdr), cudaMemcpyDeviceToHost, ctx->stream));

@@ -279,6 +279,136 @@ __global__ void __launch_bounds__(256) merge_rows_hash(uint64_t n_im, const uint
   if (lane == 0) rowlen[m] = D;
 }
 
+// Fast path used first: a warp merges FAST_ROWS consecutive immersed cells and carves their rows out
+// of chunks it takes from a global cursor, so C comes out compact without a capacity pass, and the
+// per-row counts of the transposed matrix are accumulated on the way.  Anything it cannot handle
+// (more than HASH_CAP distinct dofs in a cell, storage overflow) raises a flag and the general
+// two-pass path below redoes the whole matrix.
+constexpr int FAST_ROWS = 16;
+constexpr unsigned FAST_CHUNK = 2048;
+
+template <int NL>
+__global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint64_t *__restrict__ cand_ptr,
+                                                       const uint32_t *__restrict__ cand_bg, const uint8_t *__restrict__ acc,
+                                                       const double *__restrict__ local, const uint32_t *__restrict__ bg_dofs,
+                                                       const int32_t *__restrict__ line_of, const uint64_t *__restrict__ c_ptr,
+                                                       const uint32_t *__restrict__ c_master, const double *__restrict__ c_weight,
+                                                       uint64_t *__restrict__ rowstart, uint32_t *__restrict__ rowlen,
+                                                       uint32_t *__restrict__ out_col, double *__restrict__ out_val, uint64_t capacity,
+                                                       unsigned long long *cursor, unsigned *problem, uint32_t *__restrict__ a_cnt)
+{
+  __shared__ unsigned s_keys[8][HASH_SLOTS];
+  __shared__ double s_vals[8][HASH_SLOTS];
+  __shared__ unsigned s_list[8][HASH_SLOTS];
+  __shared__ unsigned s_dkey[8][HASH_SLOTS];
+  const unsigned w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned *keys = s_keys[w];
+  double *vals = s_vals[w];
+  unsigned *list = s_list[w];
+  unsigned *dkey = s_dkey[w];
+  const uint64_t m0 = ((uint64_t)blockIdx.x * 8 + w) * FAST_ROWS;
+  uint64_t chunk_pos = 0;
+  unsigned chunk_left = 0;
+  for (uint64_t m = m0; m < m0 + FAST_ROWS && m < n_im; ++m) {
+#pragma unroll
+    for (int k = 0; k < HASH_SLOTS / 32; ++k) { keys[lane + 32 * k] = HASH_EMPTY; vals[lane + 32 * k] = 0.0; }
+    __syncwarp();
+    const uint64_t p0 = cand_ptr[m], p1 = cand_ptr[m + 1];
+    unsigned claimed = 0;
+    bool failed = false;   // table full: bounded probing gives up instead of spinning
+    for (uint64_t base = p0; base < p1; base += 32) {
+      const uint64_t p = base + lane;
+      const bool on = p < p1 && acc[p];
+      uint32_t dofs[NL];
+      double v[NL];
+      if (on) {
+        const uint32_t *dp = bg_dofs + (uint64_t)cand_bg[p] * NL;
+        const double *lp = local + p * NL;
+#pragma unroll
+        for (int i = 0; i < NL; ++i) { dofs[i] = dp[i]; v[i] = lp[i]; }
+      }
+#pragma unroll
+      for (int i = 0; i < NL; ++i) {
+        if (on && !failed) {
+          const int32_t ln = line_of[dofs[i]];
+          unsigned s = (dofs[i] * 2654435761u) >> 24;
+          int probes = 0;
+          while (true) {
+            const unsigned old = atomicCAS(&keys[s], HASH_EMPTY, dofs[i]);
+            if (old == HASH_EMPTY) { ++claimed; break; }
+            if (old == dofs[i]) break;
+            s = (s + 1) & (HASH_SLOTS - 1);
+            if (++probes >= HASH_SLOTS) { failed = true; break; }
+          }
+          if (failed) {
+          } else if (ln < 0) {
+            atomicAdd(&vals[s], v[i]);
+          } else {
+            for (uint64_t k = c_ptr[ln]; k < c_ptr[ln + 1] && !failed; ++k) {
+              const unsigned key = c_master[k];
+              unsigned t = (key * 2654435761u) >> 24;
+              probes = 0;
+              while (true) {
+                const unsigned old = atomicCAS(&keys[t], HASH_EMPTY, key);
+                if (old == HASH_EMPTY) { ++claimed; break; }
+                if (old == key) break;
+                t = (t + 1) & (HASH_SLOTS - 1);
+                if (++probes >= HASH_SLOTS) { failed = true; break; }
+              }
+              if (!failed) atomicAdd(&vals[t], c_weight[k] * v[i]);
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    const unsigned total_claimed = __reduce_add_sync(0xffffffffu, claimed);
+    if (__any_sync(0xffffffffu, failed) || total_claimed > (unsigned)HASH_CAP) {
+      if (lane == 0) { atomicOr(problem, 1u); rowlen[m] = 0; rowstart[m] = 0; }
+      __syncwarp();
+      continue;
+    }
+    unsigned D = 0;
+#pragma unroll
+    for (int k = 0; k < HASH_SLOTS / 32; ++k) {
+      const unsigned s = lane + 32 * k;
+      const bool occ = keys[s] != HASH_EMPTY;
+      const unsigned bal = __ballot_sync(0xffffffffu, occ);
+      if (occ) { const unsigned q = D + __popc(bal & ((1u << lane) - 1u)); list[q] = s; dkey[q] = keys[s]; }  // dense list of the distinct dofs
+      D += __popc(bal);
+    }
+    __syncwarp();
+    if (D > chunk_left) {   // next chunk (the tail of the old one stays unused)
+      unsigned long long base = 0;
+      const unsigned need = D > FAST_CHUNK ? D : FAST_CHUNK;
+      if (lane == 0) base = atomicAdd(cursor, (unsigned long long)need);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base + need > capacity) {
+        if (lane == 0) { atomicOr(problem, 2u); rowlen[m] = 0; rowstart[m] = 0; }
+        chunk_left = 0;
+        __syncwarp();
+        continue;
+      }
+      chunk_pos = base;
+      chunk_left = need;
+    }
+    const uint64_t dst = chunk_pos;
+    // rank of every distinct key = its position in the row (the inner loop is a broadcast read)
+    for (unsigned e = lane; e < D; e += 32) {
+      const unsigned key = dkey[e];
+      unsigned rank = 0;
+      for (unsigned f = 0; f < D; ++f) rank += dkey[f] < key ? 1u : 0u;
+      out_col[dst + rank] = key;
+      out_val[dst + rank] = vals[list[e]];
+      atomicAdd(&a_cnt[key], 1u);
+    }
+    if (lane == 0) { rowlen[m] = D; rowstart[m] = dst; }
+    chunk_pos += D;
+    chunk_left -= D;
+    __syncwarp();
+  }
+}
+
 template <int NL>
 __global__ void __launch_bounds__(256) merge_rows_warp(uint64_t n_im, const uint32_t *__restrict__ cap, const uint64_t *cand_ptr,
                                                        const uint32_t *cand_bg, const uint8_t *acc, const double *local,
@@ -496,11 +626,58 @@ __global__ void scatter_len_by_dof(uint64_t n_im, const uint32_t *__restrict__ r
 // host side
 // ---------------------------------------------------------------------------------------
 template <int NL>
+static int transpose_rows(nm_ctx *ctx, bool counts_ready);
+
+// fast path: returns NM_OK and sets *done when the matrix was completed
+template <int NL>
+static int matrix_build_fast(nm_ctx *ctx, bool *done)
+{
+  const uint64_t n_im = ctx->n_im, n_rows = ctx->n_space_dofs;
+  *done = false;
+  if (n_im == 0 || ctx->force_general_merge) return NM_OK;
+  PhaseTimer tm(ctx, NM_T_MERGE);
+  // distinct dofs <= contributions; +25% and the chunk tails for constraint expansion
+  const uint64_t blocks = (n_im + 8 * FAST_ROWS - 1) / (8 * FAST_ROWS);
+  const uint64_t capacity = ctx->counts.n_accepted * NL + ctx->counts.n_accepted * NL / 4 + blocks * 8 * FAST_CHUNK + 1024;
+  NM_TRY(nm_ensure(ctx, ctx->c_rowstart, (n_im + 2) * sizeof(uint64_t)));
+  NM_TRY(nm_ensure(ctx, ctx->c_rowlen, (n_im + 1) * sizeof(uint32_t)));
+  NM_TRY(nm_ensure(ctx, ctx->c_col, (capacity + 1) * sizeof(uint32_t)));
+  NM_TRY(nm_ensure(ctx, ctx->c_val, (capacity + 1) * sizeof(double)));
+  NM_TRY(nm_ensure(ctx, ctx->a_cursor, (n_rows + 2) * sizeof(uint32_t) * 2));
+  NM_TRY(nm_ensure(ctx, ctx->counters, 64 * sizeof(uint64_t)));
+  unsigned long long *cursor = ctx->counters.as<unsigned long long>() + 20;
+  unsigned *problem = ctx->counters.as<unsigned>() + 44;
+  NM_CUDA(cudaMemsetAsync(cursor, 0, 16, ctx->stream));
+  NM_CUDA(cudaMemsetAsync(ctx->a_cursor.p, 0, (n_rows + 2) * sizeof(uint32_t) * 2, ctx->stream));
+  KernelTimer km(ctx, NM_T_K_MERGE);
+  merge_rows_fast<NL><<<(unsigned)blocks, 256, 0, NM_LS(ctx)>>>(
+      n_im, ctx->cand_ptr.as<uint64_t>(), ctx->cand_bg.as<uint32_t>(), ctx->cand_acc.as<uint8_t>(), ctx->cand_local.as<double>(),
+      ctx->bg_dofs.as<uint32_t>(), ctx->line_of.as<int32_t>(), ctx->c_ptr.as<uint64_t>(), ctx->c_master.as<uint32_t>(),
+      ctx->c_weight.as<double>(), ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(),
+      ctx->c_val.as<double>(), capacity, cursor, problem, ctx->a_cursor.as<uint32_t>());
+  km.stop();
+  NM_CUDA(cudaGetLastError());
+  unsigned h_problem = 0;
+  NM_CUDA(cudaMemcpyAsync(&h_problem, problem, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  tm.stop();
+  if (h_problem) return NM_OK;  // the general path redoes everything
+  NM_TRY(transpose_rows<NL>(ctx, true));
+  *done = true;
+  return NM_OK;
+}
+
+template <int NL>
 static int matrix_build_t(nm_ctx *ctx)
 {
   const uint64_t n_im = ctx->n_im, n_rows = ctx->n_space_dofs;
   ctx->matrix_valid = false;
   ctx->nnz = 0;
+  {
+    bool done = false;
+    NM_TRY(matrix_build_fast<NL>(ctx, &done));
+    if (done) return NM_OK;
+  }
   PhaseTimer tm(ctx, NM_T_MERGE);
   NM_TRY(nm_ensure(ctx, ctx->scratch_a, (n_im + 1) * sizeof(uint32_t)));
   NM_TRY(nm_ensure(ctx, ctx->c_rowstart, (n_im + 2) * sizeof(uint64_t)));
@@ -560,14 +737,20 @@ static int matrix_build_t(nm_ctx *ctx)
   }
   tm.stop();
 
-  // ---- transpose ----
+  return transpose_rows<NL>(ctx, false);
+}
+
+template <int NL>
+static int transpose_rows(nm_ctx *ctx, bool counts_ready)
+{
+  const uint64_t n_im = ctx->n_im, n_rows = ctx->n_space_dofs;
   PhaseTimer tt(ctx, NM_T_TRANSPOSE);
   NM_TRY(nm_ensure(ctx, ctx->a_cursor, (n_rows + 2) * sizeof(uint32_t) * 2));
   NM_TRY(nm_ensure(ctx, ctx->a_rowptr, (n_rows + 2) * sizeof(uint64_t)));
   uint32_t *cnt = ctx->a_cursor.as<uint32_t>(), *cursor = cnt + (n_rows + 2);
-  NM_CUDA(cudaMemsetAsync(cnt, 0, (n_rows + 2) * sizeof(uint32_t) * 2, ctx->stream));
+  if (!counts_ready) NM_CUDA(cudaMemsetAsync(cnt, 0, (n_rows + 2) * sizeof(uint32_t) * 2, ctx->stream));
   constexpr int TL = NL == 8 ? 8 : 4;
-  if (n_im) {
+  if (n_im && !counts_ready) {
     t_count<TL><<<nm_blocks(n_im * TL, 256), 256, 0, NM_LS(ctx)>>>(n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(),
                                                                    ctx->c_col.as<uint32_t>(), cnt);
     NM_CUDA(cudaGetLastError());
