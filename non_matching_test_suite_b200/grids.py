@@ -222,23 +222,29 @@ def overlapping_cells(blo: torch.Tensor, bhi: torch.Tensor, level: int, chunk: i
     return _unpack(keys, d)
 
 
+def _bits(d: int) -> int:
+    return 31 if d == 2 else 21
+
+
 def _pack(idx: torch.Tensor) -> torch.Tensor:
-    """[m, d] non-negative ints (< 2^21) -> one int64 key, last axis most significant."""
+    """[m, d] non-negative ints (< 2^31 in 2D, < 2^21 in 3D) -> one int64 key, last axis most significant."""
+    b = _bits(idx.shape[1])
     key = idx[:, 0].clone()
     for k in range(1, idx.shape[1]):
-        key = key | (idx[:, k] << (21 * k))
+        key = key | (idx[:, k] << (b * k))
     return key
 
 
 def _unpack(key: torch.Tensor, d: int) -> torch.Tensor:
-    mask = (1 << 21) - 1
-    return torch.stack([(key >> (21 * k)) & mask for k in range(d)], dim=1)
+    b = _bits(d)
+    mask = (1 << b) - 1
+    return torch.stack([(key >> (b * k)) & mask for k in range(d)], dim=1)
 
 
 def _morton(idx: torch.Tensor) -> torch.Tensor:
     d = idx.shape[1]
     code = torch.zeros(idx.shape[0], dtype=I64, device=idx.device)
-    for b in range(20, -1, -1):
+    for b in range(_bits(d) - 1, -1, -1):
         for k in range(d - 1, -1, -1):
             code = (code << 1) | ((idx[:, k] >> b) & 1)
     return code
@@ -347,7 +353,7 @@ def background_grid(lmap: LevelMap, cycles: int, near: Optional[Tuple[torch.Tens
     d, lf = lmap.d, lmap.lf
     dev = lmap.lvl.device
     Lfine = lf + cycles
-    assert Lfine <= 20, "vertex keys are packed in 21 bits per axis"
+    assert Lfine <= _bits(d) - 1, "vertex keys are packed in %d bits per axis" % _bits(d)
     levels0 = [int(v) for v in torch.unique(lmap.lvl).tolist()]
     pos_l, lev_l = [], []
     for l0 in levels0:
