@@ -278,15 +278,16 @@ def run_native(args):
     peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback")
     per_cand = 296 if d == 3 else 104      # pair ids 8 B + background cell 2^d*d*8 B + immersed cell 2^(d-1)*d*8 B
     per_acc_vals = 64 if d == 3 else 32    # 2^d local values written per accepted pair
+    clip_name = "clip_moments3_kernel" if d == 3 else "clip_local_kernel<2>"
     kernels = {
-        "clip_local_kernel": (phases["k_clip"], n_cand * per_cand + n_acc * per_acc_vals),
-        "cand_count+cand_fill": (phases["k_cand_count"] + phases["k_cand_fill"], 0),
-        "merge_rows_warp": (phases["k_merge"], n_acc * ((36 if d == 3 else 20) + per_acc_vals)),
+        clip_name: (phases["k_clip"], n_cand * per_cand + n_acc * per_acc_vals),
+        "cand_probe+cand_place": (phases["k_cand_count"] + phases["k_cand_fill"], 0),
+        "merge_rows_fast": (phases["k_merge"], n_acc * ((36 if d == 3 else 20) + per_acc_vals)),
     }
     dom = max(kernels, key=lambda k: kernels[k][0])
-    dom_ms, dom_bytes = kernels["clip_local_kernel"]
+    dom_ms, dom_bytes = kernels[clip_name]
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    roofline = {"kernel": "clip_local_kernel<%d>" % d, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"kernel": clip_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
                 "kernel_ms": dom_ms, "largest_kernel_by_time": dom,
                 "kernel_ms_all": {k: v[0] for k, v in kernels.items()}}
