@@ -126,6 +126,12 @@ int nm_set_immersed(nm_ctx *ctx, int dim, int spacedim, uint64_t n_cells, const 
  * sum(weights) > tol.  degree == 0 -> NM_ERR_INVALID (the reference AssertThrows). */
 int nm_intersect(nm_ctx *ctx, unsigned degree, double tol, nm_counts *counts);
 
+/* flags[b] = 1 iff the closed bounding box of background cell b meets the bounding box of some
+ * immersed cell: the refinement flagging loop of the drivers' adjust_grids()
+ * (examples/lagrange_multiplier/1d2d/lagrange_multiplier.cc:361-470, same R-tree query as
+ * src/coupling_utilities.cc:53-55).  Needs only nm_set_background + nm_set_immersed. */
+int nm_flag_overlapped_background(nm_ctx *ctx, uint8_t *flags, int where);
+
 /* Results of nm_intersect, ordered by (immersed cell, background cell) ascending.
  * Any output pointer may be NULL. */
 int nm_get_candidates(nm_ctx *ctx, uint32_t *immersed, uint32_t *background, int where);

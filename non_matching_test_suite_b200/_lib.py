@@ -23,7 +23,7 @@ PHASES = ["upload", "index", "candidates", "split", "clip", "merge", "transpose"
 
 # every symbol include/nmgpu.h declares
 SYMBOLS = ["nm_version", "nm_create", "nm_destroy", "nm_last_error", "nm_set_background", "nm_set_background_boxes",
-           "nm_set_background_dofs", "nm_set_immersed_dofs", "nm_set_immersed", "nm_intersect", "nm_get_candidates", "nm_get_pairs", "nm_get_quadrature",
+           "nm_set_background_dofs", "nm_set_immersed_dofs", "nm_set_immersed", "nm_flag_overlapped_background", "nm_intersect", "nm_get_candidates", "nm_get_pairs", "nm_get_quadrature",
            "nm_get_split_codes", "nm_build_sparsity", "nm_assemble", "nm_assemble_from_quadrature", "nm_get_csr",
            "nm_spmv", "nm_get_timings", "nm_get_launch_count", "nm_device_bytes", "nm_get_stream"]
 
@@ -63,6 +63,7 @@ def load():
     L.nm_set_immersed.argtypes = [P, I, I, U64, P, P, C.c_uint32, U64, I]
     L.nm_set_background_dofs.argtypes = [P, P, U64, U64, P, P, P, P, I]
     L.nm_set_immersed_dofs.argtypes = [P, P, C.c_uint32, U64, I]
+    L.nm_flag_overlapped_background.argtypes = [P, P, I]
     L.nm_intersect.argtypes = [P, C.c_uint, C.c_double, C.POINTER(Counts)]
     L.nm_get_candidates.argtypes = [P, P, P, I]
     L.nm_get_pairs.argtypes = [P, P, P, P, I]
@@ -167,6 +168,12 @@ class Context:
                                          dofs_per_cell, n_dofs, w))
         self.n_im_dofs = n_dofs
         self.n_im = int(verts.shape[0])
+
+    def flag_overlapped_background(self, n_bg: int):
+        """uint8 flag per background cell: closed box meets some immersed box (adjust_grids flagging)."""
+        out = torch.empty(n_bg, dtype=torch.uint8)
+        self._chk(self.L.nm_flag_overlapped_background(self.h, _ptr(out)[0], NM_HOST))
+        return out
 
     # ---- intersection -------------------------------------------------------------------
     def intersect(self, degree: int = 3, tol: float = 1e-15) -> dict:

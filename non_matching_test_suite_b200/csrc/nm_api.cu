@@ -87,6 +87,14 @@ static uint64_t held_bytes(nm_ctx *c)
   return s;
 }
 
+namespace {
+__global__ void scatter_flags(uint64_t n, const uint32_t *__restrict__ bg, uint8_t *__restrict__ flags)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[bg[i]] = 1;
+}
+}  // namespace
+
 extern "C" {
 
 int nm_version(void) { return 100; }
@@ -355,6 +363,30 @@ __global__ void gather_by_idx(uint64_t n, const uint64_t *__restrict__ idx, cons
 }  // namespace
 
 extern "C" {
+
+int nm_flag_overlapped_background(nm_ctx *ctx, uint8_t *flags, int where)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->bg_set || !ctx->im_set) return nm_fail(ctx, NM_ERR_STATE, "grids have not been set");
+  if (!flags) return nm_fail(ctx, NM_ERR_INVALID, "null output");
+  if (!ctx->intersect_valid) {   // candidate pairs only: no clipping needed for the flags
+    if (!ctx->index_valid) { PhaseTimer t(ctx, NM_T_INDEX); NM_TRY(nm_index_build(ctx)); t.stop(); }
+    PhaseTimer t(ctx, NM_T_CANDIDATES);
+    NM_TRY(nm_candidates_run(ctx));
+    t.stop();
+    ctx->candidates_only = true;
+  }
+  uint8_t *f_dev = flags;
+  if (where == NM_HOST) { NM_TRY(nm_ensure(ctx, ctx->stage_y, ctx->n_bg + 1)); f_dev = ctx->stage_y.as<uint8_t>(); }
+  NM_CUDA(cudaMemsetAsync(f_dev, 0, ctx->n_bg, ctx->stream));
+  const uint64_t nc = ctx->counts.n_candidates;
+  if (nc) scatter_flags<<<nm_blocks(nc, 256), 256, 0, NM_LS(ctx)>>>(nc, ctx->cand_bg.as<uint32_t>(), f_dev);
+  NM_CUDA(cudaGetLastError());
+  if (where == NM_HOST) NM_TRY(nm_download(ctx, flags, f_dev, ctx->n_bg, NM_HOST));
+  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return NM_OK;
+}
 
 int nm_get_pairs(nm_ctx *ctx, uint32_t *immersed, uint32_t *background, double *sum_w, int where)
 {

@@ -256,6 +256,7 @@ __device__ inline bool tri_box_overlap(const double (*v)[3], const double *H)
     const double r = h[0] * fabs(nx) + h[1] * fabs(ny) + h[2] * fabs(nz);
     sep |= fabs(d) > r;
   }
+#ifndef NM_SAT_NO_CROSS
   // axes e_i x f_j: the two end points of edge j project to the same value, so two projections
   // (edge start, opposite vertex) bound the triangle
 #pragma unroll
@@ -280,6 +281,7 @@ __device__ inline bool tri_box_overlap(const double (*v)[3], const double *H)
       sep |= fmin(q0, q1) > r || fmax(q0, q1) < -r;
     }
   }
+#endif
   return !sep;
 }
 
@@ -636,7 +638,7 @@ __device__ inline void item_clip_moments(const double *__restrict__ box, const d
 }
 
 #ifndef CM_MINB
-#define CM_MINB 2
+#define CM_MINB 3
 #endif
 #ifndef CM_WARPS_N
 #define CM_WARPS_N 8

@@ -80,6 +80,7 @@ struct nm_ctx {
   DevBuf cand_nq;     // [n_cand] u16
   DevBuf cand_acc;    // [n_cand] u8: pair accepted (sum of weights > tol)
   DevBuf counters;    // device counters (u64 x 8)
+  bool candidates_only = false;  // candidate list computed without clipping (nm_flag_overlapped_background)
   bool intersect_valid = false;
   int spmv_variant = 0;                  // NMGPU_SPMV_VARIANT: tuning knob for lanes/unroll (0 = default)
   bool force_general_merge = false;      // NMGPU_FORCE_GENERAL_MERGE=1: skip the single-pass merge (testing)

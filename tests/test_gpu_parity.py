@@ -219,3 +219,14 @@ def test_full_size_properties():
     rhs = torch.dot(x, ctx.spmv(u, transpose=True))
     assert abs(float(lhs - rhs)) <= 1e-12 * abs(float(lhs))
     ctx.close()
+
+
+def test_adjust_grids_flagging():
+    """nm_flag_overlapped_background == brute-force closed-box overlap (the drivers' adjust_grids loop)."""
+    bg, im = make_config("flower", 0, band_only=False)
+    ctx = coupling.make_context(bg, im)
+    flags = ctx.flag_overlapped_background(bg.n_cells)
+    blo, bhi = im.boxes()
+    ov = ((bg.lo[:, None, :] <= bhi[None]) & (blo[None] <= bg.hi[:, None, :])).all(-1).any(1)
+    assert torch.equal(flags.bool(), ov)
+    ctx.close()
