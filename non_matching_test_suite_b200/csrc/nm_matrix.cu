@@ -300,12 +300,14 @@ __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint
   __shared__ unsigned s_keys[8][HASH_SLOTS];
   __shared__ double s_vals[8][HASH_SLOTS];
   __shared__ unsigned s_list[8][HASH_SLOTS];
-  __shared__ unsigned s_dkey[8][HASH_SLOTS];
+  __shared__ __align__(16) unsigned s_dkey[8][HASH_SLOTS];
+  __shared__ unsigned s_cand[8][32];
   const unsigned w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned *keys = s_keys[w];
   double *vals = s_vals[w];
   unsigned *list = s_list[w];
   unsigned *dkey = s_dkey[w];
+  unsigned *cands = s_cand[w];
   const uint64_t m0 = ((uint64_t)blockIdx.x * 8 + w) * FAST_ROWS;
   uint64_t chunk_pos = 0;
   unsigned chunk_left = 0;
@@ -317,33 +319,36 @@ __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint
     unsigned claimed = 0;
     bool failed = false;   // table full: bounded probing gives up instead of spinning
     for (uint64_t base = p0; base < p1; base += 32) {
+      // accepted pairs of this chunk, compacted; then one lane per (pair, vertex) contribution
       const uint64_t p = base + lane;
       const bool on = p < p1 && acc[p];
-      uint32_t dofs[NL];
-      double v[NL];
-      if (on) {
-        const uint32_t *dp = bg_dofs + (uint64_t)cand_bg[p] * NL;
-        const double *lp = local + p * NL;
-#pragma unroll
-        for (int i = 0; i < NL; ++i) { dofs[i] = dp[i]; v[i] = lp[i]; }
-      }
-#pragma unroll
-      for (int i = 0; i < NL; ++i) {
-        if (on && !failed) {
-          const int32_t ln = line_of[dofs[i]];
-          unsigned s = (dofs[i] * 2654435761u) >> 24;
+      const unsigned bal = __ballot_sync(0xffffffffu, on);
+      if (on) cands[__popc(bal & ((1u << lane) - 1u))] = lane;
+      __syncwarp();
+      const unsigned n_entries = (unsigned)__popc(bal) * NL;
+      for (unsigned e0 = 0; e0 < n_entries; e0 += 32) {
+        const unsigned e = e0 + lane;
+        if (e < n_entries && !failed) {
+          const uint64_t q = base + cands[e / NL];
+          const unsigned i = e % NL;
+          const uint32_t dof = bg_dofs[(uint64_t)cand_bg[q] * NL + i];
+          const double v = local[q * NL + i];
+          const int32_t ln = line_of[dof];
+          unsigned s = (dof * 2654435761u) >> 24;
           int probes = 0;
           while (true) {
-            const unsigned old = atomicCAS(&keys[s], HASH_EMPTY, dofs[i]);
+            const unsigned old = atomicCAS(&keys[s], HASH_EMPTY, dof);
             if (old == HASH_EMPTY) { ++claimed; break; }
-            if (old == dofs[i]) break;
+            if (old == dof) break;
             s = (s + 1) & (HASH_SLOTS - 1);
             if (++probes >= HASH_SLOTS) { failed = true; break; }
           }
           if (failed) {
           } else if (ln < 0) {
-            atomicAdd(&vals[s], v[i]);
+            atomicAdd(&vals[s], v);
           } else {
+            // keep_constrained_entries: the constrained row stays in the pattern as a structural zero;
+            // its value goes to the masters of the line (none for a Dirichlet row)
             for (uint64_t k = c_ptr[ln]; k < c_ptr[ln + 1] && !failed; ++k) {
               const unsigned key = c_master[k];
               unsigned t = (key * 2654435761u) >> 24;
@@ -355,7 +360,7 @@ __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint
                 t = (t + 1) & (HASH_SLOTS - 1);
                 if (++probes >= HASH_SLOTS) { failed = true; break; }
               }
-              if (!failed) atomicAdd(&vals[t], c_weight[k] * v[i]);
+              if (!failed) atomicAdd(&vals[t], c_weight[k] * v);
             }
           }
         }
@@ -377,6 +382,7 @@ __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint
       if (occ) { const unsigned q = D + __popc(bal & ((1u << lane) - 1u)); list[q] = s; dkey[q] = keys[s]; }  // dense list of the distinct dofs
       D += __popc(bal);
     }
+    if (lane < 4) dkey[D + lane] = HASH_EMPTY;   // sentinel padding for the vector loads below (D <= 192 < 252)
     __syncwarp();
     if (D > chunk_left) {   // next chunk (the tail of the old one stays unused)
       unsigned long long base = 0;
@@ -393,14 +399,19 @@ __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint
       chunk_left = need;
     }
     const uint64_t dst = chunk_pos;
-    // rank of every distinct key = its position in the row (the inner loop is a broadcast read)
-    for (unsigned e = lane; e < D; e += 32) {
-      const unsigned key = dkey[e];
-      unsigned rank = 0;
-      for (unsigned f = 0; f < D; ++f) rank += dkey[f] < key ? 1u : 0u;
-      out_col[dst + rank] = key;
-      out_val[dst + rank] = vals[list[e]];
-      atomicAdd(&a_cnt[key], 1u);
+    // rank of every distinct key = its position in the row; two keys per lane share the broadcast loads
+    for (unsigned e0 = 0; e0 < D; e0 += 64) {
+      const unsigned ea = e0 + lane, eb = e0 + 32 + lane;
+      const unsigned ka = ea < D ? dkey[ea] : HASH_EMPTY, kb = eb < D ? dkey[eb] : HASH_EMPTY;
+      unsigned ra = 0, rb = 0;
+      const uint4 *dk4 = reinterpret_cast<const uint4 *>(dkey);
+      for (unsigned f = 0; f < (D + 3) / 4; ++f) {
+        const uint4 k4 = dk4[f];
+        ra += (k4.x < ka) + (k4.y < ka) + (k4.z < ka) + (k4.w < ka);
+        rb += (k4.x < kb) + (k4.y < kb) + (k4.z < kb) + (k4.w < kb);
+      }
+      if (ea < D) { out_col[dst + ra] = ka; out_val[dst + ra] = vals[list[ea]]; atomicAdd(&a_cnt[ka], 1u); }
+      if (eb < D) { out_col[dst + rb] = kb; out_val[dst + rb] = vals[list[eb]]; atomicAdd(&a_cnt[kb], 1u); }
     }
     if (lane == 0) { rowlen[m] = D; rowstart[m] = dst; }
     chunk_pos += D;
