@@ -207,8 +207,12 @@ def run_native(args):
     csr_out = {}
 
     def step(inp, x, u, y, z, host):
-        ctx.set_background(d, verts=inp["verts"], dofs=inp["dofs"], n_dofs=bg.n_dofs, c_dof=inp["c_dof"], c_ptr=inp["c_ptr"],
-                           c_master=inp["c_master"], c_weight=inp["c_weight"])
+        if "verts" in inp:   # all 2^d vertices of every background cell, as mapping.get_vertices() returns them
+            ctx.set_background(d, verts=inp["verts"], dofs=inp["dofs"], n_dofs=bg.n_dofs, c_dof=inp["c_dof"], c_ptr=inp["c_ptr"],
+                               c_master=inp["c_master"], c_weight=inp["c_weight"])
+        else:                # lo/hi corners: what include/coupling_utilities.h sends for Cartesian background cells
+            ctx.set_background(d, lo=inp["lo"], hi=inp["hi"], dofs=inp["dofs"], n_dofs=bg.n_dofs, c_dof=inp["c_dof"], c_ptr=inp["c_ptr"],
+                               c_master=inp["c_master"], c_weight=inp["c_weight"])
         ctx.set_immersed(im.dim, im.spacedim, inp["im_verts"], inp["im_dofs"], im.n_dofs)
         counts = ctx.intersect(3, 1e-15)
         ctx.build_sparsity()
@@ -308,7 +312,8 @@ def run_native(args):
     # ---- end to end: host buffers in, matrix + vectors out ----------------------------------------
     e2e = None
     if not args.no_e2e:
-        host_in = {k: v.cpu().pin_memory() for k, v in dev_in.items()}
+        host_in = {k: v.cpu().pin_memory() for k, v in dev_in.items() if k != "verts"}
+        host_in["lo"], host_in["hi"] = bg.lo.contiguous().cpu().pin_memory(), bg.hi.contiguous().cpu().pin_memory()
         xh, uh = x_dev.cpu().pin_memory(), u_dev.cpu().pin_memory()
         yh = torch.empty(bg.n_dofs, dtype=torch.float64).pin_memory()
         zh = torch.empty(im.n_dofs, dtype=torch.float64).pin_memory()
@@ -318,7 +323,7 @@ def run_native(args):
         d2h = sum(t.numel() * t.element_size() for t in out) + yh.numel() * 8 + zh.numel() * 8
         e2e = {"value": tot_acc / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": ms_e, "steps": e_steps,
-               "api": "coupling/_lib.Context: set_background(host verts)+set_immersed+intersect+build_sparsity+assemble+spmv x2+csr() read-back"}
+               "api": "_lib.Context (C ABI): nm_set_background_boxes(host lo/hi + dofs + constraint lines) + nm_set_immersed + nm_intersect + nm_build_sparsity + nm_assemble + nm_spmv x2 (host vectors) + nm_get_csr read-back into pinned host memory; the same calls include/coupling_utilities.h makes"}
         del host_in
 
     cpu_base = None

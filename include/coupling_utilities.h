@@ -96,19 +96,54 @@ void gather_vertices(const Triangulation<dim, spacedim> &tria, const Mapping<dim
   }
 }
 
+// Background cells as boxes: every configuration of the reference has Cartesian background cells
+// (GridGenerator::hyper_cube + refinements), so lo/hi corners carry the geometry in a quarter of the
+// bytes.  A cell whose vertices are not those of an axis-aligned box in deal.II order is refused
+// here exactly as the library itself would refuse it.
+template <int dim, int spacedim>
+void gather_boxes(const Triangulation<dim, spacedim> &tria, const Mapping<dim, spacedim> &mapping, std::vector<double> &lo,
+                  std::vector<double> &hi, std::vector<unsigned int> &local_of_active,
+                  std::vector<typename Triangulation<dim, spacedim>::cell_iterator> *cells)
+{
+  constexpr unsigned int nv = 1u << dim;
+  local_of_active.assign(tria.n_active_cells(), static_cast<unsigned int>(-1));
+  lo.clear();
+  hi.clear();
+  unsigned int n = 0;
+  for (const auto &cell : tria.active_cell_iterators()) {
+    if (!cell->is_locally_owned())
+      continue;
+    const auto v = mapping.get_vertices(cell);
+    AssertThrow(v.size() == nv, ExcNotImplemented());
+    bool ok = true;
+    for (unsigned int i = 0; i < nv; ++i)
+      for (unsigned int d = 0; d < spacedim; ++d)
+        ok = ok && v[i][d] == (((i >> d) & 1u) ? v[nv - 1][d] : v[0][d]);
+    AssertThrow(ok, ExcMessage("nmgpu: only Cartesian background cells are implemented"));
+    for (unsigned int d = 0; d < spacedim; ++d) {
+      lo.push_back(v[0][d]);
+      hi.push_back(v[nv - 1][d]);
+    }
+    local_of_active[cell->active_cell_index()] = n++;
+    if (cells)
+      cells->push_back(cell);
+  }
+}
+
 template <int dim0, int dim1, int spacedim>
 void set_grids(Session &s, const Triangulation<dim0, spacedim> &space, const Mapping<dim0, spacedim> &mapping0,
                const Triangulation<dim1, spacedim> &immersed, const Mapping<dim1, spacedim> &mapping1,
                std::vector<typename Triangulation<dim0, spacedim>::cell_iterator> *space_cells,
                std::vector<typename Triangulation<dim1, spacedim>::cell_iterator> *immersed_cells)
 {
-  std::vector<double> v0, v1;
+  std::vector<double> lo, hi, v1;
   // locally owned background cells, the whole immersed grid (coupling_utilities.cc:40-45)
-  gather_vertices(space, mapping0, true, v0, s.space_local_of_active, space_cells);
+  gather_boxes(space, mapping0, lo, hi, s.space_local_of_active, space_cells);
   gather_vertices(immersed, mapping1, false, v1, s.immersed_local_of_active, immersed_cells);
-  s.n_space = v0.size() / ((1u << dim0) * spacedim);
+  s.n_space = lo.size() / spacedim;
   s.n_immersed = v1.size() / ((1u << dim1) * spacedim);
-  check(s, nm_set_background(s.ctx, spacedim, s.n_space, v0.data(), nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, NM_HOST));
+  check(s, nm_set_background_boxes(s.ctx, spacedim, s.n_space, lo.data(), hi.data(), nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr,
+                                   NM_HOST));
   check(s, nm_set_immersed(s.ctx, dim1, spacedim, s.n_immersed, v1.data(), nullptr, 1, 0, NM_HOST));
   s.grids_set = true;
 }
