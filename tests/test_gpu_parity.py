@@ -230,3 +230,64 @@ def test_adjust_grids_flagging():
     ov = ((bg.lo[:, None, :] <= bhi[None]) & (blo[None] <= bg.hi[:, None, :])).all(-1).any(1)
     assert torch.equal(flags.bool(), ov)
     ctx.close()
+
+
+def _random_problem(d, n_bg, n_im, seed):
+    """Background = arbitrary axis-aligned boxes (not a tree: sizes over 1.5 decades, overlapping, unaligned),
+    every box with its own 2^d DoFs; immersed = random small segments / planar-ish quads."""
+    from non_matching_test_suite_b200.grids import BackgroundGrid, ImmersedGrid
+    g = torch.Generator().manual_seed(seed)
+    size = 10.0 ** (-2.0 + 1.5 * torch.rand(n_bg, 1, dtype=torch.float64, generator=g)) * (0.5 + torch.rand(n_bg, d, dtype=torch.float64, generator=g))
+    lo = torch.rand(n_bg, d, dtype=torch.float64, generator=g) * 0.9
+    hi = lo + size
+    dofs = torch.arange(n_bg * (1 << d), dtype=torch.int32).reshape(n_bg, 1 << d)
+    e = torch.empty(0, dtype=torch.int32)
+    bg = BackgroundGrid(d, lo, hi, dofs, n_bg * (1 << d), torch.zeros(n_bg, dtype=torch.int32), e, torch.zeros(1, dtype=torch.int64), e,
+                        torch.empty(0, dtype=torch.float64))
+    c = torch.rand(n_im, 1, d, dtype=torch.float64, generator=g)
+    if d == 2:
+        verts = c + 0.08 * (torch.rand(n_im, 2, 2, dtype=torch.float64, generator=g) - 0.5)
+    else:
+        u = 0.08 * (torch.rand(n_im, 1, 3, dtype=torch.float64, generator=g) - 0.5)
+        v = 0.08 * (torch.rand(n_im, 1, 3, dtype=torch.float64, generator=g) - 0.5)
+        w = 0.004 * (torch.rand(n_im, 1, 3, dtype=torch.float64, generator=g) - 0.5)     # slightly non-planar
+        verts = torch.cat([c, c + u, c + v, c + u + v + w], dim=1)
+    im = ImmersedGrid(d - 1, d, verts.contiguous(), torch.arange(n_im, dtype=torch.int32)[:, None], n_im)
+    return bg, im
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_arbitrary_boxes_against_oracle(c_oracle, d):
+    """The grid hash makes no assumption about the background being a tree."""
+    bg, im = _random_problem(d, 3000, 400, seed=d)
+    ref = c_oracle.assemble(bg, im, n1d=3, tol=1e-15)
+    ctx = coupling.make_context(bg, im, boxes=True)
+    counts = ctx.intersect(3, 1e-15)
+    assert counts["n_candidates"] > 2000
+    assert np.array_equal(_keys(*ctx.candidates()), ref["candidates"])
+    aim, abg, sw = ctx.pairs()
+    assert np.array_equal(_keys(aim, abg), ref["accepted"])
+    if d == 3:
+        assert np.array_equal(ctx.split_codes().numpy(), ref["codes"])
+    rp, col, val = ctx.csr()
+    assert np.array_equal(rp.numpy().astype(np.uint64), ref["rowptr"])
+    assert np.array_equal(col.numpy().astype(np.uint32), ref["col"])
+    assert np.linalg.norm(val.numpy() - ref["val"]) <= REL_FROB_TOL * np.linalg.norm(ref["val"])
+    ctx.close()
+
+
+def test_big_immersed_cells_take_the_general_merge_path(c_oracle):
+    """Immersed cells much larger than the background cells: hundreds of pairs per immersed cell overflow the
+    fast merge (192 distinct DoFs) and must come out identical through the two-pass path."""
+    from non_matching_test_suite_b200.grids import ImmersedGrid, circle_grid
+    bg, _ = make_config("disk", 4, band_only=False)
+    im = circle_grid(8)                                                      # 8 long segments across a fine band
+    ref = c_oracle.assemble(bg, im)
+    ctx = coupling.make_context(bg, im)
+    c = ctx.intersect(3, 1e-15)
+    assert c["n_accepted"] / im.n_cells > 120
+    rp, col, val = ctx.csr()
+    assert np.array_equal(col.numpy().astype(np.uint32), ref["col"])
+    assert np.array_equal(rp.numpy().astype(np.uint64), ref["rowptr"])
+    assert np.linalg.norm(val.numpy() - ref["val"]) <= REL_FROB_TOL * np.linalg.norm(ref["val"])
+    ctx.close()
