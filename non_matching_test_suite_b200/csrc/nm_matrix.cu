@@ -815,8 +815,12 @@ int nm_spmv_run(nm_ctx *ctx, int transpose, const double *x, double *y)
       else if (ctx->spmv_variant / 10 == 3) spmv_csr<1, 8, uint64_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y);
       else if (ctx->spmv_variant / 10 == 4) spmv_csr<1, 3, uint64_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y);
       else if (ctx->spmv_variant / 10 == 5) spmv_csr<1, 2, uint64_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y);
-      else if (ctx->a_rowptr32_valid) spmv_csr<1, 8, uint32_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr32.as<uint32_t>(), cl, vl, x, y);
-      else spmv_csr<1, 8, uint64_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y);
+      else if (ctx->a_rowptr32_valid && ctx->spmv_variant / 10 == 6) spmv_csr<1, 8, uint32_t><<<nm_blocks(n_rows, 128), 128, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr32.as<uint32_t>(), cl, vl, x, y);
+      else if (ctx->a_rowptr32_valid && ctx->spmv_variant / 10 == 7) spmv_csr<1, 6, uint32_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr32.as<uint32_t>(), cl, vl, x, y);
+      else if (ctx->a_rowptr32_valid && ctx->spmv_variant / 10 == 8) spmv_csr<1, 12, uint32_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr32.as<uint32_t>(), cl, vl, x, y);
+      else if (ctx->a_rowptr32_valid && ctx->spmv_variant / 10 == 9) spmv_csr<1, 8, uint32_t><<<nm_blocks(n_rows, 64), 64, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr32.as<uint32_t>(), cl, vl, x, y);
+      else if (ctx->a_rowptr32_valid) spmv_csr<1, 8, uint32_t><<<nm_blocks(n_rows, 128), 128, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr32.as<uint32_t>(), cl, vl, x, y);
+      else spmv_csr<1, 8, uint64_t><<<nm_blocks(n_rows, 128), 128, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y);
     }
   } else {
     NM_CUDA(cudaMemsetAsync(y, 0, ctx->n_im_dofs * sizeof(double), ctx->stream));
