@@ -4,6 +4,7 @@
 #include <stdlib.h>
 
 #include <new>
+#include <vector>
 
 #include "nm_common.cuh"
 
@@ -61,14 +62,18 @@ int nm_download(nm_ctx *ctx, void *dst, const void *src, size_t bytes, int where
   return NM_OK;
 }
 
+static std::vector<DevBuf *> all_buffers(nm_ctx *c)
+{
+  return {&c->bg_box, &c->bg_dofs, &c->line_of, &c->c_ptr, &c->c_master, &c->c_weight, &c->im_verts, &c->im_dofs, &c->im_split,
+          &c->im_measure, &c->idx_next, &c->idx_extra_bg, &c->idx_hash, &c->idx_tmp, &c->cand_ptr, &c->cand_tmp, &c->cand_im, &c->cand_bg,
+          &c->cand_sumw, &c->cand_local, &c->cand_nq, &c->cand_acc, &c->counters, &c->c_rowstart, &c->c_rowlen, &c->c_col, &c->c_val,
+          &c->a_rowptr, &c->a_rowptr32, &c->a_col, &c->a_val, &c->a_cursor, &c->scan_tmp, &c->scratch_a, &c->scratch_b, &c->stage_x,
+          &c->stage_y, &c->h2d_stage};
+}
+
 static void free_all(nm_ctx *c)
 {
-  DevBuf *bufs[] = {&c->bg_box, &c->bg_dofs, &c->line_of, &c->c_ptr, &c->c_master, &c->c_weight, &c->im_verts, &c->im_dofs, &c->im_split,
-                    &c->im_measure, &c->idx_keys, &c->idx_keys_alt, &c->idx_vals, &c->idx_vals_alt, &c->idx_hash, &c->idx_tmp, &c->cand_ptr, &c->cand_tmp,
-                    &c->cand_im, &c->cand_bg, &c->cand_sumw, &c->cand_local, &c->cand_nq, &c->cand_acc, &c->counters, &c->c_rowstart,
-                    &c->c_rowlen, &c->c_col, &c->c_val, &c->a_rowptr, &c->a_rowptr32, &c->a_col, &c->a_val, &c->a_cursor, &c->scan_tmp, &c->scratch_a,
-                    &c->scratch_b, &c->stage_x, &c->stage_y, &c->h2d_stage};
-  for (DevBuf *b : bufs) {
+  for (DevBuf *b : all_buffers(c)) {
     if (b->p) cudaFree(b->p);
     b->p = nullptr;
     b->cap = 0;
@@ -77,13 +82,8 @@ static void free_all(nm_ctx *c)
 
 static uint64_t held_bytes(nm_ctx *c)
 {
-  DevBuf *bufs[] = {&c->bg_box, &c->bg_dofs, &c->line_of, &c->c_ptr, &c->c_master, &c->c_weight, &c->im_verts, &c->im_dofs, &c->im_split,
-                    &c->im_measure, &c->idx_keys, &c->idx_keys_alt, &c->idx_vals, &c->idx_vals_alt, &c->idx_hash, &c->idx_tmp, &c->cand_ptr, &c->cand_tmp,
-                    &c->cand_im, &c->cand_bg, &c->cand_sumw, &c->cand_local, &c->cand_nq, &c->cand_acc, &c->counters, &c->c_rowstart,
-                    &c->c_rowlen, &c->c_col, &c->c_val, &c->a_rowptr, &c->a_rowptr32, &c->a_col, &c->a_val, &c->a_cursor, &c->scan_tmp, &c->scratch_a,
-                    &c->scratch_b, &c->stage_x, &c->stage_y, &c->h2d_stage};
   uint64_t s = 0;
-  for (DevBuf *b : bufs) s += b->cap;
+  for (DevBuf *b : all_buffers(c)) s += b->cap;
   return s;
 }
 
@@ -145,7 +145,8 @@ int nm_destroy(nm_ctx *ctx)
 
 const char *nm_last_error(const nm_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
-static int set_background_common(nm_ctx *ctx, int spacedim, uint64_t n_cells, const double *verts, const double *lo, const double *hi,
+static int set_background_common(nm_ctx *ctx, int spacedim, uint64_t n_cells, bool from_verts, const double *verts, const double *lo,
+                                 const double *hi,
                                  const uint32_t *dofs, uint64_t n_dofs, uint64_t n_constrained, const uint32_t *c_dof,
                                  const uint64_t *c_ptr, const uint32_t *c_master, const double *c_weight, int where)
 {
@@ -153,7 +154,6 @@ static int set_background_common(nm_ctx *ctx, int spacedim, uint64_t n_cells, co
   NM_CUDA(cudaSetDevice(ctx->device));
   if (spacedim != 2 && spacedim != 3) return nm_fail(ctx, NM_ERR_INVALID, "spacedim must be 2 or 3 (got %d)", spacedim);
   if (n_cells >= 0xffffffffULL || n_dofs >= 0xffffffffULL) return nm_fail(ctx, NM_ERR_UNSUPPORTED, "cell / DoF counts must fit 32 bits");
-  if (n_cells && !verts && (!lo || !hi)) return nm_fail(ctx, NM_ERR_INVALID, "null background arrays");
   if (n_constrained && (!c_dof || !c_ptr)) return nm_fail(ctx, NM_ERR_INVALID, "null constraint arrays");
   ctx->bg_set = ctx->index_valid = ctx->intersect_valid = ctx->matrix_valid = false;
   const int NV = 1 << spacedim;
@@ -163,7 +163,7 @@ static int set_background_common(nm_ctx *ctx, int spacedim, uint64_t n_cells, co
   ctx->n_space_dofs = n_dofs;
   ctx->n_constrained = n_constrained;
   // geometry
-  if (verts) {
+  if (from_verts) {
     const double *v_dev = verts;
     if (where == NM_HOST) { NM_TRY(nm_upload(ctx, ctx->h2d_stage, verts, n_cells * NV * spacedim * sizeof(double), NM_HOST)); v_dev = ctx->h2d_stage.as<double>(); }
     NM_TRY(nm_bg_layout(ctx, spacedim, n_cells, v_dev, nullptr, nullptr));
@@ -261,8 +261,8 @@ int nm_set_background(nm_ctx *ctx, int spacedim, uint64_t n_cells, const double 
                       const double *c_weight, int where)
 {
   if (ctx && n_cells && !verts) return nm_fail(ctx, NM_ERR_INVALID, "null vertex array");
-  return set_background_common(ctx, spacedim, n_cells, verts ? verts : (const double *)1, nullptr, nullptr, dofs, n_dofs, n_constrained, c_dof,
-                               c_ptr, c_master, c_weight, where);
+  return set_background_common(ctx, spacedim, n_cells, /*from_verts=*/true, verts, nullptr, nullptr, dofs, n_dofs, n_constrained, c_dof, c_ptr,
+                               c_master, c_weight, where);
 }
 
 int nm_set_background_boxes(nm_ctx *ctx, int spacedim, uint64_t n_cells, const double *lo, const double *hi, const uint32_t *dofs,
@@ -270,8 +270,8 @@ int nm_set_background_boxes(nm_ctx *ctx, int spacedim, uint64_t n_cells, const d
                             const uint32_t *c_master, const double *c_weight, int where)
 {
   if (ctx && n_cells && (!lo || !hi)) return nm_fail(ctx, NM_ERR_INVALID, "null box arrays");
-  return set_background_common(ctx, spacedim, n_cells, nullptr, lo ? lo : (const double *)1, hi ? hi : (const double *)1, dofs, n_dofs,
-                               n_constrained, c_dof, c_ptr, c_master, c_weight, where);
+  return set_background_common(ctx, spacedim, n_cells, /*from_verts=*/false, nullptr, lo, hi, dofs, n_dofs, n_constrained, c_dof, c_ptr,
+                               c_master, c_weight, where);
 }
 
 int nm_set_immersed(nm_ctx *ctx, int dim, int spacedim, uint64_t n_cells, const double *verts, const uint32_t *dofs,

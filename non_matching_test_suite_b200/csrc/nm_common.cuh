@@ -23,8 +23,8 @@ struct DevBuf {
 // Background grid-hash slot: one occupied grid cell of one level.
 struct HashSlot {
   unsigned long long key;  // packed (level, ix, iy, iz); ~0 = empty
-  uint32_t start;          // first entry in `entries`
-  uint32_t count;
+  uint32_t start;          // head of the chain of entries (a background cell id for a grid-aligned tree)
+  uint32_t count;          // length of the chain
 };
 
 struct GridIndex {
@@ -32,7 +32,6 @@ struct GridIndex {
   double org[3] = {0, 0, 0};
   double g0 = 0;            // spacing of level 0
   uint32_t level_mask = 0;  // bit k: level k holds cells
-  int max_idx[32][3];       // largest occupied index per level/axis (query clamp)
   uint32_t n_entries = 0;
   uint32_t hash_cap = 0;    // power of two
 };
@@ -65,7 +64,9 @@ struct nm_ctx {
 
   // ---- grid hash ----
   GridIndex gi;
-  DevBuf idx_keys, idx_keys_alt, idx_vals, idx_vals_alt, idx_hash, idx_tmp;
+  DevBuf idx_next;      // chain of the entries of one grid cell (next[entry id])
+  DevBuf idx_extra_bg;  // background id of entry ids >= n_bg
+  DevBuf idx_hash, idx_tmp;
 
   // ---- intersection results ----
   unsigned degree = 0;

@@ -447,8 +447,8 @@ static GridDev make_grid_dev(const nm_ctx *ctx)
   G.level_mask = ctx->gi.level_mask;
   G.hash = ctx->idx_hash.as<HashSlot>();
   G.hash_mask = ctx->gi.hash_cap - 1;
-  G.next = ctx->idx_vals.as<uint32_t>();
-  G.extra_bg = ctx->idx_vals_alt.as<uint32_t>();
+  G.next = ctx->idx_next.as<uint32_t>();
+  G.extra_bg = ctx->idx_extra_bg.as<uint32_t>();
   G.n_bg = (uint32_t)ctx->n_bg;
   G.idx_bits = ctx->gi.d == 2 ? 29 : 19;
   return G;
@@ -518,14 +518,14 @@ int nm_index_build(nm_ctx *ctx)
   while (cap < 2 * ne) cap <<= 1;
   ctx->gi.hash_cap = cap;
   NM_TRY(nm_ensure(ctx, ctx->idx_hash, (size_t)cap * sizeof(HashSlot)));
-  NM_TRY(nm_ensure(ctx, ctx->idx_vals, (ne + 1) * 4));
-  NM_TRY(nm_ensure(ctx, ctx->idx_vals_alt, (ne - n + 1) * 4));
+  NM_TRY(nm_ensure(ctx, ctx->idx_next, (ne + 1) * 4));
+  NM_TRY(nm_ensure(ctx, ctx->idx_extra_bg, (ne - n + 1) * 4));
   G = make_grid_dev(ctx);
   hash_clear<<<nm_blocks(cap, 256), 256, 0, NM_LS(ctx)>>>(ctx->idx_hash.as<HashSlot>(), cap);
-  if (d == 2) index_insert<2><<<B, T, 0, NM_LS(ctx)>>>(G, n, ctx->bg_box.as<double>(), ctx->idx_hash.as<HashSlot>(), ctx->idx_vals.as<uint32_t>(),
-                                                      ctx->idx_vals_alt.as<uint32_t>(), extra_cursor);
-  else index_insert<3><<<B, T, 0, NM_LS(ctx)>>>(G, n, ctx->bg_box.as<double>(), ctx->idx_hash.as<HashSlot>(), ctx->idx_vals.as<uint32_t>(),
-                                                ctx->idx_vals_alt.as<uint32_t>(), extra_cursor);
+  if (d == 2) index_insert<2><<<B, T, 0, NM_LS(ctx)>>>(G, n, ctx->bg_box.as<double>(), ctx->idx_hash.as<HashSlot>(), ctx->idx_next.as<uint32_t>(),
+                                                      ctx->idx_extra_bg.as<uint32_t>(), extra_cursor);
+  else index_insert<3><<<B, T, 0, NM_LS(ctx)>>>(G, n, ctx->bg_box.as<double>(), ctx->idx_hash.as<HashSlot>(), ctx->idx_next.as<uint32_t>(),
+                                                ctx->idx_extra_bg.as<uint32_t>(), extra_cursor);
   NM_CUDA(cudaGetLastError());
   ctx->index_valid = true;
   return NM_OK;
