@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--ref-cycle", type=int, default=None, help="refinement cycle of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--verts", action="store_true", help="send all 2^d vertices of every background cell instead of lo/hi boxes")
     return ap.parse_args()
 
 
@@ -194,7 +195,10 @@ def run_native(args):
     t_gen = time.time() - t0
     d = bg.spacedim
     u32 = lambda t: t.to(torch.int32).contiguous()
-    dev_in = dict(verts=bg.vertices().contiguous(), dofs=u32(bg.dofs), c_dof=u32(bg.c_dof), c_ptr=bg.c_ptr.contiguous(),
+    # background cells as lo/hi corners -- the format include/coupling_utilities.h hands to nm_set_background_boxes
+    # (pass --verts to feed all 2^d vertices per cell through nm_set_background instead)
+    geom = dict(verts=bg.vertices().contiguous()) if args.verts else dict(lo=bg.lo.contiguous(), hi=bg.hi.contiguous())
+    dev_in = dict(**geom, dofs=u32(bg.dofs), c_dof=u32(bg.c_dof), c_ptr=bg.c_ptr.contiguous(),
                   c_master=u32(bg.c_master), c_weight=bg.c_weight.contiguous(), im_verts=im.verts.contiguous(), im_dofs=u32(im.dofs))
     x_dev = (torch.rand(im.n_dofs, dtype=torch.float64, device=dev, generator=torch.Generator(device=dev).manual_seed(0)) * 2 - 1)
     u_dev = (torch.rand(bg.n_dofs, dtype=torch.float64, device=dev, generator=torch.Generator(device=dev).manual_seed(1)) * 2 - 1)
@@ -312,8 +316,7 @@ def run_native(args):
     # ---- end to end: host buffers in, matrix + vectors out ----------------------------------------
     e2e = None
     if not args.no_e2e:
-        host_in = {k: v.cpu().pin_memory() for k, v in dev_in.items() if k != "verts"}
-        host_in["lo"], host_in["hi"] = bg.lo.contiguous().cpu().pin_memory(), bg.hi.contiguous().cpu().pin_memory()
+        host_in = {k: v.cpu().pin_memory() for k, v in dev_in.items()}
         xh, uh = x_dev.cpu().pin_memory(), u_dev.cpu().pin_memory()
         yh = torch.empty(bg.n_dofs, dtype=torch.float64).pin_memory()
         zh = torch.empty(im.n_dofs, dtype=torch.float64).pin_memory()
