@@ -284,10 +284,11 @@ __global__ void __launch_bounds__(256) merge_rows_hash(uint64_t n_im, const uint
 // per-row counts of the transposed matrix are accumulated on the way.  Anything it cannot handle
 // (more than HASH_CAP distinct dofs in a cell, storage overflow) raises a flag and the general
 // two-pass path below redoes the whole matrix.
-constexpr int FAST_ROWS = 16;
-constexpr unsigned FAST_CHUNK = 2048;
+constexpr int FAST_ROWS = 64;   // consecutive immersed cells per group
 
-template <int NL>
+// GROUP lanes cooperate on one immersed cell: a full warp in 3D (~10 accepted pairs x 8 vertices), 8 lanes
+// in 2D (~3.4 pairs x 4 vertices), so that a warp merges four 2D cells at a time.
+template <int NL, int GROUP, int SLOTS, unsigned FAST_CHUNK>
 __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint64_t *__restrict__ cand_ptr,
                                                        const uint32_t *__restrict__ cand_bg, const uint8_t *__restrict__ acc,
                                                        const double *__restrict__ local, const uint32_t *__restrict__ bg_dofs,
@@ -297,36 +298,40 @@ __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint
                                                        uint32_t *__restrict__ out_col, double *__restrict__ out_val, uint64_t capacity,
                                                        unsigned long long *cursor, unsigned *problem, uint32_t *__restrict__ a_cnt)
 {
-  __shared__ unsigned s_keys[8][HASH_SLOTS];
-  __shared__ double s_vals[8][HASH_SLOTS];
-  __shared__ unsigned s_list[8][HASH_SLOTS];
-  __shared__ __align__(16) unsigned s_dkey[8][HASH_SLOTS];
-  __shared__ unsigned s_cand[8][32];
-  const unsigned w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned *keys = s_keys[w];
-  double *vals = s_vals[w];
-  unsigned *list = s_list[w];
-  unsigned *dkey = s_dkey[w];
-  unsigned *cands = s_cand[w];
-  const uint64_t m0 = ((uint64_t)blockIdx.x * 8 + w) * FAST_ROWS;
+  constexpr int NG = 256 / GROUP;                 // groups per block
+  constexpr unsigned CAP = SLOTS * 3 / 4;         // distinct dofs a group accepts
+  __shared__ unsigned s_keys[NG][SLOTS];
+  __shared__ double s_vals[NG][SLOTS];
+  __shared__ unsigned s_list[NG][SLOTS];
+  __shared__ __align__(16) unsigned s_dkey[NG][SLOTS];
+  __shared__ unsigned s_cand[NG][GROUP];
+  const unsigned g = threadIdx.x / GROUP, lane = threadIdx.x % GROUP;
+  const unsigned gbase = (threadIdx.x & 31) - lane;                      // first lane of the group inside its warp
+  const unsigned gmask = GROUP == 32 ? 0xffffffffu : (((1u << GROUP) - 1u) << gbase);
+  unsigned *keys = s_keys[g];
+  double *vals = s_vals[g];
+  unsigned *list = s_list[g];
+  unsigned *dkey = s_dkey[g];
+  unsigned *cands = s_cand[g];
+  const uint64_t m0 = ((uint64_t)blockIdx.x * NG + g) * FAST_ROWS;
   uint64_t chunk_pos = 0;
   unsigned chunk_left = 0;
   for (uint64_t m = m0; m < m0 + FAST_ROWS && m < n_im; ++m) {
 #pragma unroll
-    for (int k = 0; k < HASH_SLOTS / 32; ++k) { keys[lane + 32 * k] = HASH_EMPTY; vals[lane + 32 * k] = 0.0; }
-    __syncwarp();
+    for (int k = 0; k < SLOTS / GROUP; ++k) { keys[lane + GROUP * k] = HASH_EMPTY; vals[lane + GROUP * k] = 0.0; }
+    __syncwarp(gmask);
     const uint64_t p0 = cand_ptr[m], p1 = cand_ptr[m + 1];
     unsigned claimed = 0;
     bool failed = false;   // table full: bounded probing gives up instead of spinning
-    for (uint64_t base = p0; base < p1; base += 32) {
+    for (uint64_t base = p0; base < p1; base += GROUP) {
       // accepted pairs of this chunk, compacted; then one lane per (pair, vertex) contribution
       const uint64_t p = base + lane;
       const bool on = p < p1 && acc[p];
-      const unsigned bal = __ballot_sync(0xffffffffu, on);
+      const unsigned bal = (__ballot_sync(gmask, on) >> gbase) & (GROUP == 32 ? 0xffffffffu : ((1u << GROUP) - 1u));
       if (on) cands[__popc(bal & ((1u << lane) - 1u))] = lane;
-      __syncwarp();
+      __syncwarp(gmask);
       const unsigned n_entries = (unsigned)__popc(bal) * NL;
-      for (unsigned e0 = 0; e0 < n_entries; e0 += 32) {
+      for (unsigned e0 = 0; e0 < n_entries; e0 += GROUP) {
         const unsigned e = e0 + lane;
         if (e < n_entries && !failed) {
           const uint64_t q = base + cands[e / NL];
@@ -334,14 +339,14 @@ __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint
           const uint32_t dof = bg_dofs[(uint64_t)cand_bg[q] * NL + i];
           const double v = local[q * NL + i];
           const int32_t ln = line_of[dof];
-          unsigned s = (dof * 2654435761u) >> 24;
+          unsigned s = ((dof * 2654435761u) >> 16) & (SLOTS - 1);
           int probes = 0;
           while (true) {
             const unsigned old = atomicCAS(&keys[s], HASH_EMPTY, dof);
             if (old == HASH_EMPTY) { ++claimed; break; }
             if (old == dof) break;
-            s = (s + 1) & (HASH_SLOTS - 1);
-            if (++probes >= HASH_SLOTS) { failed = true; break; }
+            s = (s + 1) & (SLOTS - 1);
+            if (++probes >= SLOTS) { failed = true; break; }
           }
           if (failed) {
           } else if (ln < 0) {
@@ -351,48 +356,48 @@ __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint
             // its value goes to the masters of the line (none for a Dirichlet row)
             for (uint64_t k = c_ptr[ln]; k < c_ptr[ln + 1] && !failed; ++k) {
               const unsigned key = c_master[k];
-              unsigned t = (key * 2654435761u) >> 24;
+              unsigned t = ((key * 2654435761u) >> 16) & (SLOTS - 1);
               probes = 0;
               while (true) {
                 const unsigned old = atomicCAS(&keys[t], HASH_EMPTY, key);
                 if (old == HASH_EMPTY) { ++claimed; break; }
                 if (old == key) break;
-                t = (t + 1) & (HASH_SLOTS - 1);
-                if (++probes >= HASH_SLOTS) { failed = true; break; }
+                t = (t + 1) & (SLOTS - 1);
+                if (++probes >= SLOTS) { failed = true; break; }
               }
               if (!failed) atomicAdd(&vals[t], c_weight[k] * v);
             }
           }
         }
-        __syncwarp();
+        __syncwarp(gmask);
       }
     }
-    const unsigned total_claimed = __reduce_add_sync(0xffffffffu, claimed);
-    if (__any_sync(0xffffffffu, failed) || total_claimed > (unsigned)HASH_CAP) {
+    const unsigned total_claimed = __reduce_add_sync(gmask, claimed);
+    if (__any_sync(gmask, failed) || total_claimed > CAP) {
       if (lane == 0) { atomicOr(problem, 1u); rowlen[m] = 0; rowstart[m] = 0; }
-      __syncwarp();
+      __syncwarp(gmask);
       continue;
     }
     unsigned D = 0;
 #pragma unroll
-    for (int k = 0; k < HASH_SLOTS / 32; ++k) {
-      const unsigned s = lane + 32 * k;
+    for (int k = 0; k < SLOTS / GROUP; ++k) {
+      const unsigned s = lane + GROUP * k;
       const bool occ = keys[s] != HASH_EMPTY;
-      const unsigned bal = __ballot_sync(0xffffffffu, occ);
+      const unsigned bal = (__ballot_sync(gmask, occ) >> gbase) & (GROUP == 32 ? 0xffffffffu : ((1u << GROUP) - 1u));
       if (occ) { const unsigned q = D + __popc(bal & ((1u << lane) - 1u)); list[q] = s; dkey[q] = keys[s]; }  // dense list of the distinct dofs
       D += __popc(bal);
     }
-    if (lane < 4) dkey[D + lane] = HASH_EMPTY;   // sentinel padding for the vector loads below (D <= 192 < 252)
-    __syncwarp();
+    if (lane < 4) dkey[D + lane] = HASH_EMPTY;   // sentinel padding for the vector loads below (D <= 3/4 SLOTS)
+    __syncwarp(gmask);
     if (D > chunk_left) {   // next chunk (the tail of the old one stays unused)
       unsigned long long base = 0;
       const unsigned need = D > FAST_CHUNK ? D : FAST_CHUNK;
       if (lane == 0) base = atomicAdd(cursor, (unsigned long long)need);
-      base = __shfl_sync(0xffffffffu, base, 0);
+      base = __shfl_sync(gmask, base, gbase);
       if (base + need > capacity) {
         if (lane == 0) { atomicOr(problem, 2u); rowlen[m] = 0; rowstart[m] = 0; }
         chunk_left = 0;
-        __syncwarp();
+        __syncwarp(gmask);
         continue;
       }
       chunk_pos = base;
@@ -400,8 +405,8 @@ __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint
     }
     const uint64_t dst = chunk_pos;
     // rank of every distinct key = its position in the row; two keys per lane share the broadcast loads
-    for (unsigned e0 = 0; e0 < D; e0 += 64) {
-      const unsigned ea = e0 + lane, eb = e0 + 32 + lane;
+    for (unsigned e0 = 0; e0 < D; e0 += 2 * GROUP) {
+      const unsigned ea = e0 + lane, eb = e0 + GROUP + lane;
       const unsigned ka = ea < D ? dkey[ea] : HASH_EMPTY, kb = eb < D ? dkey[eb] : HASH_EMPTY;
       unsigned ra = 0, rb = 0;
       const uint4 *dk4 = reinterpret_cast<const uint4 *>(dkey);
@@ -416,7 +421,7 @@ __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint
     if (lane == 0) { rowlen[m] = D; rowstart[m] = dst; }
     chunk_pos += D;
     chunk_left -= D;
-    __syncwarp();
+    __syncwarp(gmask);
   }
 }
 
@@ -648,8 +653,10 @@ static int matrix_build_fast(nm_ctx *ctx, bool *done)
   if (n_im == 0 || ctx->force_general_merge) return NM_OK;
   PhaseTimer tm(ctx, NM_T_MERGE);
   // distinct dofs <= contributions; +25% and the chunk tails for constraint expansion
-  const uint64_t blocks = (n_im + 8 * FAST_ROWS - 1) / (8 * FAST_ROWS);
-  const uint64_t capacity = ctx->counts.n_accepted * NL + ctx->counts.n_accepted * NL / 4 + blocks * 8 * FAST_CHUNK + 1024;
+  constexpr int GROUP = NL == 8 ? 32 : 8, SLOTS = NL == 8 ? 256 : 64, NG = 256 / GROUP;
+  constexpr unsigned FAST_CHUNK = NL == 8 ? 1024 : 256;   // entries a group takes from the cursor at a time
+  const uint64_t blocks = (n_im + NG * FAST_ROWS - 1) / (NG * FAST_ROWS);
+  const uint64_t capacity = ctx->counts.n_accepted * NL + ctx->counts.n_accepted * NL / 4 + blocks * NG * FAST_CHUNK + 1024;
   NM_TRY(nm_ensure(ctx, ctx->c_rowstart, (n_im + 2) * sizeof(uint64_t)));
   NM_TRY(nm_ensure(ctx, ctx->c_rowlen, (n_im + 1) * sizeof(uint32_t)));
   NM_TRY(nm_ensure(ctx, ctx->c_col, (capacity + 1) * sizeof(uint32_t)));
@@ -661,7 +668,7 @@ static int matrix_build_fast(nm_ctx *ctx, bool *done)
   NM_CUDA(cudaMemsetAsync(cursor, 0, 16, ctx->stream));
   NM_CUDA(cudaMemsetAsync(ctx->a_cursor.p, 0, (n_rows + 2) * sizeof(uint32_t) * 2, ctx->stream));
   KernelTimer km(ctx, NM_T_K_MERGE);
-  merge_rows_fast<NL><<<(unsigned)blocks, 256, 0, NM_LS(ctx)>>>(
+  merge_rows_fast<NL, GROUP, SLOTS, FAST_CHUNK><<<(unsigned)blocks, 256, 0, NM_LS(ctx)>>>(
       n_im, ctx->cand_ptr.as<uint64_t>(), ctx->cand_bg.as<uint32_t>(), ctx->cand_acc.as<uint8_t>(), ctx->cand_local.as<double>(),
       ctx->bg_dofs.as<uint32_t>(), ctx->line_of.as<int32_t>(), ctx->c_ptr.as<uint64_t>(), ctx->c_master.as<uint32_t>(),
       ctx->c_weight.as<double>(), ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(),
