@@ -103,12 +103,12 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the CPU restatement (oracle/nm_oracle.c) on the box's host cores
 # --------------------------------------------------------------------------------------------
-def cpu_sample(config, cycle, steps, warmup):
+def cpu_sample(config, cycle, steps, warmup, threads=None):
     import torch
     from non_matching_test_suite_b200.grids import make_config
     from oracle import c_oracle as co
     co.build()
-    co.lib().nmo_set_num_threads(os.cpu_count() or 1)   # torchrun pins OMP_NUM_THREADS=1: use every host thread
+    co.lib().nmo_set_num_threads(threads or os.cpu_count() or 1)   # torchrun pins OMP_NUM_THREADS=1: set it explicitly
     cores = co.lib().nmo_num_threads()
     bg, im = make_config(config, cycle, band_only=True)
     times, acc = [], 0
@@ -332,6 +332,9 @@ def run_native(args):
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base, _, _ = cpu_sample(args.config, pick_ref_cycle(args), 1, 0)
+        # the reference as shipped runs 1 MPI rank x 1 thread (code/scripts/run_all_tests.sh): same port, one thread, smaller sample
+        one, _, _ = cpu_sample(args.config, max(0, pick_ref_cycle(args) - 2), 1, 0, threads=1)
+        cpu_base["single_thread"] = {"value": one["value"], "unit": UNIT, "cores": 1, "sample": one["sample"]}
 
     if rank == 0:
         line = {

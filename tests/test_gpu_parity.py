@@ -315,3 +315,23 @@ def test_parity_at_oracle_sized_refinements(c_oracle, name, cycle):
     allowed = REL_FROB_TOL + dropped * 1e-12 / np.linalg.norm(ref["val"])
     assert err <= allowed, (err, allowed, dropped)
     ctx.close()
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_degenerate_touching_cases_gpu(c_oracle, d):
+    """Same hand-made degenerate cases as tests/test_oracle_cpu.py, GPU against the oracle."""
+    from degenerate_cases import case_2d, case_3d
+    bg, im = case_2d() if d == 2 else case_3d()
+    ref = c_oracle.assemble(bg, im, n1d=3, tol=1e-15)
+    ctx = coupling.make_context(bg, im)
+    ctx.intersect(3, 1e-15)
+    assert np.array_equal(_keys(*ctx.candidates()), ref["candidates"])
+    aim, abg, sw = ctx.pairs()
+    assert np.array_equal(_keys(aim, abg), ref["accepted"])
+    assert np.allclose(sw.numpy(), ref["sum_w"], rtol=1e-12, atol=1e-15)
+    if d == 3:
+        assert np.array_equal(ctx.split_codes().numpy(), ref["codes"])
+    rp, col, val = ctx.csr()
+    assert np.array_equal(col.numpy().astype(np.uint32), ref["col"])
+    assert np.linalg.norm(val.numpy() - ref["val"]) <= REL_FROB_TOL * np.linalg.norm(ref["val"])
+    ctx.close()

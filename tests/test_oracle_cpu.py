@@ -173,3 +173,28 @@ def test_flower_points_match_reference_file():
     i = [k for k, l in enumerate(lines) if l.startswith("POINTS")][0]
     P = np.array([[float(x) for x in lines[i + 1 + k].split()[:2]] for k in range(256)])
     assert np.array_equal(P, flower_points().numpy())
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_degenerate_touching_cases(c_oracle, d):
+    """Rules R3/R5 on hand-made cases: the FP64 oracle agrees with exact rational arithmetic about which pairs
+    exist, and about the double counting of simplices lying in a shared face."""
+    from degenerate_cases import case_2d, case_3d
+    bg, im = case_2d() if d == 2 else case_3d()
+    ex = eo.assemble(bg, im, tol=1e-15)
+    ref = c_oracle.assemble(bg, im, n1d=3, tol=1e-15)
+    ea = np.array([(m << 32) | b for m, b in ex["accepted"]], dtype=np.uint64)
+    assert np.array_equal(ea, ref["accepted"])
+    assert np.allclose(ex["sum_w"], ref["sum_w"], rtol=1e-12, atol=1e-15)
+    per_cell = np.bincount((ref["accepted"] >> np.uint64(32)).astype(np.int64), weights=ref["sum_w"], minlength=im.n_cells)
+    if d == 2:
+        meas = im.measure().numpy()
+        assert abs(per_cell[0] - 2 * meas[0]) < 1e-14          # in a shared edge: counted for both neighbours
+        assert abs(per_cell[3] - 2 * meas[3]) < 1e-14          # along a grid line
+        assert abs(per_cell[1] - meas[1]) < 1e-14 and abs(per_cell[4] - meas[4]) < 1e-14
+        assert abs(per_cell[5] - meas[5]) < 1e-14              # on the domain boundary: one neighbour only
+    else:
+        assert abs(per_cell[0] - 2 * 0.36) < 1e-14             # quad in the shared face z = 1
+        assert abs(per_cell[2] - 4.0) < 1e-13                  # flat quad of area 4, interior of the cells
+        assert per_cell[3] == 0.0                              # vertical quad: its xy-projection is a line, no Delaunay face
+        assert ref["codes"][3] & 0x0f == 0
