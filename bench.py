@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--ref-cycle", type=int, default=None, help="refinement cycle of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--nccl-allreduce", action="store_true", help="reduce Ct.vmult with NCCL all_reduce instead of the fused NVLink push")
     ap.add_argument("--verts", action="store_true", help="send all 2^d vertices of every background cell instead of lo/hi boxes")
     return ap.parse_args()
 
@@ -209,6 +210,7 @@ def run_native(args):
     stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
 
     csr_out = {}
+    fused = {"op": None, "tried": False, "why": ""}
 
     def step(inp, x, u, y, z, host):
         if "verts" in inp:   # all 2^d vertices of every background cell, as mapping.get_vertices() returns them
@@ -221,13 +223,28 @@ def run_native(args):
         counts = ctx.intersect(3, 1e-15)
         ctx.build_sparsity()
         ctx.assemble()
-        ctx.spmv(x, transpose=False, out=y)      # Ct.vmult : partial background vector
-        ctx.spmv(u, transpose=True, out=z)       # C.Tvmult : this shard's immersed entries
-        if world > 1:
-            yy = y if not host else y_dev.copy_(y, non_blocking=True)
-            dist.all_reduce(yy)                  # the only collective of the path
+        if world > 1 and fused["op"] is None and not args.nccl_allreduce and fused["tried"] is False:
+            from non_matching_test_suite_b200.distributed import FusedCtVmult
+            fused["tried"] = True
+            op = FusedCtVmult(ctx)               # symmetric-memory result vector, peer / multicast mapped
+            ok = torch.tensor([1 if op.available else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            fused["op"] = op if int(ok.item()) == 1 else None
+            fused["why"] = "" if op.available else op.reason
+        if world > 1 and fused["op"] is not None:
+            # Ct.vmult fused with its reduction: one kernel adds this rank's rows into every rank's result over NVLink
+            xx = x if not host else x_dev.copy_(x, non_blocking=True)
+            yy = fused["op"].vmult(xx)
             if host:
                 y.copy_(yy)
+        else:
+            ctx.spmv(x, transpose=False, out=y)  # Ct.vmult : partial background vector
+            if world > 1:
+                yy = y if not host else y_dev.copy_(y, non_blocking=True)
+                dist.all_reduce(yy)              # the only collective of the path
+                if host:
+                    y.copy_(yy)
+        ctx.spmv(u, transpose=True, out=z)       # C.Tvmult : this shard's immersed entries
         out = None
         if host:
             if "buf" not in csr_out or csr_out["buf"][1].numel() < ctx.nnz:   # pinned, reused read-back buffers
@@ -346,6 +363,7 @@ def run_native(args):
             "counts_rank0": counts, "phases_ms_rank0": phases, "roofline": roofline, "spmv": spmv,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "cpu_baseline": cpu_base,
             "device_bytes_rank0": ctx.device_bytes(), "gen_seconds": t_gen,
+            "ct_vmult_reduction": ("none (1 GPU)" if world == 1 else ("nm_spmv_push over NVLink, %s" % ("multimem.red on the multicast address" if fused["op"].multicast else "red.add into peer-mapped vectors") if fused["op"] is not None else "nccl all_reduce" + (" (fused path unavailable: %s)" % fused["why"] if fused["why"] else ""))),
         }
         print(json.dumps(line), flush=True)
     ctx.close()

@@ -170,6 +170,16 @@ int nm_get_csr(nm_ctx *ctx, int transpose, uint64_t *rowptr, uint32_t *col, doub
  * y (transpose=1) is non-zero only in this rank's immersed DoFs. */
 int nm_spmv(nm_ctx *ctx, int transpose, const double *x, double *y, int where);
 
+/* Ct.vmult fused with its reduction across GPUs (stored orientation, device pointers only):
+ * every non-empty row result is ADDED into each of the `n_targets` vectors y_targets[i][n_space]
+ * with a system-scope reduction -- pass this GPU's own result vector and the peer-mapped result
+ * vectors of the other ranks (CUDA IPC / symmetric memory over NVLink), or, with multicast = 1,
+ * ONE multicast address on which the NVSwitch applies the add to every rank's copy (multimem.red).
+ * Contract: all target vectors are zero before any rank calls, and hold the full product once all
+ * ranks' calls have returned (synchronise the ranks before and after).  Replaces nm_spmv(0) +
+ * all-reduce: only the rows a rank owns cross the links. */
+int nm_spmv_push(nm_ctx *ctx, const double *x, int n_targets, double *const *y_targets, int multicast);
+
 /* Device milliseconds per phase (NM_T_*), `n` entries copied. */
 int nm_get_timings(nm_ctx *ctx, float *ms, int n);
 /* Number of this library's kernel launches since nm_create (cub's internal kernels excluded). */

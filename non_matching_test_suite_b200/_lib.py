@@ -25,7 +25,7 @@ PHASES = ["upload", "index", "candidates", "split", "clip", "merge", "transpose"
 SYMBOLS = ["nm_version", "nm_create", "nm_destroy", "nm_last_error", "nm_set_background", "nm_set_background_boxes",
            "nm_set_background_dofs", "nm_set_immersed_dofs", "nm_set_immersed", "nm_flag_overlapped_background", "nm_intersect", "nm_get_candidates", "nm_get_pairs", "nm_get_quadrature",
            "nm_get_split_codes", "nm_build_sparsity", "nm_assemble", "nm_assemble_from_quadrature", "nm_get_csr",
-           "nm_spmv", "nm_get_timings", "nm_get_launch_count", "nm_device_bytes", "nm_get_stream"]
+           "nm_spmv", "nm_spmv_push", "nm_get_timings", "nm_get_launch_count", "nm_device_bytes", "nm_get_stream"]
 
 
 class NmError(RuntimeError):
@@ -74,6 +74,7 @@ def load():
     L.nm_assemble_from_quadrature.argtypes = [P, U64, P, P, P, P, P, I]
     L.nm_get_csr.argtypes = [P, I, P, P, P, I]
     L.nm_spmv.argtypes = [P, I, P, P, I]
+    L.nm_spmv_push.argtypes = [P, P, I, C.POINTER(C.c_void_p), I]
     L.nm_get_timings.argtypes = [P, P, I]
     L.nm_device_bytes.argtypes = [P, C.POINTER(U64)]
     L.nm_get_launch_count.argtypes = [P, C.POINTER(U64)]
@@ -248,6 +249,14 @@ class Context:
             out = torch.empty(ny, dtype=torch.float64, device=x.device) if isinstance(x, torch.Tensor) else np.empty(ny)
         self._chk(self.L.nm_spmv(self.h, int(transpose), _ptr(x)[0], _ptr(out)[0], _where(x, out)))
         return out
+
+    def spmv_push(self, x: torch.Tensor, target_ptrs, multicast: bool = False):
+        """Ct.vmult fused with its cross-GPU reduction: add every non-empty row result into each of the
+        device pointers `target_ptrs` (own + peer-mapped result vectors, or one multicast pointer)."""
+        assert x.is_cuda
+        torch.cuda.current_stream().synchronize()
+        arr = (C.c_void_p * len(target_ptrs))(*[C.c_void_p(int(p)) for p in target_ptrs])
+        self._chk(self.L.nm_spmv_push(self.h, C.c_void_p(x.data_ptr()), len(target_ptrs), arr, int(multicast)))
 
     # ---- introspection ------------------------------------------------------------------
     def timings(self) -> dict:

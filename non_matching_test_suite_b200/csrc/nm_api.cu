@@ -12,6 +12,7 @@ int nm_bg_layout(nm_ctx *ctx, int d, uint64_t n, const double *verts_dev, const 
 int nm_constraints_layout(nm_ctx *ctx);
 int nm_accepted_index(nm_ctx *ctx, uint64_t **idx_dev);
 int nm_c_rows_compact(nm_ctx *ctx, uint64_t *rowptr_dev, uint32_t *col_dev, double *val_dev);
+int nm_spmv_push_run(nm_ctx *ctx, const double *x, int n_targets, double *const *targets, int multicast);
 
 int nm_fail(nm_ctx *c, int code, const char *fmt, ...)
 {
@@ -553,6 +554,20 @@ int nm_spmv(nm_ctx *ctx, int transpose, const double *x, double *y, int where)
   }
   NM_TRY(nm_spmv_run(ctx, transpose, xd, yd));
   if (where == NM_HOST) NM_TRY(nm_download(ctx, y, yd, ny * 8, NM_HOST));
+  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return NM_OK;
+}
+
+int nm_spmv_push(nm_ctx *ctx, const double *x, int n_targets, double *const *targets, int multicast)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  if (!x || !targets || n_targets < 1 || n_targets > 16) return nm_fail(ctx, NM_ERR_INVALID, "1..16 target vectors expected");
+  if (multicast && n_targets != 1) return nm_fail(ctx, NM_ERR_INVALID, "a multicast push takes exactly one (multicast) target pointer");
+  for (int i = 0; i < n_targets; ++i)
+    if (!targets[i]) return nm_fail(ctx, NM_ERR_INVALID, "null target vector");
+  NM_TRY(ensure_matrix(ctx));
+  NM_TRY(nm_spmv_push_run(ctx, x, n_targets, targets, multicast));
   NM_CUDA(cudaStreamSynchronize(ctx->stream));
   return NM_OK;
 }

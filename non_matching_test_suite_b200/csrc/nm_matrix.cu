@@ -583,6 +583,32 @@ __global__ void __launch_bounds__(256) spmv_csr(uint64_t n_rows, const PTR *__re
   if (r < n_rows && l == 0) y[r] = s;
 }
 
+// Ct.vmult fused with its reduction over NVLink: every non-empty row result is added straight into
+// the result vectors of all ranks (peer-mapped pointers, or ONE multicast pointer on which the
+// NVSwitch performs the add in every rank's copy: multimem.red).  The vectors must be zero before any
+// rank starts and are complete once every rank's kernel has finished -- no NCCL all-reduce, and only
+// the rows a rank actually owns cross the links instead of the whole background vector twice.
+struct PushTargets {
+  double *p[16];
+  int n;
+};
+
+template <int UNROLL, typename PTR, bool MULTICAST>
+__global__ void __launch_bounds__(128) spmv_csr_push(uint64_t n_rows, const PTR *__restrict__ rowptr, const uint32_t *__restrict__ col,
+                                                     const double *__restrict__ val, const double *__restrict__ x, PushTargets T)
+{
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const uint64_t b = rowptr[r], e = rowptr[r + 1];
+  if (b == e) return;
+  const double s = row_dot<1, UNROLL>(col, val, x, b, e, 0u);
+  if (MULTICAST) {
+    asm volatile("multimem.red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(T.p[0] + r), "d"(s) : "memory");
+  } else {
+    for (int t = 0; t < T.n; ++t) asm volatile("red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(T.p[t] + r), "d"(s) : "memory");
+  }
+}
+
 // rows of C: (start, len) storage, result scattered to the immersed dof of the cell
 template <int LANES, int UNROLL>
 __global__ void __launch_bounds__(256) spmv_crows(uint64_t n_im, const uint64_t *__restrict__ rowstart, const uint32_t *__restrict__ rowlen,
@@ -846,6 +872,30 @@ int nm_spmv_run(nm_ctx *ctx, int transpose, const double *x, double *y)
       else if (avg > 20) spmv_crows<4, 8><<<nm_blocks(n_im * 4, 256), 256, 0, NM_LS(ctx)>>>(n_im, rs, rl, cl, vl, idf, x, y);
       else if (avg > 6) spmv_crows<4, 2><<<nm_blocks(n_im * 4, 256), 256, 0, NM_LS(ctx)>>>(n_im, rs, rl, cl, vl, idf, x, y);
       else spmv_crows<2, 2><<<nm_blocks(n_im * 2, 256), 256, 0, NM_LS(ctx)>>>(n_im, rs, rl, cl, vl, idf, x, y);
+    }
+  }
+  NM_CUDA(cudaGetLastError());
+  tm.stop();
+  return NM_OK;
+}
+
+int nm_spmv_push_run(nm_ctx *ctx, const double *x, int n_targets, double *const *targets, int multicast)
+{
+  const uint64_t n_rows = ctx->n_space_dofs;
+  PushTargets T;
+  T.n = n_targets;
+  for (int i = 0; i < 16; ++i) T.p[i] = i < n_targets ? targets[i] : nullptr;
+  PhaseTimer tm(ctx, NM_T_SPMV);
+  const uint32_t *cl = ctx->a_col.as<uint32_t>();
+  const double *vl = ctx->a_val.as<double>();
+  if (n_rows) {
+    const unsigned B = nm_blocks(n_rows, 128);
+    if (ctx->a_rowptr32_valid) {
+      if (multicast) spmv_csr_push<8, uint32_t, true><<<B, 128, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr32.as<uint32_t>(), cl, vl, x, T);
+      else spmv_csr_push<8, uint32_t, false><<<B, 128, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr32.as<uint32_t>(), cl, vl, x, T);
+    } else {
+      if (multicast) spmv_csr_push<8, uint64_t, true><<<B, 128, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr.as<uint64_t>(), cl, vl, x, T);
+      else spmv_csr_push<8, uint64_t, false><<<B, 128, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr.as<uint64_t>(), cl, vl, x, T);
     }
   }
   NM_CUDA(cudaGetLastError());

@@ -46,3 +46,41 @@ class ShardedCouplingOperator:
 def from_context(ctx, group=None) -> ShardedCouplingOperator:
     return ShardedCouplingOperator(lambda x: ctx.spmv(x, transpose=False), lambda u: ctx.spmv(u, transpose=True),
                                    ctx.n_space_dofs, ctx.n_im_dofs, group)
+
+
+class FusedCtVmult:
+    """`Ct.vmult` + cross-GPU reduction in ONE kernel over NVLink peer memory (nm_spmv_push).
+
+    The result vector lives in symmetric memory (torch.distributed._symmetric_memory): every rank maps
+    the result vectors of all ranks, or -- when the fabric supports it -- one multicast address on which
+    the NVSwitch applies the reduction in every rank's copy (`multimem.red`).  A rank only sends the rows
+    it has entries in (its immersed cells touch ~1/N of the background), instead of all-reducing the
+    whole background vector.  `available` is False when symmetric memory cannot be set up; callers then
+    keep the NCCL all-reduce of ShardedCouplingOperator."""
+
+    def __init__(self, ctx, group=None, prefer_multicast: bool = True):
+        self.ctx, self.group = ctx, group
+        self.available, self.reason, self.multicast = False, "", False
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            dev = torch.device("cuda", ctx.device)
+            self.y = symm_mem.empty(ctx.n_space_dofs, dtype=torch.float64, device=dev)
+            grp = group if group is not None else dist.group.WORLD
+            self.hdl = symm_mem.rendezvous(self.y, grp)
+            self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+            mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+            self.multicast = bool(prefer_multicast and mc)
+            self.targets = [mc] if self.multicast else self.ptrs
+            self.available = True
+        except Exception as e:  # no symmetric memory on this system: keep NCCL
+            self.reason = "%s: %s" % (type(e).__name__, str(e)[:200])
+
+    def vmult(self, lam: torch.Tensor) -> torch.Tensor:
+        """Replicated y = A lam on every rank.  Two rank barriers bracket the kernel: all vectors are zero
+        before anyone adds, and everyone's adds have landed before anyone reads."""
+        self.y.zero_()
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        self.ctx.spmv_push(lam, self.targets, multicast=self.multicast)
+        dist.barrier(group=self.group)
+        return self.y

@@ -335,3 +335,21 @@ def test_degenerate_touching_cases_gpu(c_oracle, d):
     assert np.array_equal(col.numpy().astype(np.uint32), ref["col"])
     assert np.linalg.norm(val.numpy() - ref["val"]) <= REL_FROB_TOL * np.linalg.norm(ref["val"])
     ctx.close()
+
+
+def test_spmv_push_single_gpu():
+    """nm_spmv_push (Ct.vmult fused with its cross-GPU reduction) on one GPU: the row results are ADDED into
+    every target vector; with two local targets both receive the product on top of what they held.
+    The multi-GPU run over NVLink peer / multicast memory is tests/multi_gpu_check.py (needs >= 2 GPUs)."""
+    bg, im = make_config("sphere", 1, band_only=False)
+    ctx = coupling.make_context(bg, im)
+    ctx.intersect(3, 1e-15)
+    ctx.build_sparsity()
+    x = torch.rand(im.n_dofs, dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    y_ref = ctx.spmv(x, transpose=False)
+    y1 = torch.zeros(bg.n_dofs, dtype=torch.float64, device="cuda")
+    y2 = torch.ones(bg.n_dofs, dtype=torch.float64, device="cuda")
+    ctx.spmv_push(x, [y1.data_ptr(), y2.data_ptr()])
+    assert torch.equal(y1, y_ref)
+    assert torch.allclose(y2, y_ref + 1.0, rtol=0, atol=1e-15)
+    ctx.close()
