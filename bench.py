@@ -181,6 +181,8 @@ def run_native(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO") and not os.environ.get("NMGPU_KEEP_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's banner goes to stdout: rank 0 must print exactly one JSON line
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
