@@ -518,12 +518,22 @@ __device__ inline unsigned outcode(double x, double y, double z, const double *H
          (z <= H[2] ? 32u : 0u);
 }
 
-__device__ inline void item_clip_moments(const double *__restrict__ box, const double *__restrict__ quad, int t, double tol, ItemOut &o)
+// Clipped polygon of one (cell, triangle) item: pool vertices in cell-local coordinates, index list,
+// vertex count, unit normal of the parent triangle.  Shared by the moment kernel and the quadrature
+// emission so that both see exactly the same fan triangles (same count of points per pair).
+struct ClippedPoly {
+  VPool P;
+  unsigned long long poly;
+  int n;
+  double nx, ny, nz;
+};
+
+__device__ inline bool item_clip_polygon(const double *__restrict__ box, const double *__restrict__ quad, int t, ClippedPoly &C)
 {
+  VPool &P = C.P;
   const double lo[3] = {box[0], box[1], box[2]};
   const double H[3] = {box[4] - lo[0], box[5] - lo[1], box[6] - lo[2]};
   const int iv[3] = {t == 0 ? 1 : 0, t <= 1 ? 2 : 1, t <= 2 ? 3 : 2};
-  VPool P;
   unsigned long long code = 0;         // 6 bits per polygon position
 #pragma unroll
   for (int v = 0; v < 3; ++v) {
@@ -538,7 +548,7 @@ __device__ inline void item_clip_moments(const double *__restrict__ box, const d
     const double e2[3] = {P.c[0][2] - P.c[0][0], P.c[1][2] - P.c[1][0], P.c[2][2] - P.c[2][0]};
     nx = e1[1] * e2[2] - e1[2] * e2[1]; ny = e1[2] * e2[0] - e1[0] * e2[2]; nz = e1[0] * e2[1] - e1[1] * e2[0];
     const double n2 = nx * nx + ny * ny + nz * nz;
-    if (!(n2 > 0.0)) return;
+    if (!(n2 > 0.0)) return false;
     const double inv = rsqrt(n2);
     nx *= inv; ny *= inv; nz *= inv;
   }
@@ -550,7 +560,7 @@ __device__ inline void item_clip_moments(const double *__restrict__ box, const d
     const unsigned long long full6 = M6 & ((1ULL << (6 * n)) - 1ULL);
     const unsigned long long in6 = (code >> p) & full6;
     if (in6 == full6) continue;
-    if (in6 == 0ULL) return;
+    if (in6 == 0ULL) return false;
     const int axis = p >> 1;
     const double sgn = (p & 1) ? -1.0 : 1.0, bound = (p & 1) ? H[axis] : 0.0;
     const unsigned long long prev6 = ((in6 << 6) | (in6 >> (6 * (n - 1)))) & full6;       // position i: vertex i-1 inside
@@ -605,8 +615,21 @@ __device__ inline void item_clip_moments(const double *__restrict__ box, const d
     poly = np;
     code = nc;
     n = m;
-    if (n < 3) return;
+    if (n < 3) return false;
   }
+  C.poly = poly; C.n = n; C.nx = nx; C.ny = ny; C.nz = nz;
+  return true;
+}
+
+__device__ inline void item_clip_moments(const double *__restrict__ box, const double *__restrict__ quad, int t, double tol, ItemOut &o)
+{
+  ClippedPoly C;
+  if (!item_clip_polygon(box, quad, t, C)) return;
+  const VPool &P = C.P;
+  const unsigned long long poly = C.poly;
+  const int n = C.n;
+  const double nx = C.nx, ny = C.ny, nz = C.nz;
+  const double H[3] = {box[4] - box[0], box[5] - box[1], box[6] - box[2]};
   const double ih[3] = {__drcp_rn(H[0]), __drcp_rn(H[1]), __drcp_rn(H[2])};
   const int v0 = (int)(poly & 15u), v1 = (int)((poly >> 4) & 15u);
   const double ax = P.c[0][v0], ay = P.c[1][v0], az = P.c[2][v0];
@@ -776,12 +799,15 @@ __global__ void __launch_bounds__(CM_WARPS * 32, CM_MINB) clip_moments3_kernel(
 // ---------------------------------------------------------------------------------------
 // unfused variants for the drop-in wrapper
 // ---------------------------------------------------------------------------------------
-// points/weights of every accepted pair (what the reference returns as Quadrature<spacedim>)
-template <int D>
+// points/weights of every accepted pair (what the reference returns as Quadrature<spacedim>).
+// MOMENT_PATH: the pair was accepted by clip_moments3_kernel -- walk exactly its polygons (same SAT
+// gate, same clip, same fan, same thresholds) so that the number of points equals the count it stored.
+template <int D, bool MOMENT_PATH>
 __global__ void emit_quadrature_kernel(uint64_t n_acc, const uint64_t *__restrict__ acc_idx, const uint32_t *__restrict__ cand_im,
                                        const uint32_t *__restrict__ cand_bg, const double *__restrict__ bg_box,
                                        const double *__restrict__ im_verts, const uint8_t *__restrict__ split, double tol,
-                                       const uint64_t *__restrict__ q_off, double *__restrict__ pts, double *__restrict__ wts)
+                                       const uint64_t *__restrict__ q_off, double *__restrict__ pts, double *__restrict__ wts,
+                                       unsigned long long *n_mismatch)
 {
   const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_acc) return;
@@ -791,17 +817,53 @@ __global__ void emit_quadrature_kernel(uint64_t n_acc, const uint64_t *__restric
   PairAcc o;
   o.sumw = 0; o.nq = 0; o.dropped = 0;
   uint64_t w = q_off[p];
-  if (D == 3) {
+  const uint64_t w_end = q_off[p + 1];
+  if (D == 3 && MOMENT_PATH) {
+    const double *quad = im_verts + (uint64_t)m * 12;
+    const double H[3] = {box[4] - box[0], box[5] - box[1], box[6] - box[2]};
+    unsigned rem = (unsigned)split[m] & 15u;
+    while (rem) {
+      const int t = __ffs(rem) - 1;
+      rem &= rem - 1;
+      const int iv[3] = {t == 0 ? 1 : 0, t <= 1 ? 2 : 1, t <= 2 ? 3 : 2};
+      double tri[3][3];
+      for (int v = 0; v < 3; ++v)
+        for (int k = 0; k < 3; ++k) tri[v][k] = quad[iv[v] * 3 + k] - box[k];
+      if (!tri_box_overlap(tri, H)) continue;
+      ClippedPoly C;
+      if (!item_clip_polygon(box, quad, t, C)) continue;
+      const int v0 = (int)(C.poly & 15u);
+      const double a[3] = {C.P.c[0][v0], C.P.c[1][v0], C.P.c[2][v0]};
+      for (int j = 2; j < C.n; ++j) {
+        const int v1 = (int)((C.poly >> (4 * (j - 1))) & 15u), v2 = (int)((C.poly >> (4 * j)) & 15u);
+        const double e1[3] = {C.P.c[0][v1] - a[0], C.P.c[1][v1] - a[1], C.P.c[2][v1] - a[2]};
+        const double e2[3] = {C.P.c[0][v2] - a[0], C.P.c[1][v2] - a[1], C.P.c[2][v2] - a[2]};
+        const double J = fabs((e1[1] * e2[2] - e1[2] * e2[1]) * C.nx + (e1[2] * e2[0] - e1[0] * e2[2]) * C.ny + (e1[0] * e2[1] - e1[1] * e2[0]) * C.nz);
+        if (!(0.25 * J * J > tol * tol) || J < 1e-12) continue;       // same thresholds as item_clip_moments
+        for (int q = 0; q < c_rule.n; ++q) {
+          const double s = c_rule.x[q][0], u = c_rule.x[q][1];
+          if (w < w_end) {
+            pts[w * 3 + 0] = a[0] + s * e1[0] + u * e2[0] + box[0];
+            pts[w * 3 + 1] = a[1] + s * e1[1] + u * e2[1] + box[1];
+            pts[w * 3 + 2] = a[2] + s * e1[2] + u * e2[2] + box[2];
+            wts[w] = J * c_rule.w[q];
+          }
+          ++w;
+        }
+      }
+    }
+  } else if (D == 3) {
     pair_3d(box, im_verts + (uint64_t)m * 12, split[m], tol, o, [&](const double *x, double wq) {
-      pts[w * 3 + 0] = x[0] + box[0]; pts[w * 3 + 1] = x[1] + box[1]; pts[w * 3 + 2] = x[2] + box[2];
-      wts[w] = wq; ++w;
+      if (w < w_end) { pts[w * 3 + 0] = x[0] + box[0]; pts[w * 3 + 1] = x[1] + box[1]; pts[w * 3 + 2] = x[2] + box[2]; wts[w] = wq; }
+      ++w;
     });
   } else {
     pair_2d(box, im_verts + (uint64_t)m * 4, o, [&](const double *x, double wq) {
-      pts[w * 2 + 0] = x[0] + box[0]; pts[w * 2 + 1] = x[1] + box[1];
-      wts[w] = wq; ++w;
+      if (w < w_end) { pts[w * 2 + 0] = x[0] + box[0]; pts[w * 2 + 1] = x[1] + box[1]; wts[w] = wq; }
+      ++w;
     });
   }
+  if (w != w_end) atomicAdd(n_mismatch, 1ULL);   // the emitted count must equal the count stored with the pair
 }
 
 __global__ void gather_nq_kernel(uint64_t n_acc, const uint64_t *__restrict__ acc_idx, const uint16_t *__restrict__ nq, uint32_t *__restrict__ out)
@@ -987,16 +1049,27 @@ int nm_quadrature_emit(nm_ctx *ctx, uint64_t *q_offset, double *points, double *
     if (where == NM_HOST || !points) pts_d = pbuf.as<double>();
     if (where == NM_HOST || !weights) w_d = wbuf.as<double>();
   }
+  unsigned long long *mismatch = ctx->counters.as<unsigned long long>() + 10;
+  NM_CUDA(cudaMemsetAsync(mismatch, 0, 8, ctx->stream));
   if (na) {
-    if (d == 3)
-      emit_quadrature_kernel<3><<<nm_blocks(na, 128), 128, 0, NM_LS(ctx)>>>(na, acc_idx, ctx->cand_im.as<uint32_t>(), ctx->cand_bg.as<uint32_t>(),
-                                                                           ctx->bg_box.as<double>(), ctx->im_verts.as<double>(),
-                                                                           ctx->im_split.as<uint8_t>(), ctx->tol, offs.as<uint64_t>(), pts_d, w_d);
+    NM_TRY(upload_rule(ctx));
+    const bool moment_path = d == 3 && ctx->degree == 3 && !ctx->force_quadrature_kernel;
+    const unsigned B = nm_blocks(na, 128);
+    const uint32_t *ci = ctx->cand_im.as<uint32_t>(), *cb = ctx->cand_bg.as<uint32_t>();
+    if (d == 3 && moment_path)
+      emit_quadrature_kernel<3, true><<<B, 128, 0, NM_LS(ctx)>>>(na, acc_idx, ci, cb, ctx->bg_box.as<double>(), ctx->im_verts.as<double>(),
+                                                                ctx->im_split.as<uint8_t>(), ctx->tol, offs.as<uint64_t>(), pts_d, w_d, mismatch);
+    else if (d == 3)
+      emit_quadrature_kernel<3, false><<<B, 128, 0, NM_LS(ctx)>>>(na, acc_idx, ci, cb, ctx->bg_box.as<double>(), ctx->im_verts.as<double>(),
+                                                                 ctx->im_split.as<uint8_t>(), ctx->tol, offs.as<uint64_t>(), pts_d, w_d, mismatch);
     else
-      emit_quadrature_kernel<2><<<nm_blocks(na, 128), 128, 0, NM_LS(ctx)>>>(na, acc_idx, ctx->cand_im.as<uint32_t>(), ctx->cand_bg.as<uint32_t>(),
-                                                                           ctx->bg_box.as<double>(), ctx->im_verts.as<double>(), nullptr,
-                                                                           ctx->tol, offs.as<uint64_t>(), pts_d, w_d);
+      emit_quadrature_kernel<2, false><<<B, 128, 0, NM_LS(ctx)>>>(na, acc_idx, ci, cb, ctx->bg_box.as<double>(), ctx->im_verts.as<double>(), nullptr,
+                                                                 ctx->tol, offs.as<uint64_t>(), pts_d, w_d, mismatch);
     NM_CUDA(cudaGetLastError());
+    unsigned long long h_mis = 0;
+    NM_CUDA(cudaMemcpyAsync(&h_mis, mismatch, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    NM_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h_mis) return nm_fail(ctx, NM_ERR_STATE, "internal error: %llu pairs emitted a different number of quadrature points than counted", h_mis);
   }
   if (where == NM_HOST) {
     if (points) NM_TRY(nm_download(ctx, points, pts_d, nq * d * sizeof(double), NM_HOST));

@@ -69,10 +69,10 @@ def test_parity_against_c_oracle(c_oracle, name, cycle, boxes):
     ctx.close()
 
 
-@pytest.mark.parametrize("name,cycle", [("disk", 1), ("sphere", 0)])
+@pytest.mark.parametrize("name,cycle", [("disk", 1), ("sphere", 0), ("sphere", 4), ("flower", 6)])
 def test_quadrature_roundtrip(c_oracle, name, cycle):
     """collect -> (points, weights) -> mass matrix from the given quadrature == fused path."""
-    bg, im = make_config(name, cycle, band_only=False)
+    bg, im = make_config(name, cycle, band_only=cycle > 2)
     info = coupling.collect_quadratures_on_overlapped_grids(bg, im, 3, 1e-15)
     off, pts, w = info.q_offset, info.points, info.weights
     assert int(off[-1]) == info.counts["n_qpoints"] == w.shape[0]
