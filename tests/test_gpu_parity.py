@@ -353,3 +353,22 @@ def test_spmv_push_single_gpu():
     assert torch.equal(y1, y_ref)
     assert torch.allclose(y2, y_ref + 1.0, rtol=0, atol=1e-15)
     ctx.close()
+
+
+def test_index_range_limit_is_reported():
+    """A background whose extent spans more than 2^19 finest cells per axis (3D) cannot be indexed by the packed
+    grid key: the library must say so instead of aliasing keys."""
+    from non_matching_test_suite_b200 import _lib
+    from non_matching_test_suite_b200.grids import BackgroundGrid
+    lo = torch.tensor([[0.0, 0.0, 0.0], [0.9, 0.9, 0.9]], dtype=torch.float64)
+    hi = torch.tensor([[1e-7, 1e-7, 1e-7], [1.0, 1.0, 1.0]], dtype=torch.float64)
+    dofs = torch.arange(16, dtype=torch.int32).reshape(2, 8)
+    e = torch.empty(0, dtype=torch.int32)
+    bg = BackgroundGrid(3, lo, hi, dofs, 16, torch.zeros(2, dtype=torch.int32), e, torch.zeros(1, dtype=torch.int64), e,
+                        torch.empty(0, dtype=torch.float64))
+    _, im = make_config("sphere", 0, band_only=False)
+    ctx = coupling.make_context(bg, im, boxes=True)
+    with pytest.raises(_lib.NmError) as err:
+        ctx.intersect(3, 1e-15)
+    assert err.value.code == 3 and "2^19" in str(err.value)
+    ctx.close()
