@@ -180,6 +180,29 @@ int nm_spmv(nm_ctx *ctx, int transpose, const double *x, double *y, int where);
  * all-reduce: only the rows a rank owns cross the links. */
 int nm_spmv_push(nm_ctx *ctx, const double *x, int n_targets, double *const *y_targets, int multicast);
 
+/* ---- interface-penalisation (Nitsche) terms on a caller-supplied quadrature ----
+ * Replaces the arithmetic of assemble_nitsche_with_exact_intersections (code/include/coupling_utilities.h:306-398) and
+ * create_nitsche_rhs_with_exact_intersections (:400-481): for tuple p with background cell background[p] and points
+ * q_offset[p]..q_offset[p+1]
+ *   local(i,j) += coefficient[q] * (penalty / h) * phi_i(xi_q) * phi_j(xi_q) * weights[q]       (:366-370)
+ *   rhs(i)     += coefficient[q] * (penalty / h) * phi_i(xi_q) * rhs_values[q] * weights[q]     (:447-451)
+ * h = diameter of the background cell (:357,:429), xi_q = F^-1(x_q) on the axis-aligned Q1 cell; then
+ * AffineConstraints::distribute_local_to_global, square version (:387-388): rows and columns resolved through the
+ * constraint lines, |local(i,i)| (or the mean |diagonal| of the block if that is zero) added on the diagonal of every
+ * constrained dof; vector version (:458-459): resolved rows only.
+ * `coefficient` / `rhs_values`: values of the reference's Function objects at the points ([n_q]); coefficient may be
+ * NULL (= 1).  `what`: NM_NITSCHE_MATRIX | NM_NITSCHE_RHS (rhs_values required for the latter).
+ * Needs nm_set_background[_boxes] with dofs (or nm_set_background_dofs); no immersed grid and no nm_intersect.
+ * The result is the CONTRIBUTION (to be added to the caller's system matrix / rhs): a CSR matrix n_space x n_space
+ * with sorted columns holding every structural position the reference's add() would touch, and a dense vector. */
+#define NM_NITSCHE_MATRIX 1
+#define NM_NITSCHE_RHS 2
+int nm_assemble_nitsche(nm_ctx *ctx, uint64_t n_pairs, const uint32_t *background, const uint64_t *q_offset, const double *points,
+                        const double *weights, const double *coefficient, const double *rhs_values, double penalty, int what,
+                        int where, uint64_t *nnz);
+/* rowptr[n_space+1], col[nnz], val[nnz], rhs[n_space]; any pointer may be NULL (skipped). */
+int nm_get_nitsche(nm_ctx *ctx, uint64_t *rowptr, uint32_t *col, double *val, double *rhs, int where);
+
 /* Device milliseconds per phase (NM_T_*), `n` entries copied. */
 int nm_get_timings(nm_ctx *ctx, float *ms, int n);
 /* Number of this library's kernel launches since nm_create (cub's internal kernels excluded). */

@@ -24,7 +24,7 @@ PHASES = ["upload", "index", "candidates", "split", "clip", "merge", "transpose"
 # every symbol include/nmgpu.h declares
 SYMBOLS = ["nm_version", "nm_create", "nm_destroy", "nm_last_error", "nm_set_background", "nm_set_background_boxes",
            "nm_set_background_dofs", "nm_set_immersed_dofs", "nm_set_immersed", "nm_flag_overlapped_background", "nm_intersect", "nm_get_candidates", "nm_get_pairs", "nm_get_quadrature",
-           "nm_get_split_codes", "nm_build_sparsity", "nm_assemble", "nm_assemble_from_quadrature", "nm_get_csr",
+           "nm_get_split_codes", "nm_build_sparsity", "nm_assemble", "nm_assemble_from_quadrature", "nm_assemble_nitsche", "nm_get_nitsche", "nm_get_csr",
            "nm_spmv", "nm_spmv_push", "nm_get_timings", "nm_get_launch_count", "nm_device_bytes", "nm_get_stream"]
 
 
@@ -72,6 +72,8 @@ def load():
     L.nm_build_sparsity.argtypes = [P, C.POINTER(U64)]
     L.nm_assemble.argtypes = [P]
     L.nm_assemble_from_quadrature.argtypes = [P, U64, P, P, P, P, P, I]
+    L.nm_assemble_nitsche.argtypes = [P, U64, P, P, P, P, P, P, C.c_double, I, I, C.POINTER(U64)]
+    L.nm_get_nitsche.argtypes = [P, P, P, P, P, I]
     L.nm_get_csr.argtypes = [P, I, P, P, P, I]
     L.nm_spmv.argtypes = [P, I, P, P, I]
     L.nm_spmv_push.argtypes = [P, P, I, C.POINTER(C.c_void_p), I]
@@ -227,6 +229,27 @@ class Context:
         w = _where(im, bg, q_offset, points, weights)
         self._chk(self.L.nm_assemble_from_quadrature(self.h, int(im.shape[0]), _ptr(im)[0], _ptr(bg)[0], _ptr(q_offset)[0],
                                                      _ptr(points)[0], _ptr(weights)[0], w))
+
+    def assemble_nitsche(self, bg, q_offset, points, weights, coefficient=None, rhs_values=None, penalty=1.0, matrix=True):
+        """Nitsche terms on the given quadrature (reference coupling_utilities.h:306-481): returns
+        (rowptr, col, val) of the n_space x n_space contribution (None when matrix=False) and the rhs contribution
+        (None when rhs_values is None), on the device the inputs live on."""
+        what = (1 if matrix else 0) | (2 if rhs_values is not None else 0)
+        args = [a for a in (bg, q_offset, points, weights, coefficient, rhs_values) if a is not None]
+        w = _where(*args)
+        nnz = C.c_uint64(0)
+        self._chk(self.L.nm_assemble_nitsche(self.h, int(bg.shape[0]), _ptr(bg)[0], _ptr(q_offset)[0], _ptr(points)[0], _ptr(weights)[0],
+                                             _ptr(coefficient)[0], _ptr(rhs_values)[0], float(penalty), what, w,
+                                             C.byref(nnz)))
+        dev = "cuda" if w == NM_DEVICE else "cpu"
+        n = self.n_space_dofs
+        rp = col = val = rhs = None
+        if matrix:
+            rp, col, val = self._out(n + 1, torch.int64, dev), self._out(nnz.value, torch.int32, dev), self._out(nnz.value, torch.float64, dev)
+        if rhs_values is not None:
+            rhs = self._out(n, torch.float64, dev)
+        self._chk(self.L.nm_get_nitsche(self.h, _ptr(rp)[0], _ptr(col)[0], _ptr(val)[0], _ptr(rhs)[0], w))
+        return (rp, col, val), rhs
 
     def csr(self, transpose: bool = False, values: bool = True, device="cpu", out=None):
         """CSR of the matrix; `out=(rowptr, col, val)` reuses caller buffers (e.g. pinned host memory)

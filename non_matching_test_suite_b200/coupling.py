@@ -4,6 +4,9 @@ Same names, argument meaning and error behaviour as
   dealii::NonMatching::collect_quadratures_on_overlapped_grids            (code/include/coupling_utilities.h:508-515)
   create_coupling_sparsity_pattern_with_exact_intersections               (code/include/coupling_utilities.h:28-38)
   create_coupling_mass_matrix_with_exact_intersections                    (code/include/coupling_utilities.h:154-168)
+and, as the first widening row, of the interface-penalisation pair
+  assemble_nitsche_with_exact_intersections                               (code/include/coupling_utilities.h:306-398)
+  create_nitsche_rhs_with_exact_intersections                             (code/include/coupling_utilities.h:400-481)
 with the deal.II objects replaced by the flat arrays a wrapper extracts from them
 (`grids.BackgroundGrid` plays GridTools::Cache + DoFHandler + AffineConstraints of the space
 grid, `grids.ImmersedGrid` those of the immersed grid).  The C++ drop-in header with the
@@ -134,3 +137,53 @@ def create_coupling_mass_matrix_with_exact_intersections(space: BackgroundGrid, 
     else:
         ctx.assemble()
     return CouplingMatrix(ctx)
+
+
+def _values_at(fn, points: torch.Tensor) -> Optional[torch.Tensor]:
+    """Function<spacedim>::value_list of the reference: a callable on the [n_q, spacedim] points, a number, or None."""
+    if fn is None:
+        return None
+    if callable(fn):
+        v = fn(points)
+    else:
+        v = torch.full((points.shape[0],), float(fn), dtype=torch.float64, device=points.device)
+    if tuple(v.shape) != (points.shape[0],):
+        raise ValueError("function values must have one entry per quadrature point")
+    return v.to(torch.float64).contiguous()
+
+
+def assemble_nitsche_with_exact_intersections(space: BackgroundGrid, cells_and_quads: IntersectionInfo, nitsche_coefficient=1.0,
+                                              penalty: float = 1.0):
+    """Reference: code/include/coupling_utilities.h:306-398.  Returns the contribution
+    sum_pairs sum_q c(x_q) penalty/h phi_i phi_j w_q, distributed through the space constraints, as CSR
+    (rowptr, col, val) of an n_space x n_space matrix; the caller adds it to its system matrix, as the reference's
+    distribute_local_to_global does in place (:387-388)."""
+    ctx = cells_and_quads.ctx
+    if ctx.n_space_dofs != space.n_dofs:
+        raise ValueError("matrix dimensions do not match the DoF handler")                        # AssertDimension :319-320
+    if len(cells_and_quads) == 0:
+        raise ValueError("The background and immersed mesh must overlap in order to use this function.")   # Assert :323-325
+    if cells_and_quads.points is None:
+        raise ValueError("cells_and_quads carries no quadrature (collect with with_quadrature=True)")
+    pts = cells_and_quads.points.contiguous()
+    csr, _ = ctx.assemble_nitsche(cells_and_quads.space_cell.contiguous(), cells_and_quads.q_offset.contiguous(), pts,
+                                  cells_and_quads.weights.contiguous(), _values_at(nitsche_coefficient, pts), None, penalty)
+    return csr
+
+
+def create_nitsche_rhs_with_exact_intersections(space: BackgroundGrid, cells_and_quads: IntersectionInfo, rhs_function,
+                                                coefficient=1.0, penalty: float = 1.0) -> torch.Tensor:
+    """Reference: code/include/coupling_utilities.h:400-481.  Returns the contribution to the right-hand side
+    sum_pairs sum_q c(x_q) penalty/h phi_i f(x_q) w_q, distributed through the space constraints (:458-459)."""
+    ctx = cells_and_quads.ctx
+    if ctx.n_space_dofs != space.n_dofs:
+        raise ValueError("vector size does not match the DoF handler")                            # AssertDimension :413
+    if cells_and_quads.points is None:
+        raise ValueError("cells_and_quads carries no quadrature (collect with with_quadrature=True)")
+    pts = cells_and_quads.points.contiguous()
+    if len(cells_and_quads) == 0:
+        return torch.zeros(space.n_dofs, dtype=torch.float64, device=pts.device)
+    _, rhs = ctx.assemble_nitsche(cells_and_quads.space_cell.contiguous(), cells_and_quads.q_offset.contiguous(), pts,
+                                  cells_and_quads.weights.contiguous(), _values_at(coefficient, pts), _values_at(rhs_function, pts),
+                                  penalty, matrix=False)
+    return rhs

@@ -69,7 +69,8 @@ static std::vector<DevBuf *> all_buffers(nm_ctx *c)
           &c->im_measure, &c->idx_next, &c->idx_extra_bg, &c->idx_hash, &c->idx_tmp, &c->cand_ptr, &c->cand_tmp, &c->cand_im, &c->cand_bg,
           &c->cand_sumw, &c->cand_local, &c->cand_nq, &c->cand_acc, &c->counters, &c->c_rowstart, &c->c_rowlen, &c->c_col, &c->c_val,
           &c->a_rowptr, &c->a_rowptr32, &c->a_col, &c->a_val, &c->a_cursor, &c->scan_tmp, &c->scratch_a, &c->scratch_b, &c->stage_x,
-          &c->stage_y, &c->h2d_stage};
+          &c->stage_y, &c->h2d_stage, &c->nit_cnt, &c->nit_keys, &c->nit_vals, &c->nit_rkeys, &c->nit_rvals, &c->nit_rowptr,
+          &c->nit_col, &c->nit_val, &c->nit_rhs};
 }
 
 static void free_all(nm_ctx *c)
@@ -500,6 +501,38 @@ int nm_assemble_from_quadrature(nm_ctx *ctx, uint64_t n_pairs, const uint32_t *i
   }
   ctx->local_from_user = true;
   return ensure_matrix(ctx);
+}
+
+int nm_assemble_nitsche(nm_ctx *ctx, uint64_t n_pairs, const uint32_t *background, const uint64_t *q_offset, const double *points,
+                        const double *weights, const double *coefficient, const double *rhs_values, double penalty, int what,
+                        int where, uint64_t *nnz)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->bg_set || !ctx->bg_dofs_set) return nm_fail(ctx, NM_ERR_STATE, "background cells and dofs have not been set");
+  if (!(what & (NM_NITSCHE_MATRIX | NM_NITSCHE_RHS)) || (what & ~(NM_NITSCHE_MATRIX | NM_NITSCHE_RHS)))
+    return nm_fail(ctx, NM_ERR_INVALID, "what must be NM_NITSCHE_MATRIX, NM_NITSCHE_RHS or both");
+  if ((what & NM_NITSCHE_RHS) && !rhs_values && n_pairs) return nm_fail(ctx, NM_ERR_INVALID, "NM_NITSCHE_RHS needs rhs_values");
+  if (n_pairs && (!background || !q_offset || !points || !weights)) return nm_fail(ctx, NM_ERR_INVALID, "null quadrature arrays");
+  if (where != NM_HOST && where != NM_DEVICE) return nm_fail(ctx, NM_ERR_INVALID, "where must be NM_HOST or NM_DEVICE");
+  ctx->nit_has_matrix = ctx->nit_has_rhs = false;
+  NM_TRY(nm_nitsche_run(ctx, n_pairs, background, q_offset, points, weights, coefficient, rhs_values, penalty, what, where));
+  if (nnz) *nnz = ctx->nit_nnz;
+  return NM_OK;
+}
+
+int nm_get_nitsche(nm_ctx *ctx, uint64_t *rowptr, uint32_t *col, double *val, double *rhs, int where)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  if ((rowptr || col || val) && !ctx->nit_has_matrix) return nm_fail(ctx, NM_ERR_STATE, "no Nitsche matrix has been assembled");
+  if (rhs && !ctx->nit_has_rhs) return nm_fail(ctx, NM_ERR_STATE, "no Nitsche right-hand side has been assembled");
+  NM_TRY(nm_download(ctx, rowptr, ctx->nit_rowptr.p, (ctx->n_space_dofs + 1) * 8, where));
+  NM_TRY(nm_download(ctx, col, ctx->nit_col.p, ctx->nit_nnz * 4, where));
+  NM_TRY(nm_download(ctx, val, ctx->nit_val.p, ctx->nit_nnz * 8, where));
+  NM_TRY(nm_download(ctx, rhs, ctx->nit_rhs.p, ctx->n_space_dofs * 8, where));
+  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return NM_OK;
 }
 
 int nm_get_csr(nm_ctx *ctx, int transpose, uint64_t *rowptr, uint32_t *col, double *val, int where)

@@ -104,6 +104,12 @@ struct nm_ctx {
   DevBuf a_cursor;  // scratch
   bool matrix_valid = false;
 
+  // ---- interface-penalisation terms (nm_nitsche.cu): square matrix on the space dofs + right-hand side ----
+  DevBuf nit_cnt, nit_keys, nit_vals, nit_rkeys, nit_rvals;
+  DevBuf nit_rowptr, nit_col, nit_val, nit_rhs;
+  uint64_t nit_nnz = 0;
+  bool nit_has_matrix = false, nit_has_rhs = false;
+
   // ---- scratch ----
   DevBuf scan_tmp, scratch_a, scratch_b, stage_x, stage_y, h2d_stage;
 
@@ -179,6 +185,8 @@ int nm_quadrature_emit(nm_ctx *ctx, uint64_t *q_offset, double *points, double *
 int nm_local_from_quadrature(nm_ctx *ctx, uint64_t n_pairs, const uint32_t *im, const uint32_t *bg, const uint64_t *q_offset,
                              const double *points, const double *weights, int where);
 int nm_matrix_build(nm_ctx *ctx);
+int nm_nitsche_run(nm_ctx *ctx, uint64_t n_pairs, const uint32_t *bg, const uint64_t *q_offset, const double *points,
+                   const double *weights, const double *coefficient, const double *rhs_values, double penalty, int what, int where);
 int nm_spmv_run(nm_ctx *ctx, int transpose, const double *x_dev, double *y_dev);
 int nm_exclusive_scan_u64(nm_ctx *ctx, const uint64_t *in, uint64_t *out, uint64_t n);
 int nm_exclusive_scan_u32_to_u64(nm_ctx *ctx, const uint32_t *in, uint64_t *out, uint64_t n);

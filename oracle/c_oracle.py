@@ -41,6 +41,9 @@ def lib():
         L.nmo_build_csr.restype = C.c_int64
         L.nmo_build_csr.argtypes = [C.c_int, C.c_int64, P, P, P, P, C.c_int64, P, P, P, P,
                                     C.POINTER(P), C.POINTER(P), C.POINTER(P)]
+        L.nmo_nitsche.restype = C.c_int64
+        L.nmo_nitsche.argtypes = [C.c_int, C.c_int64, P, P, P, P, P, P, C.c_double, P, P, P, P, P, P, P,
+                                  C.POINTER(P), C.POINTER(P), C.POINTER(P), P]
         L.nmo_spmv.argtypes = [C.c_int, C.c_int64, C.c_int64, P, P, P, P, P]
         L.nmo_free.argtypes = [P]
         L.nmo_num_threads.restype = C.c_int
@@ -133,6 +136,32 @@ def build_csr(d, acc, local, bg, im):
     for p in (rp, cl, vl):
         lib().nmo_free(p)
     return rowptr, col, val
+
+
+def nitsche(bg, bg_ids, q_offset, points, weights, coefficient=None, rhs_values=None, penalty=1.0):
+    """Nitsche matrix contribution (scipy CSR, duplicates summed, explicit zeros kept) and rhs (or None) on the given
+    quadrature: reference code/include/coupling_utilities.h:306-481 restated in nmo_nitsche."""
+    import scipy.sparse as sp
+    d = bg.spacedim
+    ids = _np(bg_ids, np.uint32); qo = _np(q_offset, np.uint64)
+    pts = _np(points, np.float64); wts = _np(weights, np.float64)
+    cf = None if coefficient is None else _np(coefficient, np.float64)
+    fv = None if rhs_values is None else _np(rhs_values, np.float64)
+    bl, bh = _np(bg.lo, np.float64), _np(bg.hi, np.float64)
+    bd = _np(bg.dofs, np.uint32)
+    has_c = _np(bg.c_dof, np.int64).shape[0] > 0
+    line_of = line_table(bg) if has_c else None
+    cp = _np(bg.c_ptr, np.int64); cm = _np(bg.c_master, np.uint32); cw = _np(bg.c_weight, np.float64)
+    rhs = np.zeros(bg.n_dofs) if fv is not None else None
+    r, c, v = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    n = lib().nmo_nitsche(d, ids.shape[0], _p(ids), _p(qo), _p(pts), _p(wts), _p(cf), _p(fv), float(penalty), _p(bl), _p(bh),
+                          _p(bd), _p(line_of), _p(cp), _p(cm), _p(cw), C.byref(r), C.byref(c), C.byref(v), _p(rhs))
+    rows = _take(r, n, np.uint32).astype(np.int64); cols = _take(c, n, np.uint32).astype(np.int64); vals = _take(v, n, np.float64)
+    for p in (r, c, v):
+        lib().nmo_free(p)
+    A = sp.coo_matrix((vals, (rows, cols)), shape=(bg.n_dofs, bg.n_dofs)).tocsr()
+    A.sum_duplicates(); A.sort_indices()
+    return A, rhs
 
 
 def spmv(transpose, rowptr, col, val, x, n_rows, n_cols):

@@ -529,6 +529,85 @@ int64_t nmo_build_csr(int d, int64_t n_acc, const uint64_t *acc, const double *l
   return nnz;
 }
 
+/* ------------------------------------------------------------------------- */
+/* interface-penalisation (Nitsche) terms on a given quadrature               */
+/* ------------------------------------------------------------------------- */
+/* code/include/coupling_utilities.h:306-398 (matrix) and :400-481 (right-hand side) for FE_Q(1) on axis-aligned
+   cells: per tuple local(i,j) += c_q (penalty/h) phi_i phi_j w_q (:366-370), rhs(i) += c_q (penalty/h) phi_i f_q w_q
+   (:447-451), h = cell->diameter() (:357,:429), then AffineConstraints::distribute_local_to_global
+   [UPSTREAM deal.II 9.4 affine_constraints.templates.h: rows and columns resolved through the lines; for every
+   constrained local dof |local(i,i)|, or the mean of |local(k,k)| when that is zero, is added on its diagonal].
+   Output: unsorted COO records (duplicates to be summed by the caller) and a dense rhs. */
+int64_t nmo_nitsche(int d, int64_t n_pairs, const uint32_t *bg, const uint64_t *q_off, const double *pts, const double *wts,
+                    const double *coeff, const double *fval, double penalty, const double *bg_lo, const double *bg_hi,
+                    const uint32_t *bg_dofs, const int32_t *line_of, const int64_t *c_ptr, const uint32_t *c_master,
+                    const double *c_weight, uint32_t **row_out, uint32_t **col_out, double **val_out, double *rhs)
+{
+  const int nl = 1 << d;
+  int64_t cap = n_pairs * nl * nl + 64, n = 0;
+  uint32_t *R = malloc(sizeof(uint32_t) * (size_t)cap), *Cc = malloc(sizeof(uint32_t) * (size_t)cap);
+  double *V = malloc(sizeof(double) * (size_t)cap);
+  for (int64_t p = 0; p < n_pairs; ++p) {
+    const double *lo = bg_lo + (int64_t)bg[p] * d, *hi = bg_hi + (int64_t)bg[p] * d;
+    double h = 0, L[8][8], F[8];
+    for (int k = 0; k < d; ++k) h += (hi[k] - lo[k]) * (hi[k] - lo[k]);
+    h = sqrt(h);
+    memset(L, 0, sizeof L);
+    memset(F, 0, sizeof F);
+    for (uint64_t q = q_off[p]; q < q_off[p + 1]; ++q) {
+      double xi[3], phi[8];
+      for (int k = 0; k < d; ++k) xi[k] = (pts[q * d + k] - lo[k]) / (hi[k] - lo[k]);
+      for (int i = 0; i < nl; ++i) {
+        double v = 1.0;
+        for (int k = 0; k < d; ++k) v *= ((i >> k) & 1) ? xi[k] : 1.0 - xi[k];
+        phi[i] = v;
+      }
+      const double c = coeff ? coeff[q] : 1.0;
+      for (int i = 0; i < nl; ++i) {
+        for (int j = 0; j < nl; ++j) L[i][j] += c * (penalty / h) * phi[i] * phi[j] * wts[q];
+        if (fval) F[i] += c * (penalty / h) * phi[i] * fval[q] * wts[q];
+      }
+    }
+    const uint32_t *dof = bg_dofs + (int64_t)bg[p] * nl;
+    double avg = 0;
+    for (int i = 0; i < nl; ++i) avg += fabs(L[i][i]);
+    avg /= nl;
+    for (int i = 0; i < nl; ++i) {
+      const int32_t li = line_of ? line_of[dof[i]] : -1;
+      const int64_t ib = li < 0 ? 0 : c_ptr[li], ie = li < 0 ? 1 : c_ptr[li + 1];
+      for (int64_t a = ib; a < ie; ++a) {
+        const uint32_t r = li < 0 ? dof[i] : c_master[a];
+        const double wr = li < 0 ? 1.0 : c_weight[a];
+        if (rhs && fval) rhs[r] += wr * F[i];
+        for (int j = 0; j < nl; ++j) {
+          const int32_t lj = line_of ? line_of[dof[j]] : -1;
+          const int64_t jb = lj < 0 ? 0 : c_ptr[lj], je = lj < 0 ? 1 : c_ptr[lj + 1];
+          for (int64_t b = jb; b < je; ++b) {
+            if (n + 2 > cap) {
+              cap *= 2;
+              R = realloc(R, sizeof(uint32_t) * (size_t)cap); Cc = realloc(Cc, sizeof(uint32_t) * (size_t)cap);
+              V = realloc(V, sizeof(double) * (size_t)cap);
+            }
+            R[n] = r; Cc[n] = lj < 0 ? dof[j] : c_master[b];
+            V[n] = wr * (lj < 0 ? 1.0 : c_weight[b]) * L[i][j];
+            ++n;
+          }
+        }
+      }
+      if (li >= 0) {
+        if (n + 2 > cap) {
+          cap *= 2;
+          R = realloc(R, sizeof(uint32_t) * (size_t)cap); Cc = realloc(Cc, sizeof(uint32_t) * (size_t)cap);
+          V = realloc(V, sizeof(double) * (size_t)cap);
+        }
+        R[n] = dof[i]; Cc[n] = dof[i]; V[n] = fabs(L[i][i]) != 0.0 ? fabs(L[i][i]) : avg; ++n;
+      }
+    }
+  }
+  *row_out = R; *col_out = Cc; *val_out = V;
+  return n;
+}
+
 /* y = A x (transpose = 0) or y = A^T x (transpose = 1); y must be zero-length-correct */
 void nmo_spmv(int transpose, int64_t n_rows, int64_t n_cols, const uint64_t *rowptr, const uint32_t *col,
               const double *val, const double *x, double *y)

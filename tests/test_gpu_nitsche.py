@@ -1,0 +1,117 @@
+"""GPU parity of the interface-penalisation terms (nm_assemble_nitsche) against the oracle on the SAME quadrature:
+reference code/include/coupling_utilities.h:306-481.  Pattern (every structural position the reference's add() touches)
+bit-exact; values within 1e-13 relative Frobenius norm (same points, same formula; only the summation order differs)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from non_matching_test_suite_b200 import _lib, coupling
+from non_matching_test_suite_b200.grids import BackgroundGrid, make_config
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-13
+
+
+def _coef(x):
+    return 2.0 + torch.sin(3.0 * x[:, 0]) * torch.cos(x[:, -1])
+
+
+def _f(x):
+    return torch.exp(-x[:, 0]) * (1.0 + x[:, 1] ** 2)
+
+
+def _csr(t, n):
+    rp, col, val = (a.cpu().numpy() for a in t)
+    return sp.csr_matrix((val, col, rp), shape=(n, n))
+
+
+@pytest.mark.parametrize("name,cycle", [("disk", 0), ("disk", 3), ("flower", 1), ("sphere", 0), ("sphere", 1)])
+def test_nitsche_matches_oracle_on_the_same_quadrature(c_oracle, name, cycle):
+    bg, im = make_config(name, cycle, band_only=False)
+    info = coupling.collect_quadratures_on_overlapped_grids(bg, im, 3, 1e-15)
+    assert len(info) > 0
+    csr = coupling.assemble_nitsche_with_exact_intersections(bg, info, _coef, penalty=10.0)
+    rhs = coupling.create_nitsche_rhs_with_exact_intersections(bg, info, _f, _coef, penalty=10.0)
+    A = _csr(csr, bg.n_dofs)
+    Ar, br = c_oracle.nitsche(bg, info.space_cell, info.q_offset, info.points, info.weights, _coef(info.points), _f(info.points), 10.0)
+    assert np.array_equal(A.indptr, Ar.indptr) and np.array_equal(A.indices, Ar.indices)
+    assert np.linalg.norm(A.data - Ar.data) <= REL_TOL * np.linalg.norm(Ar.data)
+    assert np.linalg.norm(rhs.numpy() - br) <= REL_TOL * np.linalg.norm(br)
+    # symmetric up to rounding (phi_i phi_j), constrained rows hold their diagonal only
+    assert abs(A - A.T).max() <= 1e-14 * abs(A).max()
+    for dof in bg.c_dof.numpy()[:50]:
+        row = A.getrow(int(dof))
+        assert row.nnz <= 1 and (row.nnz == 0 or row.indices[0] == dof)
+    info.ctx.close()
+
+
+@pytest.mark.parametrize("name,cycle", [("disk", 2), ("sphere", 1)])
+def test_nitsche_known_answers_without_constraints(name, cycle):
+    """Partition of unity: with every dof unconstrained, sum_ij A_ij = sum_q c penalty / h w_q and sum_i rhs_i the same
+    with f; constant c = 2 and penalty = 10 as in the drivers (interface_penalisation/1d2d/smooth_disk.cc:435-450)."""
+    bg, im = make_config(name, cycle, band_only=False)
+    e = torch.empty(0, dtype=torch.int32)
+    free = BackgroundGrid(bg.spacedim, bg.lo, bg.hi, bg.dofs, bg.n_dofs, bg.level, e, torch.zeros(1, dtype=torch.int64), e,
+                          torch.empty(0, dtype=torch.float64))
+    info = coupling.collect_quadratures_on_overlapped_grids(free, im, 3, 1e-15)
+    A = _csr(coupling.assemble_nitsche_with_exact_intersections(free, info, 2.0, penalty=10.0), bg.n_dofs)
+    rhs = coupling.create_nitsche_rhs_with_exact_intersections(free, info, _f, 2.0, penalty=10.0).numpy()
+    h = torch.sqrt(((bg.hi - bg.lo) ** 2).sum(dim=1))[info.space_cell.long()]
+    nq = (info.q_offset[1:] - info.q_offset[:-1])
+    per_q = torch.repeat_interleave(h, nq)
+    expect = float((2.0 * 10.0 / per_q * info.weights).sum())
+    assert abs(A.sum() - expect) <= 1e-12 * expect
+    expect_r = float((2.0 * 10.0 / per_q * info.weights * _f(info.points)).sum())
+    assert abs(rhs.sum() - expect_r) <= 1e-12 * abs(expect_r)
+    # and sum_q w_q is the measure of the (triangulated) immersed grid
+    assert abs(float(info.weights.sum()) - float(info.sum_w.sum())) <= 1e-12 * float(info.sum_w.sum())
+    info.ctx.close()
+
+
+def test_nitsche_device_inputs_equal_host_inputs_bitwise():
+    bg, im = make_config("sphere", 1, band_only=False)
+    ctx = coupling.make_context(bg, im, boxes=True)
+    ctx.intersect(3, 1e-15)
+    aim, abg, _ = ctx.pairs()
+    off, pts, w = ctx.quadrature()
+    (rp, col, val), rhs = ctx.assemble_nitsche(abg, off, pts, w, _coef(pts), _f(pts), 10.0)
+    offd, ptsd, wd = ctx.quadrature(device="cuda")
+    assert torch.equal(ptsd.cpu(), pts)
+    (rpd, cold, vald), rhsd = ctx.assemble_nitsche(abg.cuda(), offd, ptsd, wd, _coef(pts).cuda(), _f(pts).cuda(), 10.0)
+    assert rpd.is_cuda and torch.equal(rpd.cpu(), rp) and torch.equal(cold.cpu(), col)
+    assert torch.equal(vald.cpu(), val) and torch.equal(rhsd.cpu(), rhs)
+    # run-to-run reproducible
+    (_, _, val2), rhs2 = ctx.assemble_nitsche(abg, off, pts, w, _coef(pts), _f(pts), 10.0)
+    assert torch.equal(val2, val) and torch.equal(rhs2, rhs)
+    # coefficient = None means 1
+    (_, _, v1), _ = ctx.assemble_nitsche(abg, off, pts, w, None, None, 10.0)
+    (_, _, v2), _ = ctx.assemble_nitsche(abg, off, pts, w, torch.ones_like(w), None, 10.0)
+    assert torch.equal(v1, v2)
+    ctx.close()
+
+
+def test_nitsche_errors():
+    bg, im = make_config("disk", 0, band_only=False)
+    ctx = _lib.Context(0)
+    off = torch.tensor([0, 1], dtype=torch.int64); pts = torch.tensor([[0.5, 0.5]], dtype=torch.float64)
+    w = torch.ones(1, dtype=torch.float64); ids = torch.zeros(1, dtype=torch.int32)
+    with pytest.raises(_lib.NmError) as e:           # nothing set yet
+        ctx.assemble_nitsche(ids, off, pts, w)
+    assert e.value.code == 4
+    coupling.set_grids(ctx, bg, im)
+    with pytest.raises(_lib.NmError) as e:           # cell id out of range
+        ctx.assemble_nitsche(torch.tensor([bg.n_cells], dtype=torch.int32), off, pts, w)
+    assert e.value.code == 1 and "out of range" in str(e.value)
+    with pytest.raises(_lib.NmError) as e:           # nothing assembled after a failed call
+        ctx._chk(ctx.L.nm_get_nitsche(ctx.h, None, None, None, _lib._ptr(w)[0], 0))
+    assert e.value.code == 4
+    # empty input is fine and gives an empty contribution
+    (rp, col, val), _ = ctx.assemble_nitsche(torch.empty(0, dtype=torch.int32), torch.zeros(1, dtype=torch.int64),
+                                             torch.empty(0, 2, dtype=torch.float64), torch.empty(0, dtype=torch.float64))
+    assert col.numel() == 0 and int(rp.abs().sum()) == 0
+    with pytest.raises(ValueError):
+        info = coupling.IntersectionInfo(ctx, ids[:0], ids[:0], w[:0], off[:1], pts[:0], w[:0])
+        coupling.assemble_nitsche_with_exact_intersections(bg, info)
+    ctx.close()
