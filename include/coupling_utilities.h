@@ -9,8 +9,13 @@
 //
 // Implemented instantiations: <2,1,2> and <3,2,3> with FE_Q(1) on Cartesian background cells and
 // FE_DGQ(0) on the immersed grid (every LM configuration in data/*.prm).  Anything else raises
-// ExcNotImplemented -- there is no CPU fallback.  The Nitsche entry points of the reference
-// header (:306-481) are not part of this path; keep the reference's own versions for them.
+// ExcNotImplemented -- there is no CPU fallback.
+//
+// First widening row, same boundary:
+//   assemble_nitsche_with_exact_intersections<...>                       reference :306-398
+//   create_nitsche_rhs_with_exact_intersections<...>                     reference :400-481
+// for FE_Q(1) on Cartesian background cells; the Function objects are evaluated here on the host
+// (value_list, as the reference does at :349,:438-441), everything else runs on the GPU.
 //
 // Build: add -I<repo>/include and link -L<repo>/non_matching_test_suite_b200 -lnmgpu.
 // The GPU is chosen with the environment variable NMGPU_DEVICE (default 0; with MPI set it to the
@@ -18,6 +23,7 @@
 #ifndef nmgpu_coupling_utilities_h
 #define nmgpu_coupling_utilities_h
 
+#include <deal.II/base/function.h>
 #include <deal.II/base/point.h>
 #include <deal.II/base/quadrature.h>
 #include <deal.II/dofs/dof_handler.h>
@@ -46,7 +52,7 @@ namespace nmgpu_detail {
 // calls of one refinement cycle find each other through the triangulation addresses.
 struct Session {
   nm_ctx *ctx = nullptr;
-  bool grids_set = false;
+  bool grids_set = false, space_set = false;
   std::uint64_t n_space = 0, n_immersed = 0;
   std::vector<unsigned int> space_local_of_active;     // active_cell_index -> row in the arrays sent to the GPU (or -1)
   std::vector<unsigned int> immersed_local_of_active;
@@ -146,22 +152,18 @@ void set_grids(Session &s, const Triangulation<dim0, spacedim> &space, const Map
                                    NM_HOST));
   check(s, nm_set_immersed(s.ctx, dim1, spacedim, s.n_immersed, v1.data(), nullptr, 1, 0, NM_HOST));
   s.grids_set = true;
+  s.space_set = true;
 }
 
-// DoF indices per cell + the lines of the closed AffineConstraints object as CSR.
-template <int dim0, int dim1, int spacedim, typename number>
-void set_dofs(Session &s, const DoFHandler<dim0, spacedim> &space_dh, const DoFHandler<dim1, spacedim> &immersed_dh,
-              const AffineConstraints<number> &constraints, const AffineConstraints<number> &immersed_constraints)
+// DoF indices of the background cells + the lines of the closed AffineConstraints object as CSR.
+template <int dim0, int spacedim, typename number>
+void set_space_dofs(Session &s, const DoFHandler<dim0, spacedim> &space_dh, const AffineConstraints<number> &constraints)
 {
   const auto &space_fe = space_dh.get_fe();
-  const auto &immersed_fe = immersed_dh.get_fe();
-  AssertThrow(space_fe.n_components() == 1 && immersed_fe.n_components() == 1, ExcNotImplemented());
+  AssertThrow(space_fe.n_components() == 1, ExcNotImplemented());
   AssertThrow(space_fe.n_dofs_per_cell() == (1u << dim0), ExcMessage("nmgpu: the background space must be FE_Q(1)"));
-  AssertThrow(immersed_fe.n_dofs_per_cell() == 1, ExcMessage("nmgpu: the immersed space must be FE_DGQ(0)"));
-  AssertThrow(immersed_constraints.n_constraints() == 0, ExcNotImplemented());
-
-  std::vector<std::uint32_t> d0(s.n_space * (1u << dim0)), d1(s.n_immersed);
-  std::vector<types::global_dof_index> tmp0(1u << dim0), tmp1(1);
+  std::vector<std::uint32_t> d0(s.n_space * (1u << dim0));
+  std::vector<types::global_dof_index> tmp0(1u << dim0);
   for (const auto &cell : space_dh.active_cell_iterators()) {
     const unsigned int l = s.space_local_of_active[cell->active_cell_index()];
     if (l == static_cast<unsigned int>(-1))
@@ -169,10 +171,6 @@ void set_dofs(Session &s, const DoFHandler<dim0, spacedim> &space_dh, const DoFH
     cell->get_dof_indices(tmp0);
     for (unsigned int i = 0; i < tmp0.size(); ++i)
       d0[std::size_t(l) * tmp0.size() + i] = static_cast<std::uint32_t>(tmp0[i]);
-  }
-  for (const auto &cell : immersed_dh.active_cell_iterators()) {
-    cell->get_dof_indices(tmp1);
-    d1[s.immersed_local_of_active[cell->active_cell_index()]] = static_cast<std::uint32_t>(tmp1[0]);
   }
   std::vector<std::uint32_t> c_dof, c_master;
   std::vector<std::uint64_t> c_ptr(1, 0);
@@ -189,7 +187,76 @@ void set_dofs(Session &s, const DoFHandler<dim0, spacedim> &space_dh, const DoFH
     }
   check(s, nm_set_background_dofs(s.ctx, d0.data(), space_dh.n_dofs(), c_dof.size(), c_dof.data(), c_ptr.data(), c_master.data(),
                                   c_weight.data(), NM_HOST));
+}
+
+template <int dim0, int dim1, int spacedim, typename number>
+void set_dofs(Session &s, const DoFHandler<dim0, spacedim> &space_dh, const DoFHandler<dim1, spacedim> &immersed_dh,
+              const AffineConstraints<number> &constraints, const AffineConstraints<number> &immersed_constraints)
+{
+  const auto &immersed_fe = immersed_dh.get_fe();
+  AssertThrow(immersed_fe.n_components() == 1, ExcNotImplemented());
+  AssertThrow(immersed_fe.n_dofs_per_cell() == 1, ExcMessage("nmgpu: the immersed space must be FE_DGQ(0)"));
+  AssertThrow(immersed_constraints.n_constraints() == 0, ExcNotImplemented());
+  set_space_dofs<dim0, spacedim>(s, space_dh, constraints);
+  std::vector<std::uint32_t> d1(s.n_immersed);
+  std::vector<types::global_dof_index> tmp1(1);
+  for (const auto &cell : immersed_dh.active_cell_iterators()) {
+    cell->get_dof_indices(tmp1);
+    d1[s.immersed_local_of_active[cell->active_cell_index()]] = static_cast<std::uint32_t>(tmp1[0]);
+  }
   check(s, nm_set_immersed_dofs(s.ctx, d1.data(), 1, immersed_dh.n_dofs(), NM_HOST));
+}
+
+// Background geometry only (the Nitsche terms do not look at the immersed grid).
+template <int dim0, int spacedim>
+void set_space_grid(Session &s, const Triangulation<dim0, spacedim> &space, const Mapping<dim0, spacedim> &mapping0)
+{
+  std::vector<double> lo, hi;
+  gather_boxes(space, mapping0, lo, hi, s.space_local_of_active, nullptr);
+  s.n_space = lo.size() / spacedim;
+  check(s, nm_set_background_boxes(s.ctx, spacedim, s.n_space, lo.data(), hi.data(), nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr,
+                                   NM_HOST));
+  s.space_set = true;
+}
+
+// Flatten the tuples for nm_assemble_nitsche and evaluate the caller's Function objects at the points.
+template <int dim0, int dim1, int spacedim, typename number>
+void nitsche_from_info(Session &s,
+                       const std::vector<std::tuple<typename Triangulation<dim0, spacedim>::cell_iterator,
+                                                    typename Triangulation<dim1, spacedim>::cell_iterator, Quadrature<spacedim>>> &info,
+                       const bool owned_only, const Function<spacedim, number> &coefficient, const Function<spacedim, number> *rhs_function,
+                       const double penalty, const int what)
+{
+  std::vector<std::uint32_t> bg;
+  std::vector<std::uint64_t> off(1, 0);
+  std::vector<double> pts, w, cv, fv;
+  std::vector<number> tmp;
+  for (const auto &t : info) {
+    const auto &cell = std::get<0>(t);
+    if (!cell->is_active() || (owned_only && !cell->is_locally_owned()))   // reference :345 / :428
+      continue;
+    const unsigned int l = s.space_local_of_active[cell->active_cell_index()];
+    if (l == static_cast<unsigned int>(-1))
+      continue;
+    bg.push_back(l);
+    const auto &q = std::get<2>(t);
+    tmp.resize(q.size());
+    coefficient.value_list(q.get_points(), tmp);
+    cv.insert(cv.end(), tmp.begin(), tmp.end());
+    if (rhs_function) {
+      rhs_function->value_list(q.get_points(), tmp);
+      fv.insert(fv.end(), tmp.begin(), tmp.end());
+    }
+    for (unsigned int k = 0; k < q.size(); ++k) {
+      for (unsigned int d = 0; d < spacedim; ++d)
+        pts.push_back(q.point(k)[d]);
+      w.push_back(q.weight(k));
+    }
+    off.push_back(w.size());
+  }
+  std::uint64_t nnz = 0;
+  check(s, nm_assemble_nitsche(s.ctx, bg.size(), bg.data(), off.data(), pts.data(), w.data(), cv.data(), rhs_function ? fv.data() : nullptr,
+                               penalty, what, NM_HOST, &nnz));
 }
 
 // Hand the caller's (cell, cell, Quadrature) tuples to the device: inverse mapping, shape
@@ -330,6 +397,80 @@ void create_coupling_mass_matrix_with_exact_intersections(
                  /*col_indices_are_sorted=*/true);
     }
   matrix.compress(VectorOperation::add); // reference :289
+}
+
+// Reference: code/include/coupling_utilities.h:306-398.  Adds
+//   sum_q c(x_q) (penalty / h) phi_i(x_q) phi_j(x_q) w_q,   h = space_cell->diameter(),
+// distributed through `space_constraints`, to `matrix` (which must already hold these positions, as the reference's
+// system matrix does); like the reference it does not compress.
+template <int dim0, int dim1, int spacedim, typename Matrix>
+void assemble_nitsche_with_exact_intersections(
+    const DoFHandler<dim0, spacedim> &space_dh,
+    const std::vector<std::tuple<typename Triangulation<dim0, spacedim>::cell_iterator,
+                                 typename Triangulation<dim1, spacedim>::cell_iterator, Quadrature<spacedim>>> &cells_and_quads,
+    Matrix &matrix, const AffineConstraints<typename Matrix::value_type> &space_constraints, const ComponentMask &space_comps,
+    const Mapping<dim0, spacedim> &space_mapping, const Function<spacedim, typename Matrix::value_type> &nitsche_coefficient,
+    const double penalty)
+{
+  AssertDimension(matrix.m(), space_dh.n_dofs());
+  AssertDimension(matrix.n(), space_dh.n_dofs());
+  Assert((dim1 <= dim0) && (dim0 <= spacedim), ExcMessage("This function can only work if dim1<=dim0<=spacedim"));
+  Assert(cells_and_quads.size() > 0,
+         ExcMessage("The background and immersed mesh must overlap in order to use this function."));
+  AssertThrow(space_comps.size() <= 1, ExcNotImplemented());
+
+  auto &s = nmgpu_detail::session(&space_dh.get_triangulation(), &std::get<1>(cells_and_quads.front())->get_triangulation());
+  if (!s.space_set)
+    nmgpu_detail::set_space_grid<dim0, spacedim>(s, space_dh.get_triangulation(), space_mapping);
+  nmgpu_detail::set_space_dofs<dim0, spacedim>(s, space_dh, space_constraints);
+  nmgpu_detail::nitsche_from_info<dim0, dim1, spacedim, typename Matrix::value_type>(s, cells_and_quads, /*owned_only=*/true,
+                                                                                     nitsche_coefficient, nullptr, penalty,
+                                                                                     NM_NITSCHE_MATRIX);
+  const types::global_dof_index n = space_dh.n_dofs();
+  std::vector<std::uint64_t> rowptr(n + 1);
+  nmgpu_detail::check(s, nm_get_nitsche(s.ctx, rowptr.data(), nullptr, nullptr, nullptr, NM_HOST));
+  std::vector<std::uint32_t> col(rowptr[n]);
+  std::vector<double> val(rowptr[n]);
+  nmgpu_detail::check(s, nm_get_nitsche(s.ctx, nullptr, col.data(), val.data(), nullptr, NM_HOST));
+  std::vector<types::global_dof_index> cols;
+  std::vector<typename Matrix::value_type> vals;
+  for (types::global_dof_index r = 0; r < n; ++r)
+    if (rowptr[r + 1] > rowptr[r]) {
+      cols.assign(col.begin() + rowptr[r], col.begin() + rowptr[r + 1]);
+      vals.assign(val.begin() + rowptr[r], val.begin() + rowptr[r + 1]);
+      matrix.add(r, static_cast<types::global_dof_index>(cols.size()), cols.data(), vals.data(), /*elide_zero_values=*/true,
+                 /*col_indices_are_sorted=*/true);
+    }
+}
+
+// Reference: code/include/coupling_utilities.h:400-481.  Adds
+//   sum_q c(x_q) (penalty / h) phi_i(x_q) f(x_q) w_q
+// distributed through `space_constraints`, to `rhs_vector`; no compress, like the reference.
+template <int dim0, int dim1, int spacedim, typename Vector>
+void create_nitsche_rhs_with_exact_intersections(
+    const DoFHandler<dim0, spacedim> &space_dh,
+    const std::vector<std::tuple<typename Triangulation<dim0, spacedim>::cell_iterator,
+                                 typename Triangulation<dim1, spacedim>::cell_iterator, Quadrature<spacedim>>> &cells_and_quads,
+    Vector &rhs_vector, const AffineConstraints<double> &space_constraints, const Mapping<dim0, spacedim> &space_mapping,
+    const Function<spacedim, double> &rhs_function, const Function<spacedim, double> &coefficient, const double penalty)
+{
+  AssertDimension(rhs_vector.size(), space_dh.n_dofs());
+  Assert(dim1 <= dim0, ExcMessage("This function can only work if dim1<=dim0"));
+  if (cells_and_quads.empty())
+    return;
+  auto &s = nmgpu_detail::session(&space_dh.get_triangulation(), &std::get<1>(cells_and_quads.front())->get_triangulation());
+  if (!s.space_set)
+    nmgpu_detail::set_space_grid<dim0, spacedim>(s, space_dh.get_triangulation(), space_mapping);
+  nmgpu_detail::set_space_dofs<dim0, spacedim>(s, space_dh, space_constraints);
+  // the reference's rhs loop takes every active cell (:428), not only locally owned ones; the arrays sent to the GPU
+  // hold the locally owned cells, which is the same set on one rank
+  nmgpu_detail::nitsche_from_info<dim0, dim1, spacedim, double>(s, cells_and_quads, /*owned_only=*/false, coefficient, &rhs_function,
+                                                                penalty, NM_NITSCHE_RHS);
+  std::vector<double> rhs(space_dh.n_dofs());
+  nmgpu_detail::check(s, nm_get_nitsche(s.ctx, nullptr, nullptr, nullptr, rhs.data(), NM_HOST));
+  for (types::global_dof_index r = 0; r < space_dh.n_dofs(); ++r)
+    if (rhs[r] != 0.)
+      rhs_vector(r) += rhs[r];
 }
 
 } // namespace NonMatching

@@ -35,9 +35,39 @@ public:
   const Point<dim> &point(unsigned k) const { return pts[k]; }
   double weight(unsigned k) const { return wts[k]; }
   const std::vector<double> &get_weights() const { return wts; }
+  const std::vector<Point<dim>> &get_points() const { return pts; }
 private:
   std::vector<Point<dim>> pts;
   std::vector<double> wts;
+};
+
+template <int dim, typename number = double> class Function {
+public:
+  virtual ~Function() = default;
+  virtual number value(const Point<dim> &p, const unsigned int component = 0) const = 0;
+  virtual void value_list(const std::vector<Point<dim>> &points, std::vector<number> &values, const unsigned int component = 0) const
+  {
+    for (std::size_t i = 0; i < points.size(); ++i) values[i] = value(points[i], component);
+  }
+};
+namespace Functions {
+template <int dim, typename number = double> class ConstantFunction : public Function<dim, number> {
+public:
+  explicit ConstantFunction(number v) : v(v) {}
+  number value(const Point<dim> &, const unsigned int = 0) const override { return v; }
+private:
+  number v;
+};
+} // namespace Functions
+
+template <typename T> class Vector {
+public:
+  explicit Vector(std::size_t n) : v(n, T(0)) {}
+  std::size_t size() const { return v.size(); }
+  T &operator()(std::size_t i) { return v[i]; }
+  const T &operator()(std::size_t i) const { return v[i]; }
+private:
+  std::vector<T> v;
 };
 
 template <int dim, int spacedim> class DoFHandler;
@@ -52,6 +82,8 @@ public:
     unsigned idx = 0;
     unsigned active_cell_index() const { return idx; }
     bool is_locally_owned() const { return true; }
+    bool is_active() const { return true; }
+    const Triangulation &get_triangulation() const { return *t; }
     int level() const { return 0; }
     int index() const { return int(idx); }
     void get_dof_indices(std::vector<types::global_dof_index> &v) const;

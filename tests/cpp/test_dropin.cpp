@@ -9,6 +9,15 @@
 
 using namespace dealii;
 
+// the Function objects a Nitsche driver passes (interface_penalisation/1d2d/smooth_disk.cc:435-450 uses
+// ConstantFunction(2.0) and its Solution class); non-constant here so that the per-point values matter
+template <int spacedim> struct Coefficient : Function<spacedim> {
+  double value(const Point<spacedim> &p, const unsigned int = 0) const override { return 2.0 + p[0]; }
+};
+template <int spacedim> struct BoundaryValue : Function<spacedim> {
+  double value(const Point<spacedim> &p, const unsigned int = 0) const override { return 1.0 + p[1] * p[1]; }
+};
+
 template <int dim0, int dim1, int spacedim> int run(std::ifstream &in, const char *out_path)
 {
   Triangulation<dim0, spacedim> space;
@@ -76,6 +85,22 @@ template <int dim0, int dim1, int spacedim> int run(std::ifstream &in, const cha
       auto it = matrix.data[r].find(c);
       std::fprintf(f, "%u %u %.17g\n", r, c, it == matrix.data[r].end() ? 0.0 : it->second);
     }
+  // the two interface-penalisation calls of the Nitsche drivers, on the same tuples
+  StubSparseMatrix<double> system_matrix(n_space_dofs, n_space_dofs);
+  Vector<double> system_rhs(n_space_dofs);
+  NonMatching::assemble_nitsche_with_exact_intersections<dim0, dim1, spacedim>(space_dh, cells_and_quads, system_matrix, constraints,
+                                                                              ComponentMask(), space_mapping, Coefficient<spacedim>(),
+                                                                              10.0);
+  NonMatching::create_nitsche_rhs_with_exact_intersections<dim0, dim1, spacedim>(space_dh, cells_and_quads, system_rhs, constraints,
+                                                                                space_mapping, BoundaryValue<spacedim>(),
+                                                                                Functions::ConstantFunction<spacedim>(2.0), 10.0);
+  if (system_matrix.compressed) return 6;   // the reference leaves compress() to the driver
+  std::size_t n_nit = 0;
+  for (const auto &r : system_matrix.data) n_nit += r.size();
+  std::fprintf(f, "%zu\n", n_nit);
+  for (unsigned r = 0; r < n_space_dofs; ++r)
+    for (const auto &e : system_matrix.data[r]) std::fprintf(f, "%u %u %.17g\n", r, e.first, e.second);
+  for (unsigned r = 0; r < n_space_dofs; ++r) std::fprintf(f, "%.17g\n", system_rhs(r));
   std::fclose(f);
   // error behaviour of the reference: AssertThrow(degree > 0)
   try {

@@ -66,3 +66,22 @@ def test_cpp_driver_matches_oracle(tmp_path, c_oracle, name, cycle):
     assert np.array_equal(got[:, 0].astype(np.int64), rows)
     assert np.array_equal(got[:, 1].astype(np.uint32), ref["col"])
     assert np.linalg.norm(got[:, 2] - ref["val"]) <= 1e-12 * np.linalg.norm(ref["val"])
+    # Nitsche matrix and rhs of the same driver against the oracle on the same quadrature (the library's own, which
+    # is bitwise reproducible, collected again here)
+    import scipy.sparse as sp
+    from non_matching_test_suite_b200 import coupling
+    info = coupling.collect_quadratures_on_overlapped_grids(bg, im, 3, 1e-15)
+    A, b = c_oracle.nitsche(bg, info.space_cell, info.q_offset, info.points, info.weights, 2.0 + info.points[:, 0],
+                            1.0 + info.points[:, 1] ** 2, 10.0)
+    # rhs call of the driver used the constant coefficient 2
+    _, b = c_oracle.nitsche(bg, info.space_cell, info.q_offset, info.points, info.weights, np.full(info.weights.shape[0], 2.0),
+                            1.0 + info.points[:, 1] ** 2, 10.0)
+    n_nit = int(lines[2 + nnz])
+    ent = np.array([[float(x) for x in l.split()] for l in lines[3 + nnz:3 + nnz + n_nit]])
+    G = sp.csr_matrix((ent[:, 2], (ent[:, 0].astype(np.int64), ent[:, 1].astype(np.int64))), shape=(bg.n_dofs, bg.n_dofs))
+    A.eliminate_zeros()                      # matrix.add elides exact zeros
+    assert abs(G - A).max() <= 1e-13 * abs(A).max()
+    assert (G != 0).nnz == (A != 0).nnz
+    rhs = np.array([float(x) for x in lines[3 + nnz + n_nit:3 + nnz + n_nit + bg.n_dofs]])
+    assert np.linalg.norm(rhs - b) <= 1e-13 * np.linalg.norm(b)
+    info.ctx.close()
