@@ -181,8 +181,12 @@ def run_native(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO") and not os.environ.get("NMGPU_KEEP_NCCL_DEBUG"):
-        os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's banner goes to stdout: rank 0 must print exactly one JSON line
+    # NCCL writes its version banner / debug lines to stdout; rank 0 must print exactly one JSON line there, so NCCL's
+    # own output is sent to stderr.  NCCL honours NCCL_DEBUG_FILE only above the VERSION level, hence VERSION -> WARN
+    # (which still prints the banner, now to stderr).
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)

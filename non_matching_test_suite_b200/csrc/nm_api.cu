@@ -70,7 +70,7 @@ static std::vector<DevBuf *> all_buffers(nm_ctx *c)
           &c->cand_sumw, &c->cand_local, &c->cand_nq, &c->cand_acc, &c->counters, &c->c_rowstart, &c->c_rowlen, &c->c_col, &c->c_val,
           &c->a_rowptr, &c->a_rowptr32, &c->a_col, &c->a_val, &c->a_cursor, &c->scan_tmp, &c->scratch_a, &c->scratch_b, &c->stage_x,
           &c->stage_y, &c->h2d_stage, &c->nit_cnt, &c->nit_keys, &c->nit_vals, &c->nit_rkeys, &c->nit_rvals, &c->nit_rowptr,
-          &c->nit_col, &c->nit_val, &c->nit_rhs};
+          &c->nit_col, &c->nit_val, &c->nit_rhs, &c->row_bits, &c->row_prefix, &c->row_ids};
 }
 
 static void free_all(nm_ctx *c)
@@ -123,6 +123,7 @@ int nm_create(nm_ctx **out, int device)
   { const char *e = getenv("NMGPU_FORCE_QUADRATURE"); ctx->force_quadrature_kernel = e && e[0] == '1'; }
   { const char *e = getenv("NMGPU_FORCE_GENERAL_MERGE"); ctx->force_general_merge = e && e[0] == '1'; }
   { const char *e = getenv("NMGPU_SPMV_VARIANT"); ctx->spmv_variant = e ? atoi(e) : 0; }
+  { const char *e = getenv("NMGPU_COMPACT_ROWS"); ctx->compact_rows_env = e ? (e[0] == '1' ? 1 : 0) : -1; }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   if (nm_ensure(ctx, ctx->counters, 64 * sizeof(uint64_t)) != NM_OK) { delete ctx; return NM_ERR_NOMEM; }
@@ -542,6 +543,15 @@ int nm_get_csr(nm_ctx *ctx, int transpose, uint64_t *rowptr, uint32_t *col, doub
   NM_TRY(ensure_matrix(ctx));
   PhaseTimer tm(ctx, NM_T_DOWNLOAD);
   if (!transpose) {
+    if (ctx->compact_rows && rowptr) {   // expand the compact row offsets to one per global dof
+      uint64_t *rp = rowptr;
+      if (where == NM_HOST) {
+        NM_TRY(nm_ensure(ctx, ctx->stage_x, (ctx->n_space_dofs + 2) * 8));
+        rp = ctx->stage_x.as<uint64_t>();
+      }
+      NM_TRY(nm_stored_rowptr_global(ctx, rp));
+      if (where == NM_HOST) NM_TRY(nm_download(ctx, rowptr, rp, (ctx->n_space_dofs + 1) * 8, NM_HOST));
+    } else
     NM_TRY(nm_download(ctx, rowptr, ctx->a_rowptr.p, (ctx->n_space_dofs + 1) * 8, where));
     NM_TRY(nm_download(ctx, col, ctx->a_col.p, ctx->nnz * 4, where));
     NM_TRY(nm_download(ctx, val, ctx->a_val.p, ctx->nnz * 8, where));

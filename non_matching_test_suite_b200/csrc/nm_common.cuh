@@ -102,6 +102,13 @@ struct nm_ctx {
   DevBuf a_col;     // u32 (immersed dof)
   DevBuf a_val;     // f64
   DevBuf a_cursor;  // scratch
+  // compact-row mode (sharded grids: the global dof count is far larger than what this rank touches): the stored
+  // orientation keeps only the rows with entries; a_rowptr has n_local_rows + 1 entries and row r is global dof
+  // row_ids[r].  row_bits = bitmap of touched dofs, row_prefix[w] = touched dofs before word w (rank queries).
+  bool compact_rows = false;
+  int compact_rows_env = -1;  // NMGPU_COMPACT_ROWS: 0 / 1 force, -1 automatic
+  uint64_t n_local_rows = 0;
+  DevBuf row_bits, row_prefix, row_ids;
   bool matrix_valid = false;
 
   // ---- interface-penalisation terms (nm_nitsche.cu): square matrix on the space dofs + right-hand side ----
@@ -188,5 +195,6 @@ int nm_matrix_build(nm_ctx *ctx);
 int nm_nitsche_run(nm_ctx *ctx, uint64_t n_pairs, const uint32_t *bg, const uint64_t *q_offset, const double *points,
                    const double *weights, const double *coefficient, const double *rhs_values, double penalty, int what, int where);
 int nm_spmv_run(nm_ctx *ctx, int transpose, const double *x_dev, double *y_dev);
+int nm_stored_rowptr_global(nm_ctx *ctx, uint64_t *rowptr_dev);
 int nm_exclusive_scan_u64(nm_ctx *ctx, const uint64_t *in, uint64_t *out, uint64_t n);
 int nm_exclusive_scan_u32_to_u64(nm_ctx *ctx, const uint32_t *in, uint64_t *out, uint64_t n);

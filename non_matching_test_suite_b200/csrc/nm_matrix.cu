@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint
                                                        const uint32_t *__restrict__ c_master, const double *__restrict__ c_weight,
                                                        uint64_t *__restrict__ rowstart, uint32_t *__restrict__ rowlen,
                                                        uint32_t *__restrict__ out_col, double *__restrict__ out_val, uint64_t capacity,
-                                                       unsigned long long *cursor, unsigned *problem, uint32_t *__restrict__ a_cnt)
+                                                       unsigned long long *cursor, unsigned *problem, uint32_t *__restrict__ a_cnt, int mark_bits)
 {
   constexpr int NG = 256 / GROUP;                 // groups per block
   constexpr unsigned CAP = SLOTS * 3 / 4;         // distinct dofs a group accepts
@@ -415,8 +415,15 @@ __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint
         ra += (k4.x < ka) + (k4.y < ka) + (k4.z < ka) + (k4.w < ka);
         rb += (k4.x < kb) + (k4.y < kb) + (k4.z < kb) + (k4.w < kb);
       }
-      if (ea < D) { out_col[dst + ra] = ka; out_val[dst + ra] = vals[list[ea]]; atomicAdd(&a_cnt[ka], 1u); }
-      if (eb < D) { out_col[dst + rb] = kb; out_val[dst + rb] = vals[list[eb]]; atomicAdd(&a_cnt[kb], 1u); }
+      // per-dof entry counts for the transpose -- or, in compact-row mode, only the bitmap of touched dofs
+      if (ea < D) {
+        out_col[dst + ra] = ka; out_val[dst + ra] = vals[list[ea]];
+        if (mark_bits) atomicOr(&a_cnt[ka >> 5], 1u << (ka & 31)); else atomicAdd(&a_cnt[ka], 1u);
+      }
+      if (eb < D) {
+        out_col[dst + rb] = kb; out_val[dst + rb] = vals[list[eb]];
+        if (mark_bits) atomicOr(&a_cnt[kb >> 5], 1u << (kb & 31)); else atomicAdd(&a_cnt[kb], 1u);
+      }
     }
     if (lane == 0) { rowlen[m] = D; rowstart[m] = dst; }
     chunk_pos += D;
@@ -462,9 +469,21 @@ __global__ void __launch_bounds__(256) merge_rows_block(unsigned n_big, const ui
 // ---------------------------------------------------------------------------------------
 // transpose C (rows = immersed cells) -> stored orientation (rows = space dofs)
 // ---------------------------------------------------------------------------------------
+// global dof -> row of the stored matrix: identity, or the rank of the dof among the touched dofs
+struct RowMap {
+  const uint32_t *bits;     // nullptr: identity
+  const uint64_t *prefix;
+  __device__ __forceinline__ uint32_t operator()(uint32_t dof) const
+  {
+    if (!bits) return dof;
+    const uint32_t w = dof >> 5;
+    return (uint32_t)prefix[w] + __popc(bits[w] & ((1u << (dof & 31)) - 1u));
+  }
+};
+
 template <int LANES>
-__global__ void t_count(uint64_t n_im, const uint64_t *__restrict__ rowstart, const uint32_t *__restrict__ rowlen,
-                        const uint32_t *__restrict__ col, uint32_t *__restrict__ cnt)
+__global__ void t_mark(uint64_t n_im, const uint64_t *__restrict__ rowstart, const uint32_t *__restrict__ rowlen,
+                       const uint32_t *__restrict__ col, uint32_t *__restrict__ bits)
 {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t m = t / LANES;
@@ -472,13 +491,49 @@ __global__ void t_count(uint64_t n_im, const uint64_t *__restrict__ rowstart, co
   if (m >= n_im) return;
   const uint64_t s = rowstart[m];
   const uint32_t n = rowlen[m];
-  for (uint32_t k = l; k < n; k += LANES) atomicAdd(&cnt[col[s + k]], 1u);
+  for (uint32_t k = l; k < n; k += LANES) { const uint32_t d = col[s + k]; atomicOr(&bits[d >> 5], 1u << (d & 31)); }
+}
+
+__global__ void bits_popc(uint64_t nw, const uint32_t *__restrict__ bits, uint32_t *__restrict__ out)
+{
+  const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < nw) out[w] = __popc(bits[w]);
+  if (w == nw) out[w] = 0;
+}
+
+__global__ void row_ids_kernel(uint64_t nw, const uint32_t *__restrict__ bits, const uint64_t *__restrict__ prefix, uint32_t *__restrict__ ids)
+{
+  const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nw) return;
+  uint32_t b = bits[w];
+  uint64_t o = prefix[w];
+  while (b) { const int k = __ffs(b) - 1; ids[o++] = (uint32_t)(w * 32 + k); b &= b - 1; }
+}
+
+// row offsets per GLOBAL dof from the compact ones (nm_get_csr): an untouched dof gets the offset of the next touched one
+__global__ void expand_rowptr(uint64_t n_rows, RowMap map, const uint64_t *__restrict__ rowptr_local, uint64_t *__restrict__ out)
+{
+  const uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d <= n_rows) out[d] = rowptr_local[map((uint32_t)d)];
+}
+
+template <int LANES>
+__global__ void t_count(uint64_t n_im, const uint64_t *__restrict__ rowstart, const uint32_t *__restrict__ rowlen,
+                        const uint32_t *__restrict__ col, RowMap map, uint32_t *__restrict__ cnt)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t m = t / LANES;
+  const unsigned l = t % LANES;
+  if (m >= n_im) return;
+  const uint64_t s = rowstart[m];
+  const uint32_t n = rowlen[m];
+  for (uint32_t k = l; k < n; k += LANES) atomicAdd(&cnt[map(col[s + k])], 1u);
 }
 
 template <int LANES>
 __global__ void t_scatter(uint64_t n_im, const uint64_t *__restrict__ rowstart, const uint32_t *__restrict__ rowlen,
                           const uint32_t *__restrict__ col, const double *__restrict__ val, const uint32_t *__restrict__ im_dofs,
-                          const uint64_t *__restrict__ a_rowptr, uint32_t *__restrict__ cursor, uint32_t *__restrict__ a_col,
+                          RowMap map, const uint64_t *__restrict__ a_rowptr, uint32_t *__restrict__ cursor, uint32_t *__restrict__ a_col,
                           double *__restrict__ a_val)
 {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -489,7 +544,7 @@ __global__ void t_scatter(uint64_t n_im, const uint64_t *__restrict__ rowstart, 
   const uint32_t n = rowlen[m];
   const uint32_t c = im_dofs[m];
   for (uint32_t k = l; k < n; k += LANES) {
-    const uint32_t r = col[s + k];
+    const uint32_t r = map(col[s + k]);
     const uint64_t pos = a_rowptr[r] + atomicAdd(&cursor[r], 1u);
     a_col[pos] = c;
     a_val[pos] = val[s + k];
@@ -571,7 +626,8 @@ __device__ inline double row_dot(const uint32_t *__restrict__ col, const double 
 
 template <int LANES, int UNROLL, typename PTR>
 __global__ void __launch_bounds__(256) spmv_csr(uint64_t n_rows, const PTR *__restrict__ rowptr, const uint32_t *__restrict__ col,
-                                                const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y)
+                                                const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
+                                                const uint32_t *__restrict__ row_ids)
 {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t r = t / LANES;
@@ -580,7 +636,7 @@ __global__ void __launch_bounds__(256) spmv_csr(uint64_t n_rows, const PTR *__re
   if (r < n_rows) s = row_dot<LANES, UNROLL>(col, val, x, rowptr[r], rowptr[r + 1], l);
 #pragma unroll
   for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, LANES);
-  if (r < n_rows && l == 0) y[r] = s;
+  if (r < n_rows && l == 0) y[row_ids ? row_ids[r] : r] = s;   // compact-row mode: y was zeroed, row r is dof row_ids[r]
 }
 
 // Ct.vmult fused with its reduction over NVLink: every non-empty row result is added straight into
@@ -595,17 +651,19 @@ struct PushTargets {
 
 template <int UNROLL, typename PTR, bool MULTICAST>
 __global__ void __launch_bounds__(128) spmv_csr_push(uint64_t n_rows, const PTR *__restrict__ rowptr, const uint32_t *__restrict__ col,
-                                                     const double *__restrict__ val, const double *__restrict__ x, PushTargets T)
+                                                     const double *__restrict__ val, const double *__restrict__ x, PushTargets T,
+                                                     const uint32_t *__restrict__ row_ids)
 {
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_rows) return;
   const uint64_t b = rowptr[r], e = rowptr[r + 1];
   if (b == e) return;
   const double s = row_dot<1, UNROLL>(col, val, x, b, e, 0u);
+  const uint64_t g = row_ids ? row_ids[r] : r;
   if (MULTICAST) {
-    asm volatile("multimem.red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(T.p[0] + r), "d"(s) : "memory");
+    asm volatile("multimem.red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(T.p[0] + g), "d"(s) : "memory");
   } else {
-    for (int t = 0; t < T.n; ++t) asm volatile("red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(T.p[t] + r), "d"(s) : "memory");
+    for (int t = 0; t < T.n; ++t) asm volatile("red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(T.p[t] + g), "d"(s) : "memory");
   }
 }
 
@@ -687,18 +745,27 @@ static int matrix_build_fast(nm_ctx *ctx, bool *done)
   NM_TRY(nm_ensure(ctx, ctx->c_rowlen, (n_im + 1) * sizeof(uint32_t)));
   NM_TRY(nm_ensure(ctx, ctx->c_col, (capacity + 1) * sizeof(uint32_t)));
   NM_TRY(nm_ensure(ctx, ctx->c_val, (capacity + 1) * sizeof(double)));
-  NM_TRY(nm_ensure(ctx, ctx->a_cursor, (n_rows + 2) * sizeof(uint32_t) * 2));
+  uint32_t *dof_marks = nullptr;   // per-dof counts, or the bitmap of touched dofs in compact-row mode
+  if (ctx->compact_rows) {
+    const uint64_t nw = n_rows / 32 + 2;
+    NM_TRY(nm_ensure(ctx, ctx->row_bits, nw * sizeof(uint32_t)));
+    NM_CUDA(cudaMemsetAsync(ctx->row_bits.p, 0, nw * sizeof(uint32_t), ctx->stream));
+    dof_marks = ctx->row_bits.as<uint32_t>();
+  } else {
+    NM_TRY(nm_ensure(ctx, ctx->a_cursor, (n_rows + 2) * sizeof(uint32_t) * 2));
+    NM_CUDA(cudaMemsetAsync(ctx->a_cursor.p, 0, (n_rows + 2) * sizeof(uint32_t) * 2, ctx->stream));
+    dof_marks = ctx->a_cursor.as<uint32_t>();
+  }
   NM_TRY(nm_ensure(ctx, ctx->counters, 64 * sizeof(uint64_t)));
   unsigned long long *cursor = ctx->counters.as<unsigned long long>() + 20;
   unsigned *problem = ctx->counters.as<unsigned>() + 44;
   NM_CUDA(cudaMemsetAsync(cursor, 0, 16, ctx->stream));
-  NM_CUDA(cudaMemsetAsync(ctx->a_cursor.p, 0, (n_rows + 2) * sizeof(uint32_t) * 2, ctx->stream));
   KernelTimer km(ctx, NM_T_K_MERGE);
   merge_rows_fast<NL, GROUP, SLOTS, FAST_CHUNK><<<(unsigned)blocks, 256, 0, NM_LS(ctx)>>>(
       n_im, ctx->cand_ptr.as<uint64_t>(), ctx->cand_bg.as<uint32_t>(), ctx->cand_acc.as<uint8_t>(), ctx->cand_local.as<double>(),
       ctx->bg_dofs.as<uint32_t>(), ctx->line_of.as<int32_t>(), ctx->c_ptr.as<uint64_t>(), ctx->c_master.as<uint32_t>(),
       ctx->c_weight.as<double>(), ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(),
-      ctx->c_val.as<double>(), capacity, cursor, problem, ctx->a_cursor.as<uint32_t>());
+      ctx->c_val.as<double>(), capacity, cursor, problem, dof_marks, ctx->compact_rows ? 1 : 0);
   km.stop();
   NM_CUDA(cudaGetLastError());
   unsigned h_problem = 0;
@@ -717,6 +784,10 @@ static int matrix_build_t(nm_ctx *ctx)
   const uint64_t n_im = ctx->n_im, n_rows = ctx->n_space_dofs;
   ctx->matrix_valid = false;
   ctx->nnz = 0;
+  // sharded grids carry the global dof numbering: keep per-dof arrays out of the step when this rank can touch only a
+  // small part of the dofs (each cell has 2^d of them)
+  ctx->compact_rows = ctx->compact_rows_env >= 0 ? ctx->compact_rows_env == 1 : n_rows > 4 * ctx->n_bg;
+  ctx->n_local_rows = n_rows;
   {
     bool done = false;
     NM_TRY(matrix_build_fast<NL>(ctx, &done));
@@ -787,16 +858,44 @@ static int matrix_build_t(nm_ctx *ctx)
 template <int NL>
 static int transpose_rows(nm_ctx *ctx, bool counts_ready)
 {
-  const uint64_t n_im = ctx->n_im, n_rows = ctx->n_space_dofs;
+  const uint64_t n_im = ctx->n_im, n_dofs = ctx->n_space_dofs;
   PhaseTimer tt(ctx, NM_T_TRANSPOSE);
+  constexpr int TL = NL == 8 ? 8 : 4;
+  RowMap map{nullptr, nullptr};
+  uint64_t n_rows = n_dofs;   // rows of the stored matrix: all dofs, or only the touched ones
+  if (ctx->compact_rows) {
+    const uint64_t nw = n_dofs / 32 + 1;   // the bitmap holds one more (zero) word so that rank(n_dofs) is defined
+    if (!counts_ready) {                   // general merge path: the bitmap has not been filled yet
+      NM_TRY(nm_ensure(ctx, ctx->row_bits, (nw + 1) * sizeof(uint32_t)));
+      NM_CUDA(cudaMemsetAsync(ctx->row_bits.p, 0, (nw + 1) * sizeof(uint32_t), ctx->stream));
+      if (n_im) {
+        t_mark<TL><<<nm_blocks(n_im * TL, 256), 256, 0, NM_LS(ctx)>>>(n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(),
+                                                                      ctx->c_col.as<uint32_t>(), ctx->row_bits.as<uint32_t>());
+        NM_CUDA(cudaGetLastError());
+      }
+    }
+    NM_TRY(nm_ensure(ctx, ctx->scratch_b, (nw + 2) * sizeof(uint32_t)));
+    NM_TRY(nm_ensure(ctx, ctx->row_prefix, (nw + 2) * sizeof(uint64_t)));
+    bits_popc<<<nm_blocks(nw + 1, 256), 256, 0, NM_LS(ctx)>>>(nw, ctx->row_bits.as<uint32_t>(), ctx->scratch_b.as<uint32_t>());
+    NM_CUDA(cudaGetLastError());
+    NM_TRY(nm_exclusive_scan_u32_to_u64(ctx, ctx->scratch_b.as<uint32_t>(), ctx->row_prefix.as<uint64_t>(), nw + 1));
+    NM_CUDA(cudaMemcpyAsync(&n_rows, ctx->row_prefix.as<uint64_t>() + nw, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    NM_CUDA(cudaStreamSynchronize(ctx->stream));
+    NM_TRY(nm_ensure(ctx, ctx->row_ids, (n_rows + 1) * sizeof(uint32_t)));
+    row_ids_kernel<<<nm_blocks(nw, 256), 256, 0, NM_LS(ctx)>>>(nw, ctx->row_bits.as<uint32_t>(), ctx->row_prefix.as<uint64_t>(),
+                                                               ctx->row_ids.as<uint32_t>());
+    NM_CUDA(cudaGetLastError());
+    map = RowMap{ctx->row_bits.as<uint32_t>(), ctx->row_prefix.as<uint64_t>()};
+    counts_ready = false;   // the merge marked bits, the counts per compact row are taken below
+  }
+  ctx->n_local_rows = n_rows;
   NM_TRY(nm_ensure(ctx, ctx->a_cursor, (n_rows + 2) * sizeof(uint32_t) * 2));
   NM_TRY(nm_ensure(ctx, ctx->a_rowptr, (n_rows + 2) * sizeof(uint64_t)));
   uint32_t *cnt = ctx->a_cursor.as<uint32_t>(), *cursor = cnt + (n_rows + 2);
   if (!counts_ready) NM_CUDA(cudaMemsetAsync(cnt, 0, (n_rows + 2) * sizeof(uint32_t) * 2, ctx->stream));
-  constexpr int TL = NL == 8 ? 8 : 4;
   if (n_im && !counts_ready) {
     t_count<TL><<<nm_blocks(n_im * TL, 256), 256, 0, NM_LS(ctx)>>>(n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(),
-                                                                   ctx->c_col.as<uint32_t>(), cnt);
+                                                                   ctx->c_col.as<uint32_t>(), map, cnt);
     NM_CUDA(cudaGetLastError());
   }
   NM_TRY(nm_exclusive_scan_u32_to_u64(ctx, cnt, ctx->a_rowptr.as<uint64_t>(), n_rows + 1));
@@ -809,7 +908,7 @@ static int transpose_rows(nm_ctx *ctx, bool counts_ready)
   if (n_im) {
     t_scatter<TL><<<nm_blocks(n_im * TL, 256), 256, 0, NM_LS(ctx)>>>(
         n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(), ctx->c_val.as<double>(),
-        ctx->im_dofs.as<uint32_t>(), ctx->a_rowptr.as<uint64_t>(), cursor, ctx->a_col.as<uint32_t>(), ctx->a_val.as<double>());
+        ctx->im_dofs.as<uint32_t>(), map, ctx->a_rowptr.as<uint64_t>(), cursor, ctx->a_col.as<uint32_t>(), ctx->a_val.as<double>());
     NM_CUDA(cudaGetLastError());
   }
   if (n_rows) {
@@ -829,31 +928,50 @@ static int transpose_rows(nm_ctx *ctx, bool counts_ready)
   return NM_OK;
 }
 
+// row offsets of the stored orientation, one per global dof (+1), whatever the internal row mode
+int nm_stored_rowptr_global(nm_ctx *ctx, uint64_t *rowptr_dev)
+{
+  const uint64_t n_dofs = ctx->n_space_dofs;
+  if (!ctx->compact_rows) {
+    NM_CUDA(cudaMemcpyAsync(rowptr_dev, ctx->a_rowptr.p, (n_dofs + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    return NM_OK;
+  }
+  const RowMap map{ctx->row_bits.as<uint32_t>(), ctx->row_prefix.as<uint64_t>()};
+  expand_rowptr<<<nm_blocks(n_dofs + 1, 256), 256, 0, NM_LS(ctx)>>>(n_dofs, map, ctx->a_rowptr.as<uint64_t>(), rowptr_dev);
+  NM_CUDA(cudaGetLastError());
+  return NM_OK;
+}
+
 int nm_matrix_build(nm_ctx *ctx) { return ctx->spacedim == 3 ? matrix_build_t<8>(ctx) : matrix_build_t<4>(ctx); }
 
 int nm_spmv_run(nm_ctx *ctx, int transpose, const double *x, double *y)
 {
-  const uint64_t n_rows = ctx->n_space_dofs, n_im = ctx->n_im;
+  const uint64_t n_rows = ctx->n_local_rows, n_im = ctx->n_im;
   PhaseTimer tm(ctx, transpose ? NM_T_SPMV_T : NM_T_SPMV);
   if (!transpose) {
+    const uint32_t *ids = nullptr;
+    if (ctx->compact_rows) {   // only the touched rows are computed; the rest of y is zero
+      NM_CUDA(cudaMemsetAsync(y, 0, ctx->n_space_dofs * sizeof(double), ctx->stream));
+      ids = ctx->row_ids.as<uint32_t>();
+    }
     const double avg = n_rows ? (double)ctx->nnz / (double)n_rows : 0;
     const uint64_t *rp = ctx->a_rowptr.as<uint64_t>();
     const uint32_t *cl = ctx->a_col.as<uint32_t>();
     const double *vl = ctx->a_val.as<double>();
     if (n_rows) {
-      if (avg > 24) spmv_csr<8, 4, uint64_t><<<nm_blocks(n_rows * 8, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y);
-      else if (avg > 8) spmv_csr<4, 4, uint64_t><<<nm_blocks(n_rows * 4, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y);
-      else if (ctx->spmv_variant / 10 == 1) spmv_csr<1, 4, uint64_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y);
-      else if (ctx->spmv_variant / 10 == 2) spmv_csr<2, 2, uint64_t><<<nm_blocks(n_rows * 2, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y);
-      else if (ctx->spmv_variant / 10 == 3) spmv_csr<1, 8, uint64_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y);
-      else if (ctx->spmv_variant / 10 == 4) spmv_csr<1, 3, uint64_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y);
-      else if (ctx->spmv_variant / 10 == 5) spmv_csr<1, 2, uint64_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y);
-      else if (ctx->a_rowptr32_valid && ctx->spmv_variant / 10 == 6) spmv_csr<1, 8, uint32_t><<<nm_blocks(n_rows, 128), 128, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr32.as<uint32_t>(), cl, vl, x, y);
-      else if (ctx->a_rowptr32_valid && ctx->spmv_variant / 10 == 7) spmv_csr<1, 6, uint32_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr32.as<uint32_t>(), cl, vl, x, y);
-      else if (ctx->a_rowptr32_valid && ctx->spmv_variant / 10 == 8) spmv_csr<1, 12, uint32_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr32.as<uint32_t>(), cl, vl, x, y);
-      else if (ctx->a_rowptr32_valid && ctx->spmv_variant / 10 == 9) spmv_csr<1, 8, uint32_t><<<nm_blocks(n_rows, 64), 64, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr32.as<uint32_t>(), cl, vl, x, y);
-      else if (ctx->a_rowptr32_valid) spmv_csr<1, 8, uint32_t><<<nm_blocks(n_rows, 128), 128, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr32.as<uint32_t>(), cl, vl, x, y);
-      else spmv_csr<1, 8, uint64_t><<<nm_blocks(n_rows, 128), 128, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y);
+      if (avg > 24) spmv_csr<8, 4, uint64_t><<<nm_blocks(n_rows * 8, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y, ids);
+      else if (avg > 8) spmv_csr<4, 4, uint64_t><<<nm_blocks(n_rows * 4, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y, ids);
+      else if (ctx->spmv_variant / 10 == 1) spmv_csr<1, 4, uint64_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y, ids);
+      else if (ctx->spmv_variant / 10 == 2) spmv_csr<2, 2, uint64_t><<<nm_blocks(n_rows * 2, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y, ids);
+      else if (ctx->spmv_variant / 10 == 3) spmv_csr<1, 8, uint64_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y, ids);
+      else if (ctx->spmv_variant / 10 == 4) spmv_csr<1, 3, uint64_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y, ids);
+      else if (ctx->spmv_variant / 10 == 5) spmv_csr<1, 2, uint64_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y, ids);
+      else if (ctx->a_rowptr32_valid && ctx->spmv_variant / 10 == 6) spmv_csr<1, 8, uint32_t><<<nm_blocks(n_rows, 128), 128, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr32.as<uint32_t>(), cl, vl, x, y, ids);
+      else if (ctx->a_rowptr32_valid && ctx->spmv_variant / 10 == 7) spmv_csr<1, 6, uint32_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr32.as<uint32_t>(), cl, vl, x, y, ids);
+      else if (ctx->a_rowptr32_valid && ctx->spmv_variant / 10 == 8) spmv_csr<1, 12, uint32_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr32.as<uint32_t>(), cl, vl, x, y, ids);
+      else if (ctx->a_rowptr32_valid && ctx->spmv_variant / 10 == 9) spmv_csr<1, 8, uint32_t><<<nm_blocks(n_rows, 64), 64, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr32.as<uint32_t>(), cl, vl, x, y, ids);
+      else if (ctx->a_rowptr32_valid) spmv_csr<1, 8, uint32_t><<<nm_blocks(n_rows, 128), 128, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr32.as<uint32_t>(), cl, vl, x, y, ids);
+      else spmv_csr<1, 8, uint64_t><<<nm_blocks(n_rows, 128), 128, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y, ids);
     }
   } else {
     NM_CUDA(cudaMemsetAsync(y, 0, ctx->n_im_dofs * sizeof(double), ctx->stream));
@@ -881,7 +999,8 @@ int nm_spmv_run(nm_ctx *ctx, int transpose, const double *x, double *y)
 
 int nm_spmv_push_run(nm_ctx *ctx, const double *x, int n_targets, double *const *targets, int multicast)
 {
-  const uint64_t n_rows = ctx->n_space_dofs;
+  const uint64_t n_rows = ctx->n_local_rows;
+  const uint32_t *ids = ctx->compact_rows ? ctx->row_ids.as<uint32_t>() : nullptr;
   PushTargets T;
   T.n = n_targets;
   for (int i = 0; i < 16; ++i) T.p[i] = i < n_targets ? targets[i] : nullptr;
@@ -891,11 +1010,11 @@ int nm_spmv_push_run(nm_ctx *ctx, const double *x, int n_targets, double *const 
   if (n_rows) {
     const unsigned B = nm_blocks(n_rows, 128);
     if (ctx->a_rowptr32_valid) {
-      if (multicast) spmv_csr_push<8, uint32_t, true><<<B, 128, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr32.as<uint32_t>(), cl, vl, x, T);
-      else spmv_csr_push<8, uint32_t, false><<<B, 128, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr32.as<uint32_t>(), cl, vl, x, T);
+      if (multicast) spmv_csr_push<8, uint32_t, true><<<B, 128, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr32.as<uint32_t>(), cl, vl, x, T, ids);
+      else spmv_csr_push<8, uint32_t, false><<<B, 128, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr32.as<uint32_t>(), cl, vl, x, T, ids);
     } else {
-      if (multicast) spmv_csr_push<8, uint64_t, true><<<B, 128, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr.as<uint64_t>(), cl, vl, x, T);
-      else spmv_csr_push<8, uint64_t, false><<<B, 128, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr.as<uint64_t>(), cl, vl, x, T);
+      if (multicast) spmv_csr_push<8, uint64_t, true><<<B, 128, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr.as<uint64_t>(), cl, vl, x, T, ids);
+      else spmv_csr_push<8, uint64_t, false><<<B, 128, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr.as<uint64_t>(), cl, vl, x, T, ids);
     }
   }
   NM_CUDA(cudaGetLastError());

@@ -372,3 +372,35 @@ def test_index_range_limit_is_reported():
         ctx.intersect(3, 1e-15)
     assert err.value.code == 3 and "2^19" in str(err.value)
     ctx.close()
+
+
+@pytest.mark.parametrize("name,cycle", [("disk", 2), ("sphere", 1)])
+@pytest.mark.parametrize("general_merge", [False, True])
+def test_compact_row_mode_is_the_same_matrix(monkeypatch, name, cycle, general_merge):
+    """Compact-row storage of the stored orientation (used when a shard touches a small part of the global dofs,
+    forced here with NMGPU_COMPACT_ROWS=1): identical CSR, identical products, identical fused push."""
+    bg, im = make_config(name, cycle, band_only=False)
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(im.n_dofs, dtype=torch.float64, generator=g) * 2 - 1
+    u = torch.rand(bg.n_dofs, dtype=torch.float64, generator=g) * 2 - 1
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("NMGPU_COMPACT_ROWS", mode)
+        if general_merge:
+            monkeypatch.setenv("NMGPU_FORCE_GENERAL_MERGE", "1")
+        ctx = coupling.make_context(bg, im, boxes=True)
+        ctx.intersect(3, 1e-15)
+        rp, col, val = ctx.csr(transpose=False)
+        rpd, cold, vald = ctx.csr(transpose=False, device="cuda")
+        assert torch.equal(rpd.cpu(), rp) and torch.equal(cold.cpu(), col) and torch.equal(vald.cpu(), val)
+        y = ctx.spmv(x, transpose=False)
+        yd = ctx.spmv(x.cuda(), transpose=False)
+        assert torch.equal(yd.cpu(), y)
+        z = ctx.spmv(u, transpose=True)
+        t1 = torch.zeros(bg.n_dofs, dtype=torch.float64, device="cuda")
+        ctx.spmv_push(x.cuda(), [t1.data_ptr()])
+        assert torch.equal(t1.cpu(), y)
+        out[mode] = (rp, col, val, y, z)
+        ctx.close()
+    for a, b in zip(out["0"], out["1"]):
+        assert torch.equal(a, b)
