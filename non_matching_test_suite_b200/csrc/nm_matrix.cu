@@ -530,6 +530,9 @@ __global__ void t_count(uint64_t n_im, const uint64_t *__restrict__ rowstart, co
   for (uint32_t k = l; k < n; k += LANES) atomicAdd(&cnt[map(col[s + k])], 1u);
 }
 
+// The chain per entry is col -> (row offset, cursor atomic) -> two stores, all to scattered addresses: the kernel is
+// bound by memory latency, so every lane keeps T_UNROLL independent chains in flight.
+constexpr int T_UNROLL = 4;
 template <int LANES>
 __global__ void t_scatter(uint64_t n_im, const uint64_t *__restrict__ rowstart, const uint32_t *__restrict__ rowlen,
                           const uint32_t *__restrict__ col, const double *__restrict__ val, const uint32_t *__restrict__ im_dofs,
@@ -543,11 +546,26 @@ __global__ void t_scatter(uint64_t n_im, const uint64_t *__restrict__ rowstart, 
   const uint64_t s = rowstart[m];
   const uint32_t n = rowlen[m];
   const uint32_t c = im_dofs[m];
-  for (uint32_t k = l; k < n; k += LANES) {
-    const uint32_t r = map(col[s + k]);
-    const uint64_t pos = a_rowptr[r] + atomicAdd(&cursor[r], 1u);
-    a_col[pos] = c;
-    a_val[pos] = val[s + k];
+  for (uint32_t k0 = l; k0 < n; k0 += LANES * T_UNROLL) {
+    uint32_t r[T_UNROLL];
+    double v[T_UNROLL];
+    uint64_t pos[T_UNROLL];
+#pragma unroll
+    for (int u = 0; u < T_UNROLL; ++u) {
+      const uint32_t k = k0 + u * LANES;
+      const bool ok = k < n;
+      r[u] = ok ? col[s + k] : 0xffffffffu;
+      v[u] = ok ? val[s + k] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < T_UNROLL; ++u)
+      if (r[u] != 0xffffffffu) { r[u] = map(r[u]); }
+#pragma unroll
+    for (int u = 0; u < T_UNROLL; ++u)
+      if (k0 + u * LANES < n) pos[u] = a_rowptr[r[u]] + atomicAdd(&cursor[r[u]], 1u);
+#pragma unroll
+    for (int u = 0; u < T_UNROLL; ++u)
+      if (k0 + u * LANES < n) { a_col[pos[u]] = c; a_val[pos[u]] = v[u]; }
   }
 }
 
@@ -561,11 +579,17 @@ __device__ inline void cswap(uint32_t &ka, double &va, uint32_t &kb, double &vb)
   ka = k; kb = K; va = v; vb = V;
 }
 
-__global__ void t_sort_rows(uint64_t n_rows, const uint64_t *__restrict__ rowptr, uint32_t *__restrict__ col, double *__restrict__ val)
+// rowptr32 (optional): 32-bit copy of the row offsets for the SpMV, written on the way
+__global__ void t_sort_rows(uint64_t n_rows, const uint64_t *__restrict__ rowptr, uint32_t *__restrict__ col, double *__restrict__ val,
+                            uint32_t *__restrict__ rowptr32)
 {
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_rows) return;
   const uint64_t s = rowptr[r], e = rowptr[r + 1];
+  if (rowptr32) {
+    rowptr32[r] = (uint32_t)s;
+    if (r + 1 == n_rows) rowptr32[n_rows] = (uint32_t)e;
+  }
   const uint64_t n = e - s;
   if (n <= 1) return;
   if (n <= 8) {
@@ -693,7 +717,7 @@ __global__ void __attribute__((unused)) rowlen_to_u64(uint64_t n, const uint32_t
   if (i == n) out[i] = 0;
 }
 
-__global__ void narrow_rowptr(uint64_t n, const uint64_t *__restrict__ in, uint32_t *__restrict__ out)
+__global__ void __attribute__((unused)) narrow_rowptr(uint64_t n, const uint64_t *__restrict__ in, uint32_t *__restrict__ out)
 {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (uint32_t)in[i];
@@ -911,17 +935,19 @@ static int transpose_rows(nm_ctx *ctx, bool counts_ready)
         ctx->im_dofs.as<uint32_t>(), map, ctx->a_rowptr.as<uint64_t>(), cursor, ctx->a_col.as<uint32_t>(), ctx->a_val.as<double>());
     NM_CUDA(cudaGetLastError());
   }
-  if (n_rows) {
-    t_sort_rows<<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr.as<uint64_t>(), ctx->a_col.as<uint32_t>(), ctx->a_val.as<double>());
-    NM_CUDA(cudaGetLastError());
-  }
-  // 32-bit row offsets for the SpMV when they fit (halves the row-pointer traffic)
+  // 32-bit row offsets for the SpMV when they fit (halves the row-pointer traffic), written by the sort kernel
   ctx->a_rowptr32_valid = false;
+  uint32_t *rp32 = nullptr;
   if (nnz < 0xffffffffULL) {
     NM_TRY(nm_ensure(ctx, ctx->a_rowptr32, (n_rows + 2) * sizeof(uint32_t)));
-    narrow_rowptr<<<nm_blocks(n_rows + 1, 256), 256, 0, NM_LS(ctx)>>>(n_rows + 1, ctx->a_rowptr.as<uint64_t>(), ctx->a_rowptr32.as<uint32_t>());
-    NM_CUDA(cudaGetLastError());
+    rp32 = ctx->a_rowptr32.as<uint32_t>();
+    if (n_rows == 0) NM_CUDA(cudaMemsetAsync(rp32, 0, 8, ctx->stream));
     ctx->a_rowptr32_valid = true;
+  }
+  if (n_rows) {
+    t_sort_rows<<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr.as<uint64_t>(), ctx->a_col.as<uint32_t>(), ctx->a_val.as<double>(),
+                                                                rp32);
+    NM_CUDA(cudaGetLastError());
   }
   tt.stop();
   ctx->matrix_valid = true;
