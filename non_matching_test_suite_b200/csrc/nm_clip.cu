@@ -555,11 +555,20 @@ __device__ inline bool item_clip_polygon(const double *__restrict__ box, const d
   unsigned long long poly = 0x210ULL;  // pool indices, 4 bits per polygon position
   int n = 3, nv = 3;
   constexpr unsigned long long M6 = 0x0041041041041041ULL;  // bit 0 of every 6-bit group
+  // Every lane walks only the planes that cut ITS polygon (lowest first): the trip count of the warp is the largest
+  // number of cutting planes of a lane, not six, and no lane idles through planes it does not need.  A plane that has
+  // been applied is all-inside afterwards (new vertices carry `forced`), so it is never picked again.
 #pragma unroll 1
-  for (int p = 0; p < 6; ++p) {
+  while (true) {
+    // AND of the outcodes of all n positions (positions >= n read as inside)
+    const unsigned long long cf = code | ~((1ULL << (6 * n)) - 1ULL);
+    const unsigned long long a1 = cf & (cf >> 30);            // groups 0..4 &= groups 5..9
+    const unsigned long long a2 = a1 & (a1 >> 12);            // group 0 &= 2, group 1 &= 3
+    const unsigned all_in = (unsigned)(a2 & (a2 >> 6) & (a1 >> 24)) & 63u;
+    if (all_in == 63u) break;
+    const int p = __ffs(~all_in & 63u) - 1;
     const unsigned long long full6 = M6 & ((1ULL << (6 * n)) - 1ULL);
     const unsigned long long in6 = (code >> p) & full6;
-    if (in6 == full6) continue;
     if (in6 == 0ULL) return false;
     const int axis = p >> 1;
     const double sgn = (p & 1) ? -1.0 : 1.0, bound = (p & 1) ? H[axis] : 0.0;
