@@ -584,42 +584,45 @@ __device__ inline bool item_clip_polygon(const double *__restrict__ box, const d
     const unsigned forced = (2u << p) - 1u;   // planes already applied count as inside for a new vertex
     unsigned long long np = 0, nc = 0;
     int m = 0;
-    {  // entering edge: last outside vertex -> first inside vertex
-      const int vp = (int)((poly >> (4 * (s == 0 ? n - 1 : s - 1))) & 15u), vq = (int)(pr & 15u);
-      const double dp = sgn * (P.c[axis][vp] - bound), dq = sgn * (P.c[axis][vq] - bound);
-      if (dq > 0.0) {
-        const double tt = dp * __drcp_rn(dp - dq);
-        double x[3];
+    // The pool lives in local memory: fetch the four end points of the entering and the leaving edge in ONE round of
+    // loads (all indices come from the bit lists), then work in registers.
+    const int ve_p = (int)((poly >> (4 * (s == 0 ? n - 1 : s - 1))) & 15u), ve_q = (int)(pr & 15u);        // outside -> first inside
+    const int vl_p = (int)((pr >> (4 * (len - 1))) & 15u), vl_q = (int)((pr >> (4 * len)) & 15u);           // last inside -> outside
+    double ep[3], eq[3], lp[3], lq[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) x[k] = P.c[k][vp] + tt * (P.c[k][vq] - P.c[k][vp]);
-        x[axis] = bound;  // on the plane by construction
+    for (int k = 0; k < 3; ++k) { ep[k] = P.c[k][ve_p]; eq[k] = P.c[k][ve_q]; lp[k] = P.c[k][vl_p]; lq[k] = P.c[k][vl_q]; }
+    const double e_dp = sgn * ((axis == 0 ? ep[0] : axis == 1 ? ep[1] : ep[2]) - bound);
+    const double e_dq = sgn * ((axis == 0 ? eq[0] : axis == 1 ? eq[1] : eq[2]) - bound);
+    const double l_dp = sgn * ((axis == 0 ? lp[0] : axis == 1 ? lp[1] : lp[2]) - bound);
+    const double l_dq = sgn * ((axis == 0 ? lq[0] : axis == 1 ? lq[1] : lq[2]) - bound);
+    if (e_dq > 0.0) {  // entering edge
+      const double tt = e_dp * __drcp_rn(e_dp - e_dq);
+      double x[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) P.c[k][nv] = x[k];
-        np = (unsigned long long)nv;
-        nc = (unsigned long long)(outcode(x[0], x[1], x[2], H) | forced);
-        m = 1;
-        ++nv;
-      }
+      for (int k = 0; k < 3; ++k) x[k] = ep[k] + tt * (eq[k] - ep[k]);
+      if (axis == 0) x[0] = bound; else if (axis == 1) x[1] = bound; else x[2] = bound;  // on the plane by construction
+#pragma unroll
+      for (int k = 0; k < 3; ++k) P.c[k][nv] = x[k];
+      np = (unsigned long long)nv;
+      nc = (unsigned long long)(outcode(x[0], x[1], x[2], H) | forced);
+      m = 1;
+      ++nv;
     }
     np |= (pr & ((1ULL << (4 * len)) - 1ULL)) << (4 * m);
     nc |= (cr & ((1ULL << (6 * len)) - 1ULL)) << (6 * m);
     m += len;
-    {  // leaving edge: last inside vertex -> first outside vertex
-      const int vp = (int)((pr >> (4 * (len - 1))) & 15u), vq = (int)((pr >> (4 * len)) & 15u);
-      const double dp = sgn * (P.c[axis][vp] - bound), dq = sgn * (P.c[axis][vq] - bound);
-      if (dp > 0.0) {
-        const double tt = dp * __drcp_rn(dp - dq);
-        double x[3];
+    if (l_dp > 0.0) {  // leaving edge
+      const double tt = l_dp * __drcp_rn(l_dp - l_dq);
+      double x[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) x[k] = P.c[k][vp] + tt * (P.c[k][vq] - P.c[k][vp]);
-        x[axis] = bound;
+      for (int k = 0; k < 3; ++k) x[k] = lp[k] + tt * (lq[k] - lp[k]);
+      if (axis == 0) x[0] = bound; else if (axis == 1) x[1] = bound; else x[2] = bound;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) P.c[k][nv] = x[k];
-        np |= (unsigned long long)nv << (4 * m);
-        nc |= (unsigned long long)(outcode(x[0], x[1], x[2], H) | forced) << (6 * m);
-        ++m;
-        ++nv;
-      }
+      for (int k = 0; k < 3; ++k) P.c[k][nv] = x[k];
+      np |= (unsigned long long)nv << (4 * m);
+      nc |= (unsigned long long)(outcode(x[0], x[1], x[2], H) | forced) << (6 * m);
+      ++m;
+      ++nv;
     }
     poly = np;
     code = nc;
