@@ -122,7 +122,6 @@ int nm_create(nm_ctx **out, int device)
   }
   { const char *e = getenv("NMGPU_FORCE_QUADRATURE"); ctx->force_quadrature_kernel = e && e[0] == '1'; }
   { const char *e = getenv("NMGPU_FORCE_GENERAL_MERGE"); ctx->force_general_merge = e && e[0] == '1'; }
-  { const char *e = getenv("NMGPU_SPMV_VARIANT"); ctx->spmv_variant = e ? atoi(e) : 0; }
   { const char *e = getenv("NMGPU_COMPACT_ROWS"); ctx->compact_rows_env = e ? (e[0] == '1' ? 1 : 0) : -1; }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;

@@ -165,70 +165,6 @@ __device__ inline void clip_step(const Poly &in, Poly &out, double bound)
   out.n = m;
 }
 
-// Polygon for the throughput kernel: coordinate-major so that one routine serves all six planes
-// (a single copy of the code keeps the kernel inside the instruction cache).
-struct PolyC {
-  double c[3][NM_MAXV];
-  int n;
-};
-
-// Convex variant of the Sutherland-Hodgman step.  The inside vertices of a convex polygon form
-// one cyclic run, so the step is: classify all vertices (bit mask), compute the (at most two)
-// crossing points -- every lane does the same two reciprocals in lockstep instead of branching
-// per edge -- and copy the run.  Emits the same vertex set as clip_step, rotated.
-// Returns false (and leaves `out` untouched) when the plane does not cut: the caller keeps `in`.
-__device__ inline bool clip_convex(const PolyC &in, PolyC &out, int axis, bool upper, double bound)
-{
-  const int n = in.n;
-  const double sgn = upper ? -1.0 : 1.0;
-  unsigned inside = 0;
-#pragma unroll 1
-  for (int i = 0; i < n; ++i) inside |= (sgn * (in.c[axis][i] - bound) >= 0.0 ? 1u : 0u) << i;
-  const unsigned full = (1u << n) - 1u;
-  if (inside == 0u) { out.n = 0; return true; }
-  if (inside == full) return false;
-  int s = 0, len = n;
-  const bool cut = true;
-  int m = 0;
-  {
-    const unsigned prev = ((inside << 1) | (inside >> (n - 1))) & full;  // bit i: vertex i-1 inside
-    s = __ffs(inside & ~prev) - 1;                                         // run start
-    const unsigned rot = ((inside >> s) | (inside << (n - s))) & full;     // run as the low bits
-    len = __ffs(~rot) - 1;                                                 // run length (< n)
-    // entering edge  p = s-1 (outside) -> q = s (inside)
-    const int ip = s == 0 ? n - 1 : s - 1;
-    const double dp = sgn * (in.c[axis][ip] - bound), dq = sgn * (in.c[axis][s] - bound);
-    if (dq > 0.0) {
-      const double t = dp * __drcp_rn(dp - dq);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) out.c[k][0] = in.c[k][ip] + t * (in.c[k][s] - in.c[k][ip]);
-      out.c[axis][0] = bound;  // on the plane by construction: later inside-tests see it as inside
-      m = 1;
-    }
-  }
-  for (int k = 0; k < len; ++k) {
-    int i = s + k;
-    if (i >= n) i -= n;
-    out.c[0][m] = in.c[0][i]; out.c[1][m] = in.c[1][i]; out.c[2][m] = in.c[2][i];
-    ++m;
-  }
-  {
-    // leaving edge  p = e (inside) -> q = e+1 (outside)
-    int ie = s + len - 1; if (ie >= n) ie -= n;
-    const int iq = ie + 1 == n ? 0 : ie + 1;
-    const double dp = sgn * (in.c[axis][ie] - bound), dq = sgn * (in.c[axis][iq] - bound);
-    if (dp > 0.0 && m < NM_MAXV) {
-      const double t = dp * __drcp_rn(dp - dq);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) out.c[k][m] = in.c[k][ie] + t * (in.c[k][iq] - in.c[k][ie]);
-      out.c[axis][m] = bound;
-      ++m;
-    }
-  }
-  out.n = m;
-  (void)cut;
-  return true;
-}
 
 // Separating-axis test triangle vs box [0,H] (box normals, triangle normal, 9 edge cross
 // products).  Conservative on equality (touching = overlap); used only to keep triangles that

@@ -10,6 +10,7 @@
 #include "../../include/nmgpu.h"
 
 #define NM_SM_COUNT_B200 148
+#define NM_STATS_BLOCKS (8 * NM_SM_COUNT_B200)  // grid of the extent-statistics kernels: 8 blocks per SM
 
 // ---------------------------------------------------------------------------------------
 // device buffer that only grows; reused across calls so that a step does no cudaMalloc
@@ -52,6 +53,7 @@ struct nm_ctx {
   DevBuf c_master;  // u32
   DevBuf c_weight;  // f64
   bool bg_set = false, bg_dofs_set = false, index_valid = false;
+  bool bg_stats_ready = false;  // idx_tmp holds the extent statistics of the current boxes (taken by the lo/hi layout kernel)
 
   // ---- immersed ----
   int dim1 = 0;
@@ -83,7 +85,6 @@ struct nm_ctx {
   DevBuf counters;    // device counters (u64 x 8)
   bool candidates_only = false;  // candidate list computed without clipping (nm_flag_overlapped_background)
   bool intersect_valid = false;
-  int spmv_variant = 0;                  // NMGPU_SPMV_VARIANT: tuning knob for lanes/unroll (0 = default)
   bool force_general_merge = false;      // NMGPU_FORCE_GENERAL_MERGE=1: skip the single-pass merge (testing)
   bool force_quadrature_kernel = false;  // NMGPU_FORCE_QUADRATURE=1: per-point kernel even where moments apply
   bool local_from_user = false;  // cand_local was filled by nm_assemble_from_quadrature

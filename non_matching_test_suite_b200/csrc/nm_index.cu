@@ -18,6 +18,8 @@
 // reported from the cell whose index is the per-axis max of the two lower ends.
 #include <cub/cub.cuh>
 
+#include <thrust/iterator/transform_iterator.h>
+
 #include "nm_common.cuh"
 
 namespace {
@@ -85,24 +87,6 @@ __global__ void bg_boxes_from_verts(uint64_t n, const double *__restrict__ verts
   b[4] = hi[0]; b[5] = hi[1]; b[6] = hi[2]; b[7] = 0;
 }
 
-template <int D>
-__global__ void bg_boxes_from_lohi(uint64_t n, const double *__restrict__ lo, const double *__restrict__ hi,
-                                   double *__restrict__ box, int *bad)
-{
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double *b = box + i * 8;
-  bool ok = true;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    b[k] = k < D ? lo[i * D + k] : 0.0;
-    b[4 + k] = k < D ? hi[i * D + k] : 0.0;
-    ok &= b[k] <= b[4 + k];
-  }
-  b[3] = b[7] = 0;
-  if (!ok) atomicAdd(bad, 1);
-}
-
 __global__ void fill_line_of(uint64_t n_c, const uint32_t *__restrict__ c_dof, int32_t *__restrict__ line_of, uint64_t n_dofs, int *bad)
 {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -113,22 +97,25 @@ __global__ void fill_line_of(uint64_t n_c, const uint32_t *__restrict__ c_dof, i
 }
 
 // per-block partial min of lo, min positive extent, max hi  -> out[block][8]
-template <int D>
-__global__ void bg_stats(uint64_t n, const double *__restrict__ box, double *__restrict__ out)
-{
+struct BoxStats {
   double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY}, g = INFINITY, gm = 0;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    const double *b = box + i * 8;
+  template <int D> __device__ __forceinline__ void add(const double *lo, const double *hi)
+  {
     double e = 0;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-      mn[k] = fmin(mn[k], b[k]);
-      mx[k] = fmax(mx[k], b[4 + k]);
-      e = fmax(e, b[4 + k] - b[k]);
+      mn[k] = fmin(mn[k], lo[k]);
+      mx[k] = fmax(mx[k], hi[k]);
+      e = fmax(e, hi[k] - lo[k]);
     }
     if (e > 0) g = fmin(g, e);
     gm = fmax(gm, e);
   }
+  __device__ inline void reduce_to(double *__restrict__ out) const;
+};
+
+__device__ inline void BoxStats::reduce_to(double *__restrict__ out) const
+{
   typedef cub::BlockReduce<double, 256> BR;
   __shared__ typename BR::TempStorage tmp;
   double r[8];
@@ -138,6 +125,35 @@ __global__ void bg_stats(uint64_t n, const double *__restrict__ box, double *__r
   r[7] = BR(tmp).Reduce(gm, cub::Max());
   if (threadIdx.x == 0)
     for (int k = 0; k < 8; ++k) out[blockIdx.x * 8 + k] = r[k];
+}
+
+// lo/hi corners -> 64-byte boxes, with the extent statistics of the grid index taken in the same pass
+// (grid-stride, 256 threads per block, out[gridDim.x][8])
+template <int D>
+__global__ void __launch_bounds__(256) bg_boxes_from_lohi_stats(uint64_t n, const double *__restrict__ lo, const double *__restrict__ hi,
+                                                                double *__restrict__ box, int *bad, double *__restrict__ out)
+{
+  BoxStats S;
+  int n_bad = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    double l[3] = {0, 0, 0}, h[3] = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < D; ++k) { l[k] = lo[i * D + k]; h[k] = hi[i * D + k]; n_bad += !(l[k] <= h[k]); }
+    double4 *b = reinterpret_cast<double4 *>(box + i * 8);
+    b[0] = make_double4(l[0], l[1], l[2], 0.0);
+    b[1] = make_double4(h[0], h[1], h[2], 0.0);
+    S.add<D>(l, h);
+  }
+  if (n_bad) atomicAdd(bad, n_bad);
+  S.reduce_to(out);
+}
+
+template <int D>
+__global__ void bg_stats(uint64_t n, const double *__restrict__ box, double *__restrict__ out)
+{
+  BoxStats S;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) S.add<D>(box + i * 8, box + i * 8 + 4);
+  S.reduce_to(out);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -382,7 +398,7 @@ struct U32ToU64 {
 
 int nm_exclusive_scan_u32_to_u64(nm_ctx *ctx, const uint32_t *in, uint64_t *out, uint64_t n)
 {
-  cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t *> it(in, U32ToU64());
+  thrust::transform_iterator<U32ToU64, const uint32_t *, uint64_t> it(in, U32ToU64());
   size_t bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, out, n, ctx->stream);
   NM_TRY(nm_ensure(ctx, ctx->scan_tmp, bytes));
@@ -397,13 +413,16 @@ int nm_bg_layout(nm_ctx *ctx, int d, uint64_t n, const double *verts_dev, const 
   int *bad = ctx->counters.as<int>();
   NM_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
   const unsigned T = 256, B = nm_blocks(n, T);
+  ctx->bg_stats_ready = false;
   if (n) {
     if (verts_dev) {
       if (d == 2) bg_boxes_from_verts<2><<<B, T, 0, NM_LS(ctx)>>>(n, verts_dev, ctx->bg_box.as<double>(), bad);
       else bg_boxes_from_verts<3><<<B, T, 0, NM_LS(ctx)>>>(n, verts_dev, ctx->bg_box.as<double>(), bad);
     } else {
-      if (d == 2) bg_boxes_from_lohi<2><<<B, T, 0, NM_LS(ctx)>>>(n, lo_dev, hi_dev, ctx->bg_box.as<double>(), bad);
-      else bg_boxes_from_lohi<3><<<B, T, 0, NM_LS(ctx)>>>(n, lo_dev, hi_dev, ctx->bg_box.as<double>(), bad);
+      NM_TRY(nm_ensure(ctx, ctx->idx_tmp, NM_STATS_BLOCKS * 8 * sizeof(double)));
+      if (d == 2) bg_boxes_from_lohi_stats<2><<<NM_STATS_BLOCKS, 256, 0, NM_LS(ctx)>>>(n, lo_dev, hi_dev, ctx->bg_box.as<double>(), bad, ctx->idx_tmp.as<double>());
+      else bg_boxes_from_lohi_stats<3><<<NM_STATS_BLOCKS, 256, 0, NM_LS(ctx)>>>(n, lo_dev, hi_dev, ctx->bg_box.as<double>(), bad, ctx->idx_tmp.as<double>());
+      ctx->bg_stats_ready = true;
     }
     NM_CUDA(cudaGetLastError());
   }
@@ -466,11 +485,14 @@ int nm_index_build(nm_ctx *ctx)
     hash_clear<<<1, 32, 0, NM_LS(ctx)>>>(ctx->idx_hash.as<HashSlot>(), 1);
     return NM_OK; }
   // 1. origin and level-0 spacing
-  const unsigned SB = 1184;  // 8 blocks per SM
+  constexpr unsigned SB = NM_STATS_BLOCKS;
   NM_TRY(nm_ensure(ctx, ctx->idx_tmp, SB * 8 * sizeof(double)));
-  if (d == 2) bg_stats<2><<<SB, 256, 0, NM_LS(ctx)>>>(n, ctx->bg_box.as<double>(), ctx->idx_tmp.as<double>());
-  else bg_stats<3><<<SB, 256, 0, NM_LS(ctx)>>>(n, ctx->bg_box.as<double>(), ctx->idx_tmp.as<double>());
-  NM_CUDA(cudaGetLastError());
+  if (!ctx->bg_stats_ready) {   // the lo/hi layout kernel has already taken them
+    if (d == 2) bg_stats<2><<<SB, 256, 0, NM_LS(ctx)>>>(n, ctx->bg_box.as<double>(), ctx->idx_tmp.as<double>());
+    else bg_stats<3><<<SB, 256, 0, NM_LS(ctx)>>>(n, ctx->bg_box.as<double>(), ctx->idx_tmp.as<double>());
+    NM_CUDA(cudaGetLastError());
+  }
+  ctx->bg_stats_ready = false;  // idx_tmp is reused below
   static thread_local double h_stats[SB * 8];
   NM_CUDA(cudaMemcpyAsync(h_stats, ctx->idx_tmp.p, sizeof(h_stats), cudaMemcpyDeviceToHost, ctx->stream));
   NM_CUDA(cudaStreamSynchronize(ctx->stream));

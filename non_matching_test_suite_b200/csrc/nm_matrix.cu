@@ -710,19 +710,6 @@ __global__ void __launch_bounds__(256) spmv_crows(uint64_t n_im, const uint64_t 
   if (r < n_im && l == 0) y[im_dofs[r]] = s;
 }
 
-__global__ void __attribute__((unused)) rowlen_to_u64(uint64_t n, const uint32_t *__restrict__ len, uint64_t *__restrict__ out)
-{
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = len[i];
-  if (i == n) out[i] = 0;
-}
-
-__global__ void __attribute__((unused)) narrow_rowptr(uint64_t n, const uint64_t *__restrict__ in, uint32_t *__restrict__ out)
-{
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (uint32_t)in[i];
-}
-
 // compact copy of C's rows (for nm_get_csr(transpose = 1)): row index = immersed dof
 template <int LANES>
 __global__ void c_compact(uint64_t n_im, const uint64_t *__restrict__ rowstart, const uint32_t *__restrict__ rowlen,
@@ -985,17 +972,10 @@ int nm_spmv_run(nm_ctx *ctx, int transpose, const double *x, double *y)
     const uint32_t *cl = ctx->a_col.as<uint32_t>();
     const double *vl = ctx->a_val.as<double>();
     if (n_rows) {
+      // rows of the coupling matrix are short (a space dof meets 3-8 immersed cells): one thread per row with eight
+      // independent load chains is the fastest shape measured; longer rows get 4 or 8 lanes
       if (avg > 24) spmv_csr<8, 4, uint64_t><<<nm_blocks(n_rows * 8, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y, ids);
       else if (avg > 8) spmv_csr<4, 4, uint64_t><<<nm_blocks(n_rows * 4, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y, ids);
-      else if (ctx->spmv_variant / 10 == 1) spmv_csr<1, 4, uint64_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y, ids);
-      else if (ctx->spmv_variant / 10 == 2) spmv_csr<2, 2, uint64_t><<<nm_blocks(n_rows * 2, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y, ids);
-      else if (ctx->spmv_variant / 10 == 3) spmv_csr<1, 8, uint64_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y, ids);
-      else if (ctx->spmv_variant / 10 == 4) spmv_csr<1, 3, uint64_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y, ids);
-      else if (ctx->spmv_variant / 10 == 5) spmv_csr<1, 2, uint64_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y, ids);
-      else if (ctx->a_rowptr32_valid && ctx->spmv_variant / 10 == 6) spmv_csr<1, 8, uint32_t><<<nm_blocks(n_rows, 128), 128, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr32.as<uint32_t>(), cl, vl, x, y, ids);
-      else if (ctx->a_rowptr32_valid && ctx->spmv_variant / 10 == 7) spmv_csr<1, 6, uint32_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr32.as<uint32_t>(), cl, vl, x, y, ids);
-      else if (ctx->a_rowptr32_valid && ctx->spmv_variant / 10 == 8) spmv_csr<1, 12, uint32_t><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr32.as<uint32_t>(), cl, vl, x, y, ids);
-      else if (ctx->a_rowptr32_valid && ctx->spmv_variant / 10 == 9) spmv_csr<1, 8, uint32_t><<<nm_blocks(n_rows, 64), 64, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr32.as<uint32_t>(), cl, vl, x, y, ids);
       else if (ctx->a_rowptr32_valid) spmv_csr<1, 8, uint32_t><<<nm_blocks(n_rows, 128), 128, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr32.as<uint32_t>(), cl, vl, x, y, ids);
       else spmv_csr<1, 8, uint64_t><<<nm_blocks(n_rows, 128), 128, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y, ids);
     }
@@ -1006,14 +986,7 @@ int nm_spmv_run(nm_ctx *ctx, int transpose, const double *x, double *y)
     const uint32_t *rl = ctx->c_rowlen.as<uint32_t>(), *cl = ctx->c_col.as<uint32_t>(), *idf = ctx->im_dofs.as<uint32_t>();
     const double *vl = ctx->c_val.as<double>();
     if (n_im) {
-      const int cv = ctx->spmv_variant % 10;
-      if (avg > 20 && cv == 1) spmv_crows<8, 4><<<nm_blocks(n_im * 8, 256), 256, 0, NM_LS(ctx)>>>(n_im, rs, rl, cl, vl, idf, x, y);
-      else if (avg > 20 && cv == 2) spmv_crows<2, 8><<<nm_blocks(n_im * 2, 256), 256, 0, NM_LS(ctx)>>>(n_im, rs, rl, cl, vl, idf, x, y);
-      else if (avg > 20 && cv == 3) spmv_crows<4, 8><<<nm_blocks(n_im * 4, 256), 256, 0, NM_LS(ctx)>>>(n_im, rs, rl, cl, vl, idf, x, y);
-      else if (avg > 20 && cv == 4) spmv_crows<2, 4><<<nm_blocks(n_im * 2, 256), 256, 0, NM_LS(ctx)>>>(n_im, rs, rl, cl, vl, idf, x, y);
-      else if (avg > 20 && cv == 5) spmv_crows<1, 8><<<nm_blocks(n_im, 256), 256, 0, NM_LS(ctx)>>>(n_im, rs, rl, cl, vl, idf, x, y);
-      else if (avg > 20 && cv == 6) spmv_crows<4, 4><<<nm_blocks(n_im * 4, 256), 256, 0, NM_LS(ctx)>>>(n_im, rs, rl, cl, vl, idf, x, y);
-      else if (avg > 20) spmv_crows<4, 8><<<nm_blocks(n_im * 4, 256), 256, 0, NM_LS(ctx)>>>(n_im, rs, rl, cl, vl, idf, x, y);
+      if (avg > 20) spmv_crows<4, 8><<<nm_blocks(n_im * 4, 256), 256, 0, NM_LS(ctx)>>>(n_im, rs, rl, cl, vl, idf, x, y);
       else if (avg > 6) spmv_crows<4, 2><<<nm_blocks(n_im * 4, 256), 256, 0, NM_LS(ctx)>>>(n_im, rs, rl, cl, vl, idf, x, y);
       else spmv_crows<2, 2><<<nm_blocks(n_im * 2, 256), 256, 0, NM_LS(ctx)>>>(n_im, rs, rl, cl, vl, idf, x, y);
     }
