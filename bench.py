@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--ref-cycle", type=int, default=None, help="refinement cycle of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-separate-calls", action="store_true",
+                    help="end-to-end leg through nm_set_background_boxes + nm_set_immersed + nm_intersect + ... instead of nm_assemble_host")
     ap.add_argument("--nccl-allreduce", action="store_true", help="reduce Ct.vmult with NCCL all_reduce instead of the fused NVLink push")
     ap.add_argument("--verts", action="store_true", help="send all 2^d vertices of every background cell instead of lo/hi boxes")
     return ap.parse_args()
@@ -219,6 +221,11 @@ def run_native(args):
     fused = {"op": None, "tried": False, "why": ""}
 
     def step(inp, x, u, y, z, host):
+        if host and "lo" in inp and not args.e2e_separate_calls:
+            # one call from host arrays: uploads queued up front, each phase waits only for what it reads
+            counts = ctx.assemble_host(d, inp["lo"], inp["hi"], inp["dofs"], bg.n_dofs, inp["c_dof"], inp["c_ptr"], inp["c_master"],
+                                       inp["c_weight"], im.dim, inp["im_verts"], inp["im_dofs"], im.n_dofs, 3, 1e-15)
+            return finish_step(counts, x, u, y, z, host)
         if "verts" in inp:   # all 2^d vertices of every background cell, as mapping.get_vertices() returns them
             ctx.set_background(d, verts=inp["verts"], dofs=inp["dofs"], n_dofs=bg.n_dofs, c_dof=inp["c_dof"], c_ptr=inp["c_ptr"],
                                c_master=inp["c_master"], c_weight=inp["c_weight"])
@@ -229,6 +236,9 @@ def run_native(args):
         counts = ctx.intersect(3, 1e-15)
         ctx.build_sparsity()
         ctx.assemble()
+        return finish_step(counts, x, u, y, z, host)
+
+    def finish_step(counts, x, u, y, z, host):
         if world > 1 and fused["op"] is None and not args.nccl_allreduce and fused["tried"] is False:
             from non_matching_test_suite_b200.distributed import FusedCtVmult
             fused["tried"] = True
@@ -349,7 +359,11 @@ def run_native(args):
         d2h = sum(t.numel() * t.element_size() for t in out) + yh.numel() * 8 + zh.numel() * 8
         e2e = {"value": tot_acc / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": ms_e, "steps": e_steps,
-               "api": "_lib.Context (C ABI): nm_set_background_boxes(host lo/hi + dofs + constraint lines) + nm_set_immersed + nm_intersect + nm_build_sparsity + nm_assemble + nm_spmv x2 (host vectors) + nm_get_csr read-back into pinned host memory; the same calls include/coupling_utilities.h makes"}
+               "api": ("_lib.Context (C ABI): nm_set_background_boxes(host lo/hi + dofs + constraint lines) + nm_set_immersed + nm_intersect + "
+                       "nm_build_sparsity + nm_assemble" if (args.e2e_separate_calls or args.verts) else
+                       "_lib.Context (C ABI): nm_assemble_host (host lo/hi + dofs + constraint lines + immersed grid in one call, uploads "
+                       "overlapped with the phases that do not need them yet)") +
+                      " + nm_spmv x2 (host vectors) + nm_get_csr read-back into pinned host memory"}
         del host_in
 
     cpu_base = None

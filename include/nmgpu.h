@@ -180,6 +180,36 @@ int nm_spmv(nm_ctx *ctx, int transpose, const double *x, double *y, int where);
  * all-reduce: only the rows a rank owns cross the links. */
 int nm_spmv_push(nm_ctx *ctx, const double *x, int n_targets, double *const *y_targets, int multicast);
 
+/* ---- the whole assembly from HOST arrays in one call, uploads overlapped with the computation ----
+ * Same result as nm_set_background_boxes + nm_set_immersed + nm_intersect + nm_build_sparsity + nm_assemble with
+ * NM_HOST pointers, i.e. what collect_quadratures_on_overlapped_grids (code/src/coupling_utilities.cc:22-69) followed by
+ * create_coupling_sparsity_pattern / create_coupling_mass_matrix_with_exact_intersections
+ * (code/include/coupling_utilities.h:28-152, :154-304) compute, but all host->device copies are queued up front on a
+ * copy stream and each phase waits only for the arrays it reads: the grid index is built while the immersed grid is
+ * still in flight, candidates / clipping run while the DoF tables and constraint lines arrive.  With pinned host memory
+ * the copies are asynchronous; with pageable memory the call is still correct, only not overlapped.
+ * All pointers are host pointers and are not used after the call returns.  Read the matrix with nm_get_csr. */
+typedef struct {
+  int spacedim;                 /* 2 or 3 */
+  uint64_t n_bg;                /* background cells (axis-aligned boxes) */
+  const double *lo, *hi;        /* [n_bg][spacedim] */
+  const uint32_t *bg_dofs;      /* [n_bg][2^spacedim] */
+  uint64_t n_space_dofs;
+  uint64_t n_constrained;       /* constraint lines as in nm_set_background */
+  const uint32_t *c_dof;
+  const uint64_t *c_ptr;
+  const uint32_t *c_master;
+  const double *c_weight;
+  int dim;                      /* spacedim - 1 */
+  uint64_t n_im;
+  const double *im_verts;       /* [n_im][2^dim][spacedim] */
+  const uint32_t *im_dofs;      /* [n_im] */
+  uint64_t n_im_dofs;
+  unsigned degree;              /* quadrature degree, > 0 */
+  double tol;
+} nm_host_problem;
+int nm_assemble_host(nm_ctx *ctx, const nm_host_problem *problem, nm_counts *counts, uint64_t *nnz);
+
 /* ---- interface-penalisation (Nitsche) terms on a caller-supplied quadrature ----
  * Replaces the arithmetic of assemble_nitsche_with_exact_intersections (code/include/coupling_utilities.h:306-398) and
  * create_nitsche_rhs_with_exact_intersections (:400-481): for tuple p with background cell background[p] and points

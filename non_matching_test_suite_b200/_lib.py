@@ -24,7 +24,7 @@ PHASES = ["upload", "index", "candidates", "split", "clip", "merge", "transpose"
 # every symbol include/nmgpu.h declares
 SYMBOLS = ["nm_version", "nm_create", "nm_destroy", "nm_last_error", "nm_set_background", "nm_set_background_boxes",
            "nm_set_background_dofs", "nm_set_immersed_dofs", "nm_set_immersed", "nm_flag_overlapped_background", "nm_intersect", "nm_get_candidates", "nm_get_pairs", "nm_get_quadrature",
-           "nm_get_split_codes", "nm_build_sparsity", "nm_assemble", "nm_assemble_from_quadrature", "nm_assemble_nitsche", "nm_get_nitsche", "nm_get_csr",
+           "nm_get_split_codes", "nm_build_sparsity", "nm_assemble", "nm_assemble_from_quadrature", "nm_assemble_host", "nm_assemble_nitsche", "nm_get_nitsche", "nm_get_csr",
            "nm_spmv", "nm_spmv_push", "nm_get_timings", "nm_get_launch_count", "nm_device_bytes", "nm_get_stream"]
 
 
@@ -32,6 +32,14 @@ class NmError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__("%s: %s" % (STATUS.get(code, str(code)), msg))
         self.code = code
+
+
+class HostProblem(C.Structure):
+    """nm_host_problem of include/nmgpu.h."""
+    _fields_ = [("spacedim", C.c_int), ("n_bg", C.c_uint64), ("lo", C.c_void_p), ("hi", C.c_void_p), ("bg_dofs", C.c_void_p),
+                ("n_space_dofs", C.c_uint64), ("n_constrained", C.c_uint64), ("c_dof", C.c_void_p), ("c_ptr", C.c_void_p),
+                ("c_master", C.c_void_p), ("c_weight", C.c_void_p), ("dim", C.c_int), ("n_im", C.c_uint64), ("im_verts", C.c_void_p),
+                ("im_dofs", C.c_void_p), ("n_im_dofs", C.c_uint64), ("degree", C.c_uint), ("tol", C.c_double)]
 
 
 class Counts(C.Structure):
@@ -72,6 +80,7 @@ def load():
     L.nm_build_sparsity.argtypes = [P, C.POINTER(U64)]
     L.nm_assemble.argtypes = [P]
     L.nm_assemble_from_quadrature.argtypes = [P, U64, P, P, P, P, P, I]
+    L.nm_assemble_host.argtypes = [P, C.POINTER(HostProblem), C.POINTER(Counts), C.POINTER(U64)]
     L.nm_assemble_nitsche.argtypes = [P, U64, P, P, P, P, P, P, C.c_double, I, I, C.POINTER(U64)]
     L.nm_get_nitsche.argtypes = [P, P, P, P, P, I]
     L.nm_get_csr.argtypes = [P, I, P, P, P, I]
@@ -229,6 +238,25 @@ class Context:
         w = _where(im, bg, q_offset, points, weights)
         self._chk(self.L.nm_assemble_from_quadrature(self.h, int(im.shape[0]), _ptr(im)[0], _ptr(bg)[0], _ptr(q_offset)[0],
                                                      _ptr(points)[0], _ptr(weights)[0], w))
+
+    def assemble_host(self, spacedim, lo, hi, dofs, n_dofs, c_dof, c_ptr, c_master, c_weight, im_dim, im_verts, im_dofs, n_im_dofs,
+                      degree, tol):
+        """Whole assembly from HOST arrays (torch CPU tensors, ideally pinned) in one call with the uploads overlapped
+        with the computation (nm_assemble_host); afterwards the context is in the same state as after
+        set_background(lo, hi, ...) + set_immersed + intersect + build_sparsity + assemble."""
+        arrs = (lo, hi, dofs, c_dof, c_ptr, c_master, c_weight, im_verts, im_dofs)
+        if _where(*arrs) != NM_HOST:
+            raise ValueError("assemble_host takes host arrays")
+        hp = HostProblem(spacedim, int(lo.shape[0]), _ptr(lo)[0], _ptr(hi)[0], _ptr(dofs)[0], int(n_dofs), int(c_dof.shape[0]),
+                         _ptr(c_dof)[0], _ptr(c_ptr)[0], _ptr(c_master)[0], _ptr(c_weight)[0], im_dim, int(im_verts.shape[0]),
+                         _ptr(im_verts)[0], _ptr(im_dofs)[0], int(n_im_dofs), int(degree), float(tol))
+        cnt, nnz = Counts(), C.c_uint64(0)
+        self._chk(self.L.nm_assemble_host(self.h, C.byref(hp), C.byref(cnt), C.byref(nnz)))
+        self.spacedim, self.n_bg, self.n_space_dofs = spacedim, int(lo.shape[0]), int(n_dofs)
+        self.n_im, self.n_im_dofs = int(im_verts.shape[0]), int(n_im_dofs)
+        self.counts = cnt.as_dict()
+        self.nnz = int(nnz.value)
+        return self.counts
 
     def assemble_nitsche(self, bg, q_offset, points, weights, coefficient=None, rhs_values=None, penalty=1.0, matrix=True):
         """Nitsche terms on the given quadrature (reference coupling_utilities.h:306-481): returns

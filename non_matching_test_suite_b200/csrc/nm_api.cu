@@ -9,7 +9,7 @@
 #include "nm_common.cuh"
 
 int nm_bg_layout(nm_ctx *ctx, int d, uint64_t n, const double *verts_dev, const double *lo_dev, const double *hi_dev);
-int nm_constraints_layout(nm_ctx *ctx);
+int nm_constraints_layout(nm_ctx *ctx, const uint32_t *c_dof_dev);  // c_dof_dev: [n_constrained] constrained dof ids on the device
 int nm_accepted_index(nm_ctx *ctx, uint64_t **idx_dev);
 int nm_c_rows_compact(nm_ctx *ctx, uint64_t *rowptr_dev, uint32_t *col_dev, double *val_dev);
 int nm_spmv_push_run(nm_ctx *ctx, const double *x, int n_targets, double *const *targets, int multicast);
@@ -141,6 +141,9 @@ int nm_destroy(nm_ctx *ctx)
   if (ctx->ev2) cudaEventDestroy(ctx->ev2);
   if (ctx->ev3) cudaEventDestroy(ctx->ev3);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (cudaEvent_t e : ctx->ev_copy)
+    if (e) cudaEventDestroy(e);
   delete ctx;
   return NM_OK;
 }
@@ -198,7 +201,7 @@ static int set_background_common(nm_ctx *ctx, int spacedim, uint64_t n_cells, bo
   else { NM_TRY(nm_ensure(ctx, ctx->c_ptr, 16)); NM_CUDA(cudaMemsetAsync(ctx->c_ptr.p, 0, 16, ctx->stream)); }
   NM_TRY(nm_upload(ctx, ctx->c_master, c_master, n_masters * sizeof(uint32_t), where));
   NM_TRY(nm_upload(ctx, ctx->c_weight, c_weight, n_masters * sizeof(double), where));
-  NM_TRY(nm_constraints_layout(ctx));
+  NM_TRY(nm_constraints_layout(ctx, ctx->scratch_a.as<uint32_t>()));
   tm.stop();
   ctx->bg_set = true;
   return NM_OK;
@@ -222,7 +225,7 @@ static int set_constraints(nm_ctx *ctx, uint64_t n_dofs, uint64_t n_constrained,
   else { NM_TRY(nm_ensure(ctx, ctx->c_ptr, 16)); NM_CUDA(cudaMemsetAsync(ctx->c_ptr.p, 0, 16, ctx->stream)); }
   NM_TRY(nm_upload(ctx, ctx->c_master, c_master, n_masters * sizeof(uint32_t), where));
   NM_TRY(nm_upload(ctx, ctx->c_weight, c_weight, n_masters * sizeof(double), where));
-  return nm_constraints_layout(ctx);
+  return nm_constraints_layout(ctx, ctx->scratch_a.as<uint32_t>());
 }
 
 int nm_set_background_dofs(nm_ctx *ctx, const uint32_t *dofs, uint64_t n_dofs, uint64_t n_constrained, const uint32_t *c_dof,
@@ -303,6 +306,8 @@ int nm_set_immersed(nm_ctx *ctx, int dim, int spacedim, uint64_t n_cells, const 
   return NM_OK;
 }
 
+static int intersect_after_index(nm_ctx *ctx);
+
 int nm_intersect(nm_ctx *ctx, unsigned degree, double tol, nm_counts *counts)
 {
   if (!ctx) return NM_ERR_INVALID;
@@ -319,6 +324,14 @@ int nm_intersect(nm_ctx *ctx, unsigned degree, double tol, nm_counts *counts)
     NM_TRY(nm_index_build(ctx));
     t.stop();
   }
+  NM_TRY(intersect_after_index(ctx));
+  if (counts) *counts = ctx->counts;
+  return NM_OK;
+}
+
+// candidates -> quad split -> clip + integrate (the grid index is valid)
+static int intersect_after_index(nm_ctx *ctx)
+{
   {
     PhaseTimer t(ctx, NM_T_CANDIDATES);
     NM_TRY(nm_candidates_run(ctx));
@@ -335,7 +348,6 @@ int nm_intersect(nm_ctx *ctx, unsigned degree, double tol, nm_counts *counts)
     t.stop();
   }
   ctx->intersect_valid = true;
-  if (counts) *counts = ctx->counts;
   return NM_OK;
 }
 
@@ -532,6 +544,95 @@ int nm_get_nitsche(nm_ctx *ctx, uint64_t *rowptr, uint32_t *col, double *val, do
   NM_TRY(nm_download(ctx, val, ctx->nit_val.p, ctx->nit_nnz * 8, where));
   NM_TRY(nm_download(ctx, rhs, ctx->nit_rhs.p, ctx->n_space_dofs * 8, where));
   NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return NM_OK;
+}
+
+int nm_assemble_host(nm_ctx *ctx, const nm_host_problem *P, nm_counts *counts, uint64_t *nnz)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  if (!P) return nm_fail(ctx, NM_ERR_INVALID, "null problem");
+  const int d = P->spacedim;
+  if (d != 2 && d != 3) return nm_fail(ctx, NM_ERR_INVALID, "spacedim must be 2 or 3 (got %d)", d);
+  if (P->dim != d - 1)
+    return nm_fail(ctx, NM_ERR_UNSUPPORTED, "only codimension-1 immersed grids are implemented (<2,1,2> and <3,2,3>); got dim=%d spacedim=%d", P->dim, d);
+  if (P->degree == 0) return nm_fail(ctx, NM_ERR_INVALID, "Invalid quadrature degree.");  // coupling_utilities.cc:32
+  if (P->n_bg >= 0xffffffffULL || P->n_space_dofs >= 0xffffffffULL || P->n_im >= 0xffffffffULL || P->n_im_dofs >= 0xffffffffULL)
+    return nm_fail(ctx, NM_ERR_UNSUPPORTED, "cell / DoF counts must fit 32 bits");
+  if ((P->n_bg && (!P->lo || !P->hi || !P->bg_dofs)) || (P->n_im && (!P->im_verts || !P->im_dofs)))
+    return nm_fail(ctx, NM_ERR_INVALID, "null grid arrays");
+  if (P->n_constrained && (!P->c_dof || !P->c_ptr)) return nm_fail(ctx, NM_ERR_INVALID, "null constraint arrays");
+  const uint64_t n_masters = P->n_constrained ? P->c_ptr[P->n_constrained] : 0;
+  if (n_masters && (!P->c_master || !P->c_weight)) return nm_fail(ctx, NM_ERR_INVALID, "null constraint master arrays");
+  if (!ctx->copy_stream) {
+    NM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t &e : ctx->ev_copy) NM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  ctx->bg_set = ctx->bg_dofs_set = ctx->im_set = ctx->im_dofs_set = false;
+  ctx->index_valid = ctx->intersect_valid = ctx->matrix_valid = false;
+  ctx->local_from_user = false;
+  ctx->spacedim = d; ctx->n_bg = P->n_bg; ctx->n_space_dofs = P->n_space_dofs;
+  ctx->n_constrained = P->n_constrained; ctx->n_cmasters = n_masters;
+  ctx->dim1 = P->dim; ctx->n_im = P->n_im; ctx->n_im_dofs = P->n_im_dofs;
+  ctx->degree = P->degree; ctx->tol = P->tol;
+  const int NV = 1 << d, NVI = 1 << P->dim;
+
+  // ---- 0. every host->device copy, queued on the copy stream in the order the phases need them ----
+  const size_t b_box = P->n_bg * d * sizeof(double), b_box_al = (b_box + 255) & ~size_t(255);
+  const size_t b_cdof = P->n_constrained * sizeof(uint32_t);   // constrained dof ids travel behind the boxes in the staging buffer
+  NM_TRY(nm_ensure(ctx, ctx->h2d_stage, 2 * b_box_al + b_cdof + 512));
+  NM_TRY(nm_ensure(ctx, ctx->im_verts, P->n_im * NVI * d * sizeof(double)));
+  NM_TRY(nm_ensure(ctx, ctx->im_dofs, P->n_im * sizeof(uint32_t)));
+  NM_TRY(nm_ensure(ctx, ctx->bg_dofs, P->n_bg * NV * sizeof(uint32_t)));
+  NM_TRY(nm_ensure(ctx, ctx->c_ptr, (P->n_constrained + 2) * sizeof(uint64_t)));
+  NM_TRY(nm_ensure(ctx, ctx->c_master, n_masters * sizeof(uint32_t)));
+  NM_TRY(nm_ensure(ctx, ctx->c_weight, n_masters * sizeof(double)));
+  NM_CUDA(cudaStreamSynchronize(ctx->stream));   // earlier work of this context may still read those buffers
+  cudaStream_t cs = ctx->copy_stream;
+  auto h2d = [&](void *dst, const void *src, size_t bytes) -> cudaError_t {
+    return bytes ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, cs) : cudaSuccess;
+  };
+  double *lo_dev = ctx->h2d_stage.as<double>(), *hi_dev = reinterpret_cast<double *>(ctx->h2d_stage.as<char>() + b_box_al);
+  NM_CUDA(h2d(lo_dev, P->lo, b_box));
+  NM_CUDA(h2d(hi_dev, P->hi, b_box));
+  NM_CUDA(cudaEventRecord(ctx->ev_copy[0], cs));
+  NM_CUDA(h2d(ctx->im_verts.p, P->im_verts, P->n_im * NVI * d * sizeof(double)));
+  NM_CUDA(h2d(ctx->im_dofs.p, P->im_dofs, P->n_im * sizeof(uint32_t)));
+  NM_CUDA(cudaEventRecord(ctx->ev_copy[1], cs));
+  NM_CUDA(h2d(ctx->bg_dofs.p, P->bg_dofs, P->n_bg * NV * sizeof(uint32_t)));
+  uint32_t *c_dof_dev = reinterpret_cast<uint32_t *>(ctx->h2d_stage.as<char>() + 2 * b_box_al);
+  NM_CUDA(h2d(c_dof_dev, P->c_dof, b_cdof));
+  if (P->n_constrained) NM_CUDA(h2d(ctx->c_ptr.p, P->c_ptr, (P->n_constrained + 1) * sizeof(uint64_t)));
+  else NM_CUDA(cudaMemsetAsync(ctx->c_ptr.p, 0, 16, cs));
+  NM_CUDA(h2d(ctx->c_master.p, P->c_master, n_masters * sizeof(uint32_t)));
+  NM_CUDA(h2d(ctx->c_weight.p, P->c_weight, n_masters * sizeof(double)));
+  NM_CUDA(cudaEventRecord(ctx->ev_copy[2], cs));
+
+  // ---- 1. boxes -> layout + grid index (the immersed grid is still in flight) ----
+  NM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[0], 0));
+  {
+    PhaseTimer t(ctx, NM_T_UPLOAD);
+    NM_TRY(nm_bg_layout(ctx, d, P->n_bg, nullptr, lo_dev, hi_dev));
+    t.stop();
+  }
+  ctx->bg_set = true;
+  {
+    PhaseTimer t(ctx, NM_T_INDEX);
+    NM_TRY(nm_index_build(ctx));
+    t.stop();
+  }
+  // ---- 2. immersed grid -> candidates, split, clip (the DoF tables are still in flight) ----
+  NM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[1], 0));
+  ctx->im_set = ctx->im_dofs_set = true;
+  NM_TRY(intersect_after_index(ctx));
+  // ---- 3. DoF tables + constraint lines -> merge, transpose ----
+  NM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[2], 0));
+  NM_TRY(nm_constraints_layout(ctx, c_dof_dev));
+  ctx->bg_dofs_set = true;
+  NM_TRY(nm_matrix_build(ctx));
+  NM_CUDA(cudaStreamSynchronize(cs));
+  if (counts) *counts = ctx->counts;
+  if (nnz) *nnz = ctx->nnz;
   return NM_OK;
 }
 

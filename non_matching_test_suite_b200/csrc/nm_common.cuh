@@ -40,6 +40,8 @@ struct GridIndex {
 struct nm_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;           // host->device copies of nm_assemble_host
+  cudaEvent_t ev_copy[3] = {nullptr, nullptr, nullptr};
   std::string err;
   int sm_count = NM_SM_COUNT_B200;
 

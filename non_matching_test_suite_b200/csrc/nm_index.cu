@@ -436,7 +436,7 @@ int nm_bg_layout(nm_ctx *ctx, int d, uint64_t n, const double *verts_dev, const 
   return NM_OK;
 }
 
-int nm_constraints_layout(nm_ctx *ctx)
+int nm_constraints_layout(nm_ctx *ctx, const uint32_t *c_dof_dev)
 {
   NM_TRY(nm_ensure(ctx, ctx->line_of, (ctx->n_space_dofs + 1) * sizeof(int32_t)));
   NM_CUDA(cudaMemsetAsync(ctx->line_of.p, 0xff, ctx->n_space_dofs * sizeof(int32_t), ctx->stream));
@@ -444,7 +444,7 @@ int nm_constraints_layout(nm_ctx *ctx)
     int *bad = ctx->counters.as<int>();
     NM_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
     fill_line_of<<<nm_blocks(ctx->n_constrained, 256), 256, 0, NM_LS(ctx)>>>(
-        ctx->n_constrained, ctx->scratch_a.as<uint32_t>(), ctx->line_of.as<int32_t>(), ctx->n_space_dofs, bad);
+        ctx->n_constrained, c_dof_dev, ctx->line_of.as<int32_t>(), ctx->n_space_dofs, bad);
     NM_CUDA(cudaGetLastError());
     int h_bad = 0;
     NM_CUDA(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

@@ -404,3 +404,34 @@ def test_compact_row_mode_is_the_same_matrix(monkeypatch, name, cycle, general_m
         ctx.close()
     for a, b in zip(out["0"], out["1"]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("name,cycle", [("disk", 2), ("sphere", 1)])
+@pytest.mark.parametrize("pinned", [False, True])
+def test_assemble_host_equals_separate_calls(name, cycle, pinned):
+    """nm_assemble_host (uploads overlapped with the phases) leaves the context in the same state as the separate
+    calls: same counts, same CSR bitwise, same products; the context can be reused for another problem."""
+    from non_matching_test_suite_b200 import _lib
+    bg, im = make_config(name, cycle, band_only=False)
+    ref = coupling.make_context(bg, im, boxes=True)
+    c_ref = ref.intersect(3, 1e-15)
+    rp, col, val = ref.csr(transpose=False)
+    pin = (lambda t: t.contiguous().pin_memory()) if pinned else (lambda t: t.contiguous())
+    i32 = lambda t: t.to(torch.int32)
+    args = (bg.spacedim, pin(bg.lo), pin(bg.hi), pin(i32(bg.dofs)), bg.n_dofs, pin(i32(bg.c_dof)), pin(bg.c_ptr.to(torch.int64)),
+            pin(i32(bg.c_master)), pin(bg.c_weight), im.dim, pin(im.verts), pin(i32(im.dofs)), im.n_dofs)
+    ctx = _lib.Context(0)
+    for _ in range(2):          # second round: buffers are reused while nothing of the first is in flight
+        c = ctx.assemble_host(*args, 3, 1e-15)
+        assert c == c_ref
+        rp2, col2, val2 = ctx.csr(transpose=False)
+        assert torch.equal(rp2, rp) and torch.equal(col2, col) and torch.equal(val2, val)
+    x = torch.rand(im.n_dofs, dtype=torch.float64, generator=torch.Generator().manual_seed(2))
+    assert torch.equal(ctx.spmv(x), ref.spmv(x))
+    # pairs / quadrature are available as after nm_intersect
+    a, b = ctx.pairs(), ref.pairs()
+    assert all(torch.equal(p, q) for p, q in zip(a, b))
+    with pytest.raises(_lib.NmError) as e:
+        ctx.assemble_host(*args, 0, 1e-15)
+    assert e.value.code == 1 and "Invalid quadrature degree" in str(e.value)
+    ctx.close(); ref.close()
