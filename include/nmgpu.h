@@ -70,10 +70,10 @@ enum {
   NM_T_SPMV_T = 8,     /* last nm_spmv, transposed                                         */
   NM_T_DOWNLOAD = 9,   /* device->host copies of the last nm_get_*                         */
   /* single kernels, events directly around the launch */
-  NM_T_K_CLIP = 10,        /* clip_local_kernel                                            */
-  NM_T_K_CAND_COUNT = 11,  /* cand_count                                                   */
-  NM_T_K_CAND_FILL = 12,   /* cand_fill                                                    */
-  NM_T_K_MERGE = 13,       /* merge_rows_warp                                              */
+  NM_T_K_CLIP = 10,        /* clip_moments3_kernel (3D) / clip_local_kernel (2D)           */
+  NM_T_K_CAND_COUNT = 11,  /* cand_probe                                                   */
+  NM_T_K_CAND_FILL = 12,   /* cand_place                                                   */
+  NM_T_K_MERGE = 13,       /* merge_rows_fast (general path: merge_rows_hash)              */
   NM_T_COUNT = 16
 };
 
