@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-separate-calls", action="store_true",
                     help="end-to-end leg through nm_set_background_boxes + nm_set_immersed + nm_intersect + ... instead of nm_assemble_host")
+    ap.add_argument("--ct-vmult", choices=["replicated", "owned"], default="replicated",
+                    help="result of Ct.vmult on N > 1 GPUs: replicated on every rank (all-reduce semantics, the default) or "
+                         "distributed by contiguous background-dof ranges like the reference's Trilinos vector (reduce-scatter semantics)")
     ap.add_argument("--nccl-allreduce", action="store_true", help="reduce Ct.vmult with NCCL all_reduce instead of the fused NVLink push")
     ap.add_argument("--verts", action="store_true", help="send all 2^d vertices of every background cell instead of lo/hi boxes")
     return ap.parse_args()
@@ -216,6 +219,8 @@ def run_native(args):
 
     ctx = _lib.Context(local)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+    from non_matching_test_suite_b200.distributed import from_context, owned_dof_range
+    sharded_op = from_context(ctx)
 
     csr_out = {}
     fused = {"op": None, "tried": False, "why": ""}
@@ -247,7 +252,20 @@ def run_native(args):
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             fused["op"] = op if int(ok.item()) == 1 else None
             fused["why"] = "" if op.available else op.reason
-        if world > 1 and fused["op"] is not None:
+        if world > 1 and fused["op"] is not None and args.ct_vmult == "owned":
+            # reduce-scatter semantics: every row result crosses NVLink once, to the rank that owns the dof
+            xx = x if not host else x_dev.copy_(x, non_blocking=True)
+            yy = fused["op"].vmult_owned(xx)
+            if host:
+                lo_o, hi_o = owned_dof_range(bg.n_dofs, rank, world)
+                y[lo_o:hi_o].copy_(yy)
+        elif world > 1 and args.ct_vmult == "owned":
+            xx = x if not host else x_dev.copy_(x, non_blocking=True)
+            yy = sharded_op.vmult_owned(xx)      # SpMV + NCCL reduce_scatter
+            if host:
+                lo_o, hi_o = owned_dof_range(bg.n_dofs, rank, world)
+                y[lo_o:hi_o].copy_(yy)
+        elif world > 1 and fused["op"] is not None:
             # Ct.vmult fused with its reduction: one kernel adds this rank's rows into every rank's result over NVLink
             xx = x if not host else x_dev.copy_(x, non_blocking=True)
             yy = fused["op"].vmult(xx)
@@ -383,12 +401,27 @@ def run_native(args):
             "counts_rank0": counts, "phases_ms_rank0": phases, "roofline": roofline, "spmv": spmv,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "cpu_baseline": cpu_base,
             "device_bytes_rank0": ctx.device_bytes(), "gen_seconds": t_gen,
-            "ct_vmult_reduction": ("none (1 GPU)" if world == 1 else ("nm_spmv_push over NVLink, %s" % ("multimem.red on the multicast address" if fused["op"].multicast else "red.add into peer-mapped vectors") if fused["op"] is not None else "nccl all_reduce" + (" (fused path unavailable: %s)" % fused["why"] if fused["why"] else ""))),
+            "ct_vmult_reduction": ct_vmult_label(world, args, fused),
         }
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def ct_vmult_label(world, args, fused):
+    """How the partial Ct.vmult results of the ranks were combined in the timed step."""
+    if world == 1:
+        return "none (1 GPU)"
+    why = " (fused path unavailable: %s)" % fused["why"] if fused["why"] else ""
+    if args.ct_vmult == "owned":
+        if fused["op"] is not None:
+            return "result distributed by dof ownership: nm_spmv_push_owned over NVLink (red.add into the owner's peer-mapped vector)"
+        return "result distributed by dof ownership: nccl reduce_scatter" + why
+    if fused["op"] is not None:
+        return "replicated result: nm_spmv_push over NVLink, %s" % ("multimem.red on the multicast address" if fused["op"].multicast
+                                                                    else "red.add into peer-mapped vectors")
+    return "replicated result: nccl all_reduce" + why
 
 
 def main():

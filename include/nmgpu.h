@@ -180,6 +180,13 @@ int nm_spmv(nm_ctx *ctx, int transpose, const double *x, double *y, int where);
  * all-reduce: only the rows a rank owns cross the links. */
 int nm_spmv_push(nm_ctx *ctx, const double *x, int n_targets, double *const *y_targets, int multicast);
 
+/* The same fused product with reduce-scatter semantics, for a consumer that is distributed by background-dof ownership
+ * like the reference's (Ct*lambda is a TrilinosWrappers::MPI::Vector, 2d3d/lagrange_multiplier.cc:627-643): rank k owns
+ * the dofs [k*rows_per_rank, (k+1)*rows_per_rank) (the last rank up to n_space) and every row result is added only into
+ * y_targets[owner][dof] -- this GPU's own vector or a peer-mapped one.  Each vector has n_space entries; after all
+ * ranks' calls the owned range of a rank's vector holds the product.  Same zero-before / synchronise-after contract. */
+int nm_spmv_push_owned(nm_ctx *ctx, const double *x, int n_ranks, double *const *y_targets, uint64_t rows_per_rank);
+
 /* ---- the whole assembly from HOST arrays in one call, uploads overlapped with the computation ----
  * Same result as nm_set_background_boxes + nm_set_immersed + nm_intersect + nm_build_sparsity + nm_assemble with
  * NM_HOST pointers, i.e. what collect_quadratures_on_overlapped_grids (code/src/coupling_utilities.cc:22-69) followed by

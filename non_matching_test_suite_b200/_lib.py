@@ -25,7 +25,7 @@ PHASES = ["upload", "index", "candidates", "split", "clip", "merge", "transpose"
 SYMBOLS = ["nm_version", "nm_create", "nm_destroy", "nm_last_error", "nm_set_background", "nm_set_background_boxes",
            "nm_set_background_dofs", "nm_set_immersed_dofs", "nm_set_immersed", "nm_flag_overlapped_background", "nm_intersect", "nm_get_candidates", "nm_get_pairs", "nm_get_quadrature",
            "nm_get_split_codes", "nm_build_sparsity", "nm_assemble", "nm_assemble_from_quadrature", "nm_assemble_host", "nm_assemble_nitsche", "nm_get_nitsche", "nm_get_csr",
-           "nm_spmv", "nm_spmv_push", "nm_get_timings", "nm_get_launch_count", "nm_device_bytes", "nm_get_stream"]
+           "nm_spmv", "nm_spmv_push", "nm_spmv_push_owned", "nm_get_timings", "nm_get_launch_count", "nm_device_bytes", "nm_get_stream"]
 
 
 class NmError(RuntimeError):
@@ -86,6 +86,7 @@ def load():
     L.nm_get_csr.argtypes = [P, I, P, P, P, I]
     L.nm_spmv.argtypes = [P, I, P, P, I]
     L.nm_spmv_push.argtypes = [P, P, I, C.POINTER(C.c_void_p), I]
+    L.nm_spmv_push_owned.argtypes = [P, P, I, C.POINTER(C.c_void_p), U64]
     L.nm_get_timings.argtypes = [P, P, I]
     L.nm_device_bytes.argtypes = [P, C.POINTER(U64)]
     L.nm_get_launch_count.argtypes = [P, C.POINTER(U64)]
@@ -308,6 +309,14 @@ class Context:
         torch.cuda.current_stream().synchronize()
         arr = (C.c_void_p * len(target_ptrs))(*[C.c_void_p(int(p)) for p in target_ptrs])
         self._chk(self.L.nm_spmv_push(self.h, C.c_void_p(x.data_ptr()), len(target_ptrs), arr, int(multicast)))
+
+    def spmv_push_owned(self, x: torch.Tensor, rank_ptrs, rows_per_rank: int):
+        """Ct.vmult with reduce-scatter semantics: every non-empty row result is added into the vector of the rank
+        that owns the dof (contiguous ranges of `rows_per_rank` dofs); `rank_ptrs[k]` = rank k's result vector."""
+        assert x.is_cuda
+        torch.cuda.current_stream().synchronize()
+        arr = (C.c_void_p * len(rank_ptrs))(*[C.c_void_p(int(p)) for p in rank_ptrs])
+        self._chk(self.L.nm_spmv_push_owned(self.h, C.c_void_p(x.data_ptr()), len(rank_ptrs), arr, int(rows_per_rank)))
 
     # ---- introspection ------------------------------------------------------------------
     def timings(self) -> dict:

@@ -715,6 +715,20 @@ int nm_spmv_push(nm_ctx *ctx, const double *x, int n_targets, double *const *tar
   return NM_OK;
 }
 
+int nm_spmv_push_owned(nm_ctx *ctx, const double *x, int n_ranks, double *const *y_targets, uint64_t rows_per_rank)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  if (!x || !y_targets || n_ranks < 1 || n_ranks > 16) return nm_fail(ctx, NM_ERR_INVALID, "1..16 rank vectors expected");
+  if (rows_per_rank == 0) return nm_fail(ctx, NM_ERR_INVALID, "rows_per_rank must be positive");
+  for (int i = 0; i < n_ranks; ++i)
+    if (!y_targets[i]) return nm_fail(ctx, NM_ERR_INVALID, "null target vector");
+  NM_TRY(ensure_matrix(ctx));
+  NM_TRY(nm_spmv_push_owned_run(ctx, x, n_ranks, y_targets, rows_per_rank));
+  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return NM_OK;
+}
+
 int nm_get_timings(nm_ctx *ctx, float *ms, int n)
 {
   if (!ctx || !ms) return NM_ERR_INVALID;

@@ -199,5 +199,6 @@ int nm_nitsche_run(nm_ctx *ctx, uint64_t n_pairs, const uint32_t *bg, const uint
                    const double *weights, const double *coefficient, const double *rhs_values, double penalty, int what, int where);
 int nm_spmv_run(nm_ctx *ctx, int transpose, const double *x_dev, double *y_dev);
 int nm_stored_rowptr_global(nm_ctx *ctx, uint64_t *rowptr_dev);
+int nm_spmv_push_owned_run(nm_ctx *ctx, const double *x, int n_ranks, double *const *targets, uint64_t rows_per_rank);
 int nm_exclusive_scan_u64(nm_ctx *ctx, const uint64_t *in, uint64_t *out, uint64_t n);
 int nm_exclusive_scan_u32_to_u64(nm_ctx *ctx, const uint32_t *in, uint64_t *out, uint64_t n);

@@ -34,6 +34,29 @@ class ShardedCouplingOperator:
             dist.all_reduce(y, op=dist.ReduceOp.SUM, group=self.group)
         return y
 
+    def owned_range(self, rank: Optional[int] = None):
+        """Background dofs owned by `rank` when the result of Ct.vmult is distributed: contiguous ranges of
+        ceil(m / world) dofs, the layout of a linear Epetra map."""
+        return owned_dof_range(self.m, dist.get_rank(self.group) if rank is None and dist.is_initialized() else (rank or 0), self.world)
+
+    def vmult_owned(self, lam: torch.Tensor) -> torch.Tensor:
+        """The owned slice of y = A lam (reference: Ct*lambda lands in a vector distributed by dof ownership):
+        reduce-scatter instead of all-reduce.  NCCL reduce_scatter needs equal chunks, so the partial vector is padded
+        to world * rows_per_rank; gloo (CPU tests) has no reduce_scatter and takes the slice of an all-reduce."""
+        y = self.local_vmult(lam)
+        if self.world == 1:
+            return y
+        lo, hi = self.owned_range()
+        rpr = rows_per_rank(self.m, self.world)
+        if y.is_cuda:
+            pad = torch.zeros(rpr * self.world, dtype=y.dtype, device=y.device)
+            pad[:self.m] = y
+            out = torch.empty(rpr, dtype=y.dtype, device=y.device)
+            dist.reduce_scatter_tensor(out, pad, op=dist.ReduceOp.SUM, group=self.group)
+            return out[:hi - lo]
+        dist.all_reduce(y, op=dist.ReduceOp.SUM, group=self.group)
+        return y[lo:hi].clone()
+
     def Tvmult(self, u: torch.Tensor) -> torch.Tensor:
         """z = A^T u  (reference: C.Tvmult).  A rank's result is non-zero only in its own immersed DoFs,
         so the replicated vector is the element-wise sum over ranks."""
@@ -41,6 +64,17 @@ class ShardedCouplingOperator:
         if self.world > 1:
             dist.all_reduce(z, op=dist.ReduceOp.SUM, group=self.group)
         return z
+
+
+def rows_per_rank(n_dofs: int, world: int) -> int:
+    return max(1, -(-n_dofs // world))
+
+
+def owned_dof_range(n_dofs: int, rank: int, world: int):
+    rpr = rows_per_rank(n_dofs, world)
+    lo = min(n_dofs, rank * rpr)
+    hi = n_dofs if rank == world - 1 else min(n_dofs, lo + rpr)
+    return lo, hi
 
 
 def from_context(ctx, group=None) -> ShardedCouplingOperator:
@@ -74,6 +108,19 @@ class FusedCtVmult:
             self.available = True
         except Exception as e:  # no symmetric memory on this system: keep NCCL
             self.reason = "%s: %s" % (type(e).__name__, str(e)[:200])
+
+    def vmult_owned(self, lam: torch.Tensor) -> torch.Tensor:
+        """The slice of y = A lam this rank owns (contiguous dof ranges, `owned_dof_range`): every row result crosses
+        NVLink once, to its owner, instead of once per rank (nm_spmv_push_owned).  Returns a view of the symmetric
+        buffer.  Only the owned slice is zeroed and valid."""
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        lo, hi = owned_dof_range(self.ctx.n_space_dofs, rank, world)
+        self.y[lo:hi].zero_()
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        self.ctx.spmv_push_owned(lam, self.ptrs, rows_per_rank(self.ctx.n_space_dofs, world))
+        dist.barrier(group=self.group)
+        return self.y[lo:hi]
 
     def vmult(self, lam: torch.Tensor) -> torch.Tensor:
         """Replicated y = A lam on every rank.  Two rank barriers bracket the kernel: all vectors are zero

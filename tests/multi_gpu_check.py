@@ -51,6 +51,22 @@ def main():
             print("world %d  n_space %d  multicast=%s  rel err %.2e  spmv+allreduce %.3f ms  fused push %.3f ms" % (
                 world, bg.n_dofs, f.multicast, err, t_nccl, t_fused), flush=True)
         ok &= err < 1e-12
+        if not prefer_mc:
+            # reduce-scatter semantics: the owned slice of the fused push and of SpMV + NCCL reduce_scatter
+            lo, hi = nmd.owned_dof_range(bg.n_dofs, rank, world)
+            y_own = f.vmult_owned(lam).clone()
+            y_rs = ref_op.vmult_owned(lam)
+            scale = float(y_ref.abs().max())
+            e_own = float((y_own - y_ref[lo:hi]).abs().max()) / scale if hi > lo else 0.0
+            e_rs = float((y_rs - y_ref[lo:hi]).abs().max()) / scale if hi > lo else 0.0
+            t_own = timed(lambda: f.vmult_owned(lam))
+            t_rs = timed(lambda: ref_op.vmult_owned(lam))
+            errs = torch.tensor([e_own, e_rs], dtype=torch.float64, device=dev)
+            dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                print("world %d  owned slices: rel err fused %.2e  nccl reduce_scatter %.2e   spmv+reduce_scatter %.3f ms  fused owned push %.3f ms" % (
+                    world, float(errs[0]), float(errs[1]), t_rs, t_own), flush=True)
+            ok &= float(errs.max()) < 1e-12
         if not f.multicast and prefer_mc:
             break
     ctx.close()

@@ -30,12 +30,13 @@ def _worker(rank, world, port, out):
     lam = torch.rand(im.n_dofs, dtype=torch.float64, generator=g)
     u = torch.rand(bg.n_dofs, dtype=torch.float64, generator=g)
     y, z = op.vmult(lam), op.Tvmult(u)
+    y_own = op.vmult_owned(lam)          # reduce-scatter semantics: the slice of the dofs this rank owns
     # columns owned by this rank only
     owned = np.unique(A.nonzero()[1])
     if rank == 0:
-        torch.save({"y": y, "z": z, "owned": owned}, out)
+        torch.save({"y": y, "z": z, "owned": owned, "y_own": y_own, "range": op.owned_range()}, out)
     else:
-        torch.save({"owned": owned}, out + ".1")
+        torch.save({"owned": owned, "y_own": y_own, "range": op.owned_range()}, out + ".1")
     dist.barrier()
     dist.destroy_process_group()
 
@@ -57,3 +58,22 @@ def test_two_rank_gloo(tmp_path, c_oracle):
     u = torch.rand(bg.n_dofs, dtype=torch.float64, generator=g)
     assert np.allclose(got["y"].numpy(), A @ lam.numpy(), rtol=1e-13, atol=1e-16)
     assert np.allclose(got["z"].numpy(), A.T @ u.numpy(), rtol=1e-13, atol=1e-16)
+    # the owned slices tile the background vector and concatenate to the replicated result
+    assert got["range"][0] == 0 and got["range"][1] == other["range"][0] and other["range"][1] == bg.n_dofs
+    assert torch.equal(torch.cat([got["y_own"], other["y_own"]]), got["y"])
+
+
+def test_owned_dof_ranges_tile_the_vector():
+    from non_matching_test_suite_b200.distributed import owned_dof_range, rows_per_rank
+    for n in (0, 1, 7, 8, 1000003):
+        for world in (1, 2, 3, 8):
+            rpr = rows_per_rank(n, world)
+            prev = 0
+            for r in range(world):
+                lo, hi = owned_dof_range(n, r, world)
+                assert lo == prev and lo <= hi <= n
+                # the device kernel's owner rule: min(dof // rows_per_rank, world - 1)
+                for dof in {lo, hi - 1} if hi > lo else set():
+                    assert min(dof // rpr, world - 1) == r
+                prev = hi
+            assert prev == n

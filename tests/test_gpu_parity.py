@@ -435,3 +435,24 @@ def test_assemble_host_equals_separate_calls(name, cycle, pinned):
         ctx.assemble_host(*args, 0, 1e-15)
     assert e.value.code == 1 and "Invalid quadrature degree" in str(e.value)
     ctx.close(); ref.close()
+
+
+def test_spmv_push_owned_single_gpu():
+    """nm_spmv_push_owned with three pretend ranks on one GPU: each dof's row result lands only in the vector of the
+    range that owns it; the last range takes the remainder."""
+    from non_matching_test_suite_b200.distributed import owned_dof_range, rows_per_rank
+    bg, im = make_config("sphere", 1, band_only=False)
+    ctx = coupling.make_context(bg, im)
+    ctx.intersect(3, 1e-15)
+    ctx.build_sparsity()
+    x = torch.rand(im.n_dofs, dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(4))
+    y_ref = ctx.spmv(x, transpose=False)
+    world = 3
+    ys = [torch.zeros(bg.n_dofs, dtype=torch.float64, device="cuda") for _ in range(world)]
+    ctx.spmv_push_owned(x, [y.data_ptr() for y in ys], rows_per_rank(bg.n_dofs, world))
+    for r, y in enumerate(ys):
+        lo, hi = owned_dof_range(bg.n_dofs, r, world)
+        assert torch.equal(y[lo:hi], y_ref[lo:hi])
+        mask = torch.ones(bg.n_dofs, dtype=torch.bool, device="cuda"); mask[lo:hi] = False
+        assert float(y[mask].abs().sum()) == 0.0
+    ctx.close()
