@@ -468,9 +468,17 @@ void create_nitsche_rhs_with_exact_intersections(
                                                                 penalty, NM_NITSCHE_RHS);
   std::vector<double> rhs(space_dh.n_dofs());
   nmgpu_detail::check(s, nm_get_nitsche(s.ctx, nullptr, nullptr, nullptr, rhs.data(), NM_HOST));
+  // one batched add: off-process rows are legal for the distributed vector types and reach their owner in the caller's
+  // compress(VectorOperation::add), exactly like the element-wise adds of distribute_local_to_global
+  std::vector<types::global_dof_index> rows;
+  std::vector<typename Vector::value_type> vals;
   for (types::global_dof_index r = 0; r < space_dh.n_dofs(); ++r)
-    if (rhs[r] != 0.)
-      rhs_vector(r) += rhs[r];
+    if (rhs[r] != 0.) {
+      rows.push_back(r);
+      vals.push_back(static_cast<typename Vector::value_type>(rhs[r]));
+    }
+  if (!rows.empty())
+    rhs_vector.add(rows, vals);
 }
 
 } // namespace NonMatching

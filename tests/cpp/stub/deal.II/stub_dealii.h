@@ -62,7 +62,12 @@ private:
 
 template <typename T> class Vector {
 public:
+  using value_type = T;
   explicit Vector(std::size_t n) : v(n, T(0)) {}
+  void add(const std::vector<types::global_dof_index> &indices, const std::vector<T> &values)
+  {
+    for (std::size_t k = 0; k < indices.size(); ++k) v[indices[k]] += values[k];
+  }
   std::size_t size() const { return v.size(); }
   T &operator()(std::size_t i) { return v[i]; }
   const T &operator()(std::size_t i) const { return v[i]; }

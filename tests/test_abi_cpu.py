@@ -54,3 +54,20 @@ def test_wrapper_argument_checks_mirror_the_reference():
     bg, im = make_config("disk", 0, band_only=False)
     with pytest.raises(ValueError, match="Invalid quadrature degree"):
         coupling.collect_quadratures_on_overlapped_grids(bg, im, 0)
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """nm_counts and nm_host_problem as a C compiler lays them out against the ctypes mirrors in _lib.py."""
+    import subprocess
+    from non_matching_test_suite_b200 import _lib
+    src = tmp_path / "layout.c"
+    fields = [n for n, _ in _lib.HostProblem._fields_]
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "nmgpu.h"\nint main(void){\n'
+                   'printf("%zu %zu\\n", sizeof(nm_counts), sizeof(nm_host_problem));\n' +
+                   "".join('printf("%%zu\\n", offsetof(nm_host_problem, %s));\n' % f for f in fields) + "return 0;}\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["/usr/bin/gcc", "-std=c11", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().split()
+    assert int(out[0]) == ctypes.sizeof(_lib.Counts) and int(out[1]) == ctypes.sizeof(_lib.HostProblem)
+    for f, off in zip(fields, out[2:]):
+        assert getattr(_lib.HostProblem, f).offset == int(off), f
