@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--ref-cycle", type=int, default=None, help="refinement cycle of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-two-in-flight", action="store_true",
+                    help="additionally report the end-to-end throughput with two independent steps in flight (two contexts, two host "
+                         "threads): PCIe is full duplex, so the uploads of one step run under the read-back of the other")
     ap.add_argument("--e2e-separate-calls", action="store_true",
                     help="end-to-end leg through nm_set_background_boxes + nm_set_immersed + nm_intersect + ... instead of nm_assemble_host")
     ap.add_argument("--ct-vmult", choices=["replicated", "owned"], default="replicated",
@@ -382,6 +385,8 @@ def run_native(args):
                        "_lib.Context (C ABI): nm_assemble_host (host lo/hi + dofs + constraint lines + immersed grid in one call, uploads "
                        "overlapped with the phases that do not need them yet)") +
                       " + nm_spmv x2 (host vectors) + nm_get_csr read-back into pinned host memory"}
+        if args.e2e_two_in_flight and world == 1 and "lo" in host_in:
+            e2e["two_steps_in_flight"] = two_in_flight(_lib, local, ctx, host_in, xh, uh, bg, im, d, e_steps, tot_acc)
         del host_in
 
     cpu_base = None
@@ -407,6 +412,57 @@ def run_native(args):
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def two_in_flight(_lib, local, ctx0, host_in, xh, uh, bg, im, d, steps, pairs_per_step):
+    """End-to-end throughput for a STREAM of problems: two contexts, each driven by its own host thread through the same
+    calls as the e2e leg (every step uploads its inputs from pinned memory and reads its matrix and vectors back), so the
+    host->device traffic of one step overlaps the device->host traffic and the kernels of the other.  Wall clock between
+    device synchronisations; reported next to `e2e`, never instead of it."""
+    import threading
+    import torch
+    ctxs = [ctx0, _lib.Context(local)]
+    outs = [{}, {}]
+
+    def one(c, o):
+        c.assemble_host(d, host_in["lo"], host_in["hi"], host_in["dofs"], bg.n_dofs, host_in["c_dof"], host_in["c_ptr"], host_in["c_master"],
+                        host_in["c_weight"], im.dim, host_in["im_verts"], host_in["im_dofs"], im.n_dofs, 3, 1e-15)
+        if "y" not in o:
+            cap = int(c.nnz * 1.05) + 16
+            o["y"] = torch.empty(bg.n_dofs, dtype=torch.float64).pin_memory()
+            o["z"] = torch.empty(im.n_dofs, dtype=torch.float64).pin_memory()
+            o["csr"] = (torch.empty(bg.n_dofs + 1, dtype=torch.int64).pin_memory(), torch.empty(cap, dtype=torch.int32).pin_memory(),
+                        torch.empty(cap, dtype=torch.float64).pin_memory())
+        c.spmv(xh, transpose=False, out=o["y"])
+        c.spmv(uh, transpose=True, out=o["z"])
+        c.csr(transpose=False, values=True, out=o["csr"])
+
+    for c, o in zip(ctxs, outs):       # warm-up: allocations of both contexts
+        one(c, o)
+    torch.cuda.synchronize()
+    errs = []
+
+    def worker(i):
+        try:
+            for _ in range(steps):
+                one(ctxs[i], outs[i])
+        except Exception as e:  # surfaced after the join
+            errs.append(e)
+
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if errs:
+        raise errs[0]
+    same = all(torch.equal(a, b) for a, b in zip(outs[0]["csr"], outs[1]["csr"])) and torch.equal(outs[0]["y"], outs[1]["y"])
+    ctxs[1].close()
+    return {"value": 2 * steps * pairs_per_step / dt, "unit": UNIT, "ms_per_step": dt / (2 * steps) * 1e3, "steps": 2 * steps,
+            "contexts": 2, "results_identical": bool(same), "timing": "wall clock between device synchronisations"}
 
 
 def ct_vmult_label(world, args, fused):
