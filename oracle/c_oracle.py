@@ -38,6 +38,7 @@ def lib():
         L.nmo_orient2d.argtypes = [P, P, P]
         L.nmo_incircle.argtypes = [P, P, P, P]
         L.nmo_pairs.argtypes = [C.c_int, C.c_int64, P, P, P, P, P, C.c_int, C.c_double, P, P, P, P]
+        L.nmo_pairs_quadrature.argtypes = [C.c_int, C.c_int64, P, P, P, P, P, C.c_int, C.c_double, P, P, P]
         L.nmo_build_csr.restype = C.c_int64
         L.nmo_build_csr.argtypes = [C.c_int, C.c_int64, P, P, P, P, C.c_int64, P, P, P, P,
                                     C.POINTER(P), C.POINTER(P), C.POINTER(P)]
@@ -114,6 +115,20 @@ def pairs(d, cand, bg_lo, bg_hi, im_verts, codes, n1d=3, tol=1e-15):
     return sumw, local, nq, dropped.value
 
 
+def quadrature(d, pairs_keys, nq, bg_lo, bg_hi, im_verts, codes, n1d=3, tol=1e-15):
+    """(q_offset, points, weights) of the given pairs in the reference's own subdivision (nmo_pairs_quadrature);
+    `nq` = the per-pair point counts `pairs()` reported."""
+    keys = _np(pairs_keys, np.uint64)
+    q_off = np.concatenate([[0], np.cumsum(_np(nq, np.int64))]).astype(np.uint64)
+    pts = np.zeros((int(q_off[-1]), d)); wts = np.zeros(int(q_off[-1]))
+    cd = None if codes is None else _np(codes, np.uint8)
+    rc = lib().nmo_pairs_quadrature(d, keys.shape[0], _p(keys), _p(_np(bg_lo, np.float64)), _p(_np(bg_hi, np.float64)),
+                                    _p(_np(im_verts, np.float64)), _p(cd), n1d, tol, _p(q_off), _p(pts), _p(wts))
+    if rc != 0:
+        raise ValueError("nmo_pairs_quadrature failed (%d): unsupported rule or inconsistent point counts" % rc)
+    return q_off, pts, wts
+
+
 def line_table(bg):
     n = bg.n_dofs
     line_of = np.full(n, -1, dtype=np.int32)
@@ -185,3 +200,10 @@ def assemble(bg, im, n1d: int = 3, tol: float = 1e-15, threads: Optional[int] = 
     rowptr, col, val = build_csr(d, acc, local[keep], bg, im)
     return dict(candidates=cand, codes=codes, sum_w_all=sumw, accepted=acc, sum_w=sumw[keep], local=local[keep],
                 nq=nq[keep], dropped=dropped, rowptr=rowptr, col=col, val=val)
+
+
+def assemble_with_quadrature(bg, im, n1d: int = 3, tol: float = 1e-15):
+    """assemble() plus the per-pair quadrature in the reference's subdivision: adds q_offset, points, weights."""
+    r = assemble(bg, im, n1d, tol)
+    r["q_offset"], r["points"], r["weights"] = quadrature(bg.spacedim, r["accepted"], r["nq"], bg.lo, bg.hi, im.verts, r["codes"], n1d, tol)
+    return r

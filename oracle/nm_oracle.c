@@ -304,7 +304,18 @@ static int rule_tri(int n, double (*x)[2], double *w)
 /* ------------------------------------------------------------------------- */
 /* per-pair geometry                                                          */
 /* ------------------------------------------------------------------------- */
-typedef struct { double sumw; double local[8]; int nq; int dropped; } pair_out;
+typedef struct {
+  double sumw; double local[8]; int nq; int dropped;
+  double *qp, *qw; /* optional sinks for the quadrature points / weights of the pair (nmo_pairs_quadrature) */
+} pair_out;
+
+static inline void emit_point(pair_out *o, int d, const double *x, double w)
+{
+  if (o->qp) {
+    for (int k = 0; k < d; ++k) o->qp[(int64_t)o->nq * d + k] = x[k];
+    o->qw[o->nq] = w;
+  }
+}
 
 static inline void q1_accumulate(int d, const double *lo, const double *hi, const double *x, double w, double *local)
 { /* xi = F^{-1}(x) on an axis-aligned cell; phi_i = prod_k (bit_k(i) ? xi_k : 1 - xi_k)
@@ -360,6 +371,7 @@ static void pair_2d(const double *lo, const double *hi, const double *seg, int n
       double x[2] = {a[0] + gx[q] * (b[0] - a[0]), a[1] + gx[q] * (b[1] - a[1])};
       double w = J * gw[q];
       o->sumw += w;
+      emit_point(o, 2, x, w);
       o->nq++;
       q1_accumulate(2, lo, hi, x, w, o->local);
     }
@@ -398,6 +410,7 @@ static void tri_quadrature(const double *lo, const double *hi, const double *a, 
     for (int k = 0; k < 3; ++k) x[k] = a[k] + gx[q][0] * e1[k] + gx[q][1] * e2[k];
     double w = J * gw[q];
     o->sumw += w;
+    emit_point(o, 3, x, w);
     o->nq++;
     q1_accumulate(3, lo, hi, x, w, o->local);
   }
@@ -466,6 +479,32 @@ int nmo_pairs(int d, int64_t n_cand, const uint64_t *cand, const double *bg_lo, 
   }
   if (n_dropped) *n_dropped = dropped;
   return 0;
+}
+
+/* The Quadrature<spacedim> of every given pair, in the reference's own subdivision (2D: the two CDT triangles of the
+ * background quad, intersections.cc:375-388; 3D: tetrahedra x Delaunay triangles, :459-503), as
+ * collect_quadratures_on_overlapped_grids returns it in its tuples (coupling_utilities.cc:57-66).
+ * q_off[n+1] must hold the offsets built from the point counts nmo_pairs reported. */
+int nmo_pairs_quadrature(int d, int64_t n, const uint64_t *pairs, const double *bg_lo, const double *bg_hi, const double *im_verts,
+                         const uint8_t *codes, int n1d, double tol, const uint64_t *q_off, double *pts, double *wts)
+{
+  double tx[16][2], tw[16];
+  if (d == 2 ? rule_1d(n1d, tw, tw) == 0 : rule_tri(n1d, tx, tw) == 0) return -1;
+  int bad = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : bad)
+  for (int64_t i = 0; i < n; ++i) {
+    uint32_t m = (uint32_t)(pairs[i] >> 32), b = (uint32_t)pairs[i];
+    pair_out o;
+    memset(&o, 0, sizeof(o));
+    o.qp = pts + (int64_t)q_off[i] * d;
+    o.qw = wts + q_off[i];
+    if (d == 2)
+      pair_2d(bg_lo + 2 * (int64_t)b, bg_hi + 2 * (int64_t)b, im_verts + 4 * (int64_t)m, n1d, tol, &o);
+    else
+      pair_3d(bg_lo + 3 * (int64_t)b, bg_hi + 3 * (int64_t)b, im_verts + 12 * (int64_t)m, codes[m], n1d, tol, &o);
+    bad += (uint64_t)o.nq != q_off[i + 1] - q_off[i];
+  }
+  return bad ? -2 : 0;
 }
 
 /* ------------------------------------------------------------------------- */

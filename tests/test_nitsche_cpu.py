@@ -105,3 +105,70 @@ def test_oracle_nitsche_zero_diagonal_uses_block_average(c_oracle):
     phi = np.array([0.0, 0.5, 0.0, 0.5])
     diag = 4.0 / h * phi * phi * 0.3
     assert A[0, 0] == pytest.approx(np.abs(diag).mean(), rel=1e-15)
+
+
+@pytest.mark.parametrize("name,cycle", [("disk", 1), ("sphere", 0)])
+def test_oracle_quadrature_in_the_reference_subdivision(c_oracle, name, cycle):
+    """nmo_pairs_quadrature emits the points the oracle integrates with: per pair the weights sum to sum_w and the
+    Q1 local vector recomputed from the points is the oracle's."""
+    from non_matching_test_suite_b200.grids import make_config
+    bg, im = make_config(name, cycle, band_only=False)
+    r = c_oracle.assemble_with_quadrature(bg, im)
+    d = bg.spacedim
+    qo = r["q_offset"].astype(np.int64)
+    assert qo[-1] == r["nq"].sum() and r["points"].shape == (qo[-1], d)
+    sw = np.add.reduceat(r["weights"], qo[:-1])
+    assert np.abs(sw - r["sum_w"]).max() <= 1e-15 * r["sum_w"].max()
+    cells = (r["accepted"] & np.uint64(0xffffffff)).astype(np.int64)
+    lo, hi = bg.lo.numpy()[cells], bg.hi.numpy()[cells]
+    per_q = np.repeat(np.arange(len(cells)), np.diff(qo))
+    xi = (r["points"] - lo[per_q]) / (hi[per_q] - lo[per_q])
+    assert xi.min() >= -1e-12 and xi.max() <= 1 + 1e-12          # every point lies in its background cell
+    for i in range(1 << d):
+        phi = np.prod([xi[:, k] if (i >> k) & 1 else 1 - xi[:, k] for k in range(d)], axis=0)
+        loc = np.add.reduceat(phi * r["weights"], qo[:-1])
+        assert np.abs(loc - r["local"][:, i]).max() <= 1e-14 * np.abs(r["local"]).max()
+
+
+def _clip_segment(p0, p1, lo, hi):
+    """Liang-Barsky: parameter range of the segment inside the closed box, or None."""
+    t0, t1 = 0.0, 1.0
+    for k in range(2):
+        dk = p1[k] - p0[k]
+        for bound, sgn in ((lo[k], 1.0), (hi[k], -1.0)):
+            a, b = sgn * dk, sgn * (bound - p0[k])          # a t >= b
+            if a == 0:
+                if b > 0:
+                    return None
+            elif a > 0:
+                t0 = max(t0, b / a)
+            else:
+                t1 = min(t1, b / a)
+    return (t0, t1) if t0 < t1 else None
+
+
+def test_nitsche_2d_does_not_depend_on_the_subdivision(c_oracle):
+    """Rule R1 for the Nitsche terms in 2D: phi_i phi_j has degree 4 along a segment and the 3-point rule is exact to
+    degree 5, so the matrix built on the reference's subdivision (segment cut at the CDT diagonal of the background
+    quad) equals the one built on the undivided clipped segment; same for a rhs with a linear boundary function."""
+    from non_matching_test_suite_b200.grids import make_config
+    bg, im = make_config("disk", 1, band_only=False)
+    r = c_oracle.assemble_with_quadrature(bg, im)
+    cells = (r["accepted"] & np.uint64(0xffffffff)).astype(np.int64)
+    segs = (r["accepted"] >> np.uint64(32)).astype(np.int64)
+    g = 0.5 + 0.5 * np.sqrt(3.0 / 5.0) * np.array([-1.0, 0.0, 1.0]); gw = np.array([5.0, 8.0, 5.0]) / 18.0
+    pts, wts, qo = [], [], [0]
+    for c, m in zip(cells, segs):
+        p0, p1 = im.verts[m, 0].numpy(), im.verts[m, 1].numpy()
+        tr = _clip_segment(p0, p1, bg.lo[c].numpy(), bg.hi[c].numpy())
+        assert tr is not None
+        a, b = p0 + tr[0] * (p1 - p0), p0 + tr[1] * (p1 - p0)
+        pts.append(a[None, :] + g[:, None] * (b - a)[None, :]); wts.append(np.hypot(*(b - a)) * gw); qo.append(qo[-1] + 3)
+    pts, wts, qo = np.concatenate(pts), np.concatenate(wts), np.array(qo, dtype=np.uint64)
+    f_ref, f_one = 1.0 + r["points"][:, 0] - 2.0 * r["points"][:, 1], 1.0 + pts[:, 0] - 2.0 * pts[:, 1]
+    A1, b1 = c_oracle.nitsche(bg, cells, r["q_offset"], r["points"], r["weights"], None, f_ref, 10.0)
+    A2, b2 = c_oracle.nitsche(bg, cells, qo, pts, wts, None, f_one, 10.0)
+    assert r["points"].shape[0] > pts.shape[0]                 # the reference's subdivision really has more pieces
+    assert np.array_equal(A1.indptr, A2.indptr) and np.array_equal(A1.indices, A2.indices)
+    assert np.linalg.norm(A1.data - A2.data) <= 1e-13 * np.linalg.norm(A1.data)
+    assert np.linalg.norm(b1 - b2) <= 1e-13 * np.linalg.norm(b1)
