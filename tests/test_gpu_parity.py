@@ -456,3 +456,30 @@ def test_spmv_push_owned_single_gpu():
         mask = torch.ones(bg.n_dofs, dtype=torch.bool, device="cuda"); mask[lo:hi] = False
         assert float(y[mask].abs().sum()) == 0.0
     ctx.close()
+
+
+@pytest.mark.parametrize("name,cycle", [("disk", 2), ("sphere", 1)])
+def test_mass_matrix_from_the_reference_subdivision_quadrature(c_oracle, name, cycle):
+    """create_coupling_mass_matrix_with_exact_intersections fed with a FOREIGN cells_and_quads vector: the oracle's
+    quadrature in the reference's own subdivision (CDT triangles / tetrahedra x Delaunay triangles: 2-3x the points of
+    our collect, different order inside a pair), and in a shuffled tuple order.  The matrix is the oracle's: pattern
+    bit-exact, values 1e-12 (rule R1: degree <= 3 integrand, both subdivisions are exact)."""
+    bg, im = make_config(name, cycle, band_only=False)
+    ref = c_oracle.assemble_with_quadrature(bg, im, 3, 1e-15)
+    n = ref["accepted"].shape[0]
+    perm = np.random.default_rng(7).permutation(n)
+    qo = ref["q_offset"].astype(np.int64)
+    cnt = np.diff(qo)[perm]
+    off = np.concatenate([[0], np.cumsum(cnt)])
+    idx = np.concatenate([np.arange(qo[p], qo[p + 1]) for p in perm])
+    im_ids = (ref["accepted"] >> np.uint64(32)).astype(np.int32)[perm]
+    bg_ids = (ref["accepted"] & np.uint64(0xffffffff)).astype(np.int32)[perm]
+    ctx = coupling.make_context(bg, im, boxes=True)
+    ctx.assemble_from_quadrature(torch.from_numpy(im_ids), torch.from_numpy(bg_ids), torch.from_numpy(off),
+                                 torch.from_numpy(np.ascontiguousarray(ref["points"][idx])), torch.from_numpy(np.ascontiguousarray(ref["weights"][idx])))
+    rp, col, val = ctx.csr(transpose=False)
+    assert np.array_equal(rp.numpy().astype(np.uint64), ref["rowptr"])
+    assert np.array_equal(col.numpy().astype(np.uint32), ref["col"])
+    err = np.linalg.norm(val.numpy() - ref["val"]) / np.linalg.norm(ref["val"])
+    assert err <= REL_FROB_TOL, err
+    ctx.close()
