@@ -184,6 +184,35 @@ def pair_integrals_2d(lo, hi, seg):
     return float(scale), local
 
 
+# Boole's rule: rational nodes, exact to degree 5 (phi_i phi_j has degree 4 along a segment)
+_BOOLE = ((Fr(0), Fr(7, 90)), (Fr(1, 4), Fr(32, 90)), (Fr(1, 2), Fr(12, 90)), (Fr(3, 4), Fr(32, 90)), (Fr(1), Fr(7, 90)))
+
+
+def nitsche_block_2d(lo, hi, seg):
+    """Exact  int phi_i phi_j ds  over (segment n rectangle), 4x4, doubles in / doubles out: the local block of
+    assemble_nitsche_with_exact_intersections (code/include/coupling_utilities.h:366-370) for coefficient = 1 and
+    penalty / h = 1, i.e. what the reference's 3-point rule evaluates exactly on each of its sub-segments."""
+    lo = [Fr(float(x)) for x in lo]; hi = [Fr(float(x)) for x in hi]
+    p0 = [Fr(float(x)) for x in seg[0]]; p1 = [Fr(float(x)) for x in seg[1]]
+    clip = clip_segment_box(p0, p1, lo, hi)
+    if clip is None:
+        return [[0.0] * 4 for _ in range(4)]
+    t0, t1 = clip
+    d = [p1[k] - p0[k] for k in range(2)]
+    length = mpmath.sqrt(_mpf(d[0]) * _mpf(d[0]) + _mpf(d[1]) * _mpf(d[1]))
+    h = [hi[k] - lo[k] for k in range(2)]
+    acc = [[Fr(0)] * 4 for _ in range(4)]
+    for s, w in _BOOLE:
+        t = t0 + s * (t1 - t0)
+        xi = [(p0[k] + t * d[k] - lo[k]) / h[k] for k in range(2)]
+        phi = [_shape(i, xi) for i in range(4)]
+        for i in range(4):
+            for j in range(4):
+                acc[i][j] += w * phi[i] * phi[j]
+    scale = length * _mpf(t1 - t0)
+    return [[float(scale * _mpf(a)) for a in row] for row in acc]
+
+
 def _cross(u, v):
     return (u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0])
 

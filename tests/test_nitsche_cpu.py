@@ -172,3 +172,36 @@ def test_nitsche_2d_does_not_depend_on_the_subdivision(c_oracle):
     assert np.array_equal(A1.indptr, A2.indptr) and np.array_equal(A1.indices, A2.indices)
     assert np.linalg.norm(A1.data - A2.data) <= 1e-13 * np.linalg.norm(A1.data)
     assert np.linalg.norm(b1 - b2) <= 1e-13 * np.linalg.norm(b1)
+
+
+def test_nitsche_2d_against_exact_rational_blocks(c_oracle):
+    """The C oracle's Nitsche matrix on its own (reference-subdivision) quadrature against exact rational integration
+    of phi_i phi_j over (segment n cell) (oracle/exact_oracle.py::nitsche_block_2d), with constant coefficient, pushed
+    through the same constraint algebra in numpy: pins quadrature + formula + scatter of the 2D case."""
+    from oracle import exact_oracle as eo
+    from non_matching_test_suite_b200.grids import make_config
+    bg, im = make_config("disk", 0, band_only=False)
+    r = c_oracle.assemble_with_quadrature(bg, im)
+    cells = (r["accepted"] & np.uint64(0xffffffff)).astype(np.int64)
+    segs = (r["accepted"] >> np.uint64(32)).astype(np.int64)
+    pen, c0 = 10.0, 2.0
+    A, _ = c_oracle.nitsche(bg, cells, r["q_offset"], r["points"], r["weights"], np.full(r["weights"].shape[0], c0), None, pen)
+    n = bg.n_dofs
+    D = np.zeros((n, n))
+    lines = {int(bg.c_dof[k]): [(int(bg.c_master[a]), float(bg.c_weight[a])) for a in range(int(bg.c_ptr[k]), int(bg.c_ptr[k + 1]))]
+             for k in range(bg.c_dof.shape[0])}
+    for c, m in zip(cells, segs):
+        lo, hi = bg.lo[c].numpy(), bg.hi[c].numpy()
+        h = np.sqrt(((hi - lo) ** 2).sum())
+        L = c0 * pen / h * np.array(eo.nitsche_block_2d(lo, hi, im.verts[m].numpy()))
+        dofs = bg.dofs[c].numpy()
+        res = [lines[int(g)] if int(g) in lines else [(int(g), 1.0)] for g in dofs]
+        for i in range(4):
+            for rr, wr in res[i]:
+                for j in range(4):
+                    for cc, wc in res[j]:
+                        D[rr, cc] += wr * wc * L[i, j]
+            if int(dofs[i]) in lines:
+                D[dofs[i], dofs[i]] += abs(L[i, i]) if L[i, i] != 0 else np.abs(np.diag(L)).mean()
+    assert len(lines) > 0                                   # hanging-node lines take part
+    assert np.abs(A.toarray() - D).max() <= 1e-13 * np.abs(D).max()
