@@ -198,3 +198,30 @@ def test_degenerate_touching_cases(c_oracle, d):
         assert abs(per_cell[2] - 4.0) < 1e-13                  # flat quad of area 4, interior of the cells
         assert per_cell[3] == 0.0                              # vertical quad: its xy-projection is a line, no Delaunay face
         assert ref["codes"][3] & 0x0f == 0
+
+
+def test_random_quads_and_boxes_c_oracle_against_exact(c_oracle):
+    """Pair level, random general-position data: skewed (non-planar) quads of random size against random anisotropic
+    boxes -- the FP64 C restatement (tetrahedra x Delaunay triangles, 7-point rule) against exact rational clipping and
+    integration, including the split code and the local Q1 vector."""
+    rng = np.random.default_rng(20240607)
+    n = 60
+    lo = rng.uniform(-1, 1, (n, 3)); hi = lo + rng.uniform(0.05, 1.0, (n, 3))
+    quads = np.zeros((n, 4, 3))
+    for i in range(n):
+        c = 0.5 * (lo[i] + hi[i]) + rng.uniform(-0.3, 0.3, 3) * (hi[i] - lo[i])
+        e1, e2 = rng.standard_normal(3), rng.standard_normal(3)
+        s = rng.uniform(0.2, 1.5) * (hi[i] - lo[i]).max()
+        for v, (a, b) in enumerate(((-1, -1), (1, -1), (-1, 1), (1, 1))):      # deal.II vertex order
+            quads[i, v] = c + 0.5 * s * (a * e1 + b * e2) + 0.1 * s * rng.standard_normal(3)
+    codes = c_oracle.quad_split(quads)
+    cand = (np.arange(n, dtype=np.uint64) << np.uint64(32)) | np.arange(n, dtype=np.uint64)
+    sumw, local, nq, dropped = c_oracle.pairs(3, cand, lo, hi, quads, codes, 3, 1e-15)
+    hits = 0
+    for i in range(n):
+        assert eo.quad_split_code(quads[i]) == int(codes[i])
+        s_ex, l_ex = eo.pair_integrals_3d(lo[i], hi[i], quads[i])
+        assert abs(sumw[i] - s_ex) <= 1e-13 * max(s_ex, 1e-3)
+        assert np.abs(local[i] - np.array(l_ex)).max() <= 1e-13 * max(s_ex, 1e-3)
+        hits += s_ex > 0
+    assert hits > n // 2
