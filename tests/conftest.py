@@ -21,3 +21,14 @@ def c_oracle():
     from oracle import c_oracle as co
     co.build()
     return co
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _native_library():
+    """The tests load non_matching_test_suite_b200/libnmgpu.so; on a fresh checkout (the .so is not in the history)
+    build it once with the repo's own Makefile (nvcc cross-compiles sm_100a without a GPU)."""
+    lib = os.path.join(ROOT, "non_matching_test_suite_b200", "libnmgpu.so")
+    if not os.path.exists(lib):
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "non_matching_test_suite_b200", "csrc")])
+    yield
