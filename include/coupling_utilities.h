@@ -54,15 +54,39 @@ struct Session {
   nm_ctx *ctx = nullptr;
   bool grids_set = false, space_set = false;
   std::uint64_t n_space = 0, n_immersed = 0;
+  std::size_t space_active_cells = 0, immersed_active_cells = 0;   // n_active_cells() of the grids on the device
   std::vector<unsigned int> space_local_of_active;     // active_cell_index -> row in the arrays sent to the GPU (or -1)
   std::vector<unsigned int> immersed_local_of_active;
+  // Fingerprint of the vector collect_quadratures_on_overlapped_grids returned last.  When the sparsity / mass-matrix
+  // calls receive that same vector (the reference's flow: 2d3d/lagrange_multiplier.cc:750-753 -> 488-490 -> 599-602)
+  // the quadrature is still on the device and nothing is sent back; any other vector takes the upload path.
+  struct {
+    bool valid = false;
+    std::size_t size = 0;
+    const void *first = nullptr, *last = nullptr;      // point storage of the first / last Quadrature
+    double w_first = 0, w_last = 0;
+  } own;
+  // the DoF tables on the device were taken from these objects
+  struct {
+    bool valid = false;
+    const void *space_dh = nullptr, *immersed_dh = nullptr, *constraints = nullptr;
+    std::uint64_t n_space = 0, n_immersed = 0, n_constraints = 0;
+  } dofs;
   ~Session() { if (ctx) nm_destroy(ctx); }
 };
 
+using SessionMap = std::map<std::pair<const void *, const void *>, std::unique_ptr<Session>>;
+inline SessionMap &sessions()
+{
+  // never destroyed: no CUDA call may run during static destruction, when the runtime may already be gone;
+  // nmgpu_release() frees the contexts (and their device memory) explicitly
+  static SessionMap *m = new SessionMap();
+  return *m;
+}
+
 inline Session &session(const void *space_tria, const void *immersed_tria)
 {
-  static std::map<std::pair<const void *, const void *>, std::unique_ptr<Session>> sessions;
-  auto &slot = sessions[{space_tria, immersed_tria}];
+  auto &slot = sessions()[{space_tria, immersed_tria}];
   if (!slot) {
     slot = std::make_unique<Session>();
     const char *dev = std::getenv("NMGPU_DEVICE");
@@ -70,6 +94,27 @@ inline Session &session(const void *space_tria, const void *immersed_tria)
     AssertThrow(rc == NM_OK, ExcMessage("nmgpu: no CUDA device / context creation failed (there is no CPU fallback)"));
   }
   return *slot;
+}
+
+// The grids on the device are those of an earlier call: still the same mesh?  (A refine/coarsen between
+// collect_quadratures_on_overlapped_grids and the matrix calls changes the active cell count.)
+template <int dim0, int dim1, int spacedim>
+bool grids_current(const Session &s, const Triangulation<dim0, spacedim> &space, const Triangulation<dim1, spacedim> &immersed)
+{
+  return s.grids_set && s.space_active_cells == space.n_active_cells() && s.immersed_active_cells == immersed.n_active_cells();
+}
+
+template <typename Info> bool is_own_result(const Session &s, const Info &info)
+{
+  if (!s.own.valid || info.size() != s.own.size)
+    return false;
+  if (info.empty())
+    return true;
+  const auto &qf = std::get<2>(info.front());
+  const auto &ql = std::get<2>(info.back());
+  return qf.size() > 0 && ql.size() > 0 && static_cast<const void *>(qf.get_points().data()) == s.own.first &&
+         static_cast<const void *>(ql.get_points().data()) == s.own.last && qf.weight(0) == s.own.w_first &&
+         ql.weight(ql.size() - 1) == s.own.w_last;
 }
 
 inline void check(const Session &s, int rc)
@@ -153,6 +198,10 @@ void set_grids(Session &s, const Triangulation<dim0, spacedim> &space, const Map
   check(s, nm_set_immersed(s.ctx, dim1, spacedim, s.n_immersed, v1.data(), nullptr, 1, 0, NM_HOST));
   s.grids_set = true;
   s.space_set = true;
+  s.space_active_cells = space.n_active_cells();
+  s.immersed_active_cells = immersed.n_active_cells();
+  s.own.valid = false;
+  s.dofs.valid = false;
 }
 
 // DoF indices of the background cells + the lines of the closed AffineConstraints object as CSR.
@@ -175,18 +224,19 @@ void set_space_dofs(Session &s, const DoFHandler<dim0, spacedim> &space_dh, cons
   std::vector<std::uint32_t> c_dof, c_master;
   std::vector<std::uint64_t> c_ptr(1, 0);
   std::vector<double> c_weight;
-  for (types::global_dof_index i = 0; i < space_dh.n_dofs(); ++i)
-    if (constraints.is_constrained(i)) {
-      c_dof.push_back(static_cast<std::uint32_t>(i));
-      if (const auto *entries = constraints.get_constraint_entries(i))
-        for (const auto &e : *entries) {
-          c_master.push_back(static_cast<std::uint32_t>(e.first));
-          c_weight.push_back(static_cast<double>(e.second));
-        }
-      c_ptr.push_back(c_master.size());
+  // the lines of the (closed, hence index-sorted) constraint object; never is_constrained(i) over all dofs, which
+  // asserts on a distributed AffineConstraints with local_lines
+  for (const auto &line : constraints.get_lines()) {
+    c_dof.push_back(static_cast<std::uint32_t>(line.index));
+    for (const auto &e : line.entries) {
+      c_master.push_back(static_cast<std::uint32_t>(e.first));
+      c_weight.push_back(static_cast<double>(e.second));
     }
+    c_ptr.push_back(c_master.size());
+  }
   check(s, nm_set_background_dofs(s.ctx, d0.data(), space_dh.n_dofs(), c_dof.size(), c_dof.data(), c_ptr.data(), c_master.data(),
                                   c_weight.data(), NM_HOST));
+  s.dofs.valid = false;   // set_dofs marks the pair of tables valid again
 }
 
 template <int dim0, int dim1, int spacedim, typename number>
@@ -197,6 +247,11 @@ void set_dofs(Session &s, const DoFHandler<dim0, spacedim> &space_dh, const DoFH
   AssertThrow(immersed_fe.n_components() == 1, ExcNotImplemented());
   AssertThrow(immersed_fe.n_dofs_per_cell() == 1, ExcMessage("nmgpu: the immersed space must be FE_DGQ(0)"));
   AssertThrow(immersed_constraints.n_constraints() == 0, ExcNotImplemented());
+  // the sparsity and the mass-matrix call of one cycle pass the same handlers and constraints: send the tables once
+  if (s.dofs.valid && s.dofs.space_dh == &space_dh && s.dofs.immersed_dh == &immersed_dh && s.dofs.constraints == &constraints &&
+      s.dofs.n_space == space_dh.n_dofs() && s.dofs.n_immersed == immersed_dh.n_dofs() && s.dofs.n_constraints == constraints.n_constraints())
+    return;
+  s.dofs.valid = false;
   set_space_dofs<dim0, spacedim>(s, space_dh, constraints);
   std::vector<std::uint32_t> d1(s.n_immersed);
   std::vector<types::global_dof_index> tmp1(1);
@@ -205,6 +260,13 @@ void set_dofs(Session &s, const DoFHandler<dim0, spacedim> &space_dh, const DoFH
     d1[s.immersed_local_of_active[cell->active_cell_index()]] = static_cast<std::uint32_t>(tmp1[0]);
   }
   check(s, nm_set_immersed_dofs(s.ctx, d1.data(), 1, immersed_dh.n_dofs(), NM_HOST));
+  s.dofs.space_dh = &space_dh;
+  s.dofs.immersed_dh = &immersed_dh;
+  s.dofs.constraints = &constraints;
+  s.dofs.n_space = space_dh.n_dofs();
+  s.dofs.n_immersed = immersed_dh.n_dofs();
+  s.dofs.n_constraints = constraints.n_constraints();
+  s.dofs.valid = true;
 }
 
 // Background geometry only (the Nitsche terms do not look at the immersed grid).
@@ -217,6 +279,10 @@ void set_space_grid(Session &s, const Triangulation<dim0, spacedim> &space, cons
   check(s, nm_set_background_boxes(s.ctx, spacedim, s.n_space, lo.data(), hi.data(), nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr,
                                    NM_HOST));
   s.space_set = true;
+  s.grids_set = false;   // the immersed grid of this context (if any) no longer matches
+  s.space_active_cells = space.n_active_cells();
+  s.own.valid = false;
+  s.dofs.valid = false;
 }
 
 // Flatten the tuples for nm_assemble_nitsche and evaluate the caller's Function objects at the points.
@@ -283,6 +349,24 @@ void assemble_from_info(Session &s,
   check(s, nm_assemble_from_quadrature(s.ctx, info.size(), im.data(), bg.data(), off.data(), pts.data(), w.data(), NM_HOST));
 }
 
+// The matrix of the context, rows with entries only, handed to `visit(row, n, cols, vals)` (vals == nullptr: pattern).
+template <typename Visit> void for_each_stored_row(Session &s, const bool with_values, Visit &&visit)
+{
+  std::uint64_t nnz = 0, n_rows = 0;
+  check(s, nm_build_sparsity(s.ctx, &nnz));
+  check(s, nm_get_csr_compact(s.ctx, &n_rows, nullptr, nullptr, nullptr, nullptr, NM_HOST));
+  std::vector<std::uint32_t> ids(n_rows), len(n_rows), col(nnz);
+  std::vector<double> val(with_values ? nnz : 0);
+  check(s, nm_get_csr_compact(s.ctx, &n_rows, ids.data(), len.data(), col.data(), with_values ? val.data() : nullptr, NM_HOST));
+  std::vector<types::global_dof_index> cols;
+  std::size_t o = 0;
+  for (std::uint64_t r = 0; r < n_rows; ++r) {
+    cols.assign(col.begin() + o, col.begin() + o + len[r]);
+    visit(static_cast<types::global_dof_index>(ids[r]), static_cast<types::global_dof_index>(len[r]), cols, with_values ? val.data() + o : nullptr);
+    o += len[r];
+  }
+}
+
 } // namespace nmgpu_detail
 
 template <int dim0, int dim1, int spacedim>
@@ -322,7 +406,18 @@ collect_quadratures_on_overlapped_grids(const GridTools::Cache<dim0, spacedim> &
     for (std::size_t k = 0; k < nq; ++k)
       for (unsigned int d = 0; d < spacedim; ++d)
         qp[k][d] = pts[(off[p] + k) * spacedim + d];
-    cells_with_quadratures.emplace_back(space_cells[bg[p]], immersed_cells[im[p]], Quadrature<spacedim>(qp, qw));
+    cells_with_quadratures.emplace_back(space_cells[bg[p]], immersed_cells[im[p]], Quadrature<spacedim>(std::move(qp), std::move(qw)));
+  }
+  // remember what was handed out (the element storage does not move when the vector is returned)
+  s.own.valid = true;
+  s.own.size = cells_with_quadratures.size();
+  if (!cells_with_quadratures.empty()) {
+    const auto &qf = std::get<2>(cells_with_quadratures.front());
+    const auto &ql = std::get<2>(cells_with_quadratures.back());
+    s.own.first = qf.get_points().data();
+    s.own.last = ql.get_points().data();
+    s.own.w_first = qf.weight(0);
+    s.own.w_last = ql.weight(ql.size() - 1);
   }
   return cells_with_quadratures;
 }
@@ -342,21 +437,15 @@ void create_coupling_sparsity_pattern_with_exact_intersections(
   AssertThrow(space_comps.size() <= 1 && immersed_comps.size() <= 1, ExcNotImplemented());
 
   auto &s = nmgpu_detail::session(&space_dh.get_triangulation(), &immersed_dh.get_triangulation());
-  AssertThrow(s.grids_set, ExcMessage("nmgpu: collect_quadratures_on_overlapped_grids must be called on these grids first"));
+  AssertThrow((nmgpu_detail::grids_current<dim0, dim1, spacedim>(s, space_dh.get_triangulation(), immersed_dh.get_triangulation())),
+              ExcMessage("nmgpu: collect_quadratures_on_overlapped_grids must be called on these grids first (and again after a mesh change)"));
   nmgpu_detail::set_dofs<dim0, dim1, spacedim>(s, space_dh, immersed_dh, constraints, immersed_constraints);
-  nmgpu_detail::assemble_from_info<dim0, dim1, spacedim>(s, intersections_info);
-
-  std::uint64_t nnz = 0;
-  nmgpu_detail::check(s, nm_build_sparsity(s.ctx, &nnz));
-  std::vector<std::uint64_t> rowptr(space_dh.n_dofs() + 1);
-  std::vector<std::uint32_t> col(nnz);
-  nmgpu_detail::check(s, nm_get_csr(s.ctx, 0, rowptr.data(), col.data(), nullptr, NM_HOST));
-  std::vector<types::global_dof_index> cols;
-  for (types::global_dof_index r = 0; r < space_dh.n_dofs(); ++r)
-    if (rowptr[r + 1] > rowptr[r]) {
-      cols.assign(col.begin() + rowptr[r], col.begin() + rowptr[r + 1]);
-      sparsity.add_entries(r, cols.begin(), cols.end(), /*indices_are_sorted=*/true);
-    }
+  if (!nmgpu_detail::is_own_result(s, intersections_info)) {   // a foreign vector: its quadrature has to travel to the device
+    nmgpu_detail::assemble_from_info<dim0, dim1, spacedim>(s, intersections_info);
+    s.own.valid = false;
+  }
+  nmgpu_detail::for_each_stored_row(s, false, [&](types::global_dof_index r, types::global_dof_index, const std::vector<types::global_dof_index> &cols,
+                                                  const double *) { sparsity.add_entries(r, cols.begin(), cols.end(), /*indices_are_sorted=*/true); });
 }
 
 template <int dim0, int dim1, int spacedim, typename Matrix>
@@ -374,28 +463,24 @@ void create_coupling_mass_matrix_with_exact_intersections(
   AssertThrow(space_comps.size() <= 1 && immersed_comps.size() <= 1, ExcNotImplemented());
 
   auto &s = nmgpu_detail::session(&space_dh.get_triangulation(), &immersed_dh.get_triangulation());
-  if (!s.grids_set)  // the caller built cells_and_quads elsewhere: take the geometry from the mappings given here
+  // the caller built cells_and_quads elsewhere, or the mesh changed since: take the geometry from the mappings given here
+  if (!nmgpu_detail::grids_current<dim0, dim1, spacedim>(s, space_dh.get_triangulation(), immersed_dh.get_triangulation()))
     nmgpu_detail::set_grids<dim0, dim1, spacedim>(s, space_dh.get_triangulation(), space_mapping, immersed_dh.get_triangulation(),
                                                   immersed_mapping, nullptr, nullptr);
   nmgpu_detail::set_dofs<dim0, dim1, spacedim>(s, space_dh, immersed_dh, space_constraints, immersed_constraints);
-  nmgpu_detail::assemble_from_info<dim0, dim1, spacedim>(s, cells_and_quads);
-
-  std::uint64_t nnz = 0;
-  nmgpu_detail::check(s, nm_build_sparsity(s.ctx, &nnz));
-  std::vector<std::uint64_t> rowptr(space_dh.n_dofs() + 1);
-  std::vector<std::uint32_t> col(nnz);
-  std::vector<double> val(nnz);
-  nmgpu_detail::check(s, nm_get_csr(s.ctx, 0, rowptr.data(), col.data(), val.data(), NM_HOST));
-  std::vector<types::global_dof_index> cols;
+  if (nmgpu_detail::is_own_result(s, cells_and_quads))
+    nmgpu_detail::check(s, nm_assemble(s.ctx));                 // the quadrature never left the device
+  else {
+    nmgpu_detail::assemble_from_info<dim0, dim1, spacedim>(s, cells_and_quads);
+    s.own.valid = false;
+  }
   std::vector<typename Matrix::value_type> vals;
-  for (types::global_dof_index r = 0; r < space_dh.n_dofs(); ++r)
-    if (rowptr[r + 1] > rowptr[r]) {
-      cols.assign(col.begin() + rowptr[r], col.begin() + rowptr[r + 1]);
-      vals.assign(val.begin() + rowptr[r], val.begin() + rowptr[r + 1]);
-      // zeros are skipped exactly like distribute_local_to_global does (constrained rows stay structural zeros)
-      matrix.add(r, static_cast<types::global_dof_index>(cols.size()), cols.data(), vals.data(), /*elide_zero_values=*/true,
-                 /*col_indices_are_sorted=*/true);
-    }
+  nmgpu_detail::for_each_stored_row(s, true, [&](types::global_dof_index r, types::global_dof_index n, const std::vector<types::global_dof_index> &cols,
+                                                 const double *v) {
+    vals.assign(v, v + n);
+    // zeros are skipped exactly like distribute_local_to_global does (constrained rows stay structural zeros)
+    matrix.add(r, n, cols.data(), vals.data(), /*elide_zero_values=*/true, /*col_indices_are_sorted=*/true);
+  });
   matrix.compress(VectorOperation::add); // reference :289
 }
 
@@ -420,7 +505,7 @@ void assemble_nitsche_with_exact_intersections(
   AssertThrow(space_comps.size() <= 1, ExcNotImplemented());
 
   auto &s = nmgpu_detail::session(&space_dh.get_triangulation(), &std::get<1>(cells_and_quads.front())->get_triangulation());
-  if (!s.space_set)
+  if (!s.space_set || s.space_active_cells != space_dh.get_triangulation().n_active_cells())   // first use, or the mesh changed
     nmgpu_detail::set_space_grid<dim0, spacedim>(s, space_dh.get_triangulation(), space_mapping);
   nmgpu_detail::set_space_dofs<dim0, spacedim>(s, space_dh, space_constraints);
   nmgpu_detail::nitsche_from_info<dim0, dim1, spacedim, typename Matrix::value_type>(s, cells_and_quads, /*owned_only=*/true,
@@ -459,7 +544,7 @@ void create_nitsche_rhs_with_exact_intersections(
   if (cells_and_quads.empty())
     return;
   auto &s = nmgpu_detail::session(&space_dh.get_triangulation(), &std::get<1>(cells_and_quads.front())->get_triangulation());
-  if (!s.space_set)
+  if (!s.space_set || s.space_active_cells != space_dh.get_triangulation().n_active_cells())   // first use, or the mesh changed
     nmgpu_detail::set_space_grid<dim0, spacedim>(s, space_dh.get_triangulation(), space_mapping);
   nmgpu_detail::set_space_dofs<dim0, spacedim>(s, space_dh, space_constraints);
   // the reference's rhs loop takes every active cell (:428), not only locally owned ones; the arrays sent to the GPU
@@ -480,6 +565,10 @@ void create_nitsche_rhs_with_exact_intersections(
   if (!rows.empty())
     rhs_vector.add(rows, vals);
 }
+
+// Frees every GPU context (and its device memory) this header created.  The contexts are otherwise kept for the life
+// of the process, so that the calls of one refinement cycle find the device-resident results of the previous call.
+inline void nmgpu_release() { nmgpu_detail::sessions().clear(); }
 
 } // namespace NonMatching
 } // namespace dealii

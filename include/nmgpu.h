@@ -42,7 +42,8 @@ typedef enum {
   NM_ERR_NOMEM = 5
 } nm_status;
 
-enum { NM_HOST = 0, NM_DEVICE = 1 };
+enum { NM_HOST = 0, NM_DEVICE = 1,
+       NM_HOST_ASYNC = 2 /* nm_get_csr_compact only: pinned host buffers, copies complete at nm_sync_downloads() */ };
 
 /* Counters of one nm_intersect() call. */
 typedef struct {
@@ -164,11 +165,39 @@ int nm_assemble_from_quadrature(nm_ctx *ctx, uint64_t n_pairs, const uint32_t *i
  * val may be NULL (pattern only). */
 int nm_get_csr(nm_ctx *ctx, int transpose, uint64_t *rowptr, uint32_t *col, double *val, int where);
 
+/* The stored orientation without its empty rows -- what a caller needs to replay the reference's
+ * dsp.add_entries(row, ...) / matrix.add(row, ...) calls (coupling_utilities.h:127-129, :285-287), and
+ * the only form that stays small on a shard of a multi-GPU run, where the global dof count is far
+ * larger than what one rank touches:
+ *   row_ids[n_rows]  global space dof of every row that holds entries, ascending
+ *   row_len[n_rows]  number of entries of that row
+ *   col / val [nnz]  the rows back to back, columns (immersed dofs) ascending within a row.
+ * Any pointer may be NULL; *n_rows is always set, so a first call with NULL arrays sizes the buffers
+ * (nnz comes from nm_build_sparsity).  where = NM_HOST_ASYNC queues the copies on a separate stream
+ * and returns: the (pinned) host buffers are complete after nm_sync_downloads(); the next assembly on
+ * this context may be started in between -- its uploads and kernels overlap the read-back, and it waits
+ * for the copies only where it would overwrite the matrix. */
+int nm_get_csr_compact(nm_ctx *ctx, uint64_t *n_rows, uint32_t *row_ids, uint32_t *row_len, uint32_t *col, double *val, int where);
+int nm_sync_downloads(nm_ctx *ctx);
+
 /* transpose = 0: y[n_space] = A x[n_immersed]      (reference: Ct.vmult,  2d3d/...cc:627)
  * transpose = 1: y[n_immersed] = A^T x[n_space]    (reference: C = transpose_operator(Ct), :628)
  * With a sharded immersed grid y (transpose=0) is this rank's partial sum -- all-reduce it;
  * y (transpose=1) is non-zero only in this rank's immersed DoFs. */
 int nm_spmv(nm_ctx *ctx, int transpose, const double *x, double *y, int where);
+
+/* The same products in LOCAL numbering, for a consumer that is distributed like the reference's
+ * (TrilinosWrappers::MPI::Vector, 2d3d/lagrange_multiplier.cc:627-643) and holds only the entries a
+ * rank works on.  NM_LOCAL_IMMERSED: entry m belongs to immersed cell m of this context's (shard of
+ * the) immersed grid; NM_LOCAL_ROWS: entry r belongs to row_ids[r] of nm_get_csr_compact.
+ *   transpose = 0: y[n_rows]  = A x[n_cells]     transpose = 1: y[n_cells] = A^T x[n_rows]
+ * No global-length vector crosses the host/device boundary and nothing global-length is zeroed. */
+enum { NM_LOCAL_IMMERSED = 0, NM_LOCAL_ROWS = 1 };
+int nm_spmv_local(nm_ctx *ctx, int transpose, const double *x, double *y, int where);
+/* Scatter a local vector into a global-numbered DEVICE vector (entries outside the local set are left
+ * untouched) / gather the local entries out of one.  `where_local` places the local vector. */
+int nm_local_to_global(nm_ctx *ctx, int which, const double *local, int where_local, double *global_dev);
+int nm_global_to_local(nm_ctx *ctx, int which, const double *global_dev, double *local, int where_local);
 
 /* Ct.vmult fused with its reduction across GPUs (stored orientation, device pointers only):
  * every non-empty row result is ADDED into each of the `n_targets` vectors y_targets[i][n_space]
@@ -239,6 +268,21 @@ int nm_assemble_nitsche(nm_ctx *ctx, uint64_t n_pairs, const uint32_t *backgroun
                         int where, uint64_t *nnz);
 /* rowptr[n_space+1], col[nnz], val[nnz], rhs[n_space]; any pointer may be NULL (skipped). */
 int nm_get_nitsche(nm_ctx *ctx, uint64_t *rowptr, uint32_t *col, double *val, double *rhs, int where);
+
+/* Introspection (tests and the benchmark): which code path the last calls took. */
+enum {
+  NM_INFO_MERGE_PATH = 0,   /* matrix built by: 0 = single-pass hash merge, 1 = general two-pass merge        */
+  NM_INFO_COMPACT_ROWS = 1, /* stored orientation keeps only touched rows internally (sharded grids)           */
+  NM_INFO_STORED_ROWS = 2,  /* rows the stored orientation holds internally                                    */
+  NM_INFO_NNZ = 3,
+  NM_INFO_INDEX_KIND = 4,   /* candidate index: 1 = per-cell chains (any boxes), 2 = brick bitmasks (grid-aligned tree) */
+  NM_INFO_HOST_SYNCS = 5    /* host synchronisations with the stream since nm_create                           */
+};
+int nm_get_info(nm_ctx *ctx, int key, uint64_t *value);
+
+/* Measured FP64 throughput of this GPU: a register-resident chain of dependent-free DFMAs on every SM for about
+ * `ms_target` milliseconds; *flops_per_s counts 2 flops per DFMA.  The denominator of the FP64 roofline fraction. */
+int nm_measure_fp64_peak(nm_ctx *ctx, double ms_target, double *flops_per_s);
 
 /* Device milliseconds per phase (NM_T_*), `n` entries copied. */
 int nm_get_timings(nm_ctx *ctx, float *ms, int n);

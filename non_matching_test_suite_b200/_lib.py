@@ -16,7 +16,9 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnmgpu.so")
 
-NM_HOST, NM_DEVICE = 0, 1
+NM_HOST, NM_DEVICE, NM_HOST_ASYNC = 0, 1, 2
+NM_LOCAL_IMMERSED, NM_LOCAL_ROWS = 0, 1
+INFO = {"merge_path": 0, "compact_rows": 1, "stored_rows": 2, "nnz": 3, "index_kind": 4, "host_syncs": 5}
 STATUS = {0: "NM_OK", 1: "NM_ERR_INVALID", 2: "NM_ERR_CUDA", 3: "NM_ERR_UNSUPPORTED", 4: "NM_ERR_STATE", 5: "NM_ERR_NOMEM"}
 PHASES = ["upload", "index", "candidates", "split", "clip", "merge", "transpose", "spmv", "spmv_t", "download",
           "k_clip", "k_cand_count", "k_cand_fill", "k_merge"]
@@ -25,7 +27,8 @@ PHASES = ["upload", "index", "candidates", "split", "clip", "merge", "transpose"
 SYMBOLS = ["nm_version", "nm_create", "nm_destroy", "nm_last_error", "nm_set_background", "nm_set_background_boxes",
            "nm_set_background_dofs", "nm_set_immersed_dofs", "nm_set_immersed", "nm_flag_overlapped_background", "nm_intersect", "nm_get_candidates", "nm_get_pairs", "nm_get_quadrature",
            "nm_get_split_codes", "nm_build_sparsity", "nm_assemble", "nm_assemble_from_quadrature", "nm_assemble_host", "nm_assemble_nitsche", "nm_get_nitsche", "nm_get_csr",
-           "nm_spmv", "nm_spmv_push", "nm_spmv_push_owned", "nm_get_timings", "nm_get_launch_count", "nm_device_bytes", "nm_get_stream"]
+           "nm_get_csr_compact", "nm_sync_downloads", "nm_spmv", "nm_spmv_local", "nm_local_to_global", "nm_global_to_local",
+           "nm_spmv_push", "nm_spmv_push_owned", "nm_get_info", "nm_measure_fp64_peak", "nm_get_timings", "nm_get_launch_count", "nm_device_bytes", "nm_get_stream"]
 
 
 class NmError(RuntimeError):
@@ -85,6 +88,13 @@ def load():
     L.nm_get_nitsche.argtypes = [P, P, P, P, P, I]
     L.nm_get_csr.argtypes = [P, I, P, P, P, I]
     L.nm_spmv.argtypes = [P, I, P, P, I]
+    L.nm_get_csr_compact.argtypes = [P, C.POINTER(U64), P, P, P, P, I]
+    L.nm_sync_downloads.argtypes = [P]
+    L.nm_spmv_local.argtypes = [P, I, P, P, I]
+    L.nm_local_to_global.argtypes = [P, I, P, I, P]
+    L.nm_global_to_local.argtypes = [P, I, P, P, I]
+    L.nm_get_info.argtypes = [P, I, C.POINTER(U64)]
+    L.nm_measure_fp64_peak.argtypes = [P, C.c_double, C.POINTER(C.c_double)]
     L.nm_spmv_push.argtypes = [P, P, I, C.POINTER(C.c_void_p), I]
     L.nm_spmv_push_owned.argtypes = [P, P, I, C.POINTER(C.c_void_p), U64]
     L.nm_get_timings.argtypes = [P, P, I]
@@ -294,6 +304,70 @@ class Context:
         self._chk(self.L.nm_get_csr(self.h, int(transpose), _ptr(rp)[0], _ptr(col)[0], _ptr(val)[0], _where(rp)))
         return rp, col, val
 
+    def csr_compact(self, values: bool = True, device="cpu", out=None, asynchronous: bool = False):
+        """The stored orientation without its empty rows: (row_ids, row_len, col, val) -- nm_get_csr_compact.
+        `out=(row_ids, row_len, col, val)` reuses caller buffers (pinned host memory for `asynchronous=True`, in which
+        case the arrays are complete only after `sync_downloads()`)."""
+        nnz = self.build_sparsity()
+        n = C.c_uint64(0)
+        self._chk(self.L.nm_get_csr_compact(self.h, C.byref(n), None, None, None, None, NM_HOST))
+        nr = int(n.value)
+        if out is not None:
+            ids, ln, col, val = out[0][:nr], out[1][:nr], out[2][:nnz], (out[3][:nnz] if values and out[3] is not None else None)
+        else:
+            ids, ln = self._out(nr, torch.int32, device), self._out(nr, torch.int32, device)
+            col = self._out(nnz, torch.int32, device)
+            val = self._out(nnz, torch.float64, device) if values else None
+        w = _where(ids, ln, col, val)
+        if asynchronous:
+            if w != NM_HOST or not all(t.is_pinned() for t in (ids, ln, col) + ((val,) if val is not None else ())):
+                raise ValueError("an asynchronous read-back needs pinned host buffers")
+            w = NM_HOST_ASYNC
+        self._chk(self.L.nm_get_csr_compact(self.h, C.byref(n), _ptr(ids)[0], _ptr(ln)[0], _ptr(col)[0], _ptr(val)[0], w))
+        return ids, ln, col, val
+
+    def sync_downloads(self):
+        self._chk(self.L.nm_sync_downloads(self.h))
+
+    def n_rows_local(self) -> int:
+        """Number of non-empty rows of the stored orientation (length of the NM_LOCAL_ROWS numbering)."""
+        n = C.c_uint64(0)
+        self._chk(self.L.nm_get_csr_compact(self.h, C.byref(n), None, None, None, None, NM_HOST))
+        return int(n.value)
+
+    def spmv_local(self, x, transpose: bool = False, out=None):
+        """Products in local numbering (nm_spmv_local): transpose=False: y[rows] = A x[cells]; True: y[cells] = A^T x[rows]."""
+        ny = self.n_im if transpose else self.n_rows_local()
+        if out is None:
+            out = torch.empty(ny, dtype=torch.float64, device=x.device)
+        self._chk(self.L.nm_spmv_local(self.h, int(transpose), _ptr(x)[0], _ptr(out)[0], _where(x, out)))
+        return out
+
+    def local_to_global(self, which: int, local, global_dev: torch.Tensor):
+        assert global_dev.is_cuda
+        w = _where(local)
+        torch.cuda.current_stream().synchronize()
+        self._chk(self.L.nm_local_to_global(self.h, which, _ptr(local)[0], w, C.c_void_p(global_dev.data_ptr())))
+        return global_dev
+
+    def global_to_local(self, which: int, global_dev: torch.Tensor, local):
+        assert global_dev.is_cuda
+        w = _where(local)
+        torch.cuda.current_stream().synchronize()
+        self._chk(self.L.nm_global_to_local(self.h, which, C.c_void_p(global_dev.data_ptr()), _ptr(local)[0], w))
+        return local
+
+    def info(self, key: str) -> int:
+        v = C.c_uint64(0)
+        self._chk(self.L.nm_get_info(self.h, INFO[key], C.byref(v)))
+        r = int(v.value)
+        return r - (1 << 64) if r >= (1 << 63) else r
+
+    def measure_fp64_peak(self, ms_target: float = 20.0) -> float:
+        v = C.c_double(0)
+        self._chk(self.L.nm_measure_fp64_peak(self.h, float(ms_target), C.byref(v)))
+        return float(v.value)
+
     def spmv(self, x, transpose: bool = False, out=None):
         """transpose=False: y[n_space] = A x[n_im]  (Ct.vmult);  True: y[n_im] = A^T x[n_space]  (C.Tvmult)."""
         ny = self.n_im_dofs if transpose else self.n_space_dofs
@@ -302,19 +376,21 @@ class Context:
         self._chk(self.L.nm_spmv(self.h, int(transpose), _ptr(x)[0], _ptr(out)[0], _where(x, out)))
         return out
 
-    def spmv_push(self, x: torch.Tensor, target_ptrs, multicast: bool = False):
+    def spmv_push(self, x: torch.Tensor, target_ptrs, multicast: bool = False, sync_producer: bool = True):
         """Ct.vmult fused with its cross-GPU reduction: add every non-empty row result into each of the
         device pointers `target_ptrs` (own + peer-mapped result vectors, or one multicast pointer)."""
         assert x.is_cuda
-        torch.cuda.current_stream().synchronize()
+        if sync_producer:
+            torch.cuda.current_stream().synchronize()
         arr = (C.c_void_p * len(target_ptrs))(*[C.c_void_p(int(p)) for p in target_ptrs])
         self._chk(self.L.nm_spmv_push(self.h, C.c_void_p(x.data_ptr()), len(target_ptrs), arr, int(multicast)))
 
-    def spmv_push_owned(self, x: torch.Tensor, rank_ptrs, rows_per_rank: int):
+    def spmv_push_owned(self, x: torch.Tensor, rank_ptrs, rows_per_rank: int, sync_producer: bool = True):
         """Ct.vmult with reduce-scatter semantics: every non-empty row result is added into the vector of the rank
         that owns the dof (contiguous ranges of `rows_per_rank` dofs); `rank_ptrs[k]` = rank k's result vector."""
         assert x.is_cuda
-        torch.cuda.current_stream().synchronize()
+        if sync_producer:
+            torch.cuda.current_stream().synchronize()
         arr = (C.c_void_p * len(rank_ptrs))(*[C.c_void_p(int(p)) for p in rank_ptrs])
         self._chk(self.L.nm_spmv_push_owned(self.h, C.c_void_p(x.data_ptr()), len(rank_ptrs), arr, int(rows_per_rank)))
 

@@ -70,7 +70,8 @@ static std::vector<DevBuf *> all_buffers(nm_ctx *c)
           &c->cand_sumw, &c->cand_local, &c->cand_nq, &c->cand_acc, &c->counters, &c->c_rowstart, &c->c_rowlen, &c->c_col, &c->c_val,
           &c->a_rowptr, &c->a_rowptr32, &c->a_col, &c->a_val, &c->a_cursor, &c->scan_tmp, &c->scratch_a, &c->scratch_b, &c->stage_x,
           &c->stage_y, &c->h2d_stage, &c->nit_cnt, &c->nit_keys, &c->nit_vals, &c->nit_rkeys, &c->nit_rvals, &c->nit_rowptr,
-          &c->nit_col, &c->nit_val, &c->nit_rhs, &c->row_bits, &c->row_prefix, &c->row_ids};
+          &c->nit_col, &c->nit_val, &c->nit_rhs, &c->row_bits, &c->row_prefix, &c->row_ids, &c->out_ids, &c->out_len, &c->glob_im,
+          &c->glob_dof, &c->brk_hdr, &c->brk_bit};
 }
 
 static void free_all(nm_ctx *c)
@@ -90,6 +91,24 @@ static uint64_t held_bytes(nm_ctx *c)
 }
 
 namespace {
+// FP64 peak: eight independent DFMA chains per thread, registers only
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *__restrict__ out, int iters, double a, double b)
+{
+  double x[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) x[k] = (double)(threadIdx.x + k) * 1e-3;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x[k] = fma(x[k], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += x[k];
+  if (s == 12345.678) out[blockIdx.x] = s;   // never true for the arguments used: keeps the chains alive
+}
+
 __global__ void scatter_flags(uint64_t n, const uint32_t *__restrict__ bg, uint8_t *__restrict__ flags)
 {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -122,10 +141,12 @@ int nm_create(nm_ctx **out, int device)
   }
   { const char *e = getenv("NMGPU_FORCE_QUADRATURE"); ctx->force_quadrature_kernel = e && e[0] == '1'; }
   { const char *e = getenv("NMGPU_FORCE_GENERAL_MERGE"); ctx->force_general_merge = e && e[0] == '1'; }
+  { const char *e = getenv("NMGPU_INDEX"); ctx->force_chain_index = e && e[0] == 'c'; }
   { const char *e = getenv("NMGPU_COMPACT_ROWS"); ctx->compact_rows_env = e ? (e[0] == '1' ? 1 : 0) : -1; }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   if (nm_ensure(ctx, ctx->counters, 64 * sizeof(uint64_t)) != NM_OK) { delete ctx; return NM_ERR_NOMEM; }
+  cudaMemset(ctx->counters.p, 0, 64 * sizeof(uint64_t));   // cudaMalloc does not clear: no counter or flag may start from stale bits
   *out = ctx;
   return NM_OK;
 }
@@ -142,6 +163,9 @@ int nm_destroy(nm_ctx *ctx)
   if (ctx->ev3) cudaEventDestroy(ctx->ev3);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->down_stream) { cudaStreamSynchronize(ctx->down_stream); cudaStreamDestroy(ctx->down_stream); }
+  if (ctx->ev_down_ready) cudaEventDestroy(ctx->ev_down_ready);
+  if (ctx->ev_down_done) cudaEventDestroy(ctx->ev_down_done);
   for (cudaEvent_t e : ctx->ev_copy)
     if (e) cudaEventDestroy(e);
   delete ctx;
@@ -161,6 +185,7 @@ static int set_background_common(nm_ctx *ctx, int spacedim, uint64_t n_cells, bo
   if (n_cells >= 0xffffffffULL || n_dofs >= 0xffffffffULL) return nm_fail(ctx, NM_ERR_UNSUPPORTED, "cell / DoF counts must fit 32 bits");
   if (n_constrained && (!c_dof || !c_ptr)) return nm_fail(ctx, NM_ERR_INVALID, "null constraint arrays");
   ctx->bg_set = ctx->index_valid = ctx->intersect_valid = ctx->matrix_valid = false;
+  ctx->dofs_checked = false;
   const int NV = 1 << spacedim;
   PhaseTimer tm(ctx, NM_T_UPLOAD);
   ctx->spacedim = spacedim;
@@ -192,7 +217,7 @@ static int set_background_common(nm_ctx *ctx, int spacedim, uint64_t n_cells, bo
   uint64_t n_masters = 0;
   if (n_constrained) {
     if (where == NM_HOST) n_masters = c_ptr[n_constrained];
-    else { NM_CUDA(cudaMemcpyAsync(&n_masters, c_ptr + n_constrained, 8, cudaMemcpyDeviceToHost, ctx->stream)); NM_CUDA(cudaStreamSynchronize(ctx->stream)); }
+    else { NM_CUDA(cudaMemcpyAsync(&n_masters, c_ptr + n_constrained, 8, cudaMemcpyDeviceToHost, ctx->stream)); NM_SYNC(ctx); }
     if (n_masters && (!c_master || !c_weight)) return nm_fail(ctx, NM_ERR_INVALID, "null constraint master arrays");
   }
   ctx->n_cmasters = n_masters;
@@ -216,7 +241,7 @@ static int set_constraints(nm_ctx *ctx, uint64_t n_dofs, uint64_t n_constrained,
   uint64_t n_masters = 0;
   if (n_constrained) {
     if (where == NM_HOST) n_masters = c_ptr[n_constrained];
-    else { NM_CUDA(cudaMemcpyAsync(&n_masters, c_ptr + n_constrained, 8, cudaMemcpyDeviceToHost, ctx->stream)); NM_CUDA(cudaStreamSynchronize(ctx->stream)); }
+    else { NM_CUDA(cudaMemcpyAsync(&n_masters, c_ptr + n_constrained, 8, cudaMemcpyDeviceToHost, ctx->stream)); NM_SYNC(ctx); }
     if (n_masters && (!c_master || !c_weight)) return nm_fail(ctx, NM_ERR_INVALID, "null constraint master arrays");
   }
   ctx->n_cmasters = n_masters;
@@ -237,6 +262,7 @@ int nm_set_background_dofs(nm_ctx *ctx, const uint32_t *dofs, uint64_t n_dofs, u
   if (ctx->n_bg && !dofs) return nm_fail(ctx, NM_ERR_INVALID, "null DoF array");
   if (n_dofs >= 0xffffffffULL) return nm_fail(ctx, NM_ERR_UNSUPPORTED, "DoF counts must fit 32 bits");
   ctx->matrix_valid = false;  // intersection results stay valid: they do not depend on the numbering
+  ctx->dofs_checked = false;
   PhaseTimer tm(ctx, NM_T_UPLOAD, true);
   NM_TRY(nm_upload(ctx, ctx->bg_dofs, dofs, ctx->n_bg * (1u << ctx->spacedim) * sizeof(uint32_t), where));
   NM_TRY(set_constraints(ctx, n_dofs, n_constrained, c_dof, c_ptr, c_master, c_weight, where));
@@ -255,6 +281,7 @@ int nm_set_immersed_dofs(nm_ctx *ctx, const uint32_t *dofs, uint32_t dofs_per_ce
   if (ctx->n_im && !dofs) return nm_fail(ctx, NM_ERR_INVALID, "null DoF array");
   if (n_dofs >= 0xffffffffULL) return nm_fail(ctx, NM_ERR_UNSUPPORTED, "DoF counts must fit 32 bits");
   ctx->matrix_valid = false;
+  ctx->dofs_checked = false;
   ctx->n_im_dofs = n_dofs;
   NM_TRY(nm_upload(ctx, ctx->im_dofs, dofs, ctx->n_im * sizeof(uint32_t), where));
   ctx->im_dofs_set = true;
@@ -292,6 +319,7 @@ int nm_set_immersed(nm_ctx *ctx, int dim, int spacedim, uint64_t n_cells, const 
   if (n_cells >= 0xffffffffULL || n_dofs >= 0xffffffffULL) return nm_fail(ctx, NM_ERR_UNSUPPORTED, "cell / DoF counts must fit 32 bits");
   if (n_cells && !verts) return nm_fail(ctx, NM_ERR_INVALID, "null immersed arrays");
   ctx->im_set = ctx->intersect_valid = ctx->matrix_valid = false;
+  ctx->dofs_checked = false;
   PhaseTimer tm(ctx, NM_T_UPLOAD, /*accumulate=*/ctx->bg_set);
   ctx->dim1 = dim;
   ctx->n_im = n_cells;
@@ -360,7 +388,7 @@ int nm_get_candidates(nm_ctx *ctx, uint32_t *immersed, uint32_t *background, int
   const uint64_t n = ctx->counts.n_candidates;
   NM_TRY(nm_download(ctx, immersed, ctx->cand_im.p, n * 4, where));
   NM_TRY(nm_download(ctx, background, ctx->cand_bg.p, n * 4, where));
-  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  NM_SYNC(ctx);
   tm.stop();
   return NM_OK;
 }
@@ -398,7 +426,7 @@ int nm_flag_overlapped_background(nm_ctx *ctx, uint8_t *flags, int where)
   if (nc) scatter_flags<<<nm_blocks(nc, 256), 256, 0, NM_LS(ctx)>>>(nc, ctx->cand_bg.as<uint32_t>(), f_dev);
   NM_CUDA(cudaGetLastError());
   if (where == NM_HOST) NM_TRY(nm_download(ctx, flags, f_dev, ctx->n_bg, NM_HOST));
-  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  NM_SYNC(ctx);
   return NM_OK;
 }
 
@@ -416,12 +444,12 @@ int nm_get_pairs(nm_ctx *ctx, uint32_t *immersed, uint32_t *background, double *
   if (na && immersed) {
     uint32_t *dst = where == NM_DEVICE ? immersed : ctx->stage_y.as<uint32_t>();
     gather_by_idx<uint32_t><<<B, 256, 0, NM_LS(ctx)>>>(na, idx, ctx->cand_im.as<uint32_t>(), dst);
-    if (where == NM_HOST) { NM_TRY(nm_download(ctx, immersed, dst, na * 4, NM_HOST)); NM_CUDA(cudaStreamSynchronize(ctx->stream)); }
+    if (where == NM_HOST) { NM_TRY(nm_download(ctx, immersed, dst, na * 4, NM_HOST)); NM_SYNC(ctx); }
   }
   if (na && background) {
     uint32_t *dst = where == NM_DEVICE ? background : ctx->stage_y.as<uint32_t>();
     gather_by_idx<uint32_t><<<B, 256, 0, NM_LS(ctx)>>>(na, idx, ctx->cand_bg.as<uint32_t>(), dst);
-    if (where == NM_HOST) { NM_TRY(nm_download(ctx, background, dst, na * 4, NM_HOST)); NM_CUDA(cudaStreamSynchronize(ctx->stream)); }
+    if (where == NM_HOST) { NM_TRY(nm_download(ctx, background, dst, na * 4, NM_HOST)); NM_SYNC(ctx); }
   }
   if (na && sum_w) {
     double *dst = where == NM_DEVICE ? sum_w : ctx->stage_y.as<double>();
@@ -429,7 +457,7 @@ int nm_get_pairs(nm_ctx *ctx, uint32_t *immersed, uint32_t *background, double *
     if (where == NM_HOST) { NM_TRY(nm_download(ctx, sum_w, dst, na * 8, NM_HOST)); }
   }
   NM_CUDA(cudaGetLastError());
-  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  NM_SYNC(ctx);
   tm.stop();
   return NM_OK;
 }
@@ -452,7 +480,7 @@ int nm_get_split_codes(nm_ctx *ctx, uint8_t *codes, int where)
   if (!ctx->intersect_valid) return nm_fail(ctx, NM_ERR_STATE, "nm_intersect has not been run");
   if (ctx->spacedim != 3) return nm_fail(ctx, NM_ERR_INVALID, "split codes exist for immersed quads (spacedim 3) only");
   NM_TRY(nm_download(ctx, codes, ctx->im_split.p, ctx->n_im, where));
-  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  NM_SYNC(ctx);
   return NM_OK;
 }
 
@@ -543,7 +571,7 @@ int nm_get_nitsche(nm_ctx *ctx, uint64_t *rowptr, uint32_t *col, double *val, do
   NM_TRY(nm_download(ctx, col, ctx->nit_col.p, ctx->nit_nnz * 4, where));
   NM_TRY(nm_download(ctx, val, ctx->nit_val.p, ctx->nit_nnz * 8, where));
   NM_TRY(nm_download(ctx, rhs, ctx->nit_rhs.p, ctx->n_space_dofs * 8, where));
-  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  NM_SYNC(ctx);
   return NM_OK;
 }
 
@@ -570,6 +598,7 @@ int nm_assemble_host(nm_ctx *ctx, const nm_host_problem *P, nm_counts *counts, u
   }
   ctx->bg_set = ctx->bg_dofs_set = ctx->im_set = ctx->im_dofs_set = false;
   ctx->index_valid = ctx->intersect_valid = ctx->matrix_valid = false;
+  ctx->dofs_checked = false;
   ctx->local_from_user = false;
   ctx->spacedim = d; ctx->n_bg = P->n_bg; ctx->n_space_dofs = P->n_space_dofs;
   ctx->n_constrained = P->n_constrained; ctx->n_cmasters = n_masters;
@@ -587,7 +616,7 @@ int nm_assemble_host(nm_ctx *ctx, const nm_host_problem *P, nm_counts *counts, u
   NM_TRY(nm_ensure(ctx, ctx->c_ptr, (P->n_constrained + 2) * sizeof(uint64_t)));
   NM_TRY(nm_ensure(ctx, ctx->c_master, n_masters * sizeof(uint32_t)));
   NM_TRY(nm_ensure(ctx, ctx->c_weight, n_masters * sizeof(double)));
-  NM_CUDA(cudaStreamSynchronize(ctx->stream));   // earlier work of this context may still read those buffers
+  NM_SYNC(ctx);   // earlier work of this context may still read those buffers
   cudaStream_t cs = ctx->copy_stream;
   auto h2d = [&](void *dst, const void *src, size_t bytes) -> cudaError_t {
     return bytes ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, cs) : cudaSuccess;
@@ -675,7 +704,7 @@ int nm_get_csr(nm_ctx *ctx, int transpose, uint64_t *rowptr, uint32_t *col, doub
       NM_TRY(nm_download(ctx, val, vl, ctx->nnz * 8, NM_HOST));
     }
   }
-  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  NM_SYNC(ctx);
   tm.stop();
   return NM_OK;
 }
@@ -697,7 +726,7 @@ int nm_spmv(nm_ctx *ctx, int transpose, const double *x, double *y, int where)
   }
   NM_TRY(nm_spmv_run(ctx, transpose, xd, yd));
   if (where == NM_HOST) NM_TRY(nm_download(ctx, y, yd, ny * 8, NM_HOST));
-  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  NM_SYNC(ctx);
   return NM_OK;
 }
 
@@ -711,7 +740,7 @@ int nm_spmv_push(nm_ctx *ctx, const double *x, int n_targets, double *const *tar
     if (!targets[i]) return nm_fail(ctx, NM_ERR_INVALID, "null target vector");
   NM_TRY(ensure_matrix(ctx));
   NM_TRY(nm_spmv_push_run(ctx, x, n_targets, targets, multicast));
-  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  NM_SYNC(ctx);
   return NM_OK;
 }
 
@@ -725,7 +754,182 @@ int nm_spmv_push_owned(nm_ctx *ctx, const double *x, int n_ranks, double *const 
     if (!y_targets[i]) return nm_fail(ctx, NM_ERR_INVALID, "null target vector");
   NM_TRY(ensure_matrix(ctx));
   NM_TRY(nm_spmv_push_owned_run(ctx, x, n_ranks, y_targets, rows_per_rank));
-  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  NM_SYNC(ctx);
+  return NM_OK;
+}
+
+int nm_get_info(nm_ctx *ctx, int key, uint64_t *value)
+{
+  if (!ctx || !value) return NM_ERR_INVALID;
+  switch (key) {
+    case NM_INFO_MERGE_PATH: *value = (uint64_t)(int64_t)ctx->merge_path; return NM_OK;
+    case NM_INFO_COMPACT_ROWS: *value = ctx->compact_rows ? 1 : 0; return NM_OK;
+    case NM_INFO_STORED_ROWS: *value = ctx->matrix_valid ? ctx->n_local_rows : 0; return NM_OK;
+    case NM_INFO_NNZ: *value = ctx->matrix_valid ? ctx->nnz : 0; return NM_OK;
+    case NM_INFO_INDEX_KIND: *value = (uint64_t)ctx->index_kind; return NM_OK;
+    case NM_INFO_HOST_SYNCS: *value = ctx->n_syncs; return NM_OK;
+    default: return nm_fail(ctx, NM_ERR_INVALID, "unknown info key %d", key);
+  }
+}
+
+static int ensure_down_stream(nm_ctx *ctx)
+{
+  if (ctx->down_stream) return NM_OK;
+  NM_CUDA(cudaStreamCreateWithFlags(&ctx->down_stream, cudaStreamNonBlocking));
+  NM_CUDA(cudaEventCreateWithFlags(&ctx->ev_down_ready, cudaEventDisableTiming));
+  NM_CUDA(cudaEventCreateWithFlags(&ctx->ev_down_done, cudaEventDisableTiming));
+  return NM_OK;
+}
+
+int nm_get_csr_compact(nm_ctx *ctx, uint64_t *n_rows, uint32_t *row_ids, uint32_t *row_len, uint32_t *col, double *val, int where)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  if (where != NM_HOST && where != NM_DEVICE && where != NM_HOST_ASYNC) return nm_fail(ctx, NM_ERR_INVALID, "where must be NM_HOST, NM_DEVICE or NM_HOST_ASYNC");
+  NM_TRY(ensure_matrix(ctx));
+  PhaseTimer tm(ctx, NM_T_DOWNLOAD);
+  uint64_t nr = 0;
+  const uint32_t *ids = nullptr, *len = nullptr;
+  NM_TRY(nm_nonempty_rows(ctx, &nr, &ids, &len));
+  if (n_rows) *n_rows = nr;
+  if (where == NM_HOST_ASYNC) {
+    // the copies run on their own stream behind everything queued so far; the next matrix build waits for them
+    NM_TRY(ensure_down_stream(ctx));
+    NM_CUDA(cudaEventRecord(ctx->ev_down_ready, ctx->stream));
+    NM_CUDA(cudaStreamWaitEvent(ctx->down_stream, ctx->ev_down_ready, 0));
+    cudaStream_t ds = ctx->down_stream;
+    if (row_ids && nr) NM_CUDA(cudaMemcpyAsync(row_ids, ids, nr * 4, cudaMemcpyDeviceToHost, ds));
+    if (row_len && nr) NM_CUDA(cudaMemcpyAsync(row_len, len, nr * 4, cudaMemcpyDeviceToHost, ds));
+    if (col && ctx->nnz) NM_CUDA(cudaMemcpyAsync(col, ctx->a_col.p, ctx->nnz * 4, cudaMemcpyDeviceToHost, ds));
+    if (val && ctx->nnz) NM_CUDA(cudaMemcpyAsync(val, ctx->a_val.p, ctx->nnz * 8, cudaMemcpyDeviceToHost, ds));
+    NM_CUDA(cudaEventRecord(ctx->ev_down_done, ds));
+    ctx->download_pending = true;
+    tm.stop();
+    return NM_OK;
+  }
+  NM_TRY(nm_download(ctx, row_ids, ids, nr * 4, where));
+  NM_TRY(nm_download(ctx, row_len, len, nr * 4, where));
+  NM_TRY(nm_download(ctx, col, ctx->a_col.p, ctx->nnz * 4, where));
+  NM_TRY(nm_download(ctx, val, ctx->a_val.p, ctx->nnz * 8, where));
+  NM_SYNC(ctx);
+  tm.stop();
+  return NM_OK;
+}
+
+int nm_sync_downloads(nm_ctx *ctx)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->down_stream) NM_CUDA(cudaStreamSynchronize(ctx->down_stream));
+  ctx->download_pending = false;
+  return NM_OK;
+}
+
+static int local_count(nm_ctx *ctx, int which, uint64_t *n)
+{
+  if (which == NM_LOCAL_IMMERSED) { *n = ctx->n_im; return NM_OK; }
+  if (which == NM_LOCAL_ROWS) return nm_nonempty_rows(ctx, n, nullptr, nullptr);
+  return nm_fail(ctx, NM_ERR_INVALID, "which must be NM_LOCAL_IMMERSED or NM_LOCAL_ROWS");
+}
+
+int nm_local_to_global(nm_ctx *ctx, int which, const double *local, int where_local, double *global_dev)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  if (!local || !global_dev) return nm_fail(ctx, NM_ERR_INVALID, "null vector");
+  NM_TRY(ensure_matrix(ctx));
+  uint64_t n = 0;
+  NM_TRY(local_count(ctx, which, &n));
+  const double *src = local;
+  if (where_local == NM_HOST) { NM_TRY(nm_upload(ctx, ctx->stage_x, local, n * 8, NM_HOST)); src = ctx->stage_x.as<double>(); }
+  NM_TRY(nm_local_map(ctx, which, 1, src, global_dev));
+  NM_SYNC(ctx);
+  return NM_OK;
+}
+
+int nm_global_to_local(nm_ctx *ctx, int which, const double *global_dev, double *local, int where_local)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  if (!local || !global_dev) return nm_fail(ctx, NM_ERR_INVALID, "null vector");
+  NM_TRY(ensure_matrix(ctx));
+  uint64_t n = 0;
+  NM_TRY(local_count(ctx, which, &n));
+  double *dst = local;
+  if (where_local == NM_HOST) { NM_TRY(nm_ensure(ctx, ctx->stage_y, (n + 1) * 8)); dst = ctx->stage_y.as<double>(); }
+  NM_TRY(nm_local_map(ctx, which, 0, global_dev, dst));
+  if (where_local == NM_HOST) NM_TRY(nm_download(ctx, local, dst, n * 8, NM_HOST));
+  NM_SYNC(ctx);
+  return NM_OK;
+}
+
+int nm_spmv_local(nm_ctx *ctx, int transpose, const double *x, double *y, int where)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  if (!x || !y) return nm_fail(ctx, NM_ERR_INVALID, "null vector");
+  NM_TRY(ensure_matrix(ctx));
+  uint64_t n_rows = 0;
+  NM_TRY(nm_nonempty_rows(ctx, &n_rows, nullptr, nullptr));
+  const uint64_t nx = transpose ? n_rows : ctx->n_im, ny = transpose ? ctx->n_im : n_rows;
+  // global-numbered scratch vectors live on the device only: entries this shard never addresses are never read
+  NM_TRY(nm_ensure(ctx, ctx->glob_im, (ctx->n_im_dofs + 1) * 8));
+  NM_TRY(nm_ensure(ctx, ctx->glob_dof, (ctx->n_space_dofs + 1) * 8));
+  const double *xd = x;
+  double *yd = y;
+  if (where == NM_HOST) {
+    NM_TRY(nm_upload(ctx, ctx->stage_x, x, nx * 8, NM_HOST));
+    NM_TRY(nm_ensure(ctx, ctx->stage_y, (ny + 1) * 8));
+    xd = ctx->stage_x.as<double>();
+    yd = ctx->stage_y.as<double>();
+  }
+  double *xg = transpose ? ctx->glob_dof.as<double>() : ctx->glob_im.as<double>();
+  NM_TRY(nm_local_map(ctx, transpose ? NM_LOCAL_ROWS : NM_LOCAL_IMMERSED, 1, xd, xg));
+  if (transpose || ctx->compact_rows) {
+    // the kernel writes the local numbering directly: row r of the compact stored matrix / immersed cell m
+    NM_TRY(nm_spmv_run(ctx, transpose, xg, yd, NM_SPMV_LOCAL_OUT));
+  } else {
+    // full-row mode: one result per dof, the non-empty rows are picked out afterwards
+    double *yg = ctx->glob_dof.as<double>();
+    NM_TRY(nm_spmv_run(ctx, 0, xg, yg));
+    NM_TRY(nm_local_map(ctx, NM_LOCAL_ROWS, 0, yg, yd));
+  }
+  if (where == NM_HOST) NM_TRY(nm_download(ctx, y, yd, ny * 8, NM_HOST));
+  NM_SYNC(ctx);
+  return NM_OK;
+}
+
+int nm_measure_fp64_peak(nm_ctx *ctx, double ms_target, double *flops_per_s)
+{
+  if (!ctx || !flops_per_s) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  NM_TRY(nm_ensure(ctx, ctx->scratch_a, 1 << 20));
+  const unsigned blocks = (unsigned)ctx->sm_count * 8u, threads = 256;
+  auto run = [&](int iters, float *ms) -> int {
+    NM_CUDA(cudaEventRecord(ctx->ev2, ctx->stream));
+    dfma_peak_kernel<<<blocks, threads, 0, NM_LS(ctx)>>>(ctx->scratch_a.as<double>(), iters, 0.999999, 1e-9);
+    NM_CUDA(cudaGetLastError());
+    NM_CUDA(cudaEventRecord(ctx->ev3, ctx->stream));
+    NM_CUDA(cudaEventSynchronize(ctx->ev3));
+    NM_CUDA(cudaEventElapsedTime(ms, ctx->ev2, ctx->ev3));
+    return NM_OK;
+  };
+  float ms = 0;
+  int iters = 2000;
+  NM_TRY(run(iters, &ms));   // warm-up + calibration
+  NM_TRY(run(iters, &ms));
+  if (ms_target > 0 && ms > 0) {
+    double scale = ms_target / ms;
+    if (scale > 200) scale = 200;
+    if (scale > 1) iters = (int)(iters * scale);
+  }
+  double best = 0;
+  for (int rep = 0; rep < 3; ++rep) {
+    NM_TRY(run(iters, &ms));
+    const double flops = 2.0 * 32.0 * (double)iters * (double)blocks * (double)threads;
+    if (ms > 0 && flops / (ms * 1e-3) > best) best = flops / (ms * 1e-3);
+  }
+  *flops_per_s = best;
   return NM_OK;
 }
 

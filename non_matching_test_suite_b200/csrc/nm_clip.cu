@@ -822,14 +822,17 @@ __global__ void gather_nq_kernel(uint64_t n_acc, const uint64_t *__restrict__ ac
 }
 
 // local coupling vector from caller-supplied quadrature (coupling_utilities.h:238-274):
-// xi_q = F^-1(x_q) on the axis-aligned cell, local(i) += phi_i(xi_q) w_q.
+// xi_q = F^-1(x_q) on the axis-aligned cell, local(i) += phi_i(xi_q) w_q.  A pair that appears in several tuples adds
+// up, as the reference's per-tuple distribute_local_to_global does (:285-287); `claim` (one bit per candidate) tells
+// the first tuple of a pair from the later ones, so that the pair is counted once.
 template <int D>
 __global__ void local_from_quadrature_kernel(uint64_t n_pairs, const uint32_t *__restrict__ im, const uint32_t *__restrict__ bg,
                                              const uint64_t *__restrict__ q_off, const double *__restrict__ pts,
                                              const double *__restrict__ wts, const uint64_t *__restrict__ cand_ptr,
                                              const uint32_t *__restrict__ cand_bg, const double *__restrict__ bg_box, uint64_t n_im,
                                              double *__restrict__ sumw_out, double *__restrict__ local_out,
-                                             uint8_t *__restrict__ acc_out, unsigned long long *n_missing)
+                                             uint8_t *__restrict__ acc_out, uint32_t *__restrict__ claim, unsigned long long *n_missing,
+                                             unsigned long long *n_distinct)
 {
   constexpr int NL = 1 << D;
   const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -853,10 +856,12 @@ __global__ void local_from_quadrature_kernel(uint64_t n_pairs, const uint32_t *_
     if (D == 3) q1_add_3d(o, (x[0] - box[0]) * ih[0], (x[1] - box[1]) * ih[1], (x[2] - box[2]) * ih[2], wts[q]);
     else q1_add_2d(o, (x[0] - box[0]) * ih[0], (x[1] - box[1]) * ih[1], wts[q]);
   }
-  sumw_out[lo] = o.sumw;
-  acc_out[lo] = 1;
+  const unsigned bit = 1u << (lo & 31);
+  if (!(atomicOr(&claim[lo >> 5], bit) & bit)) { acc_out[lo] = 1; atomicAdd(n_distinct, 1ULL); }
+  // the buffers were cleared: a pair given once receives exactly its own sums
+  atomicAdd(&sumw_out[lo], o.sumw);
 #pragma unroll
-  for (int i = 0; i < NL; ++i) local_out[lo * NL + i] = o.loc[i];
+  for (int i = 0; i < NL; ++i) atomicAdd(&local_out[lo * NL + i], o.loc[i]);
 }
 
 __global__ void flag_to_u64(uint64_t n, const uint8_t *__restrict__ f, uint64_t *__restrict__ out)
@@ -892,7 +897,7 @@ int nm_split_run(nm_ctx *ctx)
     NM_CUDA(cudaGetLastError());
     unsigned long long h = 0;
     NM_CUDA(cudaMemcpyAsync(&h, ties, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    NM_CUDA(cudaStreamSynchronize(ctx->stream));
+    NM_SYNC(ctx);
     ctx->counts.n_split_ties = h;
   } else {
     segment_measure_kernel<<<nm_blocks(n, 256), 256, 0, NM_LS(ctx)>>>(n, ctx->im_verts.as<double>(), ctx->im_measure.as<double>());
@@ -949,7 +954,7 @@ int nm_clip_run(nm_ctx *ctx)
   NM_CUDA(cudaGetLastError());
   unsigned long long h[4];
   NM_CUDA(cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  NM_SYNC(ctx);
   ctx->counts.n_accepted = h[0];
   ctx->counts.n_qpoints = h[1];
   ctx->counts.n_dropped = h[2];
@@ -1016,14 +1021,14 @@ int nm_quadrature_emit(nm_ctx *ctx, uint64_t *q_offset, double *points, double *
     NM_CUDA(cudaGetLastError());
     unsigned long long h_mis = 0;
     NM_CUDA(cudaMemcpyAsync(&h_mis, mismatch, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    NM_CUDA(cudaStreamSynchronize(ctx->stream));
+    NM_SYNC(ctx);
     if (h_mis) return nm_fail(ctx, NM_ERR_STATE, "internal error: %llu pairs emitted a different number of quadrature points than counted", h_mis);
   }
   if (where == NM_HOST) {
     if (points) NM_TRY(nm_download(ctx, points, pts_d, nq * d * sizeof(double), NM_HOST));
     if (weights) NM_TRY(nm_download(ctx, weights, w_d, nq * sizeof(double), NM_HOST));
   }
-  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  NM_SYNC(ctx);
   return NM_OK;
 }
 
@@ -1054,25 +1059,28 @@ int nm_local_from_quadrature(nm_ctx *ctx, uint64_t n_pairs, const uint32_t *im, 
   NM_TRY(nm_ensure(ctx, ctx->cand_sumw, (nc + 1) * sizeof(double)));
   NM_TRY(nm_ensure(ctx, ctx->cand_local, (nc + 1) * NL * sizeof(double)));
   NM_TRY(nm_ensure(ctx, ctx->cand_acc, nc + 1));
+  NM_TRY(nm_ensure(ctx, ctx->scratch_b, (nc / 32 + 2) * sizeof(uint32_t)));   // one claim bit per candidate
   NM_CUDA(cudaMemsetAsync(ctx->cand_acc.p, 0, nc + 1, ctx->stream));
   NM_CUDA(cudaMemsetAsync(ctx->cand_sumw.p, 0, (nc + 1) * sizeof(double), ctx->stream));
-  unsigned long long *missing = ctx->counters.as<unsigned long long>() + 9;
-  NM_CUDA(cudaMemsetAsync(missing, 0, 8, ctx->stream));
+  NM_CUDA(cudaMemsetAsync(ctx->cand_local.p, 0, (nc + 1) * NL * sizeof(double), ctx->stream));
+  NM_CUDA(cudaMemsetAsync(ctx->scratch_b.p, 0, (nc / 32 + 2) * sizeof(uint32_t), ctx->stream));
+  unsigned long long *missing = ctx->counters.as<unsigned long long>() + 9;    // [9] pairs without overlapping boxes, [10] distinct pairs
+  NM_CUDA(cudaMemsetAsync(missing, 0, 16, ctx->stream));
   if (n_pairs) {
     if (d == 3)
       local_from_quadrature_kernel<3><<<nm_blocks(n_pairs, 128), 128, 0, NM_LS(ctx)>>>(
           n_pairs, im_d, bg_d, qo_d, p_d, w_d, ctx->cand_ptr.as<uint64_t>(), ctx->cand_bg.as<uint32_t>(), ctx->bg_box.as<double>(), ctx->n_im,
-          ctx->cand_sumw.as<double>(), ctx->cand_local.as<double>(), ctx->cand_acc.as<uint8_t>(), missing);
+          ctx->cand_sumw.as<double>(), ctx->cand_local.as<double>(), ctx->cand_acc.as<uint8_t>(), ctx->scratch_b.as<uint32_t>(), missing, missing + 1);
     else
       local_from_quadrature_kernel<2><<<nm_blocks(n_pairs, 128), 128, 0, NM_LS(ctx)>>>(
           n_pairs, im_d, bg_d, qo_d, p_d, w_d, ctx->cand_ptr.as<uint64_t>(), ctx->cand_bg.as<uint32_t>(), ctx->bg_box.as<double>(), ctx->n_im,
-          ctx->cand_sumw.as<double>(), ctx->cand_local.as<double>(), ctx->cand_acc.as<uint8_t>(), missing);
+          ctx->cand_sumw.as<double>(), ctx->cand_local.as<double>(), ctx->cand_acc.as<uint8_t>(), ctx->scratch_b.as<uint32_t>(), missing, missing + 1);
     NM_CUDA(cudaGetLastError());
   }
-  unsigned long long h = 0;
-  NM_CUDA(cudaMemcpyAsync(&h, missing, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  NM_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (h) return nm_fail(ctx, NM_ERR_INVALID, "%llu of the given pairs do not have overlapping bounding boxes on the grids set in this context", h);
-  ctx->counts.n_accepted = n_pairs;
+  unsigned long long h[2] = {0, 0};
+  NM_CUDA(cudaMemcpyAsync(h, missing, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  NM_SYNC(ctx);
+  if (h[0]) return nm_fail(ctx, NM_ERR_INVALID, "%llu of the given pairs do not have overlapping bounding boxes on the grids set in this context", h[0]);
+  ctx->counts.n_accepted = h[1];   // distinct pairs
   return NM_OK;
 }

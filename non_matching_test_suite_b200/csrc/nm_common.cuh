@@ -41,6 +41,11 @@ struct nm_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;           // host->device copies of nm_assemble_host
+  cudaStream_t down_stream = nullptr;           // device->host copies of nm_get_csr_compact(NM_HOST_ASYNC)
+  cudaEvent_t ev_down_ready = nullptr, ev_down_done = nullptr;
+  bool download_pending = false;                // the next matrix build must wait for ev_down_done
+  uint64_t n_syncs = 0;                         // host synchronisations with the stream (counter read-backs) since nm_create
+  int index_kind = 0;                           // grid index in use: 0 = none yet, 1 = per-cell chains, 2 = brick bitmasks
   cudaEvent_t ev_copy[3] = {nullptr, nullptr, nullptr};
   std::string err;
   int sm_count = NM_SM_COUNT_B200;
@@ -65,12 +70,15 @@ struct nm_ctx {
   DevBuf im_split;    // [n_im] u8 (3D)
   DevBuf im_measure;  // [n_im] f64
   bool im_set = false, im_dofs_set = false;
+  bool dofs_checked = false;   // both dof tables verified against the declared dof counts (reset by every upload)
 
   // ---- grid hash ----
   GridIndex gi;
   DevBuf idx_next;      // chain of the entries of one grid cell (next[entry id])
   DevBuf idx_extra_bg;  // background id of entry ids >= n_bg
   DevBuf idx_hash, idx_tmp;
+  DevBuf brk_hdr, brk_bit;  // brick index: header (levels, origins, flags), bit of every cell inside its brick
+  bool force_chain_index = false;  // NMGPU_INDEX=chains: skip the brick index (testing)
 
   // ---- intersection results ----
   unsigned degree = 0;
@@ -112,7 +120,12 @@ struct nm_ctx {
   int compact_rows_env = -1;  // NMGPU_COMPACT_ROWS: 0 / 1 force, -1 automatic
   uint64_t n_local_rows = 0;
   DevBuf row_bits, row_prefix, row_ids;
+  // list of the non-empty rows for the compact read-back / local numbering (built on demand, nm_nonempty_rows)
+  DevBuf out_ids, out_len;
+  uint64_t n_out_rows = 0;
+  bool out_rows_valid = false;
   bool matrix_valid = false;
+  int merge_path = -1;   // which merge built the matrix: 0 = single-pass hash merge, 1 = general two-pass path
 
   // ---- interface-penalisation terms (nm_nitsche.cu): square matrix on the space dofs + right-hand side ----
   DevBuf nit_cnt, nit_keys, nit_vals, nit_rkeys, nit_rvals;
@@ -122,6 +135,7 @@ struct nm_ctx {
 
   // ---- scratch ----
   DevBuf scan_tmp, scratch_a, scratch_b, stage_x, stage_y, h2d_stage;
+  DevBuf glob_im, glob_dof;   // global-numbered device scratch vectors of the products in local numbering
 
   // ---- timing ----
   uint64_t n_launches = 0;  // kernels of this library launched so far (cub's internal ones not counted)
@@ -139,6 +153,13 @@ int nm_fail(nm_ctx *c, int code, const char *fmt, ...);
     cudaError_t e__ = (call);                                                                      \
     if (e__ != cudaSuccess)                                                                        \
       return nm_fail(ctx, NM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+// host waits for the context's stream (counted: every one of them drains the GPU between two phases)
+#define NM_SYNC(c)                                      \
+  do {                                                  \
+    ++(c)->n_syncs;                                     \
+    NM_CUDA(cudaStreamSynchronize((c)->stream));        \
   } while (0)
 
 #define NM_TRY(call)            \
@@ -197,8 +218,11 @@ int nm_local_from_quadrature(nm_ctx *ctx, uint64_t n_pairs, const uint32_t *im, 
 int nm_matrix_build(nm_ctx *ctx);
 int nm_nitsche_run(nm_ctx *ctx, uint64_t n_pairs, const uint32_t *bg, const uint64_t *q_offset, const double *points,
                    const double *weights, const double *coefficient, const double *rhs_values, double penalty, int what, int where);
-int nm_spmv_run(nm_ctx *ctx, int transpose, const double *x_dev, double *y_dev);
+#define NM_SPMV_LOCAL_OUT 1
+int nm_spmv_run(nm_ctx *ctx, int transpose, const double *x_dev, double *y_dev, int flags = 0);
 int nm_stored_rowptr_global(nm_ctx *ctx, uint64_t *rowptr_dev);
 int nm_spmv_push_owned_run(nm_ctx *ctx, const double *x, int n_ranks, double *const *targets, uint64_t rows_per_rank);
+int nm_nonempty_rows(nm_ctx *ctx, uint64_t *n_rows_out, const uint32_t **ids_dev, const uint32_t **len_dev);
+int nm_local_map(nm_ctx *ctx, int which, int to_global, const double *src, double *dst);
 int nm_exclusive_scan_u64(nm_ctx *ctx, const uint64_t *in, uint64_t *out, uint64_t n);
 int nm_exclusive_scan_u32_to_u64(nm_ctx *ctx, const uint32_t *in, uint64_t *out, uint64_t n);

@@ -21,6 +21,7 @@
 #include <thrust/iterator/transform_iterator.h>
 
 #include "nm_common.cuh"
+#include "nm_brick.cuh"
 
 namespace {
 
@@ -376,6 +377,302 @@ __global__ void cand_place(GridDev G, uint64_t n_im, const double *__restrict__ 
   });
 }
 
+
+// ---------------------------------------------------------------------------------------
+// brick index: the fast path for grid-aligned trees (every reference configuration)
+// ---------------------------------------------------------------------------------------
+// A background cell of a hyper_cube refinement occupies exactly one cell of the uniform grid of its
+// own level, and its corners are c(i) = org_k + i * g_k bit for bit.  When that holds for every cell
+// (verified below, cell by cell, on the raw doubles) the grid cells are grouped into bricks of 64
+// (4x4x4, 8x8 in 2D): one 32-byte hash slot per occupied brick carries a 64-bit occupancy mask and the
+// offset of the brick's cell ids, which are stored in bit order.  A query then costs one slot per
+// brick (<= 8 per level instead of 27..64 per-cell slots), the occupied slots of a surface band fit in
+// L2, and the closed-box test needs no box at all: it is done once per axis on the reconstructed
+// corners, which ARE the raw doubles, so the candidate set is still exactly the reference's
+// (coupling_utilities.cc:53-55).  Any cell that fails the verification, two cells in one grid cell, or
+// an overfull table raise `bad`, and the per-cell chain index above takes over.
+struct BrickSlot {
+  unsigned long long key;   // packed (level, bx, by, bz); ~0 = empty
+  unsigned long long mask;  // occupied grid cells of the brick
+  uint32_t base;            // first id of the brick in BrickDev::ids
+  uint32_t pad0;
+  unsigned long long pad1;
+};
+
+struct BrickHeader {
+  unsigned long long lvl_min[32][3];  // per level and axis: smallest lower corner, order-preserving encoding
+  unsigned level_mask;
+  unsigned bad;
+  unsigned long long cursor;
+};
+
+struct BrickDev {
+  BrickSlot *slots;
+  uint32_t slot_mask;   // capacity - 1
+  uint32_t *ids;
+  BrickHeader *hdr;
+  double g0;
+  int idx_bits;
+};
+
+template <int D>
+__device__ __forceinline__ unsigned long long brick_key(int level, long long bx, long long by, long long bz)
+{
+  return pack_key(D, level, bx, by, bz);
+}
+
+// levels present and the per-level origin
+template <int D>
+__global__ void __launch_bounds__(256) brick_levels(double g0, uint64_t n, const double *__restrict__ box, BrickHeader *hdr)
+{
+  __shared__ unsigned long long s_min[32][3];
+  __shared__ unsigned s_mask;
+  for (int i = threadIdx.x; i < 96; i += blockDim.x) s_min[i / 3][i % 3] = ~0ULL;
+  if (threadIdx.x == 0) s_mask = 0;
+  __syncthreads();
+  int cur = -1;
+  unsigned long long mn[3] = {~0ULL, ~0ULL, ~0ULL};
+  unsigned bits = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const double *b = box + i * 8;
+    double e = 0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) e = fmax(e, b[4 + k] - b[k]);
+    const int level = level_of(e, g0);
+    if (level != cur) {
+      if (cur >= 0)
+        for (int k = 0; k < D; ++k) atomicMin(&s_min[cur][k], mn[k]);
+      cur = level;
+      mn[0] = mn[1] = mn[2] = ~0ULL;
+      bits |= 1u << level;
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) { const unsigned long long v = nmbrick::ord_encode(b[k]); mn[k] = v < mn[k] ? v : mn[k]; }
+  }
+  if (cur >= 0)
+    for (int k = 0; k < D; ++k) atomicMin(&s_min[cur][k], mn[k]);
+  if (bits) atomicOr(&s_mask, bits);
+  __syncthreads();
+  const unsigned m = s_mask;
+  for (int i = threadIdx.x; i < 96; i += blockDim.x)
+    if (((m >> (i / 3)) & 1u) && (i % 3) < D) atomicMin(&hdr->lvl_min[i / 3][i % 3], s_min[i / 3][i % 3]);
+  if (threadIdx.x == 0 && m) atomicOr(&hdr->level_mask, m);
+}
+
+__global__ void brick_clear(BrickSlot *s, uint32_t cap)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cap) { s[i].key = ~0ULL; s[i].mask = 0ULL; }
+}
+
+// every cell verifies that it IS a cell of its level grid, claims the slot of its brick and sets its bit
+template <int D>
+__global__ void __launch_bounds__(256) brick_insert(BrickDev B, uint64_t n, const double *__restrict__ box, uint32_t *__restrict__ cell_slot,
+                                                    uint8_t *__restrict__ cell_bit)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  constexpr int SH = nmbrick::BrickShape<D>::SH;
+  const double *b = box + i * 8;
+  double e = 0;
+#pragma unroll
+  for (int k = 0; k < D; ++k) e = fmax(e, b[4 + k] - b[k]);
+  const int level = level_of(e, B.g0);
+  const double g = B.g0 * (double)(1ULL << level), inv = 1.0 / g;
+  long long idx[3] = {0, 0, 0};
+  bool ok = true;
+  const long long lim = 1LL << B.idx_bits;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    const double org = nmbrick::ord_decode(B.hdr->lvl_min[level][k]);
+    const long long j = llrint((b[k] - org) * inv);
+    ok &= j >= 0 && j < lim - 1 && nmbrick::grid_corner(org, j, g) == b[k] && nmbrick::grid_corner(org, j + 1, g) == b[4 + k];
+    idx[k] = j;
+  }
+  if (!ok) { atomicOr(&B.hdr->bad, 1u); cell_slot[i] = 0xffffffffu; return; }
+  const unsigned bit = D == 3 ? (unsigned)((idx[0] & 3) | ((idx[1] & 3) << 2) | ((idx[2] & 3) << 4)) : (unsigned)((idx[0] & 7) | ((idx[1] & 7) << 3));
+  const unsigned long long key = brick_key<D>(level, idx[0] >> SH, idx[1] >> SH, idx[2] >> SH);
+  uint32_t s = (uint32_t)mix64(key) & B.slot_mask;
+  int probes = 0;
+  while (true) {
+    const unsigned long long old = atomicCAS(&B.slots[s].key, ~0ULL, key);
+    if (old == ~0ULL || old == key) break;
+    s = (s + 1) & B.slot_mask;
+    if (++probes > 512) { atomicOr(&B.hdr->bad, 2u); cell_slot[i] = 0xffffffffu; return; }   // table too full: not a surface band
+  }
+  const unsigned long long prev = atomicOr(&B.slots[s].mask, 1ULL << bit);
+  if ((prev >> bit) & 1ULL) atomicOr(&B.hdr->bad, 4u);   // two cells in one grid cell: overlapping boxes
+  cell_slot[i] = s;
+  cell_bit[i] = (uint8_t)bit;
+}
+
+__global__ void brick_base(BrickDev B, uint32_t cap)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long m = 0;
+  if (i < cap && B.slots[i].key != ~0ULL) m = B.slots[i].mask;
+  const unsigned c = (unsigned)__popcll(m);
+  // one atomic per warp
+  unsigned inc = c;
+  const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (unsigned)o) inc += v; }
+  const unsigned total = __shfl_sync(0xffffffffu, inc, 31);
+  unsigned long long base = 0;
+  if (lane == 31 && total) base = atomicAdd(&B.hdr->cursor, (unsigned long long)total);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  if (c) B.slots[i].base = (uint32_t)(base + inc - c);
+}
+
+__global__ void brick_fill(BrickDev B, uint64_t n, const uint32_t *__restrict__ cell_slot, const uint8_t *__restrict__ cell_bit)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t s = cell_slot[i];
+  if (s == 0xffffffffu) return;
+  const unsigned bit = cell_bit[i];
+  const BrickSlot sl = B.slots[s];
+  B.ids[sl.base + __popcll(sl.mask & ((1ULL << bit) - 1ULL))] = (uint32_t)i;
+}
+
+// per level: the exact range of grid indices whose closed cell meets [qlo, qhi] along every axis
+template <int D>
+__device__ __forceinline__ bool brick_level_range(const BrickDev &B, int level, const double *qlo, const double *qhi, long long *L, long long *H)
+{
+  const double g = B.g0 * (double)(1ULL << level), inv = 1.0 / g;
+  const long long top = (1LL << B.idx_bits) - 2;
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < D; ++k) ok &= nmbrick::axis_range(nmbrick::ord_decode(B.hdr->lvl_min[level][k]), g, inv, top, qlo[k], qhi[k], L[k], H[k]);
+  for (int k = D; k < 3; ++k) L[k] = H[k] = 0;
+  return ok;
+}
+
+__device__ __forceinline__ bool brick_find(const BrickDev &B, unsigned long long key, BrickSlot &out)
+{
+  uint32_t s = (uint32_t)mix64(key) & B.slot_mask;
+  while (true) {
+    const ulonglong2 km = *reinterpret_cast<const ulonglong2 *>(&B.slots[s]);
+    if (km.x == key) { out.key = km.x; out.mask = km.y; out.base = B.slots[s].base; return true; }
+    if (km.x == ~0ULL) return false;
+    s = (s + 1) & B.slot_mask;
+  }
+}
+
+// G lanes per immersed cell: the bricks of a level are probed in parallel lanes, the hits are collected in shared
+// memory, ordered by rank counting and stored as one row of at most CAP ids (the true count is recorded even when
+// it exceeds CAP; cand_place_brick probes such cells again).
+template <int D, int G, int CAP>
+__global__ void __launch_bounds__(128) cand_probe_brick(BrickDev B, uint64_t n_im, const double *__restrict__ im_verts,
+                                                        uint32_t *__restrict__ cnt, uint32_t *__restrict__ tmp)
+{
+  constexpr int NVI = 1 << (D - 1), CPB = 128 / G, SH = nmbrick::BrickShape<D>::SH;
+  __shared__ uint32_t s_ids[CPB][CAP];
+  __shared__ unsigned s_n[CPB];
+  const unsigned g = threadIdx.x / G, l = threadIdx.x % G;
+  const unsigned gbase = (threadIdx.x & 31) - l;
+  const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << gbase);
+  const uint64_t m = (uint64_t)blockIdx.x * CPB + g;
+  if (m >= n_im) return;   // whole groups leave together
+  if (l == 0) s_n[g] = 0;
+  double lo[3], hi[3];
+  im_box<D, NVI>(im_verts + m * NVI * D, lo, hi);
+  __syncwarp(gmask);
+  uint32_t lm = B.hdr->level_mask;
+  while (lm) {
+    const int level = __ffs(lm) - 1;
+    lm &= lm - 1;
+    long long L[3], H[3];
+    if (!brick_level_range<D>(B, level, lo, hi, L, H)) continue;
+    const long long b0[3] = {L[0] >> SH, L[1] >> SH, L[2] >> SH};
+    const int nb[3] = {(int)((H[0] >> SH) - b0[0]) + 1, (int)((H[1] >> SH) - b0[1]) + 1, D == 3 ? (int)((H[2] >> SH) - b0[2]) + 1 : 1};
+    const int T = nb[0] * nb[1] * nb[2];
+    for (int t = (int)l; t < T; t += G) {
+      const int tx = t % nb[0], ty = (t / nb[0]) % nb[1], tz = t / (nb[0] * nb[1]);
+      const long long bx = b0[0] + tx, by = b0[1] + ty, bz = b0[2] + tz;
+      BrickSlot sl;
+      if (!brick_find(B, brick_key<D>(level, bx, by, bz), sl)) continue;
+      unsigned long long hits = sl.mask & nmbrick::brick_query_mask<D>(L, H, bx, by, bz);
+      const unsigned nh = (unsigned)__popcll(hits);
+      if (!nh) continue;
+      unsigned pos = atomicAdd(&s_n[g], nh);
+      while (hits) {
+        const int bit = __ffsll((long long)hits) - 1;
+        hits &= hits - 1;
+        if (pos < (unsigned)CAP) s_ids[g][pos] = B.ids[sl.base + __popcll(sl.mask & ((1ULL << bit) - 1ULL))];
+        ++pos;
+      }
+    }
+  }
+  __syncwarp(gmask);
+  const unsigned total = s_n[g];
+  if (l == 0) cnt[m] = total;
+  if (total <= (unsigned)CAP) {
+    uint32_t *row = tmp + m * CAP;
+    for (unsigned e = l; e < total; e += G) {
+      const uint32_t v = s_ids[g][e];
+      unsigned r = 0;
+      for (unsigned j = 0; j < total; ++j) r += s_ids[g][j] < v ? 1u : 0u;
+      row[r] = v;
+    }
+  }
+}
+
+// all candidates of one immersed cell, one thread (cells whose row overflowed CAP)
+template <int D, typename Emit>
+__device__ inline void brick_query_serial(const BrickDev &B, const double *lo, const double *hi, Emit emit)
+{
+  constexpr int SH = nmbrick::BrickShape<D>::SH;
+  uint32_t lm = B.hdr->level_mask;
+  while (lm) {
+    const int level = __ffs(lm) - 1;
+    lm &= lm - 1;
+    long long L[3], H[3];
+    if (!brick_level_range<D>(B, level, lo, hi, L, H)) continue;
+    for (long long bz = L[2] >> SH; bz <= (H[2] >> SH); ++bz)
+      for (long long by = L[1] >> SH; by <= (H[1] >> SH); ++by)
+        for (long long bx = L[0] >> SH; bx <= (H[0] >> SH); ++bx) {
+          BrickSlot sl;
+          if (!brick_find(B, brick_key<D>(level, bx, by, bz), sl)) continue;
+          unsigned long long hits = sl.mask & nmbrick::brick_query_mask<D>(L, H, bx, by, bz);
+          while (hits) {
+            const int bit = __ffsll((long long)hits) - 1;
+            hits &= hits - 1;
+            emit(B.ids[sl.base + __popcll(sl.mask & ((1ULL << bit) - 1ULL))]);
+          }
+        }
+  }
+}
+
+template <int D, int CAP, int LANES>
+__global__ void cand_place_brick(BrickDev B, uint64_t n_im, const double *__restrict__ im_verts, const uint64_t *__restrict__ ptr,
+                                 const uint32_t *__restrict__ tmp, uint32_t *__restrict__ cand_im, uint32_t *__restrict__ cand_bg)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t m = t / LANES;
+  const unsigned l = t % LANES;
+  if (m >= n_im) return;
+  const uint64_t p0 = ptr[m];
+  const uint32_t n = (uint32_t)(ptr[m + 1] - p0);
+  if (n <= CAP) {
+    const uint32_t *row = tmp + m * CAP;
+    for (uint32_t k = l; k < n; k += LANES) { cand_bg[p0 + k] = row[k]; cand_im[p0 + k] = (uint32_t)m; }
+    return;
+  }
+  if (l != 0) return;
+  constexpr int NVI = 1 << (D - 1);
+  double lo[3], hi[3];
+  im_box<D, NVI>(im_verts + m * NVI * D, lo, hi);
+  uint64_t p = p0;
+  brick_query_serial<D>(B, lo, hi, [&](uint32_t b) {
+    uint64_t j = p;
+    while (j > p0 && cand_bg[j - 1] > b) { cand_bg[j] = cand_bg[j - 1]; --j; }
+    cand_bg[j] = b;
+    cand_im[p] = (uint32_t)m;
+    ++p;
+  });
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------
@@ -428,7 +725,7 @@ int nm_bg_layout(nm_ctx *ctx, int d, uint64_t n, const double *verts_dev, const 
   }
   int h_bad = 0;
   NM_CUDA(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  NM_SYNC(ctx);
   if (h_bad)
     return nm_fail(ctx, NM_ERR_UNSUPPORTED,
                    "%d background cell(s) are not axis-aligned boxes in deal.II vertex order; only Cartesian "
@@ -448,7 +745,7 @@ int nm_constraints_layout(nm_ctx *ctx, const uint32_t *c_dof_dev)
     NM_CUDA(cudaGetLastError());
     int h_bad = 0;
     NM_CUDA(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    NM_CUDA(cudaStreamSynchronize(ctx->stream));
+    NM_SYNC(ctx);
     if (h_bad) return nm_fail(ctx, NM_ERR_INVALID, "%d constrained DoF index(es) >= n_dofs", h_bad);
   }
   return NM_OK;
@@ -473,6 +770,9 @@ static GridDev make_grid_dev(const nm_ctx *ctx)
   return G;
 }
 
+static int chain_index_build(nm_ctx *ctx);
+static int brick_index_build(nm_ctx *ctx);
+
 int nm_index_build(nm_ctx *ctx)
 {
   const int d = ctx->spacedim;
@@ -495,7 +795,7 @@ int nm_index_build(nm_ctx *ctx)
   ctx->bg_stats_ready = false;  // idx_tmp is reused below
   static thread_local double h_stats[SB * 8];
   NM_CUDA(cudaMemcpyAsync(h_stats, ctx->idx_tmp.p, sizeof(h_stats), cudaMemcpyDeviceToHost, ctx->stream));
-  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  NM_SYNC(ctx);
   double org[3] = {INFINITY, INFINITY, INFINITY}, top[3] = {-INFINITY, -INFINITY, -INFINITY}, g0 = INFINITY, gmax = 0;
   for (unsigned b = 0; b < SB; ++b) {
     for (int k = 0; k < 3; ++k) { org[k] = fmin(org[k], h_stats[b * 8 + k]); top[k] = fmax(top[k], h_stats[b * 8 + 3 + k]); }
@@ -514,6 +814,20 @@ int nm_index_build(nm_ctx *ctx)
                      "background spans more than 2^%d finest cells along axis %d (extent %g, finest cell %g)", bits, k,
                      top[k] - org[k], g0);
 
+  if (!ctx->force_chain_index) {
+    NM_TRY(brick_index_build(ctx));
+    ctx->index_kind = 2;
+    ctx->index_valid = true;
+    return NM_OK;
+  }
+  return chain_index_build(ctx);
+}
+
+// per-cell chain index: any boxes (a cell may cover several grid cells of its level)
+static int chain_index_build(nm_ctx *ctx)
+{
+  const int d = ctx->spacedim;
+  const uint64_t n = ctx->n_bg;
   // 2. size of the table: number of (cell, grid cell) registrations
   GridDev G = make_grid_dev(ctx);
   NM_TRY(nm_ensure(ctx, ctx->counters, 64 * sizeof(uint64_t)));
@@ -529,7 +843,7 @@ int nm_index_build(nm_ctx *ctx)
   NM_CUDA(cudaGetLastError());
   unsigned long long h_hdr[3];
   NM_CUDA(cudaMemcpyAsync(h_hdr, ctx->counters.p, sizeof(h_hdr), cudaMemcpyDeviceToHost, ctx->stream));
-  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  NM_SYNC(ctx);
   if ((unsigned)(h_hdr[0] & 0xffffffffu)) return nm_fail(ctx, NM_ERR_UNSUPPORTED, "background cells outside the indexable grid range");
   const uint64_t ne = h_hdr[2];
   if (ne >= 0x7fffffffULL) return nm_fail(ctx, NM_ERR_UNSUPPORTED, "grid index needs %llu entries (limit 2^31)", (unsigned long long)ne);
@@ -549,12 +863,107 @@ int nm_index_build(nm_ctx *ctx)
   else index_insert<3><<<B, T, 0, NM_LS(ctx)>>>(G, n, ctx->bg_box.as<double>(), ctx->idx_hash.as<HashSlot>(), ctx->idx_next.as<uint32_t>(),
                                                 ctx->idx_extra_bg.as<uint32_t>(), extra_cursor);
   NM_CUDA(cudaGetLastError());
+  ctx->index_kind = 1;
   ctx->index_valid = true;
   return NM_OK;
 }
 
+static BrickDev make_brick_dev(const nm_ctx *ctx)
+{
+  BrickDev B;
+  B.slots = ctx->idx_hash.as<BrickSlot>();
+  B.slot_mask = ctx->gi.hash_cap - 1;
+  B.ids = ctx->idx_extra_bg.as<uint32_t>();
+  B.hdr = ctx->brk_hdr.as<BrickHeader>();
+  B.g0 = ctx->gi.g0;
+  B.idx_bits = ctx->gi.d == 2 ? 29 : 19;
+  return B;
+}
+
+// brick index (grid-aligned trees): levels + per-level origins, verification + insertion, id offsets, ids.  No host
+// synchronisation: a failed verification is noticed with the candidate count (nm_candidates_run) and the chain index
+// takes over.
+static int brick_index_build(nm_ctx *ctx)
+{
+  const int d = ctx->spacedim;
+  const uint64_t n = ctx->n_bg;
+  uint32_t cap = 64;
+  while (cap < n / 2 + 1) cap <<= 1;   // a surface band fills ~1/25 brick per cell; a fuller table raises `bad`
+  ctx->gi.hash_cap = cap;
+  ctx->gi.n_entries = (uint32_t)n;
+  NM_TRY(nm_ensure(ctx, ctx->idx_hash, (size_t)cap * sizeof(BrickSlot)));
+  NM_TRY(nm_ensure(ctx, ctx->idx_next, (n + 1) * 4));       // slot of every cell
+  NM_TRY(nm_ensure(ctx, ctx->brk_bit, n + 1));              // bit of every cell inside its brick
+  NM_TRY(nm_ensure(ctx, ctx->idx_extra_bg, (n + 1) * 4));   // cell ids, brick by brick in bit order
+  NM_TRY(nm_ensure(ctx, ctx->brk_hdr, sizeof(BrickHeader)));
+  BrickHeader *hdr = ctx->brk_hdr.as<BrickHeader>();
+  NM_CUDA(cudaMemsetAsync(hdr, 0xff, sizeof(hdr->lvl_min), ctx->stream));
+  NM_CUDA(cudaMemsetAsync(&hdr->level_mask, 0, sizeof(BrickHeader) - sizeof(hdr->lvl_min), ctx->stream));
+  const BrickDev B = make_brick_dev(ctx);
+  const unsigned T = 256, NB = nm_blocks(n, T);
+  const unsigned GB = NB < (unsigned)ctx->sm_count * 8u ? NB : (unsigned)ctx->sm_count * 8u;
+  const double *box = ctx->bg_box.as<double>();
+  if (d == 2) brick_levels<2><<<GB, T, 0, NM_LS(ctx)>>>(B.g0, n, box, hdr);
+  else brick_levels<3><<<GB, T, 0, NM_LS(ctx)>>>(B.g0, n, box, hdr);
+  brick_clear<<<nm_blocks(cap, 256), 256, 0, NM_LS(ctx)>>>(B.slots, cap);
+  if (d == 2) brick_insert<2><<<NB, T, 0, NM_LS(ctx)>>>(B, n, box, ctx->idx_next.as<uint32_t>(), ctx->brk_bit.as<uint8_t>());
+  else brick_insert<3><<<NB, T, 0, NM_LS(ctx)>>>(B, n, box, ctx->idx_next.as<uint32_t>(), ctx->brk_bit.as<uint8_t>());
+  brick_base<<<nm_blocks(cap, 256), 256, 0, NM_LS(ctx)>>>(B, cap);
+  brick_fill<<<NB, T, 0, NM_LS(ctx)>>>(B, n, ctx->idx_next.as<uint32_t>(), ctx->brk_bit.as<uint8_t>());
+  NM_CUDA(cudaGetLastError());
+  return NM_OK;
+}
+
 template <int D, int CAP>
-static int candidates_run_t(nm_ctx *ctx)
+static int candidates_run_chains(nm_ctx *ctx);
+
+// candidates through the brick index; *fell_back is set when the verification of the index failed
+template <int D, int CAP, int G>
+static int candidates_run_bricks(nm_ctx *ctx, bool *fell_back)
+{
+  const uint64_t n_im = ctx->n_im;
+  const BrickDev B = make_brick_dev(ctx);
+  *fell_back = false;
+  NM_TRY(nm_ensure(ctx, ctx->scratch_a, (n_im + 1) * sizeof(uint32_t)));
+  NM_TRY(nm_ensure(ctx, ctx->cand_ptr, (n_im + 1) * sizeof(uint64_t)));
+  NM_TRY(nm_ensure(ctx, ctx->cand_tmp, (n_im + 1) * CAP * sizeof(uint32_t)));
+  ctx->counts.n_candidates = 0;
+  NM_CUDA(cudaMemsetAsync(ctx->scratch_a.as<uint32_t>() + n_im, 0, 4, ctx->stream));
+  constexpr int CPB = 128 / G;
+  KernelTimer kc(ctx, NM_T_K_CAND_COUNT);
+  if (n_im)
+    cand_probe_brick<D, G, CAP><<<nm_blocks(n_im, CPB), 128, 0, NM_LS(ctx)>>>(B, n_im, ctx->im_verts.as<double>(), ctx->scratch_a.as<uint32_t>(),
+                                                                             ctx->cand_tmp.as<uint32_t>());
+  kc.stop();
+  NM_CUDA(cudaGetLastError());
+  NM_TRY(nm_exclusive_scan_u32_to_u64(ctx, ctx->scratch_a.as<uint32_t>(), ctx->cand_ptr.as<uint64_t>(), n_im + 1));
+  uint64_t n_cand = 0;
+  unsigned bad = 0;
+  NM_CUDA(cudaMemcpyAsync(&n_cand, ctx->cand_ptr.as<uint64_t>() + n_im, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  NM_CUDA(cudaMemcpyAsync(&bad, &B.hdr->bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  NM_SYNC(ctx);
+  if (bad) {   // not a grid-aligned tree (or not a surface band): redo with the general index
+    NM_TRY(chain_index_build(ctx));
+    *fell_back = true;
+    return NM_OK;
+  }
+  if (n_cand >= 0xffffffffULL * 16) return nm_fail(ctx, NM_ERR_UNSUPPORTED, "too many candidate pairs (%llu)", (unsigned long long)n_cand);
+  ctx->counts.n_candidates = n_cand;
+  NM_TRY(nm_ensure(ctx, ctx->cand_im, (n_cand + 1) * 4));
+  NM_TRY(nm_ensure(ctx, ctx->cand_bg, (n_cand + 1) * 4));
+  constexpr int LANES = 8;
+  KernelTimer kf(ctx, NM_T_K_CAND_FILL);
+  if (n_im)
+    cand_place_brick<D, CAP, LANES><<<nm_blocks(n_im * LANES, 256), 256, 0, NM_LS(ctx)>>>(B, n_im, ctx->im_verts.as<double>(), ctx->cand_ptr.as<uint64_t>(),
+                                                                                        ctx->cand_tmp.as<uint32_t>(), ctx->cand_im.as<uint32_t>(),
+                                                                                        ctx->cand_bg.as<uint32_t>());
+  kf.stop();
+  NM_CUDA(cudaGetLastError());
+  return NM_OK;
+}
+
+template <int D, int CAP>
+static int candidates_run_chains(nm_ctx *ctx)
 {
   const uint64_t n_im = ctx->n_im;
   GridDev G = make_grid_dev(ctx);
@@ -573,7 +982,7 @@ static int candidates_run_t(nm_ctx *ctx)
   NM_TRY(nm_exclusive_scan_u32_to_u64(ctx, ctx->scratch_a.as<uint32_t>(), ctx->cand_ptr.as<uint64_t>(), n_im + 1));
   uint64_t n_cand = 0;
   NM_CUDA(cudaMemcpyAsync(&n_cand, ctx->cand_ptr.as<uint64_t>() + n_im, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  NM_SYNC(ctx);
   if (n_cand >= 0xffffffffULL * 16) return nm_fail(ctx, NM_ERR_UNSUPPORTED, "too many candidate pairs (%llu)", (unsigned long long)n_cand);
   ctx->counts.n_candidates = n_cand;
   NM_TRY(nm_ensure(ctx, ctx->cand_im, (n_cand + 1) * 4));
@@ -588,4 +997,13 @@ static int candidates_run_t(nm_ctx *ctx)
   return NM_OK;
 }
 
-int nm_candidates_run(nm_ctx *ctx) { return ctx->spacedim == 2 ? candidates_run_t<2, 16>(ctx) : candidates_run_t<3, 40>(ctx); }
+int nm_candidates_run(nm_ctx *ctx)
+{
+  if (ctx->n_im == 0) { NM_TRY(nm_ensure(ctx, ctx->cand_ptr, 16)); ctx->counts.n_candidates = 0; NM_CUDA(cudaMemsetAsync(ctx->cand_ptr.p, 0, 8, ctx->stream)); return NM_OK; }
+  if (ctx->index_kind == 2 && ctx->n_bg) {
+    bool fell_back = false;
+    NM_TRY((ctx->spacedim == 2 ? candidates_run_bricks<2, 16, 4>(ctx, &fell_back) : candidates_run_bricks<3, 40, 8>(ctx, &fell_back)));
+    if (!fell_back) return NM_OK;
+  }
+  return ctx->spacedim == 2 ? candidates_run_chains<2, 16>(ctx) : candidates_run_chains<3, 40>(ctx);
+}

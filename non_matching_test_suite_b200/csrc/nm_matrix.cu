@@ -727,7 +727,7 @@ __global__ void __launch_bounds__(256) spmv_crows(uint64_t n_im, const uint64_t 
   }
 #pragma unroll
   for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, LANES);
-  if (r < n_im && l == 0) y[im_dofs[r]] = s;
+  if (r < n_im && l == 0) y[im_dofs ? im_dofs[r] : r] = s;   // im_dofs == nullptr: result in local (cell) numbering
 }
 
 // compact copy of C's rows (for nm_get_csr(transpose = 1)): row index = immersed dof
@@ -743,6 +743,52 @@ __global__ void c_compact(uint64_t n_im, const uint64_t *__restrict__ rowstart, 
   const uint64_t s = rowstart[m], d = out_ptr[im_dofs[m]];
   const uint32_t n = rowlen[m];
   for (uint32_t k = l; k < n; k += LANES) { out_col[d + k] = col[s + k]; if (out_val) out_val[d + k] = val[s + k]; }
+}
+
+// rows of the stored orientation that hold entries (full-row mode: most dofs of a band-only background have none)
+__global__ void nonempty_flags(uint64_t n_rows, const uint64_t *__restrict__ rowptr, uint32_t *__restrict__ flag)
+{
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_rows) flag[r] = rowptr[r + 1] > rowptr[r] ? 1u : 0u;
+  if (r == n_rows) flag[r] = 0u;
+}
+
+// row_ids / row_len of the non-empty rows; ids == nullptr: row r is dof r (full-row mode), pos = compaction offsets
+__global__ void compact_rows_out(uint64_t n_rows, const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ ids,
+                                 const uint64_t *__restrict__ pos, uint32_t *__restrict__ out_ids, uint32_t *__restrict__ out_len)
+{
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const uint64_t b = rowptr[r], e = rowptr[r + 1];
+  if (pos) {
+    if (e == b) return;
+    const uint64_t o = pos[r];
+    if (out_ids) out_ids[o] = (uint32_t)r;
+    if (out_len) out_len[o] = (uint32_t)(e - b);
+  } else {
+    if (out_ids) out_ids[r] = ids[r];
+    if (out_len) out_len[r] = (uint32_t)(e - b);
+  }
+}
+
+// vectors in local numbering <-> the global numbering the kernels address: idx[i] = global position of local entry i
+__global__ void scatter_by_index(uint64_t n, const uint32_t *__restrict__ idx, const double *__restrict__ local, double *__restrict__ global)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) global[idx[i]] = local[i];
+}
+__global__ void gather_by_index(uint64_t n, const uint32_t *__restrict__ idx, const double *__restrict__ global, double *__restrict__ local)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) local[i] = global[idx[i]];
+}
+
+// dof tables come from the caller: an index beyond the declared dof count would send the merge out of bounds
+__global__ void check_index_range(uint64_t n, const uint32_t *__restrict__ idx, uint32_t limit, unsigned *bad)
+{
+  unsigned b = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) b |= idx[i] >= limit ? 1u : 0u;
+  if (__any_sync(0xffffffffu, b) && (threadIdx.x & 31) == 0) atomicOr(bad, 1u);
 }
 
 __global__ void scatter_len_by_dof(uint64_t n_im, const uint32_t *__restrict__ rowlen, const uint32_t *__restrict__ im_dofs, uint32_t *__restrict__ out)
@@ -790,7 +836,7 @@ static int matrix_build_fast(nm_ctx *ctx, bool *done)
   NM_TRY(nm_ensure(ctx, ctx->counters, 64 * sizeof(uint64_t)));
   unsigned long long *cursor = ctx->counters.as<unsigned long long>() + 20;
   unsigned *problem = ctx->counters.as<unsigned>() + 44;
-  NM_CUDA(cudaMemsetAsync(cursor, 0, 16, ctx->stream));
+  NM_CUDA(cudaMemsetAsync(cursor, 0, 32, ctx->stream));   // bytes 160..191: the chunk cursor AND the problem flag (byte 176)
   KernelTimer km(ctx, NM_T_K_MERGE);
   merge_rows_fast<NL, GROUP, SLOTS, FAST_CHUNK><<<(unsigned)blocks, 256, 0, NM_LS(ctx)>>>(
       n_im, ctx->cand_ptr.as<uint64_t>(), ctx->cand_bg.as<uint32_t>(), ctx->cand_acc.as<uint8_t>(), ctx->cand_local.as<double>(),
@@ -801,10 +847,11 @@ static int matrix_build_fast(nm_ctx *ctx, bool *done)
   NM_CUDA(cudaGetLastError());
   unsigned h_problem = 0;
   NM_CUDA(cudaMemcpyAsync(&h_problem, problem, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  NM_SYNC(ctx);
   tm.stop();
   if (h_problem) return NM_OK;  // the general path redoes everything
   NM_TRY(transpose_rows<NL>(ctx, true));
+  ctx->merge_path = 0;
   *done = true;
   return NM_OK;
 }
@@ -814,6 +861,7 @@ static int matrix_build_t(nm_ctx *ctx)
 {
   const uint64_t n_im = ctx->n_im, n_rows = ctx->n_space_dofs;
   ctx->matrix_valid = false;
+  ctx->out_rows_valid = false;
   ctx->nnz = 0;
   // sharded grids carry the global dof numbering: keep per-dof arrays out of the step when this rank can touch only a
   // small part of the dofs (each cell has 2^d of them)
@@ -824,6 +872,7 @@ static int matrix_build_t(nm_ctx *ctx)
     NM_TRY(matrix_build_fast<NL>(ctx, &done));
     if (done) return NM_OK;
   }
+  ctx->merge_path = 1;
   PhaseTimer tm(ctx, NM_T_MERGE);
   NM_TRY(nm_ensure(ctx, ctx->scratch_a, (n_im + 1) * sizeof(uint32_t)));
   NM_TRY(nm_ensure(ctx, ctx->c_rowstart, (n_im + 2) * sizeof(uint64_t)));
@@ -843,7 +892,7 @@ static int matrix_build_t(nm_ctx *ctx)
   unsigned h_hdr[4];
   NM_CUDA(cudaMemcpyAsync(&total_cap, ctx->c_rowstart.as<uint64_t>() + n_im, 8, cudaMemcpyDeviceToHost, ctx->stream));
   NM_CUDA(cudaMemcpyAsync(h_hdr, hdr, 16, cudaMemcpyDeviceToHost, ctx->stream));
-  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  NM_SYNC(ctx);
   if (h_hdr[0] > (unsigned)BLOCK_CAP)
     return nm_fail(ctx, NM_ERR_UNSUPPORTED,
                    "an immersed cell couples to %u (dof, value) contributions; at most %d per immersed cell are implemented "
@@ -911,7 +960,7 @@ static int transpose_rows(nm_ctx *ctx, bool counts_ready)
     NM_CUDA(cudaGetLastError());
     NM_TRY(nm_exclusive_scan_u32_to_u64(ctx, ctx->scratch_b.as<uint32_t>(), ctx->row_prefix.as<uint64_t>(), nw + 1));
     NM_CUDA(cudaMemcpyAsync(&n_rows, ctx->row_prefix.as<uint64_t>() + nw, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    NM_CUDA(cudaStreamSynchronize(ctx->stream));
+    NM_SYNC(ctx);
     NM_TRY(nm_ensure(ctx, ctx->row_ids, (n_rows + 1) * sizeof(uint32_t)));
     row_ids_kernel<<<nm_blocks(nw, 256), 256, 0, NM_LS(ctx)>>>(nw, ctx->row_bits.as<uint32_t>(), ctx->row_prefix.as<uint64_t>(),
                                                                ctx->row_ids.as<uint32_t>());
@@ -932,7 +981,7 @@ static int transpose_rows(nm_ctx *ctx, bool counts_ready)
   NM_TRY(nm_exclusive_scan_u32_to_u64(ctx, cnt, ctx->a_rowptr.as<uint64_t>(), n_rows + 1));
   uint64_t nnz = 0;
   NM_CUDA(cudaMemcpyAsync(&nnz, ctx->a_rowptr.as<uint64_t>() + n_rows, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  NM_SYNC(ctx);
   ctx->nnz = nnz;
   NM_TRY(nm_ensure(ctx, ctx->a_col, (nnz + 1) * sizeof(uint32_t)));
   NM_TRY(nm_ensure(ctx, ctx->a_val, (nnz + 1) * sizeof(double)));
@@ -975,15 +1024,45 @@ int nm_stored_rowptr_global(nm_ctx *ctx, uint64_t *rowptr_dev)
   return NM_OK;
 }
 
-int nm_matrix_build(nm_ctx *ctx) { return ctx->spacedim == 3 ? matrix_build_t<8>(ctx) : matrix_build_t<4>(ctx); }
+static int check_dof_tables(nm_ctx *ctx)
+{
+  if (ctx->dofs_checked) return NM_OK;
+  unsigned *bad = ctx->counters.as<unsigned>() + 48;   // [48] background table, [49] immersed table
+  NM_CUDA(cudaMemsetAsync(bad, 0, 8, ctx->stream));
+  const uint64_t nb = ctx->n_bg * (1ull << ctx->spacedim), ni = ctx->n_im;
+  const unsigned G = (unsigned)ctx->sm_count * 8u;
+  if (nb) check_index_range<<<G, 256, 0, NM_LS(ctx)>>>(nb, ctx->bg_dofs.as<uint32_t>(), (uint32_t)ctx->n_space_dofs, bad);
+  if (ni) check_index_range<<<G, 256, 0, NM_LS(ctx)>>>(ni, ctx->im_dofs.as<uint32_t>(), (uint32_t)ctx->n_im_dofs, bad + 1);
+  NM_CUDA(cudaGetLastError());
+  unsigned h[2] = {0, 0};
+  NM_CUDA(cudaMemcpyAsync(h, bad, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  NM_SYNC(ctx);
+  if (h[0]) return nm_fail(ctx, NM_ERR_INVALID, "background DoF table holds indices >= n_dofs (%llu)", (unsigned long long)ctx->n_space_dofs);
+  if (h[1]) return nm_fail(ctx, NM_ERR_INVALID, "immersed DoF table holds indices >= n_dofs (%llu)", (unsigned long long)ctx->n_im_dofs);
+  ctx->dofs_checked = true;
+  return NM_OK;
+}
 
-int nm_spmv_run(nm_ctx *ctx, int transpose, const double *x, double *y)
+int nm_matrix_build(nm_ctx *ctx)
+{
+  NM_TRY(check_dof_tables(ctx));
+  if (ctx->download_pending) {   // an asynchronous read-back of the previous matrix may still be reading the buffers rebuilt here
+    NM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_down_done, 0));
+    ctx->download_pending = false;
+  }
+  return ctx->spacedim == 3 ? matrix_build_t<8>(ctx) : matrix_build_t<4>(ctx);
+}
+
+// flags: NM_SPMV_LOCAL_OUT -- y in local numbering (transpose = 0: y[r] for stored row r, compact-row mode only;
+// transpose = 1: y[m] for immersed cell m) and nothing outside the computed entries is written.
+int nm_spmv_run(nm_ctx *ctx, int transpose, const double *x, double *y, int flags)
 {
   const uint64_t n_rows = ctx->n_local_rows, n_im = ctx->n_im;
+  const bool local_out = (flags & NM_SPMV_LOCAL_OUT) != 0;
   PhaseTimer tm(ctx, transpose ? NM_T_SPMV_T : NM_T_SPMV);
   if (!transpose) {
     const uint32_t *ids = nullptr;
-    if (ctx->compact_rows) {   // only the touched rows are computed; the rest of y is zero
+    if (ctx->compact_rows && !local_out) {   // only the touched rows are computed; the rest of y is zero
       NM_CUDA(cudaMemsetAsync(y, 0, ctx->n_space_dofs * sizeof(double), ctx->stream));
       ids = ctx->row_ids.as<uint32_t>();
     }
@@ -1000,10 +1079,10 @@ int nm_spmv_run(nm_ctx *ctx, int transpose, const double *x, double *y)
       else spmv_csr<1, 8, uint64_t><<<nm_blocks(n_rows, 128), 128, 0, NM_LS(ctx)>>>(n_rows, rp, cl, vl, x, y, ids);
     }
   } else {
-    NM_CUDA(cudaMemsetAsync(y, 0, ctx->n_im_dofs * sizeof(double), ctx->stream));
+    if (!local_out) NM_CUDA(cudaMemsetAsync(y, 0, ctx->n_im_dofs * sizeof(double), ctx->stream));
     const double avg = n_im ? (double)ctx->nnz / (double)n_im : 0;
     const uint64_t *rs = ctx->c_rowstart.as<uint64_t>();
-    const uint32_t *rl = ctx->c_rowlen.as<uint32_t>(), *cl = ctx->c_col.as<uint32_t>(), *idf = ctx->im_dofs.as<uint32_t>();
+    const uint32_t *rl = ctx->c_rowlen.as<uint32_t>(), *cl = ctx->c_col.as<uint32_t>(), *idf = local_out ? nullptr : ctx->im_dofs.as<uint32_t>();
     const double *vl = ctx->c_val.as<double>();
     if (n_im) {
       if (avg > 20) spmv_crows<4, 8><<<nm_blocks(n_im * 4, 256), 256, 0, NM_LS(ctx)>>>(n_im, rs, rl, cl, vl, idf, x, y);
@@ -1072,6 +1151,58 @@ int nm_c_rows_compact(nm_ctx *ctx, uint64_t *rowptr_dev, uint32_t *col_dev, doub
   if (n_im && col_dev)
     c_compact<8><<<nm_blocks(n_im * 8, 256), 256, 0, NM_LS(ctx)>>>(n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(),
                                                                  ctx->c_val.as<double>(), ctx->im_dofs.as<uint32_t>(), rowptr_dev, col_dev, val_dev);
+  NM_CUDA(cudaGetLastError());
+  return NM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// compact read-back of the stored orientation and vectors in local numbering
+// ---------------------------------------------------------------------------------------
+// List of the rows that hold entries: ctx->row_ids (compact-row mode: already there) or built here from the row
+// offsets (full-row mode) into ctx->out_ids / ctx->out_len.  Returns device pointers valid until the next matrix build.
+int nm_nonempty_rows(nm_ctx *ctx, uint64_t *n_rows_out, const uint32_t **ids_dev, const uint32_t **len_dev)
+{
+  const uint64_t n_rows = ctx->n_local_rows;
+  if (!ctx->out_rows_valid) {
+    uint64_t n_out = n_rows;
+    const uint64_t *pos = nullptr;
+    if (!ctx->compact_rows) {
+      NM_TRY(nm_ensure(ctx, ctx->scratch_a, (n_rows + 2) * sizeof(uint32_t)));
+      NM_TRY(nm_ensure(ctx, ctx->scratch_b, (n_rows + 2) * sizeof(uint64_t)));
+      nonempty_flags<<<nm_blocks(n_rows + 1, 256), 256, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr.as<uint64_t>(), ctx->scratch_a.as<uint32_t>());
+      NM_CUDA(cudaGetLastError());
+      NM_TRY(nm_exclusive_scan_u32_to_u64(ctx, ctx->scratch_a.as<uint32_t>(), ctx->scratch_b.as<uint64_t>(), n_rows + 1));
+      NM_CUDA(cudaMemcpyAsync(&n_out, ctx->scratch_b.as<uint64_t>() + n_rows, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      NM_SYNC(ctx);
+      pos = ctx->scratch_b.as<uint64_t>();
+    }
+    NM_TRY(nm_ensure(ctx, ctx->out_ids, (n_out + 1) * sizeof(uint32_t)));
+    NM_TRY(nm_ensure(ctx, ctx->out_len, (n_out + 1) * sizeof(uint32_t)));
+    if (n_rows) {
+      compact_rows_out<<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr.as<uint64_t>(), ctx->row_ids.as<uint32_t>(), pos,
+                                                                     ctx->out_ids.as<uint32_t>(), ctx->out_len.as<uint32_t>());
+      NM_CUDA(cudaGetLastError());
+    }
+    ctx->n_out_rows = n_out;
+    ctx->out_rows_valid = true;
+  }
+  if (n_rows_out) *n_rows_out = ctx->n_out_rows;
+  if (ids_dev) *ids_dev = ctx->out_ids.as<uint32_t>();
+  if (len_dev) *len_dev = ctx->out_len.as<uint32_t>();
+  return NM_OK;
+}
+
+// which = NM_LOCAL_IMMERSED: local entry m <-> global immersed dof im_dofs[m];  NM_LOCAL_ROWS: local entry r <-> dof of the
+// r-th non-empty row.  Device pointers.
+int nm_local_map(nm_ctx *ctx, int which, int to_global, const double *src, double *dst)
+{
+  uint64_t n = 0;
+  const uint32_t *idx = nullptr;
+  if (which == NM_LOCAL_IMMERSED) { n = ctx->n_im; idx = ctx->im_dofs.as<uint32_t>(); }
+  else NM_TRY(nm_nonempty_rows(ctx, &n, &idx, nullptr));
+  if (!n) return NM_OK;
+  if (to_global) scatter_by_index<<<nm_blocks(n, 256), 256, 0, NM_LS(ctx)>>>(n, idx, src, dst);
+  else gather_by_index<<<nm_blocks(n, 256), 256, 0, NM_LS(ctx)>>>(n, idx, src, dst);
   NM_CUDA(cudaGetLastError());
   return NM_OK;
 }

@@ -321,7 +321,7 @@ int nm_nitsche_run(nm_ctx *ctx, uint64_t n_pairs, const uint32_t *bg, const uint
     run_starts_kernel<<<nm_blocks(n + 1, 256), 256, 0, NM_LS(ctx)>>>(n, head, upos, start);
     NM_CUDA(cudaGetLastError());
     NM_CUDA(cudaMemcpyAsync(&n_cut, upos + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    NM_CUDA(cudaStreamSynchronize(ctx->stream));
+    NM_SYNC(ctx);
   }
   (void)id_in;
 
@@ -340,7 +340,7 @@ int nm_nitsche_run(nm_ctx *ctx, uint64_t n_pairs, const uint32_t *bg, const uint
   NM_CUDA(cudaMemcpyAsync(&tot[0], off_m + n_cut, 8, cudaMemcpyDeviceToHost, ctx->stream));
   NM_CUDA(cudaMemcpyAsync(&tot[1], off_r + n_cut, 8, cudaMemcpyDeviceToHost, ctx->stream));
   NM_CUDA(cudaMemcpyAsync(&bad, n_bad, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  NM_SYNC(ctx);
   if (bad) return nm_fail(ctx, NM_ERR_INVALID, "%llu background cell ids are out of range", bad);
   const uint64_t n_m = want_m ? tot[0] : 0, n_r = f_d ? tot[1] : 0;
 
@@ -384,7 +384,7 @@ int nm_nitsche_run(nm_ctx *ctx, uint64_t n_pairs, const uint32_t *bg, const uint
       NM_TRY(nm_exclusive_scan_u64(ctx, mhead, mupos, n_m + 1));
       uint64_t nu = 0;
       NM_CUDA(cudaMemcpyAsync(&nu, mupos + n_m, 8, cudaMemcpyDeviceToHost, ctx->stream));
-      NM_CUDA(cudaStreamSynchronize(ctx->stream));
+      NM_SYNC(ctx);
       ctx->nit_nnz = nu;
       NM_TRY(nm_ensure(ctx, ctx->nit_col, (nu + 1) * 4));
       NM_TRY(nm_ensure(ctx, ctx->nit_val, (nu + 1) * 8));
@@ -410,7 +410,7 @@ int nm_nitsche_run(nm_ctx *ctx, uint64_t n_pairs, const uint32_t *bg, const uint
       NM_CUDA(cudaGetLastError());
     }
   }
-  NM_CUDA(cudaStreamSynchronize(ctx->stream));
+  NM_SYNC(ctx);
   ctx->nit_has_matrix = want_m;
   ctx->nit_has_rhs = want_r;
   return NM_OK;

@@ -92,9 +92,10 @@ class FusedCtVmult:
     whole background vector.  `available` is False when symmetric memory cannot be set up; callers then
     keep the NCCL all-reduce of ShardedCouplingOperator."""
 
-    def __init__(self, ctx, group=None, prefer_multicast: bool = True):
+    def __init__(self, ctx, group=None, prefer_multicast: bool = True, device_barrier: bool = True):
         self.ctx, self.group = ctx, group
         self.available, self.reason, self.multicast = False, "", False
+        self.sync_kind = "host barriers (NCCL) around the kernel"
         try:
             import torch.distributed._symmetric_memory as symm_mem
             dev = torch.device("cuda", ctx.device)
@@ -105,9 +106,30 @@ class FusedCtVmult:
             mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
             self.multicast = bool(prefer_multicast and mc)
             self.targets = [mc] if self.multicast else self.ptrs
+            # the library launches on its own stream: zeroing, the rank barriers and the kernel are ordered on that
+            # stream, so no host synchronisation sits between them
+            self.stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+            self._dev_barrier = bool(device_barrier and hasattr(self.hdl, "barrier"))
+            if self._dev_barrier:
+                self.sync_kind = "device-side rank barriers in symmetric memory, stream-ordered with the kernel"
+            self.y.zero_()
+            torch.cuda.synchronize()
             self.available = True
         except Exception as e:  # no symmetric memory on this system: keep NCCL
             self.reason = "%s: %s" % (type(e).__name__, str(e)[:200])
+
+    def _barrier(self):
+        """All ranks have reached this point of the library stream.  Device side (signal pads of the symmetric-memory
+        handle) when the handle offers it; otherwise the host waits for the stream and the ranks meet in NCCL."""
+        if self._dev_barrier:
+            try:
+                self.hdl.barrier(channel=0)
+                return
+            except Exception:     # API not usable on this build: the same on every rank, so all fall back together
+                self._dev_barrier = False
+                self.sync_kind = "host barriers (NCCL) around the kernel"
+        torch.cuda.current_stream().synchronize()
+        dist.barrier(group=self.group)
 
     def vmult_owned(self, lam: torch.Tensor) -> torch.Tensor:
         """The slice of y = A lam this rank owns (contiguous dof ranges, `owned_dof_range`): every row result crosses
@@ -115,19 +137,23 @@ class FusedCtVmult:
         buffer.  Only the owned slice is zeroed and valid."""
         world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         lo, hi = owned_dof_range(self.ctx.n_space_dofs, rank, world)
-        self.y[lo:hi].zero_()
-        torch.cuda.synchronize()
-        dist.barrier(group=self.group)
-        self.ctx.spmv_push_owned(lam, self.ptrs, rows_per_rank(self.ctx.n_space_dofs, world))
-        dist.barrier(group=self.group)
+        torch.cuda.current_stream().synchronize()          # lam is ready
+        with torch.cuda.stream(self.stream):
+            self.y[lo:hi].zero_()
+            self._barrier()                                # every owner has cleared its slice
+            self.ctx.spmv_push_owned(lam, self.ptrs, rows_per_rank(self.ctx.n_space_dofs, world), sync_producer=False)
+            self._barrier()                                # every rank's adds have been issued and have landed
+        torch.cuda.current_stream().wait_stream(self.stream)
         return self.y[lo:hi]
 
     def vmult(self, lam: torch.Tensor) -> torch.Tensor:
         """Replicated y = A lam on every rank.  Two rank barriers bracket the kernel: all vectors are zero
         before anyone adds, and everyone's adds have landed before anyone reads."""
-        self.y.zero_()
-        torch.cuda.synchronize()
-        dist.barrier(group=self.group)
-        self.ctx.spmv_push(lam, self.targets, multicast=self.multicast)
-        dist.barrier(group=self.group)
+        torch.cuda.current_stream().synchronize()
+        with torch.cuda.stream(self.stream):
+            self.y.zero_()
+            self._barrier()
+            self.ctx.spmv_push(lam, self.targets, multicast=self.multicast, sync_producer=False)
+            self._barrier()
+        torch.cuda.current_stream().wait_stream(self.stream)
         return self.y

@@ -151,15 +151,16 @@ def flower_grid(n_bisections: int = 0, device="cpu") -> ImmersedGrid:
 
 
 def sphere_grid(n_per_edge: int, R: float = 0.3, center=(0.5, 0.5, 0.5), device="cpu",
-                patches=range(6)) -> ImmersedGrid:
+                patches=range(6), rows: Optional[int] = None) -> ImmersedGrid:
     """hyper_sphere<2,3>: six patches of the projected cube, n x n bilinear quads each with
-    vertices on the sphere (equi-angular spacing along patch edges)."""
+    vertices on the sphere (equi-angular spacing along patch edges).  `rows` keeps only the first
+    rows of every patch (a sample of the grid, bit-identical to the same cells of the whole one)."""
     n = n_per_edge
     t = torch.tan(math.pi / 4 * (2.0 * torch.arange(n + 1, dtype=F64, device=device) / n - 1.0))
     t[0], t[-1] = -1.0, 1.0
     if n % 2 == 0:
         t[n // 2] = 0.0
-    a, b = torch.meshgrid(t, t, indexing="ij")
+    a, b = torch.meshgrid(t if rows is None else t[:min(n, rows) + 1], t, indexing="ij")
     one = torch.ones_like(a)
     faces = [
         (one, a, b), (-one, b, a),      # +x, -x
@@ -583,24 +584,50 @@ def _exchange_keys(local: torch.Tensor) -> torch.Tensor:
 
 
 def weak_scaling_sizes(name: str, cycle: int, world: int) -> Tuple[int, Optional[int]]:
-    """(background cycle, immersed resolution override) such that every rank keeps roughly the
-    single-GPU number of immersed cells: the immersed grid gets `world` times the cells, the
-    background follows with whole refinement levels."""
+    """(refinement cycle, immersed resolution override) of the global problem on `world` GPUs.  Every size is a TRUE
+    refinement cycle of the named configuration (BASELINE.json: "synthetic refinements of the named configs"): the
+    sphere gains one cycle (4x the pairs) per factor 4 of GPUs, rounded up, so that 1 / 2 / 4 / 8 GPUs run cycles
+    c / c+1 / c+1 / c+2 -- with c = 8 that is 6.4e7 pairs on one GPU (configs[3]) and 1.0e9 pairs on eight
+    (configs[4]); a rank holds either the single-GPU number of immersed cells or twice that.  The 2D curves gain one
+    cycle (2x the pairs) per factor 2."""
     if world == 1:
         return cycle, None
     if name == "sphere":
-        n = int(round(4 * (1 << cycle) * math.sqrt(world)))
-        n += n % 2                                    # even: the equator stays a grid line
-        return cycle + int(math.floor(math.log2(n / (4 * (1 << cycle))) + 1e-9)), n
+        k = int(math.ceil(math.log2(world) / 2.0 - 1e-9))
+        return cycle + k, 4 * (1 << (cycle + k))
+    k = int(math.ceil(math.log2(world) - 1e-9))
     if name == "disk":
-        n = 32 * (1 << cycle) * world
-        return cycle + int(math.floor(math.log2(world) + 1e-9)), n
-    k = int(math.floor(math.log2(world) + 1e-9))      # flower: bisections only
-    return cycle + k, cycle + k
+        return cycle + k, 32 * (1 << (cycle + k))
+    return cycle + k, cycle + k                        # flower: bisections only
+
+
+def sample_problem(name: str, cycle: int, n_cells: int, device="cpu"):
+    """A bounded SAMPLE of config `name` at refinement `cycle`: the first `n_cells` immersed cells of the true grid of
+    that cycle and the band of background cells near them, at the true mesh sizes of that cycle (used by the CPU
+    baseline / reference arm of bench.py, which cannot afford the whole workload)."""
+    cfg = CONFIGS[name]
+    d = cfg["d"]
+    if name == "disk":
+        im0, im = circle_grid(32, device=device), circle_grid(32 * (1 << cycle), device=device)
+    elif name == "flower":
+        im0, im = flower_grid(0, device=device), flower_grid(cycle, device=device)
+    else:
+        n = 4 * (1 << cycle)
+        im0 = sphere_grid(2, device=device)
+        if n_cells >= n * n:
+            im = sphere_grid(n, device=device, patches=range(min(6, -(-n_cells // (n * n)))))
+        else:
+            im = sphere_grid(n, device=device, patches=[0], rows=-(-n_cells // n))   # the first rows of the +x patch
+    n_global = {"disk": 32 * (1 << cycle), "flower": 256 * (1 << cycle), "sphere": 6 * (4 * (1 << cycle)) ** 2}[name]
+    k = min(n_cells, im.n_cells)
+    im = ImmersedGrid(im.dim, im.spacedim, im.verts[:k].clone(), im.dofs[:k].clone(), n_global)
+    lmap = build_level_map(d, 4, cfg["band_rounds"], *im0.boxes())
+    bg = background_grid(lmap, cycle, near=im.boxes(), want_coords=False)
+    return bg, im
 
 
 def shard_problem(name: str, cycle: int, rank: int = 0, world: int = 1, device="cpu", weak: bool = False,
-                  want_coords: bool = True):
+                  want_coords: bool = True, standalone: bool = False):
     """This rank's share of config `name`: a contiguous range of immersed cells and the background
     cells near them, with global DoF numbering.
 
@@ -632,7 +659,9 @@ def shard_problem(name: str, cycle: int, rank: int = 0, world: int = 1, device="
     first, last = shard_range(n_global, rank, world)
     im = ImmersedGrid(im.dim, im.spacedim, im.verts[first:last].clone(), im.dofs[first:last].clone(), im.n_dofs)
     lmap = build_level_map(d, 4, cfg["band_rounds"], *im0.boxes())
-    bg = background_grid(lmap, bg_cycle, near=im.boxes(), key_exchange=_exchange_keys, want_coords=want_coords)
+    # standalone: this rank's share generated without a process group (its own dof numbering): one rank of a
+    # `world`-GPU run reproduced on a single GPU, e.g. to size its memory
+    bg = background_grid(lmap, bg_cycle, near=im.boxes(), key_exchange=None if standalone else _exchange_keys, want_coords=want_coords)
     info = {"global_immersed_cells": n_global, "background_dofs": bg.n_dofs, "background_cycle": bg_cycle,
             "immersed_resolution": n_im, "rank0_background_cells": bg.n_cells, "rank0_immersed_cells": im.n_cells}
     return bg, im, info

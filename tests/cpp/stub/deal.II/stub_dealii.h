@@ -177,6 +177,18 @@ public:
     return it == lines.end() ? nullptr : &it->second;
   }
   size_type n_constraints() const { return lines.size(); }
+  // deal.II: AffineConstraints::get_lines() -> range of ConstraintLine {index, entries, inhomogeneity}, sorted by index
+  struct ConstraintLine {
+    size_type index;
+    std::vector<std::pair<size_type, number>> entries;
+    number inhomogeneity;
+  };
+  std::vector<ConstraintLine> get_lines() const
+  {
+    std::vector<ConstraintLine> r;
+    for (const auto &l : lines) r.push_back({l.first, l.second, number(0)});
+    return r;
+  }
 };
 
 class ComponentMask {
@@ -209,6 +221,25 @@ public:
   void compress(VectorOperation::values) { compressed = true; }
   unsigned rows, cols;
   std::vector<std::map<types::global_dof_index, T>> data;
+  bool compressed = false;
+};
+// Append-only sink with the add()/compress() shape of a deal.II matrix: what a timing run needs (no per-entry map).
+template <typename T> class StubFlatMatrix {
+public:
+  using value_type = T;
+  StubFlatMatrix(unsigned r, unsigned c) : rows(r), cols(c) {}
+  unsigned m() const { return rows; }
+  unsigned n() const { return cols; }
+  void add(types::global_dof_index row, types::global_dof_index n_cols, const types::global_dof_index *c, const T *v, bool elide_zero = true,
+           bool = false)
+  {
+    for (unsigned k = 0; k < n_cols; ++k)
+      if (!elide_zero || v[k] != T(0)) { r_.push_back(row); c_.push_back(c[k]); v_.push_back(v[k]); }
+  }
+  void compress(VectorOperation::values) { compressed = true; }
+  unsigned rows, cols;
+  std::vector<types::global_dof_index> r_, c_;
+  std::vector<T> v_;
   bool compressed = false;
 };
 } // namespace dealii

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared():
     hdr = open(os.path.join(ROOT, "include", "nmgpu.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    return sorted(set(re.findall(r"\b(nm_[a-z_]+)\s*\(", hdr)))
+    return sorted(set(re.findall(r"\b(nm_[a-z_0-9]+)\s*\(", hdr)))
 
 
 def test_header_symbols_are_exported():

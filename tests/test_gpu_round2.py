@@ -1,0 +1,199 @@
+"""GPU tests of what round 2 added: the brick candidate index against the chain index, the compact read-back and the
+products in local numbering against the global forms, the asynchronous read-back, the merge-path flag the advisor
+found uninitialised, and the multi-GPU check as a test (skipped below 2 GPUs)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from non_matching_test_suite_b200 import _lib, coupling
+from non_matching_test_suite_b200.grids import make_config, circle_grid
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _keys(im, bg):
+    return (im.numpy().astype(np.uint64) << np.uint64(32)) | bg.numpy().astype(np.uint32).astype(np.uint64)
+
+
+@pytest.mark.parametrize("name,cycle,band", [("disk", 3, False), ("flower", 2, False), ("sphere", 1, False), ("sphere", 4, True), ("flower", 8, True)])
+def test_brick_index_equals_chain_index(monkeypatch, c_oracle, name, cycle, band):
+    """Grid-aligned trees take the brick index; its candidate list is the chain index's, entry by entry, and both are
+    the oracle's closed-box set."""
+    bg, im = make_config(name, cycle, band_only=band)
+    ctx = coupling.make_context(bg, im, boxes=True)
+    ctx.intersect(3, 1e-15)
+    assert ctx.info("index_kind") == 2
+    k_brick = _keys(*ctx.candidates())
+    ctx.close()
+    monkeypatch.setenv("NMGPU_INDEX", "chains")
+    ctx = coupling.make_context(bg, im, boxes=True)
+    ctx.intersect(3, 1e-15)
+    assert ctx.info("index_kind") == 1
+    k_chain = _keys(*ctx.candidates())
+    ctx.close()
+    assert np.array_equal(k_brick, k_chain)
+    ilo, ihi = im.boxes()
+    assert np.array_equal(k_brick, c_oracle.candidates(bg.lo, bg.hi, ilo, ihi))
+
+
+def test_brick_index_refuses_what_it_cannot_verify():
+    """Boxes that are not cells of one grid (random sizes, overlapping) fail the per-cell verification and the chain
+    index takes over without the caller noticing."""
+    from test_gpu_parity import _random_problem
+    bg, im = _random_problem(3, 2000, 300, seed=5)
+    ctx = coupling.make_context(bg, im, boxes=True)
+    c = ctx.intersect(3, 1e-15)
+    assert ctx.info("index_kind") == 1 and c["n_candidates"] > 1000
+    ctx.close()
+    # a tree whose coordinates are NOT dyadic: [0, 0.3]^2 refined -- cells are grid cells only up to rounding
+    n = 37
+    g = 0.3 / n
+    ii, jj = torch.meshgrid(torch.arange(n, dtype=torch.float64), torch.arange(n, dtype=torch.float64), indexing="ij")
+    lo = torch.stack([ii.reshape(-1) * g, jj.reshape(-1) * g], 1)
+    hi = torch.stack([(ii.reshape(-1) + 1) * g, (jj.reshape(-1) + 1) * g], 1)
+    from non_matching_test_suite_b200.grids import BackgroundGrid
+    e = torch.empty(0, dtype=torch.int32)
+    dofs = torch.arange(n * n * 4, dtype=torch.int32).reshape(-1, 4)
+    bg2 = BackgroundGrid(2, lo, hi, dofs, n * n * 4, torch.zeros(n * n, dtype=torch.int32), e, torch.zeros(1, dtype=torch.int64), e,
+                         torch.empty(0, dtype=torch.float64))
+    im2 = circle_grid(64, R=0.1, center=(0.15, 0.15))
+    ctx = coupling.make_context(bg2, im2, boxes=True)
+    ctx.intersect(3, 1e-15)
+    got = _keys(*ctx.candidates())
+    ilo, ihi = im2.boxes()
+    ov = ((bg2.lo[None] <= ihi[:, None]) & (ilo[:, None] <= bg2.hi[None])).all(-1)        # [im, bg] brute force on the raw doubles
+    want = np.array([(m << 32) | b for m, b in torch.nonzero(ov).tolist()], dtype=np.uint64)
+    assert np.array_equal(got, want)          # whichever index ran, the set is the closed-box set
+    ctx.close()
+
+
+@pytest.mark.parametrize("name,cycle", [("disk", 2), ("sphere", 2)])
+@pytest.mark.parametrize("compact", ["0", "1"])
+def test_compact_readback_and_local_products(monkeypatch, name, cycle, compact):
+    monkeypatch.setenv("NMGPU_COMPACT_ROWS", compact)
+    bg, im = make_config(name, cycle, band_only=True)
+    ctx = coupling.make_context(bg, im, boxes=True)
+    ctx.intersect(3, 1e-15)
+    rp, col, val = ctx.csr()
+    ids, ln, col_c, val_c = ctx.csr_compact()
+    lens = (rp[1:] - rp[:-1])
+    nz = torch.nonzero(lens).flatten()
+    assert torch.equal(ids.long(), nz) and torch.equal(ln.long(), lens[nz])
+    assert torch.equal(col_c, col) and torch.equal(val_c, val)
+    assert ctx.n_rows_local() == nz.numel() and ctx.info("compact_rows") == int(compact)
+    # products in local numbering = the global products restricted to the local entries
+    g = torch.Generator().manual_seed(3)
+    x_loc = torch.rand(im.n_cells, dtype=torch.float64, generator=g)
+    u_loc = torch.rand(nz.numel(), dtype=torch.float64, generator=g)
+    x_glob = torch.zeros(im.n_dofs, dtype=torch.float64); x_glob[im.dofs.long().flatten()] = x_loc
+    u_glob = torch.zeros(bg.n_dofs, dtype=torch.float64); u_glob[nz] = u_loc
+    y = ctx.spmv(x_glob, transpose=False)
+    z = ctx.spmv(u_glob, transpose=True)
+    y_loc = ctx.spmv_local(x_loc, transpose=False)
+    z_loc = ctx.spmv_local(u_loc, transpose=True)
+    assert torch.equal(y_loc, y[nz]) and torch.equal(z_loc, z[im.dofs.long().flatten()])
+    # device vectors, and the scatter / gather helpers
+    yd = ctx.spmv_local(x_loc.cuda(), transpose=False)
+    assert torch.equal(yd.cpu(), y_loc)
+    gl = torch.full((bg.n_dofs,), -7.0, dtype=torch.float64, device="cuda")
+    ctx.local_to_global(_lib.NM_LOCAL_ROWS, u_loc, gl)
+    assert torch.equal(gl.cpu()[nz], u_loc) and float((gl.cpu() == -7.0).sum()) == bg.n_dofs - nz.numel()
+    back = torch.empty(nz.numel(), dtype=torch.float64)
+    ctx.global_to_local(_lib.NM_LOCAL_ROWS, gl, back)
+    assert torch.equal(back, u_loc)
+    ctx.close()
+
+
+def test_asynchronous_readback_overlaps_the_next_assembly():
+    """nm_get_csr_compact(NM_HOST_ASYNC): the matrix of step k is complete after nm_sync_downloads even though the next
+    assembly on the same context was started in between."""
+    bg, im = make_config("sphere", 3, band_only=True)
+    bg2, im2 = make_config("sphere", 2, band_only=True)
+    ctx = coupling.make_context(bg, im, boxes=True)
+    ctx.intersect(3, 1e-15)
+    want = [t.clone() for t in ctx.csr_compact()]
+    nnz = ctx.nnz
+    bufs = (torch.empty(want[0].numel() + 8, dtype=torch.int32).pin_memory(), torch.empty(want[0].numel() + 8, dtype=torch.int32).pin_memory(),
+            torch.empty(nnz + 8, dtype=torch.int32).pin_memory(), torch.empty(nnz + 8, dtype=torch.float64).pin_memory())
+    got = ctx.csr_compact(out=bufs, asynchronous=True)
+    coupling.set_grids(ctx, bg2, im2, boxes=True)         # the next problem on the same context, before the copies are waited for
+    ctx.intersect(3, 1e-15)
+    ctx.build_sparsity()
+    ctx.sync_downloads()
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        ctx.csr_compact(out=tuple(t.clone() for t in want), asynchronous=True)      # pageable buffers are refused
+    ctx.close()
+
+
+def test_merge_path_flag_is_reset_after_a_fallback():
+    """the `problem` flag of the single-pass merge was never cleared, so one overflow sent every later
+    build of the context through both merges.  Force one fallback, then expect the fast path again."""
+    bg, _ = make_config("disk", 4, band_only=False)
+    ctx = coupling.make_context(bg, circle_grid(8), boxes=True)      # 8 long segments: > 48 distinct dofs per immersed cell
+    ctx.intersect(3, 1e-15)
+    ctx.build_sparsity()
+    assert ctx.info("merge_path") == 1
+    bg4, im4 = make_config("disk", 4, band_only=False)
+    coupling.set_grids(ctx, bg4, im4, boxes=True)
+    ctx.intersect(3, 1e-15)
+    ctx.build_sparsity()
+    assert ctx.info("merge_path") == 0
+    fresh = coupling.make_context(bg4, im4, boxes=True)               # a brand-new context starts from cleared flags
+    fresh.intersect(3, 1e-15)
+    fresh.build_sparsity()
+    assert fresh.info("merge_path") == 0
+    assert torch.equal(fresh.csr()[2], ctx.csr()[2])
+    ctx.close(); fresh.close()
+
+
+def test_from_quadrature_accumulates_repeated_pairs_and_checks_ranges():
+    """the same (space cell, immersed cell) pair given twice must add up like the reference's
+    distribute_local_to_global does per tuple (coupling_utilities.h:285-287); out-of-range dof tables are refused."""
+    bg, im = make_config("disk", 1, band_only=False)
+    info = coupling.collect_quadratures_on_overlapped_grids(bg, im, 3, 1e-15)
+    ctx = info.ctx
+    _, _, val_once = ctx.csr()
+    # every tuple split in two halves of its points, given as two tuples of the same pair
+    off = info.q_offset
+    n = len(info)
+    im2 = torch.cat([info.immersed_cell, info.immersed_cell]); bg2 = torch.cat([info.space_cell, info.space_cell])
+    first = (off[1:] - off[:-1]) // 2
+    cnt = torch.cat([first, (off[1:] - off[:-1]) - first])
+    off2 = torch.zeros(2 * n + 1, dtype=torch.int64); off2[1:] = torch.cumsum(cnt, 0)
+    idx = torch.cat([torch.cat([torch.arange(int(off[i]), int(off[i] + first[i])) for i in range(n)]),
+                     torch.cat([torch.arange(int(off[i] + first[i]), int(off[i + 1])) for i in range(n)])])
+    ctx.assemble_from_quadrature(im2.contiguous(), bg2.contiguous(), off2, info.points[idx].contiguous(), info.weights[idx].contiguous())
+    _, _, val_twice = ctx.csr()
+    assert (val_twice - val_once).norm() <= 1e-13 * val_once.norm()
+    bad = bg.dofs.clone(); bad[0, 0] = bg.n_dofs + 5
+    ctx.set_background_dofs(bad.to(torch.int32).contiguous(), bg.n_dofs)
+    with pytest.raises(_lib.NmError) as e:      # checked before the merge dereferences the table
+        ctx.build_sparsity()
+    assert e.value.code == 1 and "DoF table" in str(e.value)
+    ctx.close()
+
+
+def test_fp64_peak_is_measured():
+    ctx = _lib.Context(0)
+    p = ctx.measure_fp64_peak(5.0)
+    assert 5e12 < p < 1e14, p          # B200: ~37-40 TFLOP/s FP64
+    ctx.close()
+
+
+def test_fused_ct_vmult_on_two_gpus():
+    """tests/multi_gpu_check.py under torchrun: fused Ct.vmult (replicated and owned) against SpMV + NCCL.  Needs 2 GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    port = 29600 + os.getpid() % 300
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(ROOT, "tests", "multi_gpu_check.py"), "4"],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    assert "rel err" in r.stdout
