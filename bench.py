@@ -506,13 +506,16 @@ def run_problem(args, torch, dist, _lib, ctx, P, rank, world, local, dev, peak, 
     if "fp64" not in roofline:
         roofline["fp64"] = {"flops": None, "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "frac": None,
                             "peak_source": "nm_measure_fp64_peak (DFMA chains, this run)"}
-    # SpMV bytes: entries + the rows / columns this rank really touches (not the global vector lengths)
-    a_bytes = 12 * nnz + 16 * n_rows + 8 * P.n_im
+    # SpMV bytes: entries + the rows the kernel walks (all dofs in full-row mode, the touched ones in compact-row mode: never
+    # the global dof count of a sharded run) + the vector entries this rank's columns address
+    stored_rows = ctx.info("stored_rows")
+    a_bytes = 12 * nnz + 16 * stored_rows + 8 * P.n_im
     c_bytes = 12 * nnz + 16 * P.n_im + 8 * n_rows
     spmv = {"Ct_vmult_GBs": a_bytes / (phases["spmv"] * 1e-3) / 1e9 if phases["spmv"] > 0 else None,
             "C_Tvmult_GBs": c_bytes / (phases["spmv_t"] * 1e-3) / 1e9 if phases["spmv_t"] > 0 else None,
-            "nnz": nnz, "stored_rows_with_entries": n_rows, "immersed_cells": P.n_im,
-            "bytes_formula": "12*nnz + 16*n_rows + 8*n_cols with the rows / columns this rank holds entries in",
+            "nnz": nnz, "stored_rows": stored_rows, "stored_rows_with_entries": n_rows, "immersed_cells": P.n_im,
+            "bytes_formula": "Ct.vmult: 12*nnz + 16*stored_rows + 8*immersed_cells; C.Tvmult: 12*nnz + 16*immersed_cells + 8*rows_with_entries "
+                             "(stored_rows = rows the kernel walks: every dof of this rank's background in full-row mode, touched dofs in compact-row mode)",
             "note": "per rank, kernel only (the cross-GPU reduction is inside the fused Ct.vmult kernel when it is used)"}
     spmv["Ct_vmult_frac_hbm"] = spmv["Ct_vmult_GBs"] / peak if spmv["Ct_vmult_GBs"] else None
     spmv["C_Tvmult_frac_hbm"] = spmv["C_Tvmult_GBs"] / peak if spmv["C_Tvmult_GBs"] else None

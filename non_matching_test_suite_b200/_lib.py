@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnmgpu.so")
+LIB_PATH = os.environ.get("NMGPU_LIB") or os.path.join(_HERE, "libnmgpu.so")   # NMGPU_LIB: another build of the same library (kernel experiments)
 
 NM_HOST, NM_DEVICE, NM_HOST_ASYNC = 0, 1, 2
 NM_LOCAL_IMMERSED, NM_LOCAL_ROWS = 0, 1

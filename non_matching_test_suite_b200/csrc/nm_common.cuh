@@ -31,6 +31,7 @@ struct HashSlot {
 struct GridIndex {
   int d = 0;
   double org[3] = {0, 0, 0};
+  double brick_org[3] = {0, 0, 0};   // origin shared by the grids of all levels (brick index)
   double g0 = 0;            // spacing of level 0
   uint32_t level_mask = 0;  // bit k: level k holds cells
   uint32_t n_entries = 0;
@@ -78,6 +79,7 @@ struct nm_ctx {
   DevBuf idx_extra_bg;  // background id of entry ids >= n_bg
   DevBuf idx_hash, idx_tmp;
   DevBuf brk_hdr, brk_bit;  // brick index: header (levels, origins, flags), bit of every cell inside its brick
+  bool brick_roomy = false;        // the brick table was sized so that it cannot overflow
   bool force_chain_index = false;  // NMGPU_INDEX=chains: skip the brick index (testing)
 
   // ---- intersection results ----

@@ -100,6 +100,7 @@ __global__ void fill_line_of(uint64_t n_c, const uint32_t *__restrict__ c_dof, i
 // per-block partial min of lo, min positive extent, max hi  -> out[block][8]
 struct BoxStats {
   double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY}, g = INFINITY, gm = 0;
+  double gml[3] = {0, 0, 0};   // lower corner of one cell of the largest extent (anchors the grid of every level)
   template <int D> __device__ __forceinline__ void add(const double *lo, const double *hi)
   {
     double e = 0;
@@ -110,22 +111,36 @@ struct BoxStats {
       e = fmax(e, hi[k] - lo[k]);
     }
     if (e > 0) g = fmin(g, e);
-    gm = fmax(gm, e);
+    if (e > gm) {
+      gm = e;
+#pragma unroll
+      for (int k = 0; k < D; ++k) gml[k] = lo[k];
+    }
   }
   __device__ inline void reduce_to(double *__restrict__ out) const;
 };
+
+constexpr int NM_STATS_W = 12;   // doubles per block: min lo (3), max hi (3), min extent, max extent, corner of a coarsest cell (3), pad
 
 __device__ inline void BoxStats::reduce_to(double *__restrict__ out) const
 {
   typedef cub::BlockReduce<double, 256> BR;
   __shared__ typename BR::TempStorage tmp;
+  __shared__ double s_gm, s_gml[3];
   double r[8];
   for (int k = 0; k < 3; ++k) { r[k] = BR(tmp).Reduce(mn[k], cub::Min()); __syncthreads(); }
   for (int k = 0; k < 3; ++k) { r[3 + k] = BR(tmp).Reduce(mx[k], cub::Max()); __syncthreads(); }
   r[6] = BR(tmp).Reduce(g, cub::Min()); __syncthreads();
   r[7] = BR(tmp).Reduce(gm, cub::Max());
-  if (threadIdx.x == 0)
-    for (int k = 0; k < 8; ++k) out[blockIdx.x * 8 + k] = r[k];
+  if (threadIdx.x == 0) { s_gm = r[7]; s_gml[0] = s_gml[1] = s_gml[2] = 0; }
+  __syncthreads();
+  if (gm == s_gm && gm > 0) { s_gml[0] = gml[0]; s_gml[1] = gml[1]; s_gml[2] = gml[2]; }   // any one of the coarsest cells (benign race)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 8; ++k) out[blockIdx.x * NM_STATS_W + k] = r[k];
+    for (int k = 0; k < 3; ++k) out[blockIdx.x * NM_STATS_W + 8 + k] = s_gml[k];
+    out[blockIdx.x * NM_STATS_W + 11] = 0;
+  }
 }
 
 // lo/hi corners -> 64-byte boxes, with the extent statistics of the grid index taken in the same pass
@@ -382,15 +397,16 @@ __global__ void cand_place(GridDev G, uint64_t n_im, const double *__restrict__ 
 // brick index: the fast path for grid-aligned trees (every reference configuration)
 // ---------------------------------------------------------------------------------------
 // A background cell of a hyper_cube refinement occupies exactly one cell of the uniform grid of its
-// own level, and its corners are c(i) = org_k + i * g_k bit for bit.  When that holds for every cell
-// (verified below, cell by cell, on the raw doubles) the grid cells are grouped into bricks of 64
-// (4x4x4, 8x8 in 2D): one 32-byte hash slot per occupied brick carries a 64-bit occupancy mask and the
-// offset of the brick's cell ids, which are stored in bit order.  A query then costs one slot per
-// brick (<= 8 per level instead of 27..64 per-cell slots), the occupied slots of a surface band fit in
-// L2, and the closed-box test needs no box at all: it is done once per axis on the reconstructed
-// corners, which ARE the raw doubles, so the candidate set is still exactly the reference's
-// (coupling_utilities.cc:53-55).  Any cell that fails the verification, two cells in one grid cell, or
-// an overfull table raise `bad`, and the per-cell chain index above takes over.
+// own level, and its corners are c(i) = org + i * g_k bit for bit (one origin for all levels:
+// nmbrick::aligned_origin).  When that holds for every cell (verified below, cell by cell, on the raw
+// doubles) the grid cells are grouped into bricks of 64 (4x4x4, 8x8 in 2D): one 32-byte hash slot per
+// occupied brick carries a 64-bit occupancy mask and the offset of the brick's cell ids, which are
+// stored in bit order.  A query then costs one slot per brick (<= 8 per level instead of 27..64 per-cell
+// slots), the occupied slots of a surface band fit in L2, and the closed-box test needs no box at all:
+// it is done once per axis on the reconstructed corners, which ARE the raw doubles, so the candidate
+// set is still exactly the reference's (coupling_utilities.cc:53-55).  Any cell that fails the
+// verification, two cells in one grid cell, or an overfull table raise `bad`, and the per-cell chain
+// index above takes over.
 struct BrickSlot {
   unsigned long long key;   // packed (level, bx, by, bz); ~0 = empty
   unsigned long long mask;  // occupied grid cells of the brick
@@ -400,10 +416,9 @@ struct BrickSlot {
 };
 
 struct BrickHeader {
-  unsigned long long lvl_min[32][3];  // per level and axis: smallest lower corner, order-preserving encoding
-  unsigned level_mask;
-  unsigned bad;
-  unsigned long long cursor;
+  unsigned level_mask;        // levels that hold cells
+  unsigned bad;               // 1: a cell is not a grid cell, 2: table overfull, 4: two cells in one grid cell
+  unsigned long long cursor;  // ids handed out so far
 };
 
 struct BrickDev {
@@ -411,52 +426,24 @@ struct BrickDev {
   uint32_t slot_mask;   // capacity - 1
   uint32_t *ids;
   BrickHeader *hdr;
-  double g0;
+  double org[3];
+  double g0, inv0;
   int idx_bits;
 };
 
-template <int D>
-__device__ __forceinline__ unsigned long long brick_key(int level, long long bx, long long by, long long bz)
+__device__ __forceinline__ double pow2_neg(int k) { return __hiloint2double((1023 - k) << 20, 0); }   // 2^-k, 0 <= k < 1023
+
+__device__ __forceinline__ uint32_t brick_hash(unsigned long long key)
 {
-  return pack_key(D, level, bx, by, bz);
+  uint32_t h = (uint32_t)key * 0x9E3779B1u ^ ((uint32_t)(key >> 32) * 0x85EBCA77u);
+  h ^= h >> 15; h *= 0xC2B2AE3Du; h ^= h >> 13;
+  return h;
 }
 
-// levels present and the per-level origin
 template <int D>
-__global__ void __launch_bounds__(256) brick_levels(double g0, uint64_t n, const double *__restrict__ box, BrickHeader *hdr)
+__device__ __forceinline__ unsigned long long brick_key(int level, int bx, int by, int bz)
 {
-  __shared__ unsigned long long s_min[32][3];
-  __shared__ unsigned s_mask;
-  for (int i = threadIdx.x; i < 96; i += blockDim.x) s_min[i / 3][i % 3] = ~0ULL;
-  if (threadIdx.x == 0) s_mask = 0;
-  __syncthreads();
-  int cur = -1;
-  unsigned long long mn[3] = {~0ULL, ~0ULL, ~0ULL};
-  unsigned bits = 0;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    const double *b = box + i * 8;
-    double e = 0;
-#pragma unroll
-    for (int k = 0; k < D; ++k) e = fmax(e, b[4 + k] - b[k]);
-    const int level = level_of(e, g0);
-    if (level != cur) {
-      if (cur >= 0)
-        for (int k = 0; k < D; ++k) atomicMin(&s_min[cur][k], mn[k]);
-      cur = level;
-      mn[0] = mn[1] = mn[2] = ~0ULL;
-      bits |= 1u << level;
-    }
-#pragma unroll
-    for (int k = 0; k < D; ++k) { const unsigned long long v = nmbrick::ord_encode(b[k]); mn[k] = v < mn[k] ? v : mn[k]; }
-  }
-  if (cur >= 0)
-    for (int k = 0; k < D; ++k) atomicMin(&s_min[cur][k], mn[k]);
-  if (bits) atomicOr(&s_mask, bits);
-  __syncthreads();
-  const unsigned m = s_mask;
-  for (int i = threadIdx.x; i < 96; i += blockDim.x)
-    if (((m >> (i / 3)) & 1u) && (i % 3) < D) atomicMin(&hdr->lvl_min[i / 3][i % 3], s_min[i / 3][i % 3]);
-  if (threadIdx.x == 0 && m) atomicOr(&hdr->level_mask, m);
+  return pack_key(D, level, bx, by, bz);
 }
 
 __global__ void brick_clear(BrickSlot *s, uint32_t cap)
@@ -470,47 +457,65 @@ template <int D>
 __global__ void __launch_bounds__(256) brick_insert(BrickDev B, uint64_t n, const double *__restrict__ box, uint32_t *__restrict__ cell_slot,
                                                     uint8_t *__restrict__ cell_bit)
 {
+  __shared__ unsigned s_levels;
+  if (threadIdx.x == 0) s_levels = 0;
+  __syncthreads();
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
   constexpr int SH = nmbrick::BrickShape<D>::SH;
-  const double *b = box + i * 8;
-  double e = 0;
+  unsigned my_level_bit = 0;
+  if (i < n) {
+    const double *b = box + i * 8;
+    double e = 0;
 #pragma unroll
-  for (int k = 0; k < D; ++k) e = fmax(e, b[4 + k] - b[k]);
-  const int level = level_of(e, B.g0);
-  const double g = B.g0 * (double)(1ULL << level), inv = 1.0 / g;
-  long long idx[3] = {0, 0, 0};
-  bool ok = true;
-  const long long lim = 1LL << B.idx_bits;
+    for (int k = 0; k < D; ++k) e = fmax(e, b[4 + k] - b[k]);
+    const int level = nmbrick::level_of_extent(e, B.g0);
+    const double g = B.g0 * (double)(1u << level), inv = B.inv0 * pow2_neg(level);
+    int idx[3] = {0, 0, 0};
+    bool ok = true;
+    const int lim = 1 << B.idx_bits;
 #pragma unroll
-  for (int k = 0; k < D; ++k) {
-    const double org = nmbrick::ord_decode(B.hdr->lvl_min[level][k]);
-    const long long j = llrint((b[k] - org) * inv);
-    ok &= j >= 0 && j < lim - 1 && nmbrick::grid_corner(org, j, g) == b[k] && nmbrick::grid_corner(org, j + 1, g) == b[4 + k];
-    idx[k] = j;
+    for (int k = 0; k < D; ++k) {
+      const double t = rint((b[k] - B.org[k]) * inv);
+      ok &= t >= 0.0 && t < (double)(lim - 1);
+      const int j = ok ? (int)t : 0;
+      ok &= nmbrick::grid_corner(B.org[k], j, g) == b[k] && nmbrick::grid_corner(B.org[k], j + 1, g) == b[4 + k];
+      idx[k] = j;
+    }
+    uint32_t slot = 0xffffffffu;
+    unsigned bit = 0;
+    if (!ok) {
+      atomicOr(&B.hdr->bad, 1u);
+    } else {
+      bit = D == 3 ? (unsigned)((idx[0] & 3) | ((idx[1] & 3) << 2) | ((idx[2] & 3) << 4)) : (unsigned)((idx[0] & 7) | ((idx[1] & 7) << 3));
+      const unsigned long long key = brick_key<D>(level, idx[0] >> SH, idx[1] >> SH, idx[2] >> SH);
+      uint32_t s = brick_hash(key) & B.slot_mask;
+      int probes = 0;
+      while (true) {
+        const unsigned long long old = atomicCAS(&B.slots[s].key, ~0ULL, key);
+        if (old == ~0ULL || old == key) { slot = s; break; }
+        s = (s + 1) & B.slot_mask;
+        if (++probes > 256) { atomicOr(&B.hdr->bad, 2u); break; }   // table too full: not a surface band
+      }
+      if (slot != 0xffffffffu) {
+        const unsigned long long prev = atomicOr(&B.slots[slot].mask, 1ULL << bit);
+        if ((prev >> bit) & 1ULL) atomicOr(&B.hdr->bad, 4u);   // two cells in one grid cell: overlapping boxes
+        my_level_bit = 1u << level;
+      }
+    }
+    cell_slot[i] = slot;
+    cell_bit[i] = (uint8_t)bit;
   }
-  if (!ok) { atomicOr(&B.hdr->bad, 1u); cell_slot[i] = 0xffffffffu; return; }
-  const unsigned bit = D == 3 ? (unsigned)((idx[0] & 3) | ((idx[1] & 3) << 2) | ((idx[2] & 3) << 4)) : (unsigned)((idx[0] & 7) | ((idx[1] & 7) << 3));
-  const unsigned long long key = brick_key<D>(level, idx[0] >> SH, idx[1] >> SH, idx[2] >> SH);
-  uint32_t s = (uint32_t)mix64(key) & B.slot_mask;
-  int probes = 0;
-  while (true) {
-    const unsigned long long old = atomicCAS(&B.slots[s].key, ~0ULL, key);
-    if (old == ~0ULL || old == key) break;
-    s = (s + 1) & B.slot_mask;
-    if (++probes > 512) { atomicOr(&B.hdr->bad, 2u); cell_slot[i] = 0xffffffffu; return; }   // table too full: not a surface band
-  }
-  const unsigned long long prev = atomicOr(&B.slots[s].mask, 1ULL << bit);
-  if ((prev >> bit) & 1ULL) atomicOr(&B.hdr->bad, 4u);   // two cells in one grid cell: overlapping boxes
-  cell_slot[i] = s;
-  cell_bit[i] = (uint8_t)bit;
+  my_level_bit = __reduce_or_sync(0xffffffffu, my_level_bit);
+  if ((threadIdx.x & 31) == 0 && my_level_bit) atomicOr(&s_levels, my_level_bit);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_levels) atomicOr(&B.hdr->level_mask, s_levels);
 }
 
 __global__ void brick_base(BrickDev B, uint32_t cap)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long m = 0;
-  if (i < cap && B.slots[i].key != ~0ULL) m = B.slots[i].mask;
+  if (i < cap) m = B.slots[i].mask;   // empty slots carry an empty mask
   const unsigned c = (unsigned)__popcll(m);
   // one atomic per warp
   unsigned inc = c;
@@ -531,42 +536,39 @@ __global__ void brick_fill(BrickDev B, uint64_t n, const uint32_t *__restrict__ 
   const uint32_t s = cell_slot[i];
   if (s == 0xffffffffu) return;
   const unsigned bit = cell_bit[i];
-  const BrickSlot sl = B.slots[s];
-  B.ids[sl.base + __popcll(sl.mask & ((1ULL << bit) - 1ULL))] = (uint32_t)i;
+  const unsigned long long mask = B.slots[s].mask;
+  B.ids[B.slots[s].base + __popcll(mask & ((1ULL << bit) - 1ULL))] = (uint32_t)i;
 }
 
-// per level: the exact range of grid indices whose closed cell meets [qlo, qhi] along every axis
-template <int D>
-__device__ __forceinline__ bool brick_level_range(const BrickDev &B, int level, const double *qlo, const double *qhi, long long *L, long long *H)
+// the exact range of grid indices of `level` whose closed cell meets [qlo, qhi] along `axis`
+__device__ __forceinline__ bool brick_axis_range(const BrickDev &B, int level, int axis, double qlo, double qhi, int &L, int &H)
 {
-  const double g = B.g0 * (double)(1ULL << level), inv = 1.0 / g;
-  const long long top = (1LL << B.idx_bits) - 2;
-  bool ok = true;
-#pragma unroll
-  for (int k = 0; k < D; ++k) ok &= nmbrick::axis_range(nmbrick::ord_decode(B.hdr->lvl_min[level][k]), g, inv, top, qlo[k], qhi[k], L[k], H[k]);
-  for (int k = D; k < 3; ++k) L[k] = H[k] = 0;
-  return ok;
+  const double g = B.g0 * (double)(1u << level), inv = B.inv0 * pow2_neg(level);
+  const double org = axis == 0 ? B.org[0] : (axis == 1 ? B.org[1] : B.org[2]);
+  return nmbrick::axis_range(org, g, inv, (1 << B.idx_bits) - 2, qlo, qhi, L, H);
 }
 
-__device__ __forceinline__ bool brick_find(const BrickDev &B, unsigned long long key, BrickSlot &out)
+__device__ __forceinline__ bool brick_find(const BrickDev &B, unsigned long long key, unsigned long long &mask, uint32_t &base)
 {
-  uint32_t s = (uint32_t)mix64(key) & B.slot_mask;
+  uint32_t s = brick_hash(key) & B.slot_mask;
   while (true) {
     const ulonglong2 km = *reinterpret_cast<const ulonglong2 *>(&B.slots[s]);
-    if (km.x == key) { out.key = km.x; out.mask = km.y; out.base = B.slots[s].base; return true; }
+    if (km.x == key) { mask = km.y; base = B.slots[s].base; return true; }
     if (km.x == ~0ULL) return false;
     s = (s + 1) & B.slot_mask;
   }
 }
 
-// G lanes per immersed cell: the bricks of a level are probed in parallel lanes, the hits are collected in shared
-// memory, ordered by rank counting and stored as one row of at most CAP ids (the true count is recorded even when
-// it exceeds CAP; cand_place_brick probes such cells again).
+// G lanes per immersed cell.  Lane (s * D + a) computes the index range of axis a for the s-th level of a pass (two
+// levels per pass), the ranges go round by shuffle, then the bricks of both levels are probed in parallel lanes.  The
+// hits are collected in shared memory, ordered by rank counting and stored as one row of at most CAP ids (the true
+// count is recorded even when it exceeds CAP; cand_place_brick probes such cells again).
 template <int D, int G, int CAP>
 __global__ void __launch_bounds__(128) cand_probe_brick(BrickDev B, uint64_t n_im, const double *__restrict__ im_verts,
                                                         uint32_t *__restrict__ cnt, uint32_t *__restrict__ tmp)
 {
-  constexpr int NVI = 1 << (D - 1), CPB = 128 / G, SH = nmbrick::BrickShape<D>::SH;
+  constexpr int NVI = 1 << (D - 1), CPB = 128 / G, SH = nmbrick::BrickShape<D>::SH, NSL = 2;
+  static_assert(G >= NSL * D, "one lane per (level slot, axis)");
   __shared__ uint32_t s_ids[CPB][CAP];
   __shared__ unsigned s_n[CPB];
   const unsigned g = threadIdx.x / G, l = threadIdx.x % G;
@@ -575,31 +577,58 @@ __global__ void __launch_bounds__(128) cand_probe_brick(BrickDev B, uint64_t n_i
   const uint64_t m = (uint64_t)blockIdx.x * CPB + g;
   if (m >= n_im) return;   // whole groups leave together
   if (l == 0) s_n[g] = 0;
-  double lo[3], hi[3];
-  im_box<D, NVI>(im_verts + m * NVI * D, lo, hi);
-  __syncwarp(gmask);
+  // the bounding interval of the immersed cell along "my" axis
+  const int ax = (int)(l % D), sl = (int)(l / D);
+  double qlo, qhi;
+  {
+    const double *v = im_verts + m * NVI * D + ax;
+    qlo = qhi = v[0];
+#pragma unroll
+    for (int q = 1; q < NVI; ++q) { const double x = v[q * D]; qlo = fmin(qlo, x); qhi = fmax(qhi, x); }
+  }
   uint32_t lm = B.hdr->level_mask;
+  __syncwarp(gmask);
   while (lm) {
-    const int level = __ffs(lm) - 1;
-    lm &= lm - 1;
-    long long L[3], H[3];
-    if (!brick_level_range<D>(B, level, lo, hi, L, H)) continue;
-    const long long b0[3] = {L[0] >> SH, L[1] >> SH, L[2] >> SH};
-    const int nb[3] = {(int)((H[0] >> SH) - b0[0]) + 1, (int)((H[1] >> SH) - b0[1]) + 1, D == 3 ? (int)((H[2] >> SH) - b0[2]) + 1 : 1};
-    const int T = nb[0] * nb[1] * nb[2];
-    for (int t = (int)l; t < T; t += G) {
-      const int tx = t % nb[0], ty = (t / nb[0]) % nb[1], tz = t / (nb[0] * nb[1]);
-      const long long bx = b0[0] + tx, by = b0[1] + ty, bz = b0[2] + tz;
-      BrickSlot sl;
-      if (!brick_find(B, brick_key<D>(level, bx, by, bz), sl)) continue;
-      unsigned long long hits = sl.mask & nmbrick::brick_query_mask<D>(L, H, bx, by, bz);
+    int lev[NSL];
+#pragma unroll
+    for (int s = 0; s < NSL; ++s) { lev[s] = lm ? __ffs(lm) - 1 : -1; lm &= lm - 1; }
+    const int my_level = sl == 0 ? lev[0] : (sl == 1 ? lev[1] : -1);
+    int myL = 1, myH = 0;   // empty
+    if (my_level >= 0 && !brick_axis_range(B, my_level, ax, qlo, qhi, myL, myH)) { myL = 1; myH = 0; }
+    int L[NSL][3], H[NSL][3], b0[NSL][3], nb[NSL][3], T[NSL];
+#pragma unroll
+    for (int s = 0; s < NSL; ++s) {
+      bool ok = lev[s] >= 0;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        if (a < D) {
+          L[s][a] = __shfl_sync(gmask, myL, gbase + s * D + a);
+          H[s][a] = __shfl_sync(gmask, myH, gbase + s * D + a);
+        } else { L[s][a] = 0; H[s][a] = 0; }
+        ok &= L[s][a] <= H[s][a];
+        b0[s][a] = L[s][a] >> SH;
+        nb[s][a] = (H[s][a] >> SH) - b0[s][a] + 1;
+      }
+      T[s] = ok ? nb[s][0] * nb[s][1] * nb[s][2] : 0;
+    }
+    const int Ttot = T[0] + T[1];
+    for (int t = (int)l; t < Ttot; t += G) {
+      const int s = t < T[0] ? 0 : 1;
+      const int tt = s ? t - T[0] : t;
+      const int n0 = s ? nb[1][0] : nb[0][0], n1 = s ? nb[1][1] : nb[0][1];
+      const int tx = tt % n0, ty = (tt / n0) % n1, tz = tt / (n0 * n1);
+      const int bx = (s ? b0[1][0] : b0[0][0]) + tx, by = (s ? b0[1][1] : b0[0][1]) + ty, bz = (s ? b0[1][2] : b0[0][2]) + tz;
+      unsigned long long mask;
+      uint32_t base;
+      if (!brick_find(B, brick_key<D>(s ? lev[1] : lev[0], bx, by, bz), mask, base)) continue;
+      unsigned long long hits = mask & nmbrick::brick_query_mask<D>(s ? L[1] : L[0], s ? H[1] : H[0], bx, by, bz);
       const unsigned nh = (unsigned)__popcll(hits);
       if (!nh) continue;
       unsigned pos = atomicAdd(&s_n[g], nh);
       while (hits) {
         const int bit = __ffsll((long long)hits) - 1;
         hits &= hits - 1;
-        if (pos < (unsigned)CAP) s_ids[g][pos] = B.ids[sl.base + __popcll(sl.mask & ((1ULL << bit) - 1ULL))];
+        if (pos < (unsigned)CAP) s_ids[g][pos] = B.ids[base + __popcll(mask & ((1ULL << bit) - 1ULL))];
         ++pos;
       }
     }
@@ -627,18 +656,21 @@ __device__ inline void brick_query_serial(const BrickDev &B, const double *lo, c
   while (lm) {
     const int level = __ffs(lm) - 1;
     lm &= lm - 1;
-    long long L[3], H[3];
-    if (!brick_level_range<D>(B, level, lo, hi, L, H)) continue;
-    for (long long bz = L[2] >> SH; bz <= (H[2] >> SH); ++bz)
-      for (long long by = L[1] >> SH; by <= (H[1] >> SH); ++by)
-        for (long long bx = L[0] >> SH; bx <= (H[0] >> SH); ++bx) {
-          BrickSlot sl;
-          if (!brick_find(B, brick_key<D>(level, bx, by, bz), sl)) continue;
-          unsigned long long hits = sl.mask & nmbrick::brick_query_mask<D>(L, H, bx, by, bz);
+    int L[3] = {0, 0, 0}, H[3] = {0, 0, 0};
+    bool ok = true;
+    for (int k = 0; k < D; ++k) ok &= brick_axis_range(B, level, k, lo[k], hi[k], L[k], H[k]);
+    if (!ok) continue;
+    for (int bz = L[2] >> SH; bz <= (H[2] >> SH); ++bz)
+      for (int by = L[1] >> SH; by <= (H[1] >> SH); ++by)
+        for (int bx = L[0] >> SH; bx <= (H[0] >> SH); ++bx) {
+          unsigned long long mask;
+          uint32_t base;
+          if (!brick_find(B, brick_key<D>(level, bx, by, bz), mask, base)) continue;
+          unsigned long long hits = mask & nmbrick::brick_query_mask<D>(L, H, bx, by, bz);
           while (hits) {
             const int bit = __ffsll((long long)hits) - 1;
             hits &= hits - 1;
-            emit(B.ids[sl.base + __popcll(sl.mask & ((1ULL << bit) - 1ULL))]);
+            emit(B.ids[base + __popcll(mask & ((1ULL << bit) - 1ULL))]);
           }
         }
   }
@@ -716,7 +748,7 @@ int nm_bg_layout(nm_ctx *ctx, int d, uint64_t n, const double *verts_dev, const 
       if (d == 2) bg_boxes_from_verts<2><<<B, T, 0, NM_LS(ctx)>>>(n, verts_dev, ctx->bg_box.as<double>(), bad);
       else bg_boxes_from_verts<3><<<B, T, 0, NM_LS(ctx)>>>(n, verts_dev, ctx->bg_box.as<double>(), bad);
     } else {
-      NM_TRY(nm_ensure(ctx, ctx->idx_tmp, NM_STATS_BLOCKS * 8 * sizeof(double)));
+      NM_TRY(nm_ensure(ctx, ctx->idx_tmp, NM_STATS_BLOCKS * NM_STATS_W * sizeof(double)));
       if (d == 2) bg_boxes_from_lohi_stats<2><<<NM_STATS_BLOCKS, 256, 0, NM_LS(ctx)>>>(n, lo_dev, hi_dev, ctx->bg_box.as<double>(), bad, ctx->idx_tmp.as<double>());
       else bg_boxes_from_lohi_stats<3><<<NM_STATS_BLOCKS, 256, 0, NM_LS(ctx)>>>(n, lo_dev, hi_dev, ctx->bg_box.as<double>(), bad, ctx->idx_tmp.as<double>());
       ctx->bg_stats_ready = true;
@@ -771,7 +803,7 @@ static GridDev make_grid_dev(const nm_ctx *ctx)
 }
 
 static int chain_index_build(nm_ctx *ctx);
-static int brick_index_build(nm_ctx *ctx);
+static int brick_index_build(nm_ctx *ctx, bool roomy);
 
 int nm_index_build(nm_ctx *ctx)
 {
@@ -786,25 +818,29 @@ int nm_index_build(nm_ctx *ctx)
     return NM_OK; }
   // 1. origin and level-0 spacing
   constexpr unsigned SB = NM_STATS_BLOCKS;
-  NM_TRY(nm_ensure(ctx, ctx->idx_tmp, SB * 8 * sizeof(double)));
+  NM_TRY(nm_ensure(ctx, ctx->idx_tmp, SB * NM_STATS_W * sizeof(double)));
   if (!ctx->bg_stats_ready) {   // the lo/hi layout kernel has already taken them
     if (d == 2) bg_stats<2><<<SB, 256, 0, NM_LS(ctx)>>>(n, ctx->bg_box.as<double>(), ctx->idx_tmp.as<double>());
     else bg_stats<3><<<SB, 256, 0, NM_LS(ctx)>>>(n, ctx->bg_box.as<double>(), ctx->idx_tmp.as<double>());
     NM_CUDA(cudaGetLastError());
   }
   ctx->bg_stats_ready = false;  // idx_tmp is reused below
-  static thread_local double h_stats[SB * 8];
+  static thread_local double h_stats[SB * NM_STATS_W];
   NM_CUDA(cudaMemcpyAsync(h_stats, ctx->idx_tmp.p, sizeof(h_stats), cudaMemcpyDeviceToHost, ctx->stream));
   NM_SYNC(ctx);
   double org[3] = {INFINITY, INFINITY, INFINITY}, top[3] = {-INFINITY, -INFINITY, -INFINITY}, g0 = INFINITY, gmax = 0;
+  double anchor[3] = {0, 0, 0};
   for (unsigned b = 0; b < SB; ++b) {
-    for (int k = 0; k < 3; ++k) { org[k] = fmin(org[k], h_stats[b * 8 + k]); top[k] = fmax(top[k], h_stats[b * 8 + 3 + k]); }
-    g0 = fmin(g0, h_stats[b * 8 + 6]);
-    gmax = fmax(gmax, h_stats[b * 8 + 7]);
+    const double *h = h_stats + b * NM_STATS_W;
+    for (int k = 0; k < 3; ++k) { org[k] = fmin(org[k], h[k]); top[k] = fmax(top[k], h[3 + k]); }
+    g0 = fmin(g0, h[6]);
+    if (h[7] > gmax) { gmax = h[7]; for (int k = 0; k < 3; ++k) anchor[k] = h[8 + k]; }
   }
   if (!(g0 < INFINITY)) g0 = 1.0;  // all cells degenerate
   for (int k = 0; k < 3; ++k) ctx->gi.org[k] = k < d ? org[k] : 0.0;
   ctx->gi.g0 = g0;
+  // one origin for the grids of all levels (brick index): a coarsest cell's corner, moved down by whole coarsest cells
+  for (int k = 0; k < 3; ++k) ctx->gi.brick_org[k] = (k < d && gmax > 0) ? nmbrick::aligned_origin(org[k], anchor[k], gmax) : 0.0;
   if (gmax > g0 * 2147483648.0)
     return nm_fail(ctx, NM_ERR_UNSUPPORTED, "background cell extents span more than 31 octaves (%g .. %g)", g0, gmax);
   const int bits = d == 2 ? 29 : 19;
@@ -815,8 +851,7 @@ int nm_index_build(nm_ctx *ctx)
                      top[k] - org[k], g0);
 
   if (!ctx->force_chain_index) {
-    NM_TRY(brick_index_build(ctx));
-    ctx->index_kind = 2;
+    NM_TRY(brick_index_build(ctx, false));
     ctx->index_valid = true;
     return NM_OK;
   }
@@ -875,42 +910,44 @@ static BrickDev make_brick_dev(const nm_ctx *ctx)
   B.slot_mask = ctx->gi.hash_cap - 1;
   B.ids = ctx->idx_extra_bg.as<uint32_t>();
   B.hdr = ctx->brk_hdr.as<BrickHeader>();
+  for (int k = 0; k < 3; ++k) B.org[k] = ctx->gi.brick_org[k];
   B.g0 = ctx->gi.g0;
+  B.inv0 = 1.0 / ctx->gi.g0;
   B.idx_bits = ctx->gi.d == 2 ? 29 : 19;
   return B;
 }
 
-// brick index (grid-aligned trees): levels + per-level origins, verification + insertion, id offsets, ids.  No host
-// synchronisation: a failed verification is noticed with the candidate count (nm_candidates_run) and the chain index
-// takes over.
-static int brick_index_build(nm_ctx *ctx)
+// brick index (grid-aligned trees): verification + insertion, id offsets, ids.  No host synchronisation: a failed
+// verification is noticed with the candidate count (nm_candidates_run) and the chain index takes over.
+// `roomy`: a table that cannot overflow (one slot per cell and more); the default holds a surface band comfortably
+// (~25 cells per occupied brick) and is cleared and scanned four times faster.
+static int brick_index_build(nm_ctx *ctx, bool roomy)
 {
   const int d = ctx->spacedim;
   const uint64_t n = ctx->n_bg;
-  uint32_t cap = 64;
-  while (cap < n / 2 + 1) cap <<= 1;   // a surface band fills ~1/25 brick per cell; a fuller table raises `bad`
+  const uint64_t want = roomy ? 2 * n + 1 : n / 8 + 1;
+  uint32_t cap = 1024;
+  while (cap < want) cap <<= 1;
   ctx->gi.hash_cap = cap;
   ctx->gi.n_entries = (uint32_t)n;
+  ctx->brick_roomy = roomy;
   NM_TRY(nm_ensure(ctx, ctx->idx_hash, (size_t)cap * sizeof(BrickSlot)));
   NM_TRY(nm_ensure(ctx, ctx->idx_next, (n + 1) * 4));       // slot of every cell
   NM_TRY(nm_ensure(ctx, ctx->brk_bit, n + 1));              // bit of every cell inside its brick
   NM_TRY(nm_ensure(ctx, ctx->idx_extra_bg, (n + 1) * 4));   // cell ids, brick by brick in bit order
   NM_TRY(nm_ensure(ctx, ctx->brk_hdr, sizeof(BrickHeader)));
   BrickHeader *hdr = ctx->brk_hdr.as<BrickHeader>();
-  NM_CUDA(cudaMemsetAsync(hdr, 0xff, sizeof(hdr->lvl_min), ctx->stream));
-  NM_CUDA(cudaMemsetAsync(&hdr->level_mask, 0, sizeof(BrickHeader) - sizeof(hdr->lvl_min), ctx->stream));
+  NM_CUDA(cudaMemsetAsync(hdr, 0, sizeof(BrickHeader), ctx->stream));
   const BrickDev B = make_brick_dev(ctx);
   const unsigned T = 256, NB = nm_blocks(n, T);
-  const unsigned GB = NB < (unsigned)ctx->sm_count * 8u ? NB : (unsigned)ctx->sm_count * 8u;
   const double *box = ctx->bg_box.as<double>();
-  if (d == 2) brick_levels<2><<<GB, T, 0, NM_LS(ctx)>>>(B.g0, n, box, hdr);
-  else brick_levels<3><<<GB, T, 0, NM_LS(ctx)>>>(B.g0, n, box, hdr);
   brick_clear<<<nm_blocks(cap, 256), 256, 0, NM_LS(ctx)>>>(B.slots, cap);
   if (d == 2) brick_insert<2><<<NB, T, 0, NM_LS(ctx)>>>(B, n, box, ctx->idx_next.as<uint32_t>(), ctx->brk_bit.as<uint8_t>());
   else brick_insert<3><<<NB, T, 0, NM_LS(ctx)>>>(B, n, box, ctx->idx_next.as<uint32_t>(), ctx->brk_bit.as<uint8_t>());
   brick_base<<<nm_blocks(cap, 256), 256, 0, NM_LS(ctx)>>>(B, cap);
   brick_fill<<<NB, T, 0, NM_LS(ctx)>>>(B, n, ctx->idx_next.as<uint32_t>(), ctx->brk_bit.as<uint8_t>());
   NM_CUDA(cudaGetLastError());
+  ctx->index_kind = 2;
   return NM_OK;
 }
 
@@ -942,7 +979,11 @@ static int candidates_run_bricks(nm_ctx *ctx, bool *fell_back)
   NM_CUDA(cudaMemcpyAsync(&n_cand, ctx->cand_ptr.as<uint64_t>() + n_im, 8, cudaMemcpyDeviceToHost, ctx->stream));
   NM_CUDA(cudaMemcpyAsync(&bad, &B.hdr->bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
   NM_SYNC(ctx);
-  if (bad) {   // not a grid-aligned tree (or not a surface band): redo with the general index
+  if (bad == 2 && !ctx->brick_roomy) {   // a tree, but denser in bricks than a surface band: same index, roomy table
+    NM_TRY(brick_index_build(ctx, true));
+    return candidates_run_bricks<D, CAP, G>(ctx, fell_back);
+  }
+  if (bad) {   // not a grid-aligned tree: redo with the general index
     NM_TRY(chain_index_build(ctx));
     *fell_back = true;
     return NM_OK;

@@ -34,7 +34,7 @@ template <int NL>
 __global__ void row_capacity_kernel(uint64_t n_im, const uint64_t *__restrict__ cand_ptr, const uint32_t *__restrict__ cand_bg,
                                     const uint8_t *__restrict__ acc, const uint32_t *__restrict__ bg_dofs,
                                     const int32_t *__restrict__ line_of, const uint64_t *__restrict__ c_ptr,
-                                    uint32_t *__restrict__ cap, unsigned *max_cap, unsigned *n_big)
+                                    uint32_t *__restrict__ cap, unsigned *max_cap, unsigned *n_big, uint32_t n_dofs, unsigned *bad_dof)
 {
   const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= n_im) return;
@@ -44,6 +44,7 @@ __global__ void row_capacity_kernel(uint64_t n_im, const uint64_t *__restrict__ 
     const uint32_t *dofs = bg_dofs + (uint64_t)cand_bg[p] * NL;
 #pragma unroll
     for (int i = 0; i < NL; ++i) {
+      if (dofs[i] >= n_dofs) { atomicOr(bad_dof, 1u); continue; }   // the caller's table points outside the declared dofs
       const int32_t ln = line_of[dofs[i]];
       c += 1 + (ln >= 0 ? (uint32_t)(c_ptr[ln + 1] - c_ptr[ln]) : 0u);
     }
@@ -203,6 +204,45 @@ __device__ inline unsigned hash_insert(unsigned *keys, unsigned dof)
   }
 }
 
+constexpr unsigned NO_SLOT = 0xffffffffu;
+
+// claim (or find) the slot of `key` in a SLOTS-entry open-addressing table; bounded probing gives up instead of spinning
+template <int SLOTS>
+__device__ __forceinline__ unsigned hash_claim(unsigned *keys, unsigned key, unsigned &claimed, bool &failed)
+{
+  unsigned s = ((key * 2654435761u) >> 16) & (SLOTS - 1);
+  int probes = 0;
+  while (true) {
+    const unsigned old = atomicCAS(&keys[s], HASH_EMPTY, key);
+    if (old == HASH_EMPTY) { ++claimed; return s; }
+    if (old == key) return s;
+    s = (s + 1) & (SLOTS - 1);
+    if (++probes >= SLOTS) { failed = true; return NO_SLOT; }
+  }
+}
+
+// vals[slot] += v for every lane of the group that carries a contribution (slot != NO_SLOT), in a FIXED order: lanes
+// that hit the same slot in this instruction are found with match.any, the lowest of them adds the values in ascending
+// lane order and is the only one that touches the slot.  No floating-point atomics: the sums are bit-reproducible.
+__device__ __forceinline__ void group_accumulate(unsigned gmask, unsigned wlane, double *vals, unsigned slot, double v)
+{
+  const bool has = slot != NO_SLOT;
+  const unsigned grp = __match_any_sync(gmask, has ? slot : (0x80000000u | wlane));   // a lane without a contribution matches nobody
+  const bool leader = has && (unsigned)(__ffs(grp) - 1) == wlane;
+  const unsigned mx = __reduce_max_sync(gmask, has ? (unsigned)__popc(grp) : 1u);
+  double sum = v;
+  unsigned rest = grp & (grp - 1u);   // the other lanes of my slot, ascending
+  for (unsigned j = 1; j < mx; ++j) {
+    const bool more = rest != 0u;
+    const int src = more ? __ffs(rest) - 1 : (int)wlane;
+    rest &= rest - 1u;
+    const double o = __shfl_sync(gmask, v, src);
+    if (leader && more) sum += o;
+  }
+  if (leader) vals[slot] += sum;
+  __syncwarp(gmask);
+}
+
 template <int NL>
 __global__ void __launch_bounds__(256) merge_rows_hash(uint64_t n_im, const uint32_t *__restrict__ cap, const uint64_t *__restrict__ cand_ptr,
                                                        const uint32_t *__restrict__ cand_bg, const uint8_t *__restrict__ acc,
@@ -233,6 +273,8 @@ __global__ void __launch_bounds__(256) merge_rows_hash(uint64_t n_im, const uint
     const bool on = p < p1 && acc[p];
     uint32_t dofs[NL];
     double v[NL];
+#pragma unroll
+    for (int i = 0; i < NL; ++i) { dofs[i] = 0; v[i] = 0.0; }
     if (on) {
       const uint32_t *dp = bg_dofs + (uint64_t)cand_bg[p] * NL;
       const double *lp = local + p * NL;
@@ -241,18 +283,22 @@ __global__ void __launch_bounds__(256) merge_rows_hash(uint64_t n_im, const uint
     }
 #pragma unroll
     for (int i = 0; i < NL; ++i) {
+      // one (pair, vertex) contribution per lane, added in lane order (group_accumulate): no floating-point atomics
+      int32_t ln = -1;
+      unsigned s = NO_SLOT;
       if (on) {
-        const int32_t ln = line_of[dofs[i]];
-        const unsigned s = hash_insert(keys, dofs[i]);
-        if (ln < 0) {
-          atomicAdd(&vals[s], v[i]);
-        } else {
-          // keep_constrained_entries: the constrained row stays in the pattern, structurally zero;
-          // its value goes to the masters of the line (none for a Dirichlet row)
-          for (uint64_t k = c_ptr[ln]; k < c_ptr[ln + 1]; ++k) atomicAdd(&vals[hash_insert(keys, c_master[k])], c_weight[k] * v[i]);
-        }
+        ln = line_of[dofs[i]];
+        s = hash_insert(keys, dofs[i]);   // keep_constrained_entries: a constrained row stays in the pattern, structurally zero
       }
-      __syncwarp();
+      group_accumulate(0xffffffffu, lane, vals, (on && ln < 0) ? s : NO_SLOT, v[i]);
+      const unsigned nm = (on && ln >= 0) ? (unsigned)(c_ptr[ln + 1] - c_ptr[ln]) : 0u;   // masters of the line (none for a Dirichlet row)
+      const unsigned nm_max = __reduce_max_sync(0xffffffffu, nm);
+      for (unsigned k = 0; k < nm_max; ++k) {
+        unsigned t = NO_SLOT;
+        double wv = 0.0;
+        if (k < nm) { const uint64_t kk = c_ptr[ln] + k; t = hash_insert(keys, c_master[kk]); wv = c_weight[kk] * v[i]; }
+        group_accumulate(0xffffffffu, lane, vals, t, wv);
+      }
     }
   }
   // distinct keys -> list
@@ -288,7 +334,7 @@ constexpr int FAST_ROWS = 64;   // consecutive immersed cells per group
 
 // GROUP lanes cooperate on one immersed cell: a full warp in 3D (~10 accepted pairs x 8 vertices), 8 lanes
 // in 2D (~3.4 pairs x 4 vertices), so that a warp merges four 2D cells at a time.
-template <int NL, int GROUP, int SLOTS, unsigned FAST_CHUNK>
+template <int NL, int GROUP, int SLOTS>
 __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint64_t *__restrict__ cand_ptr,
                                                        const uint32_t *__restrict__ cand_bg, const uint8_t *__restrict__ acc,
                                                        const double *__restrict__ local, const uint32_t *__restrict__ bg_dofs,
@@ -296,7 +342,8 @@ __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint
                                                        const uint32_t *__restrict__ c_master, const double *__restrict__ c_weight,
                                                        uint64_t *__restrict__ rowstart, uint32_t *__restrict__ rowlen,
                                                        uint32_t *__restrict__ out_col, double *__restrict__ out_val, uint64_t capacity,
-                                                       unsigned long long *cursor, unsigned *problem, uint32_t *__restrict__ a_cnt, int mark_bits)
+                                                       unsigned long long *cursor, unsigned *problem, uint32_t *__restrict__ a_cnt, int mark_bits,
+                                                       uint32_t n_dofs, unsigned rows_per_group, unsigned chunk)
 {
   constexpr int NG = 256 / GROUP;                 // groups per block
   constexpr unsigned CAP = SLOTS * 3 / 4;         // distinct dofs a group accepts
@@ -313,10 +360,10 @@ __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint
   unsigned *list = s_list[g];
   unsigned *dkey = s_dkey[g];
   unsigned *cands = s_cand[g];
-  const uint64_t m0 = ((uint64_t)blockIdx.x * NG + g) * FAST_ROWS;
+  const uint64_t m0 = ((uint64_t)blockIdx.x * NG + g) * rows_per_group;
   uint64_t chunk_pos = 0;
   unsigned chunk_left = 0;
-  for (uint64_t m = m0; m < m0 + FAST_ROWS && m < n_im; ++m) {
+  for (uint64_t m = m0; m < m0 + rows_per_group && m < n_im; ++m) {
 #pragma unroll
     for (int k = 0; k < SLOTS / GROUP; ++k) { keys[lane + GROUP * k] = HASH_EMPTY; vals[lane + GROUP * k] = 0.0; }
     __syncwarp(gmask);
@@ -333,43 +380,38 @@ __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint
       const unsigned n_entries = (unsigned)__popc(bal) * NL;
       for (unsigned e0 = 0; e0 < n_entries; e0 += GROUP) {
         const unsigned e = e0 + lane;
-        if (e < n_entries && !failed) {
+        const bool on_e = e < n_entries && !failed;
+        double v = 0.0;
+        int32_t ln = -1;
+        unsigned s = NO_SLOT;
+        if (on_e) {
           const uint64_t q = base + cands[e / NL];
           const unsigned i = e % NL;
           const uint32_t dof = bg_dofs[(uint64_t)cand_bg[q] * NL + i];
-          const double v = local[q * NL + i];
-          const int32_t ln = line_of[dof];
-          unsigned s = ((dof * 2654435761u) >> 16) & (SLOTS - 1);
-          int probes = 0;
-          while (true) {
-            const unsigned old = atomicCAS(&keys[s], HASH_EMPTY, dof);
-            if (old == HASH_EMPTY) { ++claimed; break; }
-            if (old == dof) break;
-            s = (s + 1) & (SLOTS - 1);
-            if (++probes >= SLOTS) { failed = true; break; }
-          }
-          if (failed) {
-          } else if (ln < 0) {
-            atomicAdd(&vals[s], v);
+          v = local[q * NL + i];
+          if (dof >= n_dofs) {   // the caller's table points outside the declared dofs: reported as NM_ERR_INVALID
+            atomicOr(problem, 4u);
+            failed = true;
           } else {
-            // keep_constrained_entries: the constrained row stays in the pattern as a structural zero;
-            // its value goes to the masters of the line (none for a Dirichlet row)
-            for (uint64_t k = c_ptr[ln]; k < c_ptr[ln + 1] && !failed; ++k) {
-              const unsigned key = c_master[k];
-              unsigned t = ((key * 2654435761u) >> 16) & (SLOTS - 1);
-              probes = 0;
-              while (true) {
-                const unsigned old = atomicCAS(&keys[t], HASH_EMPTY, key);
-                if (old == HASH_EMPTY) { ++claimed; break; }
-                if (old == key) break;
-                t = (t + 1) & (SLOTS - 1);
-                if (++probes >= SLOTS) { failed = true; break; }
-              }
-              if (!failed) atomicAdd(&vals[t], c_weight[k] * v);
-            }
+            ln = line_of[dof];
+            s = hash_claim<SLOTS>(keys, dof, claimed, failed);
           }
         }
-        __syncwarp(gmask);
+        // keep_constrained_entries: a constrained row stays in the pattern as a structural zero (its slot is claimed,
+        // nothing is added); its value goes to the masters of the line (none for a Dirichlet row)
+        group_accumulate(gmask, gbase + lane, vals, (on_e && !failed && ln < 0) ? s : NO_SLOT, v);
+        const unsigned nm = (on_e && !failed && ln >= 0) ? (unsigned)(c_ptr[ln + 1] - c_ptr[ln]) : 0u;
+        const unsigned nm_max = __reduce_max_sync(gmask, nm);
+        for (unsigned k = 0; k < nm_max; ++k) {
+          unsigned t = NO_SLOT;
+          double wv = 0.0;
+          if (k < nm && !failed) {
+            const uint64_t kk = c_ptr[ln] + k;
+            t = hash_claim<SLOTS>(keys, c_master[kk], claimed, failed);
+            wv = c_weight[kk] * v;
+          }
+          group_accumulate(gmask, gbase + lane, vals, failed ? NO_SLOT : t, wv);
+        }
       }
     }
     const unsigned total_claimed = __reduce_add_sync(gmask, claimed);
@@ -391,7 +433,7 @@ __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint
     __syncwarp(gmask);
     if (D > chunk_left) {   // next chunk (the tail of the old one stays unused)
       unsigned long long base = 0;
-      const unsigned need = D > FAST_CHUNK ? D : FAST_CHUNK;
+      const unsigned need = D > chunk ? D : chunk;
       if (lane == 0) base = atomicAdd(cursor, (unsigned long long)need);
       base = __shfl_sync(gmask, base, gbase);
       if (base + need > capacity) {
@@ -815,9 +857,13 @@ static int matrix_build_fast(nm_ctx *ctx, bool *done)
   PhaseTimer tm(ctx, NM_T_MERGE);
   // distinct dofs <= contributions; +25% and the chunk tails for constraint expansion
   constexpr int GROUP = NL == 8 ? 32 : 8, SLOTS = NL == 8 ? 256 : 64, NG = 256 / GROUP;
-  constexpr unsigned FAST_CHUNK = NL == 8 ? 1024 : 256;   // entries a group takes from the cursor at a time
-  const uint64_t blocks = (n_im + NG * FAST_ROWS - 1) / (NG * FAST_ROWS);
-  const uint64_t capacity = ctx->counts.n_accepted * NL + ctx->counts.n_accepted * NL / 4 + blocks * NG * FAST_CHUNK + 1024;
+  // consecutive immersed cells per group: FAST_ROWS when the grid is large, fewer on small grids so that every SM still
+  // gets a few blocks (a 2 K-cell curve on one block of 64-row groups took as long as a 500 K-cell one)
+  uint64_t rpg = (n_im + (uint64_t)NG * 4 * ctx->sm_count - 1) / ((uint64_t)NG * 4 * ctx->sm_count);
+  rpg = rpg < 1 ? 1 : (rpg > FAST_ROWS ? FAST_ROWS : rpg);
+  const unsigned chunk = (unsigned)(rpg * (NL == 8 ? 16 : 4));   // entries a group takes from the cursor at a time
+  const uint64_t blocks = (n_im + NG * rpg - 1) / (NG * rpg);
+  const uint64_t capacity = ctx->counts.n_accepted * NL + ctx->counts.n_accepted * NL / 4 + blocks * NG * chunk + 1024;
   NM_TRY(nm_ensure(ctx, ctx->c_rowstart, (n_im + 2) * sizeof(uint64_t)));
   NM_TRY(nm_ensure(ctx, ctx->c_rowlen, (n_im + 1) * sizeof(uint32_t)));
   NM_TRY(nm_ensure(ctx, ctx->c_col, (capacity + 1) * sizeof(uint32_t)));
@@ -838,17 +884,18 @@ static int matrix_build_fast(nm_ctx *ctx, bool *done)
   unsigned *problem = ctx->counters.as<unsigned>() + 44;
   NM_CUDA(cudaMemsetAsync(cursor, 0, 32, ctx->stream));   // bytes 160..191: the chunk cursor AND the problem flag (byte 176)
   KernelTimer km(ctx, NM_T_K_MERGE);
-  merge_rows_fast<NL, GROUP, SLOTS, FAST_CHUNK><<<(unsigned)blocks, 256, 0, NM_LS(ctx)>>>(
+  merge_rows_fast<NL, GROUP, SLOTS><<<(unsigned)blocks, 256, 0, NM_LS(ctx)>>>(
       n_im, ctx->cand_ptr.as<uint64_t>(), ctx->cand_bg.as<uint32_t>(), ctx->cand_acc.as<uint8_t>(), ctx->cand_local.as<double>(),
       ctx->bg_dofs.as<uint32_t>(), ctx->line_of.as<int32_t>(), ctx->c_ptr.as<uint64_t>(), ctx->c_master.as<uint32_t>(),
       ctx->c_weight.as<double>(), ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(),
-      ctx->c_val.as<double>(), capacity, cursor, problem, dof_marks, ctx->compact_rows ? 1 : 0);
+      ctx->c_val.as<double>(), capacity, cursor, problem, dof_marks, ctx->compact_rows ? 1 : 0, (uint32_t)n_rows, (unsigned)rpg, chunk);
   km.stop();
   NM_CUDA(cudaGetLastError());
   unsigned h_problem = 0;
   NM_CUDA(cudaMemcpyAsync(&h_problem, problem, 4, cudaMemcpyDeviceToHost, ctx->stream));
   NM_SYNC(ctx);
   tm.stop();
+  if (h_problem & 4u) return nm_fail(ctx, NM_ERR_INVALID, "background DoF table holds indices >= n_dofs (%llu)", (unsigned long long)n_rows);
   if (h_problem) return NM_OK;  // the general path redoes everything
   NM_TRY(transpose_rows<NL>(ctx, true));
   ctx->merge_path = 0;
@@ -884,7 +931,8 @@ static int matrix_build_t(nm_ctx *ctx)
   if (n_im) {
     row_capacity_kernel<NL><<<nm_blocks(n_im, 128), 128, 0, NM_LS(ctx)>>>(
         n_im, ctx->cand_ptr.as<uint64_t>(), ctx->cand_bg.as<uint32_t>(), ctx->cand_acc.as<uint8_t>(), ctx->bg_dofs.as<uint32_t>(),
-        ctx->line_of.as<int32_t>(), ctx->c_ptr.as<uint64_t>(), ctx->scratch_a.as<uint32_t>(), hdr, hdr + 1);
+        ctx->line_of.as<int32_t>(), ctx->c_ptr.as<uint64_t>(), ctx->scratch_a.as<uint32_t>(), hdr, hdr + 1, (uint32_t)n_rows,
+        ctx->counters.as<unsigned>() + 48);
     NM_CUDA(cudaGetLastError());
   }
   NM_TRY(nm_exclusive_scan_u32_to_u64(ctx, ctx->scratch_a.as<uint32_t>(), ctx->c_rowstart.as<uint64_t>(), n_im + 1));
@@ -892,7 +940,10 @@ static int matrix_build_t(nm_ctx *ctx)
   unsigned h_hdr[4];
   NM_CUDA(cudaMemcpyAsync(&total_cap, ctx->c_rowstart.as<uint64_t>() + n_im, 8, cudaMemcpyDeviceToHost, ctx->stream));
   NM_CUDA(cudaMemcpyAsync(h_hdr, hdr, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  unsigned h_bad_dof = 0;
+  NM_CUDA(cudaMemcpyAsync(&h_bad_dof, ctx->counters.as<unsigned>() + 48, 4, cudaMemcpyDeviceToHost, ctx->stream));
   NM_SYNC(ctx);
+  if (h_bad_dof) return nm_fail(ctx, NM_ERR_INVALID, "background DoF table holds indices >= n_dofs (%llu)", (unsigned long long)n_rows);
   if (h_hdr[0] > (unsigned)BLOCK_CAP)
     return nm_fail(ctx, NM_ERR_UNSUPPORTED,
                    "an immersed cell couples to %u (dof, value) contributions; at most %d per immersed cell are implemented "
@@ -1024,21 +1075,20 @@ int nm_stored_rowptr_global(nm_ctx *ctx, uint64_t *rowptr_dev)
   return NM_OK;
 }
 
+// The immersed DoF table becomes column indices the SpMV dereferences: verified here (one small pass per upload).
+// The background table is verified where it is read, by the merge kernels.
 static int check_dof_tables(nm_ctx *ctx)
 {
-  if (ctx->dofs_checked) return NM_OK;
-  unsigned *bad = ctx->counters.as<unsigned>() + 48;   // [48] background table, [49] immersed table
+  unsigned *bad = ctx->counters.as<unsigned>() + 48;   // [48] background table (merge kernels), [49] immersed table
   NM_CUDA(cudaMemsetAsync(bad, 0, 8, ctx->stream));
-  const uint64_t nb = ctx->n_bg * (1ull << ctx->spacedim), ni = ctx->n_im;
-  const unsigned G = (unsigned)ctx->sm_count * 8u;
-  if (nb) check_index_range<<<G, 256, 0, NM_LS(ctx)>>>(nb, ctx->bg_dofs.as<uint32_t>(), (uint32_t)ctx->n_space_dofs, bad);
-  if (ni) check_index_range<<<G, 256, 0, NM_LS(ctx)>>>(ni, ctx->im_dofs.as<uint32_t>(), (uint32_t)ctx->n_im_dofs, bad + 1);
+  if (ctx->dofs_checked) return NM_OK;
+  const uint64_t ni = ctx->n_im;
+  if (ni) check_index_range<<<nm_blocks(ni, 256 * 8), 256, 0, NM_LS(ctx)>>>(ni, ctx->im_dofs.as<uint32_t>(), (uint32_t)ctx->n_im_dofs, bad + 1);
   NM_CUDA(cudaGetLastError());
-  unsigned h[2] = {0, 0};
-  NM_CUDA(cudaMemcpyAsync(h, bad, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  unsigned h = 0;
+  NM_CUDA(cudaMemcpyAsync(&h, bad + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
   NM_SYNC(ctx);
-  if (h[0]) return nm_fail(ctx, NM_ERR_INVALID, "background DoF table holds indices >= n_dofs (%llu)", (unsigned long long)ctx->n_space_dofs);
-  if (h[1]) return nm_fail(ctx, NM_ERR_INVALID, "immersed DoF table holds indices >= n_dofs (%llu)", (unsigned long long)ctx->n_im_dofs);
+  if (h) return nm_fail(ctx, NM_ERR_INVALID, "immersed DoF table holds indices >= n_dofs (%llu)", (unsigned long long)ctx->n_im_dofs);
   ctx->dofs_checked = true;
   return NM_OK;
 }

@@ -25,18 +25,18 @@ static void test_axis_range(std::mt19937_64 &rng)
   for (int rep = 0; rep < 200000; ++rep) {
     const double org = (U(rng) - 0.5) * 4;
     const double g = (rep & 1) ? ldexp(1.0, -(int)(U(rng) * 20)) : (0.1 + U(rng)) * ldexp(1.0, -(int)(U(rng) * 20));
-    const long long top = 200;
+    const int top = 200;
     double qlo, qhi;
     const int mode = rep % 5;
-    if (mode == 0) { const long long i = (long long)(U(rng) * 150); qlo = grid_corner(org, i, g); qhi = grid_corner(org, i + (long long)(U(rng) * 4), g); }  // touching corners
-    else if (mode == 1) { const long long i = (long long)(U(rng) * 150); qhi = grid_corner(org, i, g); qlo = qhi - U(rng) * 3 * g; }
+    if (mode == 0) { const int i = (int)(U(rng) * 150); qlo = grid_corner(org, i, g); qhi = grid_corner(org, i + (int)(U(rng) * 4), g); }  // touching corners
+    else if (mode == 1) { const int i = (int)(U(rng) * 150); qhi = grid_corner(org, i, g); qlo = qhi - U(rng) * 3 * g; }
     else { qlo = org + (U(rng) * 220 - 10) * g; qhi = qlo + U(rng) * 5 * g; }
-    long long L, H;
-    const bool ok = axis_range(org, g, 1.0 / g, top, qlo, qhi, L, H);
+    int L, H;
+    const bool ok = axis_range(org, g, 1.0 / g, (int)top, qlo, qhi, L, H);
     // brute force
-    long long bl = 1, bh = 0;
+    int bl = 1, bh = 0;
     bool any = false;
-    for (long long i = 0; i <= top; ++i) {
+    for (int i = 0; i <= top; ++i) {
       const double lo = grid_corner(org, i, g), hi = grid_corner(org, i + 1, g);
       if (lo <= qhi && qlo <= hi) { if (!any) bl = i; bh = i; any = true; }
     }
@@ -51,12 +51,12 @@ static void test_query_mask(std::mt19937_64 &rng)
   constexpr int SH = BrickShape<D>::SH, E = BrickShape<D>::EDGE;
   std::uniform_int_distribution<int> I(0, 40);
   for (int rep = 0; rep < 100000; ++rep) {
-    long long L[3] = {0, 0, 0}, H[3] = {0, 0, 0}, b[3] = {0, 0, 0};
+    int L[3] = {0, 0, 0}, H[3] = {0, 0, 0}, b[3] = {0, 0, 0};
     for (int k = 0; k < D; ++k) { L[k] = I(rng); H[k] = L[k] + I(rng) % 7; b[k] = I(rng) / E + (I(rng) % 3 - 1); if (b[k] < 0) b[k] = 0; }
     const unsigned long long m = brick_query_mask<D>(L, H, b[0], b[1], b[2]);
     unsigned long long ref = 0;
     for (int bit = 0; bit < 64; ++bit) {
-      long long idx[3] = {0, 0, 0};
+      int idx[3] = {0, 0, 0};
       if (D == 3) { idx[0] = (b[0] << SH) + (bit & 3); idx[1] = (b[1] << SH) + ((bit >> 2) & 3); idx[2] = (b[2] << SH) + ((bit >> 4) & 3); }
       else { idx[0] = (b[0] << SH) + (bit & 7); idx[1] = (b[1] << SH) + ((bit >> 3) & 7); }
       bool in = true;
@@ -73,7 +73,7 @@ static void test_whole_query(std::mt19937_64 &rng)
 {
   constexpr int SH = BrickShape<D>::SH;
   std::uniform_real_distribution<double> U(0, 1);
-  const double g0 = 1.0 / 64, org0[3] = {-1.0, -1.0, -1.0};
+  const double g0 = 1.0 / 64, org0[3] = {-1.0, -1.0, -1.0};   // band cells start at arbitrary fine indices: min corner is generally NOT on the coarse grid
   struct Cell { int level; long long idx[3]; double lo[3], hi[3]; };
   std::vector<Cell> cells;
   const int n0 = 128;
@@ -96,18 +96,24 @@ static void test_whole_query(std::mt19937_64 &rng)
       }
     }
   }
-  // per-level origins = min lower corner, indices relative to them
-  double org[2][3];
-  for (int l = 0; l < 2; ++l) for (int k = 0; k < 3; ++k) org[l][k] = 1e300;
-  for (auto &c : cells) for (int k = 0; k < D; ++k) org[c.level][k] = fmin(org[c.level][k], c.lo[k]);
-  std::map<std::tuple<int, long long, long long, long long>, std::pair<unsigned long long, std::vector<int>>> bricks;
+  // ONE origin for both levels (aligned_origin): the corner of a coarsest cell moved down by whole coarsest cells
+  double lo_min[3] = {1e300, 1e300, 1e300}, lo_coarse[3] = {0, 0, 0}, gmax = 0;
+  for (auto &c : cells) {
+    for (int k = 0; k < D; ++k) lo_min[k] = fmin(lo_min[k], c.lo[k]);
+    if (c.hi[0] - c.lo[0] > gmax) { gmax = c.hi[0] - c.lo[0]; for (int k = 0; k < D; ++k) lo_coarse[k] = c.lo[k]; }
+  }
+  double org[3] = {0, 0, 0};
+  for (int k = 0; k < D; ++k) org[k] = aligned_origin(lo_min[k], lo_coarse[k], gmax);
+  std::map<std::tuple<int, int, int, int>, std::pair<unsigned long long, std::vector<int>>> bricks;
   for (size_t i = 0; i < cells.size(); ++i) {
     auto &c = cells[i];
+    const int level = level_of_extent(c.hi[0] - c.lo[0], g0);
+    CHECK(level == c.level);
     const double g = g0 * (1 << c.level);
-    long long j[3] = {0, 0, 0};
+    int j[3] = {0, 0, 0};
     for (int k = 0; k < D; ++k) {
-      j[k] = llrint((c.lo[k] - org[c.level][k]) / g);
-      CHECK(grid_corner(org[c.level][k], j[k], g) == c.lo[k] && grid_corner(org[c.level][k], j[k] + 1, g) == c.hi[k]);
+      j[k] = (int)llrint((c.lo[k] - org[k]) / g);
+      CHECK(j[k] >= 0 && grid_corner(org[k], j[k], g) == c.lo[k] && grid_corner(org[k], j[k] + 1, g) == c.hi[k]);
     }
     const unsigned bit = D == 3 ? (unsigned)((j[0] & 3) | ((j[1] & 3) << 2) | ((j[2] & 3) << 4)) : (unsigned)((j[0] & 7) | ((j[1] & 7) << 3));
     auto &b = bricks[{c.level, j[0] >> SH, j[1] >> SH, j[2] >> SH}];
@@ -128,13 +134,13 @@ static void test_whole_query(std::mt19937_64 &rng)
     std::set<int> got, ref;
     for (int level = 0; level < 2; ++level) {
       const double g = g0 * (1 << level);
-      long long L[3] = {0, 0, 0}, H[3] = {0, 0, 0};
+      int L[3] = {0, 0, 0}, H[3] = {0, 0, 0};
       bool ok = true;
-      for (int k = 0; k < D; ++k) ok = ok && axis_range(org[level][k], g, 1.0 / g, (1LL << 19) - 2, qlo[k], qhi[k], L[k], H[k]);
+      for (int k = 0; k < D; ++k) ok = ok && axis_range(org[k], g, 1.0 / g, (1 << 19) - 2, qlo[k], qhi[k], L[k], H[k]);
       if (!ok) continue;
-      for (long long bz = L[2] >> SH; bz <= (H[2] >> SH); ++bz)
-        for (long long by = L[1] >> SH; by <= (H[1] >> SH); ++by)
-          for (long long bx = L[0] >> SH; bx <= (H[0] >> SH); ++bx) {
+      for (int bz = L[2] >> SH; bz <= (H[2] >> SH); ++bz)
+        for (int by = L[1] >> SH; by <= (H[1] >> SH); ++by)
+          for (int bx = L[0] >> SH; bx <= (H[0] >> SH); ++bx) {
             auto it = bricks.find({level, bx, by, bz});
             if (it == bricks.end()) continue;
             unsigned long long hits = it->second.first & brick_query_mask<D>(L, H, bx, by, bz);

@@ -197,3 +197,25 @@ def test_fused_ct_vmult_on_two_gpus():
                        capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
     assert "rel err" in r.stdout
+
+
+@pytest.mark.parametrize("name,cycle", [("sphere", 4), ("flower", 7), ("disk", 3)])
+def test_assembly_is_bitwise_reproducible(name, cycle):
+    """The merge adds the contributions of one matrix entry in a fixed order (match.any groups, ascending lanes): both
+    orientations and both products are bit-identical from run to run, hanging-node rows included."""
+    bg, im = make_config(name, cycle, band_only=cycle > 3, device="cuda")
+    assert bg.c_dof.numel() > 0
+    runs = []
+    for rep in range(3):
+        ctx = coupling.make_context(bg, im, on_device=True, boxes=True)
+        ctx.intersect(3, 1e-15)
+        _, col, val = ctx.csr(device="cuda")
+        _, colt, valt = ctx.csr(transpose=True, device="cuda")
+        z = ctx.spmv(torch.ones(bg.n_dofs, dtype=torch.float64, device="cuda"), transpose=True)
+        y = ctx.spmv(torch.ones(im.n_dofs, dtype=torch.float64, device="cuda"), transpose=False)
+        assert ctx.info("merge_path") == 0
+        runs.append([t.clone() for t in (col, val, colt, valt, y, z)])
+        ctx.close()
+    for r in runs[1:]:
+        for a, b in zip(runs[0], r):
+            assert torch.equal(a, b)
