@@ -589,9 +589,20 @@ def run_e2e(args, torch, dist, _lib, ctx, P, rank, world, dev, timed, get_fused,
         io["d2h"] = sum(t.numel() * t.element_size() for t in state["out"]) + yh.numel() * 8 + zh.numel() * 8
         return counts
 
+    trace = os.environ.get("NMGPU_BENCH_TRACE") == "1" and rank == 0
+    tr = []
+
+    def mark(label, t0):
+        if trace:
+            tr.append("%s %.1f" % (label, (time.perf_counter() - t0) * 1e3))
+        return time.perf_counter()
+
     def step_local():
+        t0 = time.perf_counter()
         counts = assemble_host()
+        t0 = mark("assemble_host", t0)
         nr = ctx.n_rows_local()
+        t0 = mark("n_rows", t0)
         if world == 1:
             ctx.spmv_local(xh, transpose=False, out=yh[:nr])                      # Ct.vmult, touched rows only
             y_bytes = nr * 8
@@ -606,14 +617,21 @@ def run_e2e(args, torch, dist, _lib, ctx, P, rank, world, dev, timed, get_fused,
                 yy = op.vmult(xg) if op is not None else sharded_op.vmult(xg)
                 ctx.global_to_local(_lib.NM_LOCAL_ROWS, yy, yh[:nr])              # replicated result: read the touched rows
                 y_bytes = nr * 8
+        t0 = mark("ct_vmult", t0)
         ctx.spmv_local(uh[:nr], transpose=True, out=zh)                           # C.Tvmult, this shard's cells
+        t0 = mark("c_tvmult", t0)
         buf = csr_bufs[state["k"] % len(csr_bufs)]
         state["k"] += 1
         if pipelined:
             ctx.sync_downloads()     # the previous step's matrix: it left the device under this step's uploads and kernels
+            t0 = mark("sync_downloads", t0)
             state["out"] = ctx.csr_compact(out=buf, asynchronous=True)
         else:
             state["out"] = ctx.csr_compact(out=buf)
+        t0 = mark("readback_call", t0)
+        if trace:
+            sys.stderr.write("e2e step: " + " | ".join(tr) + "\n")
+            del tr[:]
         io["h2d"] = h2d_in + xh.numel() * 8 + nr * 8
         io["d2h"] = sum(t.numel() * t.element_size() for t in state["out"]) + y_bytes + zh.numel() * 8
         return counts

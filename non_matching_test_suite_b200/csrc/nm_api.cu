@@ -71,7 +71,7 @@ static std::vector<DevBuf *> all_buffers(nm_ctx *c)
           &c->a_rowptr, &c->a_rowptr32, &c->a_col, &c->a_val, &c->a_cursor, &c->scan_tmp, &c->scratch_a, &c->scratch_b, &c->stage_x,
           &c->stage_y, &c->h2d_stage, &c->nit_cnt, &c->nit_keys, &c->nit_vals, &c->nit_rkeys, &c->nit_rvals, &c->nit_rowptr,
           &c->nit_col, &c->nit_val, &c->nit_rhs, &c->row_bits, &c->row_prefix, &c->row_ids, &c->out_ids, &c->out_len, &c->glob_im,
-          &c->glob_dof, &c->brk_hdr, &c->brk_bit};
+          &c->glob_dof, &c->brk_hdr, &c->brk_bit, &c->clip_lut};
 }
 
 static void free_all(nm_ctx *c)

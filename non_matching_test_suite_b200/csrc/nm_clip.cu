@@ -13,6 +13,8 @@
 // (x - lo), which is exact in sign and keeps full precision for band cells of size 1e-6.
 #include "nm_common.cuh"
 #include "nm_predicates.cuh"
+#include "nm_clip_core.cuh"
+using namespace nmclip;
 
 namespace {
 
@@ -165,61 +167,6 @@ __device__ inline void clip_step(const Poly &in, Poly &out, double bound)
   out.n = m;
 }
 
-
-// Separating-axis test triangle vs box [0,H] (box normals, triangle normal, 9 edge cross
-// products).  Conservative on equality (touching = overlap); used only to keep triangles that
-// cannot contribute out of the clipping stage.
-__device__ inline bool tri_box_overlap(const double (*v)[3], const double *H)
-{
-  const double h[3] = {0.5 * H[0], 0.5 * H[1], 0.5 * H[2]};
-  double p[3][3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int k = 0; k < 3; ++k) p[i][k] = v[i][k] - h[k];
-  bool sep = false;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const double mn = fmin(p[0][k], fmin(p[1][k], p[2][k])), mx = fmax(p[0][k], fmax(p[1][k], p[2][k]));
-    sep |= mn > h[k] || mx < -h[k];
-  }
-  const double f[3][3] = {{p[1][0] - p[0][0], p[1][1] - p[0][1], p[1][2] - p[0][2]},
-                          {p[2][0] - p[1][0], p[2][1] - p[1][1], p[2][2] - p[1][2]},
-                          {p[0][0] - p[2][0], p[0][1] - p[2][1], p[0][2] - p[2][2]}};
-  {
-    const double nx = f[0][1] * f[1][2] - f[0][2] * f[1][1], ny = f[0][2] * f[1][0] - f[0][0] * f[1][2], nz = f[0][0] * f[1][1] - f[0][1] * f[1][0];
-    const double d = nx * p[0][0] + ny * p[0][1] + nz * p[0][2];
-    const double r = h[0] * fabs(nx) + h[1] * fabs(ny) + h[2] * fabs(nz);
-    sep |= fabs(d) > r;
-  }
-#ifndef NM_SAT_NO_CROSS
-  // axes e_i x f_j: the two end points of edge j project to the same value, so two projections
-  // (edge start, opposite vertex) bound the triangle
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    const int ia = j, ib = (j + 2) % 3;
-    {  // e_x x f_j = (0, -fz, fy)
-      const double a = -f[j][2], b = f[j][1];
-      const double q0 = a * p[ia][1] + b * p[ia][2], q1 = a * p[ib][1] + b * p[ib][2];
-      const double r = h[1] * fabs(a) + h[2] * fabs(b);
-      sep |= fmin(q0, q1) > r || fmax(q0, q1) < -r;
-    }
-    {  // e_y x f_j = (fz, 0, -fx)
-      const double a = f[j][2], b = -f[j][0];
-      const double q0 = a * p[ia][0] + b * p[ia][2], q1 = a * p[ib][0] + b * p[ib][2];
-      const double r = h[0] * fabs(a) + h[2] * fabs(b);
-      sep |= fmin(q0, q1) > r || fmax(q0, q1) < -r;
-    }
-    {  // e_z x f_j = (-fy, fx, 0)
-      const double a = -f[j][1], b = f[j][0];
-      const double q0 = a * p[ia][0] + b * p[ia][1], q1 = a * p[ib][0] + b * p[ib][1];
-      const double r = h[0] * fabs(a) + h[1] * fabs(b);
-      sep |= fmin(q0, q1) > r || fmax(q0, q1) < -r;
-    }
-  }
-#endif
-  return !sep;
-}
 
 template <class F>
 __device__ inline void triangle_in_box(const double (*tri)[3], const double *H, F &&visit_subtriangle)
@@ -429,185 +376,6 @@ __global__ void __launch_bounds__(128) clip_local_kernel(uint64_t n_cand, const 
 // which is what the reference's degree-5 rule evaluates exactly for the Q1 x P0 integrand
 // (degree <= 3 on a planar piece; SURVEY.md rule R1).  The items of one candidate sit next to
 // each other in the ring, so they are combined with two shuffles in a fixed order.
-struct ItemOut {
-  double area2;   // sum of J = 2 * area over kept sub-triangles
-  double m[7];    // A-weighted sums for u, v, w, uv, uw, vw, uvw (constants applied at the end)
-  unsigned nfan, dropped;
-};
-
-// Stage-2 work of one (candidate, triangle) item.
-//
-// The polygon is never copied: vertices live in a pool (3 originals + at most 2 per plane <= 15,
-// local memory); the polygon is a list of 4-bit pool indices packed in one 64-bit register, and a
-// second register holds, position by position, the 6-bit Cohen-Sutherland outcode of each vertex
-// (one "inside" bit per box plane, computed once when the vertex is created).  Classifying the
-// polygon against a plane is a mask of that register, the inside run is found with ffs on the
-// strided bits, and the new polygon is spliced with shifts -- no loop over vertices and no memory
-// traffic except for the (at most two) edge/plane crossings.
-struct VPool {
-  double c[3][16];
-};
-
-__device__ inline unsigned outcode(double x, double y, double z, const double *H)
-{
-  return (x >= 0.0 ? 1u : 0u) | (x <= H[0] ? 2u : 0u) | (y >= 0.0 ? 4u : 0u) | (y <= H[1] ? 8u : 0u) | (z >= 0.0 ? 16u : 0u) |
-         (z <= H[2] ? 32u : 0u);
-}
-
-// Clipped polygon of one (cell, triangle) item: pool vertices in cell-local coordinates, index list,
-// vertex count, unit normal of the parent triangle.  Shared by the moment kernel and the quadrature
-// emission so that both see exactly the same fan triangles (same count of points per pair).
-struct ClippedPoly {
-  VPool P;
-  unsigned long long poly;
-  int n;
-  double nx, ny, nz;
-};
-
-__device__ inline bool item_clip_polygon(const double *__restrict__ box, const double *__restrict__ quad, int t, ClippedPoly &C)
-{
-  VPool &P = C.P;
-  const double lo[3] = {box[0], box[1], box[2]};
-  const double H[3] = {box[4] - lo[0], box[5] - lo[1], box[6] - lo[2]};
-  const int iv[3] = {t == 0 ? 1 : 0, t <= 1 ? 2 : 1, t <= 2 ? 3 : 2};
-  unsigned long long code = 0;         // 6 bits per polygon position
-#pragma unroll
-  for (int v = 0; v < 3; ++v) {
-    const double x = quad[iv[v] * 3 + 0] - lo[0], y = quad[iv[v] * 3 + 1] - lo[1], z = quad[iv[v] * 3 + 2] - lo[2];
-    P.c[0][v] = x; P.c[1][v] = y; P.c[2][v] = z;
-    code |= (unsigned long long)outcode(x, y, z, H) << (6 * v);
-  }
-  // unit normal of the parent triangle: J of a coplanar sub-triangle = |cross . n|
-  double nx, ny, nz;
-  {
-    const double e1[3] = {P.c[0][1] - P.c[0][0], P.c[1][1] - P.c[1][0], P.c[2][1] - P.c[2][0]};
-    const double e2[3] = {P.c[0][2] - P.c[0][0], P.c[1][2] - P.c[1][0], P.c[2][2] - P.c[2][0]};
-    nx = e1[1] * e2[2] - e1[2] * e2[1]; ny = e1[2] * e2[0] - e1[0] * e2[2]; nz = e1[0] * e2[1] - e1[1] * e2[0];
-    const double n2 = nx * nx + ny * ny + nz * nz;
-    if (!(n2 > 0.0)) return false;
-    const double inv = rsqrt(n2);
-    nx *= inv; ny *= inv; nz *= inv;
-  }
-  unsigned long long poly = 0x210ULL;  // pool indices, 4 bits per polygon position
-  int n = 3, nv = 3;
-  constexpr unsigned long long M6 = 0x0041041041041041ULL;  // bit 0 of every 6-bit group
-  // Every lane walks only the planes that cut ITS polygon (lowest first): the trip count of the warp is the largest
-  // number of cutting planes of a lane, not six, and no lane idles through planes it does not need.  A plane that has
-  // been applied is all-inside afterwards (new vertices carry `forced`), so it is never picked again.
-#pragma unroll 1
-  while (true) {
-    // AND of the outcodes of all n positions (positions >= n read as inside)
-    const unsigned long long cf = code | ~((1ULL << (6 * n)) - 1ULL);
-    const unsigned long long a1 = cf & (cf >> 30);            // groups 0..4 &= groups 5..9
-    const unsigned long long a2 = a1 & (a1 >> 12);            // group 0 &= 2, group 1 &= 3
-    const unsigned all_in = (unsigned)(a2 & (a2 >> 6) & (a1 >> 24)) & 63u;
-    if (all_in == 63u) break;
-    const int p = __ffs(~all_in & 63u) - 1;
-    const unsigned long long full6 = M6 & ((1ULL << (6 * n)) - 1ULL);
-    const unsigned long long in6 = (code >> p) & full6;
-    if (in6 == 0ULL) return false;
-    const int axis = p >> 1;
-    const double sgn = (p & 1) ? -1.0 : 1.0, bound = (p & 1) ? H[axis] : 0.0;
-    const unsigned long long prev6 = ((in6 << 6) | (in6 >> (6 * (n - 1)))) & full6;       // position i: vertex i-1 inside
-    const int s6 = __ffsll((long long)(in6 & ~prev6)) - 1;                                  // run start (bit index)
-    const int s = __popcll(M6 & ((1ULL << s6) - 1ULL));
-    const unsigned long long rot6 = ((in6 >> s6) | (in6 << (6 * n - s6))) & full6;
-    const int l6 = __ffsll((long long)(~rot6 & full6)) - 1;                                 // run length (bit index), < 6n
-    const int len = __popcll(M6 & ((1ULL << l6) - 1ULL));
-    // both lists rotated so that the run comes first
-    const unsigned long long pr = (poly >> (4 * s)) | (poly << (4 * (n - s)));
-    const unsigned long long cr = (code >> s6) | (code << (6 * n - s6));
-    const unsigned forced = (2u << p) - 1u;   // planes already applied count as inside for a new vertex
-    unsigned long long np = 0, nc = 0;
-    int m = 0;
-    // The pool lives in local memory: fetch the four end points of the entering and the leaving edge in ONE round of
-    // loads (all indices come from the bit lists), then work in registers.
-    const int ve_p = (int)((poly >> (4 * (s == 0 ? n - 1 : s - 1))) & 15u), ve_q = (int)(pr & 15u);        // outside -> first inside
-    const int vl_p = (int)((pr >> (4 * (len - 1))) & 15u), vl_q = (int)((pr >> (4 * len)) & 15u);           // last inside -> outside
-    double ep[3], eq[3], lp[3], lq[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { ep[k] = P.c[k][ve_p]; eq[k] = P.c[k][ve_q]; lp[k] = P.c[k][vl_p]; lq[k] = P.c[k][vl_q]; }
-    const double e_dp = sgn * ((axis == 0 ? ep[0] : axis == 1 ? ep[1] : ep[2]) - bound);
-    const double e_dq = sgn * ((axis == 0 ? eq[0] : axis == 1 ? eq[1] : eq[2]) - bound);
-    const double l_dp = sgn * ((axis == 0 ? lp[0] : axis == 1 ? lp[1] : lp[2]) - bound);
-    const double l_dq = sgn * ((axis == 0 ? lq[0] : axis == 1 ? lq[1] : lq[2]) - bound);
-    if (e_dq > 0.0) {  // entering edge
-      const double tt = e_dp * __drcp_rn(e_dp - e_dq);
-      double x[3];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) x[k] = ep[k] + tt * (eq[k] - ep[k]);
-      if (axis == 0) x[0] = bound; else if (axis == 1) x[1] = bound; else x[2] = bound;  // on the plane by construction
-#pragma unroll
-      for (int k = 0; k < 3; ++k) P.c[k][nv] = x[k];
-      np = (unsigned long long)nv;
-      nc = (unsigned long long)(outcode(x[0], x[1], x[2], H) | forced);
-      m = 1;
-      ++nv;
-    }
-    np |= (pr & ((1ULL << (4 * len)) - 1ULL)) << (4 * m);
-    nc |= (cr & ((1ULL << (6 * len)) - 1ULL)) << (6 * m);
-    m += len;
-    if (l_dp > 0.0) {  // leaving edge
-      const double tt = l_dp * __drcp_rn(l_dp - l_dq);
-      double x[3];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) x[k] = lp[k] + tt * (lq[k] - lp[k]);
-      if (axis == 0) x[0] = bound; else if (axis == 1) x[1] = bound; else x[2] = bound;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) P.c[k][nv] = x[k];
-      np |= (unsigned long long)nv << (4 * m);
-      nc |= (unsigned long long)(outcode(x[0], x[1], x[2], H) | forced) << (6 * m);
-      ++m;
-      ++nv;
-    }
-    poly = np;
-    code = nc;
-    n = m;
-    if (n < 3) return false;
-  }
-  C.poly = poly; C.n = n; C.nx = nx; C.ny = ny; C.nz = nz;
-  return true;
-}
-
-__device__ inline void item_clip_moments(const double *__restrict__ box, const double *__restrict__ quad, int t, double tol, ItemOut &o)
-{
-  ClippedPoly C;
-  if (!item_clip_polygon(box, quad, t, C)) return;
-  const VPool &P = C.P;
-  const unsigned long long poly = C.poly;
-  const int n = C.n;
-  const double nx = C.nx, ny = C.ny, nz = C.nz;
-  const double H[3] = {box[4] - box[0], box[5] - box[1], box[6] - box[2]};
-  const double ih[3] = {__drcp_rn(H[0]), __drcp_rn(H[1]), __drcp_rn(H[2])};
-  const int v0 = (int)(poly & 15u), v1 = (int)((poly >> 4) & 15u);
-  const double ax = P.c[0][v0], ay = P.c[1][v0], az = P.c[2][v0];
-  const double f0 = ax * ih[0], g0 = ay * ih[1], h0 = az * ih[2];
-  double px = P.c[0][v1], py = P.c[1][v1], pz = P.c[2][v1];
-  double f1 = px * ih[0], g1 = py * ih[1], h1 = pz * ih[2];
-  for (int j = 2; j < n; ++j) {
-    const int vj = (int)((poly >> (4 * j)) & 15u);
-    const double qx = P.c[0][vj], qy = P.c[1][vj], qz = P.c[2][vj];
-    const double f2 = qx * ih[0], g2 = qy * ih[1], h2 = qz * ih[2];
-    const double e1x = px - ax, e1y = py - ay, e1z = pz - az, e2x = qx - ax, e2y = qy - ay, e2z = qz - az;
-    const double J = fabs((e1y * e2z - e1z * e2y) * nx + (e1z * e2x - e1x * e2z) * ny + (e1x * e2y - e1y * e2x) * nz);
-    if (0.25 * J * J > tol * tol) {                      // squared_area > tol^2     intersections.cc:477,493
-      if (J < 1e-12) {                                   // intersections.cc:710
-        o.dropped++;
-      } else {
-        const double Sf = f0 + f1 + f2, Sg = g0 + g1 + g2, Sh = h0 + h1 + h2;
-        const double fg = f0 * g0 + f1 * g1 + f2 * g2, fh = f0 * h0 + f1 * h1 + f2 * h2, gh = g0 * h0 + g1 * h1 + g2 * h2;
-        const double fgh = f0 * g0 * h0 + f1 * g1 * h1 + f2 * g2 * h2;
-        o.area2 += J;
-        o.m[0] += J * Sf; o.m[1] += J * Sg; o.m[2] += J * Sh;
-        o.m[3] += J * (Sf * Sg + fg); o.m[4] += J * (Sf * Sh + fh); o.m[5] += J * (Sg * Sh + gh);
-        o.m[6] += J * (Sf * Sg * Sh + Sf * gh + Sg * fh + Sh * fg + 2.0 * fgh);
-        o.nfan++;
-      }
-    }
-    px = qx; py = qy; pz = qz; f1 = f2; g1 = g2; h1 = h2;
-  }
-}
-
 #ifndef CM_MINB
 #define CM_MINB 3
 #endif
@@ -621,9 +389,12 @@ __global__ void __launch_bounds__(CM_WARPS * 32, CM_MINB) clip_moments3_kernel(
     uint64_t n_cand, const uint32_t *__restrict__ cand_im, const uint32_t *__restrict__ cand_bg, const double *__restrict__ bg_box,
     const double *__restrict__ im_verts, const uint8_t *__restrict__ split, const double *__restrict__ im_measure, double tol,
     unsigned nq_per_tri, double *__restrict__ sumw_out, double *__restrict__ local_out, uint16_t *__restrict__ nq_out,
-    uint8_t *__restrict__ acc_out, unsigned long long *counters)
+    uint8_t *__restrict__ acc_out, unsigned long long *counters, const uint32_t *__restrict__ lut_global)
 {
   __shared__ uint32_t s_ring[CM_WARPS][128];
+  __shared__ uint32_t s_lut[256];   // section polygons: cyclic order of the cut box edges per corner sign pattern
+  for (unsigned i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = lut_global[i];
+  __syncthreads();
   const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   uint32_t *ring = s_ring[w];
   const uint64_t wstart = ((uint64_t)blockIdx.x * CM_WARPS + w) * (32 * CM_CHUNKS);
@@ -652,7 +423,7 @@ __global__ void __launch_bounds__(CM_WARPS * 32, CM_MINB) clip_moments3_kernel(
         for (int v = 0; v < 3; ++v)
 #pragma unroll
           for (int k = 0; k < 3; ++k) tri[v][k] = quad[iv[v] * 3 + k] - box[k];
-        if (tri_box_overlap(tri, H)) { items |= (unsigned)t << (2 * nitems); ++nitems; }
+        if (tri_gate(tri, H)) { items |= (unsigned)t << (2 * nitems); ++nitems; }
       }
       if (nitems == 0) { sumw_out[c] = 0.0; acc_out[c] = 0; nq_out[c] = 0; }
     }
@@ -684,7 +455,7 @@ __global__ void __launch_bounds__(CM_WARPS * 32, CM_MINB) clip_moments3_kernel(
       const uint64_t cc = wstart + cl;
       if (on) {
         m = cand_im[cc];
-        item_clip_moments(bg_box + (uint64_t)cand_bg[cc] * 8, im_verts + (uint64_t)m * 12, (int)(it & 3), tol, o);
+        item_moments(bg_box + (uint64_t)cand_bg[cc] * 8, im_verts + (uint64_t)m * 12, (int)(it & 3), tol, s_lut, o);
       }
       // combine the (adjacent, at most three) items of a candidate in ring order
       const uint32_t cl1 = __shfl_down_sync(0xffffffffu, cl, 1), cl2 = __shfl_down_sync(0xffffffffu, cl, 2);
@@ -714,12 +485,9 @@ __global__ void __launch_bounds__(CM_WARPS * 32, CM_MINB) clip_moments3_kernel(
         const unsigned nq = ok ? nfan * nq_per_tri : 0u;
         nq_out[cc] = (uint16_t)nq;
         if (ok) {
-          const double M1 = sumw, Mu = tot[1] * (1.0 / 6.0), Mv = tot[2] * (1.0 / 6.0), Mw = tot[3] * (1.0 / 6.0);
-          const double Muv = tot[4] * (1.0 / 24.0), Muw = tot[5] * (1.0 / 24.0), Mvw = tot[6] * (1.0 / 24.0), Muvw = tot[7] * (1.0 / 120.0);
-          // phi_i = prod_k (bit_k(i) ? u_k : 1 - u_k)
-          const double l7 = Muvw, l3 = Muv - Muvw, l5 = Muw - Muvw, l6 = Mvw - Muvw;
-          const double l1 = Mu - Muv - l5, l2 = Mv - Muv - l6, l4 = Mw - Muw - l6;
-          const double l0 = M1 - (l1 + l2 + l3 + l4 + l5 + l6 + l7);
+          double l8[8], sw_;
+          moments_to_local(tot, sw_, l8);
+          const double l0 = l8[0], l1 = l8[1], l2 = l8[2], l3 = l8[3], l4 = l8[4], l5 = l8[5], l6 = l8[6], l7 = l8[7];
           double2 *dst = reinterpret_cast<double2 *>(local_out + cc * 8);
           dst[0] = make_double2(l0, l1); dst[1] = make_double2(l2, l3); dst[2] = make_double2(l4, l5); dst[3] = make_double2(l6, l7);
           c_acc++; c_nq += nq;
@@ -755,7 +523,7 @@ __global__ void emit_quadrature_kernel(uint64_t n_acc, const uint64_t *__restric
                                        const uint32_t *__restrict__ cand_bg, const double *__restrict__ bg_box,
                                        const double *__restrict__ im_verts, const uint8_t *__restrict__ split, double tol,
                                        const uint64_t *__restrict__ q_off, double *__restrict__ pts, double *__restrict__ wts,
-                                       unsigned long long *n_mismatch)
+                                       unsigned long long *n_mismatch, const uint32_t *__restrict__ lut)
 {
   const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_acc) return;
@@ -777,9 +545,9 @@ __global__ void emit_quadrature_kernel(uint64_t n_acc, const uint64_t *__restric
       double tri[3][3];
       for (int v = 0; v < 3; ++v)
         for (int k = 0; k < 3; ++k) tri[v][k] = quad[iv[v] * 3 + k] - box[k];
-      if (!tri_box_overlap(tri, H)) continue;
+      if (!tri_gate(tri, H)) continue;
       ClippedPoly C;
-      if (!item_clip_polygon(box, quad, t, C)) continue;
+      if (!item_polygon(box, quad, t, lut, C)) continue;
       const int v0 = (int)(C.poly & 15u);
       const double a[3] = {C.P.c[0][v0], C.P.c[1][v0], C.P.c[2][v0]};
       for (int j = 2; j < C.n; ++j) {
@@ -908,6 +676,13 @@ int nm_split_run(nm_ctx *ctx)
 
 static int upload_rule(nm_ctx *ctx)
 {
+  if (!ctx->clip_lut.p) {   // section polygons: cut box edges in cyclic order, per corner sign pattern (built once per context)
+    uint32_t lut[256];
+    section_lut_build(lut);
+    NM_TRY(nm_ensure(ctx, ctx->clip_lut, sizeof(lut)));
+    NM_CUDA(cudaMemcpyAsync(ctx->clip_lut.p, lut, sizeof(lut), cudaMemcpyHostToDevice, ctx->stream));
+    NM_SYNC(ctx);   // `lut` lives on this stack frame
+  }
   Rule r;
   if (!make_rule(ctx->dim1, ctx->degree, r))
     return nm_fail(ctx, NM_ERR_UNSUPPORTED, "QGaussSimplex<%d>(n_points_1D=%u) is not tabulated (supported: %s)", ctx->dim1,
@@ -939,7 +714,7 @@ int nm_clip_run(nm_ctx *ctx)
     clip_moments3_kernel<<<nm_blocks(nc, CM_WARPS * 32 * CM_CHUNKS), CM_WARPS * 32, 0, NM_LS(ctx)>>>(
         nc, ctx->cand_im.as<uint32_t>(), ctx->cand_bg.as<uint32_t>(), ctx->bg_box.as<double>(), ctx->im_verts.as<double>(),
         ctx->im_split.as<uint8_t>(), ctx->im_measure.as<double>(), ctx->tol, 7u, ctx->cand_sumw.as<double>(),
-        ctx->cand_local.as<double>(), ctx->cand_nq.as<uint16_t>(), ctx->cand_acc.as<uint8_t>(), cnt);
+        ctx->cand_local.as<double>(), ctx->cand_nq.as<uint16_t>(), ctx->cand_acc.as<uint8_t>(), cnt, ctx->clip_lut.as<uint32_t>());
   else if (d == 3)
     clip_local_kernel<3><<<B, T, 0, NM_LS(ctx)>>>(nc, ctx->cand_im.as<uint32_t>(), ctx->cand_bg.as<uint32_t>(), ctx->bg_box.as<double>(),
                                                    ctx->im_verts.as<double>(), ctx->im_split.as<uint8_t>(), ctx->im_measure.as<double>(),
@@ -1011,13 +786,13 @@ int nm_quadrature_emit(nm_ctx *ctx, uint64_t *q_offset, double *points, double *
     const uint32_t *ci = ctx->cand_im.as<uint32_t>(), *cb = ctx->cand_bg.as<uint32_t>();
     if (d == 3 && moment_path)
       emit_quadrature_kernel<3, true><<<B, 128, 0, NM_LS(ctx)>>>(na, acc_idx, ci, cb, ctx->bg_box.as<double>(), ctx->im_verts.as<double>(),
-                                                                ctx->im_split.as<uint8_t>(), ctx->tol, offs.as<uint64_t>(), pts_d, w_d, mismatch);
+                                                                ctx->im_split.as<uint8_t>(), ctx->tol, offs.as<uint64_t>(), pts_d, w_d, mismatch, ctx->clip_lut.as<uint32_t>());
     else if (d == 3)
       emit_quadrature_kernel<3, false><<<B, 128, 0, NM_LS(ctx)>>>(na, acc_idx, ci, cb, ctx->bg_box.as<double>(), ctx->im_verts.as<double>(),
-                                                                 ctx->im_split.as<uint8_t>(), ctx->tol, offs.as<uint64_t>(), pts_d, w_d, mismatch);
+                                                                 ctx->im_split.as<uint8_t>(), ctx->tol, offs.as<uint64_t>(), pts_d, w_d, mismatch, ctx->clip_lut.as<uint32_t>());
     else
       emit_quadrature_kernel<2, false><<<B, 128, 0, NM_LS(ctx)>>>(na, acc_idx, ci, cb, ctx->bg_box.as<double>(), ctx->im_verts.as<double>(), nullptr,
-                                                                 ctx->tol, offs.as<uint64_t>(), pts_d, w_d, mismatch);
+                                                                 ctx->tol, offs.as<uint64_t>(), pts_d, w_d, mismatch, ctx->clip_lut.as<uint32_t>());
     NM_CUDA(cudaGetLastError());
     unsigned long long h_mis = 0;
     NM_CUDA(cudaMemcpyAsync(&h_mis, mismatch, 8, cudaMemcpyDeviceToHost, ctx->stream));

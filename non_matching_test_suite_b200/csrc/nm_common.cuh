@@ -137,6 +137,7 @@ struct nm_ctx {
 
   // ---- scratch ----
   DevBuf scan_tmp, scratch_a, scratch_b, stage_x, stage_y, h2d_stage;
+  DevBuf clip_lut;            // 256-entry table of the section algorithm (nm_clip_core.cuh)
   DevBuf glob_im, glob_dof;   // global-numbered device scratch vectors of the products in local numbering
 
   // ---- timing ----

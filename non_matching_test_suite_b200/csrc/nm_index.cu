@@ -569,7 +569,8 @@ __global__ void __launch_bounds__(128) cand_probe_brick(BrickDev B, uint64_t n_i
 {
   constexpr int NVI = 1 << (D - 1), CPB = 128 / G, SH = nmbrick::BrickShape<D>::SH, NSL = 2;
   static_assert(G >= NSL * D, "one lane per (level slot, axis)");
-  __shared__ uint32_t s_ids[CPB][CAP];
+  static_assert(CAP % 4 == 0, "rows are read four ids at a time");
+  __shared__ __align__(16) uint32_t s_ids[CPB][CAP];
   __shared__ unsigned s_n[CPB];
   const unsigned g = threadIdx.x / G, l = threadIdx.x % G;
   const unsigned gbase = (threadIdx.x & 31) - l;
@@ -577,6 +578,7 @@ __global__ void __launch_bounds__(128) cand_probe_brick(BrickDev B, uint64_t n_i
   const uint64_t m = (uint64_t)blockIdx.x * CPB + g;
   if (m >= n_im) return;   // whole groups leave together
   if (l == 0) s_n[g] = 0;
+  for (unsigned k = l; k < (unsigned)CAP; k += G) s_ids[g][k] = 0xffffffffu;   // padding compares as "not smaller"
   // the bounding interval of the immersed cell along "my" axis
   const int ax = (int)(l % D), sl = (int)(l / D);
   double qlo, qhi;
@@ -616,7 +618,13 @@ __global__ void __launch_bounds__(128) cand_probe_brick(BrickDev B, uint64_t n_i
       const int s = t < T[0] ? 0 : 1;
       const int tt = s ? t - T[0] : t;
       const int n0 = s ? nb[1][0] : nb[0][0], n1 = s ? nb[1][1] : nb[0][1];
-      const int tx = tt % n0, ty = (tt / n0) % n1, tz = tt / (n0 * n1);
+      int tx, ty, tz;
+      if (n0 <= 2 && n1 <= 2) {   // the usual case (a query spans at most two bricks per axis): no integer division
+        tx = n0 == 2 ? (tt & 1) : 0;
+        const int r = n0 == 2 ? (tt >> 1) : tt;
+        ty = n1 == 2 ? (r & 1) : 0;
+        tz = n1 == 2 ? (r >> 1) : r;
+      } else { tx = tt % n0; ty = (tt / n0) % n1; tz = tt / (n0 * n1); }
       const int bx = (s ? b0[1][0] : b0[0][0]) + tx, by = (s ? b0[1][1] : b0[0][1]) + ty, bz = (s ? b0[1][2] : b0[0][2]) + tz;
       unsigned long long mask;
       uint32_t base;
@@ -638,10 +646,14 @@ __global__ void __launch_bounds__(128) cand_probe_brick(BrickDev B, uint64_t n_i
   if (l == 0) cnt[m] = total;
   if (total <= (unsigned)CAP) {
     uint32_t *row = tmp + m * CAP;
+    const uint4 *ids4 = reinterpret_cast<const uint4 *>(s_ids[g]);
     for (unsigned e = l; e < total; e += G) {
       const uint32_t v = s_ids[g][e];
       unsigned r = 0;
-      for (unsigned j = 0; j < total; ++j) r += s_ids[g][j] < v ? 1u : 0u;
+      for (unsigned j = 0; j < (total + 3) / 4; ++j) {
+        const uint4 q = ids4[j];
+        r += (q.x < v) + (q.y < v) + (q.z < v) + (q.w < v);
+      }
       row[r] = v;
     }
   }

@@ -221,26 +221,28 @@ __device__ __forceinline__ unsigned hash_claim(unsigned *keys, unsigned key, uns
   }
 }
 
-// vals[slot] += v for every lane of the group that carries a contribution (slot != NO_SLOT), in a FIXED order: lanes
-// that hit the same slot in this instruction are found with match.any, the lowest of them adds the values in ascending
-// lane order and is the only one that touches the slot.  No floating-point atomics: the sums are bit-reproducible.
-__device__ __forceinline__ void group_accumulate(unsigned gmask, unsigned wlane, double *vals, unsigned slot, double v)
+// Order-independent accumulation.  The contributions to one matrix entry arrive from several lanes in an order the
+// hardware chooses; floating-point adds would make the last bits depend on it.  They are therefore summed as 64-bit
+// FIXED-POINT integers (integer addition is associative, the shared-memory atomic is native): every contribution of an
+// immersed cell is scaled by 2^e, with e chosen from M = sum |sum_w| over the cell's accepted pairs such that
+// M 2^e lies in [2^59, 2^60) -- no entry can exceed M, so nothing overflows, and one unit is M 2^-60, far below the
+// rounding of the double-precision inputs (entries are >= 1e-4 M where it matters for the 1e-12 Frobenius bar).
+// The result is bit-identical from run to run and across row groupings.
+struct FixedScale {
+  double scale, inv;
+};
+__device__ __forceinline__ FixedScale fixed_scale_for(double m_sum)
 {
-  const bool has = slot != NO_SLOT;
-  const unsigned grp = __match_any_sync(gmask, has ? slot : (0x80000000u | wlane));   // a lane without a contribution matches nobody
-  const bool leader = has && (unsigned)(__ffs(grp) - 1) == wlane;
-  const unsigned mx = __reduce_max_sync(gmask, has ? (unsigned)__popc(grp) : 1u);
-  double sum = v;
-  unsigned rest = grp & (grp - 1u);   // the other lanes of my slot, ascending
-  for (unsigned j = 1; j < mx; ++j) {
-    const bool more = rest != 0u;
-    const int src = more ? __ffs(rest) - 1 : (int)wlane;
-    rest &= rest - 1u;
-    const double o = __shfl_sync(gmask, v, src);
-    if (leader && more) sum += o;
-  }
-  if (leader) vals[slot] += sum;
-  __syncwarp(gmask);
+  int e = 0;
+  (void)frexp(m_sum, &e);          // m_sum = f 2^e, f in [0.5, 1)
+  FixedScale f;
+  f.scale = ldexp(1.0, 60 - e);
+  f.inv = ldexp(1.0, e - 60);
+  return f;
+}
+__device__ __forceinline__ void fixed_add(long long *vals, unsigned slot, double v, const FixedScale &f)
+{
+  atomicAdd(reinterpret_cast<unsigned long long *>(&vals[slot]), (unsigned long long)__double2ll_rn(v * f.scale));
 }
 
 template <int NL>
@@ -250,10 +252,11 @@ __global__ void __launch_bounds__(256) merge_rows_hash(uint64_t n_im, const uint
                                                        const int32_t *__restrict__ line_of, const uint64_t *__restrict__ c_ptr,
                                                        const uint32_t *__restrict__ c_master, const double *__restrict__ c_weight,
                                                        const uint64_t *__restrict__ rowstart, uint32_t *__restrict__ rowlen,
-                                                       uint32_t *__restrict__ out_col, double *__restrict__ out_val)
+                                                       uint32_t *__restrict__ out_col, double *__restrict__ out_val,
+                                                       const double *__restrict__ sumw)
 {
   __shared__ unsigned s_keys[8][HASH_SLOTS];
-  __shared__ double s_vals[8][HASH_SLOTS];
+  __shared__ long long s_vals[8][HASH_SLOTS];
   __shared__ unsigned s_list[8][HASH_SLOTS];
   const unsigned w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint64_t m = (uint64_t)blockIdx.x * 8 + w;
@@ -262,12 +265,18 @@ __global__ void __launch_bounds__(256) merge_rows_hash(uint64_t n_im, const uint
   if (cp > HASH_CAP) return;  // sort-based kernels take these
   if (cp == 0) { if (lane == 0) rowlen[m] = 0; return; }
   unsigned *keys = s_keys[w];
-  double *vals = s_vals[w];
+  long long *vals = s_vals[w];
   unsigned *list = s_list[w];
 #pragma unroll
-  for (int k = 0; k < HASH_SLOTS / 32; ++k) { keys[lane + 32 * k] = HASH_EMPTY; vals[lane + 32 * k] = 0.0; }
+  for (int k = 0; k < HASH_SLOTS / 32; ++k) { keys[lane + 32 * k] = HASH_EMPTY; vals[lane + 32 * k] = 0; }
   __syncwarp();
   const uint64_t p0 = cand_ptr[m], p1 = cand_ptr[m + 1];
+  double m_sum = 0.0;
+  for (uint64_t p = p0 + lane; p < p1; p += 32)
+    if (acc[p]) m_sum += fabs(sumw[p]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m_sum += __shfl_xor_sync(0xffffffffu, m_sum, o);
+  const FixedScale fs = fixed_scale_for(m_sum);
   for (uint64_t base = p0; base < p1; base += 32) {
     const uint64_t p = base + lane;
     const bool on = p < p1 && acc[p];
@@ -283,22 +292,18 @@ __global__ void __launch_bounds__(256) merge_rows_hash(uint64_t n_im, const uint
     }
 #pragma unroll
     for (int i = 0; i < NL; ++i) {
-      // one (pair, vertex) contribution per lane, added in lane order (group_accumulate): no floating-point atomics
-      int32_t ln = -1;
-      unsigned s = NO_SLOT;
       if (on) {
-        ln = line_of[dofs[i]];
-        s = hash_insert(keys, dofs[i]);   // keep_constrained_entries: a constrained row stays in the pattern, structurally zero
+        const int32_t ln = line_of[dofs[i]];
+        const unsigned s = hash_insert(keys, dofs[i]);
+        if (ln < 0) {
+          fixed_add(vals, s, v[i], fs);
+        } else {
+          // keep_constrained_entries: the constrained row stays in the pattern, structurally zero;
+          // its value goes to the masters of the line (none for a Dirichlet row)
+          for (uint64_t k = c_ptr[ln]; k < c_ptr[ln + 1]; ++k) fixed_add(vals, hash_insert(keys, c_master[k]), c_weight[k] * v[i], fs);
+        }
       }
-      group_accumulate(0xffffffffu, lane, vals, (on && ln < 0) ? s : NO_SLOT, v[i]);
-      const unsigned nm = (on && ln >= 0) ? (unsigned)(c_ptr[ln + 1] - c_ptr[ln]) : 0u;   // masters of the line (none for a Dirichlet row)
-      const unsigned nm_max = __reduce_max_sync(0xffffffffu, nm);
-      for (unsigned k = 0; k < nm_max; ++k) {
-        unsigned t = NO_SLOT;
-        double wv = 0.0;
-        if (k < nm) { const uint64_t kk = c_ptr[ln] + k; t = hash_insert(keys, c_master[kk]); wv = c_weight[kk] * v[i]; }
-        group_accumulate(0xffffffffu, lane, vals, t, wv);
-      }
+      __syncwarp();
     }
   }
   // distinct keys -> list
@@ -320,7 +325,7 @@ __global__ void __launch_bounds__(256) merge_rows_hash(uint64_t n_im, const uint
     unsigned rank = 0;
     for (unsigned f = 0; f < D; ++f) rank += keys[list[f]] < key ? 1u : 0u;
     out_col[dst + rank] = key;
-    out_val[dst + rank] = vals[s];
+    out_val[dst + rank] = (double)vals[s] * fs.inv;
   }
   if (lane == 0) rowlen[m] = D;
 }
@@ -337,6 +342,7 @@ constexpr int FAST_ROWS = 64;   // consecutive immersed cells per group
 template <int NL, int GROUP, int SLOTS>
 __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint64_t *__restrict__ cand_ptr,
                                                        const uint32_t *__restrict__ cand_bg, const uint8_t *__restrict__ acc,
+                                                       const double *__restrict__ sumw,
                                                        const double *__restrict__ local, const uint32_t *__restrict__ bg_dofs,
                                                        const int32_t *__restrict__ line_of, const uint64_t *__restrict__ c_ptr,
                                                        const uint32_t *__restrict__ c_master, const double *__restrict__ c_weight,
@@ -348,7 +354,7 @@ __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint
   constexpr int NG = 256 / GROUP;                 // groups per block
   constexpr unsigned CAP = SLOTS * 3 / 4;         // distinct dofs a group accepts
   __shared__ unsigned s_keys[NG][SLOTS];
-  __shared__ double s_vals[NG][SLOTS];
+  __shared__ long long s_vals[NG][SLOTS];
   __shared__ unsigned s_list[NG][SLOTS];
   __shared__ __align__(16) unsigned s_dkey[NG][SLOTS];
   __shared__ unsigned s_cand[NG][GROUP];
@@ -356,7 +362,7 @@ __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint
   const unsigned gbase = (threadIdx.x & 31) - lane;                      // first lane of the group inside its warp
   const unsigned gmask = GROUP == 32 ? 0xffffffffu : (((1u << GROUP) - 1u) << gbase);
   unsigned *keys = s_keys[g];
-  double *vals = s_vals[g];
+  long long *vals = s_vals[g];
   unsigned *list = s_list[g];
   unsigned *dkey = s_dkey[g];
   unsigned *cands = s_cand[g];
@@ -365,9 +371,15 @@ __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint
   unsigned chunk_left = 0;
   for (uint64_t m = m0; m < m0 + rows_per_group && m < n_im; ++m) {
 #pragma unroll
-    for (int k = 0; k < SLOTS / GROUP; ++k) { keys[lane + GROUP * k] = HASH_EMPTY; vals[lane + GROUP * k] = 0.0; }
+    for (int k = 0; k < SLOTS / GROUP; ++k) { keys[lane + GROUP * k] = HASH_EMPTY; vals[lane + GROUP * k] = 0; }
     __syncwarp(gmask);
     const uint64_t p0 = cand_ptr[m], p1 = cand_ptr[m + 1];
+    double m_sum = 0.0;   // bound of every entry of this cell: fixes the fixed-point scale
+    for (uint64_t p = p0 + lane; p < p1; p += GROUP)
+      if (acc[p]) m_sum += fabs(sumw[p]);
+#pragma unroll
+    for (int o = GROUP / 2; o > 0; o >>= 1) m_sum += __shfl_xor_sync(gmask, m_sum, o);
+    const FixedScale fs = fixed_scale_for(m_sum);
     unsigned claimed = 0;
     bool failed = false;   // table full: bounded probing gives up instead of spinning
     for (uint64_t base = p0; base < p1; base += GROUP) {
@@ -399,19 +411,17 @@ __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint
         }
         // keep_constrained_entries: a constrained row stays in the pattern as a structural zero (its slot is claimed,
         // nothing is added); its value goes to the masters of the line (none for a Dirichlet row)
-        group_accumulate(gmask, gbase + lane, vals, (on_e && !failed && ln < 0) ? s : NO_SLOT, v);
-        const unsigned nm = (on_e && !failed && ln >= 0) ? (unsigned)(c_ptr[ln + 1] - c_ptr[ln]) : 0u;
-        const unsigned nm_max = __reduce_max_sync(gmask, nm);
-        for (unsigned k = 0; k < nm_max; ++k) {
-          unsigned t = NO_SLOT;
-          double wv = 0.0;
-          if (k < nm && !failed) {
-            const uint64_t kk = c_ptr[ln] + k;
-            t = hash_claim<SLOTS>(keys, c_master[kk], claimed, failed);
-            wv = c_weight[kk] * v;
+        if (on_e && !failed) {
+          if (ln < 0) {
+            fixed_add(vals, s, v, fs);
+          } else {
+            for (uint64_t k = c_ptr[ln]; k < c_ptr[ln + 1] && !failed; ++k) {
+              const unsigned t = hash_claim<SLOTS>(keys, c_master[k], claimed, failed);
+              if (!failed) fixed_add(vals, t, c_weight[k] * v, fs);
+            }
           }
-          group_accumulate(gmask, gbase + lane, vals, failed ? NO_SLOT : t, wv);
         }
+        __syncwarp(gmask);
       }
     }
     const unsigned total_claimed = __reduce_add_sync(gmask, claimed);
@@ -459,11 +469,11 @@ __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint
       }
       // per-dof entry counts for the transpose -- or, in compact-row mode, only the bitmap of touched dofs
       if (ea < D) {
-        out_col[dst + ra] = ka; out_val[dst + ra] = vals[list[ea]];
+        out_col[dst + ra] = ka; out_val[dst + ra] = (double)vals[list[ea]] * fs.inv;
         if (mark_bits) atomicOr(&a_cnt[ka >> 5], 1u << (ka & 31)); else atomicAdd(&a_cnt[ka], 1u);
       }
       if (eb < D) {
-        out_col[dst + rb] = kb; out_val[dst + rb] = vals[list[eb]];
+        out_col[dst + rb] = kb; out_val[dst + rb] = (double)vals[list[eb]] * fs.inv;
         if (mark_bits) atomicOr(&a_cnt[kb >> 5], 1u << (kb & 31)); else atomicAdd(&a_cnt[kb], 1u);
       }
     }
@@ -885,7 +895,8 @@ static int matrix_build_fast(nm_ctx *ctx, bool *done)
   NM_CUDA(cudaMemsetAsync(cursor, 0, 32, ctx->stream));   // bytes 160..191: the chunk cursor AND the problem flag (byte 176)
   KernelTimer km(ctx, NM_T_K_MERGE);
   merge_rows_fast<NL, GROUP, SLOTS><<<(unsigned)blocks, 256, 0, NM_LS(ctx)>>>(
-      n_im, ctx->cand_ptr.as<uint64_t>(), ctx->cand_bg.as<uint32_t>(), ctx->cand_acc.as<uint8_t>(), ctx->cand_local.as<double>(),
+      n_im, ctx->cand_ptr.as<uint64_t>(), ctx->cand_bg.as<uint32_t>(), ctx->cand_acc.as<uint8_t>(), ctx->cand_sumw.as<double>(),
+      ctx->cand_local.as<double>(),
       ctx->bg_dofs.as<uint32_t>(), ctx->line_of.as<int32_t>(), ctx->c_ptr.as<uint64_t>(), ctx->c_master.as<uint32_t>(),
       ctx->c_weight.as<double>(), ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(),
       ctx->c_val.as<double>(), capacity, cursor, problem, dof_marks, ctx->compact_rows ? 1 : 0, (uint32_t)n_rows, (unsigned)rpg, chunk);
@@ -959,7 +970,7 @@ static int matrix_build_t(nm_ctx *ctx)
         n_im, ctx->scratch_a.as<uint32_t>(), ctx->cand_ptr.as<uint64_t>(), ctx->cand_bg.as<uint32_t>(), ctx->cand_acc.as<uint8_t>(),
         ctx->cand_local.as<double>(), ctx->bg_dofs.as<uint32_t>(), ctx->line_of.as<int32_t>(), ctx->c_ptr.as<uint64_t>(),
         ctx->c_master.as<uint32_t>(), ctx->c_weight.as<double>(), ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(),
-        ctx->c_col.as<uint32_t>(), ctx->c_val.as<double>());
+        ctx->c_col.as<uint32_t>(), ctx->c_val.as<double>(), ctx->cand_sumw.as<double>());
     km.stop();
     if (h_hdr[3])
     merge_rows_warp<NL><<<nm_blocks(n_im, warps), warps * 32, smem, NM_LS(ctx)>>>(

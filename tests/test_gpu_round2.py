@@ -172,7 +172,7 @@ def test_from_quadrature_accumulates_repeated_pairs_and_checks_ranges():
     ctx.assemble_from_quadrature(im2.contiguous(), bg2.contiguous(), off2, info.points[idx].contiguous(), info.weights[idx].contiguous())
     _, _, val_twice = ctx.csr()
     assert (val_twice - val_once).norm() <= 1e-13 * val_once.norm()
-    bad = bg.dofs.clone(); bad[0, 0] = bg.n_dofs + 5
+    bad = bg.dofs.clone(); bad[int(info.space_cell[0]), 0] = bg.n_dofs + 5     # a cell the merge reads (it holds an accepted pair)
     ctx.set_background_dofs(bad.to(torch.int32).contiguous(), bg.n_dofs)
     with pytest.raises(_lib.NmError) as e:      # checked before the merge dereferences the table
         ctx.build_sparsity()
