@@ -668,7 +668,7 @@ def dropin_flow(torch, config, cycle):
     try:
         if not os.path.exists(exe):
             os.makedirs(os.path.dirname(exe), exist_ok=True)
-            subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "tests", "cpp", "stub"),
+            subprocess.check_call(["g++", "-std=c++17", "-O2", "-pthread", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "tests", "cpp", "stub"),
                                    os.path.join(ROOT, "tests", "cpp", "bench_dropin.cpp"), "-o", exe, "-L" + lib, "-lnmgpu", "-Wl,-rpath," + lib])
         bg, im = make_config(config, cycle, band_only=True, device="cuda")
         with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:

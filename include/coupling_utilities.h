@@ -34,9 +34,11 @@
 #include <deal.II/lac/affine_constraints.h>
 
 #include <cstdint>
+#include <algorithm>
 #include <cstdlib>
 #include <map>
 #include <memory>
+#include <thread>
 #include <tuple>
 #include <utility>
 #include <vector>
@@ -115,6 +117,35 @@ template <typename Info> bool is_own_result(const Session &s, const Info &info)
   return qf.size() > 0 && ql.size() > 0 && static_cast<const void *>(qf.get_points().data()) == s.own.first &&
          static_cast<const void *>(ql.get_points().data()) == s.own.last && qf.weight(0) == s.own.w_first &&
          ql.weight(ql.size() - 1) == s.own.w_last;
+}
+
+// Host threads for the embarrassingly parallel part of the marshalling (building the millions of Quadrature objects the
+// reference's return type demands).  NMGPU_HOST_THREADS overrides; the drivers' own threading is not touched.
+inline unsigned int host_threads()
+{
+  if (const char *e = std::getenv("NMGPU_HOST_THREADS"))
+    return std::max(1, std::atoi(e));
+  const unsigned int hw = std::thread::hardware_concurrency();
+  return hw == 0 ? 1u : std::min(hw, 8u);
+}
+
+template <typename F> void parallel_for(const std::size_t n, F &&body)
+{
+  const unsigned int nt = static_cast<unsigned int>(std::min<std::size_t>(host_threads(), n / 4096 + 1));
+  if (nt <= 1) {
+    for (std::size_t i = 0; i < n; ++i)
+      body(i);
+    return;
+  }
+  std::vector<std::thread> pool;
+  for (unsigned int t = 0; t < nt; ++t)
+    pool.emplace_back([&, t]() {
+      const std::size_t b = n * t / nt, e = n * (t + 1) / nt;
+      for (std::size_t i = b; i < e; ++i)
+        body(i);
+    });
+  for (auto &th : pool)
+    th.join();
 }
 
 inline void check(const Session &s, int rc)
@@ -397,17 +428,17 @@ collect_quadratures_on_overlapped_grids(const GridTools::Cache<dim0, spacedim> &
   nmgpu_detail::check(s, nm_get_pairs(s.ctx, im.data(), bg.data(), nullptr, NM_HOST));
   nmgpu_detail::check(s, nm_get_quadrature(s.ctx, off.data(), pts.data(), w.data(), NM_HOST));
 
-  std::vector<std::tuple<SpaceIt, ImmIt, Quadrature<spacedim>>> cells_with_quadratures;
-  cells_with_quadratures.reserve(counts.n_accepted);
-  for (std::uint64_t p = 0; p < counts.n_accepted; ++p) {
+  // one tuple per accepted pair, built in parallel: every tuple owns two heap vectors (what Quadrature<spacedim> is)
+  std::vector<std::tuple<SpaceIt, ImmIt, Quadrature<spacedim>>> cells_with_quadratures(counts.n_accepted);
+  nmgpu_detail::parallel_for(counts.n_accepted, [&](const std::size_t p) {
     const std::size_t nq = off[p + 1] - off[p];
     std::vector<Point<spacedim>> qp(nq);
     std::vector<double> qw(w.begin() + off[p], w.begin() + off[p + 1]);
     for (std::size_t k = 0; k < nq; ++k)
       for (unsigned int d = 0; d < spacedim; ++d)
         qp[k][d] = pts[(off[p] + k) * spacedim + d];
-    cells_with_quadratures.emplace_back(space_cells[bg[p]], immersed_cells[im[p]], Quadrature<spacedim>(std::move(qp), std::move(qw)));
-  }
+    cells_with_quadratures[p] = std::make_tuple(space_cells[bg[p]], immersed_cells[im[p]], Quadrature<spacedim>(std::move(qp), std::move(qw)));
+  });
   // remember what was handed out (the element storage does not move when the vector is returned)
   s.own.valid = true;
   s.own.size = cells_with_quadratures.size();

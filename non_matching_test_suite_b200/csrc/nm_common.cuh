@@ -44,6 +44,8 @@ struct nm_ctx {
   cudaStream_t copy_stream = nullptr;           // host->device copies of nm_assemble_host
   cudaStream_t down_stream = nullptr;           // device->host copies of nm_get_csr_compact(NM_HOST_ASYNC)
   cudaEvent_t ev_down_ready = nullptr, ev_down_done = nullptr;
+  void *pin[2] = {nullptr, nullptr};            // pinned bounce buffers for large transfers from / to pageable memory
+  cudaEvent_t ev_pin[2] = {nullptr, nullptr};
   bool download_pending = false;                // the next matrix build must wait for ev_down_done
   uint64_t n_syncs = 0;                         // host synchronisations with the stream (counter read-backs) since nm_create
   int index_kind = 0;                           // grid index in use: 0 = none yet, 1 = per-cell chains, 2 = brick bitmasks

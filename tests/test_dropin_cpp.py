@@ -18,7 +18,7 @@ BIN = os.path.join(ROOT, "tests", "cpp", "_build", "test_dropin")
 def build_driver():
     os.makedirs(os.path.dirname(BIN), exist_ok=True)
     lib = os.path.join(ROOT, "non_matching_test_suite_b200")
-    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-pthread", "-I" + os.path.join(ROOT, "include"),
            "-I" + os.path.join(ROOT, "tests", "cpp", "stub"), os.path.join(ROOT, "tests", "cpp", "test_dropin.cpp"), "-o", BIN,
            "-L" + lib, "-lnmgpu", "-Wl,-rpath," + lib]
     subprocess.check_call(cmd)
