@@ -246,6 +246,35 @@ typedef struct {
 } nm_host_problem;
 int nm_assemble_host(nm_ctx *ctx, const nm_host_problem *problem, nm_counts *counts, uint64_t *nnz);
 
+/* ---- higher polynomial degrees: FE_Q(p) on the background, FE_DGQ(q) on the immersed grid ----
+ * The arithmetic of create_coupling_mass_matrix_with_exact_intersections for any tensor-product Lagrange pair
+ * (code/include/coupling_utilities.h:238-289):
+ *   xi_q = F_bg^-1(x_q) (:248-249), eta_q = F_im^-1(x_q) on the codimension-one cell (:251-254),
+ *   local(i,j) += phi_i(xi_q) psi_j(eta_q) w_q (:258-274), distribute_local_to_global through the space constraints
+ *   (:285-287), and the pattern of create_coupling_sparsity_pattern_with_exact_intersections with
+ *   keep_constrained_entries = true (:100-139).
+ * An element is described by its degree and its unit support points IN ITS OWN DOF ORDER (deal.II:
+ * fe.get_unit_support_points()); the shape functions are the Lagrange polynomials of those points, so no numbering
+ * convention is assumed.  Limits: degree <= 5, <= 64 background and <= 16 immersed DoFs per cell; background cells
+ * axis-aligned as everywhere in this library; no immersed constraints.
+ *   nm_set_finite_elements  after nm_set_background* / nm_set_immersed (their `dofs` may be NULL): DoF tables
+ *                           [n_cells][dofs_per_cell] and the space constraint lines (as in nm_set_background)
+ *   nm_assemble_fe          immersed == NULL: on the quadrature of the context's own nm_intersect (it never leaves the
+ *                           device); otherwise on the caller's tuples, exactly as the reference signature passes them
+ *                           (pair i = (immersed[i], background[i]), points q_offset[i] .. q_offset[i+1])
+ * Afterwards nm_get_csr / nm_get_csr_compact / nm_spmv / nm_spmv_local work on the result; NM_LOCAL_IMMERSED then
+ * numbers the immersed entries (cell, local dof) = cell * dofs_per_cell + local dof. */
+typedef struct {
+  unsigned degree;
+  unsigned dofs_per_cell;
+  const double *unit_support_points;   /* [dofs_per_cell][dim] (host); may be NULL for a one-dof element */
+} nm_fe;
+int nm_set_finite_elements(nm_ctx *ctx, const nm_fe *space_fe, const uint32_t *space_dofs, uint64_t n_space_dofs, uint64_t n_constrained,
+                           const uint32_t *c_dof, const uint64_t *c_ptr, const uint32_t *c_master, const double *c_weight,
+                           const nm_fe *immersed_fe, const uint32_t *immersed_dofs, uint64_t n_immersed_dofs, int where);
+int nm_assemble_fe(nm_ctx *ctx, uint64_t n_pairs, const uint32_t *immersed, const uint32_t *background, const uint64_t *q_offset,
+                   const double *points, const double *weights, int where, uint64_t *nnz);
+
 /* ---- interface-penalisation (Nitsche) terms on a caller-supplied quadrature ----
  * Replaces the arithmetic of assemble_nitsche_with_exact_intersections (code/include/coupling_utilities.h:306-398) and
  * create_nitsche_rhs_with_exact_intersections (:400-481): for tuple p with background cell background[p] and points

@@ -28,7 +28,7 @@ SYMBOLS = ["nm_version", "nm_create", "nm_destroy", "nm_last_error", "nm_set_bac
            "nm_set_background_dofs", "nm_set_immersed_dofs", "nm_set_immersed", "nm_flag_overlapped_background", "nm_intersect", "nm_get_candidates", "nm_get_pairs", "nm_get_quadrature",
            "nm_get_split_codes", "nm_build_sparsity", "nm_assemble", "nm_assemble_from_quadrature", "nm_assemble_host", "nm_assemble_nitsche", "nm_get_nitsche", "nm_get_csr",
            "nm_get_csr_compact", "nm_sync_downloads", "nm_spmv", "nm_spmv_local", "nm_local_to_global", "nm_global_to_local",
-           "nm_spmv_push", "nm_spmv_push_owned", "nm_get_info", "nm_measure_fp64_peak", "nm_get_timings", "nm_get_launch_count", "nm_device_bytes", "nm_get_stream"]
+           "nm_spmv_push", "nm_spmv_push_owned", "nm_set_finite_elements", "nm_assemble_fe", "nm_get_info", "nm_measure_fp64_peak", "nm_get_timings", "nm_get_launch_count", "nm_device_bytes", "nm_get_stream"]
 
 
 class NmError(RuntimeError):
@@ -43,6 +43,11 @@ class HostProblem(C.Structure):
                 ("n_space_dofs", C.c_uint64), ("n_constrained", C.c_uint64), ("c_dof", C.c_void_p), ("c_ptr", C.c_void_p),
                 ("c_master", C.c_void_p), ("c_weight", C.c_void_p), ("dim", C.c_int), ("n_im", C.c_uint64), ("im_verts", C.c_void_p),
                 ("im_dofs", C.c_void_p), ("n_im_dofs", C.c_uint64), ("degree", C.c_uint), ("tol", C.c_double)]
+
+
+class FeDesc(C.Structure):
+    """nm_fe of include/nmgpu.h."""
+    _fields_ = [("degree", C.c_uint), ("dofs_per_cell", C.c_uint), ("unit_support_points", C.c_void_p)]
 
 
 class Counts(C.Structure):
@@ -93,6 +98,8 @@ def load():
     L.nm_spmv_local.argtypes = [P, I, P, P, I]
     L.nm_local_to_global.argtypes = [P, I, P, I, P]
     L.nm_global_to_local.argtypes = [P, I, P, P, I]
+    L.nm_set_finite_elements.argtypes = [P, C.POINTER(FeDesc), P, U64, U64, P, P, P, P, C.POINTER(FeDesc), P, U64, I]
+    L.nm_assemble_fe.argtypes = [P, U64, P, P, P, P, P, I, C.POINTER(U64)]
     L.nm_get_info.argtypes = [P, I, C.POINTER(U64)]
     L.nm_measure_fp64_peak.argtypes = [P, C.c_double, C.POINTER(C.c_double)]
     L.nm_spmv_push.argtypes = [P, P, I, C.POINTER(C.c_void_p), I]
@@ -290,6 +297,39 @@ class Context:
         self._chk(self.L.nm_get_nitsche(self.h, _ptr(rp)[0], _ptr(col)[0], _ptr(val)[0], _ptr(rhs)[0], w))
         return (rp, col, val), rhs
 
+    # ---- general finite elements (FE_Q(p) x FE_DGQ(q)) ---------------------------------------
+    def set_finite_elements(self, space_fe, space_dofs, n_space_dofs, immersed_fe, immersed_dofs, n_immersed_dofs,
+                            c_dof=None, c_ptr=None, c_master=None, c_weight=None):
+        """`space_fe` / `immersed_fe` = (degree, unit support points [dofs_per_cell, dim] in the element's dof order);
+        dof tables [n_cells, dofs_per_cell]; constraint lines of the space as in set_background (nm_set_finite_elements)."""
+        keep = []
+
+        def desc(fe):
+            deg, sp = fe
+            sp = np.ascontiguousarray(np.asarray(sp, dtype=np.float64))
+            keep.append(sp)
+            return FeDesc(int(deg), int(sp.shape[0]), sp.ctypes.data_as(C.c_void_p) if sp.size else None)
+        fs, fi = desc(space_fe), desc(immersed_fe)
+        n_c = 0 if c_dof is None else int(c_dof.shape[0])
+        w = _where(space_dofs, immersed_dofs, c_dof, c_ptr, c_master, c_weight)
+        self._chk(self.L.nm_set_finite_elements(self.h, C.byref(fs), _ptr(space_dofs)[0], int(n_space_dofs), n_c, _ptr(c_dof)[0], _ptr(c_ptr)[0],
+                                                _ptr(c_master)[0], _ptr(c_weight)[0], C.byref(fi), _ptr(immersed_dofs)[0], int(n_immersed_dofs), w))
+        self.n_space_dofs, self.n_im_dofs = int(n_space_dofs), int(n_immersed_dofs)
+        self.fe_dofs_per_cell = (fs.dofs_per_cell, fi.dofs_per_cell)
+
+    def assemble_fe(self, im=None, bg=None, q_offset=None, points=None, weights=None) -> int:
+        """Coupling matrix for the elements set with set_finite_elements: on the context's own intersection quadrature
+        (no arguments) or on the given tuples (nm_assemble_fe).  Returns nnz."""
+        nnz = C.c_uint64(0)
+        if im is None:
+            self._chk(self.L.nm_assemble_fe(self.h, 0, None, None, None, None, None, NM_DEVICE, C.byref(nnz)))
+        else:
+            w = _where(im, bg, q_offset, points, weights)
+            self._chk(self.L.nm_assemble_fe(self.h, int(im.shape[0]), _ptr(im)[0], _ptr(bg)[0], _ptr(q_offset)[0], _ptr(points)[0],
+                                            _ptr(weights)[0], w, C.byref(nnz)))
+        self.nnz = int(nnz.value)
+        return self.nnz
+
     def csr(self, transpose: bool = False, values: bool = True, device="cpu", out=None):
         """CSR of the matrix; `out=(rowptr, col, val)` reuses caller buffers (e.g. pinned host memory)
         of at least the needed size and returns views of them."""
@@ -337,7 +377,7 @@ class Context:
 
     def spmv_local(self, x, transpose: bool = False, out=None):
         """Products in local numbering (nm_spmv_local): transpose=False: y[rows] = A x[cells]; True: y[cells] = A^T x[rows]."""
-        ny = self.n_im if transpose else self.n_rows_local()
+        ny = self.n_im * getattr(self, "fe_dofs_per_cell", (0, 1))[1] if transpose else self.n_rows_local()
         if out is None:
             out = torch.empty(ny, dtype=torch.float64, device=x.device)
         self._chk(self.L.nm_spmv_local(self.h, int(transpose), _ptr(x)[0], _ptr(out)[0], _where(x, out)))

@@ -130,7 +130,8 @@ static std::vector<DevBuf *> all_buffers(nm_ctx *c)
           &c->a_rowptr, &c->a_rowptr32, &c->a_col, &c->a_val, &c->a_cursor, &c->scan_tmp, &c->scratch_a, &c->scratch_b, &c->stage_x,
           &c->stage_y, &c->h2d_stage, &c->nit_cnt, &c->nit_keys, &c->nit_vals, &c->nit_rkeys, &c->nit_rvals, &c->nit_rowptr,
           &c->nit_col, &c->nit_val, &c->nit_rhs, &c->row_bits, &c->row_prefix, &c->row_ids, &c->out_ids, &c->out_len, &c->glob_im,
-          &c->glob_dof, &c->brk_hdr, &c->brk_bit, &c->clip_lut};
+          &c->glob_dof, &c->brk_hdr, &c->brk_bit, &c->clip_lut, &c->fe_bg_dofs, &c->fe_im_dofs, &c->fe_pairs, &c->fe_qoff,
+          &c->fe_pts, &c->fe_w, &c->fe_recoff, &c->fe_keys, &c->fe_vals};
 }
 
 static void free_all(nm_ctx *c)
@@ -249,6 +250,7 @@ static int set_background_common(nm_ctx *ctx, int spacedim, uint64_t n_cells, bo
   if (n_constrained && (!c_dof || !c_ptr)) return nm_fail(ctx, NM_ERR_INVALID, "null constraint arrays");
   ctx->bg_set = ctx->index_valid = ctx->intersect_valid = ctx->matrix_valid = false;
   ctx->dofs_checked = false;
+  ctx->fe_general = false;
   const int NV = 1 << spacedim;
   PhaseTimer tm(ctx, NM_T_UPLOAD);
   ctx->spacedim = spacedim;
@@ -316,6 +318,17 @@ static int set_constraints(nm_ctx *ctx, uint64_t n_dofs, uint64_t n_constrained,
   return nm_constraints_layout(ctx, ctx->scratch_a.as<uint32_t>());
 }
 
+}  // extern "C"
+
+// constraint lines of the space (shared with nm_fe.cu)
+int nm_constraints_set(nm_ctx *ctx, uint64_t n_dofs, uint64_t n_constrained, const uint32_t *c_dof, const uint64_t *c_ptr, const uint32_t *c_master,
+                       const double *c_weight, int where)
+{
+  return set_constraints(ctx, n_dofs, n_constrained, c_dof, c_ptr, c_master, c_weight, where);
+}
+
+extern "C" {
+
 int nm_set_background_dofs(nm_ctx *ctx, const uint32_t *dofs, uint64_t n_dofs, uint64_t n_constrained, const uint32_t *c_dof,
                            const uint64_t *c_ptr, const uint32_t *c_master, const double *c_weight, int where)
 {
@@ -326,6 +339,7 @@ int nm_set_background_dofs(nm_ctx *ctx, const uint32_t *dofs, uint64_t n_dofs, u
   if (n_dofs >= 0xffffffffULL) return nm_fail(ctx, NM_ERR_UNSUPPORTED, "DoF counts must fit 32 bits");
   ctx->matrix_valid = false;  // intersection results stay valid: they do not depend on the numbering
   ctx->dofs_checked = false;
+  ctx->fe_general = false;
   PhaseTimer tm(ctx, NM_T_UPLOAD, true);
   NM_TRY(nm_upload(ctx, ctx->bg_dofs, dofs, ctx->n_bg * (1u << ctx->spacedim) * sizeof(uint32_t), where));
   NM_TRY(set_constraints(ctx, n_dofs, n_constrained, c_dof, c_ptr, c_master, c_weight, where));
@@ -550,6 +564,10 @@ int nm_get_split_codes(nm_ctx *ctx, uint8_t *codes, int where)
 static int ensure_matrix(nm_ctx *ctx)
 {
   if (!ctx->intersect_valid) return nm_fail(ctx, NM_ERR_STATE, "nm_intersect has not been run");
+  if (ctx->fe_general) {   // general elements: the matrix is built by nm_assemble_fe, never implicitly
+    if (!ctx->matrix_valid) return nm_fail(ctx, NM_ERR_STATE, "nm_assemble_fe has not been run on the finite elements set with nm_set_finite_elements");
+    return NM_OK;
+  }
   if (!ctx->bg_dofs_set || !ctx->im_dofs_set)
     return nm_fail(ctx, NM_ERR_STATE, "DoF indices have not been set (nm_set_background_dofs / nm_set_immersed_dofs)");
   if (!ctx->matrix_valid) NM_TRY(nm_matrix_build(ctx));
@@ -662,6 +680,7 @@ int nm_assemble_host(nm_ctx *ctx, const nm_host_problem *P, nm_counts *counts, u
   ctx->bg_set = ctx->bg_dofs_set = ctx->im_set = ctx->im_dofs_set = false;
   ctx->index_valid = ctx->intersect_valid = ctx->matrix_valid = false;
   ctx->dofs_checked = false;
+  ctx->fe_general = false;
   ctx->local_from_user = false;
   ctx->spacedim = d; ctx->n_bg = P->n_bg; ctx->n_space_dofs = P->n_space_dofs;
   ctx->n_constrained = P->n_constrained; ctx->n_cmasters = n_masters;
@@ -890,7 +909,7 @@ int nm_sync_downloads(nm_ctx *ctx)
 
 static int local_count(nm_ctx *ctx, int which, uint64_t *n)
 {
-  if (which == NM_LOCAL_IMMERSED) { *n = ctx->n_im; return NM_OK; }
+  if (which == NM_LOCAL_IMMERSED) { *n = ctx->n_crows; return NM_OK; }
   if (which == NM_LOCAL_ROWS) return nm_nonempty_rows(ctx, n, nullptr, nullptr);
   return nm_fail(ctx, NM_ERR_INVALID, "which must be NM_LOCAL_IMMERSED or NM_LOCAL_ROWS");
 }
@@ -934,7 +953,7 @@ int nm_spmv_local(nm_ctx *ctx, int transpose, const double *x, double *y, int wh
   NM_TRY(ensure_matrix(ctx));
   uint64_t n_rows = 0;
   NM_TRY(nm_nonempty_rows(ctx, &n_rows, nullptr, nullptr));
-  const uint64_t nx = transpose ? n_rows : ctx->n_im, ny = transpose ? ctx->n_im : n_rows;
+  const uint64_t nx = transpose ? n_rows : ctx->n_crows, ny = transpose ? ctx->n_crows : n_rows;
   // global-numbered scratch vectors live on the device only: entries this shard never addresses are never read
   NM_TRY(nm_ensure(ctx, ctx->glob_im, (ctx->n_im_dofs + 1) * 8));
   NM_TRY(nm_ensure(ctx, ctx->glob_dof, (ctx->n_space_dofs + 1) * 8));

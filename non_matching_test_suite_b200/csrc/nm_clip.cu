@@ -41,6 +41,28 @@ bool make_rule(int dim1, unsigned n, Rule &r)
                 r.n = 4; r.x[0][0] = 0.5 - b; r.x[1][0] = 0.5 - a; r.x[2][0] = 0.5 + a; r.x[3][0] = 0.5 + b;
                 r.w[0] = r.w[3] = wb; r.w[1] = r.w[2] = wa; return true; }
     }
+    if (n >= 5 && n <= 8) {  // Newton on P_n: the rules the drivers ask for at degree p >= 2 (n = 2p + 1, 2d3d/lagrange_multiplier.cc:750-753)
+      r.n = (int)n;
+      for (int i = 0; i < (int)n; ++i) {
+        double z = cos(3.14159265358979323846 * (i + 0.75) / (n + 0.5)), pp = 1.0;
+        for (int it = 0; it < 100; ++it) {
+          double p1 = 1.0, p2 = 0.0;
+          for (int j = 0; j < (int)n; ++j) { const double p3 = p2; p2 = p1; p1 = ((2.0 * j + 1.0) * z * p2 - j * p3) / (j + 1.0); }
+          pp = n * (z * p1 - p2) / (z * z - 1.0);
+          const double dz = p1 / pp;
+          z -= dz;
+          if (fabs(dz) < 1e-16) break;
+        }
+        {
+          double p1 = 1.0, p2 = 0.0;
+          for (int j = 0; j < (int)n; ++j) { const double p3 = p2; p2 = p1; p1 = ((2.0 * j + 1.0) * z * p2 - j * p3) / (j + 1.0); }
+          pp = n * (z * p1 - p2) / (z * z - 1.0);
+        }
+        r.x[n - 1 - i][0] = 0.5 + 0.5 * z;
+        r.w[n - 1 - i] = 1.0 / ((1.0 - z * z) * pp * pp);
+      }
+      return true;
+    }
     return false;
   }
   if (n == 1) { r.n = 1; r.x[0][0] = r.x[0][1] = 1.0 / 3.0; r.w[0] = 0.5; return true; }
@@ -686,7 +708,7 @@ static int upload_rule(nm_ctx *ctx)
   Rule r;
   if (!make_rule(ctx->dim1, ctx->degree, r))
     return nm_fail(ctx, NM_ERR_UNSUPPORTED, "QGaussSimplex<%d>(n_points_1D=%u) is not tabulated (supported: %s)", ctx->dim1,
-                   ctx->degree, ctx->dim1 == 1 ? "1..4" : "1..3");
+                   ctx->degree, ctx->dim1 == 1 ? "1..8" : "1..3");
   NM_CUDA(cudaMemcpyToSymbolAsync(c_rule, &r, sizeof(Rule), 0, cudaMemcpyHostToDevice, ctx->stream));
   return NM_OK;
 }

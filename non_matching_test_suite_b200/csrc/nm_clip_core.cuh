@@ -1,6 +1,6 @@
 // Geometry core of the 3D clip kernels: triangle-vs-box gate, clipped polygon, closed-form moments.  Pure functions of
 // their arguments, compiled for the device by nm_clip.cu and for the HOST by tests/cpp/clip_core_host.cpp, which checks
-// them pair by pair against the CPU oracle (reference: code/src/intersections.cc:437-509, 693-746).
+// them pair by pair against an independent CPU restatement (reference: code/src/intersections.cc:437-509, 693-746).
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -472,8 +472,10 @@ NMC_UNROLL
 // ---------------------------------------------------------------------------------------
 // what the kernels call: one switch for the gate, the polygon and (through them) the quadrature emission
 // ---------------------------------------------------------------------------------------
+// 0: clip the triangle by the box planes (the kernel's algorithm); 1: section algorithm (measured on B200 at sphere
+// cycle 8: 22.6 ms against 14.4 ms -- kept as a cross-check of the polygon construction, tests/test_clip_core_cpu.py)
 #ifndef NM_CLIP_SECTION
-#define NM_CLIP_SECTION 1
+#define NM_CLIP_SECTION 0
 #endif
 
 // stage-1 gate: can triangle `tri` (cell-local coordinates) meet the box [0, H] at all?  Conservative.

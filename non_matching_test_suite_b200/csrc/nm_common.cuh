@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/nmgpu.h"
 
@@ -110,6 +111,8 @@ struct nm_ctx {
   DevBuf c_col;       // u32
   DevBuf c_val;       // f64
   uint64_t nnz = 0;
+  uint64_t n_crows = 0;             // rows of C and the immersed dof of each (set by whichever path built the matrix)
+  DevBuf *crow_dofs = nullptr;
   // stored orientation (rows = space dofs), compact CSR
   DevBuf a_rowptr32;  // same as u32 when nnz < 2^32
   bool a_rowptr32_valid = false;
@@ -136,6 +139,13 @@ struct nm_ctx {
   DevBuf nit_rowptr, nit_col, nit_val, nit_rhs;
   uint64_t nit_nnz = 0;
   bool nit_has_matrix = false, nit_has_rhs = false;
+
+  // ---- general finite elements (nm_fe.cu): FE_Q(p) background x FE_DGQ(q) immersed ----
+  bool fe_general = false;          // nm_set_finite_elements was called: the matrix comes from nm_assemble_fe
+  int fe_nb = 0, fe_ni = 0;         // dofs per background / immersed cell
+  std::vector<unsigned char> fe;    // the device constant block (node tables, dof -> node maps)
+  DevBuf fe_bg_dofs, fe_im_dofs;    // [n_bg][fe_nb], [n_im][fe_ni] u32
+  DevBuf fe_pairs, fe_qoff, fe_pts, fe_w, fe_recoff, fe_keys, fe_vals;
 
   // ---- scratch ----
   DevBuf scan_tmp, scratch_a, scratch_b, stage_x, stage_y, h2d_stage;
@@ -221,6 +231,7 @@ int nm_quadrature_emit(nm_ctx *ctx, uint64_t *q_offset, double *points, double *
 int nm_local_from_quadrature(nm_ctx *ctx, uint64_t n_pairs, const uint32_t *im, const uint32_t *bg, const uint64_t *q_offset,
                              const double *points, const double *weights, int where);
 int nm_matrix_build(nm_ctx *ctx);
+int nm_transpose_build(nm_ctx *ctx);
 int nm_nitsche_run(nm_ctx *ctx, uint64_t n_pairs, const uint32_t *bg, const uint64_t *q_offset, const double *points,
                    const double *weights, const double *coefficient, const double *rhs_values, double penalty, int what, int where);
 #define NM_SPMV_LOCAL_OUT 1

@@ -221,28 +221,26 @@ __device__ __forceinline__ unsigned hash_claim(unsigned *keys, unsigned key, uns
   }
 }
 
-// Order-independent accumulation.  The contributions to one matrix entry arrive from several lanes in an order the
-// hardware chooses; floating-point adds would make the last bits depend on it.  They are therefore summed as 64-bit
-// FIXED-POINT integers (integer addition is associative, the shared-memory atomic is native): every contribution of an
-// immersed cell is scaled by 2^e, with e chosen from M = sum |sum_w| over the cell's accepted pairs such that
-// M 2^e lies in [2^59, 2^60) -- no entry can exceed M, so nothing overflows, and one unit is M 2^-60, far below the
-// rounding of the double-precision inputs (entries are >= 1e-4 M where it matters for the 1e-12 Frobenius bar).
-// The result is bit-identical from run to run and across row groupings.
-struct FixedScale {
-  double scale, inv;
-};
-__device__ __forceinline__ FixedScale fixed_scale_for(double m_sum)
+// vals[slot] += v for every lane of the group that carries a contribution (slot != NO_SLOT), in a FIXED order: lanes
+// that hit the same slot in this instruction are found with match.any, the lowest of them adds the values in ascending
+// lane order and is the only one that touches the slot.  No floating-point atomics: the sums are bit-reproducible.
+__device__ __forceinline__ void group_accumulate(unsigned gmask, unsigned wlane, double *vals, unsigned slot, double v)
 {
-  int e = 0;
-  (void)frexp(m_sum, &e);          // m_sum = f 2^e, f in [0.5, 1)
-  FixedScale f;
-  f.scale = ldexp(1.0, 60 - e);
-  f.inv = ldexp(1.0, e - 60);
-  return f;
-}
-__device__ __forceinline__ void fixed_add(long long *vals, unsigned slot, double v, const FixedScale &f)
-{
-  atomicAdd(reinterpret_cast<unsigned long long *>(&vals[slot]), (unsigned long long)__double2ll_rn(v * f.scale));
+  const bool has = slot != NO_SLOT;
+  const unsigned grp = __match_any_sync(gmask, has ? slot : (0x80000000u | wlane));   // a lane without a contribution matches nobody
+  const bool leader = has && (unsigned)(__ffs(grp) - 1) == wlane;
+  const unsigned mx = __reduce_max_sync(gmask, has ? (unsigned)__popc(grp) : 1u);
+  double sum = v;
+  unsigned rest = grp & (grp - 1u);   // the other lanes of my slot, ascending
+  for (unsigned j = 1; j < mx; ++j) {
+    const bool more = rest != 0u;
+    const int src = more ? __ffs(rest) - 1 : (int)wlane;
+    rest &= rest - 1u;
+    const double o = __shfl_sync(gmask, v, src);
+    if (leader && more) sum += o;
+  }
+  if (leader) vals[slot] += sum;
+  __syncwarp(gmask);
 }
 
 template <int NL>
@@ -252,11 +250,10 @@ __global__ void __launch_bounds__(256) merge_rows_hash(uint64_t n_im, const uint
                                                        const int32_t *__restrict__ line_of, const uint64_t *__restrict__ c_ptr,
                                                        const uint32_t *__restrict__ c_master, const double *__restrict__ c_weight,
                                                        const uint64_t *__restrict__ rowstart, uint32_t *__restrict__ rowlen,
-                                                       uint32_t *__restrict__ out_col, double *__restrict__ out_val,
-                                                       const double *__restrict__ sumw)
+                                                       uint32_t *__restrict__ out_col, double *__restrict__ out_val)
 {
   __shared__ unsigned s_keys[8][HASH_SLOTS];
-  __shared__ long long s_vals[8][HASH_SLOTS];
+  __shared__ double s_vals[8][HASH_SLOTS];
   __shared__ unsigned s_list[8][HASH_SLOTS];
   const unsigned w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint64_t m = (uint64_t)blockIdx.x * 8 + w;
@@ -265,18 +262,12 @@ __global__ void __launch_bounds__(256) merge_rows_hash(uint64_t n_im, const uint
   if (cp > HASH_CAP) return;  // sort-based kernels take these
   if (cp == 0) { if (lane == 0) rowlen[m] = 0; return; }
   unsigned *keys = s_keys[w];
-  long long *vals = s_vals[w];
+  double *vals = s_vals[w];
   unsigned *list = s_list[w];
 #pragma unroll
-  for (int k = 0; k < HASH_SLOTS / 32; ++k) { keys[lane + 32 * k] = HASH_EMPTY; vals[lane + 32 * k] = 0; }
+  for (int k = 0; k < HASH_SLOTS / 32; ++k) { keys[lane + 32 * k] = HASH_EMPTY; vals[lane + 32 * k] = 0.0; }
   __syncwarp();
   const uint64_t p0 = cand_ptr[m], p1 = cand_ptr[m + 1];
-  double m_sum = 0.0;
-  for (uint64_t p = p0 + lane; p < p1; p += 32)
-    if (acc[p]) m_sum += fabs(sumw[p]);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m_sum += __shfl_xor_sync(0xffffffffu, m_sum, o);
-  const FixedScale fs = fixed_scale_for(m_sum);
   for (uint64_t base = p0; base < p1; base += 32) {
     const uint64_t p = base + lane;
     const bool on = p < p1 && acc[p];
@@ -292,18 +283,22 @@ __global__ void __launch_bounds__(256) merge_rows_hash(uint64_t n_im, const uint
     }
 #pragma unroll
     for (int i = 0; i < NL; ++i) {
+      // one (pair, vertex) contribution per lane, added in lane order (group_accumulate): no floating-point atomics
+      int32_t ln = -1;
+      unsigned s = NO_SLOT;
       if (on) {
-        const int32_t ln = line_of[dofs[i]];
-        const unsigned s = hash_insert(keys, dofs[i]);
-        if (ln < 0) {
-          fixed_add(vals, s, v[i], fs);
-        } else {
-          // keep_constrained_entries: the constrained row stays in the pattern, structurally zero;
-          // its value goes to the masters of the line (none for a Dirichlet row)
-          for (uint64_t k = c_ptr[ln]; k < c_ptr[ln + 1]; ++k) fixed_add(vals, hash_insert(keys, c_master[k]), c_weight[k] * v[i], fs);
-        }
+        ln = line_of[dofs[i]];
+        s = hash_insert(keys, dofs[i]);   // keep_constrained_entries: a constrained row stays in the pattern, structurally zero
       }
-      __syncwarp();
+      group_accumulate(0xffffffffu, lane, vals, (on && ln < 0) ? s : NO_SLOT, v[i]);
+      const unsigned nm = (on && ln >= 0) ? (unsigned)(c_ptr[ln + 1] - c_ptr[ln]) : 0u;   // masters of the line (none for a Dirichlet row)
+      const unsigned nm_max = __reduce_max_sync(0xffffffffu, nm);
+      for (unsigned k = 0; k < nm_max; ++k) {
+        unsigned t = NO_SLOT;
+        double wv = 0.0;
+        if (k < nm) { const uint64_t kk = c_ptr[ln] + k; t = hash_insert(keys, c_master[kk]); wv = c_weight[kk] * v[i]; }
+        group_accumulate(0xffffffffu, lane, vals, t, wv);
+      }
     }
   }
   // distinct keys -> list
@@ -325,7 +320,7 @@ __global__ void __launch_bounds__(256) merge_rows_hash(uint64_t n_im, const uint
     unsigned rank = 0;
     for (unsigned f = 0; f < D; ++f) rank += keys[list[f]] < key ? 1u : 0u;
     out_col[dst + rank] = key;
-    out_val[dst + rank] = (double)vals[s] * fs.inv;
+    out_val[dst + rank] = vals[s];
   }
   if (lane == 0) rowlen[m] = D;
 }
@@ -342,7 +337,6 @@ constexpr int FAST_ROWS = 64;   // consecutive immersed cells per group
 template <int NL, int GROUP, int SLOTS>
 __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint64_t *__restrict__ cand_ptr,
                                                        const uint32_t *__restrict__ cand_bg, const uint8_t *__restrict__ acc,
-                                                       const double *__restrict__ sumw,
                                                        const double *__restrict__ local, const uint32_t *__restrict__ bg_dofs,
                                                        const int32_t *__restrict__ line_of, const uint64_t *__restrict__ c_ptr,
                                                        const uint32_t *__restrict__ c_master, const double *__restrict__ c_weight,
@@ -354,7 +348,7 @@ __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint
   constexpr int NG = 256 / GROUP;                 // groups per block
   constexpr unsigned CAP = SLOTS * 3 / 4;         // distinct dofs a group accepts
   __shared__ unsigned s_keys[NG][SLOTS];
-  __shared__ long long s_vals[NG][SLOTS];
+  __shared__ double s_vals[NG][SLOTS];
   __shared__ unsigned s_list[NG][SLOTS];
   __shared__ __align__(16) unsigned s_dkey[NG][SLOTS];
   __shared__ unsigned s_cand[NG][GROUP];
@@ -362,7 +356,7 @@ __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint
   const unsigned gbase = (threadIdx.x & 31) - lane;                      // first lane of the group inside its warp
   const unsigned gmask = GROUP == 32 ? 0xffffffffu : (((1u << GROUP) - 1u) << gbase);
   unsigned *keys = s_keys[g];
-  long long *vals = s_vals[g];
+  double *vals = s_vals[g];
   unsigned *list = s_list[g];
   unsigned *dkey = s_dkey[g];
   unsigned *cands = s_cand[g];
@@ -371,15 +365,9 @@ __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint
   unsigned chunk_left = 0;
   for (uint64_t m = m0; m < m0 + rows_per_group && m < n_im; ++m) {
 #pragma unroll
-    for (int k = 0; k < SLOTS / GROUP; ++k) { keys[lane + GROUP * k] = HASH_EMPTY; vals[lane + GROUP * k] = 0; }
+    for (int k = 0; k < SLOTS / GROUP; ++k) { keys[lane + GROUP * k] = HASH_EMPTY; vals[lane + GROUP * k] = 0.0; }
     __syncwarp(gmask);
     const uint64_t p0 = cand_ptr[m], p1 = cand_ptr[m + 1];
-    double m_sum = 0.0;   // bound of every entry of this cell: fixes the fixed-point scale
-    for (uint64_t p = p0 + lane; p < p1; p += GROUP)
-      if (acc[p]) m_sum += fabs(sumw[p]);
-#pragma unroll
-    for (int o = GROUP / 2; o > 0; o >>= 1) m_sum += __shfl_xor_sync(gmask, m_sum, o);
-    const FixedScale fs = fixed_scale_for(m_sum);
     unsigned claimed = 0;
     bool failed = false;   // table full: bounded probing gives up instead of spinning
     for (uint64_t base = p0; base < p1; base += GROUP) {
@@ -411,17 +399,19 @@ __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint
         }
         // keep_constrained_entries: a constrained row stays in the pattern as a structural zero (its slot is claimed,
         // nothing is added); its value goes to the masters of the line (none for a Dirichlet row)
-        if (on_e && !failed) {
-          if (ln < 0) {
-            fixed_add(vals, s, v, fs);
-          } else {
-            for (uint64_t k = c_ptr[ln]; k < c_ptr[ln + 1] && !failed; ++k) {
-              const unsigned t = hash_claim<SLOTS>(keys, c_master[k], claimed, failed);
-              if (!failed) fixed_add(vals, t, c_weight[k] * v, fs);
-            }
+        group_accumulate(gmask, gbase + lane, vals, (on_e && !failed && ln < 0) ? s : NO_SLOT, v);
+        const unsigned nm = (on_e && !failed && ln >= 0) ? (unsigned)(c_ptr[ln + 1] - c_ptr[ln]) : 0u;
+        const unsigned nm_max = __reduce_max_sync(gmask, nm);
+        for (unsigned k = 0; k < nm_max; ++k) {
+          unsigned t = NO_SLOT;
+          double wv = 0.0;
+          if (k < nm && !failed) {
+            const uint64_t kk = c_ptr[ln] + k;
+            t = hash_claim<SLOTS>(keys, c_master[kk], claimed, failed);
+            wv = c_weight[kk] * v;
           }
+          group_accumulate(gmask, gbase + lane, vals, failed ? NO_SLOT : t, wv);
         }
-        __syncwarp(gmask);
       }
     }
     const unsigned total_claimed = __reduce_add_sync(gmask, claimed);
@@ -469,11 +459,11 @@ __global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint
       }
       // per-dof entry counts for the transpose -- or, in compact-row mode, only the bitmap of touched dofs
       if (ea < D) {
-        out_col[dst + ra] = ka; out_val[dst + ra] = (double)vals[list[ea]] * fs.inv;
+        out_col[dst + ra] = ka; out_val[dst + ra] = vals[list[ea]];
         if (mark_bits) atomicOr(&a_cnt[ka >> 5], 1u << (ka & 31)); else atomicAdd(&a_cnt[ka], 1u);
       }
       if (eb < D) {
-        out_col[dst + rb] = kb; out_val[dst + rb] = (double)vals[list[eb]] * fs.inv;
+        out_col[dst + rb] = kb; out_val[dst + rb] = vals[list[eb]];
         if (mark_bits) atomicOr(&a_cnt[kb >> 5], 1u << (kb & 31)); else atomicAdd(&a_cnt[kb], 1u);
       }
     }
@@ -895,8 +885,7 @@ static int matrix_build_fast(nm_ctx *ctx, bool *done)
   NM_CUDA(cudaMemsetAsync(cursor, 0, 32, ctx->stream));   // bytes 160..191: the chunk cursor AND the problem flag (byte 176)
   KernelTimer km(ctx, NM_T_K_MERGE);
   merge_rows_fast<NL, GROUP, SLOTS><<<(unsigned)blocks, 256, 0, NM_LS(ctx)>>>(
-      n_im, ctx->cand_ptr.as<uint64_t>(), ctx->cand_bg.as<uint32_t>(), ctx->cand_acc.as<uint8_t>(), ctx->cand_sumw.as<double>(),
-      ctx->cand_local.as<double>(),
+      n_im, ctx->cand_ptr.as<uint64_t>(), ctx->cand_bg.as<uint32_t>(), ctx->cand_acc.as<uint8_t>(), ctx->cand_local.as<double>(),
       ctx->bg_dofs.as<uint32_t>(), ctx->line_of.as<int32_t>(), ctx->c_ptr.as<uint64_t>(), ctx->c_master.as<uint32_t>(),
       ctx->c_weight.as<double>(), ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(),
       ctx->c_val.as<double>(), capacity, cursor, problem, dof_marks, ctx->compact_rows ? 1 : 0, (uint32_t)n_rows, (unsigned)rpg, chunk);
@@ -923,6 +912,8 @@ static int matrix_build_t(nm_ctx *ctx)
   ctx->nnz = 0;
   // sharded grids carry the global dof numbering: keep per-dof arrays out of the step when this rank can touch only a
   // small part of the dofs (each cell has 2^d of them)
+  ctx->n_crows = n_im;                 // FE_DGQ(0): one row of C per immersed cell, its column id = the cell's dof
+  ctx->crow_dofs = &ctx->im_dofs;
   ctx->compact_rows = ctx->compact_rows_env >= 0 ? ctx->compact_rows_env == 1 : n_rows > 4 * ctx->n_bg;
   ctx->n_local_rows = n_rows;
   {
@@ -970,7 +961,7 @@ static int matrix_build_t(nm_ctx *ctx)
         n_im, ctx->scratch_a.as<uint32_t>(), ctx->cand_ptr.as<uint64_t>(), ctx->cand_bg.as<uint32_t>(), ctx->cand_acc.as<uint8_t>(),
         ctx->cand_local.as<double>(), ctx->bg_dofs.as<uint32_t>(), ctx->line_of.as<int32_t>(), ctx->c_ptr.as<uint64_t>(),
         ctx->c_master.as<uint32_t>(), ctx->c_weight.as<double>(), ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(),
-        ctx->c_col.as<uint32_t>(), ctx->c_val.as<double>(), ctx->cand_sumw.as<double>());
+        ctx->c_col.as<uint32_t>(), ctx->c_val.as<double>());
     km.stop();
     if (h_hdr[3])
     merge_rows_warp<NL><<<nm_blocks(n_im, warps), warps * 32, smem, NM_LS(ctx)>>>(
@@ -1000,7 +991,7 @@ static int matrix_build_t(nm_ctx *ctx)
 template <int NL>
 static int transpose_rows(nm_ctx *ctx, bool counts_ready)
 {
-  const uint64_t n_im = ctx->n_im, n_dofs = ctx->n_space_dofs;
+  const uint64_t n_im = ctx->n_crows, n_dofs = ctx->n_space_dofs;   // rows of C: immersed cells (FE_DGQ(0)) or (cell, dof) pairs
   PhaseTimer tt(ctx, NM_T_TRANSPOSE);
   constexpr int TL = NL == 8 ? 8 : 4;
   RowMap map{nullptr, nullptr};
@@ -1050,7 +1041,7 @@ static int transpose_rows(nm_ctx *ctx, bool counts_ready)
   if (n_im) {
     t_scatter<TL><<<nm_blocks(n_im * TL, 256), 256, 0, NM_LS(ctx)>>>(
         n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(), ctx->c_val.as<double>(),
-        ctx->im_dofs.as<uint32_t>(), map, ctx->a_rowptr.as<uint64_t>(), cursor, ctx->a_col.as<uint32_t>(), ctx->a_val.as<double>());
+        ctx->crow_dofs->as<uint32_t>(), map, ctx->a_rowptr.as<uint64_t>(), cursor, ctx->a_col.as<uint32_t>(), ctx->a_val.as<double>());
     NM_CUDA(cudaGetLastError());
   }
   // 32-bit row offsets for the SpMV when they fit (halves the row-pointer traffic), written by the sort kernel
@@ -1104,6 +1095,9 @@ static int check_dof_tables(nm_ctx *ctx)
   return NM_OK;
 }
 
+// C (rows described by ctx->n_crows / crow_dofs, storage c_rowstart / c_rowlen / c_col / c_val) -> stored orientation
+int nm_transpose_build(nm_ctx *ctx) { return transpose_rows<8>(ctx, false); }
+
 int nm_matrix_build(nm_ctx *ctx)
 {
   NM_TRY(check_dof_tables(ctx));
@@ -1118,7 +1112,7 @@ int nm_matrix_build(nm_ctx *ctx)
 // transpose = 1: y[m] for immersed cell m) and nothing outside the computed entries is written.
 int nm_spmv_run(nm_ctx *ctx, int transpose, const double *x, double *y, int flags)
 {
-  const uint64_t n_rows = ctx->n_local_rows, n_im = ctx->n_im;
+  const uint64_t n_rows = ctx->n_local_rows, n_im = ctx->n_crows;
   const bool local_out = (flags & NM_SPMV_LOCAL_OUT) != 0;
   PhaseTimer tm(ctx, transpose ? NM_T_SPMV_T : NM_T_SPMV);
   if (!transpose) {
@@ -1143,7 +1137,7 @@ int nm_spmv_run(nm_ctx *ctx, int transpose, const double *x, double *y, int flag
     if (!local_out) NM_CUDA(cudaMemsetAsync(y, 0, ctx->n_im_dofs * sizeof(double), ctx->stream));
     const double avg = n_im ? (double)ctx->nnz / (double)n_im : 0;
     const uint64_t *rs = ctx->c_rowstart.as<uint64_t>();
-    const uint32_t *rl = ctx->c_rowlen.as<uint32_t>(), *cl = ctx->c_col.as<uint32_t>(), *idf = local_out ? nullptr : ctx->im_dofs.as<uint32_t>();
+    const uint32_t *rl = ctx->c_rowlen.as<uint32_t>(), *cl = ctx->c_col.as<uint32_t>(), *idf = local_out ? nullptr : ctx->crow_dofs->as<uint32_t>();
     const double *vl = ctx->c_val.as<double>();
     if (n_im) {
       if (avg > 20) spmv_crows<4, 8><<<nm_blocks(n_im * 4, 256), 256, 0, NM_LS(ctx)>>>(n_im, rs, rl, cl, vl, idf, x, y);
@@ -1204,14 +1198,14 @@ int nm_spmv_push_owned_run(nm_ctx *ctx, const double *x, int n_ranks, double *co
 // compact CSR with rows = immersed dofs (device buffers owned by the caller of this helper)
 int nm_c_rows_compact(nm_ctx *ctx, uint64_t *rowptr_dev, uint32_t *col_dev, double *val_dev)
 {
-  const uint64_t n_im = ctx->n_im, n_cols = ctx->n_im_dofs;
+  const uint64_t n_im = ctx->n_crows, n_cols = ctx->n_im_dofs;
   NM_TRY(nm_ensure(ctx, ctx->scratch_a, (n_cols + 2) * sizeof(uint32_t)));
   NM_CUDA(cudaMemsetAsync(ctx->scratch_a.p, 0, (n_cols + 2) * sizeof(uint32_t), ctx->stream));
-  if (n_im) scatter_len_by_dof<<<nm_blocks(n_im, 256), 256, 0, NM_LS(ctx)>>>(n_im, ctx->c_rowlen.as<uint32_t>(), ctx->im_dofs.as<uint32_t>(), ctx->scratch_a.as<uint32_t>());
+  if (n_im) scatter_len_by_dof<<<nm_blocks(n_im, 256), 256, 0, NM_LS(ctx)>>>(n_im, ctx->c_rowlen.as<uint32_t>(), ctx->crow_dofs->as<uint32_t>(), ctx->scratch_a.as<uint32_t>());
   NM_TRY(nm_exclusive_scan_u32_to_u64(ctx, ctx->scratch_a.as<uint32_t>(), rowptr_dev, n_cols + 1));
   if (n_im && col_dev)
     c_compact<8><<<nm_blocks(n_im * 8, 256), 256, 0, NM_LS(ctx)>>>(n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(),
-                                                                 ctx->c_val.as<double>(), ctx->im_dofs.as<uint32_t>(), rowptr_dev, col_dev, val_dev);
+                                                                 ctx->c_val.as<double>(), ctx->crow_dofs->as<uint32_t>(), rowptr_dev, col_dev, val_dev);
   NM_CUDA(cudaGetLastError());
   return NM_OK;
 }
@@ -1259,7 +1253,7 @@ int nm_local_map(nm_ctx *ctx, int which, int to_global, const double *src, doubl
 {
   uint64_t n = 0;
   const uint32_t *idx = nullptr;
-  if (which == NM_LOCAL_IMMERSED) { n = ctx->n_im; idx = ctx->im_dofs.as<uint32_t>(); }
+  if (which == NM_LOCAL_IMMERSED) { n = ctx->n_crows; idx = ctx->crow_dofs->as<uint32_t>(); }
   else NM_TRY(nm_nonempty_rows(ctx, &n, &idx, nullptr));
   if (!n) return NM_OK;
   if (to_global) scatter_by_index<<<nm_blocks(n, 256), 256, 0, NM_LS(ctx)>>>(n, idx, src, dst);

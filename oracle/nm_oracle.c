@@ -280,6 +280,25 @@ static int rule_1d(int n, double *x, double *w)
             double wa = (18.0 + sqrt(30.0)) / 72.0, wb = (18.0 - sqrt(30.0)) / 72.0;
             x[0] = 0.5 - b; x[1] = 0.5 - a; x[2] = 0.5 + a; x[3] = 0.5 + b; w[0] = w[3] = wb; w[1] = w[2] = wa; return 4; }
   }
+  if (n >= 5 && n <= 8) { /* Newton on P_n: the rules the drivers ask for at degree p >= 2 (n = 2p + 1, 2d3d/lagrange_multiplier.cc:750-753) */
+    for (int i = 0; i < n; ++i) {
+      double z = cos(3.14159265358979323846 * (i + 0.75) / (n + 0.5)), pp = 1.0;
+      for (int it = 0; it < 100; ++it) {
+        double p1 = 1.0, p2 = 0.0;
+        for (int j = 0; j < n; ++j) { double p3 = p2; p2 = p1; p1 = ((2.0 * j + 1.0) * z * p2 - j * p3) / (j + 1.0); }
+        pp = n * (z * p1 - p2) / (z * z - 1.0);
+        double dz = p1 / pp;
+        z -= dz;
+        if (fabs(dz) < 1e-16) break;
+      }
+      { double p1 = 1.0, p2 = 0.0;
+        for (int j = 0; j < n; ++j) { double p3 = p2; p2 = p1; p1 = ((2.0 * j + 1.0) * z * p2 - j * p3) / (j + 1.0); }
+        pp = n * (z * p1 - p2) / (z * z - 1.0); }
+      x[n - 1 - i] = 0.5 + 0.5 * z;
+      w[n - 1 - i] = 1.0 / ((1.0 - z * z) * pp * pp);
+    }
+    return n;
+  }
   return 0;
 }
 static int rule_tri(int n, double (*x)[2], double *w)
