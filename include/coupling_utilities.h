@@ -7,9 +7,10 @@
 //   create_coupling_sparsity_pattern_with_exact_intersections<...>       reference :28-152
 //   create_coupling_mass_matrix_with_exact_intersections<...>            reference :154-304
 //
-// Implemented instantiations: <2,1,2> and <3,2,3> with FE_Q(1) on Cartesian background cells and
-// FE_DGQ(0) on the immersed grid (every LM configuration in data/*.prm).  Anything else raises
-// ExcNotImplemented -- there is no CPU fallback.
+// Implemented instantiations: <2,1,2> and <3,2,3> on Cartesian background cells.  FE_Q(1) x FE_DGQ(0) (every LM
+// configuration in data/*.prm) runs on the fused kernels; any other FE_Q(p) x FE_DGQ(q) pair (p <= 5, <= 64 / 16 DoFs per
+// cell) on the general path (nm_set_finite_elements / nm_assemble_fe), described to the library by the elements' unit
+// support points.  Anything else raises ExcNotImplemented -- there is no CPU fallback.
 //
 // First widening row, same boundary:
 //   assemble_nitsche_with_exact_intersections<...>                       reference :306-398
@@ -55,6 +56,7 @@ namespace nmgpu_detail {
 struct Session {
   nm_ctx *ctx = nullptr;
   bool grids_set = false, space_set = false;
+  bool general_fe = false;   // the dof tables on the device belong to FE_Q(p) x FE_DGQ(q) beyond (1, 0): nm_assemble_fe builds the matrix
   std::uint64_t n_space = 0, n_immersed = 0;
   std::size_t space_active_cells = 0, immersed_active_cells = 0;   // n_active_cells() of the grids on the device
   std::vector<unsigned int> space_local_of_active;     // active_cell_index -> row in the arrays sent to the GPU (or -1)
@@ -274,23 +276,68 @@ template <int dim0, int dim1, int spacedim, typename number>
 void set_dofs(Session &s, const DoFHandler<dim0, spacedim> &space_dh, const DoFHandler<dim1, spacedim> &immersed_dh,
               const AffineConstraints<number> &constraints, const AffineConstraints<number> &immersed_constraints)
 {
+  const auto &space_fe = space_dh.get_fe();
   const auto &immersed_fe = immersed_dh.get_fe();
-  AssertThrow(immersed_fe.n_components() == 1, ExcNotImplemented());
-  AssertThrow(immersed_fe.n_dofs_per_cell() == 1, ExcMessage("nmgpu: the immersed space must be FE_DGQ(0)"));
+  AssertThrow(space_fe.n_components() == 1 && immersed_fe.n_components() == 1, ExcNotImplemented());
   AssertThrow(immersed_constraints.n_constraints() == 0, ExcNotImplemented());
   // the sparsity and the mass-matrix call of one cycle pass the same handlers and constraints: send the tables once
   if (s.dofs.valid && s.dofs.space_dh == &space_dh && s.dofs.immersed_dh == &immersed_dh && s.dofs.constraints == &constraints &&
       s.dofs.n_space == space_dh.n_dofs() && s.dofs.n_immersed == immersed_dh.n_dofs() && s.dofs.n_constraints == constraints.n_constraints())
     return;
   s.dofs.valid = false;
-  set_space_dofs<dim0, spacedim>(s, space_dh, constraints);
-  std::vector<std::uint32_t> d1(s.n_immersed);
-  std::vector<types::global_dof_index> tmp1(1);
-  for (const auto &cell : immersed_dh.active_cell_iterators()) {
-    cell->get_dof_indices(tmp1);
-    d1[s.immersed_local_of_active[cell->active_cell_index()]] = static_cast<std::uint32_t>(tmp1[0]);
+  s.general_fe = !(space_fe.n_dofs_per_cell() == (1u << dim0) && immersed_fe.n_dofs_per_cell() == 1);
+  if (!s.general_fe) {   // FE_Q(1) x FE_DGQ(0): the configuration of every shipped .prm, on the fused kernels
+    set_space_dofs<dim0, spacedim>(s, space_dh, constraints);
+    std::vector<std::uint32_t> d1(s.n_immersed);
+    std::vector<types::global_dof_index> tmp1(1);
+    for (const auto &cell : immersed_dh.active_cell_iterators()) {
+      cell->get_dof_indices(tmp1);
+      d1[s.immersed_local_of_active[cell->active_cell_index()]] = static_cast<std::uint32_t>(tmp1[0]);
+    }
+    check(s, nm_set_immersed_dofs(s.ctx, d1.data(), 1, immersed_dh.n_dofs(), NM_HOST));
+  } else {
+    // FE_Q(p) x FE_DGQ(q): the elements are described by their unit support points in their own dof order
+    auto table = [&](const auto &dh, const std::vector<unsigned int> &local_of_active, const std::uint64_t n_cells) {
+      const unsigned int dpc = dh.get_fe().n_dofs_per_cell();
+      std::vector<std::uint32_t> tab(n_cells * dpc);
+      std::vector<types::global_dof_index> tmp(dpc);
+      for (const auto &cell : dh.active_cell_iterators()) {
+        const unsigned int l = local_of_active[cell->active_cell_index()];
+        if (l == static_cast<unsigned int>(-1))
+          continue;
+        cell->get_dof_indices(tmp);
+        for (unsigned int i = 0; i < dpc; ++i)
+          tab[std::size_t(l) * dpc + i] = static_cast<std::uint32_t>(tmp[i]);
+      }
+      return tab;
+    };
+    auto support = [](const auto &fe, const unsigned int dim) {
+      const auto &pts = fe.get_unit_support_points();
+      AssertThrow(pts.size() == fe.n_dofs_per_cell(), ExcMessage("nmgpu: the element has no unit support points (not a Lagrange element)"));
+      std::vector<double> flat;
+      for (const auto &p : pts)
+        for (unsigned int k = 0; k < dim; ++k)
+          flat.push_back(p[k]);
+      return flat;
+    };
+    const auto d0 = table(space_dh, s.space_local_of_active, s.n_space);
+    const auto d1 = table(immersed_dh, s.immersed_local_of_active, s.n_immersed);
+    const auto sp0 = support(space_fe, dim0), sp1 = support(immersed_fe, dim1);
+    std::vector<std::uint32_t> c_dof, c_master;
+    std::vector<std::uint64_t> c_ptr(1, 0);
+    std::vector<double> c_weight;
+    for (const auto &line : constraints.get_lines()) {
+      c_dof.push_back(static_cast<std::uint32_t>(line.index));
+      for (const auto &e : line.entries) {
+        c_master.push_back(static_cast<std::uint32_t>(e.first));
+        c_weight.push_back(static_cast<double>(e.second));
+      }
+      c_ptr.push_back(c_master.size());
+    }
+    const nm_fe f0{space_fe.degree, space_fe.n_dofs_per_cell(), sp0.data()}, f1{immersed_fe.degree, immersed_fe.n_dofs_per_cell(), sp1.data()};
+    check(s, nm_set_finite_elements(s.ctx, &f0, d0.data(), space_dh.n_dofs(), c_dof.size(), c_dof.data(), c_ptr.data(), c_master.data(),
+                                    c_weight.data(), &f1, d1.data(), immersed_dh.n_dofs(), NM_HOST));
   }
-  check(s, nm_set_immersed_dofs(s.ctx, d1.data(), 1, immersed_dh.n_dofs(), NM_HOST));
   s.dofs.space_dh = &space_dh;
   s.dofs.immersed_dh = &immersed_dh;
   s.dofs.constraints = &constraints;
@@ -377,7 +424,19 @@ void assemble_from_info(Session &s,
     }
     off.push_back(w.size());
   }
-  check(s, nm_assemble_from_quadrature(s.ctx, info.size(), im.data(), bg.data(), off.data(), pts.data(), w.data(), NM_HOST));
+  if (s.general_fe)
+    check(s, nm_assemble_fe(s.ctx, info.size(), im.data(), bg.data(), off.data(), pts.data(), w.data(), NM_HOST, nullptr));
+  else
+    check(s, nm_assemble_from_quadrature(s.ctx, info.size(), im.data(), bg.data(), off.data(), pts.data(), w.data(), NM_HOST));
+}
+
+// the matrix from the quadrature that is still on the device (the caller handed back the vector collect_...() returned)
+inline void assemble_from_device_result(Session &s)
+{
+  if (s.general_fe)
+    check(s, nm_assemble_fe(s.ctx, 0, nullptr, nullptr, nullptr, nullptr, nullptr, NM_DEVICE, nullptr));
+  else
+    check(s, nm_assemble(s.ctx));
 }
 
 // The matrix of the context, rows with entries only, handed to `visit(row, n, cols, vals)` (vals == nullptr: pattern).
@@ -474,7 +533,8 @@ void create_coupling_sparsity_pattern_with_exact_intersections(
   if (!nmgpu_detail::is_own_result(s, intersections_info)) {   // a foreign vector: its quadrature has to travel to the device
     nmgpu_detail::assemble_from_info<dim0, dim1, spacedim>(s, intersections_info);
     s.own.valid = false;
-  }
+  } else if (s.general_fe)
+    nmgpu_detail::assemble_from_device_result(s);               // pattern and values come out of one pass
   nmgpu_detail::for_each_stored_row(s, false, [&](types::global_dof_index r, types::global_dof_index, const std::vector<types::global_dof_index> &cols,
                                                   const double *) { sparsity.add_entries(r, cols.begin(), cols.end(), /*indices_are_sorted=*/true); });
 }
@@ -500,7 +560,7 @@ void create_coupling_mass_matrix_with_exact_intersections(
                                                   immersed_mapping, nullptr, nullptr);
   nmgpu_detail::set_dofs<dim0, dim1, spacedim>(s, space_dh, immersed_dh, space_constraints, immersed_constraints);
   if (nmgpu_detail::is_own_result(s, cells_and_quads))
-    nmgpu_detail::check(s, nm_assemble(s.ctx));                 // the quadrature never left the device
+    nmgpu_detail::assemble_from_device_result(s);               // the quadrature never left the device
   else {
     nmgpu_detail::assemble_from_info<dim0, dim1, spacedim>(s, cells_and_quads);
     s.own.valid = false;

@@ -223,6 +223,7 @@ int nm_destroy(nm_ctx *ctx)
   if (ctx->ev3) cudaEventDestroy(ctx->ev3);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->down_thread.joinable()) ctx->down_thread.join();
   if (ctx->down_stream) { cudaStreamSynchronize(ctx->down_stream); cudaStreamDestroy(ctx->down_stream); }
   if (ctx->ev_down_ready) cudaEventDestroy(ctx->ev_down_ready);
   if (ctx->ev_down_done) cudaEventDestroy(ctx->ev_down_done);
@@ -875,16 +876,28 @@ int nm_get_csr_compact(nm_ctx *ctx, uint64_t *n_rows, uint32_t *row_ids, uint32_
   NM_TRY(nm_nonempty_rows(ctx, &nr, &ids, &len));
   if (n_rows) *n_rows = nr;
   if (where == NM_HOST_ASYNC) {
-    // the copies run on their own stream behind everything queued so far; the next matrix build waits for them
+    // the copies run on their own stream behind everything queued so far, issued by a helper thread; the next matrix
+    // build waits for them (nm_wait_download_issued + ev_down_done)
     NM_TRY(ensure_down_stream(ctx));
+    if (ctx->down_thread.joinable()) ctx->down_thread.join();
     NM_CUDA(cudaEventRecord(ctx->ev_down_ready, ctx->stream));
-    NM_CUDA(cudaStreamWaitEvent(ctx->down_stream, ctx->ev_down_ready, 0));
-    cudaStream_t ds = ctx->down_stream;
-    if (row_ids && nr) NM_CUDA(cudaMemcpyAsync(row_ids, ids, nr * 4, cudaMemcpyDeviceToHost, ds));
-    if (row_len && nr) NM_CUDA(cudaMemcpyAsync(row_len, len, nr * 4, cudaMemcpyDeviceToHost, ds));
-    if (col && ctx->nnz) NM_CUDA(cudaMemcpyAsync(col, ctx->a_col.p, ctx->nnz * 4, cudaMemcpyDeviceToHost, ds));
-    if (val && ctx->nnz) NM_CUDA(cudaMemcpyAsync(val, ctx->a_val.p, ctx->nnz * 8, cudaMemcpyDeviceToHost, ds));
-    NM_CUDA(cudaEventRecord(ctx->ev_down_done, ds));
+    ctx->down_issued.store(0);
+    ctx->down_rc = 0;
+    const uint64_t nnz = ctx->nnz;
+    const void *src_col = ctx->a_col.p, *src_val = ctx->a_val.p;
+    ctx->down_thread = std::thread([=]() {
+      cudaSetDevice(ctx->device);
+      cudaStream_t ds = ctx->down_stream;
+      cudaError_t e = cudaStreamWaitEvent(ds, ctx->ev_down_ready, 0);
+      if (e == cudaSuccess && row_ids && nr) e = cudaMemcpyAsync(row_ids, ids, nr * 4, cudaMemcpyDeviceToHost, ds);
+      if (e == cudaSuccess && row_len && nr) e = cudaMemcpyAsync(row_len, len, nr * 4, cudaMemcpyDeviceToHost, ds);
+      if (e == cudaSuccess && col && nnz) e = cudaMemcpyAsync(col, src_col, nnz * 4, cudaMemcpyDeviceToHost, ds);
+      if (e == cudaSuccess && val && nnz) e = cudaMemcpyAsync(val, src_val, nnz * 8, cudaMemcpyDeviceToHost, ds);
+      if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_down_done, ds);
+      ctx->down_rc = (int)e;
+      ctx->down_issued.store(1);
+      cudaStreamSynchronize(ds);
+    });
     ctx->download_pending = true;
     tm.stop();
     return NM_OK;
@@ -902,10 +915,23 @@ int nm_sync_downloads(nm_ctx *ctx)
 {
   if (!ctx) return NM_ERR_INVALID;
   NM_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->down_thread.joinable()) ctx->down_thread.join();
   if (ctx->down_stream) NM_CUDA(cudaStreamSynchronize(ctx->down_stream));
   ctx->download_pending = false;
+  if (ctx->down_rc) return nm_fail(ctx, NM_ERR_CUDA, "asynchronous read-back failed: %s", cudaGetErrorString((cudaError_t)ctx->down_rc));
   return NM_OK;
 }
+
+}  // extern "C"
+
+// before a stream may wait for ev_down_done the helper thread must have recorded it
+int nm_wait_download_issued(nm_ctx *ctx)
+{
+  while (ctx->down_thread.joinable() && !ctx->down_issued.load()) std::this_thread::yield();
+  return NM_OK;
+}
+
+extern "C" {
 
 static int local_count(nm_ctx *ctx, int which, uint64_t *n)
 {

@@ -414,7 +414,7 @@ int nm_assemble_fe(nm_ctx *ctx, uint64_t n_pairs, const uint32_t *immersed, cons
   ctx->n_local_rows = ctx->n_space_dofs;
   ctx->out_rows_valid = false;
   ctx->merge_path = 2;
-  if (ctx->download_pending) { NM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_down_done, 0)); ctx->download_pending = false; }
+  if (ctx->download_pending) { NM_TRY(nm_wait_download_issued(ctx)); NM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_down_done, 0)); ctx->download_pending = false; }
   NM_TRY(nm_transpose_build(ctx));
   if (nnz_out) *nnz_out = ctx->nnz;
   return NM_OK;

@@ -1102,6 +1102,7 @@ int nm_matrix_build(nm_ctx *ctx)
 {
   NM_TRY(check_dof_tables(ctx));
   if (ctx->download_pending) {   // an asynchronous read-back of the previous matrix may still be reading the buffers rebuilt here
+    NM_TRY(nm_wait_download_issued(ctx));
     NM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_down_done, 0));
     ctx->download_pending = false;
   }

@@ -141,8 +141,11 @@ private:
 template <int dim, int spacedim = dim> class FiniteElement {
 public:
   unsigned dpc = 1;
+  unsigned degree = 0;
+  std::vector<Point<dim>> unit_support_points;   // in the element's dof order (deal.II: FiniteElement::get_unit_support_points())
   unsigned n_components() const { return 1; }
   unsigned n_dofs_per_cell() const { return dpc; }
+  const std::vector<Point<dim>> &get_unit_support_points() const { return unit_support_points; }
 };
 
 template <int dim, int spacedim = dim> class DoFHandler {

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <fstream>
 #include <iostream>
+#include <string>
 
 using namespace dealii;
 
@@ -102,6 +103,63 @@ template <int dim0, int dim1, int spacedim> int run(std::ifstream &in, const cha
     for (const auto &e : system_matrix.data[r]) std::fprintf(f, "%u %u %.17g\n", r, e.first, e.second);
   for (unsigned r = 0; r < n_space_dofs; ++r) std::fprintf(f, "%.17g\n", system_rhs(r));
   std::fclose(f);
+  // optional second part of the grid file: higher-degree handlers on the same triangulations (FE_Q(p) x FE_DGQ(q)); the
+  // same three calls, with a rule of 2p + 1 points as the drivers choose it (2d3d/lagrange_multiplier.cc:750-753)
+  unsigned dpc0 = 0;
+  if (in >> dpc0) {
+    DoFHandler<dim0, spacedim> space_dh2;
+    DoFHandler<dim1, spacedim> immersed_dh2;
+    unsigned dpc1 = 0, ns2 = 0, ni2 = 0, nl2 = 0;
+    in >> space_dh2.fe.degree;
+    space_dh2.fe.dpc = dpc0;
+    space_dh2.fe.unit_support_points.resize(dpc0);
+    for (unsigned i = 0; i < dpc0; ++i)
+      for (int d = 0; d < dim0; ++d) in >> space_dh2.fe.unit_support_points[i][d];
+    in >> ns2;
+    space_dh2.table.resize(std::size_t(n_bg) * dpc0);
+    for (auto &v : space_dh2.table) in >> v;
+    AffineConstraints<double> constraints2;
+    in >> nl2;
+    for (unsigned l = 0; l < nl2; ++l) {
+      unsigned dof, nm;
+      in >> dof >> nm;
+      auto &line = constraints2.lines[dof];
+      for (unsigned k = 0; k < nm; ++k) { unsigned m; double w; in >> m >> w; line.emplace_back(m, w); }
+    }
+    in >> dpc1 >> immersed_dh2.fe.degree;
+    immersed_dh2.fe.dpc = dpc1;
+    immersed_dh2.fe.unit_support_points.resize(dpc1);
+    for (unsigned i = 0; i < dpc1; ++i)
+      for (int d = 0; d < dim1; ++d) in >> immersed_dh2.fe.unit_support_points[i][d];
+    in >> ni2;
+    immersed_dh2.table.resize(std::size_t(n_im) * dpc1);
+    for (auto &v : immersed_dh2.table) in >> v;
+    space_dh2.tria = &space; space_dh2.ndofs = ns2;
+    immersed_dh2.tria = &immersed; immersed_dh2.ndofs = ni2;
+    const auto info2 = NonMatching::collect_quadratures_on_overlapped_grids(space_cache, immersed_cache, 2 * space_dh2.fe.degree + 1, 1e-15);
+    DynamicSparsityPattern dsp2(ns2, ni2);
+    NonMatching::create_coupling_sparsity_pattern_with_exact_intersections(info2, space_dh2, immersed_dh2, dsp2, constraints2, ComponentMask(),
+                                                                          ComponentMask(), immersed_constraints);
+    StubSparseMatrix<double> matrix2(ns2, ni2);
+    NonMatching::create_coupling_mass_matrix_with_exact_intersections(space_dh2, immersed_dh2, info2, matrix2, constraints2, ComponentMask(),
+                                                                     ComponentMask(), space_mapping, immersed_mapping, immersed_constraints);
+    // and once more from a COPY of the tuples (a foreign vector: the quadrature travels through the host)
+    const auto copy2 = info2;
+    StubSparseMatrix<double> matrix3(ns2, ni2);
+    NonMatching::create_coupling_mass_matrix_with_exact_intersections(space_dh2, immersed_dh2, copy2, matrix3, constraints2, ComponentMask(),
+                                                                     ComponentMask(), space_mapping, immersed_mapping, immersed_constraints);
+    std::FILE *g = std::fopen((std::string(out_path) + ".fe").c_str(), "w");
+    std::size_t nnz2 = 0;
+    for (const auto &r : dsp2.entries) nnz2 += r.size();
+    std::fprintf(g, "%zu\n", nnz2);
+    for (unsigned r = 0; r < dsp2.rows; ++r)
+      for (auto c : dsp2.entries[r]) {
+        auto it = matrix2.data[r].find(c);
+        auto jt = matrix3.data[r].find(c);
+        std::fprintf(g, "%u %u %.17g %.17g\n", r, c, it == matrix2.data[r].end() ? 0.0 : it->second, jt == matrix3.data[r].end() ? 0.0 : jt->second);
+      }
+    std::fclose(g);
+  }
   // error behaviour of the reference: AssertThrow(degree > 0)
   try {
     NonMatching::collect_quadratures_on_overlapped_grids(space_cache, immersed_cache, 0, 1e-15);

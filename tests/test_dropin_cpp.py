@@ -85,3 +85,49 @@ def test_cpp_driver_matches_oracle(tmp_path, c_oracle, name, cycle):
     rhs = np.array([float(x) for x in lines[3 + nnz + n_nit:3 + nnz + n_nit + bg.n_dofs]])
     assert np.linalg.norm(rhs - b) <= 1e-13 * np.linalg.norm(b)
     info.ctx.close()
+
+
+@pytest.mark.gpu
+def test_cpp_driver_higher_degree_elements(tmp_path, c_oracle):
+    """The reference's three calls with FE_Q(2) x FE_DGQ(1) handlers through the drop-in header (general path, elements
+    described by their unit support points) against oracle/fe_oracle.py -- from the vector collect() returned (device-
+    resident quadrature) and from a copy of it (tuples through the host)."""
+    import torch
+    from oracle import fe_oracle as fo
+    from fe_helpers import uniform_background, continuous_dofs, discontinuous_dofs, random_constraint_lines
+    from non_matching_test_suite_b200.grids import BackgroundGrid, circle_grid
+    build_driver()
+    lo, hi = uniform_background(2, 10)
+    im = circle_grid(48)
+    e = torch.empty(0, dtype=torch.int32)
+    # the first part of the file: Q1 x P0 numbering of the same grids (any valid numbering will do)
+    sb1 = fo.unit_support_points(2, 1)
+    d1, n1 = continuous_dofs(lo, hi, sb1)
+    bg = BackgroundGrid(2, torch.from_numpy(lo), torch.from_numpy(hi), torch.from_numpy(d1.astype(np.int32)), n1, torch.zeros(lo.shape[0], dtype=torch.int32),
+                        e, torch.zeros(1, dtype=torch.int64), e, torch.empty(0, dtype=torch.float64))
+    grid, out = str(tmp_path / "grid.txt"), str(tmp_path / "out.txt")
+    write_grid(grid, bg, im)
+    p, q = 2, 1
+    sb, si = fo.unit_support_points(2, p, "shuffled", 1), fo.unit_support_points(1, q)
+    bd, ns = continuous_dofs(lo, hi, sb)
+    idf, ni = discontinuous_dofs(im.n_cells, si.shape[0])
+    cd, cp, cm, cw = random_constraint_lines(ns, ns // 10, seed=3)
+    with open(grid, "a") as f:
+        f.write("%d %d\n" % (sb.shape[0], p) + " ".join(repr(float(x)) for x in sb.ravel()) + "\n%d\n" % ns)
+        f.write(" ".join(str(int(x)) for x in bd.ravel()) + "\n%d\n" % len(cd))
+        for i in range(len(cd)):
+            f.write("%d %d " % (cd[i], cp[i + 1] - cp[i]) + " ".join("%d %r" % (cm[k], float(cw[k])) for k in range(int(cp[i]), int(cp[i + 1]))) + "\n")
+        f.write("%d %d\n" % (si.shape[0], q) + " ".join(repr(float(x)) for x in si.ravel()) + "\n%d\n" % ni)
+        f.write(" ".join(str(int(x)) for x in idf.ravel()) + "\n")
+    subprocess.check_call([BIN, grid, out])
+    r = c_oracle.assemble_with_quadrature(bg, im, 2 * p + 1, 1e-15)
+    pim, pbg = (r["accepted"] >> np.uint64(32)).astype(np.int64), (r["accepted"] & np.uint64(0xffffffff)).astype(np.int64)
+    want = fo.coupling_matrix(lo, hi, bd, ns, cd, cp, cm, cw, im.verts.numpy(), idf, ni, pim, pbg, r["q_offset"], r["points"], r["weights"], sb, si)
+    want.sort_indices()
+    lines = open(out + ".fe").read().split("\n")
+    nnz = int(lines[0])
+    got = np.array([[float(x) for x in l.split()] for l in lines[1:1 + nnz]])
+    rows = np.repeat(np.arange(ns), np.diff(want.indptr))
+    assert nnz == want.nnz and np.array_equal(got[:, 0].astype(np.int64), rows) and np.array_equal(got[:, 1].astype(np.int64), want.indices)
+    for k in (2, 3):
+        assert np.linalg.norm(got[:, k] - want.data) <= 1e-12 * np.linalg.norm(want.data)
