@@ -47,69 +47,11 @@ int nm_ensure(nm_ctx *ctx, DevBuf &b, size_t bytes)
   return NM_OK;
 }
 
-// Large transfers from / to PAGEABLE host memory (std::vector storage of a C++ caller) go through two pinned bounce
-// buffers: the DMA of chunk k runs while the CPU copies chunk k-1, instead of the driver's own unpipelined staging
-// (measured: 5 GB/s for a 2.5 GB read-back).  Pinned or registered caller memory is copied directly.
-static constexpr size_t PIN_CHUNK = size_t(32) << 20;
-
-static bool is_pageable(const void *p)
-{
-  cudaPointerAttributes a;
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
-  return a.type == cudaMemoryTypeUnregistered;
-}
-
-static int ensure_pins(nm_ctx *ctx)
-{
-  for (int k = 0; k < 2; ++k) {
-    if (!ctx->pin[k]) NM_CUDA(cudaHostAlloc(&ctx->pin[k], PIN_CHUNK, cudaHostAllocDefault));
-    if (!ctx->ev_pin[k]) NM_CUDA(cudaEventCreateWithFlags(&ctx->ev_pin[k], cudaEventDisableTiming));
-  }
-  return NM_OK;
-}
-
-static int staged_h2d(nm_ctx *ctx, void *dst_dev, const void *src, size_t bytes)
-{
-  NM_TRY(ensure_pins(ctx));
-  const size_t n = (bytes + PIN_CHUNK - 1) / PIN_CHUNK;
-  for (size_t k = 0; k < n; ++k) {
-    const int b = (int)(k & 1);
-    const size_t o = k * PIN_CHUNK, len = bytes - o < PIN_CHUNK ? bytes - o : PIN_CHUNK;
-    if (k >= 2) NM_CUDA(cudaEventSynchronize(ctx->ev_pin[b]));   // the DMA that last read this bounce buffer is done
-    memcpy(ctx->pin[b], static_cast<const char *>(src) + o, len);
-    NM_CUDA(cudaMemcpyAsync(static_cast<char *>(dst_dev) + o, ctx->pin[b], len, cudaMemcpyHostToDevice, ctx->stream));
-    NM_CUDA(cudaEventRecord(ctx->ev_pin[b], ctx->stream));
-  }
-  NM_SYNC(ctx);   // the bounce buffers are reused by the next call
-  return NM_OK;
-}
-
-static int staged_d2h(nm_ctx *ctx, void *dst, const void *src_dev, size_t bytes)
-{
-  NM_TRY(ensure_pins(ctx));
-  const size_t n = (bytes + PIN_CHUNK - 1) / PIN_CHUNK;
-  auto len_of = [&](size_t k) { const size_t o = k * PIN_CHUNK; return bytes - o < PIN_CHUNK ? bytes - o : PIN_CHUNK; };
-  for (size_t k = 0; k <= n; ++k) {
-    if (k < n) {
-      const int b = (int)(k & 1);
-      NM_CUDA(cudaMemcpyAsync(ctx->pin[b], static_cast<const char *>(src_dev) + k * PIN_CHUNK, len_of(k), cudaMemcpyDeviceToHost, ctx->stream));
-      NM_CUDA(cudaEventRecord(ctx->ev_pin[b], ctx->stream));
-    }
-    if (k >= 1) {   // chunk k-1 has landed: copy it out while chunk k is in flight
-      const int b = (int)((k - 1) & 1);
-      NM_CUDA(cudaEventSynchronize(ctx->ev_pin[b]));
-      memcpy(static_cast<char *>(dst) + (k - 1) * PIN_CHUNK, ctx->pin[b], len_of(k - 1));
-    }
-  }
-  return NM_OK;
-}
-
 int nm_upload(nm_ctx *ctx, DevBuf &b, const void *src, size_t bytes, int where)
 {
   NM_TRY(nm_ensure(ctx, b, bytes));
   if (bytes == 0) return NM_OK;
   if (!src) return nm_fail(ctx, NM_ERR_INVALID, "null input pointer");
-  if (where == NM_HOST && bytes >= 2 * PIN_CHUNK && is_pageable(src)) return staged_h2d(ctx, b.p, src, bytes);
   NM_CUDA(cudaMemcpyAsync(b.p, src, bytes, where == NM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
   return NM_OK;
 }
@@ -117,7 +59,6 @@ int nm_upload(nm_ctx *ctx, DevBuf &b, const void *src, size_t bytes, int where)
 int nm_download(nm_ctx *ctx, void *dst, const void *src, size_t bytes, int where)
 {
   if (bytes == 0 || !dst) return NM_OK;
-  if (where == NM_HOST && bytes >= 2 * PIN_CHUNK && is_pageable(dst)) return staged_d2h(ctx, dst, src, bytes);
   NM_CUDA(cudaMemcpyAsync(dst, src, bytes, where == NM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
   return NM_OK;
 }
@@ -227,10 +168,6 @@ int nm_destroy(nm_ctx *ctx)
   if (ctx->down_stream) { cudaStreamSynchronize(ctx->down_stream); cudaStreamDestroy(ctx->down_stream); }
   if (ctx->ev_down_ready) cudaEventDestroy(ctx->ev_down_ready);
   if (ctx->ev_down_done) cudaEventDestroy(ctx->ev_down_done);
-  for (int k = 0; k < 2; ++k) {
-    if (ctx->pin[k]) cudaFreeHost(ctx->pin[k]);
-    if (ctx->ev_pin[k]) cudaEventDestroy(ctx->ev_pin[k]);
-  }
   for (cudaEvent_t e : ctx->ev_copy)
     if (e) cudaEventDestroy(e);
   delete ctx;

@@ -47,8 +47,6 @@ struct nm_ctx {
   cudaStream_t copy_stream = nullptr;           // host->device copies of nm_assemble_host
   cudaStream_t down_stream = nullptr;           // device->host copies of nm_get_csr_compact(NM_HOST_ASYNC)
   cudaEvent_t ev_down_ready = nullptr, ev_down_done = nullptr;
-  void *pin[2] = {nullptr, nullptr};            // pinned bounce buffers for large transfers from / to pageable memory
-  cudaEvent_t ev_pin[2] = {nullptr, nullptr};
   // the copies of an asynchronous read-back are issued by a helper thread: the caller gets control back at once even
   // where the driver makes a multi-GB cudaMemcpyAsync wait (measured: 60 ms inside the call for 3.4 GB)
   std::thread down_thread;

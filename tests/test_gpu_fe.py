@@ -87,13 +87,14 @@ def test_2d_degrees_against_the_oracle(c_oracle, p, q, order):
     # the products and the local numbering (cell, local dof)
     g = np.random.default_rng(0)
     x, u = g.random(ni), g.random(ns)
-    assert np.allclose(ctx.spmv(torch.from_numpy(x), transpose=False).numpy(), want @ x, rtol=1e-12, atol=1e-15)
-    assert np.allclose(ctx.spmv(torch.from_numpy(u), transpose=True).numpy(), want.T @ u, rtol=1e-12, atol=1e-15)
+    close = lambda a, b: np.abs(a - b).max() <= 1e-12 * np.abs(b).max()     # higher-degree bases change sign: entries of A x cancel
+    assert close(ctx.spmv(torch.from_numpy(x), transpose=False).numpy(), want @ x)
+    assert close(ctx.spmv(torch.from_numpy(u), transpose=True).numpy(), want.T @ u)
     z_loc = ctx.spmv_local(torch.from_numpy(u[ctx.csr_compact()[0].long().numpy()]), transpose=True)
     assert z_loc.numel() == im.n_cells * si.shape[0]
     rows = ctx.csr_compact()[0].long().numpy()
     u0 = np.zeros(ns); u0[rows] = u[rows]
-    assert np.allclose(z_loc.numpy(), (want.T @ u0)[idf.reshape(-1).astype(np.int64)], rtol=1e-12, atol=1e-15)
+    assert close(z_loc.numpy(), (want.T @ u0)[idf.reshape(-1).astype(np.int64)])
     # the same from the caller's tuples (the reference's own signature)
     ctx.assemble_fe(t(pim.astype(np.uint32)), t(pbg.astype(np.uint32)), t(r["q_offset"].astype(np.uint64)), torch.from_numpy(r["points"]),
                     torch.from_numpy(r["weights"]))
