@@ -378,6 +378,7 @@ def run_problem(args, torch, dist, _lib, ctx, P, rank, world, local, dev, peak, 
     bg, im, d = P.bg, P.im, P.d
     stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
     sharded_op = from_context(ctx)
+    sharded_op.m, sharded_op.n = bg.n_dofs, im.n_dofs     # the context learns its sizes with the first assembly
     fused = {"op": None, "tried": False, "why": ""}
     owned = args.ct_vmult == "owned"
 
@@ -546,6 +547,22 @@ def run_e2e(args, torch, dist, _lib, ctx, P, rank, world, dev, timed, get_fused,
     pin = lambda n, dt: torch.empty(n, dtype=dt).pin_memory()
     glob = args.e2e_global_vectors
     pipelined = not args.e2e_serial and not glob and "lo" in host_in
+    # pinned host memory this rank is about to hold: inputs (already pinned above) + read-back buffers (two sets when the
+    # read-back is pipelined) + vectors; all ranks of the node share the host RAM
+    out_bytes = rows_cap * 8 + nnz_cap * 12
+    vec_bytes = 8 * (2 * P.n_im + 2 * rows_cap + bg.n_dofs // max(1, world))
+    try:
+        avail = [int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0]
+    except Exception:
+        avail = None
+    if avail is not None:
+        share = 0.8 * avail / max(1, world)       # inputs are already resident: `avail` is what is left
+        if pipelined and 2 * out_bytes + vec_bytes > share:
+            pipelined = False                     # one buffer set, blocking read-back
+        if out_bytes + vec_bytes > share:
+            del host_in
+            return {"skipped": "host memory: %.1f GB per rank needed for the read-back buffers, %.1f GB available per rank" % (
+                (out_bytes + vec_bytes) / 1e9, share / 1e9)}
     io = {"h2d": 0, "d2h": 0}
 
     if glob:
