@@ -275,6 +275,37 @@ int nm_set_finite_elements(nm_ctx *ctx, const nm_fe *space_fe, const uint32_t *s
 int nm_assemble_fe(nm_ctx *ctx, uint64_t n_pairs, const uint32_t *immersed, const uint32_t *background, const uint64_t *q_offset,
                    const double *points, const double *weights, int where, uint64_t *nnz);
 
+/* ---- the Schur-complement solve around the GPU products (the rest of solve()) ----
+ * Replaces PoissonLM::solve() (code/examples/lagrange_multiplier/2d3d/lagrange_multiplier.cc:613-659,
+ * 1d2d/lagrange_multiplier.cc:675-730) with Ct = the context's assembled coupling matrix and C its transpose:
+ *   K_inv = CG on K (ReductionControl inner_*), preconditioner = C K Ct + M applied by multiplication (:630),
+ *   S = C K_inv Ct (:632), lambda = GMRES(S, ReductionControl outer_*) (C K_inv space_rhs - embedded_rhs) (:636-642),
+ *   solution = K_inv (space_rhs - Ct lambda), then AffineConstraints::distribute with the context's constraint lines (:643,:658).
+ * ReductionControl(n, tol, reduce) stops at |r| <= tol or |r| <= reduce |r_0| (deal.II); GMRES is restarted and left-
+ * preconditioned with `gmres_basis` Krylov vectors (0 = deal.II's default, 28).  K (n_space x n_space, symmetric positive
+ * definite as the drivers assemble it, constrained rows included) and M (n_immersed x n_immersed) are CSR matrices of the
+ * caller; `inhomogeneity` (one value per constraint line, NULL = 0) is what distribute() adds.  The CG on K is
+ * preconditioned with diag(K) instead of the reference's Trilinos AMG: the same K_inv up to inner_tol, other iteration counts.
+ * All products with the coupling matrix are this library's SpMV kernels; every vector operation runs on the GPU. */
+typedef struct {
+  uint64_t n_space, n_immersed;
+  const uint64_t *k_rowptr; const uint32_t *k_col; const double *k_val;
+  const uint64_t *m_rowptr; const uint32_t *m_col; const double *m_val;
+  const double *space_rhs, *embedded_rhs;
+  const double *inhomogeneity;
+  unsigned inner_max_it; double inner_tol, inner_reduce;
+  unsigned outer_max_it; double outer_tol, outer_reduce;
+  unsigned gmres_basis;
+} nm_schur_problem;
+typedef struct {
+  unsigned outer_iterations;      /* reduction_control.last_step() of the GMRES on S */
+  uint64_t inner_iterations;      /* CG iterations on K, summed over all applications of K_inv */
+  double outer_residual;          /* preconditioned residual the GMRES stopped at */
+  double lambda_norm_sqr;         /* lambda.norm_sqr(), printed by the drivers (:644) */
+  float ms;                       /* device time of the whole solve */
+} nm_schur_stats;
+int nm_schur_solve(nm_ctx *ctx, const nm_schur_problem *problem, double *lambda, double *solution, nm_schur_stats *stats, int where);
+
 /* ---- interface-penalisation (Nitsche) terms on a caller-supplied quadrature ----
  * Replaces the arithmetic of assemble_nitsche_with_exact_intersections (code/include/coupling_utilities.h:306-398) and
  * create_nitsche_rhs_with_exact_intersections (:400-481): for tuple p with background cell background[p] and points

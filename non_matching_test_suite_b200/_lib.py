@@ -28,7 +28,7 @@ SYMBOLS = ["nm_version", "nm_create", "nm_destroy", "nm_last_error", "nm_set_bac
            "nm_set_background_dofs", "nm_set_immersed_dofs", "nm_set_immersed", "nm_flag_overlapped_background", "nm_intersect", "nm_get_candidates", "nm_get_pairs", "nm_get_quadrature",
            "nm_get_split_codes", "nm_build_sparsity", "nm_assemble", "nm_assemble_from_quadrature", "nm_assemble_host", "nm_assemble_nitsche", "nm_get_nitsche", "nm_get_csr",
            "nm_get_csr_compact", "nm_sync_downloads", "nm_spmv", "nm_spmv_local", "nm_local_to_global", "nm_global_to_local",
-           "nm_spmv_push", "nm_spmv_push_owned", "nm_set_finite_elements", "nm_assemble_fe", "nm_get_info", "nm_measure_fp64_peak", "nm_get_timings", "nm_get_launch_count", "nm_device_bytes", "nm_get_stream"]
+           "nm_spmv_push", "nm_spmv_push_owned", "nm_set_finite_elements", "nm_assemble_fe", "nm_schur_solve", "nm_get_info", "nm_measure_fp64_peak", "nm_get_timings", "nm_get_launch_count", "nm_device_bytes", "nm_get_stream"]
 
 
 class NmError(RuntimeError):
@@ -48,6 +48,19 @@ class HostProblem(C.Structure):
 class FeDesc(C.Structure):
     """nm_fe of include/nmgpu.h."""
     _fields_ = [("degree", C.c_uint), ("dofs_per_cell", C.c_uint), ("unit_support_points", C.c_void_p)]
+
+
+class SchurProblem(C.Structure):
+    """nm_schur_problem of include/nmgpu.h."""
+    _fields_ = [("n_space", C.c_uint64), ("n_immersed", C.c_uint64), ("k_rowptr", C.c_void_p), ("k_col", C.c_void_p), ("k_val", C.c_void_p),
+                ("m_rowptr", C.c_void_p), ("m_col", C.c_void_p), ("m_val", C.c_void_p), ("space_rhs", C.c_void_p), ("embedded_rhs", C.c_void_p),
+                ("inhomogeneity", C.c_void_p), ("inner_max_it", C.c_uint), ("inner_tol", C.c_double), ("inner_reduce", C.c_double),
+                ("outer_max_it", C.c_uint), ("outer_tol", C.c_double), ("outer_reduce", C.c_double), ("gmres_basis", C.c_uint)]
+
+
+class SchurStats(C.Structure):
+    _fields_ = [("outer_iterations", C.c_uint), ("inner_iterations", C.c_uint64), ("outer_residual", C.c_double),
+                ("lambda_norm_sqr", C.c_double), ("ms", C.c_float)]
 
 
 class Counts(C.Structure):
@@ -100,6 +113,7 @@ def load():
     L.nm_global_to_local.argtypes = [P, I, P, P, I]
     L.nm_set_finite_elements.argtypes = [P, C.POINTER(FeDesc), P, U64, U64, P, P, P, P, C.POINTER(FeDesc), P, U64, I]
     L.nm_assemble_fe.argtypes = [P, U64, P, P, P, P, P, I, C.POINTER(U64)]
+    L.nm_schur_solve.argtypes = [P, C.POINTER(SchurProblem), P, P, C.POINTER(SchurStats), I]
     L.nm_get_info.argtypes = [P, I, C.POINTER(U64)]
     L.nm_measure_fp64_peak.argtypes = [P, C.c_double, C.POINTER(C.c_double)]
     L.nm_spmv_push.argtypes = [P, P, I, C.POINTER(C.c_void_p), I]
@@ -329,6 +343,23 @@ class Context:
                                             _ptr(weights)[0], w, C.byref(nnz)))
         self.nnz = int(nnz.value)
         return self.nnz
+
+    def schur_solve(self, K, M, space_rhs, embedded_rhs, inner=(2000, 1e-14, 1e-12), outer=(0, 1e-11, 1e-2), inhomogeneity=None,
+                    gmres_basis: int = 28):
+        """The drivers' solve() around this context's coupling matrix (nm_schur_solve): K, M = (rowptr int64, col int32,
+        val float64) CSR triples; inner / outer = ReductionControl (max iterations, tol, reduce) of the CG on K and of the
+        GMRES on the Schur complement.  Returns (lambda, solution, stats dict), on the side the inputs live on."""
+        arrs = list(K) + list(M) + [space_rhs, embedded_rhs] + ([inhomogeneity] if inhomogeneity is not None else [])
+        w = _where(*arrs)
+        pr = SchurProblem(int(space_rhs.shape[0]), int(embedded_rhs.shape[0]), _ptr(K[0])[0], _ptr(K[1])[0], _ptr(K[2])[0], _ptr(M[0])[0],
+                          _ptr(M[1])[0], _ptr(M[2])[0], _ptr(space_rhs)[0], _ptr(embedded_rhs)[0], _ptr(inhomogeneity)[0], int(inner[0]),
+                          float(inner[1]), float(inner[2]), int(outer[0]), float(outer[1]), float(outer[2]), int(gmres_basis))
+        dev = "cuda" if w == NM_DEVICE else "cpu"
+        lam = self._out(pr.n_immersed, torch.float64, dev)
+        sol = self._out(pr.n_space, torch.float64, dev)
+        st = SchurStats()
+        self._chk(self.L.nm_schur_solve(self.h, C.byref(pr), _ptr(lam)[0], _ptr(sol)[0], C.byref(st), w))
+        return lam, sol, {n: getattr(st, n) for n, _ in SchurStats._fields_}
 
     def csr(self, transpose: bool = False, values: bool = True, device="cpu", out=None):
         """CSR of the matrix; `out=(rowptr, col, val)` reuses caller buffers (e.g. pinned host memory)

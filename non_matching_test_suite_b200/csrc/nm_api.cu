@@ -72,7 +72,7 @@ static std::vector<DevBuf *> all_buffers(nm_ctx *c)
           &c->stage_y, &c->h2d_stage, &c->nit_cnt, &c->nit_keys, &c->nit_vals, &c->nit_rkeys, &c->nit_rvals, &c->nit_rowptr,
           &c->nit_col, &c->nit_val, &c->nit_rhs, &c->row_bits, &c->row_prefix, &c->row_ids, &c->out_ids, &c->out_len, &c->glob_im,
           &c->glob_dof, &c->brk_hdr, &c->brk_bit, &c->clip_lut, &c->fe_bg_dofs, &c->fe_im_dofs, &c->fe_pairs, &c->fe_qoff,
-          &c->fe_pts, &c->fe_w, &c->fe_recoff, &c->fe_keys, &c->fe_vals};
+          &c->fe_pts, &c->fe_w, &c->fe_recoff, &c->fe_keys, &c->fe_vals, &c->solver_buf};
 }
 
 static void free_all(nm_ctx *c)

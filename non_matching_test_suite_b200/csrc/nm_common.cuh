@@ -154,6 +154,7 @@ struct nm_ctx {
 
   // ---- scratch ----
   DevBuf scan_tmp, scratch_a, scratch_b, stage_x, stage_y, h2d_stage;
+  DevBuf solver_buf;          // matrices, right-hand sides and work vectors of nm_schur_solve
   DevBuf clip_lut;            // 256-entry table of the section algorithm (nm_clip_core.cuh)
   DevBuf glob_im, glob_dof;   // global-numbered device scratch vectors of the products in local numbering
 
@@ -246,5 +247,6 @@ int nm_spmv_push_owned_run(nm_ctx *ctx, const double *x, int n_ranks, double *co
 int nm_nonempty_rows(nm_ctx *ctx, uint64_t *n_rows_out, const uint32_t **ids_dev, const uint32_t **len_dev);
 int nm_local_map(nm_ctx *ctx, int which, int to_global, const double *src, double *dst);
 int nm_wait_download_issued(nm_ctx *ctx);
+int nm_constrained_dofs(nm_ctx *ctx, uint32_t *out_dev);
 int nm_exclusive_scan_u64(nm_ctx *ctx, const uint64_t *in, uint64_t *out, uint64_t n);
 int nm_exclusive_scan_u32_to_u64(nm_ctx *ctx, const uint32_t *in, uint64_t *out, uint64_t n);

@@ -97,6 +97,12 @@ __global__ void fill_line_of(uint64_t n_c, const uint32_t *__restrict__ c_dof, i
   line_of[d] = (int32_t)i;
 }
 
+__global__ void constrained_dofs_kernel(uint64_t n_dofs, const int32_t *__restrict__ line_of, uint32_t *__restrict__ out)
+{
+  uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d < n_dofs && line_of[d] >= 0) out[line_of[d]] = (uint32_t)d;
+}
+
 // per-block partial min of lo, min positive extent, max hi  -> out[block][8]
 struct BoxStats {
   double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY}, g = INFINITY, gm = 0;
@@ -792,6 +798,15 @@ int nm_constraints_layout(nm_ctx *ctx, const uint32_t *c_dof_dev)
     NM_SYNC(ctx);
     if (h_bad) return nm_fail(ctx, NM_ERR_INVALID, "%d constrained DoF index(es) >= n_dofs", h_bad);
   }
+  return NM_OK;
+}
+
+// the constrained dof of every constraint line, in line order (device array of n_constrained entries)
+int nm_constrained_dofs(nm_ctx *ctx, uint32_t *out_dev)
+{
+  if (ctx->n_space_dofs)
+    constrained_dofs_kernel<<<nm_blocks(ctx->n_space_dofs, 256), 256, 0, NM_LS(ctx)>>>(ctx->n_space_dofs, ctx->line_of.as<int32_t>(), out_dev);
+  NM_CUDA(cudaGetLastError());
   return NM_OK;
 }
 

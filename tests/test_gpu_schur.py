@@ -1,0 +1,73 @@
+"""The Schur-complement solve of the LM drivers on the GPU (nm_schur_solve; reference 2d3d/lagrange_multiplier.cc:613-659)
+against oracle/schur_oracle.py: same operators, same GMRES, K^-1 by a sparse direct solve on the CPU.  Poisson on the
+uniform Q1 background with the immersed circle / sphere as interface, Dirichlet rows as constraint lines."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from non_matching_test_suite_b200 import coupling
+from non_matching_test_suite_b200.grids import BackgroundGrid, circle_grid, sphere_grid
+from oracle import schur_oracle as so
+from fe_helpers import uniform_background
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(d, n, im):
+    lo, hi = uniform_background(d, n)
+    nv = n + 1
+    ij = np.round((lo + 1.0) / (2.0 / n)).astype(np.int64)
+    dofs = np.zeros((lo.shape[0], 1 << d), dtype=np.int64)
+    for v in range(1 << d):
+        idx = np.zeros(lo.shape[0], dtype=np.int64)
+        for k in range(d):
+            idx += (ij[:, k] + ((v >> k) & 1)) * nv ** k
+        dofs[:, v] = idx
+    n_dofs = nv ** d
+    g = np.stack(np.meshgrid(*([np.arange(nv)] * d), indexing="ij"), -1).reshape(-1, d)[:, ::-1]     # lexicographic dof coordinates
+    on_b = ((g == 0) | (g == n)).any(1)
+    c_dof = np.nonzero(on_b)[0]
+    bg = BackgroundGrid(d, torch.from_numpy(lo), torch.from_numpy(hi), torch.from_numpy(dofs.astype(np.int32)), n_dofs,
+                        torch.zeros(lo.shape[0], dtype=torch.int32), torch.from_numpy(c_dof.astype(np.int32)),
+                        torch.zeros(len(c_dof) + 1, dtype=torch.int64), torch.empty(0, dtype=torch.int32), torch.empty(0, dtype=torch.float64))
+    x = -1.0 + g * (2.0 / n)
+    f = (2.0 / n) ** d * (1.0 + 0.3 * x[:, 0] - 0.2 * x[:, 1] ** 2)           # a load vector
+    K, f = so.constrain(so.q1_laplace_uniform(d, n), f, c_dof)
+    meas = im.measure().numpy()
+    M = sp.diags(meas).tocsr()
+    gvec = meas * (0.7 + 0.2 * im.verts.numpy()[:, 0, 0])                    # int_K g psi with g varying along the interface
+    return bg, K, M, f, gvec, c_dof
+
+
+@pytest.mark.parametrize("d,n,nim", [(2, 24, 40), (2, 48, 96), (3, 10, 3)])
+def test_schur_solve_matches_the_cpu_restatement(d, n, nim):
+    im = circle_grid(nim) if d == 2 else sphere_grid(nim)
+    bg, K, M, f, g, c_dof = _problem(d, n, im)
+    ctx = coupling.make_context(bg, im, boxes=True)
+    ctx.intersect(3, 1e-15)
+    rp, col, val = ctx.csr()
+    A = sp.csr_matrix((val.numpy(), col.numpy(), rp.numpy()), shape=(bg.n_dofs, im.n_dofs))
+    outer = (0, 1e-11, 1e-8)
+    lam_ref, u_ref, it_ref, rho_ref = so.solve(K, M, A, f, g, outer=outer)
+    u_ref[c_dof] = 0.0                                                         # distribute: homogeneous Dirichlet lines
+    csr = lambda B: (torch.from_numpy(B.indptr.astype(np.int64)), torch.from_numpy(B.indices.astype(np.int32)), torch.from_numpy(B.data.astype(np.float64)))
+    lam, u, st = ctx.schur_solve(csr(K), csr(M), torch.from_numpy(f), torch.from_numpy(g), inner=(5000, 1e-15, 1e-13), outer=outer)
+    assert st["outer_iterations"] == it_ref
+    assert np.linalg.norm(lam.numpy() - lam_ref) <= 1e-6 * np.linalg.norm(lam_ref)      # K^-1: CG to 1e-13 here, direct solve there
+    assert np.linalg.norm(u.numpy() - u_ref) <= 1e-7 * np.linalg.norm(u_ref)
+    assert abs(st["lambda_norm_sqr"] - lam_ref @ lam_ref) <= 1e-6 * (lam_ref @ lam_ref)
+    # the saddle-point equations themselves:  K u + Ct lambda = f  (free rows),  C u = g  up to the GMRES tolerance
+    free = np.ones(bg.n_dofs, dtype=bool); free[c_dof] = False
+    res1 = (K @ u.numpy() + A @ lam.numpy() - f)[free]
+    assert np.linalg.norm(res1) <= 1e-9 * np.linalg.norm(f)
+    assert np.linalg.norm(A.T @ u.numpy() - g) <= 1e-3 * np.linalg.norm(g)      # what a 1e-8 reduction of the PRECONDITIONED residual leaves
+    # the drivers' own tolerances (ReductionControl(n, 1e-11, 1e-2)) stop after a 100-fold reduction: same count
+    lam2_ref, _, it2_ref, _ = so.solve(K, M, A, f, g, outer=(0, 1e-11, 1e-2))
+    lam2, _, st2 = ctx.schur_solve(csr(K), csr(M), torch.from_numpy(f), torch.from_numpy(g), inner=(5000, 1e-15, 1e-13), outer=(0, 1e-11, 1e-2))
+    assert st2["outer_iterations"] == it2_ref and np.linalg.norm(lam2.numpy() - lam2_ref) <= 1e-6 * np.linalg.norm(lam2_ref)
+    # device-resident inputs give the same vectors
+    dev = lambda t3: tuple(t.cuda() for t in t3)
+    lam3, u3, _ = ctx.schur_solve(dev(csr(K)), dev(csr(M)), torch.from_numpy(f).cuda(), torch.from_numpy(g).cuda(), inner=(5000, 1e-15, 1e-13), outer=outer)
+    assert torch.equal(lam3.cpu(), lam) and torch.equal(u3.cpu(), u)
+    ctx.close()
