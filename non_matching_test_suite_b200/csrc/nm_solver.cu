@@ -262,7 +262,7 @@ extern "C" int nm_schur_solve(nm_ctx *ctx, const nm_schur_problem *P, double *la
   unsigned it = 0;
   double rho = 0, rho0 = 0;
   bool converged = false;
-  const unsigned max_it = P->outer_max_it ? P->outer_max_it : (unsigned)ni;
+  const unsigned max_it = P->outer_max_it ? P->outer_max_it : (unsigned)(ns < 0xffffffffULL ? ns : 0xffffffffULL);   // the 3D driver: ReductionControl(solution.size(), ...)
   std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), gamma(m + 1), y(m);
   bool first = true;
   while (!converged && it < max_it) {

@@ -20,7 +20,7 @@ def solve(K, M, A, f, g, outer=(None, 1e-11, 1e-2), basis=28):
     b = C(lu.solve(f)) - g
     n = b.shape[0]
     max_it, tol, reduce = outer
-    max_it = max_it or n
+    max_it = max_it or K.shape[0]          # the 3D driver: ReductionControl(solution.size(), ...)
     x = np.zeros(n)
     it, rho0, rho, first, done = 0, 0.0, 0.0, True, False
     while not done and it < max_it:
