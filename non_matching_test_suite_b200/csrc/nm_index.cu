@@ -573,8 +573,9 @@ template <int D, int G, int CAP>
 __global__ void __launch_bounds__(128) cand_probe_brick(BrickDev B, uint64_t n_im, const double *__restrict__ im_verts,
                                                         uint32_t *__restrict__ cnt, uint32_t *__restrict__ tmp)
 {
-  constexpr int NVI = 1 << (D - 1), CPB = 128 / G, SH = nmbrick::BrickShape<D>::SH, NSL = 2;
-  static_assert(G >= NSL * D, "one lane per (level slot, axis)");
+  constexpr int NVI = 1 << (D - 1), CPB = 128 / G, SH = nmbrick::BrickShape<D>::SH;
+  constexpr int NSL = G >= 2 * D ? 2 : 1;   // levels handled per pass: one lane per (level slot, axis) when the group has D lanes or more
+  constexpr bool SPREAD = G >= D;           // fewer lanes than axes: every lane works out all axes itself
   static_assert(CAP % 4 == 0, "rows are read four ids at a time");
   __shared__ __align__(16) uint32_t s_ids[CPB][CAP];
   __shared__ unsigned s_n[CPB];
@@ -587,31 +588,38 @@ __global__ void __launch_bounds__(128) cand_probe_brick(BrickDev B, uint64_t n_i
   for (unsigned k = l; k < (unsigned)CAP; k += G) s_ids[g][k] = 0xffffffffu;   // padding compares as "not smaller"
   // the bounding interval of the immersed cell along "my" axis
   const int ax = (int)(l % D), sl = (int)(l / D);
-  double qlo, qhi;
+  double qlo, qhi, blo[3] = {0, 0, 0}, bhi[3] = {0, 0, 0};
   {
     const double *v = im_verts + m * NVI * D + ax;
     qlo = qhi = v[0];
 #pragma unroll
     for (int q = 1; q < NVI; ++q) { const double x = v[q * D]; qlo = fmin(qlo, x); qhi = fmax(qhi, x); }
   }
+  if (!SPREAD) im_box<D, NVI>(im_verts + m * NVI * D, blo, bhi);
   uint32_t lm = B.hdr->level_mask;
   __syncwarp(gmask);
   while (lm) {
-    int lev[NSL];
+    int lev[2] = {-1, -1};
 #pragma unroll
     for (int s = 0; s < NSL; ++s) { lev[s] = lm ? __ffs(lm) - 1 : -1; lm &= lm - 1; }
     const int my_level = sl == 0 ? lev[0] : (sl == 1 ? lev[1] : -1);
     int myL = 1, myH = 0;   // empty
-    if (my_level >= 0 && !brick_axis_range(B, my_level, ax, qlo, qhi, myL, myH)) { myL = 1; myH = 0; }
-    int L[NSL][3], H[NSL][3], b0[NSL][3], nb[NSL][3], T[NSL];
+    if (SPREAD && my_level >= 0 && !brick_axis_range(B, my_level, ax, qlo, qhi, myL, myH)) { myL = 1; myH = 0; }
+    int L[2][3], H[2][3], b0[2][3], nb[2][3], T[2] = {0, 0};
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { L[s][a] = 1; H[s][a] = 0; b0[s][a] = 0; nb[s][a] = 1; }
 #pragma unroll
     for (int s = 0; s < NSL; ++s) {
       bool ok = lev[s] >= 0;
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
-        if (a < D) {
+        if (a < D && SPREAD) {
           L[s][a] = __shfl_sync(gmask, myL, gbase + s * D + a);
           H[s][a] = __shfl_sync(gmask, myH, gbase + s * D + a);
+        } else if (a < D) {
+          if (!(lev[s] >= 0 && brick_axis_range(B, lev[s], a, blo[a], bhi[a], L[s][a], H[s][a]))) { L[s][a] = 1; H[s][a] = 0; }
         } else { L[s][a] = 0; H[s][a] = 0; }
         ok &= L[s][a] <= H[s][a];
         b0[s][a] = L[s][a] >> SH;
@@ -1070,7 +1078,10 @@ int nm_candidates_run(nm_ctx *ctx)
   if (ctx->n_im == 0) { NM_TRY(nm_ensure(ctx, ctx->cand_ptr, 16)); ctx->counts.n_candidates = 0; NM_CUDA(cudaMemsetAsync(ctx->cand_ptr.p, 0, 8, ctx->stream)); return NM_OK; }
   if (ctx->index_kind == 2 && ctx->n_bg) {
     bool fell_back = false;
-    NM_TRY((ctx->spacedim == 2 ? candidates_run_bricks<2, 16, 4>(ctx, &fell_back) : candidates_run_bricks<3, 40, 8>(ctx, &fell_back)));
+#ifndef NM_CAND_G3
+#define NM_CAND_G3 2    // lanes per immersed quad in cand_probe_brick (3D); measured at sphere cycle 8: 8 lanes 2.57 ms, 4: 1.71, 2: 1.70, 1: 1.89
+#endif
+    NM_TRY((ctx->spacedim == 2 ? candidates_run_bricks<2, 16, 4>(ctx, &fell_back) : candidates_run_bricks<3, 40, NM_CAND_G3>(ctx, &fell_back)));
     if (!fell_back) return NM_OK;
   }
   return ctx->spacedim == 2 ? candidates_run_chains<2, 16>(ctx) : candidates_run_chains<3, 40>(ctx);

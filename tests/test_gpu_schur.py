@@ -40,7 +40,7 @@ def _problem(d, n, im):
     return bg, K, M, f, gvec, c_dof
 
 
-@pytest.mark.parametrize("d,n,nim", [(2, 24, 40), (2, 48, 96), (3, 10, 3)])
+@pytest.mark.parametrize("d,n,nim", [(2, 24, 40), (2, 48, 96), (3, 12, 2)])
 def test_schur_solve_matches_the_cpu_restatement(d, n, nim):
     im = circle_grid(nim) if d == 2 else sphere_grid(nim)
     bg, K, M, f, g, c_dof = _problem(d, n, im)
@@ -48,11 +48,14 @@ def test_schur_solve_matches_the_cpu_restatement(d, n, nim):
     ctx.intersect(3, 1e-15)
     rp, col, val = ctx.csr()
     A = sp.csr_matrix((val.numpy(), col.numpy(), rp.numpy()), shape=(bg.n_dofs, im.n_dofs))
-    outer = (2000, 1e-11, 1e-8)
-    lam_ref, u_ref, it_ref, rho_ref = so.solve(K, M, A, f, g, outer=outer)
+    # a 1e-8 reduction needs a basis that is not restarted: GMRES(28) on C K Ct * S stagnates (the CPU restatement does too,
+    # test_restarted_gmres_stagnation below); the drivers' own 1e-2 reduction is reached well inside the first 28 vectors
+    outer, basis = (2000, 1e-11, 1e-8), 150
+    lam_ref, u_ref, it_ref, rho_ref = so.solve(K, M, A, f, g, outer=outer, basis=basis)
+    assert it_ref < basis
     u_ref[c_dof] = 0.0                                                         # distribute: homogeneous Dirichlet lines
     csr = lambda B: (torch.from_numpy(B.indptr.astype(np.int64)), torch.from_numpy(B.indices.astype(np.int32)), torch.from_numpy(B.data.astype(np.float64)))
-    lam, u, st = ctx.schur_solve(csr(K), csr(M), torch.from_numpy(f), torch.from_numpy(g), inner=(5000, 1e-15, 1e-13), outer=outer)
+    lam, u, st = ctx.schur_solve(csr(K), csr(M), torch.from_numpy(f), torch.from_numpy(g), inner=(5000, 1e-15, 1e-13), outer=outer, gmres_basis=basis)
     assert st["outer_iterations"] == it_ref
     assert np.linalg.norm(lam.numpy() - lam_ref) <= 1e-6 * np.linalg.norm(lam_ref)      # K^-1: CG to 1e-13 here, direct solve there
     assert np.linalg.norm(u.numpy() - u_ref) <= 1e-7 * np.linalg.norm(u_ref)
@@ -61,13 +64,31 @@ def test_schur_solve_matches_the_cpu_restatement(d, n, nim):
     free = np.ones(bg.n_dofs, dtype=bool); free[c_dof] = False
     res1 = (K @ u.numpy() + A @ lam.numpy() - f)[free]
     assert np.linalg.norm(res1) <= 1e-9 * np.linalg.norm(f)
-    assert np.linalg.norm(A.T @ u.numpy() - g) <= 1e-3 * np.linalg.norm(g)      # what a 1e-8 reduction of the PRECONDITIONED residual leaves
+    assert np.linalg.norm(A.T @ u.numpy() - g) <= 1e-6 * np.linalg.norm(g)      # what a 1e-8 reduction of the PRECONDITIONED residual leaves
     # the drivers' own tolerances (ReductionControl(n, 1e-11, 1e-2)) stop after a 100-fold reduction: same count
     lam2_ref, _, it2_ref, _ = so.solve(K, M, A, f, g, outer=(2000, 1e-11, 1e-2))
     lam2, _, st2 = ctx.schur_solve(csr(K), csr(M), torch.from_numpy(f), torch.from_numpy(g), inner=(5000, 1e-15, 1e-13), outer=(2000, 1e-11, 1e-2))
     assert st2["outer_iterations"] == it2_ref and np.linalg.norm(lam2.numpy() - lam2_ref) <= 1e-6 * np.linalg.norm(lam2_ref)
     # device-resident inputs give the same vectors
     dev = lambda t3: tuple(t.cuda() for t in t3)
-    lam3, u3, _ = ctx.schur_solve(dev(csr(K)), dev(csr(M)), torch.from_numpy(f).cuda(), torch.from_numpy(g).cuda(), inner=(5000, 1e-15, 1e-13), outer=outer)
+    lam3, u3, _ = ctx.schur_solve(dev(csr(K)), dev(csr(M)), torch.from_numpy(f).cuda(), torch.from_numpy(g).cuda(), inner=(5000, 1e-15, 1e-13), outer=outer, gmres_basis=basis)
     assert torch.equal(lam3.cpu(), lam) and torch.equal(u3.cpu(), u)
+    ctx.close()
+
+
+def test_restarted_gmres_stagnation_is_reported():
+    """GMRES(28) asked for a 1e-8 reduction runs into the iteration cap -- on the CPU restatement and here, with the same
+    residual -- and the library says so (deal.II throws SolverControl::NoConvergence at the same point) instead of
+    returning a vector."""
+    im = circle_grid(40)
+    bg, K, M, f, g, c_dof = _problem(2, 24, im)
+    ctx = coupling.make_context(bg, im, boxes=True)
+    ctx.intersect(3, 1e-15)
+    rp, col, val = ctx.csr()
+    A = sp.csr_matrix((val.numpy(), col.numpy(), rp.numpy()), shape=(bg.n_dofs, im.n_dofs))
+    _, _, it_ref, rho_ref = so.solve(K, M, A, f, g, outer=(300, 1e-11, 1e-8))
+    assert it_ref == 300
+    csr = lambda B: (torch.from_numpy(B.indptr.astype(np.int64)), torch.from_numpy(B.indices.astype(np.int32)), torch.from_numpy(B.data.astype(np.float64)))
+    with pytest.raises(RuntimeError, match="did not converge in 300 iterations"):
+        ctx.schur_solve(csr(K), csr(M), torch.from_numpy(f), torch.from_numpy(g), inner=(5000, 1e-15, 1e-13), outer=(300, 1e-11, 1e-8))
     ctx.close()
