@@ -406,6 +406,26 @@ __global__ void __launch_bounds__(128) clip_local_kernel(uint64_t n_cand, const 
 #endif
 constexpr int CM_WARPS = CM_WARPS_N;    // warps per block
 constexpr int CM_CHUNKS = 8;   // chunks of 32 candidates per warp
+// Vertex pool of the clip in SHARED memory (1) or in local memory (0).  The pool is indexed by values that differ from lane
+// to lane; as local memory every such load touches one 32-byte sector per lane (ncu: 1.7 useful bytes per sector, the L1
+// pipe the busiest unit of the kernel), in shared memory with the layout [coordinate][slot][thread] the bank depends on
+// the lane only, whatever the slot.  Nine slots per thread (item_clip_polygon_v2 reuses the slots of cut-off vertices).
+#ifndef CM_SHARED_POOL
+#define CM_SHARED_POOL 0
+#endif
+#ifndef CM_JOIN
+#define CM_JOIN 0
+#endif
+#if CM_SHARED_POOL && (NM_CLIP_SLOTS != 1 || NM_CLIP_SECTION || NM_CLIP_BITS != 2)
+#error "the nine-slot shared pool needs NM_CLIP_SLOTS=1 and the plane-major box-plane clip"
+#endif
+constexpr int CM_SLOTS = 9;
+constexpr size_t CM_POOL_BYTES = CM_SHARED_POOL ? sizeof(double) * 3 * CM_SLOTS * CM_WARPS * 32 : 0;
+struct SPool {
+  double *p;   // element (k, i) of this thread at p[(k * CM_SLOTS + i) * blockDim]
+  __device__ __forceinline__ double get(int k, int i) const { return p[(k * CM_SLOTS + i) * (CM_WARPS * 32)]; }
+  __device__ __forceinline__ void set(int k, int i, double v) { p[(k * CM_SLOTS + i) * (CM_WARPS * 32)] = v; }
+};
 
 __global__ void __launch_bounds__(CM_WARPS * 32, CM_MINB) clip_moments3_kernel(
     uint64_t n_cand, const uint32_t *__restrict__ cand_im, const uint32_t *__restrict__ cand_bg, const double *__restrict__ bg_box,
@@ -415,6 +435,7 @@ __global__ void __launch_bounds__(CM_WARPS * 32, CM_MINB) clip_moments3_kernel(
 {
   __shared__ uint32_t s_ring[CM_WARPS][128];
   __shared__ uint32_t s_lut[256];   // section polygons: cyclic order of the cut box edges per corner sign pattern
+  extern __shared__ double s_pool[];
   for (unsigned i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = lut_global[i];
   __syncthreads();
   const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -475,10 +496,41 @@ __global__ void __launch_bounds__(CM_WARPS * 32, CM_MINB) clip_moments3_kernel(
       for (int i = 0; i < 7; ++i) o.m[i] = 0;
       uint32_t m = 0;
       const uint64_t cc = wstart + cl;
+#if CM_JOIN
+      // clip first, then -- with the warp converged again (lanes leave the plane loop at different trips and by two
+      // exits) -- integrate: without the explicit join the compiler may run the fan loop once per exit group
+#if CM_SHARED_POOL
+      ClippedPolyT<SPool> C;
+      C.P.p = s_pool + threadIdx.x;
+#else
+      ClippedPoly C;
+#endif
+      bool ok = false;
+      const double *box2 = bg_box;
       if (on) {
         m = cand_im[cc];
-        item_moments(bg_box + (uint64_t)cand_bg[cc] * 8, im_verts + (uint64_t)m * 12, (int)(it & 3), tol, s_lut, o);
+        box2 = bg_box + (uint64_t)cand_bg[cc] * 8;
+#if CM_SHARED_POOL
+        ok = item_clip_polygon_v2(box2, im_verts + (uint64_t)m * 12, (int)(it & 3), C);
+#else
+        ok = item_polygon(box2, im_verts + (uint64_t)m * 12, (int)(it & 3), s_lut, C);
+#endif
       }
+      __syncwarp();
+      if (ok) poly_moments(C, box2, tol, o);
+      __syncwarp();
+#else
+      if (on) {
+        m = cand_im[cc];
+#if CM_SHARED_POOL
+        ClippedPolyT<SPool> C;
+        C.P.p = s_pool + threadIdx.x;
+        item_moments_pool(bg_box + (uint64_t)cand_bg[cc] * 8, im_verts + (uint64_t)m * 12, (int)(it & 3), tol, C, o);
+#else
+        item_moments(bg_box + (uint64_t)cand_bg[cc] * 8, im_verts + (uint64_t)m * 12, (int)(it & 3), tol, s_lut, o);
+#endif
+      }
+#endif
       // combine the (adjacent, at most three) items of a candidate in ring order
       const uint32_t cl1 = __shfl_down_sync(0xffffffffu, cl, 1), cl2 = __shfl_down_sync(0xffffffffu, cl, 2);
       const uint32_t clp = __shfl_up_sync(0xffffffffu, cl, 1);
@@ -732,12 +784,17 @@ int nm_clip_run(nm_ctx *ctx)
   KernelTimer kt(ctx, NM_T_K_CLIP);
   // closed-form moments are what a rule exact to degree 3 returns: the reference's degree = 3
   // (QGaussSimplex<2>(3), exact to degree 5) qualifies; lower rules go through the quadrature kernel
-  if (d == 3 && ctx->degree == 3 && !ctx->force_quadrature_kernel)
-    clip_moments3_kernel<<<nm_blocks(nc, CM_WARPS * 32 * CM_CHUNKS), CM_WARPS * 32, 0, NM_LS(ctx)>>>(
+  if (d == 3 && ctx->degree == 3 && !ctx->force_quadrature_kernel) {
+    static bool attr_set = false;   // the pool needs more than the 48 KB a kernel gets by default
+    if (CM_POOL_BYTES && !attr_set) {
+      NM_CUDA(cudaFuncSetAttribute(clip_moments3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CM_POOL_BYTES));
+      attr_set = true;
+    }
+    clip_moments3_kernel<<<nm_blocks(nc, CM_WARPS * 32 * CM_CHUNKS), CM_WARPS * 32, CM_POOL_BYTES, NM_LS(ctx)>>>(
         nc, ctx->cand_im.as<uint32_t>(), ctx->cand_bg.as<uint32_t>(), ctx->bg_box.as<double>(), ctx->im_verts.as<double>(),
         ctx->im_split.as<uint8_t>(), ctx->im_measure.as<double>(), ctx->tol, 7u, ctx->cand_sumw.as<double>(),
         ctx->cand_local.as<double>(), ctx->cand_nq.as<uint16_t>(), ctx->cand_acc.as<uint8_t>(), cnt, ctx->clip_lut.as<uint32_t>());
-  else if (d == 3)
+  } else if (d == 3)
     clip_local_kernel<3><<<B, T, 0, NM_LS(ctx)>>>(nc, ctx->cand_im.as<uint32_t>(), ctx->cand_bg.as<uint32_t>(), ctx->bg_box.as<double>(),
                                                    ctx->im_verts.as<double>(), ctx->im_split.as<uint8_t>(), ctx->im_measure.as<double>(),
                                                    ctx->tol, ctx->cand_sumw.as<double>(), ctx->cand_local.as<double>(),

@@ -28,6 +28,25 @@
 #define NMC_FFS32(x) __builtin_ffs((int)(x))
 #endif
 
+// ---- build switches ----
+// 0: clip the triangle by the box planes (the kernel's algorithm); 1: section algorithm (measured on B200 at sphere
+// cycle 8: 22.6 ms against 14.4 ms -- kept as a cross-check of the polygon construction, tests/test_clip_core_cpu.py)
+#ifndef NM_CLIP_SECTION
+#define NM_CLIP_SECTION 0
+#endif
+// outcode layout of the box-plane clip: 1 = position-major 64-bit list (item_clip_polygon_v1), 2 = plane-major 32-bit words
+#ifndef NM_CLIP_BITS
+#define NM_CLIP_BITS 2
+#endif
+// pool slot of a new vertex, see item_clip_polygon_v2 (1 is what a nine-slot pool needs)
+#ifndef NM_CLIP_SLOTS
+#define NM_CLIP_SLOTS 0
+#endif
+// plane distances of the four edge end points: 0 = selected from the loaded coordinates, 1 = fetched by (axis, vertex) address
+#ifndef NM_CLIP_AXISLOAD
+#define NM_CLIP_AXISLOAD 0
+#endif
+
 namespace nmclip {
 
 // Separating-axis test triangle vs box [0,H] (box normals, triangle normal, 9 edge cross
@@ -45,8 +64,8 @@ NMC_UNROLL
   bool sep = false;
 NMC_UNROLL
   for (int k = 0; k < 3; ++k) {
-    const double mn = fmin(p[0][k], fmin(p[1][k], p[2][k])), mx = fmax(p[0][k], fmax(p[1][k], p[2][k]));
-    sep |= mn > h[k] || mx < -h[k];
+    // min > h or max < -h, written as comparisons: an FP64 min/max costs ~8 instructions on sm_100 (DSETP + selects)
+    sep |= (p[0][k] > h[k] && p[1][k] > h[k] && p[2][k] > h[k]) || (p[0][k] < -h[k] && p[1][k] < -h[k] && p[2][k] < -h[k]);
   }
   const double f[3][3] = {{p[1][0] - p[0][0], p[1][1] - p[0][1], p[1][2] - p[0][2]},
                           {p[2][0] - p[1][0], p[2][1] - p[1][1], p[2][2] - p[1][2]},
@@ -67,19 +86,19 @@ NMC_UNROLL
       const double a = -f[j][2], b = f[j][1];
       const double q0 = a * p[ia][1] + b * p[ia][2], q1 = a * p[ib][1] + b * p[ib][2];
       const double r = h[1] * fabs(a) + h[2] * fabs(b);
-      sep |= fmin(q0, q1) > r || fmax(q0, q1) < -r;
+      sep |= (q0 > r && q1 > r) || (q0 < -r && q1 < -r);
     }
     {  // e_y x f_j = (fz, 0, -fx)
       const double a = f[j][2], b = -f[j][0];
       const double q0 = a * p[ia][0] + b * p[ia][2], q1 = a * p[ib][0] + b * p[ib][2];
       const double r = h[0] * fabs(a) + h[2] * fabs(b);
-      sep |= fmin(q0, q1) > r || fmax(q0, q1) < -r;
+      sep |= (q0 > r && q1 > r) || (q0 < -r && q1 < -r);
     }
     {  // e_z x f_j = (-fy, fx, 0)
       const double a = -f[j][1], b = f[j][0];
       const double q0 = a * p[ia][0] + b * p[ia][1], q1 = a * p[ib][0] + b * p[ib][1];
       const double r = h[0] * fabs(a) + h[1] * fabs(b);
-      sep |= fmin(q0, q1) > r || fmax(q0, q1) < -r;
+      sep |= (q0 > r && q1 > r) || (q0 < -r && q1 < -r);
     }
   }
   }
@@ -104,6 +123,8 @@ struct ItemOut {
 // traffic except for the (at most two) edge/plane crossings.
 struct VPool {
   double c[3][16];
+  NMC_FN double get(int k, int i) const { return c[k][i]; }
+  NMC_FN void set(int k, int i, double v) { c[k][i] = v; }
 };
 
 NMC_FN unsigned outcode(double x, double y, double z, const double *H)
@@ -115,14 +136,15 @@ NMC_FN unsigned outcode(double x, double y, double z, const double *H)
 // Clipped polygon of one (cell, triangle) item: pool vertices in cell-local coordinates, index list,
 // vertex count, unit normal of the parent triangle.  Shared by the moment kernel and the quadrature
 // emission so that both see exactly the same fan triangles (same count of points per pair).
-struct ClippedPoly {
-  VPool P;
+template <class Pool> struct ClippedPolyT {
+  Pool P;
   unsigned long long poly;
   int n;
   double nx, ny, nz;
 };
+typedef ClippedPolyT<VPool> ClippedPoly;
 
-NMC_FN bool item_clip_polygon(const double *box, const double *quad, int t, ClippedPoly &C)
+NMC_FN bool item_clip_polygon_v1(const double *box, const double *quad, int t, ClippedPoly &C)
 {
   VPool &P = C.P;
   const double lo[3] = {box[0], box[1], box[2]};
@@ -227,24 +249,171 @@ NMC_UNROLL
   return true;
 }
 
+// The same clip with the outcodes kept PLANE-major in two 32-bit words: word A holds planes 0..2 (x >= 0, x <= Hx,
+// y >= 0), word B planes 3..5 (y <= Hy, z >= 0, z <= Hz); plane q of a word owns bits [10 q, 10 q + n), bit i = polygon
+// position i is inside that plane (n <= 9).  The inside mask of the plane being applied is then one bit field: run start
+// and run length are single ffs instructions on 32-bit values, and the three fields of a word are rotated / spliced
+// together (multiplication by 0x00100401 replicates a mask into the fields).  Same planes in the same order, same run,
+// same vertices as item_clip_polygon_v1 -- the two are compared candidate by candidate on the host
+// (tests/test_clip_core_cpu.py).
+NMC_FN void outcode2(double x, double y, double z, const double *H, unsigned &a, unsigned &b)
+{
+  a = (x >= 0.0 ? 1u : 0u) | (x <= H[0] ? 1u << 10 : 0u) | (y >= 0.0 ? 1u << 20 : 0u);
+  b = (y <= H[1] ? 1u : 0u) | (z >= 0.0 ? 1u << 10 : 0u) | (z <= H[2] ? 1u << 20 : 0u);
+}
+
+template <class Pool> NMC_FN bool item_clip_polygon_v2(const double *box, const double *quad, int t, ClippedPolyT<Pool> &C)
+{
+  Pool &P = C.P;
+  constexpr unsigned REP = 0x00100401u;   // bit 0 of the three fields of a word
+  const double lo[3] = {box[0], box[1], box[2]};
+  const double H[3] = {box[4] - lo[0], box[5] - lo[1], box[6] - lo[2]};
+  const int iv[3] = {t == 0 ? 1 : 0, t <= 1 ? 2 : 1, t <= 2 ? 3 : 2};
+  unsigned A = 0, B = 0;
+NMC_UNROLL
+  for (int v = 0; v < 3; ++v) {
+    const double x = quad[iv[v] * 3 + 0] - lo[0], y = quad[iv[v] * 3 + 1] - lo[1], z = quad[iv[v] * 3 + 2] - lo[2];
+    P.set(0, v, x); P.set(1, v, y); P.set(2, v, z);
+    unsigned a, b;
+    outcode2(x, y, z, H, a, b);
+    A |= a << v; B |= b << v;
+  }
+  double nx, ny, nz;
+  {
+    const double e1[3] = {P.get(0, 1) - P.get(0, 0), P.get(1, 1) - P.get(1, 0), P.get(2, 1) - P.get(2, 0)};
+    const double e2[3] = {P.get(0, 2) - P.get(0, 0), P.get(1, 2) - P.get(1, 0), P.get(2, 2) - P.get(2, 0)};
+    nx = e1[1] * e2[2] - e1[2] * e2[1]; ny = e1[2] * e2[0] - e1[0] * e2[2]; nz = e1[0] * e2[1] - e1[1] * e2[0];
+    const double n2 = nx * nx + ny * ny + nz * nz;
+    if (!(n2 > 0.0)) return false;
+    const double inv = NMC_RSQRT(n2);
+    nx *= inv; ny *= inv; nz *= inv;
+  }
+  unsigned long long poly = 0x210ULL;  // pool indices, 4 bits per polygon position
+  int n = 3, nv = 3;
+#pragma unroll 1
+  while (true) {
+    const unsigned full = (1u << n) - 1u, fullr = full * REP;
+    const unsigned tA = A ^ fullr, tB = B ^ fullr;   // set bits = positions outside a plane
+    if ((tA | tB) == 0u) break;
+    const bool inA = tA != 0u;
+    const int bpos = NMC_FFS32(inA ? tA : tB) - 1;
+    const int q = (bpos * 205) >> 11;                 // bpos / 10: field of the lowest plane that cuts
+    const int p = q + (inA ? 0 : 3);
+    const unsigned f = ((inA ? A : B) >> (10 * q)) & full;   // inside mask of plane p over the n positions
+    if (f == 0u) return false;
+    const int axis = p >> 1;
+    const double sgn = (p & 1) ? -1.0 : 1.0, bound = (p & 1) ? H[axis] : 0.0;
+    const unsigned prev = ((f << 1) | (f >> (n - 1))) & full;   // position i: vertex i-1 inside
+    const int s = NMC_FFS32(f & ~prev) - 1;                      // run start
+    const unsigned rot = ((f >> s) | (f << (n - s))) & full;
+    const int len = NMC_FFS32(~rot) - 1;                         // run length (the plane cuts: rot != full)
+    // all lists rotated so that the run comes first
+    const unsigned long long pr = (poly >> (4 * s)) | (poly << (4 * (n - s)));
+    const unsigned lowm = ((1u << (n - s)) - 1u) * REP;
+    const unsigned Ar = ((A >> s) & lowm) | ((A << (n - s)) & (fullr ^ lowm));
+    const unsigned Br = ((B >> s) & lowm) | ((B << (n - s)) & (fullr ^ lowm));
+    // planes already applied count as inside for a new vertex, and so does the opposite plane of this axis (the vertex
+    // is put ON plane p: coordinate 0 <= H resp. H >= 0)
+    const int pf = p | 1;
+    const unsigned fm = REP & ((2u << (10 * (pf < 3 ? pf : pf - 3))) - 1u);
+    const unsigned forcedA = pf < 3 ? fm : REP, forcedB = pf < 3 ? 0u : fm;
+    const unsigned keep = ((1u << len) - 1u) * REP;
+    unsigned long long np = 0;
+    unsigned nA = 0, nB = 0;
+    int m = 0;
+    const int ve_p = (int)((poly >> (4 * (s == 0 ? n - 1 : s - 1))) & 15u), ve_q = (int)(pr & 15u);        // outside -> first inside
+    const int vl_p = (int)((pr >> (4 * (len - 1))) & 15u), vl_q = (int)((pr >> (4 * len)) & 15u);           // last inside -> outside
+    double ep[3], eq[3], lp[3], lq[3];
+NMC_UNROLL
+    for (int k = 0; k < 3; ++k) { ep[k] = P.get(k, ve_p); eq[k] = P.get(k, ve_q); lp[k] = P.get(k, vl_p); lq[k] = P.get(k, vl_q); }
+#if NM_CLIP_AXISLOAD
+    // the coordinate the plane acts on, fetched by its (axis, vertex) address instead of selected from the three loaded ones
+    const double e_dp = sgn * (P.get(axis, ve_p) - bound), e_dq = sgn * (P.get(axis, ve_q) - bound);
+    const double l_dp = sgn * (P.get(axis, vl_p) - bound), l_dq = sgn * (P.get(axis, vl_q) - bound);
+#else
+    const double e_dp = sgn * ((axis == 0 ? ep[0] : axis == 1 ? ep[1] : ep[2]) - bound);
+    const double e_dq = sgn * ((axis == 0 ? eq[0] : axis == 1 ? eq[1] : eq[2]) - bound);
+    const double l_dp = sgn * ((axis == 0 ? lp[0] : axis == 1 ? lp[1] : lp[2]) - bound);
+    const double l_dq = sgn * ((axis == 0 ? lq[0] : axis == 1 ? lq[1] : lq[2]) - bound);
+#endif
+    // Pool slot of a new vertex (NM_CLIP_SLOTS).  0: the next unused one (3 + 2 per plane <= 15).  1: the slot of a vertex
+    // this plane cuts off -- the entering vertex takes that of the outside end of its edge (ve_p), the leaving one that of
+    // vl_q, or a fresh slot when both edges leave from the SAME outside vertex (exactly one vertex cut off: the only case
+    // in which the polygon grows; at most six such steps: nine slots).  2: slots 3 + 2p, 4 + 2p of plane p.
+    const bool entered = e_dq > 0.0;
+    if (entered) {  // entering edge
+      const double tt = e_dp * NMC_RCP(e_dp - e_dq);
+      double x[3];
+NMC_UNROLL
+      for (int k = 0; k < 3; ++k) x[k] = ep[k] + tt * (eq[k] - ep[k]);
+NMC_UNROLL
+#if NM_CLIP_SLOTS == 1
+      const int slot = ve_p;
+#elif NM_CLIP_SLOTS == 2
+      const int slot = 3 + 2 * p;
+#else
+      const int slot = nv++;
+#endif
+      for (int k = 0; k < 3; ++k) P.set(k, slot, x[k]);
+      P.set(axis, slot, bound);                        // on the plane by construction
+      unsigned a, b;
+      outcode2(x[0], x[1], x[2], H, a, b);
+      np = (unsigned long long)slot;
+      nA = a | forcedA; nB = b | forcedB;
+      m = 1;
+    }
+    np |= (pr & ((1ULL << (4 * len)) - 1ULL)) << (4 * m);
+    nA |= (Ar & keep) << m;
+    nB |= (Br & keep) << m;
+    m += len;
+    if (l_dp > 0.0) {  // leaving edge
+      const double tt = l_dp * NMC_RCP(l_dp - l_dq);
+      double x[3];
+NMC_UNROLL
+      for (int k = 0; k < 3; ++k) x[k] = lp[k] + tt * (lq[k] - lp[k]);
+NMC_UNROLL
+#if NM_CLIP_SLOTS == 1
+      const int slot = (vl_q != ve_p || !entered) ? vl_q : nv++;
+#elif NM_CLIP_SLOTS == 2
+      const int slot = 4 + 2 * p;
+#else
+      const int slot = nv++;
+#endif
+      for (int k = 0; k < 3; ++k) P.set(k, slot, x[k]);
+      P.set(axis, slot, bound);
+      unsigned a, b;
+      outcode2(x[0], x[1], x[2], H, a, b);
+      np |= (unsigned long long)slot << (4 * m);
+      nA |= (a | forcedA) << m; nB |= (b | forcedB) << m;
+      ++m;
+    }
+    poly = np;
+    A = nA; B = nB;
+    n = m;
+    if (n < 3) return false;
+  }
+  C.poly = poly; C.n = n; C.nx = nx; C.ny = ny; C.nz = nz;
+  return true;
+}
+
 // integrals of 1, u, v, w, uv, uw, vw, uvw over the polygon (fan from its first vertex), the reference's thresholds
 // applied per fan triangle
-NMC_FN void poly_moments(const ClippedPoly &C, const double *box, double tol, ItemOut &o)
+template <class Pool> NMC_FN void poly_moments(const ClippedPolyT<Pool> &C, const double *box, double tol, ItemOut &o)
 {
-  const VPool &P = C.P;
+  const Pool &P = C.P;
   const unsigned long long poly = C.poly;
   const int n = C.n;
   const double nx = C.nx, ny = C.ny, nz = C.nz;
   const double H[3] = {box[4] - box[0], box[5] - box[1], box[6] - box[2]};
   const double ih[3] = {NMC_RCP(H[0]), NMC_RCP(H[1]), NMC_RCP(H[2])};
   const int v0 = (int)(poly & 15u), v1 = (int)((poly >> 4) & 15u);
-  const double ax = P.c[0][v0], ay = P.c[1][v0], az = P.c[2][v0];
+  const double ax = P.get(0, v0), ay = P.get(1, v0), az = P.get(2, v0);
   const double f0 = ax * ih[0], g0 = ay * ih[1], h0 = az * ih[2];
-  double px = P.c[0][v1], py = P.c[1][v1], pz = P.c[2][v1];
+  double px = P.get(0, v1), py = P.get(1, v1), pz = P.get(2, v1);
   double f1 = px * ih[0], g1 = py * ih[1], h1 = pz * ih[2];
   for (int j = 2; j < n; ++j) {
     const int vj = (int)((poly >> (4 * j)) & 15u);
-    const double qx = P.c[0][vj], qy = P.c[1][vj], qz = P.c[2][vj];
+    const double qx = P.get(0, vj), qy = P.get(1, vj), qz = P.get(2, vj);
     const double f2 = qx * ih[0], g2 = qy * ih[1], h2 = qz * ih[2];
     const double e1x = px - ax, e1y = py - ay, e1z = pz - az, e2x = qx - ax, e2y = qy - ay, e2z = qz - az;
     const double J = fabs((e1y * e2z - e1z * e2y) * nx + (e1z * e2x - e1x * e2z) * ny + (e1x * e2y - e1y * e2x) * nz);
@@ -472,12 +641,6 @@ NMC_UNROLL
 // ---------------------------------------------------------------------------------------
 // what the kernels call: one switch for the gate, the polygon and (through them) the quadrature emission
 // ---------------------------------------------------------------------------------------
-// 0: clip the triangle by the box planes (the kernel's algorithm); 1: section algorithm (measured on B200 at sphere
-// cycle 8: 22.6 ms against 14.4 ms -- kept as a cross-check of the polygon construction, tests/test_clip_core_cpu.py)
-#ifndef NM_CLIP_SECTION
-#define NM_CLIP_SECTION 0
-#endif
-
 // stage-1 gate: can triangle `tri` (cell-local coordinates) meet the box [0, H] at all?  Conservative.
 NMC_FN bool tri_gate(const double (*tri)[3], const double *H)
 {
@@ -494,7 +657,11 @@ NMC_FN bool item_polygon(const double *box, const double *quad, int t, const uin
   return item_section_polygon(box, quad, t, lut, C);
 #else
   (void)lut;
-  return item_clip_polygon(box, quad, t, C);
+#if NM_CLIP_BITS == 2
+  return item_clip_polygon_v2(box, quad, t, C);
+#else
+  return item_clip_polygon_v1(box, quad, t, C);
+#endif
 #endif
 }
 
@@ -502,6 +669,13 @@ NMC_FN void item_moments(const double *box, const double *quad, int t, double to
 {
   ClippedPoly C;
   if (!item_polygon(box, quad, t, lut, C)) return;
+  poly_moments(C, box, tol, o);
+}
+
+// the same with the vertex pool supplied by the caller (shared memory in clip_moments3_kernel); plane-major clip only
+template <class Pool> NMC_FN void item_moments_pool(const double *box, const double *quad, int t, double tol, ClippedPolyT<Pool> &C, ItemOut &o)
+{
+  if (!item_clip_polygon_v2(box, quad, t, C)) return;
   poly_moments(C, box, tol, o);
 }
 

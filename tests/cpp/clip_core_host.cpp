@@ -10,6 +10,15 @@
 
 using namespace nmclip;
 
+#if HOST_POOL9
+// the nine-slot pool of the GPU kernel (shared memory there), with a bound check: item_clip_polygon_v2 must never ask for more
+struct Pool9 {
+  double c[3][9];
+  double get(int k, int i) const { if (i < 0 || i >= 9) { std::fprintf(stderr, "pool slot %d read\n", i); std::abort(); } return c[k][i]; }
+  void set(int k, int i, double v) { if (i < 0 || i >= 9) { std::fprintf(stderr, "pool slot %d written\n", i); std::abort(); } c[k][i] = v; }
+};
+#endif
+
 int main(int argc, char **argv)
 {
   if (argc < 3) { std::fprintf(stderr, "usage: clip_core_host <in.bin> <out.bin>\n"); return 2; }
@@ -42,7 +51,12 @@ int main(int argc, char **argv)
       ItemOut o;
       o.area2 = 0; o.nfan = 0; o.dropped = 0;
       for (int k = 0; k < 7; ++k) o.m[k] = 0;
+#if HOST_POOL9
+      ClippedPolyT<Pool9> C9;
+      item_moments_pool(box, quad, t, tol, C9, o);
+#else
       item_moments(box, quad, t, tol, lut, o);
+#endif
       tot[0] += o.area2;
       for (int k = 0; k < 7; ++k) tot[k + 1] += o.m[k];
       nfan += o.nfan; dropped += o.dropped;

@@ -15,11 +15,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "tests", "cpp", "_build")
 
 
-def _exe(section):
+VARIANTS = {"section": ["-DNM_CLIP_SECTION=1"], "clip_v1": ["-DNM_CLIP_SECTION=0", "-DNM_CLIP_BITS=1"],
+            "clip_v2": ["-DNM_CLIP_SECTION=0", "-DNM_CLIP_BITS=2"],
+            # what clip_moments3_kernel is built with: plane-major outcodes, vertex pool of nine slots (bound-checked here)
+            "clip_v2_pool9": ["-DNM_CLIP_SECTION=0", "-DNM_CLIP_BITS=2", "-DNM_CLIP_SLOTS=1", "-DHOST_POOL9=1"],
+            "clip_v2_planeslots": ["-DNM_CLIP_SECTION=0", "-DNM_CLIP_BITS=2", "-DNM_CLIP_SLOTS=2"]}
+
+
+def _exe(variant):
     os.makedirs(BUILD, exist_ok=True)
-    exe = os.path.join(BUILD, "clip_core_host_section" if section else "clip_core_host_clip")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-DNM_CLIP_SECTION=%d" % (1 if section else 0), "-o", exe,
-                           os.path.join(ROOT, "tests", "cpp", "clip_core_host.cpp")])
+    exe = os.path.join(BUILD, "clip_core_host_" + variant)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off"] + VARIANTS[variant] +
+                          ["-o", exe, os.path.join(ROOT, "tests", "cpp", "clip_core_host.cpp")])
     return exe
 
 
@@ -44,7 +51,7 @@ def _problem(bg, im, c_oracle):
     return (bg.lo.numpy()[b], bg.hi.numpy()[b], im.verts.numpy()[m], codes[m]), sumw, local, dropped
 
 
-@pytest.mark.parametrize("section", [True, False])
+@pytest.mark.parametrize("section", list(VARIANTS))
 @pytest.mark.parametrize("cycle", [0, 2, 3])
 def test_core_matches_oracle_on_sphere(tmp_path, c_oracle, section, cycle):
     bg, im = make_config("sphere", cycle, band_only=cycle > 2)
@@ -62,7 +69,7 @@ def test_core_matches_oracle_on_sphere(tmp_path, c_oracle, section, cycle):
     assert (nfan[acc] >= 1).all()
 
 
-@pytest.mark.parametrize("section", [True, False])
+@pytest.mark.parametrize("section", list(VARIANTS))
 def test_core_on_degenerate_and_random_pairs(tmp_path, c_oracle, section):
     """Faces shared by two cells (counted for both), quads through grid vertices, flat quads on grid planes, plus random
     boxes against random, slightly warped quads of all relative sizes."""
@@ -83,3 +90,18 @@ def test_core_on_degenerate_and_random_pairs(tmp_path, c_oracle, section):
         assert ((got_w > 1e-15) == (sumw > 1e-15))[np.abs(sumw) > 1e-11].all()
         scale = np.abs(sumw).max()
         assert np.abs(got_l[acc] - local[acc]).max() <= 1e-12 * scale + 1e-12 * max(1, dropped)
+
+
+def test_both_outcode_layouts_give_identical_bits(tmp_path, c_oracle):
+    """item_clip_polygon_v2 (plane-major 32-bit outcode words, slots of cut-off vertices reused: nine suffice) is the same algorithm as v1 (position-major 64-bit list):
+    same planes, same runs, same vertices -- every output double identical."""
+    from degenerate_cases import case_3d
+    from test_gpu_parity import _random_problem
+    problems = [make_config("sphere", 3, band_only=True), case_3d(), _random_problem(3, 2000, 60, seed=5), _random_problem(3, 300, 300, seed=6)]
+    for bg, im in problems:
+        args, _, _, _ = _problem(bg, im, c_oracle)
+        r1 = _run(_exe("clip_v1"), tmp_path, *args)
+        for variant in ("clip_v2", "clip_v2_pool9", "clip_v2_planeslots"):
+            r2 = _run(_exe(variant), tmp_path, *args)
+            for a, b in zip(r1, r2):
+                assert np.array_equal(a, b)
