@@ -410,6 +410,14 @@ constexpr int CM_CHUNKS = 8;   // chunks of 32 candidates per warp
 // to lane; as local memory every such load touches one 32-byte sector per lane (ncu: 1.7 useful bytes per sector, the L1
 // pipe the busiest unit of the kernel), in shared memory with the layout [coordinate][slot][thread] the bank depends on
 // the lane only, whatever the slot.  Nine slots per thread (item_clip_polygon_v2 reuses the slots of cut-off vertices).
+// Measured on B200, sphere cycle 8 (1.06e8 candidates), kernel time:
+//   local pool, slots by counter (default)                         13.28 ms
+//   local pool, slots of cut-off vertices reused (NM_CLIP_SLOTS=1) 14.83 ms     slots by plane (=2) 14.74 ms
+//   shared pool (needs NM_CLIP_SLOTS=1)                            14.69 ms     the compiler runs the fan loop per exit group of
+//                                                                               the plane loop (7 of 32 lanes active, +21 % instructions)
+//   shared pool + CM_JOIN=1 (explicit __syncwarp before the fan)   13.80 ms     long-scoreboard stalls 3.9 -> 3.4 per issue, but
+//                                                                               +11 % instructions; local pool + CM_JOIN=1: 14.23 ms
+// The kernel is bound by issue slots and dependent-instruction latency, not by the L1 pipe: the default stays.
 #ifndef CM_SHARED_POOL
 #define CM_SHARED_POOL 0
 #endif
