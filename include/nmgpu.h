@@ -124,7 +124,11 @@ int nm_set_immersed(nm_ctx *ctx, int dim, int spacedim, uint64_t n_cells, const 
  * (include/coupling_utilities.h:508-515, src/coupling_utilities.cc:22-69) for <2,1,2> and
  * <3,2,3>: candidate pairs, exact intersection, quadrature of `degree` (the reference passes
  * it on as QGaussSimplex's n_points_1D: intersections.cc:695,776,812), acceptance by
- * sum(weights) > tol.  degree == 0 -> NM_ERR_INVALID (the reference AssertThrows). */
+ * sum(weights) > tol.  degree == 0 -> NM_ERR_INVALID (the reference AssertThrows).
+ * Subdivision: the reference integrates over CGAL's pieces (tetrahedra x triangles), this library over the fan of the
+ * clipped polygon.  With a rule that is exact for the integrand (degree >= 3 in 3D, >= 2 in 2D for Q1 x P0) both give the
+ * same matrix up to rounding.  With a LOWER rule the pair set and the pattern are still the reference's, but the values
+ * are that rule on a different subdivision: they differ from a CGAL run by the quadrature error of either side. */
 int nm_intersect(nm_ctx *ctx, unsigned degree, double tol, nm_counts *counts);
 
 /* flags[b] = 1 iff the closed bounding box of background cell b meets the bounding box of some
@@ -336,7 +340,8 @@ enum {
   NM_INFO_STORED_ROWS = 2,  /* rows the stored orientation holds internally                                    */
   NM_INFO_NNZ = 3,
   NM_INFO_INDEX_KIND = 4,   /* candidate index: 1 = per-cell chains (any boxes), 2 = brick bitmasks (grid-aligned tree) */
-  NM_INFO_HOST_SYNCS = 5    /* host synchronisations with the stream since nm_create                           */
+  NM_INFO_HOST_SYNCS = 5,   /* host synchronisations with the stream since nm_create                           */
+  NM_INFO_MERGE_SLOTS = 6   /* hash slots per immersed cell of the single-pass merge that built the matrix     */
 };
 int nm_get_info(nm_ctx *ctx, int key, uint64_t *value);
 

@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("NMGPU_LIB") or os.path.join(_HERE, "libnmgpu.so")   #
 
 NM_HOST, NM_DEVICE, NM_HOST_ASYNC = 0, 1, 2
 NM_LOCAL_IMMERSED, NM_LOCAL_ROWS = 0, 1
-INFO = {"merge_path": 0, "compact_rows": 1, "stored_rows": 2, "nnz": 3, "index_kind": 4, "host_syncs": 5}
+INFO = {"merge_path": 0, "compact_rows": 1, "stored_rows": 2, "nnz": 3, "index_kind": 4, "host_syncs": 5, "merge_slots": 6}
 STATUS = {0: "NM_OK", 1: "NM_ERR_INVALID", 2: "NM_ERR_CUDA", 3: "NM_ERR_UNSUPPORTED", 4: "NM_ERR_STATE", 5: "NM_ERR_NOMEM"}
 PHASES = ["upload", "index", "candidates", "split", "clip", "merge", "transpose", "spmv", "spmv_t", "download",
           "k_clip", "k_cand_count", "k_cand_fill", "k_merge"]

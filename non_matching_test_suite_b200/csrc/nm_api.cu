@@ -788,6 +788,7 @@ int nm_get_info(nm_ctx *ctx, int key, uint64_t *value)
     case NM_INFO_NNZ: *value = ctx->matrix_valid ? ctx->nnz : 0; return NM_OK;
     case NM_INFO_INDEX_KIND: *value = (uint64_t)ctx->index_kind; return NM_OK;
     case NM_INFO_HOST_SYNCS: *value = ctx->n_syncs; return NM_OK;
+    case NM_INFO_MERGE_SLOTS: *value = ctx->merge_path == 0 ? (uint64_t)ctx->merge_slots : 0; return NM_OK;
     default: return nm_fail(ctx, NM_ERR_INVALID, "unknown info key %d", key);
   }
 }

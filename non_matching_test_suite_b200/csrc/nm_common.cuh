@@ -138,6 +138,8 @@ struct nm_ctx {
   bool out_rows_valid = false;
   bool matrix_valid = false;
   int merge_path = -1;   // which merge built the matrix: 0 = single-pass hash merge, 1 = general two-pass path
+  int merge_slots = 0;   // hash slots per cell of the single-pass merge that built it (128 or 256 in 3D, 64 in 2D)
+  bool merge_large_table = false;   // the small table overflowed on these grids: start with the large one
 
   // ---- interface-penalisation terms (nm_nitsche.cu): square matrix on the space dofs + right-hand side ----
   DevBuf nit_cnt, nit_keys, nit_vals, nit_rkeys, nit_rvals;

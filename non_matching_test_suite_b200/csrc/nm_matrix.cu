@@ -856,44 +856,60 @@ static int matrix_build_fast(nm_ctx *ctx, bool *done)
   if (n_im == 0 || ctx->force_general_merge) return NM_OK;
   PhaseTimer tm(ctx, NM_T_MERGE);
   // distinct dofs <= contributions; +25% and the chunk tails for constraint expansion
-  constexpr int GROUP = NL == 8 ? 32 : 8, SLOTS = NL == 8 ? 256 : 64, NG = 256 / GROUP;
+  constexpr int GROUP = NL == 8 ? 32 : 8, NG = 256 / GROUP;
   // consecutive immersed cells per group: FAST_ROWS when the grid is large, fewer on small grids so that every SM still
   // gets a few blocks (a 2 K-cell curve on one block of 64-row groups took as long as a 500 K-cell one)
   uint64_t rpg = (n_im + (uint64_t)NG * 4 * ctx->sm_count - 1) / ((uint64_t)NG * 4 * ctx->sm_count);
   rpg = rpg < 1 ? 1 : (rpg > FAST_ROWS ? FAST_ROWS : rpg);
   const unsigned chunk = (unsigned)(rpg * (NL == 8 ? 16 : 4));   // entries a group takes from the cursor at a time
   const uint64_t blocks = (n_im + NG * rpg - 1) / (NG * rpg);
+  // distinct dofs <= contributions; +25% and the chunk tails for constraint expansion
   const uint64_t capacity = ctx->counts.n_accepted * NL + ctx->counts.n_accepted * NL / 4 + blocks * NG * chunk + 1024;
   NM_TRY(nm_ensure(ctx, ctx->c_rowstart, (n_im + 2) * sizeof(uint64_t)));
   NM_TRY(nm_ensure(ctx, ctx->c_rowlen, (n_im + 1) * sizeof(uint32_t)));
   NM_TRY(nm_ensure(ctx, ctx->c_col, (capacity + 1) * sizeof(uint32_t)));
   NM_TRY(nm_ensure(ctx, ctx->c_val, (capacity + 1) * sizeof(double)));
-  uint32_t *dof_marks = nullptr;   // per-dof counts, or the bitmap of touched dofs in compact-row mode
-  if (ctx->compact_rows) {
-    const uint64_t nw = n_rows / 32 + 2;
-    NM_TRY(nm_ensure(ctx, ctx->row_bits, nw * sizeof(uint32_t)));
-    NM_CUDA(cudaMemsetAsync(ctx->row_bits.p, 0, nw * sizeof(uint32_t), ctx->stream));
-    dof_marks = ctx->row_bits.as<uint32_t>();
-  } else {
-    NM_TRY(nm_ensure(ctx, ctx->a_cursor, (n_rows + 2) * sizeof(uint32_t) * 2));
-    NM_CUDA(cudaMemsetAsync(ctx->a_cursor.p, 0, (n_rows + 2) * sizeof(uint32_t) * 2, ctx->stream));
-    dof_marks = ctx->a_cursor.as<uint32_t>();
-  }
   NM_TRY(nm_ensure(ctx, ctx->counters, 64 * sizeof(uint64_t)));
   unsigned long long *cursor = ctx->counters.as<unsigned long long>() + 20;
   unsigned *problem = ctx->counters.as<unsigned>() + 44;
-  NM_CUDA(cudaMemsetAsync(cursor, 0, 32, ctx->stream));   // bytes 160..191: the chunk cursor AND the problem flag (byte 176)
-  KernelTimer km(ctx, NM_T_K_MERGE);
-  merge_rows_fast<NL, GROUP, SLOTS><<<(unsigned)blocks, 256, 0, NM_LS(ctx)>>>(
-      n_im, ctx->cand_ptr.as<uint64_t>(), ctx->cand_bg.as<uint32_t>(), ctx->cand_acc.as<uint8_t>(), ctx->cand_local.as<double>(),
-      ctx->bg_dofs.as<uint32_t>(), ctx->line_of.as<int32_t>(), ctx->c_ptr.as<uint64_t>(), ctx->c_master.as<uint32_t>(),
-      ctx->c_weight.as<double>(), ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(),
-      ctx->c_val.as<double>(), capacity, cursor, problem, dof_marks, ctx->compact_rows ? 1 : 0, (uint32_t)n_rows, (unsigned)rpg, chunk);
-  km.stop();
-  NM_CUDA(cudaGetLastError());
+  // Hash slots per cell: 3/4 of them is the number of distinct dofs the fast path accepts.  The small table (half the
+  // clearing and compaction work: 7.6 -> 7.1 ms at sphere cycle 8) is tried first when the cells average few accepted
+  // pairs; a cell that overflows it raises the flag and the large table redoes the merge before the general path would.
+  const bool small_first = NL == 8 && !ctx->merge_large_table && ctx->counts.n_accepted <= 12 * n_im;
   unsigned h_problem = 0;
-  NM_CUDA(cudaMemcpyAsync(&h_problem, problem, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  NM_SYNC(ctx);
+  for (int attempt = small_first ? 0 : 1; attempt < 2; ++attempt) {
+    uint32_t *dof_marks = nullptr;   // per-dof counts, or the bitmap of touched dofs in compact-row mode
+    if (ctx->compact_rows) {
+      const uint64_t nw = n_rows / 32 + 2;
+      NM_TRY(nm_ensure(ctx, ctx->row_bits, nw * sizeof(uint32_t)));
+      NM_CUDA(cudaMemsetAsync(ctx->row_bits.p, 0, nw * sizeof(uint32_t), ctx->stream));
+      dof_marks = ctx->row_bits.as<uint32_t>();
+    } else {
+      NM_TRY(nm_ensure(ctx, ctx->a_cursor, (n_rows + 2) * sizeof(uint32_t) * 2));
+      NM_CUDA(cudaMemsetAsync(ctx->a_cursor.p, 0, (n_rows + 2) * sizeof(uint32_t) * 2, ctx->stream));
+      dof_marks = ctx->a_cursor.as<uint32_t>();
+    }
+    NM_CUDA(cudaMemsetAsync(cursor, 0, 32, ctx->stream));   // bytes 160..191: the chunk cursor AND the problem flag (byte 176)
+    KernelTimer km(ctx, NM_T_K_MERGE);
+    auto launch = [&](auto kernel) {
+      kernel<<<(unsigned)blocks, 256, 0, NM_LS(ctx)>>>(
+          n_im, ctx->cand_ptr.as<uint64_t>(), ctx->cand_bg.as<uint32_t>(), ctx->cand_acc.as<uint8_t>(), ctx->cand_local.as<double>(),
+          ctx->bg_dofs.as<uint32_t>(), ctx->line_of.as<int32_t>(), ctx->c_ptr.as<uint64_t>(), ctx->c_master.as<uint32_t>(),
+          ctx->c_weight.as<double>(), ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(),
+          ctx->c_val.as<double>(), capacity, cursor, problem, dof_marks, ctx->compact_rows ? 1 : 0, (uint32_t)n_rows, (unsigned)rpg, chunk);
+    };
+    bool launched = false;
+    if constexpr (NL == 8) {
+      if (attempt == 0) { launch(merge_rows_fast<NL, GROUP, 128>); ctx->merge_slots = 128; launched = true; }
+    }
+    if (!launched) { launch(merge_rows_fast<NL, GROUP, (NL == 8 ? 256 : 64)>); ctx->merge_slots = NL == 8 ? 256 : 64; }
+    km.stop();
+    NM_CUDA(cudaGetLastError());
+    NM_CUDA(cudaMemcpyAsync(&h_problem, problem, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    NM_SYNC(ctx);
+    if (attempt == 0 && h_problem == 1u) { ctx->merge_large_table = true; continue; }   // only "too many distinct dofs": the large table may take it
+    break;
+  }
   tm.stop();
   if (h_problem & 4u) return nm_fail(ctx, NM_ERR_INVALID, "background DoF table holds indices >= n_dofs (%llu)", (unsigned long long)n_rows);
   if (h_problem) return NM_OK;  // the general path redoes everything

@@ -219,3 +219,49 @@ def test_assembly_is_bitwise_reproducible(name, cycle):
     for r in runs[1:]:
         for a, b in zip(runs[0], r):
             assert torch.equal(a, b)
+
+
+def test_small_merge_table_overflow_falls_back_to_the_large_one(c_oracle):
+    """The single-pass merge tries 128 hash slots per immersed cell first (96 distinct dofs) when the cells average few
+    accepted pairs.  One large quad among many small ones (7 x 7 background cells: 128 distinct dofs) overflows it: the
+    256-slot table must redo the merge -- not the general two-pass path -- and the matrix must be the oracle's; the
+    context then remembers to start with the large table."""
+    from fe_helpers import uniform_background
+    from non_matching_test_suite_b200.grids import BackgroundGrid, ImmersedGrid
+    n = 16
+    lo, hi = uniform_background(3, n)
+    h = 2.0 / n
+    nv = n + 1
+    ij = np.round((lo + 1.0) / h).astype(np.int64)
+    dofs = np.zeros((lo.shape[0], 8), dtype=np.int64)
+    for v in range(8):
+        dofs[:, v] = sum((ij[:, k] + ((v >> k) & 1)) * nv ** k for k in range(3))
+    e32, e64 = torch.empty(0, dtype=torch.int32), torch.empty(0, dtype=torch.float64)
+    bg = BackgroundGrid(3, torch.from_numpy(lo), torch.from_numpy(hi), torch.from_numpy(dofs.astype(np.int32)), nv ** 3,
+                        torch.zeros(lo.shape[0], dtype=torch.int32), e32, torch.zeros(1, dtype=torch.int64), e32, e64)
+    quads = []
+    z = -1.0 + 5.37 * h                                                          # inside one layer of cells
+    a, b = -1.0 + 2.21 * h, -1.0 + 8.83 * h                                      # spans 7 x 7 cells
+    quads.append([[a, a, z], [b, a, z], [a, b, z], [b, b, z + 0.01 * h]])
+    rng = np.random.default_rng(3)
+    for _ in range(300):                                                        # small quads: one or two pairs each
+        c = -0.9 + 1.8 * rng.random(3)
+        s = 0.3 * h
+        quads.append([c, c + [s, 0, 0.1 * s], c + [0, s, 0], c + [s, s, 0.05 * s]])
+    verts = torch.tensor(np.array(quads, dtype=np.float64))
+    im = ImmersedGrid(2, 3, verts.contiguous(), torch.arange(len(quads), dtype=torch.int32)[:, None], len(quads))
+    ref = c_oracle.assemble(bg, im)
+    ctx = coupling.make_context(bg, im, boxes=True)
+    c = ctx.intersect(3, 1e-15)
+    assert c["n_accepted"] <= 12 * im.n_cells
+    rp, col, val = ctx.csr()
+    assert ctx.info("merge_path") == 0 and ctx.info("merge_slots") == 256
+    assert np.array_equal(col.numpy().astype(np.uint32), ref["col"]) and np.array_equal(rp.numpy().astype(np.uint64), ref["rowptr"])
+    assert np.linalg.norm(val.numpy() - ref["val"]) <= 1e-12 * np.linalg.norm(ref["val"])
+    # the usual grids stay on the small table
+    bg2, im2 = make_config("sphere", 3)
+    ctx2 = coupling.make_context(bg2, im2, boxes=True)
+    ctx2.intersect(3, 1e-15)
+    ctx2.build_sparsity()
+    assert ctx2.info("merge_path") == 0 and ctx2.info("merge_slots") == 128
+    ctx.close(); ctx2.close()
