@@ -524,8 +524,7 @@ def run_problem(args, torch, dist, _lib, ctx, P, rank, world, local, dev, peak, 
     # ---- end to end: host buffers in, matrix + vectors out ----------------------------------------
     e2e_res = None
     if e2e:
-        e2e_res = run_e2e(args, torch, dist, _lib, ctx, P, rank, world, dev, timed, get_fused, sharded_op, owned, tot_acc,
-                          max(1, min(steps, 4)))
+        e2e_res = run_e2e(args, torch, dist, _lib, ctx, P, rank, world, dev, timed, get_fused, sharded_op, owned, tot_acc, max(1, steps))
 
     return dict(value=value, ms=ms, counts=counts, phases=phases, launches=launches, syncs=syncs, clocks=clocks, roofline=roofline, spmv=spmv,
                 e2e=e2e_res, tot_acc=tot_acc, tot_cand=tot_cand, tot_nnz=tot_nnz, info=P.info, gen_seconds=P.gen_seconds,
@@ -621,7 +620,8 @@ def run_e2e(args, torch, dist, _lib, ctx, P, rank, world, dev, timed, get_fused,
         nr = ctx.n_rows_local()
         t0 = mark("n_rows", t0)
         if world == 1:
-            ctx.spmv_local(xh, transpose=False, out=yh[:nr])                      # Ct.vmult, touched rows only
+            # Ct.vmult (touched rows only) and C.Tvmult in one call: the upload of u overlaps the download of Ct*x
+            ctx.spmv_local_pair(xh, uh[:nr], out_ct=yh[:nr], out_c=zh)
             y_bytes = nr * 8
         else:
             ctx.local_to_global(_lib.NM_LOCAL_IMMERSED, xh, xg)                   # this shard's lambda entries
@@ -635,7 +635,8 @@ def run_e2e(args, torch, dist, _lib, ctx, P, rank, world, dev, timed, get_fused,
                 ctx.global_to_local(_lib.NM_LOCAL_ROWS, yy, yh[:nr])              # replicated result: read the touched rows
                 y_bytes = nr * 8
         t0 = mark("ct_vmult", t0)
-        ctx.spmv_local(uh[:nr], transpose=True, out=zh)                           # C.Tvmult, this shard's cells
+        if world > 1:
+            ctx.spmv_local(uh[:nr], transpose=True, out=zh)                       # C.Tvmult, this shard's cells
         t0 = mark("c_tvmult", t0)
         buf = csr_bufs[state["k"] % len(csr_bufs)]
         state["k"] += 1
@@ -663,7 +664,8 @@ def run_e2e(args, torch, dist, _lib, ctx, P, rank, world, dev, timed, get_fused,
     if glob:
         api += " + nm_spmv x2 (global-length host vectors) + nm_get_csr (global row pointers)"
     else:
-        api += (" + nm_spmv_local x2 (host vectors in local numbering: one entry per immersed cell / per touched row)" if world == 1 else
+        api += (" + nm_spmv_local_pair (both products, host vectors in local numbering: one entry per immersed cell / per touched row; the two "
+                    "directions of the link used at once)" if world == 1 else
                 " + nm_local_to_global + fused Ct.vmult (%s) + nm_spmv_local (C.Tvmult)" % args.ct_vmult) + \
                " + nm_get_csr_compact (rows with entries only" + (", asynchronous: the read-back of step k runs under the uploads and kernels of step k+1; "
                                                                  "the last one is waited for inside the timed region)" if pipelined else ")")

@@ -200,6 +200,11 @@ enum { NM_LOCAL_IMMERSED = 0, NM_LOCAL_ROWS = 1 };
 int nm_spmv_local(nm_ctx *ctx, int transpose, const double *x, double *y, int where);
 /* Scatter a local vector into a global-numbered DEVICE vector (entries outside the local set are left
  * untouched) / gather the local entries out of one.  `where_local` places the local vector. */
+/* Both products of one Schur-complement iteration in local numbering, y_ct = Ct x_ct and y_c = C x_c (sizes as in
+ * nm_spmv_local: x_ct, y_c one entry per immersed cell of this context; y_ct, x_c one per stored row).  With NM_HOST the
+ * four transfers run on separate copy streams, so that the upload of x_c overlaps the download of y_ct (pinned buffers;
+ * the two directions of the link are used at once); with NM_DEVICE it is the two nm_spmv_local calls. */
+int nm_spmv_local_pair(nm_ctx *ctx, const double *x_ct, double *y_ct, const double *x_c, double *y_c, int where);
 int nm_local_to_global(nm_ctx *ctx, int which, const double *local, int where_local, double *global_dev);
 int nm_global_to_local(nm_ctx *ctx, int which, const double *global_dev, double *local, int where_local);
 

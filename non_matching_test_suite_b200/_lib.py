@@ -27,7 +27,7 @@ PHASES = ["upload", "index", "candidates", "split", "clip", "merge", "transpose"
 SYMBOLS = ["nm_version", "nm_create", "nm_destroy", "nm_last_error", "nm_set_background", "nm_set_background_boxes",
            "nm_set_background_dofs", "nm_set_immersed_dofs", "nm_set_immersed", "nm_flag_overlapped_background", "nm_intersect", "nm_get_candidates", "nm_get_pairs", "nm_get_quadrature",
            "nm_get_split_codes", "nm_build_sparsity", "nm_assemble", "nm_assemble_from_quadrature", "nm_assemble_host", "nm_assemble_nitsche", "nm_get_nitsche", "nm_get_csr",
-           "nm_get_csr_compact", "nm_sync_downloads", "nm_spmv", "nm_spmv_local", "nm_local_to_global", "nm_global_to_local",
+           "nm_get_csr_compact", "nm_sync_downloads", "nm_spmv", "nm_spmv_local", "nm_spmv_local_pair", "nm_local_to_global", "nm_global_to_local",
            "nm_spmv_push", "nm_spmv_push_owned", "nm_set_finite_elements", "nm_assemble_fe", "nm_schur_solve", "nm_get_info", "nm_measure_fp64_peak", "nm_get_timings", "nm_get_launch_count", "nm_device_bytes", "nm_get_stream"]
 
 
@@ -109,6 +109,7 @@ def load():
     L.nm_get_csr_compact.argtypes = [P, C.POINTER(U64), P, P, P, P, I]
     L.nm_sync_downloads.argtypes = [P]
     L.nm_spmv_local.argtypes = [P, I, P, P, I]
+    L.nm_spmv_local_pair.argtypes = [P, P, P, P, P, I]
     L.nm_local_to_global.argtypes = [P, I, P, I, P]
     L.nm_global_to_local.argtypes = [P, I, P, P, I]
     L.nm_set_finite_elements.argtypes = [P, C.POINTER(FeDesc), P, U64, U64, P, P, P, P, C.POINTER(FeDesc), P, U64, I]
@@ -413,6 +414,17 @@ class Context:
             out = torch.empty(ny, dtype=torch.float64, device=x.device)
         self._chk(self.L.nm_spmv_local(self.h, int(transpose), _ptr(x)[0], _ptr(out)[0], _where(x, out)))
         return out
+
+    def spmv_local_pair(self, x_ct, x_c, out_ct=None, out_c=None):
+        """Both products of one Schur iteration in local numbering (nm_spmv_local_pair): returns (Ct x_ct [rows], C x_c [cells]);
+        with pinned host vectors the upload of x_c overlaps the download of the first result."""
+        n_cells = self.n_im * getattr(self, "fe_dofs_per_cell", (0, 1))[1]
+        if out_ct is None:
+            out_ct = torch.empty(self.n_rows_local(), dtype=torch.float64, device=x_ct.device)
+        if out_c is None:
+            out_c = torch.empty(n_cells, dtype=torch.float64, device=x_ct.device)
+        self._chk(self.L.nm_spmv_local_pair(self.h, _ptr(x_ct)[0], _ptr(out_ct)[0], _ptr(x_c)[0], _ptr(out_c)[0], _where(x_ct, out_ct, x_c, out_c)))
+        return out_ct, out_c
 
     def local_to_global(self, which: int, local, global_dev: torch.Tensor):
         assert global_dev.is_cuda

@@ -69,7 +69,7 @@ static std::vector<DevBuf *> all_buffers(nm_ctx *c)
           &c->im_measure, &c->idx_next, &c->idx_extra_bg, &c->idx_hash, &c->idx_tmp, &c->cand_ptr, &c->cand_tmp, &c->cand_im, &c->cand_bg,
           &c->cand_sumw, &c->cand_local, &c->cand_nq, &c->cand_acc, &c->counters, &c->c_rowstart, &c->c_rowlen, &c->c_col, &c->c_val,
           &c->a_rowptr, &c->a_rowptr32, &c->a_col, &c->a_val, &c->a_cursor, &c->scan_tmp, &c->scratch_a, &c->scratch_b, &c->stage_x,
-          &c->stage_y, &c->h2d_stage, &c->nit_cnt, &c->nit_keys, &c->nit_vals, &c->nit_rkeys, &c->nit_rvals, &c->nit_rowptr,
+          &c->stage_y, &c->stage_x2, &c->stage_y2, &c->h2d_stage, &c->nit_cnt, &c->nit_keys, &c->nit_vals, &c->nit_rkeys, &c->nit_rvals, &c->nit_rowptr,
           &c->nit_col, &c->nit_val, &c->nit_rhs, &c->row_bits, &c->row_prefix, &c->row_ids, &c->out_ids, &c->out_len, &c->glob_im,
           &c->glob_dof, &c->brk_hdr, &c->brk_bit, &c->clip_lut, &c->fe_bg_dofs, &c->fe_im_dofs, &c->fe_pairs, &c->fe_qoff,
           &c->fe_pts, &c->fe_w, &c->fe_recoff, &c->fe_keys, &c->fe_vals, &c->solver_buf};
@@ -941,6 +941,62 @@ int nm_spmv_local(nm_ctx *ctx, int transpose, const double *x, double *y, int wh
     NM_TRY(nm_local_map(ctx, NM_LOCAL_ROWS, 0, yg, yd));
   }
   if (where == NM_HOST) NM_TRY(nm_download(ctx, y, yd, ny * 8, NM_HOST));
+  NM_SYNC(ctx);
+  return NM_OK;
+}
+
+int nm_spmv_local_pair(nm_ctx *ctx, const double *x_ct, double *y_ct, const double *x_c, double *y_c, int where)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  if (!x_ct || !y_ct || !x_c || !y_c) return nm_fail(ctx, NM_ERR_INVALID, "null vector");
+  if (where != NM_HOST) {   // device vectors: nothing to overlap
+    NM_TRY(nm_spmv_local(ctx, 0, x_ct, y_ct, where));
+    return nm_spmv_local(ctx, 1, x_c, y_c, where);
+  }
+  NM_TRY(ensure_matrix(ctx));
+  uint64_t n_rows = 0;
+  NM_TRY(nm_nonempty_rows(ctx, &n_rows, nullptr, nullptr));
+  const uint64_t n_cells = ctx->n_crows;
+  NM_TRY(nm_sync_downloads(ctx));   // an asynchronous matrix read-back shares the download stream
+  NM_TRY(ensure_down_stream(ctx));
+  if (!ctx->copy_stream) {
+    NM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t &e : ctx->ev_copy) NM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  NM_TRY(nm_ensure(ctx, ctx->glob_im, (ctx->n_im_dofs + 1) * 8));
+  NM_TRY(nm_ensure(ctx, ctx->glob_dof, (ctx->n_space_dofs + 1) * 8));
+  NM_TRY(nm_ensure(ctx, ctx->stage_x, (n_cells + 1) * 8));
+  NM_TRY(nm_ensure(ctx, ctx->stage_y, (n_rows + 1) * 8));
+  NM_TRY(nm_ensure(ctx, ctx->stage_x2, (n_rows + 1) * 8));
+  NM_TRY(nm_ensure(ctx, ctx->stage_y2, (n_cells + 1) * 8));
+  NM_SYNC(ctx);   // earlier work of this context may still use the staging buffers
+  cudaStream_t cs = ctx->copy_stream, ds = ctx->down_stream;
+  // both inputs go up at once; the large one (x_c: one entry per stored row) travels while the first result comes down
+  if (n_cells) NM_CUDA(cudaMemcpyAsync(ctx->stage_x.p, x_ct, n_cells * 8, cudaMemcpyHostToDevice, cs));
+  NM_CUDA(cudaEventRecord(ctx->ev_copy[0], cs));
+  if (n_rows) NM_CUDA(cudaMemcpyAsync(ctx->stage_x2.p, x_c, n_rows * 8, cudaMemcpyHostToDevice, cs));
+  NM_CUDA(cudaEventRecord(ctx->ev_copy[1], cs));
+  // y_ct = Ct x_ct
+  NM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[0], 0));
+  NM_TRY(nm_local_map(ctx, NM_LOCAL_IMMERSED, 1, ctx->stage_x.as<double>(), ctx->glob_im.as<double>()));
+  if (ctx->compact_rows) {
+    NM_TRY(nm_spmv_run(ctx, 0, ctx->glob_im.as<double>(), ctx->stage_y.as<double>(), NM_SPMV_LOCAL_OUT));
+  } else {
+    NM_TRY(nm_spmv_run(ctx, 0, ctx->glob_im.as<double>(), ctx->glob_dof.as<double>()));
+    NM_TRY(nm_local_map(ctx, NM_LOCAL_ROWS, 0, ctx->glob_dof.as<double>(), ctx->stage_y.as<double>()));
+  }
+  NM_CUDA(cudaEventRecord(ctx->ev_down_ready, ctx->stream));
+  NM_CUDA(cudaStreamWaitEvent(ds, ctx->ev_down_ready, 0));
+  if (n_rows) NM_CUDA(cudaMemcpyAsync(y_ct, ctx->stage_y.p, n_rows * 8, cudaMemcpyDeviceToHost, ds));
+  // y_c = C x_c  (glob_dof is free again: same stream, after the map above)
+  NM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[1], 0));
+  NM_TRY(nm_local_map(ctx, NM_LOCAL_ROWS, 1, ctx->stage_x2.as<double>(), ctx->glob_dof.as<double>()));
+  NM_TRY(nm_spmv_run(ctx, 1, ctx->glob_dof.as<double>(), ctx->stage_y2.as<double>(), NM_SPMV_LOCAL_OUT));
+  NM_CUDA(cudaEventRecord(ctx->ev_down_done, ctx->stream));
+  NM_CUDA(cudaStreamWaitEvent(ds, ctx->ev_down_done, 0));
+  if (n_cells) NM_CUDA(cudaMemcpyAsync(y_c, ctx->stage_y2.p, n_cells * 8, cudaMemcpyDeviceToHost, ds));
+  NM_CUDA(cudaStreamSynchronize(ds));
   NM_SYNC(ctx);
   return NM_OK;
 }

@@ -155,7 +155,7 @@ struct nm_ctx {
   DevBuf fe_pairs, fe_qoff, fe_pts, fe_w, fe_recoff, fe_keys, fe_vals;
 
   // ---- scratch ----
-  DevBuf scan_tmp, scratch_a, scratch_b, stage_x, stage_y, h2d_stage;
+  DevBuf scan_tmp, scratch_a, scratch_b, stage_x, stage_y, stage_x2, stage_y2, h2d_stage;
   DevBuf solver_buf;          // matrices, right-hand sides and work vectors of nm_schur_solve
   DevBuf clip_lut;            // 256-entry table of the section algorithm (nm_clip_core.cuh)
   DevBuf glob_im, glob_dof;   // global-numbered device scratch vectors of the products in local numbering

@@ -265,3 +265,29 @@ def test_small_merge_table_overflow_falls_back_to_the_large_one(c_oracle):
     ctx2.build_sparsity()
     assert ctx2.info("merge_path") == 0 and ctx2.info("merge_slots") == 128
     ctx.close(); ctx2.close()
+
+
+@pytest.mark.parametrize("name,cycle,compact", [("sphere", 2, False), ("sphere", 3, True), ("disk", 3, False)])
+def test_both_products_in_one_call(monkeypatch, name, cycle, compact):
+    """nm_spmv_local_pair = the two nm_spmv_local calls, bit for bit, from pinned host vectors (overlapped transfers) and
+    from device vectors; also right after an asynchronous matrix read-back, which shares its download stream."""
+    if compact:
+        monkeypatch.setenv("NMGPU_COMPACT_ROWS", "1")
+    bg, im = make_config(name, cycle)
+    ctx = coupling.make_context(bg, im, boxes=True)
+    ctx.intersect(3, 1e-15)
+    ctx.build_sparsity()
+    nr = ctx.n_rows_local()
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(im.n_cells, dtype=torch.float64, generator=g) - 0.5).pin_memory()
+    u = (torch.rand(nr, dtype=torch.float64, generator=g) - 0.5).pin_memory()
+    y_ref, z_ref = ctx.spmv_local(x, transpose=False), ctx.spmv_local(u, transpose=True)
+    bufs = (torch.empty(nr, dtype=torch.int32).pin_memory(), torch.empty(nr, dtype=torch.int32).pin_memory(),
+            torch.empty(ctx.nnz, dtype=torch.int32).pin_memory(), torch.empty(ctx.nnz, dtype=torch.float64).pin_memory())
+    ctx.csr_compact(out=bufs, asynchronous=True)
+    y, z = ctx.spmv_local_pair(x, u, out_ct=torch.empty(nr, dtype=torch.float64).pin_memory(), out_c=torch.empty(im.n_cells, dtype=torch.float64).pin_memory())
+    assert torch.equal(y, y_ref) and torch.equal(z, z_ref)
+    yd, zd = ctx.spmv_local_pair(x.cuda(), u.cuda())
+    assert torch.equal(yd.cpu(), y_ref) and torch.equal(zd.cpu(), z_ref)
+    ctx.sync_downloads()
+    ctx.close()
