@@ -215,8 +215,10 @@ def run_reference(args):
 
 def workload_config(config, cycle, n_gpus, full_background=False):
     """Identical for the native and the reference arm of one (config, N)."""
-    return {"workload": "%s, synthetic refinement cycle %d, %s background with hanging-node constraints" % (
-                NAMES[config], cycle, "full" if full_background else "band-only"),
+    return {"workload": "%s, synthetic refinement cycle %d, %s" % (
+                NAMES[config], cycle, "full background with hanging-node and Dirichlet constraint lines" if full_background else
+                "band-only background (the finest-level cells near the interface: as in the full grid at this refinement, no "
+                "constraint line touches a cut cell; lines are exercised by the parity tests and the full-background sub-config)"),
             "sharding": "immersed-cell ranges, %d shard(s)" % n_gpus, "degree": 3, "tol": 1e-15,
             "l2_policy": "inputs and intermediates are larger than L2 (no flush needed)"}
 
