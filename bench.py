@@ -387,11 +387,12 @@ def run_problem(args, torch, dist, _lib, ctx, P, rank, world, local, dev, peak, 
     def assemble_device(inp):
         if "verts" in inp:   # all 2^d vertices of every background cell, as mapping.get_vertices() returns them
             ctx.set_background(d, verts=inp["verts"], dofs=inp["dofs"], n_dofs=bg.n_dofs, c_dof=inp["c_dof"], c_ptr=inp["c_ptr"],
-                               c_master=inp["c_master"], c_weight=inp["c_weight"])
+                               c_master=inp["c_master"], c_weight=inp["c_weight"], inplace=True)
         else:                # lo/hi corners: what include/coupling_utilities.h sends for Cartesian background cells
             ctx.set_background(d, lo=inp["lo"], hi=inp["hi"], dofs=inp["dofs"], n_dofs=bg.n_dofs, c_dof=inp["c_dof"], c_ptr=inp["c_ptr"],
-                               c_master=inp["c_master"], c_weight=inp["c_weight"])
-        ctx.set_immersed(im.dim, im.spacedim, inp["im_verts"], inp["im_dofs"], im.n_dofs)
+                               c_master=inp["c_master"], c_weight=inp["c_weight"], inplace=True)
+        # NM_DEVICE_INPLACE: the inputs are resident in HBM; the DoF tables and the immersed vertices are read where they are
+        ctx.set_immersed(im.dim, im.spacedim, inp["im_verts"], inp["im_dofs"], im.n_dofs, inplace=True)
         counts = ctx.intersect(3, 1e-15)
         ctx.build_sparsity()
         ctx.assemble()

@@ -43,7 +43,11 @@ typedef enum {
 } nm_status;
 
 enum { NM_HOST = 0, NM_DEVICE = 1,
-       NM_HOST_ASYNC = 2 /* nm_get_csr_compact only: pinned host buffers, copies complete at nm_sync_downloads() */ };
+       NM_HOST_ASYNC = 2,     /* nm_get_csr_compact only: pinned host buffers, copies complete at nm_sync_downloads() */
+       NM_DEVICE_INPLACE = 3  /* nm_set_background*, nm_set_background_dofs, nm_set_immersed, nm_set_immersed_dofs only: device
+                               * arrays; the DoF tables and the immersed vertices are READ WHERE THEY ARE instead of being copied
+                               * into the context.  They must stay valid and unchanged until the same input is set again or the
+                               * context is destroyed; the library never writes to them.  Everything else behaves as NM_DEVICE. */ };
 
 /* Counters of one nm_intersect() call. */
 typedef struct {

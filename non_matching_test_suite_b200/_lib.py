@@ -16,7 +16,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NMGPU_LIB") or os.path.join(_HERE, "libnmgpu.so")   # NMGPU_LIB: another build of the same library (kernel experiments)
 
-NM_HOST, NM_DEVICE, NM_HOST_ASYNC = 0, 1, 2
+NM_HOST, NM_DEVICE, NM_HOST_ASYNC, NM_DEVICE_INPLACE = 0, 1, 2, 3
 NM_LOCAL_IMMERSED, NM_LOCAL_ROWS = 0, 1
 INFO = {"merge_path": 0, "compact_rows": 1, "stored_rows": 2, "nnz": 3, "index_kind": 4, "host_syncs": 5, "merge_slots": 6}
 STATUS = {0: "NM_OK", 1: "NM_ERR_INVALID", 2: "NM_ERR_CUDA", 3: "NM_ERR_UNSUPPORTED", 4: "NM_ERR_STATE", 5: "NM_ERR_NOMEM"}
@@ -180,12 +180,21 @@ class Context:
             raise NmError(rc, self.L.nm_last_error(self.h).decode())
 
     # ---- inputs -------------------------------------------------------------------------
+    def _inplace(self, w, inplace, *keep):
+        """NM_DEVICE_INPLACE for device arrays when asked for: the library reads the DoF tables / immersed vertices where
+        they are, so the tensors are kept alive here until the input is set again."""
+        if inplace and w == NM_DEVICE:
+            self._borrowed = getattr(self, "_borrowed", {})
+            self._borrowed[keep[0]] = keep[1:]
+            return NM_DEVICE_INPLACE
+        return w
+
     def set_background(self, spacedim, verts=None, lo=None, hi=None, dofs=None, n_dofs=0, c_dof=None, c_ptr=None,
-                       c_master=None, c_weight=None):
+                       c_master=None, c_weight=None, inplace=False):
         """Either verts [n, 2^d, d] (deal.II order) or boxes lo/hi [n, d]; dofs [n, 2^d] uint32/int32;
         constraint lines as CSR over ascending c_dof (c_ptr uint64/int64)."""
         n_c = 0 if c_dof is None else int(c_dof.shape[0])
-        w = _where(verts, lo, hi, dofs, c_dof, c_ptr, c_master, c_weight)
+        w = self._inplace(_where(verts, lo, hi, dofs, c_dof, c_ptr, c_master, c_weight), inplace, "bg_dofs", dofs)
         n = int((verts if verts is not None else lo).shape[0])
         if verts is not None:
             rc = self.L.nm_set_background(self.h, spacedim, n, _ptr(verts)[0], _ptr(dofs)[0], n_dofs, n_c, _ptr(c_dof)[0],
@@ -196,19 +205,19 @@ class Context:
         self._chk(rc)
         self.spacedim, self.n_space_dofs = spacedim, n_dofs
 
-    def set_background_dofs(self, dofs, n_dofs, c_dof=None, c_ptr=None, c_master=None, c_weight=None):
+    def set_background_dofs(self, dofs, n_dofs, c_dof=None, c_ptr=None, c_master=None, c_weight=None, inplace=False):
         n_c = 0 if c_dof is None else int(c_dof.shape[0])
-        w = _where(dofs, c_dof, c_ptr, c_master, c_weight)
+        w = self._inplace(_where(dofs, c_dof, c_ptr, c_master, c_weight), inplace, "bg_dofs", dofs)
         self._chk(self.L.nm_set_background_dofs(self.h, _ptr(dofs)[0], n_dofs, n_c, _ptr(c_dof)[0], _ptr(c_ptr)[0],
                                                 _ptr(c_master)[0], _ptr(c_weight)[0], w))
         self.n_space_dofs = n_dofs
 
-    def set_immersed_dofs(self, dofs, n_dofs, dofs_per_cell=1):
-        self._chk(self.L.nm_set_immersed_dofs(self.h, _ptr(dofs)[0], dofs_per_cell, n_dofs, _where(dofs)))
+    def set_immersed_dofs(self, dofs, n_dofs, dofs_per_cell=1, inplace=False):
+        self._chk(self.L.nm_set_immersed_dofs(self.h, _ptr(dofs)[0], dofs_per_cell, n_dofs, self._inplace(_where(dofs), inplace, "im_dofs", dofs)))
         self.n_im_dofs = n_dofs
 
-    def set_immersed(self, dim, spacedim, verts, dofs, n_dofs, dofs_per_cell=1):
-        w = _where(verts, dofs)
+    def set_immersed(self, dim, spacedim, verts, dofs, n_dofs, dofs_per_cell=1, inplace=False):
+        w = self._inplace(_where(verts, dofs), inplace, "immersed", verts, dofs)
         self._chk(self.L.nm_set_immersed(self.h, dim, spacedim, int(verts.shape[0]), _ptr(verts)[0], _ptr(dofs)[0],
                                          dofs_per_cell, n_dofs, w))
         self.n_im_dofs = n_dofs

@@ -27,6 +27,7 @@ int nm_fail(nm_ctx *c, int code, const char *fmt, ...)
 
 int nm_ensure(nm_ctx *ctx, DevBuf &b, size_t bytes)
 {
+  if (b.borrowed) { b.p = nullptr; b.cap = 0; b.borrowed = false; }   // the caller's array goes back to the caller
   if (bytes <= b.cap && b.p) return NM_OK;
   if (b.p) {
     // contents are never needed across a growth
@@ -47,6 +48,21 @@ int nm_ensure(nm_ctx *ctx, DevBuf &b, size_t bytes)
   return NM_OK;
 }
 
+// where == NM_DEVICE_INPLACE: the context reads the caller's device array where it is (no copy); the array must stay
+// valid and unchanged until the input is set again or the context is destroyed
+static int adopt(nm_ctx *ctx, DevBuf &b, const void *src, size_t bytes)
+{
+  if (bytes == 0 || !src) return nm_ensure(ctx, b, bytes);
+  if (b.p && !b.borrowed) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(b.p);
+  }
+  b.p = const_cast<void *>(src);
+  b.cap = bytes;
+  b.borrowed = true;
+  return NM_OK;
+}
+
 int nm_upload(nm_ctx *ctx, DevBuf &b, const void *src, size_t bytes, int where)
 {
   NM_TRY(nm_ensure(ctx, b, bytes));
@@ -54,6 +70,12 @@ int nm_upload(nm_ctx *ctx, DevBuf &b, const void *src, size_t bytes, int where)
   if (!src) return nm_fail(ctx, NM_ERR_INVALID, "null input pointer");
   NM_CUDA(cudaMemcpyAsync(b.p, src, bytes, where == NM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
   return NM_OK;
+}
+
+// the large read-only inputs (DoF tables, immersed vertices): copied, or used where they are
+static int upload_or_adopt(nm_ctx *ctx, DevBuf &b, const void *src, size_t bytes, int where, bool inplace)
+{
+  return inplace ? adopt(ctx, b, src, bytes) : nm_upload(ctx, b, src, bytes, where);
 }
 
 int nm_download(nm_ctx *ctx, void *dst, const void *src, size_t bytes, int where)
@@ -78,16 +100,17 @@ static std::vector<DevBuf *> all_buffers(nm_ctx *c)
 static void free_all(nm_ctx *c)
 {
   for (DevBuf *b : all_buffers(c)) {
-    if (b->p) cudaFree(b->p);
+    if (b->p && !b->borrowed) cudaFree(b->p);
     b->p = nullptr;
     b->cap = 0;
+    b->borrowed = false;
   }
 }
 
 static uint64_t held_bytes(nm_ctx *c)
 {
   uint64_t s = 0;
-  for (DevBuf *b : all_buffers(c)) s += b->cap;
+  for (DevBuf *b : all_buffers(c)) s += b->borrowed ? 0 : b->cap;
   return s;
 }
 
@@ -186,6 +209,8 @@ static int set_background_common(nm_ctx *ctx, int spacedim, uint64_t n_cells, bo
   if (spacedim != 2 && spacedim != 3) return nm_fail(ctx, NM_ERR_INVALID, "spacedim must be 2 or 3 (got %d)", spacedim);
   if (n_cells >= 0xffffffffULL || n_dofs >= 0xffffffffULL) return nm_fail(ctx, NM_ERR_UNSUPPORTED, "cell / DoF counts must fit 32 bits");
   if (n_constrained && (!c_dof || !c_ptr)) return nm_fail(ctx, NM_ERR_INVALID, "null constraint arrays");
+  const bool inplace = where == NM_DEVICE_INPLACE;
+  if (inplace) where = NM_DEVICE;
   ctx->bg_set = ctx->index_valid = ctx->intersect_valid = ctx->matrix_valid = false;
   ctx->dofs_checked = false;
   ctx->fe_general = false;
@@ -216,7 +241,7 @@ static int set_background_common(nm_ctx *ctx, int spacedim, uint64_t n_cells, bo
   }
   // dofs + constraint lines (dofs may follow later through nm_set_background_dofs)
   ctx->bg_dofs_set = dofs != nullptr || n_cells == 0;
-  if (dofs) NM_TRY(nm_upload(ctx, ctx->bg_dofs, dofs, n_cells * NV * sizeof(uint32_t), where));
+  if (dofs) NM_TRY(upload_or_adopt(ctx, ctx->bg_dofs, dofs, n_cells * NV * sizeof(uint32_t), where, inplace));
   uint64_t n_masters = 0;
   if (n_constrained) {
     if (where == NM_HOST) n_masters = c_ptr[n_constrained];
@@ -278,8 +303,10 @@ int nm_set_background_dofs(nm_ctx *ctx, const uint32_t *dofs, uint64_t n_dofs, u
   ctx->matrix_valid = false;  // intersection results stay valid: they do not depend on the numbering
   ctx->dofs_checked = false;
   ctx->fe_general = false;
+  const bool inplace = where == NM_DEVICE_INPLACE;
+  if (inplace) where = NM_DEVICE;
   PhaseTimer tm(ctx, NM_T_UPLOAD, true);
-  NM_TRY(nm_upload(ctx, ctx->bg_dofs, dofs, ctx->n_bg * (1u << ctx->spacedim) * sizeof(uint32_t), where));
+  NM_TRY(upload_or_adopt(ctx, ctx->bg_dofs, dofs, ctx->n_bg * (1u << ctx->spacedim) * sizeof(uint32_t), where, inplace));
   NM_TRY(set_constraints(ctx, n_dofs, n_constrained, c_dof, c_ptr, c_master, c_weight, where));
   tm.stop();
   ctx->bg_dofs_set = true;
@@ -298,7 +325,7 @@ int nm_set_immersed_dofs(nm_ctx *ctx, const uint32_t *dofs, uint32_t dofs_per_ce
   ctx->matrix_valid = false;
   ctx->dofs_checked = false;
   ctx->n_im_dofs = n_dofs;
-  NM_TRY(nm_upload(ctx, ctx->im_dofs, dofs, ctx->n_im * sizeof(uint32_t), where));
+  NM_TRY(upload_or_adopt(ctx, ctx->im_dofs, dofs, ctx->n_im * sizeof(uint32_t), where == NM_DEVICE_INPLACE ? NM_DEVICE : where, where == NM_DEVICE_INPLACE));
   ctx->im_dofs_set = true;
   return NM_OK;
 }
@@ -333,6 +360,8 @@ int nm_set_immersed(nm_ctx *ctx, int dim, int spacedim, uint64_t n_cells, const 
     return nm_fail(ctx, NM_ERR_UNSUPPORTED, "immersed space must be FE_DGQ(0) (1 DoF per cell); got %u DoFs per cell", dofs_per_cell);
   if (n_cells >= 0xffffffffULL || n_dofs >= 0xffffffffULL) return nm_fail(ctx, NM_ERR_UNSUPPORTED, "cell / DoF counts must fit 32 bits");
   if (n_cells && !verts) return nm_fail(ctx, NM_ERR_INVALID, "null immersed arrays");
+  const bool inplace = where == NM_DEVICE_INPLACE;
+  if (inplace) where = NM_DEVICE;
   ctx->im_set = ctx->intersect_valid = ctx->matrix_valid = false;
   ctx->dofs_checked = false;
   PhaseTimer tm(ctx, NM_T_UPLOAD, /*accumulate=*/ctx->bg_set);
@@ -341,9 +370,9 @@ int nm_set_immersed(nm_ctx *ctx, int dim, int spacedim, uint64_t n_cells, const 
   ctx->n_im_dofs = n_dofs;
   if (ctx->bg_set && ctx->spacedim != spacedim) return nm_fail(ctx, NM_ERR_INVALID, "immersed spacedim %d != background spacedim %d", spacedim, ctx->spacedim);
   const int NVI = 1 << dim;
-  NM_TRY(nm_upload(ctx, ctx->im_verts, verts, n_cells * NVI * spacedim * sizeof(double), where));
+  NM_TRY(upload_or_adopt(ctx, ctx->im_verts, verts, n_cells * NVI * spacedim * sizeof(double), where, inplace));
   ctx->im_dofs_set = dofs != nullptr || n_cells == 0;
-  if (dofs) NM_TRY(nm_upload(ctx, ctx->im_dofs, dofs, n_cells * sizeof(uint32_t), where));
+  if (dofs) NM_TRY(upload_or_adopt(ctx, ctx->im_dofs, dofs, n_cells * sizeof(uint32_t), where, inplace));
   tm.stop();
   ctx->im_set = true;
   return NM_OK;

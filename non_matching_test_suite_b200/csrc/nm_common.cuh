@@ -21,6 +21,7 @@
 struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
+  bool borrowed = false;   // p is the caller's device array (NM_DEVICE_INPLACE): never freed, never written by the library
   template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 

@@ -291,3 +291,34 @@ def test_both_products_in_one_call(monkeypatch, name, cycle, compact):
     assert torch.equal(yd.cpu(), y_ref) and torch.equal(zd.cpu(), z_ref)
     ctx.sync_downloads()
     ctx.close()
+
+
+@pytest.mark.parametrize("name,cycle", [("sphere", 3), ("flower", 2)])
+def test_inputs_read_in_place_give_the_same_matrix_and_stay_untouched(name, cycle):
+    """NM_DEVICE_INPLACE: DoF tables and immersed vertices are used where the caller keeps them.  Same matrix bit for bit, the
+    arrays are never written, and the context goes back to its own copies when the inputs are set again the usual way."""
+    bg, im = make_config(name, cycle)
+    ref = coupling.make_context(bg, im, boxes=True)
+    ref.intersect(3, 1e-15)
+    want = ref.csr()
+    dev = "cuda:0"
+    lo, hi, dofs = bg.lo.to(dev), bg.hi.to(dev), bg.dofs.to(torch.int32).to(dev).contiguous()
+    cd, cp, cm, cw = bg.c_dof.to(torch.int32).to(dev), bg.c_ptr.to(dev), bg.c_master.to(torch.int32).to(dev), bg.c_weight.to(dev)
+    verts, idofs = im.verts.to(dev).contiguous(), im.dofs.to(torch.int32).to(dev).contiguous()
+    snap = [t.clone() for t in (dofs, verts, idofs)]
+    ctx = _lib.Context(0)
+    for _ in range(2):                                     # twice: the second call replaces a borrowed array by a borrowed one
+        ctx.set_background(bg.spacedim, lo=lo, hi=hi, dofs=dofs, n_dofs=bg.n_dofs, c_dof=cd, c_ptr=cp, c_master=cm, c_weight=cw, inplace=True)
+        ctx.set_immersed(im.dim, im.spacedim, verts, idofs, im.n_dofs, inplace=True)
+        ctx.intersect(3, 1e-15)
+        got = ctx.csr()
+        assert all(torch.equal(a, b) for a, b in zip(got, want))
+    held_inplace = ctx.device_bytes()
+    assert all(torch.equal(a, b) for a, b in zip((dofs, verts, idofs), snap))
+    coupling.set_grids(ctx, bg, im, boxes=True)            # host arrays again: own copies, the caller's tensors may go away
+    del dofs, verts, idofs
+    torch.cuda.empty_cache()
+    ctx.intersect(3, 1e-15)
+    assert all(torch.equal(a, b) for a, b in zip(ctx.csr(), want))
+    assert ctx.device_bytes() > held_inplace
+    ctx.close(); ref.close()
