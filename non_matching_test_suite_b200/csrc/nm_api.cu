@@ -65,6 +65,7 @@ static int adopt(nm_ctx *ctx, DevBuf &b, const void *src, size_t bytes)
 
 int nm_upload(nm_ctx *ctx, DevBuf &b, const void *src, size_t bytes, int where)
 {
+  if (where != NM_HOST && where != NM_DEVICE) return nm_fail(ctx, NM_ERR_INVALID, "where must be NM_HOST or NM_DEVICE for this call (got %d)", where);
   NM_TRY(nm_ensure(ctx, b, bytes));
   if (bytes == 0) return NM_OK;
   if (!src) return nm_fail(ctx, NM_ERR_INVALID, "null input pointer");
@@ -80,6 +81,7 @@ static int upload_or_adopt(nm_ctx *ctx, DevBuf &b, const void *src, size_t bytes
 
 int nm_download(nm_ctx *ctx, void *dst, const void *src, size_t bytes, int where)
 {
+  if (where != NM_HOST && where != NM_DEVICE) return nm_fail(ctx, NM_ERR_INVALID, "where must be NM_HOST or NM_DEVICE for this call (got %d)", where);
   if (bytes == 0 || !dst) return NM_OK;
   NM_CUDA(cudaMemcpyAsync(dst, src, bytes, where == NM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
   return NM_OK;

@@ -398,11 +398,13 @@ __global__ void __launch_bounds__(128) clip_local_kernel(uint64_t n_cand, const 
 // which is what the reference's degree-5 rule evaluates exactly for the Q1 x P0 integrand
 // (degree <= 3 on a planar piece; SURVEY.md rule R1).  The items of one candidate sit next to
 // each other in the ring, so they are combined with two shuffles in a fixed order.
+// block shape (same 24 warps per SM at 80 registers), measured at sphere cycle 8: 8 warps x 3 blocks 13.27 ms, 4 x 6 13.18,
+// 2 x 12 13.12, 4 x 7 (72 registers) 13.66, 16 x 1 (128 registers, no spills) 14.71
 #ifndef CM_MINB
-#define CM_MINB 3
+#define CM_MINB 12
 #endif
 #ifndef CM_WARPS_N
-#define CM_WARPS_N 8
+#define CM_WARPS_N 2
 #endif
 constexpr int CM_WARPS = CM_WARPS_N;    // warps per block
 constexpr int CM_CHUNKS = 8;   // chunks of 32 candidates per warp
@@ -442,10 +444,14 @@ __global__ void __launch_bounds__(CM_WARPS * 32, CM_MINB) clip_moments3_kernel(
     uint8_t *__restrict__ acc_out, unsigned long long *counters, const uint32_t *__restrict__ lut_global)
 {
   __shared__ uint32_t s_ring[CM_WARPS][128];
+#if NM_CLIP_SECTION
   __shared__ uint32_t s_lut[256];   // section polygons: cyclic order of the cut box edges per corner sign pattern
-  extern __shared__ double s_pool[];
   for (unsigned i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = lut_global[i];
   __syncthreads();
+#else
+  const uint32_t *s_lut = lut_global;   // not read by the box-plane clip
+#endif
+  extern __shared__ double s_pool[];
   const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   uint32_t *ring = s_ring[w];
   const uint64_t wstart = ((uint64_t)blockIdx.x * CM_WARPS + w) * (32 * CM_CHUNKS);

@@ -152,6 +152,14 @@ def test_error_behaviour():
     with pytest.raises(_lib.NmError) as e:
         fresh.set_background(2, verts=v.contiguous(), dofs=bg.dofs.contiguous(), n_dofs=bg.n_dofs)
     assert e.value.code == 3
+    # NM_DEVICE_INPLACE / NM_HOST_ASYNC are accepted only by the calls nmgpu.h names: anywhere else they are an error, not a
+    # pointer of the wrong kind
+    import ctypes as C
+    n_cand = ctx.intersect(3, 1e-15)["n_candidates"]
+    bi, bb = torch.empty(n_cand, dtype=torch.int32), torch.empty(n_cand, dtype=torch.int32)
+    for bad_where in (_lib.NM_DEVICE_INPLACE, _lib.NM_HOST_ASYNC, 7):
+        rc = ctx.L.nm_get_candidates(ctx.h, C.c_void_p(bi.data_ptr()), C.c_void_p(bb.data_ptr()), bad_where)
+        assert rc == 1 and b"where must be" in ctx.L.nm_last_error(ctx.h)
     fresh.close(); ctx.close()
 
 
