@@ -187,3 +187,63 @@ def create_nitsche_rhs_with_exact_intersections(space: BackgroundGrid, cells_and
                                   cells_and_quads.weights.contiguous(), _values_at(coefficient, pts), _values_at(rhs_function, pts),
                                   penalty, matrix=False)
     return rhs
+
+
+# --------------------------------------------------------------------------- #
+# general tensor-product Lagrange elements and the drivers' solve()           #
+# --------------------------------------------------------------------------- #
+@dataclass
+class FiniteElement:
+    """What the coupling path needs to know about a deal.II FiniteElement: its degree and fe.get_unit_support_points(), in
+    the element's own dof order (no numbering convention is assumed: the shape functions are the Lagrange polynomials of
+    these points)."""
+
+    degree: int
+    unit_support_points: torch.Tensor       # [dofs_per_cell, dim] in [0, 1]^dim
+
+    @property
+    def dofs_per_cell(self) -> int:
+        return int(self.unit_support_points.shape[0])
+
+
+def lagrange_element(dim: int, degree: int, nodes_1d: Optional[torch.Tensor] = None) -> FiniteElement:
+    """Tensor-product Lagrange element with lexicographic dof order (x fastest) on the given 1D nodes; default: equidistant
+    nodes, the single midpoint for degree 0 (FE_DGQ(0))."""
+    if nodes_1d is None:
+        nodes_1d = torch.tensor([0.5], dtype=torch.float64) if degree == 0 else torch.linspace(0.0, 1.0, degree + 1, dtype=torch.float64)
+    g = torch.meshgrid(*([nodes_1d] * dim), indexing="ij")
+    pts = torch.stack([a.reshape(-1) for a in reversed(g)], dim=1)          # first coordinate runs fastest
+    return FiniteElement(degree, pts.contiguous())
+
+
+def create_coupling_mass_matrix_for_elements(space: BackgroundGrid, immersed: ImmersedGrid, cells_and_quads: IntersectionInfo,
+                                             space_fe: FiniteElement, space_dofs: torch.Tensor, n_space_dofs: int,
+                                             immersed_fe: FiniteElement, immersed_dofs: torch.Tensor, n_immersed_dofs: int,
+                                             constraints=None, use_given_quadrature: bool = False) -> CouplingMatrix:
+    """create_coupling_mass_matrix_with_exact_intersections (code/include/coupling_utilities.h:154-304) for FE_Q(p) on the
+    background and FE_DGQ(q) on the immersed grid: `space_dofs` [n_cells, dofs_per_cell] / `immersed_dofs` are what
+    cell->get_dof_indices returns, `constraints` = (c_dof, c_ptr, c_master, c_weight) the lines of the closed
+    AffineConstraints (default: those of `space`, which fit its Q1 numbering only)."""
+    ctx = cells_and_quads.ctx
+    if space_dofs.shape[0] != space.n_cells or immersed_dofs.shape[0] != immersed.n_cells:
+        raise ValueError("DoF tables do not match the grids")
+    if constraints is None:
+        constraints = (None, None, None, None)
+    ctx.set_finite_elements((space_fe.degree, space_fe.unit_support_points.numpy()), _u32(space_dofs), n_space_dofs,
+                            (immersed_fe.degree, immersed_fe.unit_support_points.numpy()), _u32(immersed_dofs), n_immersed_dofs, *constraints)
+    if use_given_quadrature and cells_and_quads.points is not None:
+        ctx.assemble_fe(cells_and_quads.immersed_cell.contiguous(), cells_and_quads.space_cell.contiguous(), cells_and_quads.q_offset.contiguous(),
+                        cells_and_quads.points.contiguous(), cells_and_quads.weights.contiguous())
+    else:
+        ctx.assemble_fe()
+    return CouplingMatrix(ctx)
+
+
+def solve(coupling_matrix: CouplingMatrix, stiffness_matrix, mass_matrix, space_rhs: torch.Tensor, embedded_rhs: torch.Tensor,
+          inner=(2000, 1e-14, 1e-12), outer=(0, 1e-11, 1e-2), inhomogeneity: Optional[torch.Tensor] = None, gmres_basis: int = 28):
+    """PoissonLM::solve() (code/examples/lagrange_multiplier/2d3d/lagrange_multiplier.cc:613-659) around the GPU products of
+    `coupling_matrix`: lambda = S^-1 (C K^-1 f - g), S = C K^-1 Ct by GMRES preconditioned with C K Ct + M, K^-1 by CG, then
+    solution = K^-1 (f - Ct lambda) with the space constraints distributed.  `stiffness_matrix`, `mass_matrix` = CSR triples
+    (rowptr int64, col int32, val float64).  Returns (lambda, solution, stats)."""
+    return coupling_matrix.ctx.schur_solve(stiffness_matrix, mass_matrix, space_rhs, embedded_rhs, inner=inner, outer=outer,
+                                           inhomogeneity=inhomogeneity, gmres_basis=gmres_basis)

@@ -165,3 +165,17 @@ def test_error_behaviour_of_the_general_path():
         ctx.assemble_fe()
     assert e.value.code == 1
     ctx.close()
+
+
+def test_python_mirror_for_elements():
+    """coupling.create_coupling_mass_matrix_for_elements with (p, q) = (1, 0) described by support points = the matrix of
+    the optimised path; lagrange_element orders its points like the Q1 vertices of the grids."""
+    bg, im = make_config("sphere", 1, band_only=False)
+    info = coupling.collect_quadratures_on_overlapped_grids(bg, im, 3, 1e-15, with_quadrature=False)
+    A = _gpu_matrix(info.ctx, bg.n_dofs, im.n_dofs)
+    con = (bg.c_dof.to(torch.int32).contiguous(), bg.c_ptr.contiguous(), bg.c_master.to(torch.int32).contiguous(), bg.c_weight.contiguous())
+    C = coupling.create_coupling_mass_matrix_for_elements(bg, im, info, coupling.lagrange_element(3, 1), bg.dofs, bg.n_dofs,
+                                                          coupling.lagrange_element(2, 0), im.dofs, im.n_dofs, constraints=con)
+    assert info.ctx.info("merge_path") == 2
+    _same(_gpu_matrix(C.ctx, bg.n_dofs, im.n_dofs), A)
+    info.ctx.close()

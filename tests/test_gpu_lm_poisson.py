@@ -25,10 +25,10 @@ def test_error_tables_match_the_cpu_pipeline(c_oracle, name, cycle):
     d = bg.spacedim
     u_ex, g_ex, _ = lp.smooth_solution(d)
     ctx = coupling.make_context(bg, im, boxes=True)
-    ctx.intersect(3, 1e-15)
-    ctx.build_sparsity()
-    lam, u, st = ctx.schur_solve(_csr(ref["K"]), _csr(ref["M"]), torch.from_numpy(ref["f"]), torch.from_numpy(ref["g"]),
-                                 inner=(20000, 1e-16, 1e-13), outer=(bg.n_dofs, 1e-11, 1e-2))
+    info = coupling.collect_quadratures_on_overlapped_grids(bg, im, 3, 1e-15, ctx=ctx, with_quadrature=False)
+    C = coupling.create_coupling_mass_matrix_with_exact_intersections(bg, im, info, use_given_quadrature=False)
+    lam, u, st = coupling.solve(C, _csr(ref["K"]), _csr(ref["M"]), torch.from_numpy(ref["f"]), torch.from_numpy(ref["g"]),
+                                inner=(20000, 1e-16, 1e-13), outer=(bg.n_dofs, 1e-11, 1e-2))     # PoissonLM::solve()
     assert st["outer_iterations"] == ref["it"]
     l2, h1 = lp.errors(bg, u.numpy(), u_ex, g_ex)
     lam_norm = float(np.sqrt(np.sum(lam.numpy() ** 2 * ref["J"])))
