@@ -150,6 +150,22 @@ template <typename F> void parallel_for(const std::size_t n, F &&body)
     th.join();
 }
 
+// Receive buffer for a large read-back: not value-initialised (a std::vector would clear 2.5 GB of points on one thread
+// before the copy overwrites them), and its pages are faulted in by all host threads at once -- a first touch by the
+// copy itself costs more than the transfer.
+template <typename T> struct HostBuffer {
+  std::unique_ptr<T[]> p;
+  std::size_t n = 0;
+  explicit HostBuffer(std::size_t count) : p(count ? new T[count] : nullptr), n(count)
+  {
+    constexpr std::size_t page = 4096 / sizeof(T) ? 4096 / sizeof(T) : 1;
+    T *base = p.get();
+    parallel_for((n + page - 1) / page, [base, page](const std::size_t i) { reinterpret_cast<volatile char *>(base + i * page)[0] = 0; });
+  }
+  T *data() { return p.get(); }
+  const T &operator[](std::size_t i) const { return p[i]; }
+};
+
 inline void check(const Session &s, int rc)
 {
   AssertThrow(rc == NM_OK, ExcMessage(std::string("nmgpu: ") + nm_last_error(s.ctx)));
@@ -445,13 +461,13 @@ template <typename Visit> void for_each_stored_row(Session &s, const bool with_v
   std::uint64_t nnz = 0, n_rows = 0;
   check(s, nm_build_sparsity(s.ctx, &nnz));
   check(s, nm_get_csr_compact(s.ctx, &n_rows, nullptr, nullptr, nullptr, nullptr, NM_HOST));
-  std::vector<std::uint32_t> ids(n_rows), len(n_rows), col(nnz);
-  std::vector<double> val(with_values ? nnz : 0);
+  HostBuffer<std::uint32_t> ids(n_rows), len(n_rows), col(nnz);
+  HostBuffer<double> val(with_values ? nnz : 0);
   check(s, nm_get_csr_compact(s.ctx, &n_rows, ids.data(), len.data(), col.data(), with_values ? val.data() : nullptr, NM_HOST));
   std::vector<types::global_dof_index> cols;
   std::size_t o = 0;
   for (std::uint64_t r = 0; r < n_rows; ++r) {
-    cols.assign(col.begin() + o, col.begin() + o + len[r]);
+    cols.assign(col.data() + o, col.data() + o + len[r]);
     visit(static_cast<types::global_dof_index>(ids[r]), static_cast<types::global_dof_index>(len[r]), cols, with_values ? val.data() + o : nullptr);
     o += len[r];
   }
@@ -481,9 +497,9 @@ collect_quadratures_on_overlapped_grids(const GridTools::Cache<dim0, spacedim> &
   nm_counts counts;
   nmgpu_detail::check(s, nm_intersect(s.ctx, degree, tol, &counts));
 
-  std::vector<std::uint32_t> im(counts.n_accepted), bg(counts.n_accepted);
-  std::vector<std::uint64_t> off(counts.n_accepted + 1);
-  std::vector<double> pts(counts.n_qpoints * spacedim), w(counts.n_qpoints);
+  nmgpu_detail::HostBuffer<std::uint32_t> im(counts.n_accepted), bg(counts.n_accepted);
+  nmgpu_detail::HostBuffer<std::uint64_t> off(counts.n_accepted + 1);
+  nmgpu_detail::HostBuffer<double> pts(counts.n_qpoints * spacedim), w(counts.n_qpoints);
   nmgpu_detail::check(s, nm_get_pairs(s.ctx, im.data(), bg.data(), nullptr, NM_HOST));
   nmgpu_detail::check(s, nm_get_quadrature(s.ctx, off.data(), pts.data(), w.data(), NM_HOST));
 
@@ -492,7 +508,7 @@ collect_quadratures_on_overlapped_grids(const GridTools::Cache<dim0, spacedim> &
   nmgpu_detail::parallel_for(counts.n_accepted, [&](const std::size_t p) {
     const std::size_t nq = off[p + 1] - off[p];
     std::vector<Point<spacedim>> qp(nq);
-    std::vector<double> qw(w.begin() + off[p], w.begin() + off[p + 1]);
+    std::vector<double> qw(w.data() + off[p], w.data() + off[p + 1]);
     for (std::size_t k = 0; k < nq; ++k)
       for (unsigned int d = 0; d < spacedim; ++d)
         qp[k][d] = pts[(off[p] + k) * spacedim + d];
