@@ -7,7 +7,8 @@
 //   create_coupling_sparsity_pattern_with_exact_intersections<...>       reference :28-152
 //   create_coupling_mass_matrix_with_exact_intersections<...>            reference :154-304
 //
-// Implemented instantiations: <2,1,2> and <3,2,3> on Cartesian background cells.  FE_Q(1) x FE_DGQ(0) (every LM
+// Implemented instantiations: <2,1,2> and <3,2,3>, and the codimension-0 <2,2,2> (convex immersed quads, FE_Q(1) x FE_DGQ(0)),
+// on Cartesian background cells.  FE_Q(1) x FE_DGQ(0) (every LM
 // configuration in data/*.prm) runs on the fused kernels; any other FE_Q(p) x FE_DGQ(q) pair (p <= 5, <= 64 / 16 DoFs per
 // cell) on the general path (nm_set_finite_elements / nm_assemble_fe), described to the library by the elements' unit
 // support points.  Anything else raises ExcNotImplemented -- there is no CPU fallback.
@@ -484,7 +485,8 @@ collect_quadratures_on_overlapped_grids(const GridTools::Cache<dim0, spacedim> &
 {
   AssertThrow(dim1 <= dim0, ExcMessage("Intrinsic dimension of the immersed object must be smaller than dim0."));
   AssertThrow(degree > 0, ExcMessage("Invalid quadrature degree."));
-  AssertThrow(dim1 + 1 == dim0 && dim0 == spacedim && (spacedim == 2 || spacedim == 3), ExcNotImplemented());
+  // codimension 1 in 2D and 3D, and the codimension-0 instantiation <2,2,2> (code/src/coupling_utilities.cc:72-102)
+  AssertThrow(dim0 == spacedim && ((dim1 + 1 == dim0 && (spacedim == 2 || spacedim == 3)) || (dim1 == 2 && dim0 == 2)), ExcNotImplemented());
 
   using SpaceIt = typename Triangulation<dim0, spacedim>::cell_iterator;
   using ImmIt = typename Triangulation<dim1, spacedim>::cell_iterator;

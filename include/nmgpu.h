@@ -120,7 +120,11 @@ int nm_set_immersed_dofs(nm_ctx *ctx, const uint32_t *dofs, uint32_t dofs_per_ce
 /* Immersed grid (or this rank's contiguous shard of it) = `immersed_cache` / `immersed_dh`:
  *   verts [n_cells][2^dim][spacedim] deal.II order, dofs [n_cells][dofs_per_cell].
  * Scope: dim = spacedim-1, FE_DGQ(0) (dofs_per_cell == 1, DoFs not shared between cells),
- * no immersed constraints (never filled in the reference: 2d3d/lagrange_multiplier.cc:149). */
+ * no immersed constraints (never filled in the reference: 2d3d/lagrange_multiplier.cc:149).
+ * Also dim = spacedim = 2, the reference's codimension-0 instantiation <2,2,2> (src/coupling_utilities.cc:72-102,
+ * src/intersections.cc:307-355): convex quads in the plane of the background (a quad that is not convex is refused with
+ * NM_ERR_UNSUPPORTED); the pairs are background cell n immersed quad, the quadrature is QGaussSimplex<2>(degree) on the fan
+ * triangles of the clipped polygon, the rest of the path (acceptance, sparsity, Q1 x P0 matrix, products) is the same. */
 int nm_set_immersed(nm_ctx *ctx, int dim, int spacedim, uint64_t n_cells, const double *verts, const uint32_t *dofs,
                     uint32_t dofs_per_cell, uint64_t n_dofs, int where);
 

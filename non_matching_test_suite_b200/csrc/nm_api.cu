@@ -89,7 +89,7 @@ int nm_download(nm_ctx *ctx, void *dst, const void *src, size_t bytes, int where
 
 static std::vector<DevBuf *> all_buffers(nm_ctx *c)
 {
-  return {&c->bg_box, &c->bg_dofs, &c->line_of, &c->c_ptr, &c->c_master, &c->c_weight, &c->im_verts, &c->im_dofs, &c->im_split,
+  return {&c->bg_box, &c->bg_dofs, &c->line_of, &c->c_ptr, &c->c_master, &c->c_weight, &c->im_verts, &c->im_poly, &c->im_dofs, &c->im_split,
           &c->im_measure, &c->idx_next, &c->idx_extra_bg, &c->idx_hash, &c->idx_tmp, &c->cand_ptr, &c->cand_tmp, &c->cand_im, &c->cand_bg,
           &c->cand_sumw, &c->cand_local, &c->cand_nq, &c->cand_acc, &c->counters, &c->c_rowstart, &c->c_rowlen, &c->c_col, &c->c_val,
           &c->a_rowptr, &c->a_rowptr32, &c->a_col, &c->a_val, &c->a_cursor, &c->scan_tmp, &c->scratch_a, &c->scratch_b, &c->stage_x,
@@ -356,8 +356,9 @@ int nm_set_immersed(nm_ctx *ctx, int dim, int spacedim, uint64_t n_cells, const 
   if (!ctx) return NM_ERR_INVALID;
   NM_CUDA(cudaSetDevice(ctx->device));
   if (spacedim != 2 && spacedim != 3) return nm_fail(ctx, NM_ERR_INVALID, "spacedim must be 2 or 3 (got %d)", spacedim);
-  if (dim != spacedim - 1)
-    return nm_fail(ctx, NM_ERR_UNSUPPORTED, "only codimension-1 immersed grids are implemented (<2,1,2> and <3,2,3>); got dim=%d spacedim=%d", dim, spacedim);
+  const bool codim0 = dim == 2 && spacedim == 2;
+  if (dim != spacedim - 1 && !codim0)
+    return nm_fail(ctx, NM_ERR_UNSUPPORTED, "implemented immersed grids: codimension 1 (<2,1,2>, <3,2,3>) and codimension 0 in 2D (<2,2,2>); got dim=%d spacedim=%d", dim, spacedim);
   if (dofs_per_cell != 1)
     return nm_fail(ctx, NM_ERR_UNSUPPORTED, "immersed space must be FE_DGQ(0) (1 DoF per cell); got %u DoFs per cell", dofs_per_cell);
   if (n_cells >= 0xffffffffULL || n_dofs >= 0xffffffffULL) return nm_fail(ctx, NM_ERR_UNSUPPORTED, "cell / DoF counts must fit 32 bits");
@@ -372,7 +373,13 @@ int nm_set_immersed(nm_ctx *ctx, int dim, int spacedim, uint64_t n_cells, const 
   ctx->n_im_dofs = n_dofs;
   if (ctx->bg_set && ctx->spacedim != spacedim) return nm_fail(ctx, NM_ERR_INVALID, "immersed spacedim %d != background spacedim %d", spacedim, ctx->spacedim);
   const int NVI = 1 << dim;
-  NM_TRY(upload_or_adopt(ctx, ctx->im_verts, verts, n_cells * NVI * spacedim * sizeof(double), where, inplace));
+  ctx->codim0 = codim0;
+  if (codim0) {   // the quads go to im_poly; im_verts receives the diagonals of their boxes for the candidate search
+    NM_TRY(upload_or_adopt(ctx, ctx->im_poly, verts, n_cells * NVI * spacedim * sizeof(double), where, inplace));
+    NM_TRY(nm_quad2d_prepare(ctx));
+  } else {
+    NM_TRY(upload_or_adopt(ctx, ctx->im_verts, verts, n_cells * NVI * spacedim * sizeof(double), where, inplace));
+  }
   ctx->im_dofs_set = dofs != nullptr || n_cells == 0;
   if (dofs) NM_TRY(upload_or_adopt(ctx, ctx->im_dofs, dofs, n_cells * sizeof(uint32_t), where, inplace));
   tm.stop();
@@ -387,7 +394,8 @@ int nm_intersect(nm_ctx *ctx, unsigned degree, double tol, nm_counts *counts)
   if (!ctx) return NM_ERR_INVALID;
   NM_CUDA(cudaSetDevice(ctx->device));
   if (!ctx->bg_set || !ctx->im_set) return nm_fail(ctx, NM_ERR_STATE, "nm_set_background and nm_set_immersed must precede nm_intersect");
-  if (ctx->dim1 != ctx->spacedim - 1) return nm_fail(ctx, NM_ERR_INVALID, "immersed/background dimensions do not match");
+  if (ctx->dim1 != ctx->spacedim - 1 && !(ctx->codim0 && ctx->spacedim == 2))
+    return nm_fail(ctx, NM_ERR_INVALID, "immersed/background dimensions do not match");
   if (degree == 0) return nm_fail(ctx, NM_ERR_INVALID, "Invalid quadrature degree.");  // coupling_utilities.cc:32
   ctx->intersect_valid = ctx->matrix_valid = false;
   ctx->local_from_user = false;
@@ -633,7 +641,8 @@ int nm_assemble_host(nm_ctx *ctx, const nm_host_problem *P, nm_counts *counts, u
   const int d = P->spacedim;
   if (d != 2 && d != 3) return nm_fail(ctx, NM_ERR_INVALID, "spacedim must be 2 or 3 (got %d)", d);
   if (P->dim != d - 1)
-    return nm_fail(ctx, NM_ERR_UNSUPPORTED, "only codimension-1 immersed grids are implemented (<2,1,2> and <3,2,3>); got dim=%d spacedim=%d", P->dim, d);
+    return nm_fail(ctx, NM_ERR_UNSUPPORTED, "nm_assemble_host takes codimension-1 immersed grids (<2,1,2> and <3,2,3>); got dim=%d spacedim=%d "
+                   "(the codimension-0 case <2,2,2> goes through nm_set_immersed + nm_intersect)", P->dim, d);
   if (P->degree == 0) return nm_fail(ctx, NM_ERR_INVALID, "Invalid quadrature degree.");  // coupling_utilities.cc:32
   if (P->n_bg >= 0xffffffffULL || P->n_space_dofs >= 0xffffffffULL || P->n_im >= 0xffffffffULL || P->n_im_dofs >= 0xffffffffULL)
     return nm_fail(ctx, NM_ERR_UNSUPPORTED, "cell / DoF counts must fit 32 bits");
@@ -654,6 +663,7 @@ int nm_assemble_host(nm_ctx *ctx, const nm_host_problem *P, nm_counts *counts, u
   ctx->spacedim = d; ctx->n_bg = P->n_bg; ctx->n_space_dofs = P->n_space_dofs;
   ctx->n_constrained = P->n_constrained; ctx->n_cmasters = n_masters;
   ctx->dim1 = P->dim; ctx->n_im = P->n_im; ctx->n_im_dofs = P->n_im_dofs;
+  ctx->codim0 = false;
   ctx->degree = P->degree; ctx->tol = P->tol;
   const int NV = 1 << d, NVI = 1 << P->dim;
 

@@ -320,6 +320,86 @@ __device__ inline void pair_2d(const double *__restrict__ box, const double *__r
   o.nq += nq;
 }
 
+// Codimension 0 in 2D, the reference's <2,2,2> instantiation (code/src/intersections.cc:307-355, compute_intersection_quad_quad):
+// background rectangle n convex immersed quad.  The reference intersects the polygons with CGAL, triangulates the result
+// (CDT), keeps the triangles of area > tol and puts QGaussSimplex<2>(degree) on them (:693-746); here the quad is clipped
+// by the four lines of the cell (Sutherland-Hodgman in cell-local coordinates) and the polygon is fanned from its first
+// vertex -- the same region, and for a rule that is exact for the bilinear integrand (n_points_1D >= 2) the same integrals.
+template <class E>
+__device__ inline void pair_2d2d(const double *__restrict__ box, const double *__restrict__ quad /* [4][2], deal.II order */, double tol,
+                                 PairAcc &o, E &&emit)
+{
+  const double lo[2] = {box[0], box[1]};
+  const double H[2] = {box[4] - lo[0], box[5] - lo[1]};
+  double ax[8], ay[8], bx[8], by[8];
+  {
+    const int ring[4] = {0, 1, 3, 2};   // deal.II vertex order -> around the cell
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ax[i] = quad[2 * ring[i]] - lo[0]; ay[i] = quad[2 * ring[i] + 1] - lo[1]; }
+  }
+  int n = 4;
+  // one closed half-plane after the other: coordinate `axis` >= 0, then <= H[axis]
+#pragma unroll 1
+  for (int p = 0; p < 4 && n >= 3; ++p) {
+    const int axis = p >> 1;
+    const double sgn = (p & 1) ? -1.0 : 1.0, bound = (p & 1) ? H[axis] : 0.0;
+    int m = 0;
+    for (int i = 0; i < n; ++i) {
+      const int j = i + 1 == n ? 0 : i + 1;
+      const double da = sgn * ((axis ? ay[i] : ax[i]) - bound), db = sgn * ((axis ? ay[j] : ax[j]) - bound);
+      if (da >= 0.0) { bx[m] = ax[i]; by[m] = ay[i]; ++m; }
+      if ((da > 0.0 && db < 0.0) || (da < 0.0 && db > 0.0)) {
+        const double t = da / (da - db);
+        double x = ax[i] + t * (ax[j] - ax[i]), y = ay[i] + t * (ay[j] - ay[i]);
+        if (axis) y = bound; else x = bound;          // on the line by construction
+        bx[m] = x; by[m] = y; ++m;
+      }
+    }
+    n = m;
+    for (int i = 0; i < n; ++i) { ax[i] = bx[i]; ay[i] = by[i]; }
+  }
+  if (n < 3) return;
+  const int nq = c_rule.n;
+  for (int j = 1; j + 1 < n; ++j) {
+    const double e1[2] = {ax[j] - ax[0], ay[j] - ay[0]}, e2[2] = {ax[j + 1] - ax[0], ay[j + 1] - ay[0]};
+    const double J = fabs(e1[0] * e2[1] - e1[1] * e2[0]);       // |det B| = 2 * area     intersections.cc:702-707
+    if (!(0.5 * J > tol)) continue;                             // triangle area > tol    intersections.cc:336-337
+    if (J < 1e-12) { o.dropped++; continue; }                   // intersections.cc:710
+    for (int q = 0; q < nq; ++q) {
+      const double s = c_rule.x[q][0], t = c_rule.x[q][1];
+      const double x[2] = {ax[0] + s * e1[0] + t * e2[0], ay[0] + s * e1[1] + t * e2[1]};
+      emit(x, J * c_rule.w[q]);
+    }
+    o.nq += nq;
+  }
+}
+
+// bounding box (as the two end points of a diagonal, so that the candidate search treats the quad like a segment with
+// the same box), area and convexity of the immersed quads of the codimension-0 case
+__global__ void quad2d_prepare_kernel(uint64_t n, const double *__restrict__ poly, double *__restrict__ diag, double *__restrict__ measure,
+                                      unsigned long long *n_bad)
+{
+  const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  const double *q = poly + m * 8;
+  const int ring[4] = {0, 1, 3, 2};
+  double x[4], y[4];
+  for (int i = 0; i < 4; ++i) { x[i] = q[2 * ring[i]]; y[i] = q[2 * ring[i] + 1]; }
+  double lox = x[0], hix = x[0], loy = y[0], hiy = y[0], a2 = 0.0;
+  int pos = 0, neg = 0;
+  for (int i = 0; i < 4; ++i) {
+    const int j = (i + 1) & 3, k = (i + 2) & 3;
+    lox = x[i] < lox ? x[i] : lox; hix = x[i] > hix ? x[i] : hix;
+    loy = y[i] < loy ? y[i] : loy; hiy = y[i] > hiy ? y[i] : hiy;
+    a2 += x[i] * y[j] - x[j] * y[i];
+    const double c = (x[j] - x[i]) * (y[k] - y[j]) - (y[j] - y[i]) * (x[k] - x[j]);
+    pos += c > 0.0; neg += c < 0.0;
+  }
+  diag[m * 4 + 0] = lox; diag[m * 4 + 1] = loy; diag[m * 4 + 2] = hix; diag[m * 4 + 3] = hiy;
+  measure[m] = 0.5 * fabs(a2);
+  if ((pos && neg) || !(fabs(a2) > 0.0)) atomicAdd(n_bad, 1ULL);     // turns both ways, or no area: not a convex quad
+}
+
 // ---------------------------------------------------------------------------------------
 // the fused kernel: one thread per candidate
 // ---------------------------------------------------------------------------------------
@@ -330,7 +410,7 @@ __global__ void __launch_bounds__(128) clip_local_kernel(uint64_t n_cand, const 
                                                          const double *__restrict__ im_measure, double tol,
                                                          double *__restrict__ sumw_out, double *__restrict__ local_out,
                                                          uint16_t *__restrict__ nq_out, uint8_t *__restrict__ acc_out,
-                                                         unsigned long long *counters)
+                                                         unsigned long long *counters, int codim0)
 {
   constexpr int NL = 1 << D;
   const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -348,7 +428,10 @@ __global__ void __launch_bounds__(128) clip_local_kernel(uint64_t n_cand, const 
               [&](const double *x, double w) { q1_add_3d(o, x[0] * ih[0], x[1] * ih[1], x[2] * ih[2], w); });
     } else {
       const double ih[2] = {1.0 / (box[4] - box[0]), 1.0 / (box[5] - box[1])};
-      pair_2d(box, im_verts + (uint64_t)m * 4, o, [&](const double *x, double w) { q1_add_2d(o, x[0] * ih[0], x[1] * ih[1], w); });
+      if (codim0)   // im_verts = the quads [n][4][2]
+        pair_2d2d(box, im_verts + (uint64_t)m * 8, tol, o, [&](const double *x, double w) { q1_add_2d(o, x[0] * ih[0], x[1] * ih[1], w); });
+      else
+        pair_2d(box, im_verts + (uint64_t)m * 4, o, [&](const double *x, double w) { q1_add_2d(o, x[0] * ih[0], x[1] * ih[1], w); });
     }
     const bool ok = o.sumw > tol;                          // coupling_utilities.cc:61
     sumw_out[c] = o.sumw;
@@ -611,7 +694,7 @@ __global__ void emit_quadrature_kernel(uint64_t n_acc, const uint64_t *__restric
                                        const uint32_t *__restrict__ cand_bg, const double *__restrict__ bg_box,
                                        const double *__restrict__ im_verts, const uint8_t *__restrict__ split, double tol,
                                        const uint64_t *__restrict__ q_off, double *__restrict__ pts, double *__restrict__ wts,
-                                       unsigned long long *n_mismatch, const uint32_t *__restrict__ lut)
+                                       unsigned long long *n_mismatch, const uint32_t *__restrict__ lut, int codim0)
 {
   const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_acc) return;
@@ -659,6 +742,11 @@ __global__ void emit_quadrature_kernel(uint64_t n_acc, const uint64_t *__restric
   } else if (D == 3) {
     pair_3d(box, im_verts + (uint64_t)m * 12, split[m], tol, o, [&](const double *x, double wq) {
       if (w < w_end) { pts[w * 3 + 0] = x[0] + box[0]; pts[w * 3 + 1] = x[1] + box[1]; pts[w * 3 + 2] = x[2] + box[2]; wts[w] = wq; }
+      ++w;
+    });
+  } else if (codim0) {
+    pair_2d2d(box, im_verts + (uint64_t)m * 8, tol, o, [&](const double *x, double wq) {
+      if (w < w_end) { pts[w * 2 + 0] = x[0] + box[0]; pts[w * 2 + 1] = x[1] + box[1]; wts[w] = wq; }
       ++w;
     });
   } else {
@@ -755,10 +843,31 @@ int nm_split_run(nm_ctx *ctx)
     NM_CUDA(cudaMemcpyAsync(&h, ties, 8, cudaMemcpyDeviceToHost, ctx->stream));
     NM_SYNC(ctx);
     ctx->counts.n_split_ties = h;
-  } else {
+  } else if (!ctx->codim0) {   // (codimension 0: the areas were taken when the quads were set, nm_quad2d_prepare)
     segment_measure_kernel<<<nm_blocks(n, 256), 256, 0, NM_LS(ctx)>>>(n, ctx->im_verts.as<double>(), ctx->im_measure.as<double>());
     NM_CUDA(cudaGetLastError());
   }
+  return NM_OK;
+}
+
+// codimension 0 in 2D: from the quads in ctx->im_poly, the diagonal of every bounding box (ctx->im_verts: what the candidate
+// search reads), the areas, and a convexity check
+int nm_quad2d_prepare(nm_ctx *ctx)
+{
+  const uint64_t n = ctx->n_im;
+  NM_TRY(nm_ensure(ctx, ctx->im_verts, (n + 1) * 4 * sizeof(double)));
+  NM_TRY(nm_ensure(ctx, ctx->im_measure, (n + 1) * sizeof(double)));
+  NM_TRY(nm_ensure(ctx, ctx->counters, 64 * sizeof(uint64_t)));
+  if (n == 0) return NM_OK;
+  unsigned long long *bad = ctx->counters.as<unsigned long long>() + 9;
+  NM_CUDA(cudaMemsetAsync(bad, 0, 8, ctx->stream));
+  quad2d_prepare_kernel<<<nm_blocks(n, 256), 256, 0, NM_LS(ctx)>>>(n, ctx->im_poly.as<double>(), ctx->im_verts.as<double>(),
+                                                                    ctx->im_measure.as<double>(), bad);
+  NM_CUDA(cudaGetLastError());
+  unsigned long long h = 0;
+  NM_CUDA(cudaMemcpyAsync(&h, bad, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  NM_SYNC(ctx);
+  if (h) return nm_fail(ctx, NM_ERR_UNSUPPORTED, "%llu immersed quad(s) are not convex (or have no area): the codimension-0 path clips convex cells only", h);
   return NM_OK;
 }
 
@@ -812,12 +921,12 @@ int nm_clip_run(nm_ctx *ctx)
     clip_local_kernel<3><<<B, T, 0, NM_LS(ctx)>>>(nc, ctx->cand_im.as<uint32_t>(), ctx->cand_bg.as<uint32_t>(), ctx->bg_box.as<double>(),
                                                    ctx->im_verts.as<double>(), ctx->im_split.as<uint8_t>(), ctx->im_measure.as<double>(),
                                                    ctx->tol, ctx->cand_sumw.as<double>(), ctx->cand_local.as<double>(),
-                                                   ctx->cand_nq.as<uint16_t>(), ctx->cand_acc.as<uint8_t>(), cnt);
+                                                   ctx->cand_nq.as<uint16_t>(), ctx->cand_acc.as<uint8_t>(), cnt, 0);
   else
     clip_local_kernel<2><<<B, T, 0, NM_LS(ctx)>>>(nc, ctx->cand_im.as<uint32_t>(), ctx->cand_bg.as<uint32_t>(), ctx->bg_box.as<double>(),
-                                                   ctx->im_verts.as<double>(), nullptr, ctx->im_measure.as<double>(), ctx->tol,
-                                                   ctx->cand_sumw.as<double>(), ctx->cand_local.as<double>(), ctx->cand_nq.as<uint16_t>(),
-                                                   ctx->cand_acc.as<uint8_t>(), cnt);
+                                                   ctx->codim0 ? ctx->im_poly.as<double>() : ctx->im_verts.as<double>(), nullptr,
+                                                   ctx->im_measure.as<double>(), ctx->tol, ctx->cand_sumw.as<double>(), ctx->cand_local.as<double>(),
+                                                   ctx->cand_nq.as<uint16_t>(), ctx->cand_acc.as<uint8_t>(), cnt, ctx->codim0 ? 1 : 0);
   kt.stop();
   NM_CUDA(cudaGetLastError());
   unsigned long long h[4];
@@ -879,13 +988,15 @@ int nm_quadrature_emit(nm_ctx *ctx, uint64_t *q_offset, double *points, double *
     const uint32_t *ci = ctx->cand_im.as<uint32_t>(), *cb = ctx->cand_bg.as<uint32_t>();
     if (d == 3 && moment_path)
       emit_quadrature_kernel<3, true><<<B, 128, 0, NM_LS(ctx)>>>(na, acc_idx, ci, cb, ctx->bg_box.as<double>(), ctx->im_verts.as<double>(),
-                                                                ctx->im_split.as<uint8_t>(), ctx->tol, offs.as<uint64_t>(), pts_d, w_d, mismatch, ctx->clip_lut.as<uint32_t>());
+                                                                ctx->im_split.as<uint8_t>(), ctx->tol, offs.as<uint64_t>(), pts_d, w_d, mismatch, ctx->clip_lut.as<uint32_t>(), 0);
     else if (d == 3)
       emit_quadrature_kernel<3, false><<<B, 128, 0, NM_LS(ctx)>>>(na, acc_idx, ci, cb, ctx->bg_box.as<double>(), ctx->im_verts.as<double>(),
-                                                                 ctx->im_split.as<uint8_t>(), ctx->tol, offs.as<uint64_t>(), pts_d, w_d, mismatch, ctx->clip_lut.as<uint32_t>());
+                                                                 ctx->im_split.as<uint8_t>(), ctx->tol, offs.as<uint64_t>(), pts_d, w_d, mismatch, ctx->clip_lut.as<uint32_t>(), 0);
     else
-      emit_quadrature_kernel<2, false><<<B, 128, 0, NM_LS(ctx)>>>(na, acc_idx, ci, cb, ctx->bg_box.as<double>(), ctx->im_verts.as<double>(), nullptr,
-                                                                 ctx->tol, offs.as<uint64_t>(), pts_d, w_d, mismatch, ctx->clip_lut.as<uint32_t>());
+      emit_quadrature_kernel<2, false><<<B, 128, 0, NM_LS(ctx)>>>(na, acc_idx, ci, cb, ctx->bg_box.as<double>(),
+                                                                 ctx->codim0 ? ctx->im_poly.as<double>() : ctx->im_verts.as<double>(), nullptr,
+                                                                 ctx->tol, offs.as<uint64_t>(), pts_d, w_d, mismatch, ctx->clip_lut.as<uint32_t>(),
+                                                                 ctx->codim0 ? 1 : 0);
     NM_CUDA(cudaGetLastError());
     unsigned long long h_mis = 0;
     NM_CUDA(cudaMemcpyAsync(&h_mis, mismatch, 8, cudaMemcpyDeviceToHost, ctx->stream));

@@ -75,7 +75,9 @@ struct nm_ctx {
   // ---- immersed ----
   int dim1 = 0;
   uint64_t n_im = 0, n_im_dofs = 0;
-  DevBuf im_verts;    // [n_im][2^dim1][spacedim] f64 (AoS, cell-major)
+  DevBuf im_verts;    // [n_im][2^dim1][spacedim] f64 (AoS, cell-major); codimension 0: [n_im][2][2] = the diagonal of each quad's box
+  bool codim0 = false; // dim1 == spacedim == 2 (the reference's <2,2,2>): the quads themselves are in im_poly
+  DevBuf im_poly;     // [n_im][4][2] f64, deal.II vertex order
   DevBuf im_dofs;     // [n_im] u32
   DevBuf im_split;    // [n_im] u8 (3D)
   DevBuf im_measure;  // [n_im] f64
@@ -247,6 +249,7 @@ int nm_nitsche_run(nm_ctx *ctx, uint64_t n_pairs, const uint32_t *bg, const uint
 int nm_spmv_run(nm_ctx *ctx, int transpose, const double *x_dev, double *y_dev, int flags = 0);
 int nm_stored_rowptr_global(nm_ctx *ctx, uint64_t *rowptr_dev);
 int nm_spmv_push_owned_run(nm_ctx *ctx, const double *x, int n_ranks, double *const *targets, uint64_t rows_per_rank);
+int nm_quad2d_prepare(nm_ctx *ctx);
 int nm_nonempty_rows(nm_ctx *ctx, uint64_t *n_rows_out, const uint32_t **ids_dev, const uint32_t **len_dev);
 int nm_local_map(nm_ctx *ctx, int which, int to_global, const double *src, double *dst);
 int nm_wait_download_issued(nm_ctx *ctx);

@@ -262,6 +262,8 @@ int nm_set_finite_elements(nm_ctx *ctx, const nm_fe *space_fe, const uint32_t *s
   if (!ctx) return NM_ERR_INVALID;
   NM_CUDA(cudaSetDevice(ctx->device));
   if (!ctx->bg_set || !ctx->im_set) return nm_fail(ctx, NM_ERR_STATE, "nm_set_background and nm_set_immersed must precede nm_set_finite_elements");
+  if (ctx->codim0)
+    return nm_fail(ctx, NM_ERR_UNSUPPORTED, "general elements are implemented for codimension-1 immersed grids; the codimension-0 case <2,2,2> takes FE_Q(1) x FE_DGQ(0)");
   if (!space_fe || !immersed_fe || !space_fe->unit_support_points || (ctx->n_bg && !space_dofs) || (ctx->n_im && !immersed_dofs))
     return nm_fail(ctx, NM_ERR_INVALID, "null finite element description or DoF table");
   if (immersed_fe->dofs_per_cell > 1 && !immersed_fe->unit_support_points) return nm_fail(ctx, NM_ERR_INVALID, "null immersed support points");

@@ -77,7 +77,8 @@ class BackgroundGrid:
 
 @dataclass
 class ImmersedGrid:
-    """Codimension-1 cells: segments in 2D (dim=1) or quads in 3D (dim=2); FE_DGQ(0) DoFs."""
+    """Codimension-1 cells: segments in 2D (dim=1) or quads in 3D (dim=2); FE_DGQ(0) DoFs.  Codimension 0 in 2D
+    (dim = spacedim = 2, the reference's <2,2,2> instantiation): convex quads in the plane of the background."""
 
     dim: int
     spacedim: int
@@ -99,6 +100,10 @@ class ImmersedGrid:
         v = self.verts
         if self.dim == 1:
             return (v[:, 1] - v[:, 0]).norm(dim=1)
+        if self.spacedim == 2:          # planar quad, deal.II vertex order: shoelace over v0, v1, v3, v2
+            r = v[:, [0, 1, 3, 2]]
+            n = torch.roll(r, -1, dims=1)
+            return 0.5 * (r[..., 0] * n[..., 1] - n[..., 0] * r[..., 1]).sum(dim=1).abs()
         a = torch.linalg.cross(v[:, 1] - v[:, 0], v[:, 3] - v[:, 0]).norm(dim=1)
         b = torch.linalg.cross(v[:, 3] - v[:, 0], v[:, 2] - v[:, 0]).norm(dim=1)
         return 0.5 * (a + b)
@@ -124,6 +129,20 @@ def circle_grid(n_segments: int, R: float = 0.3, center=(0.5, 0.5), device="cpu"
     verts = torch.stack([p[:-1], p[1:]], dim=1)
     dofs = torch.arange(n_segments, dtype=torch.int32, device=device)[:, None]
     return ImmersedGrid(1, 2, verts.contiguous(), dofs, n_segments)
+
+
+def solid_grid_2d(n: int, side: float = 0.6, angle: float = 0.3, center=(0.5, 0.5), warp: float = 0.04, device="cpu") -> ImmersedGrid:
+    """A 2D body for the codimension-0 instantiation <2,2,2>: n x n convex quads covering a square of edge `side`, rotated
+    by `angle` about `center` and smoothly warped (non-affine cells), one FE_DGQ(0) dof per cell."""
+    t = torch.linspace(-0.5, 0.5, n + 1, dtype=F64, device=device)
+    X, Y = torch.meshgrid(t, t, indexing="xy")                                # X varies along the second index (x fastest)
+    Xw = X + warp * torch.sin(math.pi * (Y + 0.5)) * torch.sin(2 * math.pi * (X + 0.5))
+    Yw = Y + warp * torch.sin(math.pi * (X + 0.5)) * torch.sin(2 * math.pi * (Y + 0.5))
+    c, s_ = math.cos(angle), math.sin(angle)
+    P = torch.stack([center[0] + side * (c * Xw - s_ * Yw), center[1] + side * (s_ * Xw + c * Yw)], dim=-1)   # [n+1 (y), n+1 (x), 2]
+    v = torch.stack([P[:-1, :-1], P[:-1, 1:], P[1:, :-1], P[1:, 1:]], dim=2).reshape(n * n, 4, 2)            # deal.II order
+    dofs = torch.arange(n * n, dtype=torch.int32, device=device)[:, None]
+    return ImmersedGrid(2, 2, v.contiguous(), dofs, n * n)
 
 
 def flower_points(device="cpu") -> torch.Tensor:

@@ -39,6 +39,8 @@ def lib():
         L.nmo_incircle.argtypes = [P, P, P, P]
         L.nmo_pairs.argtypes = [C.c_int, C.c_int64, P, P, P, P, P, C.c_int, C.c_double, P, P, P, P]
         L.nmo_pairs_quadrature.argtypes = [C.c_int, C.c_int64, P, P, P, P, P, C.c_int, C.c_double, P, P, P]
+        L.nmo_pairs_codim0.argtypes = [C.c_int64, P, P, P, P, C.c_int, C.c_double, P, P, P, P]
+        L.nmo_pairs_quadrature_codim0.argtypes = [C.c_int64, P, P, P, P, C.c_int, C.c_double, P, P, P]
         L.nmo_build_csr.restype = C.c_int64
         L.nmo_build_csr.argtypes = [C.c_int, C.c_int64, P, P, P, P, C.c_int64, P, P, P, P,
                                     C.POINTER(P), C.POINTER(P), C.POINTER(P)]
@@ -113,6 +115,30 @@ def pairs(d, cand, bg_lo, bg_hi, im_verts, codes, n1d=3, tol=1e-15):
     if rc != 0:
         raise ValueError("unsupported quadrature rule n_points_1D=%d" % n1d)
     return sumw, local, nq, dropped.value
+
+
+def pairs_codim0(cand, bg_lo, bg_hi, im_verts, n1d=3, tol=1e-15):
+    """pairs() for <2,2,2>: immersed quads [n, 4, 2] in the plane of the background (nmo_pairs_codim0)."""
+    cand = _np(cand, np.uint64)
+    n = cand.shape[0]
+    sumw = np.zeros(n); local = np.zeros((n, 4)); nq = np.zeros(n, dtype=np.int32)
+    dropped = C.c_int64(0)
+    rc = lib().nmo_pairs_codim0(n, _p(cand), _p(_np(bg_lo, np.float64)), _p(_np(bg_hi, np.float64)), _p(_np(im_verts, np.float64)), n1d, tol,
+                                _p(sumw), _p(local), _p(nq), C.cast(C.byref(dropped), C.c_void_p))
+    if rc != 0:
+        raise ValueError("unsupported quadrature rule n_points_1D=%d" % n1d)
+    return sumw, local, nq, dropped.value
+
+
+def quadrature_codim0(pairs_keys, nq, bg_lo, bg_hi, im_verts, n1d=3, tol=1e-15):
+    keys = _np(pairs_keys, np.uint64)
+    q_off = np.concatenate([[0], np.cumsum(_np(nq, np.int64))]).astype(np.uint64)
+    pts = np.zeros((int(q_off[-1]), 2)); wts = np.zeros(int(q_off[-1]))
+    rc = lib().nmo_pairs_quadrature_codim0(keys.shape[0], _p(keys), _p(_np(bg_lo, np.float64)), _p(_np(bg_hi, np.float64)),
+                                           _p(_np(im_verts, np.float64)), n1d, tol, _p(q_off), _p(pts), _p(wts))
+    if rc != 0:
+        raise ValueError("nmo_pairs_quadrature_codim0 failed (%d)" % rc)
+    return q_off, pts, wts
 
 
 def quadrature(d, pairs_keys, nq, bg_lo, bg_hi, im_verts, codes, n1d=3, tol=1e-15):
@@ -193,8 +219,12 @@ def assemble(bg, im, n1d: int = 3, tol: float = 1e-15, threads: Optional[int] = 
     d = bg.spacedim
     ilo, ihi = im.boxes()
     cand = candidates(bg.lo, bg.hi, ilo, ihi)
+    codim0 = im.dim == d
     codes = quad_split(im.verts) if d == 3 else None
-    sumw, local, nq, dropped = pairs(d, cand, bg.lo, bg.hi, im.verts, codes, n1d, tol)
+    if codim0:
+        sumw, local, nq, dropped = pairs_codim0(cand, bg.lo, bg.hi, im.verts, n1d, tol)
+    else:
+        sumw, local, nq, dropped = pairs(d, cand, bg.lo, bg.hi, im.verts, codes, n1d, tol)
     keep = sumw > tol
     acc = cand[keep]
     rowptr, col, val = build_csr(d, acc, local[keep], bg, im)
@@ -205,5 +235,8 @@ def assemble(bg, im, n1d: int = 3, tol: float = 1e-15, threads: Optional[int] = 
 def assemble_with_quadrature(bg, im, n1d: int = 3, tol: float = 1e-15):
     """assemble() plus the per-pair quadrature in the reference's subdivision: adds q_offset, points, weights."""
     r = assemble(bg, im, n1d, tol)
+    if im.dim == bg.spacedim:
+        r["q_offset"], r["points"], r["weights"] = quadrature_codim0(r["accepted"], r["nq"], bg.lo, bg.hi, im.verts, n1d, tol)
+        return r
     r["q_offset"], r["points"], r["weights"] = quadrature(bg.spacedim, r["accepted"], r["nq"], bg.lo, bg.hi, im.verts, r["codes"], n1d, tol)
     return r

@@ -184,6 +184,37 @@ def pair_integrals_2d(lo, hi, seg):
     return float(scale), local
 
 
+def pair_integrals_2d2d(lo, hi, quad):
+    """(sum_w, local[4]) for a background rectangle and a convex immersed quad in its plane (the reference's <2,2,2>
+    instantiation, intersections.cc:307-355): quad clipped by the four lines of the rectangle, then the bilinear shape
+    functions integrated exactly over the fan triangles with a rational rule exact to degree 3; everything in rationals,
+    the result rounded once."""
+    lo = [Fr(float(x)) for x in lo]; hi = [Fr(float(x)) for x in hi]
+    poly = [tuple(Fr(float(c)) for c in quad[i]) for i in (0, 1, 3, 2)]        # deal.II vertex order -> around the cell
+    for axis in range(2):
+        poly = _clip_poly_halfspace(poly, axis, lo[axis], True)
+        if len(poly) < 3:
+            return 0.0, [0.0] * 4
+        poly = _clip_poly_halfspace(poly, axis, hi[axis], False)
+        if len(poly) < 3:
+            return 0.0, [0.0] * 4
+    h = [hi[k] - lo[k] for k in range(2)]
+    tot, acc = Fr(0), [Fr(0)] * 4
+    a = poly[0]
+    for j in range(1, len(poly) - 1):
+        b, c = poly[j], poly[j + 1]
+        J = abs((b[0] - a[0]) * (c[1] - a[1]) - (b[1] - a[1]) * (c[0] - a[0]))       # 2 * area, exact
+        if J == 0:
+            continue
+        tot += J / 2
+        for (s, t), w in _TRI4:                                                     # weights sum to 1/2: w * J = weight on the triangle
+            x = [a[k] + s * (b[k] - a[k]) + t * (c[k] - a[k]) for k in range(2)]
+            xi = [(x[k] - lo[k]) / h[k] for k in range(2)]
+            for i in range(4):
+                acc[i] += w * J * _shape(i, xi)
+    return float(tot), [float(v) for v in acc]
+
+
 # Boole's rule: rational nodes, exact to degree 5 (phi_i phi_j has degree 4 along a segment)
 _BOOLE = ((Fr(0), Fr(7, 90)), (Fr(1, 4), Fr(32, 90)), (Fr(1, 2), Fr(12, 90)), (Fr(3, 4), Fr(32, 90)), (Fr(1), Fr(7, 90)))
 
@@ -302,7 +333,9 @@ def assemble(bg, im, tol: float = 1e-15, cand=None):
     codes = [quad_split_code(V[m]) for m in range(len(V))] if d == 3 else None
     accepted, sumw, pattern, values = [], [], set(), {}
     for (m, b) in cand:
-        if d == 2:
+        if d == 2 and im.dim == 2:
+            s, loc = pair_integrals_2d2d(lo[b], hi[b], V[m])
+        elif d == 2:
             s, loc = pair_integrals_2d(lo[b], hi[b], V[m])
         else:
             s, loc = pair_integrals_3d(lo[b], hi[b], V[m], codes[m])

@@ -397,6 +397,106 @@ static void pair_2d(const double *lo, const double *hi, const double *seg, int n
   }
 }
 
+/* ------------------------------------------------------------------------- */
+/* codimension 0 in 2D: background quad n immersed quad (intersections.cc:307-355, compute_intersection_quad_quad) */
+/* ------------------------------------------------------------------------- */
+/* The reference intersects the two polygons with CGAL, triangulates the result with a constrained Delaunay triangulation,
+ * keeps the triangles of area > tol and puts QGaussSimplex<2> on them (intersections.cc:693-746).  Restated the other way
+ * round from the CUDA kernel: here the BOX is clipped by the four edges of the (convex) immersed quad, and the fan starts
+ * at the vertex of smallest x.  Any triangulation of the same polygon gives the same integral of the bilinear integrand
+ * once the rule is exact for degree 2 (n_points_1D >= 2), rule R1. */
+static int clip_by_edge_2d(const double (*in)[2], int n, const double *u, const double *v, double sg, double (*out)[2])
+{ /* keep the side to the left of u -> v (sg = +1 for a counter-clockwise quad) */
+  const double nx = -(v[1] - u[1]) * sg, ny = (v[0] - u[0]) * sg;
+  int m = 0;
+  for (int i = 0; i < n; ++i) {
+    const double *a = in[i], *b = in[(i + 1) % n];
+    const double fa = (a[0] - u[0]) * nx + (a[1] - u[1]) * ny, fb = (b[0] - u[0]) * nx + (b[1] - u[1]) * ny;
+    if (fa >= 0) { out[m][0] = a[0]; out[m][1] = a[1]; ++m; }
+    if ((fa > 0 && fb < 0) || (fa < 0 && fb > 0)) {
+      const double t = fa / (fa - fb);
+      out[m][0] = a[0] + t * (b[0] - a[0]); out[m][1] = a[1] + t * (b[1] - a[1]); ++m;
+    }
+  }
+  return m;
+}
+
+static void pair_2d2d(const double *lo, const double *hi, const double *quad /* [4][2], deal.II order */, int n1d, double tol, pair_out *o)
+{
+  const int ring[4] = {0, 1, 3, 2};   /* deal.II vertex order -> around the cell */
+  double Q[4][2];
+  for (int i = 0; i < 4; ++i) { Q[i][0] = quad[2 * ring[i]]; Q[i][1] = quad[2 * ring[i] + 1]; }
+  double a2 = 0;
+  for (int i = 0; i < 4; ++i) a2 += Q[i][0] * Q[(i + 1) % 4][1] - Q[(i + 1) % 4][0] * Q[i][1];
+  const double sg = a2 > 0 ? 1.0 : -1.0;
+  double A[16][2] = {{lo[0], lo[1]}, {hi[0], lo[1]}, {hi[0], hi[1]}, {lo[0], hi[1]}}, B[16][2];
+  int n = 4;
+  for (int e = 0; e < 4 && n >= 3; ++e) {
+    n = clip_by_edge_2d((const double(*)[2])A, n, Q[e], Q[(e + 1) % 4], sg, B);
+    memcpy(A, B, sizeof(double) * 2 * (size_t)n);
+  }
+  if (n < 3) return;
+  int i0 = 0;
+  for (int i = 1; i < n; ++i) if (A[i][0] < A[i0][0]) i0 = i;
+  double tx[16][2], tw[16];
+  const int ng = rule_tri(n1d, tx, tw);
+  for (int j = 1; j + 1 < n; ++j) {
+    const double *a = A[i0], *b = A[(i0 + j) % n], *c = A[(i0 + j + 1) % n];
+    const double J = fabs((b[0] - a[0]) * (c[1] - a[1]) - (b[1] - a[1]) * (c[0] - a[0]));
+    if (!(0.5 * J > tol)) continue;              /* triangle area > tol   intersections.cc:336-337 */
+    if (J < 1e-12) { o->dropped++; continue; }   /* :710 */
+    for (int q = 0; q < ng; ++q) {
+      const double x[2] = {a[0] + tx[q][0] * (b[0] - a[0]) + tx[q][1] * (c[0] - a[0]), a[1] + tx[q][0] * (b[1] - a[1]) + tx[q][1] * (c[1] - a[1])};
+      const double w = J * tw[q];
+      o->sumw += w;
+      emit_point(o, 2, x, w);
+      o->nq++;
+      q1_accumulate(2, lo, hi, x, w, o->local);
+    }
+  }
+}
+
+/* nmo_pairs / nmo_pairs_quadrature for <2,2,2>: im_verts = [n][4][2] */
+int nmo_pairs_codim0(int64_t n_cand, const uint64_t *cand, const double *bg_lo, const double *bg_hi, const double *im_verts, int n1d,
+                     double tol, double *sumw, double *local, int32_t *nq, int64_t *n_dropped)
+{
+  double tx[16][2], tw[16];
+  if (rule_tri(n1d, tx, tw) == 0) return -1;
+  int64_t dropped = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : dropped)
+  for (int64_t i = 0; i < n_cand; ++i) {
+    uint32_t m = (uint32_t)(cand[i] >> 32), b = (uint32_t)cand[i];
+    pair_out o;
+    memset(&o, 0, sizeof(o));
+    pair_2d2d(bg_lo + 2 * (int64_t)b, bg_hi + 2 * (int64_t)b, im_verts + 8 * (int64_t)m, n1d, tol, &o);
+    sumw[i] = o.sumw;
+    for (int k = 0; k < 4; ++k) local[i * 4 + k] = o.local[k];
+    if (nq) nq[i] = o.nq;
+    dropped += o.dropped;
+  }
+  if (n_dropped) *n_dropped = dropped;
+  return 0;
+}
+
+int nmo_pairs_quadrature_codim0(int64_t n, const uint64_t *pairs, const double *bg_lo, const double *bg_hi, const double *im_verts, int n1d,
+                                double tol, const uint64_t *q_off, double *pts, double *wts)
+{
+  double tx[16][2], tw[16];
+  if (rule_tri(n1d, tx, tw) == 0) return -1;
+  int bad = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : bad)
+  for (int64_t i = 0; i < n; ++i) {
+    uint32_t m = (uint32_t)(pairs[i] >> 32), b = (uint32_t)pairs[i];
+    pair_out o;
+    memset(&o, 0, sizeof(o));
+    o.qp = pts + (int64_t)q_off[i] * 2;
+    o.qw = wts + q_off[i];
+    pair_2d2d(bg_lo + 2 * (int64_t)b, bg_hi + 2 * (int64_t)b, im_verts + 8 * (int64_t)m, n1d, tol, &o);
+    bad += (uint64_t)o.nq != q_off[i + 1] - q_off[i];
+  }
+  return bad ? -2 : 0;
+}
+
 typedef struct { double n[3]; double c; } plane; /* inside: n.x >= c */
 
 static int clip_poly(const double (*in)[3], int n, const plane *P, double (*out)[3])

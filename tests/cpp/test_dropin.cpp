@@ -177,6 +177,7 @@ int main(int argc, char **argv)
   int spacedim;
   in >> spacedim;
   try {
+    if (spacedim == 22) return run<2, 2, 2>(in, argv[2]);     // codimension 0: a 2D body in the 2D background
     return spacedim == 2 ? run<2, 1, 2>(in, argv[2]) : run<3, 2, 3>(in, argv[2]);
   } catch (const std::exception &e) {
     std::cerr << "exception: " << e.what() << "\n";

@@ -28,7 +28,7 @@ def write_grid(path, bg, im):
     d = bg.spacedim
     V, D = bg.vertices().numpy(), bg.dofs.numpy()
     with open(path, "w") as f:
-        f.write("%d\n%d %d\n" % (d, bg.n_cells, bg.n_dofs))
+        f.write("%d\n%d %d\n" % (22 if im.dim == d else d, bg.n_cells, bg.n_dofs))       # 22: the codimension-0 instantiation <2,2,2>
         for c in range(bg.n_cells):
             f.write(" ".join(repr(float(x)) for x in V[c].ravel()) + " " + " ".join(str(int(x)) for x in D[c]) + "\n")
         cd, cp, cm, cw = (t.numpy() for t in (bg.c_dof, bg.c_ptr, bg.c_master, bg.c_weight))
@@ -85,6 +85,30 @@ def test_cpp_driver_matches_oracle(tmp_path, c_oracle, name, cycle):
     rhs = np.array([float(x) for x in lines[3 + nnz + n_nit:3 + nnz + n_nit + bg.n_dofs]])
     assert np.linalg.norm(rhs - b) <= 1e-13 * np.linalg.norm(b)
     info.ctx.close()
+
+
+@pytest.mark.gpu
+def test_cpp_driver_codimension_zero(tmp_path, c_oracle):
+    """The reference's three calls instantiated as <2,2,2> (a 2D body in the 2D background, code/src/coupling_utilities.cc:72-102)
+    through the drop-in header against the oracle."""
+    from non_matching_test_suite_b200.grids import solid_grid_2d
+    build_driver()
+    bg, _ = make_config("disk", 1, band_only=False)
+    im = solid_grid_2d(12)
+    grid, out = str(tmp_path / "grid.txt"), str(tmp_path / "out.txt")
+    write_grid(grid, bg, im)
+    subprocess.check_call([BIN, grid, out])
+    ref = c_oracle.assemble(bg, im, n1d=3, tol=1e-15)
+    lines = open(out).read().split("\n")
+    n_pairs, area = lines[0].split()
+    assert int(n_pairs) == ref["accepted"].shape[0]
+    assert abs(float(area) - float(im.measure().sum())) <= 1e-13
+    nnz = int(lines[1])
+    assert nnz == ref["col"].shape[0]
+    got = np.array([[float(x) for x in l.split()] for l in lines[2:2 + nnz]])
+    rows = np.repeat(np.arange(bg.n_dofs), np.diff(ref["rowptr"].astype(np.int64)))
+    assert np.array_equal(got[:, 0].astype(np.int64), rows) and np.array_equal(got[:, 1].astype(np.uint32), ref["col"])
+    assert np.linalg.norm(got[:, 2] - ref["val"]) <= 1e-12 * np.linalg.norm(ref["val"])
 
 
 @pytest.mark.gpu
