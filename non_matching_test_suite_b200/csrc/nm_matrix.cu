@@ -335,7 +335,12 @@ constexpr int FAST_ROWS = 64;   // consecutive immersed cells per group
 // GROUP lanes cooperate on one immersed cell: a full warp in 3D (~10 accepted pairs x 8 vertices), 8 lanes
 // in 2D (~3.4 pairs x 4 vertices), so that a warp merges four 2D cells at a time.
 template <int NL, int GROUP, int SLOTS>
-__global__ void __launch_bounds__(256) merge_rows_fast(uint64_t n_im, const uint64_t *__restrict__ cand_ptr,
+// resident blocks per SM the register allocation is held to; measured at sphere cycle 8: no bound (47 registers, 5
+// blocks) 7.06 ms, 6 blocks 6.91 ms, 7 or 8 blocks 7.01 ms, 1 block (the compiler takes more registers) 10.2 ms
+#ifndef NM_MERGE_MINB
+#define NM_MERGE_MINB 6
+#endif
+__global__ void __launch_bounds__(256, NM_MERGE_MINB) merge_rows_fast(uint64_t n_im, const uint64_t *__restrict__ cand_ptr,
                                                        const uint32_t *__restrict__ cand_bg, const uint8_t *__restrict__ acc,
                                                        const double *__restrict__ local, const uint32_t *__restrict__ bg_dofs,
                                                        const int32_t *__restrict__ line_of, const uint64_t *__restrict__ c_ptr,
