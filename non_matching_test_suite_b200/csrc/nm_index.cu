@@ -460,7 +460,10 @@ __global__ void brick_clear(BrickSlot *s, uint32_t cap)
 
 // every cell verifies that it IS a cell of its level grid, claims the slot of its brick and sets its bit
 template <int D>
-__global__ void __launch_bounds__(256) brick_insert(BrickDev B, uint64_t n, const double *__restrict__ box, uint32_t *__restrict__ cell_slot,
+#ifndef NM_BRICK_MINB
+#define NM_BRICK_MINB 8   // index build 2.08 -> 2.00 ms
+#endif
+__global__ void __launch_bounds__(256, NM_BRICK_MINB) brick_insert(BrickDev B, uint64_t n, const double *__restrict__ box, uint32_t *__restrict__ cell_slot,
                                                     uint8_t *__restrict__ cell_bit)
 {
   __shared__ unsigned s_levels;
