@@ -61,7 +61,7 @@ def parse():
     ap.add_argument("--e2e-serial", action="store_true", help="end-to-end leg with a blocking matrix read-back (no overlap with the next step)")
     ap.add_argument("--e2e-global-vectors", action="store_true",
                     help="end-to-end leg with global-length product vectors and row pointers (the round-1 form)")
-    ap.add_argument("--ct-vmult", choices=["replicated", "owned"], default="owned",
+    ap.add_argument("--ct-vmult", choices=["replicated", "owned", "owned-pull"], default="owned",
                     help="result of Ct.vmult on N > 1 GPUs: distributed by contiguous background-dof ranges like the reference's Trilinos "
                          "vector (reduce-scatter semantics, the default) or replicated on every rank (all-reduce semantics)")
     ap.add_argument("--nccl", action="store_true", help="reduce Ct.vmult with NCCL (reduce_scatter / all_reduce) instead of the fused NVLink push")
@@ -382,7 +382,8 @@ def run_problem(args, torch, dist, _lib, ctx, P, rank, world, local, dev, peak, 
     sharded_op = from_context(ctx)
     sharded_op.m, sharded_op.n = bg.n_dofs, im.n_dofs     # the context learns its sizes with the first assembly
     fused = {"op": None, "tried": False, "why": ""}
-    owned = args.ct_vmult == "owned"
+    owned = args.ct_vmult in ("owned", "owned-pull")
+    pull = args.ct_vmult == "owned-pull"
 
     def assemble_device(inp):
         if "verts" in inp:   # all 2^d vertices of every background cell, as mapping.get_vertices() returns them
@@ -414,7 +415,9 @@ def run_problem(args, torch, dist, _lib, ctx, P, rank, world, local, dev, peak, 
             return ctx.spmv(x, transpose=False, out=P.y)
         op = get_fused()
         if owned:
-            return op.vmult_owned(x) if op is not None else sharded_op.vmult_owned(x)
+            if op is None:
+                return sharded_op.vmult_owned(x)
+            return op.vmult_owned_pull(x) if pull else op.vmult_owned(x)
         if op is not None:
             return op.vmult(x)
         ctx.spmv(x, transpose=False, out=P.y)
@@ -542,6 +545,7 @@ def phases_sum(ph):
 def run_e2e(args, torch, dist, _lib, ctx, P, rank, world, dev, timed, get_fused, sharded_op, owned, tot_acc, e_steps):
     from non_matching_test_suite_b200.distributed import owned_dof_range
     bg, im, d = P.bg, P.im, P.d
+    pull = args.ct_vmult == "owned-pull"
     host_in = {k: v.cpu().pin_memory() for k, v in P.dev_in.items()}
     h2d_in = sum(v.numel() * v.element_size() for v in host_in.values())
     nnz_cap = int(ctx.nnz * 1.02) + 1024
@@ -630,7 +634,7 @@ def run_e2e(args, torch, dist, _lib, ctx, P, rank, world, dev, timed, get_fused,
             ctx.local_to_global(_lib.NM_LOCAL_IMMERSED, xh, xg)                   # this shard's lambda entries
             op = get_fused()
             if owned:
-                yy = op.vmult_owned(xg) if op is not None else sharded_op.vmult_owned(xg)
+                yy = (op.vmult_owned_pull(xg) if pull else op.vmult_owned(xg)) if op is not None else sharded_op.vmult_owned(xg)
                 yh[:yy.numel()].copy_(yy)                                         # the slice of the dofs this rank owns
                 y_bytes = yy.numel() * 8
             else:
@@ -745,6 +749,10 @@ def multi_gpu_checks(args, torch, dist, _lib, ctx, P, res, rank, world, local, d
     if op is not None:
         y_own = op.vmult_owned(lam)
         errs["fused_owned"] = float((y_own - y_ref[lo:hi]).abs().max()) / scale if hi > lo else 0.0
+        y_pull = op.vmult_owned_pull(lam)
+        errs["fused_owned_pull"] = float((y_pull - y_ref[lo:hi]).abs().max()) / scale if hi > lo else 0.0
+        y_pull0 = y_pull.clone()
+        errs["fused_owned_pull_not_bitwise_reproducible"] = 0.0 if torch.equal(op.vmult_owned_pull(lam), y_pull0) else 1.0
         y_rep = op.vmult(lam)
         errs["fused_replicated_%s" % ("multicast" if op.multicast else "peer")] = float((y_rep - y_ref).abs().max()) / scale
     y_rs = sharded_op.vmult_owned(lam)
@@ -803,7 +811,10 @@ def ct_vmult_label(world, args, fused):
     if world == 1:
         return "none (1 GPU)"
     why = " (fused path unavailable: %s)" % fused["why"] if fused["why"] else ""
-    if args.ct_vmult == "owned":
+    if args.ct_vmult == "owned-pull" and fused["op"] is not None:
+        return ("result distributed by dof ownership, bit-reproducible: nm_spmv_rows + nm_pull_rows (every owner reads its segment of each "
+                "rank's send buffer over NVLink and adds in rank order; %s)" % fused["op"].sync_kind)
+    if args.ct_vmult in ("owned", "owned-pull"):
         if fused["op"] is not None:
             return "result distributed by dof ownership: nm_spmv_push_owned over NVLink (red.add into the owner's peer-mapped vector; %s)" % fused["op"].sync_kind
         return "result distributed by dof ownership: nccl reduce_scatter" + why

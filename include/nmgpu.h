@@ -233,6 +233,20 @@ int nm_spmv_push(nm_ctx *ctx, const double *x, int n_targets, double *const *y_t
  * ranks' calls the owned range of a rank's vector holds the product.  Same zero-before / synchronise-after contract. */
 int nm_spmv_push_owned(nm_ctx *ctx, const double *x, int n_ranks, double *const *y_targets, uint64_t rows_per_rank);
 
+/* The same distributed result by PULLING, bit-reproducible: every rank writes the results of its stored rows (and their
+ * dof ids, ascending) into a send buffer its peers can read; every owner then adds, source rank after source rank, the
+ * segment of each buffer that falls into its dof range -- coalesced reads over NVLink and plain adds in a fixed order
+ * instead of one 8-byte remote atomic per row (non_matching_test_suite_b200/distributed.py::FusedCtVmult.vmult_owned_pull
+ * shows the set-up: symmetric memory for the send buffers, rank barriers between the steps).  Device pointers.
+ *   nm_spmv_rows      y_rows[r] = (A x)[dof of stored row r] for the rows with entries; optionally their dof ids
+ *   nm_owner_offsets  offsets[k] = first stored row owned by rank k (k = 0..n_ranks), dofs [k rows_per_rank, ...)
+ *   nm_pull_rows      y_owned[id - first_row] += val over the segment [src_offsets[me], src_offsets[me + 1]) of a
+ *                     (peer's) send buffer; an id outside [first_row, first_row + n_owned) -> NM_ERR_INVALID */
+int nm_spmv_rows(nm_ctx *ctx, const double *x, double *y_rows, uint32_t *row_ids, uint64_t *n_rows);
+int nm_owner_offsets(nm_ctx *ctx, int n_ranks, uint64_t rows_per_rank, uint64_t *offsets);
+int nm_pull_rows(nm_ctx *ctx, const uint64_t *src_offsets, int me, const uint32_t *src_row_ids, const double *src_vals, uint64_t first_row,
+                 uint64_t n_owned, double *y_owned);
+
 /* ---- the whole assembly from HOST arrays in one call, uploads overlapped with the computation ----
  * Same result as nm_set_background_boxes + nm_set_immersed + nm_intersect + nm_build_sparsity + nm_assemble with
  * NM_HOST pointers, i.e. what collect_quadratures_on_overlapped_grids (code/src/coupling_utilities.cc:22-69) followed by

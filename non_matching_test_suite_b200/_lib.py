@@ -28,7 +28,7 @@ SYMBOLS = ["nm_version", "nm_create", "nm_destroy", "nm_last_error", "nm_set_bac
            "nm_set_background_dofs", "nm_set_immersed_dofs", "nm_set_immersed", "nm_flag_overlapped_background", "nm_intersect", "nm_get_candidates", "nm_get_pairs", "nm_get_quadrature",
            "nm_get_split_codes", "nm_build_sparsity", "nm_assemble", "nm_assemble_from_quadrature", "nm_assemble_host", "nm_assemble_nitsche", "nm_get_nitsche", "nm_get_csr",
            "nm_get_csr_compact", "nm_sync_downloads", "nm_spmv", "nm_spmv_local", "nm_spmv_local_pair", "nm_local_to_global", "nm_global_to_local",
-           "nm_spmv_push", "nm_spmv_push_owned", "nm_set_finite_elements", "nm_assemble_fe", "nm_schur_solve", "nm_get_info", "nm_measure_fp64_peak", "nm_get_timings", "nm_get_launch_count", "nm_device_bytes", "nm_get_stream"]
+           "nm_spmv_push", "nm_spmv_push_owned", "nm_spmv_rows", "nm_owner_offsets", "nm_pull_rows", "nm_set_finite_elements", "nm_assemble_fe", "nm_schur_solve", "nm_get_info", "nm_measure_fp64_peak", "nm_get_timings", "nm_get_launch_count", "nm_device_bytes", "nm_get_stream"]
 
 
 class NmError(RuntimeError):
@@ -119,6 +119,9 @@ def load():
     L.nm_measure_fp64_peak.argtypes = [P, C.c_double, C.POINTER(C.c_double)]
     L.nm_spmv_push.argtypes = [P, P, I, C.POINTER(C.c_void_p), I]
     L.nm_spmv_push_owned.argtypes = [P, P, I, C.POINTER(C.c_void_p), U64]
+    L.nm_spmv_rows.argtypes = [P, P, P, P, C.POINTER(U64)]
+    L.nm_owner_offsets.argtypes = [P, I, U64, P]
+    L.nm_pull_rows.argtypes = [P, P, I, P, P, U64, U64, P]
     L.nm_get_timings.argtypes = [P, P, I]
     L.nm_device_bytes.argtypes = [P, C.POINTER(U64)]
     L.nm_get_launch_count.argtypes = [P, C.POINTER(U64)]
@@ -434,6 +437,24 @@ class Context:
             out_c = torch.empty(n_cells, dtype=torch.float64, device=x_ct.device)
         self._chk(self.L.nm_spmv_local_pair(self.h, _ptr(x_ct)[0], _ptr(out_ct)[0], _ptr(x_c)[0], _ptr(out_c)[0], _where(x_ct, out_ct, x_c, out_c)))
         return out_ct, out_c
+
+    def spmv_rows(self, x: torch.Tensor, y_rows: torch.Tensor, row_ids: Optional[torch.Tensor] = None) -> int:
+        """y_rows[r] = (A x)[dof of stored row r] for the rows with entries, optionally their dof ids (nm_spmv_rows);
+        device tensors; returns the number of rows."""
+        assert x.is_cuda and y_rows.is_cuda
+        n = C.c_uint64(0)
+        self._chk(self.L.nm_spmv_rows(self.h, C.c_void_p(x.data_ptr()), C.c_void_p(y_rows.data_ptr()),
+                                      C.c_void_p(row_ids.data_ptr()) if row_ids is not None else None, C.byref(n)))
+        return int(n.value)
+
+    def owner_offsets(self, n_ranks: int, rows_per_rank: int, offsets: torch.Tensor):
+        assert offsets.is_cuda and offsets.dtype == torch.int64 and offsets.numel() >= n_ranks + 1
+        self._chk(self.L.nm_owner_offsets(self.h, int(n_ranks), int(rows_per_rank), C.c_void_p(offsets.data_ptr())))
+
+    def pull_rows(self, src_offsets_ptr: int, me: int, src_ids_ptr: int, src_vals_ptr: int, first_row: int, y_owned: torch.Tensor):
+        """y_owned[id - first_row] += val over this rank's segment of a (peer's) send buffer (nm_pull_rows); raw device pointers."""
+        self._chk(self.L.nm_pull_rows(self.h, C.c_void_p(src_offsets_ptr), int(me), C.c_void_p(src_ids_ptr), C.c_void_p(src_vals_ptr),
+                                      int(first_row), int(y_owned.numel()), C.c_void_p(y_owned.data_ptr())))
 
     def local_to_global(self, which: int, local, global_dev: torch.Tensor):
         assert global_dev.is_cuda

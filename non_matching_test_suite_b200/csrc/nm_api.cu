@@ -819,6 +819,91 @@ int nm_spmv_push_owned(nm_ctx *ctx, const double *x, int n_ranks, double *const 
   return NM_OK;
 }
 
+}  // extern "C"
+
+namespace {
+// offsets[k] = first stored row whose dof is >= k * rows_per_rank (rows ascending by dof): the segment of owner k
+__global__ void owner_offsets_kernel(uint64_t n, const uint32_t *__restrict__ ids, int n_ranks, uint64_t rows_per_rank, uint64_t *__restrict__ off)
+{
+  const int k = threadIdx.x;
+  if (k > n_ranks) return;
+  const uint64_t bound = (uint64_t)k * rows_per_rank;
+  uint64_t lo = 0, hi = n;
+  while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if ((uint64_t)ids[mid] < bound) lo = mid + 1; else hi = mid; }
+  off[k] = lo;
+}
+// y[ids[i] - first] += vals[i] over the segment [off[me], off[me + 1]) of a (peer's) send buffer; the ids of one buffer are
+// distinct, so plain adds: the result does not depend on scheduling
+__global__ void pull_rows_kernel(const uint64_t *__restrict__ off, int me, const uint32_t *__restrict__ ids, const double *__restrict__ vals,
+                                 uint64_t first, uint64_t n_owned, double *__restrict__ y, unsigned long long *n_bad)
+{
+  const uint64_t b = off[me], e = off[me + 1];
+  for (uint64_t i = b + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t r = (uint64_t)ids[i] - first;
+    if (r < n_owned) y[r] += vals[i];
+    else atomicAdd(n_bad, 1ULL);
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int nm_spmv_rows(nm_ctx *ctx, const double *x, double *y_rows, uint32_t *row_ids, uint64_t *n_rows)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  if (!x || !y_rows) return nm_fail(ctx, NM_ERR_INVALID, "null vector");
+  NM_TRY(ensure_matrix(ctx));
+  uint64_t n = ctx->n_local_rows;
+  const uint32_t *ids = ctx->row_ids.as<uint32_t>();        // compact-row mode: every stored row has entries
+  if (!ctx->compact_rows) NM_TRY(nm_nonempty_rows(ctx, &n, &ids, nullptr));
+  if (ctx->compact_rows) {
+    NM_TRY(nm_spmv_run(ctx, 0, x, y_rows, NM_SPMV_LOCAL_OUT));
+  } else {
+    NM_TRY(nm_ensure(ctx, ctx->glob_dof, (ctx->n_space_dofs + 1) * 8));
+    NM_TRY(nm_spmv_run(ctx, 0, x, ctx->glob_dof.as<double>()));
+    NM_TRY(nm_local_map(ctx, NM_LOCAL_ROWS, 0, ctx->glob_dof.as<double>(), y_rows));
+  }
+  if (row_ids && n) NM_CUDA(cudaMemcpyAsync(row_ids, ids, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (n_rows) *n_rows = n;
+  NM_SYNC(ctx);
+  return NM_OK;
+}
+
+int nm_owner_offsets(nm_ctx *ctx, int n_ranks, uint64_t rows_per_rank, uint64_t *offsets)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  if (!offsets || n_ranks < 1 || n_ranks > 16) return nm_fail(ctx, NM_ERR_INVALID, "1..16 ranks and an offsets array expected");
+  if (rows_per_rank == 0) return nm_fail(ctx, NM_ERR_INVALID, "rows_per_rank must be positive");
+  NM_TRY(ensure_matrix(ctx));
+  uint64_t n = ctx->n_local_rows;
+  const uint32_t *ids = ctx->row_ids.as<uint32_t>();
+  if (!ctx->compact_rows) NM_TRY(nm_nonempty_rows(ctx, &n, &ids, nullptr));
+  owner_offsets_kernel<<<1, 32, 0, NM_LS(ctx)>>>(n, ids, n_ranks, rows_per_rank, offsets);
+  NM_CUDA(cudaGetLastError());
+  NM_SYNC(ctx);
+  return NM_OK;
+}
+
+int nm_pull_rows(nm_ctx *ctx, const uint64_t *src_offsets, int me, const uint32_t *src_row_ids, const double *src_vals, uint64_t first_row,
+                 uint64_t n_owned, double *y_owned)
+{
+  if (!ctx) return NM_ERR_INVALID;
+  NM_CUDA(cudaSetDevice(ctx->device));
+  if (!src_offsets || !src_row_ids || !src_vals || !y_owned || me < 0 || me >= 16) return nm_fail(ctx, NM_ERR_INVALID, "null array or bad rank");
+  NM_TRY(nm_ensure(ctx, ctx->counters, 64 * sizeof(uint64_t)));
+  unsigned long long *bad = ctx->counters.as<unsigned long long>() + 12;
+  NM_CUDA(cudaMemsetAsync(bad, 0, 8, ctx->stream));
+  pull_rows_kernel<<<(unsigned)ctx->sm_count * 8u, 256, 0, NM_LS(ctx)>>>(src_offsets, me, src_row_ids, src_vals, first_row, n_owned, y_owned, bad);
+  NM_CUDA(cudaGetLastError());
+  unsigned long long h = 0;
+  NM_CUDA(cudaMemcpyAsync(&h, bad, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  NM_SYNC(ctx);
+  if (h) return nm_fail(ctx, NM_ERR_INVALID, "%llu row(s) of the segment lie outside the owned range: offsets and ownership do not match", h);
+  return NM_OK;
+}
+
 int nm_get_info(nm_ctx *ctx, int key, uint64_t *value)
 {
   if (!ctx || !value) return NM_ERR_INVALID;

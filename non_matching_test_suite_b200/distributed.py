@@ -146,6 +146,71 @@ class FusedCtVmult:
         torch.cuda.current_stream().wait_stream(self.stream)
         return self.y[lo:hi]
 
+    def _pull_buffers(self, n_rows: int):
+        """Send buffers every peer can read (symmetric memory): row results, their dof ids, the owner offsets.  Sized once,
+        collectively, for 1.25 x the largest row count of any rank."""
+        if getattr(self, "_pull", None) is not None:
+            if n_rows > self._pull["cap"]:
+                raise RuntimeError("the matrix has more stored rows (%d) than the send buffers hold (%d): create a new FusedCtVmult" %
+                                   (n_rows, self._pull["cap"]))
+            return self._pull
+        import torch.distributed._symmetric_memory as symm_mem
+        dev = torch.device("cuda", self.ctx.device)
+        grp = self.group if self.group is not None else dist.group.WORLD
+        cap = torch.tensor([n_rows], dtype=torch.int64, device=dev)
+        dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=self.group)
+        cap = int(cap.item()) * 5 // 4 + 1024
+        bufs = {}
+        for name, n, dt in (("vals", cap, torch.float64), ("ids", cap, torch.int32), ("off", 32, torch.int64)):
+            t = symm_mem.empty(n, dtype=dt, device=dev)
+            h = symm_mem.rendezvous(t, grp)
+            bufs[name] = (t, h, [int(p) for p in h.buffer_ptrs])
+        self._pull = dict(cap=cap, **bufs)
+        return self._pull
+
+    def vmult_owned_pull(self, lam: torch.Tensor) -> torch.Tensor:
+        """The owned slice of y = A lam by pulling (nm_spmv_rows / nm_owner_offsets / nm_pull_rows): every rank leaves the
+        results of its stored rows and their dof ids in a send buffer; every owner adds the segment of each peer's buffer
+        that falls into its dof range, source rank after source rank -- bulk reads over NVLink and plain adds in a fixed
+        order, so the result is bit-reproducible, unlike the remote atomics of vmult_owned."""
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        lo, hi = owned_dof_range(self.ctx.n_space_dofs, rank, world)
+        import os, time
+        trace = os.environ.get("NMGPU_PULL_TRACE") == "1" and rank == 0
+        t0 = time.perf_counter()
+        marks = []
+
+        def mark(label):
+            nonlocal t0
+            if trace:
+                torch.cuda.synchronize()
+                marks.append("%s %.2f" % (label, (time.perf_counter() - t0) * 1e3))
+                t0 = time.perf_counter()
+        # rows with entries: in compact-row mode (every shard of a multi-GPU run) that is every stored row
+        self.ctx.build_sparsity()                          # (a no-op when the matrix is there)
+        n_rows = self.ctx.info("stored_rows") if self.ctx.info("compact_rows") else self.ctx.n_rows_local()
+        P = self._pull_buffers(n_rows)
+        torch.cuda.current_stream().synchronize()          # lam is ready
+        mark("n_rows")
+        with torch.cuda.stream(self.stream):
+            self.ctx.spmv_rows(lam, P["vals"][0], P["ids"][0])
+            mark("spmv_rows")
+            self.ctx.owner_offsets(world, rows_per_rank(self.ctx.n_space_dofs, world), P["off"][0])
+            self.y[lo:hi].zero_()
+            mark("offsets+zero")
+            self._barrier()                                # every send buffer is complete
+            mark("barrier")
+            for src in range(world):                       # fixed order
+                self.ctx.pull_rows(P["off"][2][src], rank, P["ids"][2][src], P["vals"][2][src], lo, self.y[lo:hi])
+                mark("pull%d" % src)
+            self._barrier()                                # every owner has read my buffer: it may be overwritten
+            mark("barrier")
+        torch.cuda.current_stream().wait_stream(self.stream)
+        if trace:
+            import sys
+            sys.stderr.write("pull trace: " + " | ".join(marks) + "\n")
+        return self.y[lo:hi]
+
     def vmult(self, lam: torch.Tensor) -> torch.Tensor:
         """Replicated y = A lam on every rank.  Two rank barriers bracket the kernel: all vectors are zero
         before anyone adds, and everyone's adds have landed before anyone reads."""

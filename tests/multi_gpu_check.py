@@ -59,13 +59,18 @@ def main():
             scale = float(y_ref.abs().max())
             e_own = float((y_own - y_ref[lo:hi]).abs().max()) / scale if hi > lo else 0.0
             e_rs = float((y_rs - y_ref[lo:hi]).abs().max()) / scale if hi > lo else 0.0
+            # the same slice by pulling (bulk reads of the peers' send buffers, adds in rank order): bit-reproducible
+            y_pull = f.vmult_owned_pull(lam).clone()
+            e_pull = float((y_pull - y_ref[lo:hi]).abs().max()) / scale if hi > lo else 0.0
+            e_rep = 0.0 if torch.equal(f.vmult_owned_pull(lam), y_pull) else 1.0
             t_own = timed(lambda: f.vmult_owned(lam))
+            t_pull = timed(lambda: f.vmult_owned_pull(lam))
             t_rs = timed(lambda: ref_op.vmult_owned(lam))
-            errs = torch.tensor([e_own, e_rs], dtype=torch.float64, device=dev)
+            errs = torch.tensor([e_own, e_rs, e_pull, e_rep], dtype=torch.float64, device=dev)
             dist.all_reduce(errs, op=dist.ReduceOp.MAX)
             if rank == 0:
-                print("world %d  owned slices: rel err fused %.2e  nccl reduce_scatter %.2e   spmv+reduce_scatter %.3f ms  fused owned push %.3f ms" % (
-                    world, float(errs[0]), float(errs[1]), t_rs, t_own), flush=True)
+                print("world %d  owned slices: rel err fused push %.2e  pull %.2e (repeat differs: %d)  nccl reduce_scatter %.2e   spmv+reduce_scatter %.3f ms  "
+                      "fused owned push %.3f ms  pull %.3f ms" % (world, float(errs[0]), float(errs[2]), int(errs[3]), float(errs[1]), t_rs, t_own, t_pull), flush=True)
             ok &= float(errs.max()) < 1e-12
         if not f.multicast and prefer_mc:
             break
