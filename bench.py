@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--e2e-serial", action="store_true", help="end-to-end leg with a blocking matrix read-back (no overlap with the next step)")
     ap.add_argument("--e2e-global-vectors", action="store_true",
                     help="end-to-end leg with global-length product vectors and row pointers (the round-1 form)")
+    ap.add_argument("--e2e-boxes", action="store_true", help="end-to-end leg: send lo/hi corners even when the cells are cubes")
     ap.add_argument("--ct-vmult", choices=["replicated", "owned", "owned-pull"], default="owned",
                     help="result of Ct.vmult on N > 1 GPUs: distributed by contiguous background-dof ranges like the reference's Trilinos "
                          "vector (reduce-scatter semantics, the default) or replicated on every rank (all-reduce semantics)")
@@ -547,6 +548,15 @@ def run_e2e(args, torch, dist, _lib, ctx, P, rank, world, dev, timed, get_fused,
     bg, im, d = P.bg, P.im, P.d
     pull = args.ct_vmult == "owned-pull"
     host_in = {k: v.cpu().pin_memory() for k, v in P.dev_in.items()}
+    # Cubic cells whose upper corner is fl(lo + edge) bit for bit (the reference's hyper_cube refinements: dyadic coordinates)
+    # travel as lower corner + one edge length (nm_host_problem.edge): checked here, once, outside the timed region
+    cubes = False
+    if "lo" in host_in and not args.e2e_boxes:
+        edge = (host_in["hi"][:, 0] - host_in["lo"][:, 0]).contiguous()
+        if bool((host_in["lo"] + edge[:, None] == host_in["hi"]).all()):
+            host_in["edge"] = edge.pin_memory()
+            del host_in["hi"]
+            cubes = True
     h2d_in = sum(v.numel() * v.element_size() for v in host_in.values())
     nnz_cap = int(ctx.nnz * 1.02) + 1024
     rows_cap = int(ctx.n_rows_local() * 1.02) + 1024
@@ -589,8 +599,9 @@ def run_e2e(args, torch, dist, _lib, ctx, P, rank, world, dev, timed, get_fused,
 
     def assemble_host():
         if "lo" in host_in:
-            return ctx.assemble_host(d, host_in["lo"], host_in["hi"], host_in["dofs"], bg.n_dofs, host_in["c_dof"], host_in["c_ptr"],
-                                     host_in["c_master"], host_in["c_weight"], im.dim, host_in["im_verts"], host_in["im_dofs"], im.n_dofs, 3, 1e-15)
+            return ctx.assemble_host(d, host_in["lo"], host_in.get("hi"), host_in["dofs"], bg.n_dofs, host_in["c_dof"], host_in["c_ptr"],
+                                     host_in["c_master"], host_in["c_weight"], im.dim, host_in["im_verts"], host_in["im_dofs"], im.n_dofs, 3, 1e-15,
+                                     edge=host_in.get("edge"))
         ctx.set_background(d, verts=host_in["verts"], dofs=host_in["dofs"], n_dofs=bg.n_dofs, c_dof=host_in["c_dof"], c_ptr=host_in["c_ptr"],
                            c_master=host_in["c_master"], c_weight=host_in["c_weight"])
         ctx.set_immersed(im.dim, im.spacedim, host_in["im_verts"], host_in["im_dofs"], im.n_dofs)
@@ -666,8 +677,8 @@ def run_e2e(args, torch, dist, _lib, ctx, P, rank, world, dev, timed, get_fused,
     tot = torch.tensor([io["h2d"], io["d2h"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tot)
-    api = ("nm_assemble_host (host lo/hi + dofs + constraint lines + immersed grid in one call, uploads overlapped with the phases that do "
-           "not need them yet)" if "lo" in host_in else "nm_set_background (host vertices) + nm_set_immersed + nm_intersect + nm_build_sparsity + nm_assemble")
+    api = ("nm_assemble_host (host %s + dofs + constraint lines + immersed grid in one call, uploads overlapped with the phases that do "
+           "not need them yet)" % ("lower corners + edge lengths of the cubic cells" if cubes else "lo/hi") if "lo" in host_in else "nm_set_background (host vertices) + nm_set_immersed + nm_intersect + nm_build_sparsity + nm_assemble")
     if glob:
         api += " + nm_spmv x2 (global-length host vectors) + nm_get_csr (global row pointers)"
     else:

@@ -274,6 +274,10 @@ typedef struct {
   uint64_t n_im_dofs;
   unsigned degree;              /* quadrature degree, > 0 */
   double tol;
+  const double *edge;           /* optional, [n_bg]: CUBIC cells given by lower corner and edge length -- the upper corner is
+                                 * fl(lo + edge) on every axis and `hi` is not read.  For grids where that holds bitwise
+                                 * (hyper_cube refinements: dyadic coordinates), a third of the geometry bytes less to send.
+                                 * NULL: boxes from lo / hi. */
 } nm_host_problem;
 int nm_assemble_host(nm_ctx *ctx, const nm_host_problem *problem, nm_counts *counts, uint64_t *nnz);
 

@@ -42,7 +42,7 @@ class HostProblem(C.Structure):
     _fields_ = [("spacedim", C.c_int), ("n_bg", C.c_uint64), ("lo", C.c_void_p), ("hi", C.c_void_p), ("bg_dofs", C.c_void_p),
                 ("n_space_dofs", C.c_uint64), ("n_constrained", C.c_uint64), ("c_dof", C.c_void_p), ("c_ptr", C.c_void_p),
                 ("c_master", C.c_void_p), ("c_weight", C.c_void_p), ("dim", C.c_int), ("n_im", C.c_uint64), ("im_verts", C.c_void_p),
-                ("im_dofs", C.c_void_p), ("n_im_dofs", C.c_uint64), ("degree", C.c_uint), ("tol", C.c_double)]
+                ("im_dofs", C.c_void_p), ("n_im_dofs", C.c_uint64), ("degree", C.c_uint), ("tol", C.c_double), ("edge", C.c_void_p)]
 
 
 class FeDesc(C.Structure):
@@ -285,16 +285,17 @@ class Context:
                                                      _ptr(points)[0], _ptr(weights)[0], w))
 
     def assemble_host(self, spacedim, lo, hi, dofs, n_dofs, c_dof, c_ptr, c_master, c_weight, im_dim, im_verts, im_dofs, n_im_dofs,
-                      degree, tol):
+                      degree, tol, edge=None):
         """Whole assembly from HOST arrays (torch CPU tensors, ideally pinned) in one call with the uploads overlapped
         with the computation (nm_assemble_host); afterwards the context is in the same state as after
         set_background(lo, hi, ...) + set_immersed + intersect + build_sparsity + assemble."""
-        arrs = (lo, hi, dofs, c_dof, c_ptr, c_master, c_weight, im_verts, im_dofs)
+        arrs = (lo, hi, dofs, c_dof, c_ptr, c_master, c_weight, im_verts, im_dofs, edge)
         if _where(*arrs) != NM_HOST:
             raise ValueError("assemble_host takes host arrays")
+        # edge [n_bg]: cubic cells as lower corner + edge length (hi = fl(lo + edge) on every axis; `hi` may then be None)
         hp = HostProblem(spacedim, int(lo.shape[0]), _ptr(lo)[0], _ptr(hi)[0], _ptr(dofs)[0], int(n_dofs), int(c_dof.shape[0]),
                          _ptr(c_dof)[0], _ptr(c_ptr)[0], _ptr(c_master)[0], _ptr(c_weight)[0], im_dim, int(im_verts.shape[0]),
-                         _ptr(im_verts)[0], _ptr(im_dofs)[0], int(n_im_dofs), int(degree), float(tol))
+                         _ptr(im_verts)[0], _ptr(im_dofs)[0], int(n_im_dofs), int(degree), float(tol), _ptr(edge)[0])
         cnt, nnz = Counts(), C.c_uint64(0)
         self._chk(self.L.nm_assemble_host(self.h, C.byref(hp), C.byref(cnt), C.byref(nnz)))
         self.spacedim, self.n_bg, self.n_space_dofs = spacedim, int(lo.shape[0]), int(n_dofs)

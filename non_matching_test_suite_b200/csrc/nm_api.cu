@@ -8,7 +8,8 @@
 
 #include "nm_common.cuh"
 
-int nm_bg_layout(nm_ctx *ctx, int d, uint64_t n, const double *verts_dev, const double *lo_dev, const double *hi_dev);
+int nm_bg_layout(nm_ctx *ctx, int d, uint64_t n, const double *verts_dev, const double *lo_dev, const double *hi_dev,
+                 const double *edge_dev = nullptr);
 int nm_constraints_layout(nm_ctx *ctx, const uint32_t *c_dof_dev);  // c_dof_dev: [n_constrained] constrained dof ids on the device
 int nm_accepted_index(nm_ctx *ctx, uint64_t **idx_dev);
 int nm_c_rows_compact(nm_ctx *ctx, uint64_t *rowptr_dev, uint32_t *col_dev, double *val_dev);
@@ -646,7 +647,7 @@ int nm_assemble_host(nm_ctx *ctx, const nm_host_problem *P, nm_counts *counts, u
   if (P->degree == 0) return nm_fail(ctx, NM_ERR_INVALID, "Invalid quadrature degree.");  // coupling_utilities.cc:32
   if (P->n_bg >= 0xffffffffULL || P->n_space_dofs >= 0xffffffffULL || P->n_im >= 0xffffffffULL || P->n_im_dofs >= 0xffffffffULL)
     return nm_fail(ctx, NM_ERR_UNSUPPORTED, "cell / DoF counts must fit 32 bits");
-  if ((P->n_bg && (!P->lo || !P->hi || !P->bg_dofs)) || (P->n_im && (!P->im_verts || !P->im_dofs)))
+  if ((P->n_bg && (!P->lo || (!P->hi && !P->edge) || !P->bg_dofs)) || (P->n_im && (!P->im_verts || !P->im_dofs)))
     return nm_fail(ctx, NM_ERR_INVALID, "null grid arrays");
   if (P->n_constrained && (!P->c_dof || !P->c_ptr)) return nm_fail(ctx, NM_ERR_INVALID, "null constraint arrays");
   const uint64_t n_masters = P->n_constrained ? P->c_ptr[P->n_constrained] : 0;
@@ -684,7 +685,9 @@ int nm_assemble_host(nm_ctx *ctx, const nm_host_problem *P, nm_counts *counts, u
   };
   double *lo_dev = ctx->h2d_stage.as<double>(), *hi_dev = reinterpret_cast<double *>(ctx->h2d_stage.as<char>() + b_box_al);
   NM_CUDA(h2d(lo_dev, P->lo, b_box));
-  NM_CUDA(h2d(hi_dev, P->hi, b_box));
+  // cubic cells: one edge length per cell travels instead of the upper corners (a third of the geometry bytes less)
+  if (P->edge) NM_CUDA(h2d(hi_dev, P->edge, P->n_bg * sizeof(double)));
+  else NM_CUDA(h2d(hi_dev, P->hi, b_box));
   NM_CUDA(cudaEventRecord(ctx->ev_copy[0], cs));
   NM_CUDA(h2d(ctx->im_verts.p, P->im_verts, P->n_im * NVI * d * sizeof(double)));
   NM_CUDA(h2d(ctx->im_dofs.p, P->im_dofs, P->n_im * sizeof(uint32_t)));
@@ -702,7 +705,7 @@ int nm_assemble_host(nm_ctx *ctx, const nm_host_problem *P, nm_counts *counts, u
   NM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[0], 0));
   {
     PhaseTimer t(ctx, NM_T_UPLOAD);
-    NM_TRY(nm_bg_layout(ctx, d, P->n_bg, nullptr, lo_dev, hi_dev));
+    NM_TRY(nm_bg_layout(ctx, d, P->n_bg, nullptr, lo_dev, P->edge ? nullptr : hi_dev, P->edge ? hi_dev : nullptr));
     t.stop();
   }
   ctx->bg_set = true;

@@ -153,14 +153,16 @@ __device__ inline void BoxStats::reduce_to(double *__restrict__ out) const
 // (grid-stride, 256 threads per block, out[gridDim.x][8])
 template <int D>
 __global__ void __launch_bounds__(256) bg_boxes_from_lohi_stats(uint64_t n, const double *__restrict__ lo, const double *__restrict__ hi,
-                                                                double *__restrict__ box, int *bad, double *__restrict__ out)
+                                                                const double *__restrict__ edge, double *__restrict__ box, int *bad,
+                                                                double *__restrict__ out)
 {
   BoxStats S;
   int n_bad = 0;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     double l[3] = {0, 0, 0}, h[3] = {0, 0, 0};
+    const double e = edge ? edge[i] : 0.0;     // cubic cells: the upper corner is fl(lo + edge) on every axis
 #pragma unroll
-    for (int k = 0; k < D; ++k) { l[k] = lo[i * D + k]; h[k] = hi[i * D + k]; n_bad += !(l[k] <= h[k]); }
+    for (int k = 0; k < D; ++k) { l[k] = lo[i * D + k]; h[k] = edge ? __dadd_rn(l[k], e) : hi[i * D + k]; n_bad += !(l[k] <= h[k]); }
     double4 *b = reinterpret_cast<double4 *>(box + i * 8);
     b[0] = make_double4(l[0], l[1], l[2], 0.0);
     b[1] = make_double4(h[0], h[1], h[2], 0.0);
@@ -764,7 +766,7 @@ int nm_exclusive_scan_u32_to_u64(nm_ctx *ctx, const uint32_t *in, uint64_t *out,
   return NM_OK;
 }
 
-int nm_bg_layout(nm_ctx *ctx, int d, uint64_t n, const double *verts_dev, const double *lo_dev, const double *hi_dev)
+int nm_bg_layout(nm_ctx *ctx, int d, uint64_t n, const double *verts_dev, const double *lo_dev, const double *hi_dev, const double *edge_dev)
 {
   NM_TRY(nm_ensure(ctx, ctx->bg_box, n * 8 * sizeof(double)));
   NM_TRY(nm_ensure(ctx, ctx->counters, 64 * sizeof(uint64_t)));
@@ -778,8 +780,8 @@ int nm_bg_layout(nm_ctx *ctx, int d, uint64_t n, const double *verts_dev, const 
       else bg_boxes_from_verts<3><<<B, T, 0, NM_LS(ctx)>>>(n, verts_dev, ctx->bg_box.as<double>(), bad);
     } else {
       NM_TRY(nm_ensure(ctx, ctx->idx_tmp, NM_STATS_BLOCKS * NM_STATS_W * sizeof(double)));
-      if (d == 2) bg_boxes_from_lohi_stats<2><<<NM_STATS_BLOCKS, 256, 0, NM_LS(ctx)>>>(n, lo_dev, hi_dev, ctx->bg_box.as<double>(), bad, ctx->idx_tmp.as<double>());
-      else bg_boxes_from_lohi_stats<3><<<NM_STATS_BLOCKS, 256, 0, NM_LS(ctx)>>>(n, lo_dev, hi_dev, ctx->bg_box.as<double>(), bad, ctx->idx_tmp.as<double>());
+      if (d == 2) bg_boxes_from_lohi_stats<2><<<NM_STATS_BLOCKS, 256, 0, NM_LS(ctx)>>>(n, lo_dev, hi_dev, edge_dev, ctx->bg_box.as<double>(), bad, ctx->idx_tmp.as<double>());
+      else bg_boxes_from_lohi_stats<3><<<NM_STATS_BLOCKS, 256, 0, NM_LS(ctx)>>>(n, lo_dev, hi_dev, edge_dev, ctx->bg_box.as<double>(), bad, ctx->idx_tmp.as<double>());
       ctx->bg_stats_ready = true;
     }
     NM_CUDA(cudaGetLastError());

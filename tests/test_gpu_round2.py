@@ -322,3 +322,22 @@ def test_inputs_read_in_place_give_the_same_matrix_and_stay_untouched(name, cycl
     assert all(torch.equal(a, b) for a, b in zip(ctx.csr(), want))
     assert ctx.device_bytes() > held_inplace
     ctx.close(); ref.close()
+
+
+@pytest.mark.parametrize("name,cycle", [("sphere", 3), ("disk", 5)])
+def test_assemble_host_with_cubic_cells_as_corner_and_edge(name, cycle):
+    """nm_host_problem.edge: cubic cells sent as lower corner + edge length give the matrix of the lo / hi form bit for bit
+    (the upper corner is fl(lo + edge), exact for the dyadic coordinates of a hyper_cube refinement)."""
+    bg, im = make_config(name, cycle)
+    d = bg.spacedim
+    edge = (bg.hi[:, 0] - bg.lo[:, 0]).contiguous()
+    assert bool((bg.lo + edge[:, None] == bg.hi).all())
+    args = (bg.dofs.to(torch.int32).contiguous(), bg.n_dofs, bg.c_dof.to(torch.int32).contiguous(), bg.c_ptr.contiguous(),
+            bg.c_master.to(torch.int32).contiguous(), bg.c_weight.contiguous(), im.dim, im.verts.contiguous(), im.dofs.to(torch.int32).contiguous(),
+            im.n_dofs, 3, 1e-15)
+    a, b = _lib.Context(0), _lib.Context(0)
+    ca = a.assemble_host(d, bg.lo.contiguous(), bg.hi.contiguous(), *args)
+    cb = b.assemble_host(d, bg.lo.contiguous(), None, *args, edge=edge)
+    assert ca == cb
+    assert all(torch.equal(x, y) for x, y in zip(a.csr(), b.csr()))
+    a.close(); b.close()
