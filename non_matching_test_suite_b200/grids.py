@@ -310,6 +310,42 @@ def build_level_map(d: int, initial_level: int, band_rounds: int, blo: torch.Ten
     return LevelMap(d, lf, lvl)
 
 
+def graded_config(name: str, cycle: int, stripe: int = 8, band_only: bool = True, device="cpu", dirichlet: bool = True):
+    """A variant of config `name` whose background changes level ACROSS the interface: one more refinement round is applied
+    only around every other block of `stripe` immersed cells (of the coarse grid the band rounds see), so that hanging nodes
+    sit on cut cells all along the interface -- the adaptive refinement the drivers offer (`Use space refinement`), which
+    the shipped parameter files leave off.  Exercises the constraint expansion of the assembly at scale."""
+    cfg = CONFIGS[name]
+    d = cfg["d"]
+    if name == "disk":
+        im0, im = circle_grid(32, device=device), circle_grid(32 * (1 << cycle), device=device)
+    elif name == "flower":
+        im0, im = flower_grid(0, device=device), flower_grid(cycle, device=device)
+    else:
+        im0, im = sphere_grid(2, device=device), sphere_grid(4 * (1 << cycle), device=device)
+    blo0, bhi0 = im0.boxes()
+    rounds = cfg["band_rounds"]
+    lf = 4 + rounds + 1
+    n = 1 << lf
+    lvl = torch.full((n,) * d, 4, dtype=torch.int16, device=blo0.device)
+    pick = (torch.arange(im0.n_cells, device=blo0.device) // stripe) % 2 == 0
+    for r in range(rounds + 1):
+        cur = 4 + r
+        lo_r, hi_r = (blo0, bhi0) if r < rounds else (blo0[pick], bhi0[pick])
+        pos = overlapping_cells(lo_r, hi_r, cur)
+        w = 1 << (lf - cur)
+        mark = torch.zeros((1 << cur,) * d, dtype=torch.bool, device=blo0.device)
+        mark[tuple(pos[:, k] for k in range(d))] = True
+        for k in range(d):
+            mark = mark.repeat_interleave(w, dim=k)
+        # the extra round refines only leaves that did reach the band level
+        lvl = torch.where(mark & (lvl == cur), torch.tensor(cur + 1, dtype=torch.int16, device=blo0.device), lvl)
+        lvl = _balance(lvl, d, 4, lf)
+    lmap = LevelMap(d, lf, lvl)
+    bg = background_grid(lmap, cycle, near=im.boxes() if band_only else None, dirichlet=dirichlet)
+    return bg, im
+
+
 def _balance(lvl: torch.Tensor, d: int, l0: int, lf: int) -> torch.Tensor:
     """Enforce |level difference| <= 1 across faces (2D, 3D) and edges (3D)."""
     import torch.nn.functional as F
