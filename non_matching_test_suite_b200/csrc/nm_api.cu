@@ -93,7 +93,7 @@ static std::vector<DevBuf *> all_buffers(nm_ctx *c)
   return {&c->bg_box, &c->bg_dofs, &c->line_of, &c->c_ptr, &c->c_master, &c->c_weight, &c->im_verts, &c->im_poly, &c->im_dofs, &c->im_split,
           &c->im_measure, &c->idx_next, &c->idx_extra_bg, &c->idx_hash, &c->idx_tmp, &c->cand_ptr, &c->cand_tmp, &c->cand_im, &c->cand_bg,
           &c->cand_sumw, &c->cand_local, &c->cand_nq, &c->cand_acc, &c->counters, &c->c_rowstart, &c->c_rowlen, &c->c_col, &c->c_val,
-          &c->a_rowptr, &c->a_rowptr32, &c->a_col, &c->a_val, &c->a_cursor, &c->scan_tmp, &c->scratch_a, &c->scratch_b, &c->stage_x,
+          &c->a_rowptr, &c->a_rowptr32, &c->a_col, &c->a_val, &c->a_cursor, &c->t_rec, &c->scan_tmp, &c->scratch_a, &c->scratch_b, &c->stage_x,
           &c->stage_y, &c->stage_x2, &c->stage_y2, &c->h2d_stage, &c->nit_cnt, &c->nit_keys, &c->nit_vals, &c->nit_rkeys, &c->nit_rvals, &c->nit_rowptr,
           &c->nit_col, &c->nit_val, &c->nit_rhs, &c->row_bits, &c->row_prefix, &c->row_ids, &c->out_ids, &c->out_len, &c->glob_im,
           &c->glob_dof, &c->brk_hdr, &c->brk_bit, &c->clip_lut, &c->fe_bg_dofs, &c->fe_im_dofs, &c->fe_pairs, &c->fe_qoff,

@@ -128,6 +128,7 @@ struct nm_ctx {
   DevBuf a_col;     // u32 (immersed dof)
   DevBuf a_val;     // f64
   DevBuf a_cursor;  // scratch
+  DevBuf t_rec;     // (value, column) records between the transpose scatter and its row sort
   // compact-row mode (sharded grids: the global dof count is far larger than what this rank touches): the stored
   // orientation keeps only the rows with entries; a_rowptr has n_local_rows + 1 entries and row r is global dof
   // row_ids[r].  row_bits = bitmap of touched dofs, row_prefix[w] = touched dofs before word w (rank queries).

@@ -334,11 +334,16 @@ constexpr int FAST_ROWS = 64;   // consecutive immersed cells per group
 
 // GROUP lanes cooperate on one immersed cell: a full warp in 3D (~10 accepted pairs x 8 vertices), 8 lanes
 // in 2D (~3.4 pairs x 4 vertices), so that a warp merges four 2D cells at a time.
-template <int NL, int GROUP, int SLOTS>
+// LINES = false: the caller declared no constraint line at all (band-only backgrounds, unconstrained spaces) -- the
+// per-contribution line lookup, a dependent scattered load in the middle of the chain, and the master loop drop out.
+template <int NL, int GROUP, int SLOTS, bool LINES>
 // resident blocks per SM the register allocation is held to; measured at sphere cycle 8: no bound (47 registers, 5
 // blocks) 7.06 ms, 6 blocks 6.91 ms, 7 or 8 blocks 7.01 ms, 1 block (the compiler takes more registers) 10.2 ms
 #ifndef NM_MERGE_MINB
 #define NM_MERGE_MINB 6
+#endif
+#ifndef NM_MERGE_NOLINES_KERNEL
+#define NM_MERGE_NOLINES_KERNEL 1
 #endif
 __global__ void __launch_bounds__(256, NM_MERGE_MINB) merge_rows_fast(uint64_t n_im, const uint64_t *__restrict__ cand_ptr,
                                                        const uint32_t *__restrict__ cand_bg, const uint8_t *__restrict__ acc,
@@ -398,24 +403,26 @@ __global__ void __launch_bounds__(256, NM_MERGE_MINB) merge_rows_fast(uint64_t n
             atomicOr(problem, 4u);
             failed = true;
           } else {
-            ln = line_of[dof];
+            if (LINES) ln = line_of[dof];
             s = hash_claim<SLOTS>(keys, dof, claimed, failed);
           }
         }
         // keep_constrained_entries: a constrained row stays in the pattern as a structural zero (its slot is claimed,
         // nothing is added); its value goes to the masters of the line (none for a Dirichlet row)
         group_accumulate(gmask, gbase + lane, vals, (on_e && !failed && ln < 0) ? s : NO_SLOT, v);
-        const unsigned nm = (on_e && !failed && ln >= 0) ? (unsigned)(c_ptr[ln + 1] - c_ptr[ln]) : 0u;
-        const unsigned nm_max = __reduce_max_sync(gmask, nm);
-        for (unsigned k = 0; k < nm_max; ++k) {
-          unsigned t = NO_SLOT;
-          double wv = 0.0;
-          if (k < nm && !failed) {
-            const uint64_t kk = c_ptr[ln] + k;
-            t = hash_claim<SLOTS>(keys, c_master[kk], claimed, failed);
-            wv = c_weight[kk] * v;
+        if constexpr (LINES) {
+          const unsigned nm = (on_e && !failed && ln >= 0) ? (unsigned)(c_ptr[ln + 1] - c_ptr[ln]) : 0u;
+          const unsigned nm_max = __reduce_max_sync(gmask, nm);
+          for (unsigned k = 0; k < nm_max; ++k) {
+            unsigned t = NO_SLOT;
+            double wv = 0.0;
+            if (k < nm && !failed) {
+              const uint64_t kk = c_ptr[ln] + k;
+              t = hash_claim<SLOTS>(keys, c_master[kk], claimed, failed);
+              wv = c_weight[kk] * v;
+            }
+            group_accumulate(gmask, gbase + lane, vals, failed ? NO_SLOT : t, wv);
           }
-          group_accumulate(gmask, gbase + lane, vals, failed ? NO_SLOT : t, wv);
         }
       }
     }
@@ -672,6 +679,111 @@ __global__ void __launch_bounds__(256, NM_TSORT_MINB) t_sort_rows(uint64_t n_row
   }
 }
 
+// ---- transpose with 32-bit offsets (nnz < 2^32): one scattered access less per entry on each side ----
+// `ends[r + 1]` starts as the first slot of row r and is the cursor the scatter advances, so a position costs ONE atomic
+// (no separate row-offset load), and when the scatter is done `ends` is the 32-bit row-offset array of the matrix.
+#ifndef NM_T_ABS
+#define NM_T_ABS 1
+#endif
+// NM_T_REC: the scatter writes one 16-byte (value, column) record per entry -- one sector instead of two -- and the row
+// sort, which rewrites every entry anyway, splits the records into the column and value arrays.
+#ifndef NM_T_REC
+#define NM_T_REC 1
+#endif
+struct __align__(16) TRec { double v; uint32_t c; uint32_t pad; };
+
+__global__ void t_starts32(uint64_t n_rows, const uint64_t *__restrict__ rowptr, uint32_t *__restrict__ ends)
+{
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_rows) ends[r + 1] = (uint32_t)rowptr[r];
+  if (r == 0) ends[0] = 0u;
+}
+
+template <int LANES, bool REC>
+__global__ void __launch_bounds__(256, NM_TSCATTER_MINB) t_scatter32(uint64_t n_im, const uint64_t *__restrict__ rowstart, const uint32_t *__restrict__ rowlen,
+                          const uint32_t *__restrict__ col, const double *__restrict__ val, const uint32_t *__restrict__ im_dofs,
+                          RowMap map, uint32_t *__restrict__ ends, uint32_t *__restrict__ a_col, double *__restrict__ a_val, TRec *__restrict__ rec)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t m = t / LANES;
+  const unsigned l = t % LANES;
+  if (m >= n_im) return;
+  const uint64_t s = rowstart[m];
+  const uint32_t n = rowlen[m];
+  const uint32_t c = im_dofs[m];
+  for (uint32_t k0 = l; k0 < n; k0 += LANES * T_UNROLL) {
+    uint32_t r[T_UNROLL];
+    double v[T_UNROLL];
+    uint32_t pos[T_UNROLL];
+#pragma unroll
+    for (int u = 0; u < T_UNROLL; ++u) {
+      const uint32_t k = k0 + u * LANES;
+      const bool ok = k < n;
+      r[u] = ok ? col[s + k] : 0xffffffffu;
+      v[u] = ok ? val[s + k] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < T_UNROLL; ++u)
+      if (r[u] != 0xffffffffu) { r[u] = map(r[u]); }
+#pragma unroll
+    for (int u = 0; u < T_UNROLL; ++u)
+      if (k0 + u * LANES < n) pos[u] = atomicAdd(&ends[r[u] + 1], 1u);
+#pragma unroll
+    for (int u = 0; u < T_UNROLL; ++u)
+      if (k0 + u * LANES < n) {
+        if (REC) {
+          uint4 w;
+          w.x = (uint32_t)__double2loint(v[u]); w.y = (uint32_t)__double2hiint(v[u]); w.z = c; w.w = 0u;
+          *reinterpret_cast<uint4 *>(rec + pos[u]) = w;
+        } else { a_col[pos[u]] = c; a_val[pos[u]] = v[u]; }
+      }
+  }
+}
+
+template <bool REC>
+__global__ void __launch_bounds__(256, NM_TSORT_MINB) t_sort_rows32(uint64_t n_rows, const uint32_t *__restrict__ rowptr, uint32_t *__restrict__ col,
+                                                                    double *__restrict__ val, const TRec *__restrict__ rec)
+{
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const uint32_t s = rowptr[r], e = rowptr[r + 1];
+  const uint32_t n = e - s;
+  if (n == 0 || (!REC && n == 1)) return;
+  if (n <= 8) {
+    uint32_t k[8];
+    double v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool ok = (uint32_t)i < n;
+      if (REC) {
+        uint4 w = make_uint4(0u, 0u, 0xffffffffu, 0u);
+        if (ok) w = *reinterpret_cast<const uint4 *>(rec + s + i);
+        k[i] = w.z; v[i] = __hiloint2double((int)w.y, (int)w.x);
+      } else { k[i] = ok ? col[s + i] : 0xffffffffu; v[i] = ok ? val[s + i] : 0.0; }
+    }
+    cswap(k[0], v[0], k[1], v[1]); cswap(k[2], v[2], k[3], v[3]); cswap(k[4], v[4], k[5], v[5]); cswap(k[6], v[6], k[7], v[7]);
+    cswap(k[0], v[0], k[2], v[2]); cswap(k[1], v[1], k[3], v[3]); cswap(k[4], v[4], k[6], v[6]); cswap(k[5], v[5], k[7], v[7]);
+    cswap(k[1], v[1], k[2], v[2]); cswap(k[5], v[5], k[6], v[6]); cswap(k[0], v[0], k[4], v[4]); cswap(k[3], v[3], k[7], v[7]);
+    cswap(k[1], v[1], k[5], v[5]); cswap(k[2], v[2], k[6], v[6]);
+    cswap(k[1], v[1], k[4], v[4]); cswap(k[3], v[3], k[6], v[6]);
+    cswap(k[2], v[2], k[4], v[4]); cswap(k[3], v[3], k[5], v[5]);
+    cswap(k[3], v[3], k[4], v[4]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if ((uint32_t)i < n) { col[s + i] = k[i]; val[s + i] = v[i]; }
+    return;
+  }
+  if (REC)
+    for (uint32_t i = s; i < e; ++i) { const TRec q = rec[i]; col[i] = q.c; val[i] = q.v; }
+  for (uint32_t i = s + 1; i < e; ++i) {
+    const uint32_t c = col[i];
+    const double v = val[i];
+    uint32_t j = i;
+    while (j > s && col[j - 1] > c) { col[j] = col[j - 1]; val[j] = val[j - 1]; --j; }
+    col[j] = c; val[j] = v;
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // SpMV: LANES threads per row, FP64, shuffle reduction.  Each lane issues UNROLL independent
 // (col, val, x[col]) load chains before the first FMA: with rows of 3..40 entries the kernels are
@@ -910,10 +1022,18 @@ static int matrix_build_fast(nm_ctx *ctx, bool *done)
           ctx->c_val.as<double>(), capacity, cursor, problem, dof_marks, ctx->compact_rows ? 1 : 0, (uint32_t)n_rows, (unsigned)rpg, chunk);
     };
     bool launched = false;
+    const bool lines = NM_MERGE_NOLINES_KERNEL == 0 || ctx->n_constrained != 0;
     if constexpr (NL == 8) {
-      if (attempt == 0) { launch(merge_rows_fast<NL, GROUP, 128>); ctx->merge_slots = 128; launched = true; }
+      if (attempt == 0) {
+        if (lines) launch(merge_rows_fast<NL, GROUP, 128, true>); else launch(merge_rows_fast<NL, GROUP, 128, false>);
+        ctx->merge_slots = 128; launched = true;
+      }
     }
-    if (!launched) { launch(merge_rows_fast<NL, GROUP, (NL == 8 ? 256 : 64)>); ctx->merge_slots = NL == 8 ? 256 : 64; }
+    if (!launched) {
+      constexpr int SL = NL == 8 ? 256 : 64;
+      if (lines) launch(merge_rows_fast<NL, GROUP, SL, true>); else launch(merge_rows_fast<NL, GROUP, SL, false>);
+      ctx->merge_slots = SL;
+    }
     km.stop();
     NM_CUDA(cudaGetLastError());
     NM_CUDA(cudaMemcpyAsync(&h_problem, problem, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1065,6 +1185,30 @@ static int transpose_rows(nm_ctx *ctx, bool counts_ready)
   ctx->nnz = nnz;
   NM_TRY(nm_ensure(ctx, ctx->a_col, (nnz + 1) * sizeof(uint32_t)));
   NM_TRY(nm_ensure(ctx, ctx->a_val, (nnz + 1) * sizeof(double)));
+  if (NM_T_ABS && nnz < 0xffffffffULL) {
+    // 32-bit offsets: the offset array doubles as the scatter cursor (see t_starts32)
+    ctx->a_rowptr32_valid = false;
+    NM_TRY(nm_ensure(ctx, ctx->a_rowptr32, (n_rows + 2) * sizeof(uint32_t)));
+    if (NM_T_REC) NM_TRY(nm_ensure(ctx, ctx->t_rec, (nnz + 1) * sizeof(TRec)));
+    uint32_t *ends = ctx->a_rowptr32.as<uint32_t>();
+    TRec *rec = NM_T_REC ? ctx->t_rec.as<TRec>() : nullptr;
+    t_starts32<<<nm_blocks(n_rows + 1, 256), 256, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr.as<uint64_t>(), ends);
+    NM_CUDA(cudaGetLastError());
+    if (n_im) {
+      t_scatter32<TL, NM_T_REC != 0><<<nm_blocks(n_im * TL, 256), 256, 0, NM_LS(ctx)>>>(
+          n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(), ctx->c_val.as<double>(),
+          ctx->crow_dofs->as<uint32_t>(), map, ends, ctx->a_col.as<uint32_t>(), ctx->a_val.as<double>(), rec);
+      NM_CUDA(cudaGetLastError());
+    }
+    if (n_rows) {
+      t_sort_rows32<NM_T_REC != 0><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, ends, ctx->a_col.as<uint32_t>(), ctx->a_val.as<double>(), rec);
+      NM_CUDA(cudaGetLastError());
+    }
+    ctx->a_rowptr32_valid = true;
+    tt.stop();
+    ctx->matrix_valid = true;
+    return NM_OK;
+  }
   if (n_im) {
     t_scatter<TL><<<nm_blocks(n_im * TL, 256), 256, 0, NM_LS(ctx)>>>(
         n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(), ctx->c_val.as<double>(),
