@@ -230,7 +230,7 @@ __device__ __forceinline__ void group_accumulate(unsigned gmask, unsigned wlane,
   const unsigned grp = __match_any_sync(gmask, has ? slot : (0x80000000u | wlane));   // a lane without a contribution matches nobody
   const bool leader = has && (unsigned)(__ffs(grp) - 1) == wlane;
   const unsigned mx = __reduce_max_sync(gmask, has ? (unsigned)__popc(grp) : 1u);
-  double sum = v;
+  double sum = leader ? vals[slot] + v : 0.0;   // ((slot + v_a) + v_b) + ...: the order a sequential loop over the contributions takes
   unsigned rest = grp & (grp - 1u);   // the other lanes of my slot, ascending
   for (unsigned j = 1; j < mx; ++j) {
     const bool more = rest != 0u;
@@ -239,7 +239,7 @@ __device__ __forceinline__ void group_accumulate(unsigned gmask, unsigned wlane,
     const double o = __shfl_sync(gmask, v, src);
     if (leader && more) sum += o;
   }
-  if (leader) vals[slot] += sum;
+  if (leader) vals[slot] = sum;
   __syncwarp(gmask);
 }
 
@@ -342,6 +342,12 @@ template <int NL, int GROUP, int SLOTS, bool LINES>
 #ifndef NM_MERGE_MINB
 #define NM_MERGE_MINB 6
 #endif
+#ifndef NM_MERGE_CBG
+#define NM_MERGE_CBG 2
+#endif
+#ifndef NM_MERGE_PAIRSTEPS
+#define NM_MERGE_PAIRSTEPS 1
+#endif
 #ifndef NM_MERGE_NOLINES_KERNEL
 #define NM_MERGE_NOLINES_KERNEL 1
 #endif
@@ -359,17 +365,30 @@ __global__ void __launch_bounds__(256, NM_MERGE_MINB) merge_rows_fast(uint64_t n
   constexpr unsigned CAP = SLOTS * 3 / 4;         // distinct dofs a group accepts
   __shared__ unsigned s_keys[NG][SLOTS];
   __shared__ double s_vals[NG][SLOTS];
-  __shared__ unsigned s_list[NG][SLOTS];
+  __shared__ unsigned short s_list[NG][SLOTS];   // slot of every distinct dof (SLOTS <= 256)
   __shared__ __align__(16) unsigned s_dkey[NG][SLOTS];
   __shared__ unsigned s_cand[NG][GROUP];
+#if NM_MERGE_CBG == 1
+  __shared__ unsigned s_cbg[NG][GROUP];   // background cell of every accepted pair of the chunk (loaded coalesced, once)
+#elif NM_MERGE_CBG == 2
+  // DoF rows of the accepted pairs of the chunk: every lane fetches the row of its own pair (one 32-byte sector) while
+  // the chunk is compacted, so the contribution rounds below carry no dependent global load
+  __shared__ __align__(16) unsigned s_dofs[NG][GROUP * NL];
+#endif
   const unsigned g = threadIdx.x / GROUP, lane = threadIdx.x % GROUP;
   const unsigned gbase = (threadIdx.x & 31) - lane;                      // first lane of the group inside its warp
   const unsigned gmask = GROUP == 32 ? 0xffffffffu : (((1u << GROUP) - 1u) << gbase);
   unsigned *keys = s_keys[g];
   double *vals = s_vals[g];
-  unsigned *list = s_list[g];
+  unsigned short *list = s_list[g];
   unsigned *dkey = s_dkey[g];
   unsigned *cands = s_cand[g];
+#if NM_MERGE_CBG == 1
+  unsigned *cbg = s_cbg[g];
+#elif NM_MERGE_CBG == 2
+  unsigned *sdofs = s_dofs[g];
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(bg_dofs) & 15u) == 0u;   // a table adopted in place may sit at any 4-byte address
+#endif
   const uint64_t m0 = ((uint64_t)blockIdx.x * NG + g) * rows_per_group;
   uint64_t chunk_pos = 0;
   unsigned chunk_left = 0;
@@ -385,7 +404,41 @@ __global__ void __launch_bounds__(256, NM_MERGE_MINB) merge_rows_fast(uint64_t n
       const uint64_t p = base + lane;
       const bool on = p < p1 && acc[p];
       const unsigned bal = (__ballot_sync(gmask, on) >> gbase) & (GROUP == 32 ? 0xffffffffu : ((1u << GROUP) - 1u));
+#if NM_MERGE_CBG == 1
+      if (on) { const unsigned k = __popc(bal & ((1u << lane) - 1u)); cands[k] = lane; cbg[k] = cand_bg[p]; }
+#elif NM_MERGE_CBG == 2
+      if (on) {
+        const unsigned k = __popc(bal & ((1u << lane) - 1u));
+        cands[k] = lane;
+        const uint32_t *row = bg_dofs + (uint64_t)cand_bg[p] * NL;
+        uint32_t rv[NL];
+        if (vec_ok) {
+#pragma unroll
+          for (int j = 0; j < NL / 4; ++j) {
+            const uint4 q4 = reinterpret_cast<const uint4 *>(row)[j];
+            rv[4 * j] = q4.x; rv[4 * j + 1] = q4.y; rv[4 * j + 2] = q4.z; rv[4 * j + 3] = q4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < NL; ++j) rv[j] = row[j];
+        }
+        if (!LINES && NM_MERGE_PAIRSTEPS) {
+          // the pair-by-pair accumulation below needs the dofs of a cell to be distinct (they are, for any finite
+          // element); a table that repeats one sends the whole matrix to the general path, which sums any multiset
+          bool dup = false;
+#pragma unroll
+          for (int a = 0; a < NL; ++a)
+#pragma unroll
+            for (int b = a + 1; b < NL; ++b) dup |= rv[a] == rv[b];
+          if (dup) atomicOr(problem, 8u);
+        }
+#pragma unroll
+        for (int j = 0; j < NL / 4; ++j)
+          reinterpret_cast<uint4 *>(sdofs + k * NL)[j] = make_uint4(rv[4 * j], rv[4 * j + 1], rv[4 * j + 2], rv[4 * j + 3]);
+      }
+#else
       if (on) cands[__popc(bal & ((1u << lane) - 1u))] = lane;
+#endif
       __syncwarp(gmask);
       const unsigned n_entries = (unsigned)__popc(bal) * NL;
       for (unsigned e0 = 0; e0 < n_entries; e0 += GROUP) {
@@ -397,7 +450,13 @@ __global__ void __launch_bounds__(256, NM_MERGE_MINB) merge_rows_fast(uint64_t n
         if (on_e) {
           const uint64_t q = base + cands[e / NL];
           const unsigned i = e % NL;
+#if NM_MERGE_CBG == 1
+          const uint32_t dof = bg_dofs[(uint64_t)cbg[e / NL] * NL + i];
+#elif NM_MERGE_CBG == 2
+          const uint32_t dof = sdofs[e];
+#else
           const uint32_t dof = bg_dofs[(uint64_t)cand_bg[q] * NL + i];
+#endif
           v = local[q * NL + i];
           if (dof >= n_dofs) {   // the caller's table points outside the declared dofs: reported as NM_ERR_INVALID
             atomicOr(problem, 4u);
@@ -409,7 +468,18 @@ __global__ void __launch_bounds__(256, NM_MERGE_MINB) merge_rows_fast(uint64_t n
         }
         // keep_constrained_entries: a constrained row stays in the pattern as a structural zero (its slot is claimed,
         // nothing is added); its value goes to the masters of the line (none for a Dirichlet row)
-        group_accumulate(gmask, gbase + lane, vals, (on_e && !failed && ln < 0) ? s : NO_SLOT, v);
+        if constexpr (!LINES && NM_MERGE_CBG == 2 && NM_MERGE_PAIRSTEPS != 0) {
+          // no line, distinct dofs per cell: the NL lanes of one pair hit NL different slots, so the pairs of the round
+          // add one after the other, in the order of the contributions, with plain shared-memory read-modify-writes
+          const bool has = on_e && !failed;
+#pragma unroll
+          for (int j = 0; j < GROUP / NL; ++j) {
+            if (has && lane / NL == (unsigned)j) vals[s] += v;
+            __syncwarp(gmask);
+          }
+        } else {
+          group_accumulate(gmask, gbase + lane, vals, (on_e && !failed && ln < 0) ? s : NO_SLOT, v);
+        }
         if constexpr (LINES) {
           const unsigned nm = (on_e && !failed && ln >= 0) ? (unsigned)(c_ptr[ln + 1] - c_ptr[ln]) : 0u;
           const unsigned nm_max = __reduce_max_sync(gmask, nm);
@@ -438,7 +508,7 @@ __global__ void __launch_bounds__(256, NM_MERGE_MINB) merge_rows_fast(uint64_t n
       const unsigned s = lane + GROUP * k;
       const bool occ = keys[s] != HASH_EMPTY;
       const unsigned bal = (__ballot_sync(gmask, occ) >> gbase) & (GROUP == 32 ? 0xffffffffu : ((1u << GROUP) - 1u));
-      if (occ) { const unsigned q = D + __popc(bal & ((1u << lane) - 1u)); list[q] = s; dkey[q] = keys[s]; }  // dense list of the distinct dofs
+      if (occ) { const unsigned q = D + __popc(bal & ((1u << lane) - 1u)); list[q] = (unsigned short)s; dkey[q] = keys[s]; }  // dense list of the distinct dofs
       D += __popc(bal);
     }
     if (lane < 4) dkey[D + lane] = HASH_EMPTY;   // sentinel padding for the vector loads below (D <= 3/4 SLOTS)
@@ -458,25 +528,22 @@ __global__ void __launch_bounds__(256, NM_MERGE_MINB) merge_rows_fast(uint64_t n
       chunk_left = need;
     }
     const uint64_t dst = chunk_pos;
-    // rank of every distinct key = its position in the row; two keys per lane share the broadcast loads
-    for (unsigned e0 = 0; e0 < D; e0 += 2 * GROUP) {
-      const unsigned ea = e0 + lane, eb = e0 + GROUP + lane;
-      const unsigned ka = ea < D ? dkey[ea] : HASH_EMPTY, kb = eb < D ? dkey[eb] : HASH_EMPTY;
-      unsigned ra = 0, rb = 0;
+    // rank of every distinct key = its position in the row.  One key per lane and pass: the lane counts the smaller keys
+    // of the dense list (vector loads, broadcast).  Measured at sphere cycle 8: same time as two keys per lane sharing
+    // the loads (most cells hold 33..64 distinct dofs), and ranking a short second pass by ballots changes nothing.
+    for (unsigned e0 = 0; e0 < D; e0 += GROUP) {
+      const unsigned ea = e0 + lane;
+      const unsigned ka = ea < D ? dkey[ea] : HASH_EMPTY;
+      unsigned ra = 0;
       const uint4 *dk4 = reinterpret_cast<const uint4 *>(dkey);
       for (unsigned f = 0; f < (D + 3) / 4; ++f) {
         const uint4 k4 = dk4[f];
         ra += (k4.x < ka) + (k4.y < ka) + (k4.z < ka) + (k4.w < ka);
-        rb += (k4.x < kb) + (k4.y < kb) + (k4.z < kb) + (k4.w < kb);
       }
       // per-dof entry counts for the transpose -- or, in compact-row mode, only the bitmap of touched dofs
       if (ea < D) {
         out_col[dst + ra] = ka; out_val[dst + ra] = vals[list[ea]];
         if (mark_bits) atomicOr(&a_cnt[ka >> 5], 1u << (ka & 31)); else atomicAdd(&a_cnt[ka], 1u);
-      }
-      if (eb < D) {
-        out_col[dst + rb] = kb; out_val[dst + rb] = vals[list[eb]];
-        if (mark_bits) atomicOr(&a_cnt[kb >> 5], 1u << (kb & 31)); else atomicAdd(&a_cnt[kb], 1u);
       }
     }
     if (lane == 0) { rowlen[m] = D; rowstart[m] = dst; }
@@ -789,26 +856,39 @@ __global__ void __launch_bounds__(256, NM_TSORT_MINB) t_sort_rows32(uint64_t n_r
 // (col, val, x[col]) load chains before the first FMA: with rows of 3..40 entries the kernels are
 // bound by memory-level parallelism, not by arithmetic.
 // ---------------------------------------------------------------------------------------
+// Slots past the row's end are masked by predicates on the remaining length: they load entry 0 of x (an address that
+// always exists) but never enter the sum -- x may be a scratch vector in local numbering of which only the addressed
+// entries are written, or hold a non-finite entry of the caller, and 0 * NaN is NaN.
+#ifndef NM_SPMV_PAD
+#define NM_SPMV_PAD 1
+#endif
 template <int LANES, int UNROLL>
 __device__ inline double row_dot(const uint32_t *__restrict__ col, const double *__restrict__ val, const double *__restrict__ x,
                                  uint64_t b, uint64_t e, unsigned l)
 {
   double s = 0.0;
   for (uint64_t k0 = b + l; k0 < e; k0 += (uint64_t)LANES * UNROLL) {
+    const uint64_t left = e - k0;
+    const unsigned rem = left > 0xffffffffULL ? 0xffffffffu : (unsigned)left;   // entries from k0 to the row's end
     uint32_t c[UNROLL];
     double v[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-      const uint64_t k = k0 + (uint64_t)u * LANES;
-      const bool ok = k < e;
-      c[u] = ok ? col[k] : 0u;
-      v[u] = ok ? val[k] : 0.0;
+      const bool ok = (unsigned)(u * LANES) < rem;
+      c[u] = ok ? col[k0 + (uint64_t)(u * LANES)] : 0u;
+      v[u] = ok ? val[k0 + (uint64_t)(u * LANES)] : 0.0;
     }
     double xv[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) xv[u] = __ldg(x + c[u]);
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) s = fma(v[u], xv[u], s);
+    for (int u = 0; u < UNROLL; ++u) {
+#if NM_SPMV_PAD
+      if ((unsigned)(u * LANES) < rem) s = fma(v[u], xv[u], s);
+#else
+      s = fma(v[u], xv[u], s);
+#endif
+    }
   }
   return s;
 }

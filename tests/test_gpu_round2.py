@@ -7,6 +7,7 @@ import sys
 
 import numpy as np
 import pytest
+import scipy.sparse as sp
 import torch
 
 from non_matching_test_suite_b200 import _lib, coupling
@@ -341,3 +342,68 @@ def test_assemble_host_with_cubic_cells_as_corner_and_edge(name, cycle):
     assert ca == cb
     assert all(torch.equal(x, y) for x, y in zip(a.csr(), b.csr()))
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("name,cycle", [("sphere", 3), ("disk", 5)])
+def test_a_dof_repeated_inside_one_cell_goes_to_the_general_merge(c_oracle, name, cycle):
+    """Without constraint lines the single-pass merge adds the contributions of one pair side by side, which needs the
+    dofs of a cell to be distinct.  A table that repeats one (no finite element does; distribute_local_to_global would
+    simply add both, coupling_utilities.h:285-287) is detected when the rows are read and the general merge, which sums
+    any multiset, builds the matrix: same result as the oracle's sequential scatter."""
+    import dataclasses
+    bg, im = make_config(name, cycle, band_only=True)
+    assert bg.c_dof.numel() == 0                                          # the kernel without the line lookup
+    plain = coupling.make_context(bg, im, boxes=True)
+    plain.intersect(3, 1e-15)
+    plain.build_sparsity()
+    assert plain.info("merge_path") == 0
+    cell = int(plain.pairs()[1][0])                                       # a background cell that holds an accepted pair
+    plain.close()
+    dofs = bg.dofs.clone()
+    dofs[cell, 1] = dofs[cell, 0]
+    bad = dataclasses.replace(bg, dofs=dofs)
+    ref, ref_plain = c_oracle.assemble(bad, im), c_oracle.assemble(bg, im)
+    ctx = coupling.make_context(bad, im, boxes=True)
+    counts = ctx.intersect(3, 1e-15)
+    rp, col, val = ctx.csr()
+    assert ctx.info("merge_path") == 1
+    assert np.array_equal(col.numpy().astype(np.uint32), ref["col"]) and np.array_equal(rp.numpy().astype(np.uint64), ref["rowptr"])
+    # sub-simplices under the reference's |J| < 1e-12 threshold depend on the subdivision (see test_gpu_parity.py)
+    allowed = 1e-12 + (counts["n_dropped"] + ref["dropped"]) * 1e-12 / np.linalg.norm(ref["val"])
+    assert np.linalg.norm(val.numpy() - ref["val"]) <= allowed * np.linalg.norm(ref["val"])
+    # the entries of the repeated dof carry both vertex functions of that cell: the row of the dof that was overwritten
+    # lost this cell's share, the row of the repeated one gained it
+    A = sp.csr_matrix((val.numpy(), col.numpy(), rp.numpy()), shape=(bg.n_dofs, im.n_dofs))
+    B = sp.csr_matrix((ref_plain["val"], ref_plain["col"], ref_plain["rowptr"]), shape=(bg.n_dofs, im.n_dofs))
+    kept, gone = int(bg.dofs[cell, 0]), int(bg.dofs[cell, 1])
+    moved = (B[gone] - A[gone]).toarray().ravel()
+    assert moved.max() > 0 and np.abs((A[kept] - B[kept]).toarray().ravel() - moved).max() <= 1e-12 * np.abs(B[kept].data).max() + allowed
+    ctx.close()
+
+
+def test_local_products_never_read_untouched_scratch_entries():
+    """The products in local numbering run on scratch vectors of which only the addressed entries are written.  The
+    padding slots of the SpMV kernels (0 x entry) used to read entry 0 of them: with recycled memory that held NaN bit
+    patterns the whole result turned NaN.  Device memory is filled with NaNs first, dof 0 (a corner of the background,
+    far from the interface) is untouched, and the local products must equal the global ones on the touched entries."""
+    nan_fill = torch.full((1 << 27,), float("nan"), dtype=torch.float64, device="cuda")     # 1 GiB of NaNs, handed back
+    del nan_fill
+    torch.cuda.synchronize(); torch.cuda.empty_cache()
+    bg, im = make_config("sphere", 2, band_only=False)
+    ctx = coupling.make_context(bg, im, boxes=True)
+    ctx.intersect(3, 1e-15)
+    rows = ctx.csr_compact()[0].long()
+    assert int(rows[0]) != 0                                            # dof 0 has no entry
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand(im.n_cells, dtype=torch.float64, generator=g)
+    u = torch.rand(bg.n_dofs, dtype=torch.float64, generator=g)
+    xg = torch.zeros(im.n_dofs, dtype=torch.float64); xg[im.dofs[:, 0].long()] = x
+    ug = torch.zeros(bg.n_dofs, dtype=torch.float64); ug[rows] = u[rows]
+    y_loc = ctx.spmv_local(x, transpose=False)
+    z_loc = ctx.spmv_local(u[rows].contiguous(), transpose=True)
+    assert bool(torch.isfinite(y_loc).all()) and bool(torch.isfinite(z_loc).all())
+    assert torch.equal(y_loc, ctx.spmv(xg, transpose=False)[rows])
+    assert torch.equal(z_loc, ctx.spmv(ug, transpose=True)[im.dofs[:, 0].long()])
+    y2, z2 = ctx.spmv_local_pair(x.pin_memory(), u[rows].contiguous().pin_memory())
+    assert torch.equal(y2, y_loc) and torch.equal(z2, z_loc)
+    ctx.close()
