@@ -462,6 +462,9 @@ __global__ void brick_clear(BrickSlot *s, uint32_t cap)
 
 // every cell verifies that it IS a cell of its level grid, claims the slot of its brick and sets its bit
 template <int D>
+#ifndef NM_BRICK_AGG
+#define NM_BRICK_AGG 1
+#endif
 #ifndef NM_BRICK_MINB
 #define NM_BRICK_MINB 8   // index build 2.08 -> 2.00 ms
 #endif
@@ -474,6 +477,13 @@ __global__ void __launch_bounds__(256, NM_BRICK_MINB) brick_insert(BrickDev B, u
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   constexpr int SH = nmbrick::BrickShape<D>::SH;
   unsigned my_level_bit = 0;
+  uint32_t slot = 0xffffffffu;
+  unsigned bit = 0;
+#if NM_BRICK_AGG
+  unsigned long long key = 0;
+  bool ins = false;
+  int lvl = 0;
+#endif
   if (i < n) {
     const double *b = box + i * 8;
     double e = 0;
@@ -492,8 +502,48 @@ __global__ void __launch_bounds__(256, NM_BRICK_MINB) brick_insert(BrickDev B, u
       ok &= nmbrick::grid_corner(B.org[k], j, g) == b[k] && nmbrick::grid_corner(B.org[k], j + 1, g) == b[4 + k];
       idx[k] = j;
     }
-    uint32_t slot = 0xffffffffu;
-    unsigned bit = 0;
+#if NM_BRICK_AGG
+    if (!ok) {
+      atomicOr(&B.hdr->bad, 1u);
+    } else {
+      bit = D == 3 ? (unsigned)((idx[0] & 3) | ((idx[1] & 3) << 2) | ((idx[2] & 3) << 4)) : (unsigned)((idx[0] & 7) | ((idx[1] & 7) << 3));
+      key = brick_key<D>(level, idx[0] >> SH, idx[1] >> SH, idx[2] >> SH);
+      ins = true;
+      lvl = level;
+    }
+  }
+  // Consecutive cells of a tree mostly share their brick: the lanes of a warp that carry the same key insert together,
+  // one claim and one OR per brick instead of one per cell (64 same-address atomics per full brick otherwise).
+  {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned peers = __match_any_sync(0xffffffffu, ins ? key : (0xFFFFFFFFFFFFFF00ULL | lane));   // no key has every level bit set
+    const unsigned leader = (unsigned)__ffs(peers) - 1u;
+    const unsigned long long mine = ins ? 1ULL << bit : 0ULL;
+    const unsigned lo = __reduce_or_sync(peers, (unsigned)mine), hi = __reduce_or_sync(peers, (unsigned)(mine >> 32));
+    const unsigned long long together = ((unsigned long long)hi << 32) | lo;
+    if (ins && lane == leader) {
+      uint32_t s = brick_hash(key) & B.slot_mask;
+      int probes = 0;
+      while (true) {
+        const unsigned long long old = atomicCAS(&B.slots[s].key, ~0ULL, key);
+        if (old == ~0ULL || old == key) { slot = s; break; }
+        s = (s + 1) & B.slot_mask;
+        if (++probes > 256) { atomicOr(&B.hdr->bad, 2u); break; }   // table too full: not a surface band
+      }
+      if (slot != 0xffffffffu) {
+        const unsigned long long prev = atomicOr(&B.slots[slot].mask, together);
+        // two cells in one grid cell (overlapping boxes): among the peers, or with a cell inserted earlier
+        if ((prev & together) != 0ULL || __popcll(together) != __popc(peers)) atomicOr(&B.hdr->bad, 4u);
+      }
+    }
+    slot = __shfl_sync(peers, slot, leader);
+    if (ins && slot != 0xffffffffu) my_level_bit = 1u << lvl;
+  }
+  if (i < n) {
+    cell_slot[i] = slot;
+    cell_bit[i] = (uint8_t)bit;
+  }
+#else
     if (!ok) {
       atomicOr(&B.hdr->bad, 1u);
     } else {
@@ -516,6 +566,7 @@ __global__ void __launch_bounds__(256, NM_BRICK_MINB) brick_insert(BrickDev B, u
     cell_slot[i] = slot;
     cell_bit[i] = (uint8_t)bit;
   }
+#endif
   my_level_bit = __reduce_or_sync(0xffffffffu, my_level_bit);
   if ((threadIdx.x & 31) == 0 && my_level_bit) atomicOr(&s_levels, my_level_bit);
   __syncthreads();

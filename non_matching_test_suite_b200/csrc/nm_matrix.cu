@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(256, NM_MERGE_MINB) merge_rows_fast(uint64_t n
 #pragma unroll
           for (int j = 0; j < NL; ++j) rv[j] = row[j];
         }
-        if (!LINES && NM_MERGE_PAIRSTEPS) {
+        if (NM_MERGE_PAIRSTEPS) {
           // the pair-by-pair accumulation below needs the dofs of a cell to be distinct (they are, for any finite
           // element); a table that repeats one sends the whole matrix to the general path, which sums any multiset
           bool dup = false;
@@ -468,9 +468,12 @@ __global__ void __launch_bounds__(256, NM_MERGE_MINB) merge_rows_fast(uint64_t n
         }
         // keep_constrained_entries: a constrained row stays in the pattern as a structural zero (its slot is claimed,
         // nothing is added); its value goes to the masters of the line (none for a Dirichlet row)
-        if constexpr (!LINES && NM_MERGE_CBG == 2 && NM_MERGE_PAIRSTEPS != 0) {
-          // no line, distinct dofs per cell: the NL lanes of one pair hit NL different slots, so the pairs of the round
-          // add one after the other, in the order of the contributions, with plain shared-memory read-modify-writes
+        // A round none of whose dofs sits on a line (all of them, without lines): the NL lanes of one pair hit NL
+        // different slots -- the dofs of a cell are distinct, checked above -- so the pairs of the round add one after
+        // the other, in the order of the contributions, with plain shared-memory read-modify-writes.
+        bool plain_round = false;
+        if constexpr (NM_MERGE_CBG == 2 && NM_MERGE_PAIRSTEPS != 0) plain_round = LINES ? !__any_sync(gmask, ln >= 0) : true;
+        if (plain_round) {
           const bool has = on_e && !failed;
 #pragma unroll
           for (int j = 0; j < GROUP / NL; ++j) {
@@ -480,7 +483,7 @@ __global__ void __launch_bounds__(256, NM_MERGE_MINB) merge_rows_fast(uint64_t n
         } else {
           group_accumulate(gmask, gbase + lane, vals, (on_e && !failed && ln < 0) ? s : NO_SLOT, v);
         }
-        if constexpr (LINES) {
+        if (LINES && !plain_round) {
           const unsigned nm = (on_e && !failed && ln >= 0) ? (unsigned)(c_ptr[ln + 1] - c_ptr[ln]) : 0u;
           const unsigned nm_max = __reduce_max_sync(gmask, nm);
           for (unsigned k = 0; k < nm_max; ++k) {
