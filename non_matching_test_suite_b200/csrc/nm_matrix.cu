@@ -1284,6 +1284,8 @@ static int transpose_rows(nm_ctx *ctx, bool counts_ready)
       NM_CUDA(cudaGetLastError());
     }
     if (n_rows) {
+      // (a warp-cooperative version -- the 32 rows of a warp staged in shared memory with coalesced loads and stores --
+      // measured 5.10 ms for the transpose against 4.97 ms: L1 already captures the reuse of the thread-per-row loads)
       t_sort_rows32<NM_T_REC != 0><<<nm_blocks(n_rows, 256), 256, 0, NM_LS(ctx)>>>(n_rows, ends, ctx->a_col.as<uint32_t>(), ctx->a_val.as<double>(), rec);
       NM_CUDA(cudaGetLastError());
     }
