@@ -257,3 +257,4 @@ int nm_wait_download_issued(nm_ctx *ctx);
 int nm_constrained_dofs(nm_ctx *ctx, uint32_t *out_dev);
 int nm_exclusive_scan_u64(nm_ctx *ctx, const uint64_t *in, uint64_t *out, uint64_t n);
 int nm_exclusive_scan_u32_to_u64(nm_ctx *ctx, const uint32_t *in, uint64_t *out, uint64_t n);
+int nm_exclusive_scan_u32_to_u64_and_u32(nm_ctx *ctx, const uint32_t *in, uint64_t *out, uint32_t *out32, uint64_t n);

@@ -19,6 +19,9 @@
 #include <cub/cub.cuh>
 
 #include <thrust/iterator/transform_iterator.h>
+#include <thrust/iterator/transform_output_iterator.h>
+#include <thrust/iterator/zip_iterator.h>
+#include <thrust/tuple.h>
 
 #include "nm_common.cuh"
 #include "nm_brick.cuh"
@@ -806,6 +809,25 @@ struct U32ToU64 {
   __host__ __device__ uint64_t operator()(uint32_t v) const { return (uint64_t)v; }
 };
 }  // namespace
+
+namespace {
+struct BothWidths {
+  __host__ __device__ thrust::tuple<uint64_t, uint32_t> operator()(uint64_t v) const { return thrust::make_tuple(v, (uint32_t)v); }
+};
+}  // namespace
+
+// the same scan, every prefix written twice: as 64 bits and truncated to 32 (the caller uses the narrow copy only when the
+// total turns out to fit) -- saves a pass over the offsets
+int nm_exclusive_scan_u32_to_u64_and_u32(nm_ctx *ctx, const uint32_t *in, uint64_t *out, uint32_t *out32, uint64_t n)
+{
+  thrust::transform_iterator<U32ToU64, const uint32_t *, uint64_t> it(in, U32ToU64());
+  auto both = thrust::make_transform_output_iterator(thrust::make_zip_iterator(thrust::make_tuple(out, out32)), BothWidths());
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, both, n, ctx->stream);
+  NM_TRY(nm_ensure(ctx, ctx->scan_tmp, bytes));
+  NM_CUDA(cub::DeviceScan::ExclusiveSum(ctx->scan_tmp.p, bytes, it, both, n, ctx->stream));
+  return NM_OK;
+}
 
 int nm_exclusive_scan_u32_to_u64(nm_ctx *ctx, const uint32_t *in, uint64_t *out, uint64_t n)
 {

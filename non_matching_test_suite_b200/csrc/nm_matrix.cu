@@ -750,8 +750,9 @@ __global__ void __launch_bounds__(256, NM_TSORT_MINB) t_sort_rows(uint64_t n_row
 }
 
 // ---- transpose with 32-bit offsets (nnz < 2^32): one scattered access less per entry on each side ----
-// `ends[r + 1]` starts as the first slot of row r and is the cursor the scatter advances, so a position costs ONE atomic
-// (no separate row-offset load), and when the scatter is done `ends` is the 32-bit row-offset array of the matrix.
+// `ends[r + 1]` starts as the first slot of row r (the scan of the row counts writes its prefixes a second time, as 32 bits,
+// one entry further) and is the cursor the scatter advances, so a position costs ONE atomic (no separate row-offset
+// load), and when the scatter is done `ends` is the 32-bit row-offset array of the matrix.
 #ifndef NM_T_ABS
 #define NM_T_ABS 1
 #endif
@@ -761,13 +762,6 @@ __global__ void __launch_bounds__(256, NM_TSORT_MINB) t_sort_rows(uint64_t n_row
 #define NM_T_REC 1
 #endif
 struct __align__(16) TRec { double v; uint32_t c; uint32_t pad; };
-
-__global__ void t_starts32(uint64_t n_rows, const uint64_t *__restrict__ rowptr, uint32_t *__restrict__ ends)
-{
-  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < n_rows) ends[r + 1] = (uint32_t)rowptr[r];
-  if (r == 0) ends[0] = 0u;
-}
 
 template <int LANES, bool REC>
 __global__ void __launch_bounds__(256, NM_TSCATTER_MINB) t_scatter32(uint64_t n_im, const uint64_t *__restrict__ rowstart, const uint32_t *__restrict__ rowlen,
@@ -1261,6 +1255,12 @@ static int transpose_rows(nm_ctx *ctx, bool counts_ready)
                                                                    ctx->c_col.as<uint32_t>(), map, cnt);
     NM_CUDA(cudaGetLastError());
   }
+  if (NM_T_ABS) {
+    // the offsets also as 32 bits, shifted by one entry: `ends` (see t_scatter32) comes out of the scan itself
+    NM_TRY(nm_ensure(ctx, ctx->a_rowptr32, (n_rows + 3) * sizeof(uint32_t)));
+    NM_CUDA(cudaMemsetAsync(ctx->a_rowptr32.p, 0, sizeof(uint32_t), ctx->stream));
+    NM_TRY(nm_exclusive_scan_u32_to_u64_and_u32(ctx, cnt, ctx->a_rowptr.as<uint64_t>(), ctx->a_rowptr32.as<uint32_t>() + 1, n_rows + 1));
+  } else
   NM_TRY(nm_exclusive_scan_u32_to_u64(ctx, cnt, ctx->a_rowptr.as<uint64_t>(), n_rows + 1));
   uint64_t nnz = 0;
   NM_CUDA(cudaMemcpyAsync(&nnz, ctx->a_rowptr.as<uint64_t>() + n_rows, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1269,14 +1269,11 @@ static int transpose_rows(nm_ctx *ctx, bool counts_ready)
   NM_TRY(nm_ensure(ctx, ctx->a_col, (nnz + 1) * sizeof(uint32_t)));
   NM_TRY(nm_ensure(ctx, ctx->a_val, (nnz + 1) * sizeof(double)));
   if (NM_T_ABS && nnz < 0xffffffffULL) {
-    // 32-bit offsets: the offset array doubles as the scatter cursor (see t_starts32)
+    // 32-bit offsets: the offset array doubles as the scatter cursor (see t_scatter32)
     ctx->a_rowptr32_valid = false;
-    NM_TRY(nm_ensure(ctx, ctx->a_rowptr32, (n_rows + 2) * sizeof(uint32_t)));
     if (NM_T_REC) NM_TRY(nm_ensure(ctx, ctx->t_rec, (nnz + 1) * sizeof(TRec)));
-    uint32_t *ends = ctx->a_rowptr32.as<uint32_t>();
+    uint32_t *ends = ctx->a_rowptr32.as<uint32_t>();   // filled by the scan above
     TRec *rec = NM_T_REC ? ctx->t_rec.as<TRec>() : nullptr;
-    t_starts32<<<nm_blocks(n_rows + 1, 256), 256, 0, NM_LS(ctx)>>>(n_rows, ctx->a_rowptr.as<uint64_t>(), ends);
-    NM_CUDA(cudaGetLastError());
     if (n_im) {
       t_scatter32<TL, NM_T_REC != 0><<<nm_blocks(n_im * TL, 256), 256, 0, NM_LS(ctx)>>>(
           n_im, ctx->c_rowstart.as<uint64_t>(), ctx->c_rowlen.as<uint32_t>(), ctx->c_col.as<uint32_t>(), ctx->c_val.as<double>(),

@@ -8,7 +8,7 @@ tail -6 $O/r2z_pytest.log
 python __graft_entry__.py smoke > $O/r2z_smoke.log 2>&1; echo "smoke rc $?"; tail -2 $O/r2z_smoke.log
 timeout 1200 python bench.py > $O/r2z_bench_n1.json 2> $O/r2z_bench_n1.err; echo "bench rc $?"
 timeout 600 python bench.py --impl reference > $O/r2z_ref_n1.json 2> $O/r2z_ref_n1.err; echo "ref rc $?"
-K='clip_moments3|clip_local|merge_rows|cand_probe|cand_place|brick_|index_insert|entries_count|hash_clear|t_scatter|t_sort|t_count|t_starts32|split_kernel|bg_boxes|spmv_|fill_line_of|check_|DeviceScan|bits_popc|row_ids|narrow'
+K='clip_moments3|clip_local|merge_rows|cand_probe|cand_place|brick_|index_insert|entries_count|hash_clear|t_scatter|t_sort|t_count|split_kernel|bg_boxes|spmv_|fill_line_of|check_|DeviceScan|bits_popc|row_ids|narrow'
 A="--steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-sub-configs --no-dropin --no-check"
 timeout 600 python bench.py $A > $O/plain.log 2>&1 && timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"$K" -c 160 --csv --log-file $O/r2z_launches.csv python bench.py $A > $O/ncu_launch.log 2>&1; echo "launch list rc $?"
 A6="--cycle 6 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-sub-configs --no-dropin --no-check"
