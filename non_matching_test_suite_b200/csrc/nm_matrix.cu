@@ -10,11 +10,13 @@
 //
 // Design: the immersed space is discontinuous (FE_DGQ), so an immersed cell owns its column of
 // the stored matrix exclusively.  One warp merges all accepted pairs of one immersed cell:
-// every (space dof, value) contribution is expanded through its constraint line, the entries
-// are sorted by dof in shared memory and equal dofs are summed in a fixed order.  No global
-// atomics, no global sort, bit-reproducible values.  The rows produced this way are the rows
-// of C (= columns of the stored matrix); the stored orientation is obtained by one device
-// transpose (histogram, scan, scatter, per-row sort).
+// every (space dof, value) contribution is expanded through its constraint line and added, in
+// the order of a sequential loop over the contributions, into a hash table in shared memory
+// (merge_rows_fast; cells it cannot take go through the sort-based general kernels); only the
+// distinct dofs are ordered.  No floating-point atomics, no global sort, bit-reproducible
+// values.  The rows produced this way are the rows of C (= columns of the stored matrix); the
+// stored orientation is obtained by one device transpose (counts from the merge, scan, scatter
+// of 16-byte records, per-row sort).
 #include <cub/cub.cuh>
 
 #include "nm_common.cuh"
