@@ -761,8 +761,13 @@ __device__ inline void brick_query_serial(const BrickDev &B, const double *lo, c
   }
 }
 
+// (bounded to 32 registers: the copy is the common case and waits on memory -- it wants every warp the SM can hold; the
+// serial re-query of an overflowed row may spill.  Unbounded: 57 registers, 4 blocks per SM.)
+#ifndef NM_PLACE_MINB
+#define NM_PLACE_MINB 8
+#endif
 template <int D, int CAP, int LANES>
-__global__ void cand_place_brick(BrickDev B, uint64_t n_im, const double *__restrict__ im_verts, const uint64_t *__restrict__ ptr,
+__global__ void __launch_bounds__(256, NM_PLACE_MINB) cand_place_brick(BrickDev B, uint64_t n_im, const double *__restrict__ im_verts, const uint64_t *__restrict__ ptr,
                                  const uint32_t *__restrict__ tmp, uint32_t *__restrict__ cand_im, uint32_t *__restrict__ cand_bg)
 {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
